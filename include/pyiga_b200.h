@@ -1,0 +1,198 @@
+/* pyiga_b200 — C ABI of the B200 tensor-product IgA assembly path.
+ *
+ * This is the drop-in boundary: the entry points below are what a binding of the reference
+ * (c-f-h/pyiga, a Python/Cython package) attaches to in place of its Cython assembler objects.
+ * Every function cites the reference interface it replaces (paths relative to the pyiga source
+ * tree).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - all functions return 0 on success and a negative PB200_E* code otherwise; they never throw.
+ *     The message of the last failure on the calling thread is returned by pb200_last_error().
+ *   - "h_" arguments are host pointers, "d_" arguments are device pointers on the device the handle
+ *     was created on; both are caller-owned.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  Calls are asynchronous with respect to the host unless they
+ *     write to host memory.
+ *   - tensor axes are in z,y,x order as in the reference (pyiga/bspline.py:812): axis 0 is the
+ *     slowest axis and the last physical coordinate.
+ *   - a handle is bound to one device, is not thread-safe, and different handles may be used from
+ *     different threads.
+ */
+#ifndef PYIGA_B200_H
+#define PYIGA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_MAXDIM 3
+
+#if defined(__GNUC__)
+#define PB200_API __attribute__((visibility("default")))
+#else
+#define PB200_API
+#endif
+
+enum {
+    PB200_OK = 0,
+    PB200_EINVAL = -1,      /* bad argument (message says which) */
+    PB200_ECUDA = -2,       /* CUDA runtime error */
+    PB200_ENOMEM = -3,      /* workspace too small / allocation failed */
+    PB200_EUNSUPPORTED = -4 /* configuration has no device implementation */
+};
+
+/* built-in bilinear forms (pyiga/assemblers.pyx: MassAssembler{2,3}D :26,:1158;
+ * StiffnessAssembler{2,3}D :174,:1324) */
+enum { PB200_FORM_MASS = 1, PB200_FORM_STIFFNESS = 2, PB200_FORM_CUSTOM = 100 };
+
+typedef struct pb200_assembler pb200_assembler;
+typedef struct pb200_mlstruct pb200_mlstruct;   /* multi-level band structure on the device */
+
+/* One tensor axis of the discretisation: trial space (matrix columns, `kvs0` of the reference)
+ * and test space (rows, `kvs1`); both must share the mesh (pyiga/assemblers.pyx:1343).
+ * `nodes`/`weights` are the iterated Gauss rule of pyiga/quadrature.py:3-21, nq nodes per span. */
+typedef struct {
+    int p_trial;
+    int nknots_trial;
+    const double* h_knots_trial;
+    int p_test;                 /* ignored when h_knots_test == NULL (test space == trial space) */
+    int nknots_test;
+    const double* h_knots_test;
+    int nq;                     /* Gauss nodes per span (reference: max_k p_k + 1) */
+    const double* h_nodes;      /* [numspans * nq] */
+    const double* h_weights;    /* [numspans * nq] */
+} pb200_axis_desc;
+
+/* Spline geometry map (pyiga/bspline.py:827 BSplineFunc, pyiga/geometry.py:27 NurbsFunc):
+ * knot vectors per axis and the control net in C order [N0][N1][N2][dim (+1)].  For rational
+ * maps the coordinates are premultiplied by the weight, which is the last component — exactly
+ * the `coeffs` attribute of the reference's NurbsFunc. */
+typedef struct {
+    int sdim, dim;
+    int rational;
+    int p[PB200_MAXDIM];
+    int nknots[PB200_MAXDIM];
+    const double* h_knots[PB200_MAXDIM];
+    const double* h_coeffs;
+} pb200_geo_desc;
+
+/* One term of a custom bilinear form:  integral of  C(field) * d^{slot_test} v * d^{slot_trial} u.
+ * slot 0 = function value, slot 1+k = derivative along tensor axis k (parametric). */
+typedef struct { int field, slot_test, slot_trial; } pb200_term;
+
+typedef struct {
+    int dim;
+    pb200_axis_desc axis[PB200_MAXDIM];
+    int form;                   /* PB200_FORM_* */
+    int nfields;                /* CUSTOM only: number of coefficient fields (caller uploads them) */
+    int nterms;                 /* CUSTOM only */
+    const pb200_term* terms;    /* CUSTOM only */
+    int symmetric;              /* CUSTOM only: form is symmetric and test == trial */
+} pb200_desc;
+
+typedef struct {
+    int dim;
+    int ndofs_test[PB200_MAXDIM], ndofs_trial[PB200_MAXDIM];
+    int nnodes[PB200_MAXDIM];   /* Gauss nodes per axis */
+    int nband[PB200_MAXDIM];    /* band entries per axis (len(bidx[k])) */
+    int nfields;
+    int fast_path;              /* 1 if the sum-factorised pipeline has an instantiation */
+    long long nnz;              /* prod nband */
+    long long npoints;          /* prod nnodes */
+} pb200_info;
+
+PB200_API int pb200_version(void);
+PB200_API const char* pb200_last_error(void);
+
+/* ---- assembler object -------------------------------------------------------------------------
+ * Replaces the constructor of the assembler classes (pyiga/assemblers.pyx:1336-1383): builds the
+ * span/support/band tables on the host, uploads them, and evaluates the 1D basis tables on the
+ * device (K1; replaces compute_values_derivs, pyiga/assemble_tools.py:7-12). */
+PB200_API int pb200_asm_create(const pb200_desc* desc, int device, void* stream, pb200_assembler** out);
+PB200_API int pb200_asm_destroy(pb200_assembler* a);
+PB200_API int pb200_asm_info(const pb200_assembler* a, pb200_info* info);
+
+/* re-run K1 (basis tables) — lets a benchmark keep the table evaluation inside the timed region */
+PB200_API int pb200_asm_tabulate(pb200_assembler* a, void* stream);
+
+/* Band structure of one axis: h_bidx receives nband x 2 uint32 (i,j), identical to
+ * MLStructure.from_kvs(...).bidx[axis] (pyiga/mlmatrix.py:59-65, :420-440). */
+PB200_API int pb200_asm_structure(const pb200_assembler* a, int axis, uint32_t* h_bidx);
+
+/* Geometry + coefficient fields (K2).  `d_fields` is caller-allocated, nfields*npoints doubles,
+ * layout [field][g0][g1][g2]; the handle keeps the pointer (no copy).  Replaces
+ * geo.grid_jacobian + precompute_fields (pyiga/bspline.py:897-921, geometry.py:116-123,
+ * assemblers.pyx:1389-1449). */
+PB200_API int pb200_asm_bind_fields(pb200_assembler* a, double* d_fields);
+PB200_API int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc* geo, void* stream);
+/* same, from Jacobians the caller evaluated on the Gauss grid (geometry objects that are not
+ * splines): d_jac is [npoints][dim][dim] */
+PB200_API int pb200_asm_compute_fields_from_jacobian(pb200_assembler* a, const double* d_jac, void* stream);
+
+/* Geometry evaluation on the assembler's Gauss grid or on an arbitrary tensor grid: writes
+ * [npoints][dim][dim] Jacobians and/or [npoints][dim] values (either pointer may be NULL).
+ * Replaces BSplineFunc/NurbsFunc.grid_eval / grid_jacobian. */
+PB200_API int pb200_geo_eval_grid(const pb200_geo_desc* geo, const int* npts, const double* const* h_grid,
+                        double* d_values, double* d_jac, int device, void* stream);
+
+/* ---- assembly ----------------------------------------------------------------------------------
+ * Rows of the first tensor axis in [row0_begin,row0_end) form a slab; its MLB values are the
+ * contiguous block data[bidx0 offset of row0_begin .. of row0_end][:][:].
+ * Replaces assemble_entries' S.nonzero() + asm.multi_entries(IJ) for the whole pattern
+ * (pyiga/assemble.py:741-745) with the sum-factorised pipeline; output layout is MLMatrix.data
+ * (pyiga/mlmatrix.py:201-269). */
+PB200_API int pb200_asm_workspace_bytes(const pb200_assembler* a, int row0_begin, int row0_end, size_t* bytes);
+PB200_API int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int row0_end, double* d_out,
+                           void* d_work, size_t work_bytes, void* stream);
+/* same result through the per-entry quadrature kernel (reference algorithm, for cross-checks and
+ * configurations without a fast path) */
+PB200_API int pb200_asm_assemble_mlb_entrywise(pb200_assembler* a, int row0_begin, int row0_end, double* d_out,
+                                     void* stream);
+
+/* multi_entries(indices) (pyiga/genericasm.pxi:722-758): d_ij is n x 2 uint64 (row, column),
+ * d_out n doubles; pairs outside the pattern give 0.0. */
+PB200_API int pb200_asm_multi_entries(pb200_assembler* a, const uint64_t* d_ij, size_t n, double* d_out, void* stream);
+
+/* ---- MLB matrices ------------------------------------------------------------------------------
+ * A structure handle holds the per-level row tables of an MLStructure on the device.  The one of
+ * an assembler is borrowed (owned by the assembler); stand-alone ones are built from the bidx
+ * arrays of pyiga's MLStructure (pyiga/mlmatrix.py:15-58; levels must be sorted by row with
+ * contiguous column ranges, which holds for every spline pattern) and must be destroyed. */
+PB200_API const pb200_mlstruct* pb200_asm_mlstruct(const pb200_assembler* a);
+PB200_API int pb200_mlstruct_create(int nlevels, const int* rows, const int* cols, const int* nband,
+                                    const uint32_t* const* h_bidx, int device, pb200_mlstruct** out);
+PB200_API int pb200_mlstruct_destroy(pb200_mlstruct* s);
+/* CSR export of a slab (replaces ml_nonzero_* + COO->CSR, pyiga/mlmatrix_cy.pyx:189-289,
+ * pyiga/assemble.py:745): idx_bytes is 4 or 8; d_indptr has nrows+1 entries relative to the slab. */
+PB200_API int pb200_mlb_to_csr(const pb200_mlstruct* s, int row0_begin, int row0_end, const double* d_mlb,
+                     void* d_indptr, void* d_indices, double* d_values, int idx_bytes, void* stream);
+/* y = A x for the slab rows (replaces ml_matvec_2d/3d, pyiga/mlmatrix_cy.pyx:224-325).  d_x starts
+ * at trial index x_j0_begin on axis 0 (use 0 for a full vector). */
+PB200_API int pb200_mlb_matvec(const pb200_mlstruct* s, int row0_begin, int row0_end, const double* d_mlb,
+                     const double* d_x, int x_j0_begin, double* d_y, void* stream);
+/* y = (A_0 (x) ... (x) A_{d-1}) x with dense row-major factors (pyiga/kronecker.py:15-34);
+ * d_tmp holds two buffers of max intermediate size. */
+PB200_API int pb200_kron_matvec(int d, const double* const* d_factors, const int* rows, const int* cols,
+                      const double* d_x, double* d_y, double* d_tmp, void* stream);
+
+/* K1 stand-alone (replaces bspline.active_deriv / collocation_derivs_info,
+ * pyiga/bspline_cy.pyx:126-145, pyiga/bspline.py:648-660): d_first m int32, d_values [m][nderiv+1][p+1] */
+PB200_API int pb200_basis_eval(const double* d_knots, int nknots, int p, const double* d_nodes, int m, int nderiv,
+                     int32_t* d_first, double* d_values, void* stream);
+
+/* FP64 FMA throughput probe used for the roofline denominator: runs `iters` dependent-chain DFMA
+ * rounds on every SM and returns the measured GFLOP/s through *gflops. */
+PB200_API int pb200_probe_fp64(int device, int iters, double* gflops);
+
+/* host-only helper (no CUDA call): band structure of a pair of knot vectors; h_bidx may be NULL to
+ * query the count.  Used by MLStructure.from_kvs on the host side. */
+PB200_API int pb200_band_structure(const double* h_knots_trial, int nknots_trial, int p_trial,
+                         const double* h_knots_test, int nknots_test, int p_test,
+                         uint32_t* h_bidx, int* nband);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

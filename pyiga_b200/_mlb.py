@@ -1,0 +1,88 @@
+"""Device-side multi-level band structures: CSR export and matvec of MLB value tensors."""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse
+
+from . import _device
+
+
+class DeviceStructure:
+    """Owns (or borrows, from an assembler) a ``pb200_mlstruct`` handle."""
+
+    def __init__(self, structure=None, borrowed=None, owner=None):
+        self.be = _device.backend()
+        self.structure = structure
+        self._owner = owner         # keeps the assembler alive while its structure is borrowed
+        self._owned = None
+        self.supported = True
+        if borrowed is not None:
+            self.handle = borrowed
+            return
+        S = structure
+        if S.L < 2 or S.L > 3 or any(S._row_tables(k) is None for k in range(S.L)):
+            self.supported = False
+            self.handle = None
+            return
+        L = S.L
+        rows = (C.c_int * L)(*[b[0] for b in S.bs])
+        cols = (C.c_int * L)(*[b[1] for b in S.bs])
+        nband = (C.c_int * L)(*[len(b) for b in S.bidx])
+        self._bidx_keep = [np.ascontiguousarray(b, dtype=np.uint32) for b in S.bidx]
+        ptrs = (C.c_void_p * L)(*[b.ctypes.data for b in self._bidx_keep])
+        h = C.c_void_p()
+        _device.check(self.be.lib.pb200_mlstruct_create(L, rows, cols, nband, ptrs, self.be.device_index, C.byref(h)))
+        self.handle = h
+        self._owned = h
+
+    def __del__(self):
+        try:
+            if self._owned is not None:
+                self.be.lib.pb200_mlstruct_destroy(self._owned)
+                self._owned = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _sizes(self, row0=None):
+        S = self.structure
+        n0 = S.bs[0][0]
+        ra, rb = (0, n0) if row0 is None else row0
+        rs0 = np.searchsorted(S.bidx[0][:, 0], [ra, rb])
+        nrows = (rb - ra) * int(np.prod([b[0] for b in S.bs[1:]], dtype=np.int64))
+        count = int(rs0[1] - rs0[0]) * int(np.prod([len(b) for b in S.bidx[1:]], dtype=np.int64))
+        return ra, rb, nrows, count
+
+    def csr_arrays(self, d_data, row0=None):
+        """Device CSR arrays (indptr, indices, values) of the slab; int32 unless nnz >= 2^31."""
+        be = self.be
+        ra, rb, nrows, count = self._sizes(row0)
+        idt = np.int32 if count < 2 ** 31 else np.int64
+        indptr = be.empty(nrows + 1, idt)
+        indices = be.empty(count, idt)
+        values = be.empty(count, np.float64)
+        _device.check(be.lib.pb200_mlb_to_csr(self.handle, ra, rb, be.ptr(d_data), be.ptr(indptr), be.ptr(indices),
+                                               be.ptr(values), np.dtype(idt).itemsize, be.stream()))
+        return indptr, indices, values
+
+    def to_csr(self, d_data, row0=None):
+        be = self.be
+        indptr, indices, values = self.csr_arrays(d_data, row0)
+        ra, rb, nrows, _ = self._sizes(row0)
+        A = scipy.sparse.csr_matrix((be.to_host(values), be.to_host(indices), be.to_host(indptr)),
+                                    shape=(nrows, self.structure.shape[1]))
+        A.has_sorted_indices = True
+        return A
+
+    def matvec_device(self, d_data, d_x, d_y=None, row0=None, x_j0=0):
+        be = self.be
+        ra, rb, nrows, _ = self._sizes(row0)
+        if d_y is None:
+            d_y = be.empty(nrows)
+        _device.check(be.lib.pb200_mlb_matvec(self.handle, ra, rb, be.ptr(d_data), be.ptr(d_x), int(x_j0),
+                                               be.ptr(d_y), be.stream()))
+        return d_y
+
+    def matvec(self, d_data, x):
+        be = self.be
+        return be.to_host(self.matvec_device(d_data, be.from_host(x)))

@@ -1,0 +1,251 @@
+"""Knot vectors and tensor-product spline functions (host-side descriptors).
+
+Mirrors the part of the reference's ``pyiga.bspline`` that the assembly path
+touches (``pyiga/bspline.py:36-213`` KnotVector / make_knots,
+``pyiga/bspline.py:827-921`` BSplineFunc).  These classes only hold the
+*description* of a space or a spline function; every evaluation on a Gauss
+grid is done on the device through the C-ABI (``pyiga_b200._lib``) — there is
+no host evaluation path.
+
+Index convention (same as the reference): tensor axes are in z,y,x order, i.e.
+``kvs[0]`` is the slowest axis and ``kvs[-1]`` is ``x``; coefficient arrays are
+``coeffs[i_z, i_y, i_x, component]`` with components in x,y,z order.
+"""
+import numpy as np
+
+
+class KnotVector:
+    """Open knot vector plus spline degree (reference: ``pyiga/bspline.py:36-189``).
+
+    Attributes:
+        kv (ndarray): the knots, non-decreasing, first/last repeated ``p+1`` times
+        p (int): spline degree
+    """
+
+    def __init__(self, knots, p):
+        knots = np.ascontiguousarray(knots, dtype=np.float64)
+        if knots.ndim != 1:
+            raise ValueError('knot vector must be one-dimensional')
+        assert np.all(np.diff(knots) >= 0), 'knots should be increasing'
+        self.kv = knots
+        self.p = int(p)
+        self._uniq = None       # (mesh, knot index -> mesh index)
+
+    def __repr__(self):
+        return 'KnotVector(%r, %r)' % (self.kv, self.p)
+
+    def __str__(self):
+        return '<KnotVector p=%d sz=%d>' % (self.p, self.kv.size)
+
+    def __eq__(self, other):
+        return (isinstance(other, KnotVector) or hasattr(other, 'kv')) \
+            and self.p == other.p and len(self.kv) == len(other.kv) \
+            and bool(np.allclose(self.kv, other.kv, atol=1e-8, rtol=1e-8))
+
+    def __hash__(self):
+        return hash((self.p, self.kv.size))
+
+    # -- sizes ---------------------------------------------------------------
+    @property
+    def numknots(self):
+        return self.kv.size
+
+    @property
+    def numdofs(self):
+        """Number of B-splines over this knot vector."""
+        return self.kv.size - self.p - 1
+
+    @property
+    def numspans(self):
+        """Number of non-empty knot intervals."""
+        return self.mesh.size - 1
+
+    # -- mesh ----------------------------------------------------------------
+    def _unique(self):
+        if self._uniq is None:
+            self._uniq = np.unique(self.kv, return_inverse=True)
+        return self._uniq
+
+    @property
+    def mesh(self):
+        """The distinct knots (break points)."""
+        return self._unique()[0]
+
+    def support(self, j=None):
+        if j is None:
+            return (self.kv[0], self.kv[-1])
+        return (self.kv[j], self.kv[j + self.p + 1])
+
+    def support_idx(self, j):
+        return (j, j + self.p + 1)
+
+    def mesh_support_idx(self, j):
+        k2m = self._unique()[1]
+        return (k2m[j], k2m[j + self.p + 1])
+
+    def mesh_support_idx_all(self):
+        """``(numdofs, 2)`` array: first / one-past-last mesh-span index of the support
+        of every B-spline (reference: ``pyiga/bspline.py:129-136``)."""
+        k2m = self._unique()[1]
+        n = self.numdofs
+        return np.column_stack((k2m[0:n], k2m[self.p + 1:self.p + 1 + n]))
+
+    def mesh_span_indices(self):
+        """Knot indices ``i`` with ``kv[i] != kv[i+1]`` (one per non-empty span)."""
+        k2m = self._unique()[1]
+        return np.nonzero(k2m[1:] != k2m[:-1])[0]
+
+    def first_active(self, k):
+        return k - self.p
+
+    def findspan(self, u):
+        """Knot-span index ``i`` with ``kv[i] <= u < kv[i+1]``, the right end point
+        belonging to the last span (reference: ``pyiga/bspline_cy.pyx:13-27``)."""
+        n = self.kv.size
+        if u >= self.kv[n - self.p - 1]:
+            return n - self.p - 2
+        return int(np.searchsorted(self.kv, u, side='right')) - 1
+
+    def first_active_at(self, u):
+        return self.findspan(u) - self.p
+
+    def greville(self):
+        p = self.p
+        if p == 0:
+            return 0.5 * (self.kv[1:] + self.kv[:-1])
+        g = np.array([self.kv[i + 1:i + p + 1].sum() / p for i in range(self.numdofs)])
+        return np.clip(g, self.kv[0], self.kv[-1])
+
+    def copy(self):
+        return KnotVector(self.kv.copy(), self.p)
+
+    def refine(self, new_knots=None):
+        if new_knots is None:
+            m = self.mesh
+            new_knots = 0.5 * (m[1:] + m[:-1])
+        return KnotVector(np.sort(np.concatenate((self.kv, new_knots))), self.p)
+
+    def meshsize_avg(self):
+        return abs(self.kv[-1] - self.kv[0]) / self.numspans
+
+
+def make_knots(p, a, b, n, mult=1):
+    """Open knot vector of degree `p` on `(a,b)` with `n` equal spans and interior
+    multiplicity `mult` (reference: ``pyiga/bspline.py:192-213``; the interior
+    knots come from the same ``np.arange`` call so that the floats agree)."""
+    interior = np.arange(a, b, (b - a) / n)[1:]
+    knots = np.concatenate((np.full(p + 1, a, dtype=float),
+                            np.repeat(interior, mult),
+                            np.full(p + 1, b, dtype=float)))
+    return KnotVector(knots, p)
+
+
+def numdofs(kvs):
+    if hasattr(kvs, 'numdofs'):
+        return kvs.numdofs
+    return int(np.prod([kv.numdofs for kv in kvs]))
+
+
+def _as_kv_tuple(kvs):
+    if hasattr(kvs, 'kv') and hasattr(kvs, 'p'):
+        return (kvs,)
+    return tuple(kvs)
+
+
+class _SplineFuncBase:
+    """Shared behaviour of :class:`BSplineFunc` and :class:`~pyiga_b200.geometry.NurbsFunc`."""
+
+    _rational = False
+
+    def is_scalar(self):
+        return len(self.output_shape()) == 0
+
+    def is_vector(self):
+        return len(self.output_shape()) == 1
+
+    @property
+    def support(self):
+        return tuple(kv.support() for kv in self.kvs)
+
+    # device evaluation ------------------------------------------------------
+    def _device_eval(self, gridaxes, want):
+        from . import _device
+        return _device.eval_spline_on_grid(self, gridaxes, want)
+
+    def grid_eval(self, gridaxes):
+        """Values on a tensor grid (axes in z,y,x order); evaluated on the GPU.
+
+        Reference: ``pyiga/bspline.py:874-895`` / ``pyiga/geometry.py:102-114``."""
+        assert len(gridaxes) == self.sdim, "Input has wrong dimension"
+        return self._device_eval(gridaxes, 'value')
+
+    def grid_jacobian(self, gridaxes):
+        """Jacobians on a tensor grid, ``J[..., i, j] = d f_i / d xi_j`` with ``xi_0`` the
+        *last* grid axis; evaluated on the GPU.
+
+        Reference: ``pyiga/bspline.py:897-921`` / ``pyiga/geometry.py:116-123``."""
+        assert len(gridaxes) == self.sdim, "Input has wrong dimension"
+        return self._device_eval(gridaxes, 'jacobian')
+
+    def eval(self, *x):
+        """Evaluate at a single point given in x,y,z order."""
+        coords = tuple(np.atleast_1d(np.asarray(t, dtype=float)) for t in reversed(x))
+        scalar_axes = tuple(i for i, t in enumerate(reversed(x)) if np.isscalar(t))
+        y = self.grid_eval(coords).squeeze(axis=scalar_axes)
+        return y.item() if y.shape == () else y
+
+    __call__ = eval
+
+
+class BSplineFunc(_SplineFuncBase):
+    """Tensor-product B-spline function given by knot vectors and coefficients
+    (reference: ``pyiga/bspline.py:827-871``)."""
+
+    def __init__(self, kvs, coeffs):
+        self.kvs = _as_kv_tuple(kvs)
+        self.sdim = len(self.kvs)
+        N = tuple(kv.numdofs for kv in self.kvs)
+        coeffs = np.asanyarray(coeffs)
+        if coeffs.ndim == 1:
+            assert coeffs.shape[0] == np.prod(N), "Wrong length of coefficient vector"
+            coeffs = coeffs.reshape(N)
+        assert N == coeffs.shape[:self.sdim], "Wrong shape of coefficients"
+        self.coeffs = coeffs
+        tail = coeffs.shape[self.sdim:]
+        if len(tail) == 0:
+            self.dim = 1
+        elif len(tail) == 1:
+            self.dim = tail[0]
+        else:
+            self.dim = tail
+
+    def output_shape(self):
+        return self.coeffs.shape[self.sdim:]
+
+    def copy(self):
+        return BSplineFunc(self.kvs, self.coeffs.copy())
+
+    def as_nurbs(self):
+        from .geometry import NurbsFunc
+        return NurbsFunc(self.kvs, self.coeffs.copy(), np.ones(self.coeffs.shape[:self.sdim]))
+
+    def as_vector(self):
+        if self.is_vector():
+            return self
+        assert self.is_scalar()
+        return BSplineFunc(self.kvs, self.coeffs[..., None])
+
+    def translate(self, offset):
+        return BSplineFunc(self.kvs, self.coeffs + np.asarray(offset))
+
+    def scale(self, factor):
+        return BSplineFunc(self.kvs, self.coeffs * np.asarray(factor))
+
+    def apply_matrix(self, A):
+        assert self.is_vector(), 'Can only apply matrices to vector-valued functions'
+        return BSplineFunc(self.kvs, np.matmul(np.asarray(A), self.coeffs[..., None])[..., 0])
+
+    def rotate_2d(self, angle):
+        assert self.dim == 2, 'Must be 2D vector function'
+        c, s = np.cos(angle), np.sin(angle)
+        return self.apply_matrix([[c, -s], [s, c]])

@@ -1,0 +1,1145 @@
+// C ABI of pyiga_b200 (see include/pyiga_b200.h): host-side table construction, kernel launches.
+#include "backend.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/pyiga_b200.h"
+#include "basis.cuh"
+#include "entries.cuh"
+#include "geo_fields.cuh"
+#include "mlb.cuh"
+#include "plans.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        pbError e_ = (call);                                                                       \
+        if (e_ != pbSuccess)                                                                       \
+            return fail(PB200_ECUDA, "%s failed: %s (%s:%d)", #call, pbErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel launchers (CUDA) / sequential emulation (tests only, see backend.cuh)
+// ------------------------------------------------------------------------------------------------
+static void k_basis(const double* kv, int nk, int p, const double* nodes, int m, int nd, int* first, double* values,
+                    pbStream st) {
+#ifdef PB_EMULATE
+    pb_emu_for(m, [&](long long g) { pb_basis_node(kv, nk, p, nodes, nd, first, values, (int)g); });
+#else
+    pb_basis_kernel<<<(m + 127) / 128, 128, 0, st>>>(kv, nk, p, nodes, m, nd, first, values);
+#endif
+}
+
+template <int DIM, class Prog>
+static void k_fields(const PbFieldParams& prm, pbStream st) {
+#ifdef PB_EMULATE
+    pb_emu_for(prm.npts, [&](long long i) { pb_fields_point<DIM, Prog>(prm, i); });
+#else
+    const long long blocks = std::min<long long>((prm.npts + 255) / 256, 148LL * 32);
+    pb_fields_kernel<DIM, Prog><<<(unsigned)blocks, 256, 0, st>>>(prm);
+#endif
+}
+
+// values [pts][dim] and Jacobians [pts][dim][sdim] on a tensor grid
+template <int DIM>
+PB_HD void pb_geo_grid_point(const PbGeoDev& geo, const int* G, double* values, double* jac, long long idx) {
+    int g[3];
+    long long r = idx;
+    for (int k = DIM - 1; k >= 0; --k) { g[k] = (int)(r % G[k]); r /= G[k]; }
+    PbPoint pt;
+    pb_geo_eval<DIM>(geo, g, pt);
+    if (values)
+        for (int i = 0; i < geo.dim; ++i) values[idx * geo.dim + i] = pt.x[i];
+    if (jac)
+        for (int i = 0; i < geo.dim; ++i)
+            for (int j = 0; j < DIM; ++j) jac[(idx * geo.dim + i) * DIM + j] = pt.J[i][j];
+}
+#ifndef PB_EMULATE
+template <int DIM>
+__global__ void pb_geo_grid_kernel(PbGeoDev geo, int G0, int G1, int G2, long long npts, double* values, double* jac) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int G[3] = {G0, G1, G2};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < npts; idx += stride)
+        pb_geo_grid_point<DIM>(geo, G, values, jac, idx);
+}
+#endif
+template <int DIM>
+static void k_geo_grid(const PbGeoDev& geo, const int* G, long long npts, double* values, double* jac, pbStream st) {
+#ifdef PB_EMULATE
+    pb_emu_for(npts, [&](long long i) { pb_geo_grid_point<DIM>(geo, G, values, jac, i); });
+#else
+    const long long blocks = std::min<long long>((npts + 255) / 256, 148LL * 32);
+    pb_geo_grid_kernel<DIM><<<(unsigned)blocks, 256, 0, st>>>(geo, G[0], G[1], DIM > 2 ? G[2] : 1, npts, values, jac);
+#endif
+}
+
+template <int DIM>
+static void k_entries(const PbEntryParams& prm, pbStream st) {
+#ifdef PB_EMULATE
+    pb_emu_for(prm.n, [&](long long e) { prm.out[e] = pb_entry<DIM>(prm, prm.ij[2 * e], prm.ij[2 * e + 1]); });
+#else
+    const long long blocks = std::min<long long>((prm.n + 127) / 128, 148LL * 64);
+    pb_entries_kernel<DIM><<<(unsigned)blocks, 128, 0, st>>>(prm);
+#endif
+}
+template <int DIM>
+static void k_entries_mlb(const PbEntryParams& prm, long long mu0_begin, long long count, pbStream st) {
+#ifdef PB_EMULATE
+    pb_emu_for(count, [&](long long e) { prm.out[e] = pb_entry_mlb<DIM>(prm, mu0_begin, e); });
+#else
+    const long long blocks = std::min<long long>((count + 127) / 128, 148LL * 64);
+    pb_entries_mlb_kernel<DIM><<<(unsigned)blocks, 128, 0, st>>>(prm, mu0_begin, count);
+#endif
+}
+
+template <class IdxT>
+static void k_csr(const PbMlbParams& p, long long nrows, long long count, IdxT* indptr, IdxT* indices, double* values,
+                  pbStream st) {
+#ifdef PB_EMULATE
+    pb_emu_for(nrows + 1, [&](long long r) { pb_csr_indptr_row<IdxT>(p, nrows, indptr, r); });
+    pb_emu_for(count, [&](long long e) { pb_csr_fill_elem<IdxT>(p, indices, values, e); });
+#else
+    const unsigned b1 = (unsigned)((nrows + 1 + 255) / 256);
+    const unsigned b2 = (unsigned)std::min<long long>((count + 255) / 256, 148LL * 64);
+    pb_csr_indptr_kernel<IdxT><<<b1, 256, 0, st>>>(p, nrows, indptr);
+    pb_csr_fill_kernel<IdxT><<<b2, 256, 0, st>>>(p, count, indices, values);
+#endif
+}
+
+static void k_matvec(const PbMlbParams& p, long long nrows, const double* x, int x_j0, double* y, pbStream st) {
+#ifdef PB_EMULATE
+    pb_emu_for(nrows, [&](long long r) { pb_mlb_matvec_row(p, x, x_j0, y, r); });
+#else
+    pb_mlb_matvec_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(p, nrows, x, x_j0, y);
+#endif
+}
+
+static void k_modek(const double* A, int m, int n, const double* x, long long outer, long long inner, double* y,
+                    pbStream st) {
+    const long long total = outer * m * inner;
+#ifdef PB_EMULATE
+    pb_emu_for(total, [&](long long e) { pb_modek_elem(A, m, n, x, inner, y, e); });
+#else
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 64);
+    pb_modek_kernel<<<blocks, 256, 0, st>>>(A, m, n, x, outer, inner, y);
+#endif
+}
+
+extern "C" const char* pb200_last_error(void) { return g_err.c_str(); }
+extern "C" int pb200_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------
+// walk-kernel registry
+// ------------------------------------------------------------------------------------------------
+typedef std::map<std::tuple<int, int, int>, PbWalkLaunch> WalkRegistry;
+static WalkRegistry& registry() {
+    static WalkRegistry r;      // function-local: safe to use from other objects' static initialisers
+    return r;
+}
+extern "C" void pb200_register_walk(int plan_id, int P, int Q, PbWalkLaunch fn) {
+    registry()[std::make_tuple(plan_id, P, Q)] = fn;
+}
+PbWalkLaunch pb_find_walk(int plan_id, int P, int Q) {
+    auto it = registry().find(std::make_tuple(plan_id, P, Q));
+    return it == registry().end() ? nullptr : it->second;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side axis tables
+// ------------------------------------------------------------------------------------------------
+struct KvHost {
+    int p = 0;
+    std::vector<double> kv;
+    std::vector<double> mesh;       // distinct knots
+    std::vector<int> k2m;           // knot index -> mesh index
+    std::vector<int> first;         // per span: first active function
+    std::vector<int> supp;          // [N][2] span range of each function
+    int N() const { return (int)kv.size() - p - 1; }
+    int nspans() const { return (int)mesh.size() - 1; }
+};
+
+static int build_kv(const double* knots, int nk, int p, KvHost& K) {
+    if (!knots || nk < 2 * (p + 1) || p < 0) return fail(PB200_EINVAL, "invalid knot vector (nknots=%d, p=%d)", nk, p);
+    if (p > PB_MAXP) return fail(PB200_EUNSUPPORTED, "spline degree %d above the supported maximum %d", p, PB_MAXP);
+    K.p = p;
+    K.kv.assign(knots, knots + nk);
+    for (int i = 1; i < nk; ++i)
+        if (K.kv[i] < K.kv[i - 1]) return fail(PB200_EINVAL, "knots should be increasing");
+    K.mesh.clear();
+    K.k2m.resize(nk);
+    for (int i = 0; i < nk; ++i) {
+        if (i == 0 || K.kv[i] != K.kv[i - 1]) K.mesh.push_back(K.kv[i]);
+        K.k2m[i] = (int)K.mesh.size() - 1;
+    }
+    const int n = K.nspans(), N = K.N();
+    if (n < 1 || N < 1) return fail(PB200_EINVAL, "knot vector has no spans");
+    K.first.assign(n, 0);
+    for (int i = 0; i + 1 < nk; ++i)
+        if (K.kv[i] != K.kv[i + 1]) K.first[K.k2m[i]] = i - p;   // knot span i is mesh span k2m[i]
+    K.supp.resize(2 * N);
+    for (int j = 0; j < N; ++j) {
+        K.supp[2 * j] = K.k2m[j];
+        K.supp[2 * j + 1] = K.k2m[j + p + 1];
+    }
+    for (int s = 0; s < n; ++s)
+        if (K.first[s] < 0 || K.first[s] + p >= N) return fail(PB200_EINVAL, "knot vector is not open (span %d)", s);
+    return 0;
+}
+
+// band structure: (i,j), i over test functions, j over trial functions with joint support,
+// sorted by i then j  (pyiga/mlmatrix.py:420-440)
+static void build_band(const KvHost& U, const KvHost& V, std::vector<int>& row_start, std::vector<int>& jmin,
+                       std::vector<int>& pi, std::vector<int>& pj) {
+    const int Nv = V.N(), Nu = U.N();
+    row_start.assign(Nv + 1, 0);
+    jmin.assign(Nv, 0);
+    pi.clear();
+    pj.clear();
+    int j0 = 0;
+    for (int i = 0; i < Nv; ++i) {
+        const int a = V.supp[2 * i], b = V.supp[2 * i + 1];
+        while (j0 < Nu && U.supp[2 * j0 + 1] <= a) ++j0;     // supports end in non-decreasing order
+        jmin[i] = j0;
+        row_start[i] = (int)pi.size();
+        for (int j = j0; j < Nu && U.supp[2 * j] < b; ++j) {
+            if (std::min(b, U.supp[2 * j + 1]) > std::max(a, U.supp[2 * j])) {
+                pi.push_back(i);
+                pj.push_back(j);
+            }
+        }
+    }
+    row_start[Nv] = (int)pi.size();
+}
+
+extern "C" int pb200_band_structure(const double* ku, int nku, int pu, const double* kvv, int nkv, int pv,
+                                    uint32_t* h_bidx, int* nband) {
+    KvHost U, V;
+    int rc = build_kv(ku, nku, pu, U);
+    if (rc) return rc;
+    rc = kvv ? build_kv(kvv, nkv, pv, V) : build_kv(ku, nku, pu, V);
+    if (rc) return rc;
+    std::vector<int> rs, jm, pi, pj;
+    build_band(U, V, rs, jm, pi, pj);
+    if (nband) *nband = (int)pi.size();
+    if (h_bidx)
+        for (size_t m = 0; m < pi.size(); ++m) {
+            h_bidx[2 * m] = (uint32_t)pi[m];
+            h_bidx[2 * m + 1] = (uint32_t)pj[m];
+        }
+    return 0;
+}
+
+struct AxisHost {
+    KvHost U, V;
+    bool same = true;
+    int n = 0, q = 0, G = 0, M = 0;
+    std::vector<double> nodes, weights;
+    std::vector<int> row_start, jmin, pair_i, pair_j, tr, ret_mu;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device pool: one allocation for all small tables, 256-byte aligned pieces
+// ------------------------------------------------------------------------------------------------
+struct Pool {
+    std::vector<char> host;
+    char* dev = nullptr;
+    size_t put(const void* p, size_t bytes) {
+        size_t off = (host.size() + 255) & ~size_t(255);
+        host.resize(off + bytes);
+        if (p) memcpy(host.data() + off, p, bytes);
+        return off;
+    }
+    template <class T> size_t put(const std::vector<T>& v) { return put(v.data(), v.size() * sizeof(T)); }
+};
+
+// structure-only view used by the MLB utilities (CSR export, matvec)
+struct pb200_mlstruct {
+    int device = 0;
+    int dim = 0;
+    int Nv[PB_MAXDIM] = {1, 1, 1}, Nu[PB_MAXDIM] = {1, 1, 1}, M[PB_MAXDIM] = {1, 1, 1};
+    std::vector<int> row_start0;            // host copy of the axis-0 row offsets (slab sizes)
+    const int* d_row_start[PB_MAXDIM] = {nullptr, nullptr, nullptr};
+    const int* d_jmin[PB_MAXDIM] = {nullptr, nullptr, nullptr};
+    const int* d_pair_i[PB_MAXDIM] = {nullptr, nullptr, nullptr};
+    const int* d_pair_j[PB_MAXDIM] = {nullptr, nullptr, nullptr};
+    void* mem = nullptr;                    // owned device memory (stand-alone structures)
+};
+
+struct pb200_assembler {
+    pb200_mlstruct ml;
+    int device = 0;
+    int dim = 0;
+    int form = 0;
+    int nfields = 0;
+    bool symmetric = false;
+    bool same_space = true;
+    AxisHost hax[PB_MAXDIM];
+    PbAxis dax[PB_MAXDIM];
+    size_t off_knots_u[PB_MAXDIM], off_knots_v[PB_MAXDIM];
+    Pool pool;
+    double* d_fields = nullptr;
+    std::vector<PbTerm> terms;
+    void* geo_scratch = nullptr;
+    long long npts = 0, nnz = 0;
+    int fast = 0;
+};
+
+static bool have_plan(int plan, int P, int Q) { return pb_find_walk(plan, P, Q) != nullptr; }
+
+static int detect_fast_path(const pb200_assembler* a) {
+    if (!a->same_space) return 0;
+    const int Q = a->hax[0].q;
+    for (int k = 0; k < a->dim; ++k)
+        if (a->hax[k].q != Q) return 0;
+    auto P = [&](int k) { return a->hax[k].U.p; };
+    if (a->form == PB200_FORM_MASS) {
+        for (int k = 0; k < a->dim; ++k)
+            if (!have_plan(PB_PLAN_COPY, P(k), Q)) return 0;
+        return 1;
+    }
+    if (a->form == PB200_FORM_STIFFNESS) {
+        if (a->dim == 2)
+            return have_plan(PB_PLAN_S1_2D, P(0), Q) && have_plan(PB_PLAN_FINAL4, P(1), Q);
+        return have_plan(PB_PLAN_S1A, P(0), Q) && have_plan(PB_PLAN_S1B, P(0), Q) && have_plan(PB_PLAN_FINAL4, P(1), Q)
+               && have_plan(PB_PLAN_S2B, P(1), Q) && have_plan(PB_PLAN_FINAL4, P(2), Q);
+    }
+    return 0;
+}
+
+static int run_basis(pb200_assembler* a, pbStream st) {
+    for (int k = 0; k < a->dim; ++k) {
+        AxisHost& H = a->hax[k];
+        PbAxis& D = a->dax[k];
+        const double* dku = reinterpret_cast<const double*>(a->pool.dev + a->off_knots_u[k]);
+        k_basis(dku, (int)H.U.kv.size(), H.U.p, D.nodes, H.G, D.nd, nullptr, const_cast<double*>(D.Vu), st);
+        if (!H.same) {
+            const double* dkv = reinterpret_cast<const double*>(a->pool.dev + a->off_knots_v[k]);
+            k_basis(dkv, (int)H.V.kv.size(), H.V.p, D.nodes, H.G, D.nd, nullptr, const_cast<double*>(D.Vv), st);
+        }
+    }
+    CK(pbLastError());
+    return 0;
+}
+
+extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream, pb200_assembler** out) {
+    if (!desc || !out) return fail(PB200_EINVAL, "null argument");
+    if (desc->dim < 2 || desc->dim > 3) return fail(PB200_EINVAL, "Assembler requires 2 or 3 knot vectors (dim=%d)", desc->dim);
+    if (desc->form != PB200_FORM_MASS && desc->form != PB200_FORM_STIFFNESS && desc->form != PB200_FORM_CUSTOM)
+        return fail(PB200_EINVAL, "unknown form id %d", desc->form);
+    std::unique_ptr<pb200_assembler> a(new pb200_assembler);
+    a->device = device;
+    a->dim = desc->dim;
+    a->form = desc->form;
+    const int dim = desc->dim;
+
+    a->npts = 1;
+    a->nnz = 1;
+    for (int k = 0; k < dim; ++k) {
+        const pb200_axis_desc& X = desc->axis[k];
+        AxisHost& H = a->hax[k];
+        int rc = build_kv(X.h_knots_trial, X.nknots_trial, X.p_trial, H.U);
+        if (rc) return rc;
+        H.same = (X.h_knots_test == nullptr);
+        rc = H.same ? build_kv(X.h_knots_trial, X.nknots_trial, X.p_trial, H.V)
+                    : build_kv(X.h_knots_test, X.nknots_test, X.p_test, H.V);
+        if (rc) return rc;
+        if (H.U.mesh != H.V.mesh) return fail(PB200_EINVAL, "trial and test space must share the mesh (axis %d)", k);
+        if (!H.same) a->same_space = false;
+        H.n = H.U.nspans();
+        H.q = X.nq;
+        if (H.q < 1 || H.q > 16) return fail(PB200_EINVAL, "invalid number of Gauss nodes per span: %d", H.q);
+        H.G = H.n * H.q;
+        if (!X.h_nodes || !X.h_weights) return fail(PB200_EINVAL, "Gauss rule missing (axis %d)", k);
+        H.nodes.assign(X.h_nodes, X.h_nodes + H.G);
+        H.weights.assign(X.h_weights, X.h_weights + H.G);
+        for (int s = 0; s < H.n; ++s)
+            for (int g = 0; g < H.q; ++g) {
+                const double t = H.nodes[s * H.q + g];
+                if (!(t >= H.U.mesh[s] && t <= H.U.mesh[s + 1]))
+                    return fail(PB200_EINVAL, "Gauss node %d of axis %d lies outside its span", s * H.q + g, k);
+            }
+        build_band(H.U, H.V, H.row_start, H.jmin, H.pair_i, H.pair_j);
+        H.M = (int)H.pair_i.size();
+        // transposed pairs and the retire table of the walk kernels (test == trial only)
+        H.tr.assign(H.M, -1);
+        const int P = H.U.p, N = H.V.N();
+        H.ret_mu.assign((size_t)N * (2 * P + 1), -1);
+        if (H.same) {
+            auto mu_of = [&](int i, int j) -> int {
+                if (i < 0 || j < 0 || i >= N || j >= N) return -1;
+                const int off = j - H.jmin[i];
+                if (off < 0 || off >= H.row_start[i + 1] - H.row_start[i]) return -1;
+                return H.row_start[i] + off;
+            };
+            for (int m = 0; m < H.M; ++m) H.tr[m] = mu_of(H.pair_j[m], H.pair_i[m]);
+            for (int f = 0; f < N; ++f)
+                for (int kk = 0; kk <= 2 * P; ++kk) {
+                    const int i = (kk <= P) ? f : f + (kk - P);
+                    const int j = (kk <= P) ? f + kk : f;
+                    H.ret_mu[(size_t)f * (2 * P + 1) + kk] = mu_of(i, j);
+                }
+        }
+        a->npts *= H.G;
+        a->nnz *= H.M;
+    }
+
+    if (desc->form == PB200_FORM_MASS) {
+        a->nfields = 1;
+        a->symmetric = a->same_space;
+        a->terms.push_back(PbTerm{0, 0, 0});
+    } else if (desc->form == PB200_FORM_STIFFNESS) {
+        a->nfields = dim * (dim + 1) / 2;
+        a->symmetric = a->same_space;
+        // sum_{a,b} B[b][a] d_a u d_b v with x,y,z indices a,b <-> tensor axes dim-1-a, dim-1-b
+        for (int b = 0; b < dim; ++b)
+            for (int c = 0; c < dim; ++c) {
+                const int lo = std::min(b, c), hi = std::max(b, c);
+                const int sym = lo * dim - lo * (lo - 1) / 2 + (hi - lo);
+                a->terms.push_back(PbTerm{sym, 1 + (dim - 1 - b), 1 + (dim - 1 - c)});
+            }
+    } else {
+        if (desc->nfields < 1 || desc->nfields > PB_MAXFIELDS) return fail(PB200_EINVAL, "invalid number of fields %d", desc->nfields);
+        if (desc->nterms < 1 || desc->nterms > PB_MAXTERMS || !desc->terms) return fail(PB200_EINVAL, "invalid number of terms %d", desc->nterms);
+        a->nfields = desc->nfields;
+        a->symmetric = desc->symmetric != 0;
+        for (int t = 0; t < desc->nterms; ++t) {
+            const pb200_term& T = desc->terms[t];
+            if (T.field < 0 || T.field >= a->nfields || T.slot_test < 0 || T.slot_test > dim || T.slot_trial < 0 || T.slot_trial > dim)
+                return fail(PB200_EINVAL, "invalid term %d", t);
+            a->terms.push_back(PbTerm{T.field, T.slot_test, T.slot_trial});
+        }
+    }
+
+    // ---- upload ---------------------------------------------------------------------------------
+    CK(pbSetDevice(device));
+    struct Offs { size_t nodes, weights, fu, fv, Vu, Vv, rs, jm, su, sv, pi, pj, tr, ret; } offs[PB_MAXDIM];
+    Pool& pool = a->pool;
+    const int nd = 2;
+    for (int k = 0; k < dim; ++k) {
+        AxisHost& H = a->hax[k];
+        Offs& o = offs[k];
+        a->off_knots_u[k] = pool.put(H.U.kv);
+        a->off_knots_v[k] = pool.put(H.V.kv);
+        o.nodes = pool.put(H.nodes);
+        o.weights = pool.put(H.weights);
+        o.fu = pool.put(H.U.first);
+        o.fv = pool.put(H.V.first);
+        o.Vu = pool.put(nullptr, (size_t)H.G * nd * (H.U.p + 1) * sizeof(double));
+        o.Vv = H.same ? o.Vu : pool.put(nullptr, (size_t)H.G * nd * (H.V.p + 1) * sizeof(double));
+        o.rs = pool.put(H.row_start);
+        o.jm = pool.put(H.jmin);
+        o.su = pool.put(H.U.supp);
+        o.sv = pool.put(H.V.supp);
+        o.pi = pool.put(H.pair_i);
+        o.pj = pool.put(H.pair_j);
+        o.tr = pool.put(H.tr);
+        o.ret = pool.put(H.ret_mu);
+    }
+    CK(pbMalloc((void**)&pool.dev, pool.host.size() + 256));
+    CK(pbMemcpyH2D(pool.dev, pool.host.data(), pool.host.size(), (pbStream)stream));
+    for (int k = 0; k < dim; ++k) {
+        AxisHost& H = a->hax[k];
+        PbAxis& D = a->dax[k];
+        const Offs& o = offs[k];
+        char* b = pool.dev;
+        D.n = H.n; D.q = H.q; D.G = H.G;
+        D.pu = H.U.p; D.pv = H.V.p; D.Nu = H.U.N(); D.Nv = H.V.N(); D.nd = nd; D.M = H.M;
+        D.nodes = (const double*)(b + o.nodes);
+        D.weights = (const double*)(b + o.weights);
+        D.first_u = (const int*)(b + o.fu);
+        D.first_v = (const int*)(b + o.fv);
+        D.Vu = (const double*)(b + o.Vu);
+        D.Vv = (const double*)(b + o.Vv);
+        D.row_start = (const int*)(b + o.rs);
+        D.jmin = (const int*)(b + o.jm);
+        D.supp_u = (const int*)(b + o.su);
+        D.supp_v = (const int*)(b + o.sv);
+        D.pair_i = (const int*)(b + o.pi);
+        D.pair_j = (const int*)(b + o.pj);
+        D.tr = (const int*)(b + o.tr);
+        D.ret_mu = (const int*)(b + o.ret);
+    }
+    int rc = run_basis(a.get(), (pbStream)stream);
+    if (rc) return rc;
+    CK(pbStreamSync((pbStream)stream));   // pool.host may be released by the caller's thread later
+    a->fast = detect_fast_path(a.get());
+    a->ml.device = device;
+    a->ml.dim = dim;
+    a->ml.row_start0 = a->hax[0].row_start;
+    for (int k = 0; k < dim; ++k) {
+        a->ml.Nv[k] = a->hax[k].V.N();
+        a->ml.Nu[k] = a->hax[k].U.N();
+        a->ml.M[k] = a->hax[k].M;
+        a->ml.d_row_start[k] = a->dax[k].row_start;
+        a->ml.d_jmin[k] = a->dax[k].jmin;
+        a->ml.d_pair_i[k] = a->dax[k].pair_i;
+        a->ml.d_pair_j[k] = a->dax[k].pair_j;
+    }
+    *out = a.release();
+    return 0;
+}
+
+extern "C" const pb200_mlstruct* pb200_asm_mlstruct(const pb200_assembler* a) { return a ? &a->ml : nullptr; }
+
+extern "C" int pb200_mlstruct_create(int nlevels, const int* rows, const int* cols, const int* nband,
+                                     const uint32_t* const* h_bidx, int device, pb200_mlstruct** out) {
+    if (!rows || !cols || !nband || !h_bidx || !out) return fail(PB200_EINVAL, "null argument");
+    if (nlevels < 2 || nlevels > PB_MAXDIM) return fail(PB200_EUNSUPPORTED, "MLB kernels support 2 or 3 levels (got %d)", nlevels);
+    std::unique_ptr<pb200_mlstruct> s(new pb200_mlstruct);
+    s->device = device;
+    s->dim = nlevels;
+    Pool pool;
+    size_t off[PB_MAXDIM][4];
+    for (int k = 0; k < nlevels; ++k) {
+        const int m = rows[k], M = nband[k];
+        if (m < 1 || cols[k] < 1 || M < 1) return fail(PB200_EINVAL, "empty level %d", k);
+        std::vector<int> rs(m + 1, 0), jm(m, 0), pi(M), pj(M);
+        for (int e = 0; e < M; ++e) {
+            pi[e] = (int)h_bidx[k][2 * e];
+            pj[e] = (int)h_bidx[k][2 * e + 1];
+            if (pi[e] >= m || pj[e] >= cols[k]) return fail(PB200_EINVAL, "index out of range in level %d", k);
+            if (e > 0 && (pi[e] < pi[e - 1] || (pi[e] == pi[e - 1] && pj[e] != pj[e - 1] + 1)))
+                return fail(PB200_EUNSUPPORTED, "level %d: rows must be sorted with contiguous column ranges", k);
+            rs[pi[e] + 1]++;
+        }
+        for (int i = 0; i < m; ++i) rs[i + 1] += rs[i];
+        for (int i = 0; i < m; ++i) jm[i] = rs[i + 1] > rs[i] ? pj[rs[i]] : 0;
+        s->Nv[k] = m; s->Nu[k] = cols[k]; s->M[k] = M;
+        if (k == 0) s->row_start0 = rs;
+        off[k][0] = pool.put(rs); off[k][1] = pool.put(jm); off[k][2] = pool.put(pi); off[k][3] = pool.put(pj);
+    }
+    CK(pbSetDevice(device));
+    CK(pbMalloc(&s->mem, pool.host.size() + 256));
+    CK(pbMemcpyH2D(s->mem, pool.host.data(), pool.host.size(), (pbStream)0));
+    CK(pbStreamSync((pbStream)0));
+    for (int k = 0; k < nlevels; ++k) {
+        char* b = (char*)s->mem;
+        s->d_row_start[k] = (const int*)(b + off[k][0]);
+        s->d_jmin[k] = (const int*)(b + off[k][1]);
+        s->d_pair_i[k] = (const int*)(b + off[k][2]);
+        s->d_pair_j[k] = (const int*)(b + off[k][3]);
+    }
+    *out = s.release();
+    return 0;
+}
+
+extern "C" int pb200_mlstruct_destroy(pb200_mlstruct* s) {
+    if (!s) return 0;
+    if (s->mem) { pbSetDevice(s->device); pbFree(s->mem); }
+    delete s;
+    return 0;
+}
+
+extern "C" int pb200_asm_destroy(pb200_assembler* a) {
+    if (!a) return 0;
+    pbSetDevice(a->device);
+    if (a->pool.dev) pbFree(a->pool.dev);
+    if (a->geo_scratch) pbFree(a->geo_scratch);
+    delete a;
+    return 0;
+}
+
+extern "C" int pb200_asm_tabulate(pb200_assembler* a, void* stream) {
+    if (!a) return fail(PB200_EINVAL, "null handle");
+    CK(pbSetDevice(a->device));
+    return run_basis(a, (pbStream)stream);
+}
+
+extern "C" int pb200_asm_info(const pb200_assembler* a, pb200_info* info) {
+    if (!a || !info) return fail(PB200_EINVAL, "null argument");
+    memset(info, 0, sizeof *info);
+    info->dim = a->dim;
+    for (int k = 0; k < a->dim; ++k) {
+        info->ndofs_test[k] = a->hax[k].V.N();
+        info->ndofs_trial[k] = a->hax[k].U.N();
+        info->nnodes[k] = a->hax[k].G;
+        info->nband[k] = a->hax[k].M;
+    }
+    info->nfields = a->nfields;
+    info->fast_path = a->fast;
+    info->nnz = a->nnz;
+    info->npoints = a->npts;
+    return 0;
+}
+
+extern "C" int pb200_asm_structure(const pb200_assembler* a, int axis, uint32_t* h_bidx) {
+    if (!a || !h_bidx || axis < 0 || axis >= a->dim) return fail(PB200_EINVAL, "invalid argument");
+    const AxisHost& H = a->hax[axis];
+    for (int m = 0; m < H.M; ++m) {
+        h_bidx[2 * m] = (uint32_t)H.pair_i[m];
+        h_bidx[2 * m + 1] = (uint32_t)H.pair_j[m];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: geometry tables + fields
+// ------------------------------------------------------------------------------------------------
+struct GeoTables {
+    PbGeoDev dev;
+    void* mem = nullptr;
+};
+
+// uploads knots + control net and evaluates the 1D geometry tables at the given device nodes
+static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, const double* const* d_nodes,
+                            pbStream st, GeoTables& T, bool square = true) {
+    if (!geo) return fail(PB200_EINVAL, "geometry missing");
+    if (geo->sdim != dim) return fail(PB200_EINVAL, "Geometry has wrong source dimension");
+    if (square && geo->dim != dim) return fail(PB200_EINVAL, "Geometry has wrong dimension");
+    if (geo->dim < 1 || geo->dim > 3) return fail(PB200_EUNSUPPORTED, "geometry with %d components not supported", geo->dim);
+    if (!geo->h_coeffs) return fail(PB200_EINVAL, "geometry coefficients missing");
+    const int nc = geo->dim + (geo->rational ? 1 : 0);
+    size_t bytes = 0;
+    auto reserve = [&](size_t b) { size_t o = (bytes + 255) & ~size_t(255); bytes = o + b; return o; };
+    size_t off_k[PB_MAXDIM], off_f[PB_MAXDIM], off_v[PB_MAXDIM], off_c;
+    long long ncoef = 1;
+    for (int k = 0; k < dim; ++k) {
+        if (geo->p[k] < 0 || geo->p[k] > PB_MAXP) return fail(PB200_EUNSUPPORTED, "geometry degree %d not supported", geo->p[k]);
+        if (!geo->h_knots[k] || geo->nknots[k] < 2 * (geo->p[k] + 1)) return fail(PB200_EINVAL, "invalid geometry knot vector");
+        off_k[k] = reserve(sizeof(double) * geo->nknots[k]);
+        off_f[k] = reserve(sizeof(int) * G[k]);
+        off_v[k] = reserve(sizeof(double) * G[k] * 2 * (geo->p[k] + 1));
+        ncoef *= geo->nknots[k] - geo->p[k] - 1;
+    }
+    off_c = reserve(sizeof(double) * ncoef * nc);
+    CK(pbMalloc(&T.mem, bytes + 256));
+    char* b = (char*)T.mem;
+    PbGeoDev& D = T.dev;
+    D.sdim = dim; D.dim = geo->dim; D.nc = nc; D.rational = geo->rational ? 1 : 0;
+    for (int k = 0; k < dim; ++k) {
+        D.pg[k] = geo->p[k];
+        D.Ng[k] = geo->nknots[k] - geo->p[k] - 1;
+        CK(pbMemcpyH2D(b + off_k[k], geo->h_knots[k], sizeof(double) * geo->nknots[k], st));
+        D.gfirst[k] = (const int*)(b + off_f[k]);
+        D.GV[k] = (const double*)(b + off_v[k]);
+        k_basis((const double*)(b + off_k[k]), geo->nknots[k], geo->p[k], d_nodes[k], G[k], 2, (int*)(b + off_f[k]),
+                (double*)(b + off_v[k]), st);
+    }
+    for (int k = dim; k < PB_MAXDIM; ++k) { D.pg[k] = 0; D.Ng[k] = 1; D.gfirst[k] = nullptr; D.GV[k] = nullptr; }
+    CK(pbMemcpyH2D(b + off_c, geo->h_coeffs, sizeof(double) * ncoef * nc, st));
+    D.coeffs = (const double*)(b + off_c);
+    CK(pbLastError());
+    return 0;
+}
+
+extern "C" int pb200_asm_bind_fields(pb200_assembler* a, double* d_fields) {
+    if (!a) return fail(PB200_EINVAL, "null handle");
+    a->d_fields = d_fields;
+    return 0;
+}
+
+template <int DIM, class Prog>
+static int launch_fields(const PbFieldParams& prm, pbStream st) {
+    k_fields<DIM, Prog>(prm, st);
+    CK(pbLastError());
+    return 0;
+}
+
+static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, const double* d_jac, pbStream st) {
+    if (!a) return fail(PB200_EINVAL, "null handle");
+    if (!a->d_fields) return fail(PB200_EINVAL, "no field buffer bound (pb200_asm_bind_fields)");
+    if (a->form == PB200_FORM_CUSTOM) return fail(PB200_EINVAL, "custom forms upload their fields");
+    CK(pbSetDevice(a->device));
+    PbFieldParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.dim = a->dim;
+    const double* d_nodes[PB_MAXDIM] = {nullptr, nullptr, nullptr};
+    int G[PB_MAXDIM] = {1, 1, 1};
+    for (int k = 0; k < a->dim; ++k) {
+        prm.G[k] = G[k] = a->hax[k].G;
+        prm.gw[k] = a->dax[k].weights;
+        d_nodes[k] = a->dax[k].nodes;
+    }
+    prm.fields = a->d_fields;
+    prm.npts = a->npts;
+    prm.nf = a->nfields;
+    prm.jac_in = d_jac;
+    GeoTables T;
+    if (!d_jac) {
+        if (a->geo_scratch) { CK(pbStreamSync(st)); CK(pbFree(a->geo_scratch)); a->geo_scratch = nullptr; }
+        int rc = build_geo_tables(geo, a->dim, G, d_nodes, st, T);
+        if (rc) { if (T.mem) pbFree(T.mem); return rc; }
+        a->geo_scratch = T.mem;
+        prm.geo = T.dev;
+    }
+    if (a->dim == 2)
+        return a->form == PB200_FORM_MASS ? launch_fields<2, PbProgMass<2>>(prm, st) : launch_fields<2, PbProgStiffness<2>>(prm, st);
+    return a->form == PB200_FORM_MASS ? launch_fields<3, PbProgMass<3>>(prm, st) : launch_fields<3, PbProgStiffness<3>>(prm, st);
+}
+
+extern "C" int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc* geo, void* stream) {
+    return compute_fields_impl(a, geo, nullptr, (pbStream)stream);
+}
+extern "C" int pb200_asm_compute_fields_from_jacobian(pb200_assembler* a, const double* d_jac, void* stream) {
+    if (!d_jac) return fail(PB200_EINVAL, "null Jacobian array");
+    return compute_fields_impl(a, nullptr, d_jac, (pbStream)stream);
+}
+
+extern "C" int pb200_geo_eval_grid(const pb200_geo_desc* geo, const int* npts, const double* const* h_grid,
+                                   double* d_values, double* d_jac, int device, void* stream) {
+    if (!geo || !npts || !h_grid) return fail(PB200_EINVAL, "null argument");
+    const int dim = geo->sdim;
+    if (dim < 2 || dim > 3) return fail(PB200_EUNSUPPORTED, "geometry evaluation implemented for 2 and 3 parameters");
+    if (geo->dim > 3) return fail(PB200_EUNSUPPORTED, "at most 3 output components");
+    CK(pbSetDevice(device));
+    pbStream st = (pbStream)stream;
+    double* d_nodes_mem = nullptr;
+    size_t tot = 0;
+    for (int k = 0; k < dim; ++k) tot += npts[k];
+    CK(pbMalloc((void**)&d_nodes_mem, sizeof(double) * tot));
+    const double* d_nodes[PB_MAXDIM] = {nullptr, nullptr, nullptr};
+    size_t o = 0;
+    long long total = 1;
+    for (int k = 0; k < dim; ++k) {
+        CK(pbMemcpyH2D(d_nodes_mem + o, h_grid[k], sizeof(double) * npts[k], st));
+        d_nodes[k] = d_nodes_mem + o;
+        o += npts[k];
+        total *= npts[k];
+    }
+    GeoTables T;
+    int rc = build_geo_tables(geo, dim, npts, d_nodes, st, T, /*square=*/false);
+    if (rc == 0) {
+        if (dim == 2) k_geo_grid<2>(T.dev, npts, total, d_values, d_jac, st);
+        else k_geo_grid<3>(T.dev, npts, total, d_values, d_jac, st);
+        pbError e = pbLastError();
+        if (e != pbSuccess) rc = fail(PB200_ECUDA, "geometry kernel launch failed: %s", pbErrorString(e));
+    }
+    pbStreamSync(st);
+    if (T.mem) pbFree(T.mem);
+    pbFree(d_nodes_mem);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: the sum-factorised pipeline
+// ------------------------------------------------------------------------------------------------
+struct Slab {
+    int ra, rb;             // rows of axis 0
+    int ea, eb;             // extended rows (transposed partners)
+    int sa, sb;             // spans of axis 0 covered
+    int mu_lo, mu_hi;       // band range of the rows
+    int ext_lo, ext_hi;     // band range of the extended rows
+};
+
+static int make_slab(const pb200_assembler* a, int ra, int rb, bool sym, Slab& S) {
+    const AxisHost& H = a->hax[0];
+    const int N = H.V.N();
+    if (ra < 0 || rb > N || ra >= rb) return fail(PB200_EINVAL, "invalid row slab [%d,%d) of %d rows", ra, rb, N);
+    S.ra = ra; S.rb = rb;
+    const int P = H.U.p;
+    S.ea = sym ? std::max(0, ra - P) : ra;
+    S.eb = sym ? std::min(N, rb + P) : rb;
+    S.sa = H.V.supp[2 * ra];
+    S.sb = H.V.supp[2 * (rb - 1) + 1];
+    S.mu_lo = H.row_start[ra]; S.mu_hi = H.row_start[rb];
+    S.ext_lo = H.row_start[S.ea]; S.ext_hi = H.row_start[S.eb];
+    return 0;
+}
+
+static bool uses_transposes(const pb200_assembler* a) { return a->form == PB200_FORM_STIFFNESS; }
+
+static void stage_sizes(const pb200_assembler* a, const Slab& S, size_t& x1_terms, size_t& x1_stride, size_t& x2_terms,
+                        size_t& x2_stride) {
+    const size_t Mext = (size_t)(S.ext_hi - S.ext_lo);
+    const bool st = a->form == PB200_FORM_STIFFNESS;
+    if (a->dim == 2) {
+        x1_terms = st ? 3 : 1;
+        x1_stride = Mext * a->hax[1].G;
+        x2_terms = 0; x2_stride = 0;
+    } else {
+        x1_terms = st ? 6 : 1;
+        x1_stride = Mext * a->hax[1].G * a->hax[2].G;
+        x2_terms = st ? 3 : 1;
+        x2_stride = Mext * a->hax[1].M * a->hax[2].G;
+    }
+}
+
+extern "C" int pb200_asm_workspace_bytes(const pb200_assembler* a, int row0_begin, int row0_end, size_t* bytes) {
+    if (!a || !bytes) return fail(PB200_EINVAL, "null argument");
+    if (!a->fast) { *bytes = 0; return 0; }
+    Slab S;
+    int rc = make_slab(a, row0_begin, row0_end, uses_transposes(a), S);
+    if (rc) return rc;
+    size_t t1, s1, t2, s2;
+    stage_sizes(a, S, t1, s1, t2, s2);
+    *bytes = (t1 * s1 + t2 * s2) * sizeof(double) + 512;
+    return 0;
+}
+
+static int run_stage(int plan, const pb200_assembler* a, int axis, PbWalkParams& prm, pbStream st) {
+    const AxisHost& H = a->hax[axis];
+    const PbAxis& D = a->dax[axis];
+    const int P = H.U.p, Q = H.q;
+    PbWalkLaunch fn = pb_find_walk(plan, P, Q);
+    if (!fn) return fail(PB200_EUNSUPPORTED, "no walk kernel for plan %d, p=%d, q=%d", plan, P, Q);
+    prm.N = H.V.N();
+    prm.first = D.first_u;
+    prm.V2 = D.Vu;
+    prm.ret_mu = D.ret_mu;
+    const size_t smem = (size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double);
+    const int use_smem = smem <= 160 * 1024;
+    int e = fn(&prm, use_smem, use_smem ? smem : 0, st);
+    if (e) return fail(PB200_ECUDA, "walk kernel launch failed (plan %d, p=%d, q=%d): %s", plan, P, Q, pbErrorString((pbError)e));
+    return 0;
+}
+
+extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int row0_end, double* d_out, void* d_work,
+                                      size_t work_bytes, void* stream) {
+    if (!a || !d_out) return fail(PB200_EINVAL, "null argument");
+    if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
+    if (!a->fast) return pb200_asm_assemble_mlb_entrywise(a, row0_begin, row0_end, d_out, stream);
+    CK(pbSetDevice(a->device));
+    pbStream st = (pbStream)stream;
+    const bool stiff = a->form == PB200_FORM_STIFFNESS;
+    Slab S;
+    int rc = make_slab(a, row0_begin, row0_end, uses_transposes(a), S);
+    if (rc) return rc;
+    size_t t1, s1, t2, s2;
+    stage_sizes(a, S, t1, s1, t2, s2);
+    const size_t need = (t1 * s1 + t2 * s2) * sizeof(double);
+    if (!d_work || work_bytes < need) return fail(PB200_ENOMEM, "workspace too small: need %zu bytes, have %zu", need, work_bytes);
+    double* X1 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(d_work) + 255) & ~uintptr_t(255));
+    if ((size_t)((char*)X1 - (char*)d_work) + need > work_bytes) X1 = (double*)d_work;
+    double* X2 = X1 + t1 * s1;
+    const long long npts = a->npts;
+    const double* F = a->d_fields;
+    const int keep_mode = uses_transposes(a) ? 2 : 1;
+
+    const AxisHost &H0 = a->hax[0], &H1 = a->hax[1];
+    const PbAxis &D0 = a->dax[0], &D1 = a->dax[1];
+    const long long G1 = H1.G, M1 = H1.M;
+    const int Mrows = S.mu_hi - S.mu_lo, Mext = S.ext_hi - S.ext_lo;
+
+    auto base_params = [&]() {
+        PbWalkParams p;
+        memset(&p, 0, sizeof p);
+        p.V = 1; p.X = 1;
+        return p;
+    };
+
+    if (a->dim == 2) {
+        // stage 1: axis 0,  fields[f][g0][g1] -> X1[t][mu0 - ext_lo][g1]
+        {
+            PbWalkParams p = base_params();
+            p.X = (int)G1; p.nthreads = G1;
+            p.in_sx = 1; p.in_sc = G1;
+            p.out_sx = 1; p.out_smu = G1; p.mu_base = S.ext_lo;
+            p.s_begin = S.sa; p.s_end = S.sb;
+            p.w_mode = keep_mode; p.w_lo = S.ra; p.w_hi = S.rb;
+            if (stiff) {
+                p.in[0] = F + 2 * npts; p.in[1] = F + 1 * npts; p.in[2] = F;     // B11, B01, B00
+                for (int t = 0; t < 3; ++t) p.out[t] = X1 + t * s1;
+                rc = run_stage(PB_PLAN_S1_2D, a, 0, p, st);
+            } else {
+                p.in[0] = F; p.out[0] = X1;
+                rc = run_stage(PB_PLAN_COPY, a, 0, p, st);
+            }
+            if (rc) return rc;
+        }
+        // stage 2: axis 1,  X1[t][mu0][g1] -> out[mu0 - mu_lo][mu1]
+        {
+            PbWalkParams p = base_params();
+            p.nthreads = Mrows;
+            p.u_begin = S.mu_lo; p.u_base_in = S.ext_lo; p.u_base_out = S.mu_lo;
+            p.tr_u = D0.tr;
+            p.in_su = G1; p.in_sc = 1;
+            p.out_su = M1; p.out_smu = 1; p.mu_base = 0;
+            p.s_begin = 0; p.s_end = H1.n;
+            p.out[0] = d_out;
+            if (stiff) {
+                p.in[0] = X1; p.in[1] = X1 + s1; p.in[2] = X1 + s1; p.in[3] = X1 + 2 * s1;
+                rc = run_stage(PB_PLAN_FINAL4, a, 1, p, st);
+            } else {
+                p.in[0] = X1;
+                rc = run_stage(PB_PLAN_COPY, a, 1, p, st);
+            }
+            return rc;
+        }
+    }
+
+    const AxisHost& H2 = a->hax[2];
+    const PbAxis& D2 = a->dax[2];
+    (void)D2;
+    const long long G2 = H2.G, M2 = H2.M;
+    // stage 1: axis 0,  fields[f][g0][g1][g2] -> X1[t][mu0 - ext_lo][g1][g2]
+    {
+        PbWalkParams p = base_params();
+        p.X = (int)(G1 * G2); p.nthreads = G1 * G2;
+        p.in_sx = 1; p.in_sc = G1 * G2;
+        p.out_sx = 1; p.out_smu = G1 * G2; p.mu_base = S.ext_lo;
+        p.s_begin = S.sa; p.s_end = S.sb;
+        p.w_mode = keep_mode; p.w_lo = S.ra; p.w_hi = S.rb;
+        if (stiff) {
+            PbWalkParams pa = p, pb = p;
+            pa.in[0] = F + 5 * npts; pa.in[1] = F + 4 * npts; pa.in[2] = F + 2 * npts;   // B22, B12, B02
+            for (int t = 0; t < 3; ++t) pa.out[t] = X1 + t * s1;
+            pb.in[0] = F + 3 * npts; pb.in[1] = F + 1 * npts; pb.in[2] = F;              // B11, B01, B00
+            for (int t = 0; t < 3; ++t) pb.out[t] = X1 + (3 + t) * s1;
+            rc = run_stage(PB_PLAN_S1A, a, 0, pa, st);
+            if (rc) return rc;
+            rc = run_stage(PB_PLAN_S1B, a, 0, pb, st);
+        } else {
+            p.in[0] = F; p.out[0] = X1;
+            rc = run_stage(PB_PLAN_COPY, a, 0, p, st);
+        }
+        if (rc) return rc;
+    }
+    // stage 2: axis 1,  X1[t][mu0][g1][g2] -> X2[t][mu0][mu1][g2]
+    {
+        PbWalkParams p = base_params();
+        p.X = (int)G2; p.nthreads = (long long)Mext * G2;
+        p.u_begin = S.ext_lo; p.u_base_in = S.ext_lo; p.u_base_out = S.ext_lo;
+        p.tr_u = D0.tr;
+        p.u_pair_i = D0.pair_i; p.u_pair_j = D0.pair_j;
+        p.u_mode = keep_mode; p.u_lo = S.ra; p.u_hi = S.rb;
+        p.in_su = G1 * G2; p.in_sx = 1; p.in_sc = G2;
+        p.out_su = M1 * G2; p.out_sx = 1; p.out_smu = G2; p.mu_base = 0;
+        p.s_begin = 0; p.s_end = H1.n;
+        if (stiff) {
+            PbWalkParams pa = p, pb = p;
+            pa.in[0] = X1; pa.in[1] = X1 + s1; pa.in[2] = X1 + s1; pa.in[3] = X1 + 3 * s1;
+            pa.out[0] = X2;
+            pb.in[0] = X1 + 2 * s1; pb.in[1] = X1 + 4 * s1; pb.in[2] = X1 + 5 * s1;
+            pb.out[0] = X2 + s2; pb.out[1] = X2 + 2 * s2;
+            rc = run_stage(PB_PLAN_FINAL4, a, 1, pa, st);
+            if (rc) return rc;
+            rc = run_stage(PB_PLAN_S2B, a, 1, pb, st);
+        } else {
+            p.in[0] = X1; p.out[0] = X2;
+            rc = run_stage(PB_PLAN_COPY, a, 1, p, st);
+        }
+        if (rc) return rc;
+    }
+    // stage 3: axis 2,  X2[t][mu0][mu1][g2] -> out[mu0 - mu_lo][mu1][mu2]
+    {
+        PbWalkParams p = base_params();
+        p.V = (int)M1; p.nthreads = (long long)Mrows * M1;
+        p.u_begin = S.mu_lo; p.u_base_in = S.ext_lo; p.u_base_out = S.mu_lo;
+        p.tr_u = D0.tr; p.tr_v = D1.tr;
+        p.in_su = M1 * G2; p.in_sv = G2; p.in_sc = 1;
+        p.out_su = M1 * M2; p.out_sv = M2; p.out_smu = 1; p.mu_base = 0;
+        p.s_begin = 0; p.s_end = H2.n;
+        p.out[0] = d_out;
+        if (stiff) {
+            p.in[0] = X2; p.in[1] = X2 + s2; p.in[2] = X2 + s2; p.in[3] = X2 + 2 * s2;
+            rc = run_stage(PB_PLAN_FINAL4, a, 2, p, st);
+        } else {
+            p.in[0] = X2;
+            rc = run_stage(PB_PLAN_COPY, a, 2, p, st);
+        }
+    }
+    (void)H0;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-entry path
+// ------------------------------------------------------------------------------------------------
+static void fill_entry_params(const pb200_assembler* a, PbEntryParams& prm) {
+    memset(&prm, 0, sizeof prm);
+    prm.dim = a->dim;
+    for (int k = 0; k < a->dim; ++k) prm.ax[k] = a->dax[k];
+    prm.fields = a->d_fields;
+    prm.npts = a->npts;
+    prm.nterms = (int)a->terms.size();
+    for (int t = 0; t < prm.nterms; ++t) prm.terms[t] = a->terms[t];
+}
+
+extern "C" int pb200_asm_multi_entries(pb200_assembler* a, const uint64_t* d_ij, size_t n, double* d_out, void* stream) {
+    if (!a || (n && (!d_ij || !d_out))) return fail(PB200_EINVAL, "null argument");
+    if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
+    if (n == 0) return 0;
+    CK(pbSetDevice(a->device));
+    PbEntryParams prm;
+    fill_entry_params(a, prm);
+    prm.ij = reinterpret_cast<const unsigned long long*>(d_ij);
+    prm.n = (long long)n;
+    prm.out = d_out;
+    if (a->dim == 2) k_entries<2>(prm, (pbStream)stream);
+    else k_entries<3>(prm, (pbStream)stream);
+    CK(pbLastError());
+    return 0;
+}
+
+extern "C" int pb200_asm_assemble_mlb_entrywise(pb200_assembler* a, int row0_begin, int row0_end, double* d_out, void* stream) {
+    if (!a || !d_out) return fail(PB200_EINVAL, "null argument");
+    if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
+    CK(pbSetDevice(a->device));
+    Slab S;
+    int rc = make_slab(a, row0_begin, row0_end, false, S);
+    if (rc) return rc;
+    PbEntryParams prm;
+    fill_entry_params(a, prm);
+    prm.out = d_out;
+    long long count = S.mu_hi - S.mu_lo;
+    for (int k = 1; k < a->dim; ++k) count *= a->hax[k].M;
+    if (a->dim == 2) k_entries_mlb<2>(prm, S.mu_lo, count, (pbStream)stream);
+    else k_entries_mlb<3>(prm, S.mu_lo, count, (pbStream)stream);
+    CK(pbLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLB utilities
+// ------------------------------------------------------------------------------------------------
+static int fill_mlb_params(const pb200_mlstruct* a, int ra, int rb, const double* d_mlb, PbMlbParams& p) {
+    const int N = a->Nv[0];
+    if (ra < 0 || rb > N || ra >= rb) return fail(PB200_EINVAL, "invalid row slab [%d,%d) of %d rows", ra, rb, N);
+    memset(&p, 0, sizeof p);
+    p.dim = a->dim;
+    for (int k = 0; k < a->dim; ++k) {
+        p.Nv[k] = a->Nv[k];
+        p.Nu[k] = a->Nu[k];
+        p.M[k] = a->M[k];
+        p.row_start[k] = a->d_row_start[k];
+        p.jmin[k] = a->d_jmin[k];
+        p.pair_i[k] = a->d_pair_i[k];
+        p.pair_j[k] = a->d_pair_j[k];
+    }
+    p.row0_begin = ra; p.row0_end = rb;
+    p.data = d_mlb;
+    return 0;
+}
+
+extern "C" int pb200_mlb_to_csr(const pb200_mlstruct* a, int ra, int rb, const double* d_mlb, void* d_indptr,
+                                void* d_indices, double* d_values, int idx_bytes, void* stream) {
+    if (!a || !d_mlb || !d_indptr || !d_indices || !d_values) return fail(PB200_EINVAL, "null argument");
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
+    CK(pbSetDevice(a->device));
+    PbMlbParams p;
+    int rc = fill_mlb_params(a, ra, rb, d_mlb, p);
+    if (rc) return rc;
+    long long nrows = rb - ra, count = a->row_start0[rb] - a->row_start0[ra];
+    for (int k = 1; k < a->dim; ++k) { nrows *= p.Nv[k]; count *= p.M[k]; }
+    if (idx_bytes == 4 && count > 2147483647LL) return fail(PB200_EINVAL, "slab has %lld entries: needs 64-bit CSR indices", count);
+    pbStream st = (pbStream)stream;
+    if (idx_bytes == 4) k_csr<int>(p, nrows, count, (int*)d_indptr, (int*)d_indices, d_values, st);
+    else k_csr<long long>(p, nrows, count, (long long*)d_indptr, (long long*)d_indices, d_values, st);
+    CK(pbLastError());
+    return 0;
+}
+
+extern "C" int pb200_mlb_matvec(const pb200_mlstruct* a, int ra, int rb, const double* d_mlb, const double* d_x,
+                                int x_j0_begin, double* d_y, void* stream) {
+    if (!a || !d_mlb || !d_x || !d_y) return fail(PB200_EINVAL, "null argument");
+    CK(pbSetDevice(a->device));
+    PbMlbParams p;
+    int rc = fill_mlb_params(a, ra, rb, d_mlb, p);
+    if (rc) return rc;
+    long long nrows = rb - ra;
+    for (int k = 1; k < a->dim; ++k) nrows *= p.Nv[k];
+    k_matvec(p, nrows, d_x, x_j0_begin, d_y, (pbStream)stream);
+    CK(pbLastError());
+    return 0;
+}
+
+extern "C" int pb200_kron_matvec(int d, const double* const* d_factors, const int* rows, const int* cols,
+                                 const double* d_x, double* d_y, double* d_tmp, void* stream) {
+    if (d < 1 || d > 8 || !d_factors || !rows || !cols || !d_x || !d_y) return fail(PB200_EINVAL, "invalid argument");
+    // apply the factors from the last axis to the first; intermediate shape: (rows[0..k-1] ; cols[k..])
+    long long maxsz = 1;
+    {
+        long long sz = 1;
+        for (int k = 0; k < d; ++k) sz *= cols[k];
+        maxsz = sz;
+        for (int k = d - 1; k >= 0; --k) { sz = sz / cols[k] * rows[k]; maxsz = std::max(maxsz, sz); }
+    }
+    if (d > 1 && !d_tmp) return fail(PB200_EINVAL, "temporary buffer missing");
+    const double* cur = d_x;
+    pbStream st = (pbStream)stream;
+    for (int k = d - 1; k >= 0; --k) {
+        long long outer = 1, inner = 1;
+        for (int l = 0; l < k; ++l) outer *= cols[l];
+        for (int l = k + 1; l < d; ++l) inner *= rows[l];
+        double* dst = (k == 0) ? d_y : (d_tmp + (((d - 1 - k) & 1) ? maxsz : 0));
+        k_modek(d_factors[k], rows[k], cols[k], cur, outer, inner, dst, st);
+        cur = dst;
+    }
+    CK(pbLastError());
+    return 0;
+}
+
+extern "C" int pb200_basis_eval(const double* d_knots, int nknots, int p, const double* d_nodes, int m, int nderiv,
+                                int32_t* d_first, double* d_values, void* stream) {
+    if (!d_knots || !d_nodes || !d_values) return fail(PB200_EINVAL, "null argument");
+    if (p < 0 || p > PB_MAXP) return fail(PB200_EUNSUPPORTED, "spline degree %d above the supported maximum %d", p, PB_MAXP);
+    if (nderiv < 0 || nderiv > 2) return fail(PB200_EUNSUPPORTED, "derivatives up to order 2 are supported");
+    if (m <= 0) return 0;
+    k_basis(d_knots, nknots, p, d_nodes, m, nderiv + 1, d_first, d_values, (pbStream)stream);
+    CK(pbLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 throughput probe
+// ------------------------------------------------------------------------------------------------
+#ifndef PB_EMULATE
+__global__ void __launch_bounds__(256) pb_dfma_kernel(int iters, double seed, double* sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) sink[0] = s;
+}
+
+#endif
+
+extern "C" int pb200_probe_fp64(int device, int iters, double* gflops) {
+    if (!gflops || iters < 1) return fail(PB200_EINVAL, "invalid argument");
+#ifdef PB_EMULATE
+    (void)device;
+    return fail(PB200_EUNSUPPORTED, "no device in the emulation build");
+#else
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double* sink = nullptr;
+    CK(cudaMalloc((void**)&sink, 8));
+    const int blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    pb_dfma_kernel<<<blocks, 256>>>(iters / 8 + 1, 1.0, sink);      // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        pb_dfma_kernel<<<blocks, 256>>>(iters, 1.0, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * 256.0 * blocks;
+        best = std::max(best, fl / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *gflops = best;
+    return 0;
+#endif
+}

@@ -1,0 +1,130 @@
+// Per-entry quadrature — the `multi_entries` / `entry` operator of the assembler protocol.
+//
+// Restates the reference's entry-wise path (pyiga/genericasm.pxi:691-700 `multi_entries_chunk`,
+// pyiga/assemblers.pyx:1499-1540 `entry_impl`, :1455-1494 `combine`): unravel (I,J) into per-axis
+// indices, intersect the supports of test function i and trial function j on every axis (empty ->
+// the entry stays 0), then sum the integrand over the Gauss points of the joint support.
+// One thread per requested entry.  It serves scattered index lists (hierarchical / low-rank
+// callers of the protocol) and is the general fall-back for configurations the sum-factorised
+// pipeline has no instantiation for; full-matrix assembly goes through walk.cuh instead.
+//
+// The integrand is a list of terms  C_t(g) * d^{bt} v_i(g) * d^{bu} u_j(g)  where slot 0 is the
+// function value and slot 1+k the derivative along tensor axis k.
+#pragma once
+#include "common.cuh"
+
+struct PbTerm { int field; int bt; int bu; };
+
+struct PbEntryParams {
+    int dim;
+    PbAxis ax[PB_MAXDIM];
+    const double* fields;       // [nf][G0][G1][G2]
+    long long npts;
+    int nterms;
+    PbTerm terms[PB_MAXTERMS];
+    const unsigned long long* ij;   // [n][2]
+    long long n;
+    double* out;                // [n]
+};
+
+template <int DIM>
+PB_HD double pb_entry(const PbEntryParams& prm, unsigned long long I, unsigned long long J) {
+    int i[3] = {0, 0, 0}, j[3] = {0, 0, 0};
+    for (int k = DIM - 1; k >= 0; --k) {
+        i[k] = (int)(I % (unsigned long long)prm.ax[k].Nv); I /= (unsigned long long)prm.ax[k].Nv;
+        j[k] = (int)(J % (unsigned long long)prm.ax[k].Nu); J /= (unsigned long long)prm.ax[k].Nu;
+    }
+    if (I != 0 || J != 0) return 0.0;                         // index outside the matrix
+    int sa[3] = {0, 0, 0}, sb[3] = {1, 1, 1};
+    for (int k = 0; k < DIM; ++k) {
+        const PbAxis& A = prm.ax[k];
+        sa[k] = pb_max(A.supp_v[2 * i[k]], A.supp_u[2 * j[k]]);
+        sb[k] = pb_min(A.supp_v[2 * i[k] + 1], A.supp_u[2 * j[k] + 1]);
+        if (sa[k] >= sb[k]) return 0.0;                      // no joint support
+    }
+    const PbAxis& A0 = prm.ax[0];
+    const PbAxis& A1 = prm.ax[1];
+    const PbAxis& A2 = prm.ax[DIM - 1];
+    double r = 0.0;
+    for (int s0 = sa[0]; s0 < sb[0]; ++s0) {
+        const int av0 = i[0] - A0.first_v[s0], au0 = j[0] - A0.first_u[s0];
+        for (int q0 = 0; q0 < A0.q; ++q0) {
+            const int g0 = s0 * A0.q + q0;
+            const double* Tv0 = A0.Vv + (long long)g0 * A0.nd * (A0.pv + 1);
+            const double* Tu0 = A0.Vu + (long long)g0 * A0.nd * (A0.pu + 1);
+            const double v0[2] = {Tv0[av0], Tv0[A0.pv + 1 + av0]};
+            const double u0[2] = {Tu0[au0], Tu0[A0.pu + 1 + au0]};
+            for (int s1 = sa[1]; s1 < sb[1]; ++s1) {
+                const int av1 = i[1] - A1.first_v[s1], au1 = j[1] - A1.first_u[s1];
+                for (int q1 = 0; q1 < A1.q; ++q1) {
+                    const int g1 = s1 * A1.q + q1;
+                    const double* Tv1 = A1.Vv + (long long)g1 * A1.nd * (A1.pv + 1);
+                    const double* Tu1 = A1.Vu + (long long)g1 * A1.nd * (A1.pu + 1);
+                    const double v1[2] = {Tv1[av1], Tv1[A1.pv + 1 + av1]};
+                    const double u1[2] = {Tu1[au1], Tu1[A1.pu + 1 + au1]};
+                    if constexpr (DIM == 2) {
+                        const double vt[3] = {v0[0] * v1[0], v0[1] * v1[0], v0[0] * v1[1]};
+                        const double ut[3] = {u0[0] * u1[0], u0[1] * u1[0], u0[0] * u1[1]};
+                        const long long pt = (long long)g0 * A1.G + g1;
+                        for (int t = 0; t < prm.nterms; ++t)
+                            r += prm.fields[(long long)prm.terms[t].field * prm.npts + pt]
+                                 * vt[prm.terms[t].bt] * ut[prm.terms[t].bu];
+                    } else {
+                        for (int s2 = sa[2]; s2 < sb[2]; ++s2) {
+                            const int av2 = i[2] - A2.first_v[s2], au2 = j[2] - A2.first_u[s2];
+                            for (int q2 = 0; q2 < A2.q; ++q2) {
+                                const int g2 = s2 * A2.q + q2;
+                                const double* Tv2 = A2.Vv + (long long)g2 * A2.nd * (A2.pv + 1);
+                                const double* Tu2 = A2.Vu + (long long)g2 * A2.nd * (A2.pu + 1);
+                                const double v2[2] = {Tv2[av2], Tv2[A2.pv + 1 + av2]};
+                                const double u2[2] = {Tu2[au2], Tu2[A2.pu + 1 + au2]};
+                                const double vt[4] = {v0[0] * v1[0] * v2[0], v0[1] * v1[0] * v2[0],
+                                                      v0[0] * v1[1] * v2[0], v0[0] * v1[0] * v2[1]};
+                                const double ut[4] = {u0[0] * u1[0] * u2[0], u0[1] * u1[0] * u2[0],
+                                                      u0[0] * u1[1] * u2[0], u0[0] * u1[0] * u2[1]};
+                                const long long pt = ((long long)g0 * A1.G + g1) * A2.G + g2;
+                                for (int t = 0; t < prm.nterms; ++t)
+                                    r += prm.fields[(long long)prm.terms[t].field * prm.npts + pt]
+                                         * vt[prm.terms[t].bt] * ut[prm.terms[t].bu];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return r;
+}
+
+// entry e of the MLB slab that starts at band index mu0_begin on axis 0
+template <int DIM>
+PB_HD double pb_entry_mlb(const PbEntryParams& prm, long long mu0_begin, long long e) {
+    long long r = e;
+    int mu[3] = {0, 0, 0};
+    for (int k = DIM - 1; k >= 1; --k) { mu[k] = (int)(r % prm.ax[k].M); r /= prm.ax[k].M; }
+    mu[0] = (int)(r + mu0_begin);
+    unsigned long long I = 0, J = 0;
+    for (int k = 0; k < DIM; ++k) {
+        I = I * (unsigned long long)prm.ax[k].Nv + (unsigned long long)prm.ax[k].pair_i[mu[k]];
+        J = J * (unsigned long long)prm.ax[k].Nu + (unsigned long long)prm.ax[k].pair_j[mu[k]];
+    }
+    return pb_entry<DIM>(prm, I, J);
+}
+
+#if defined(__CUDACC__)
+template <int DIM>
+__global__ void __launch_bounds__(128) pb_entries_kernel(const __grid_constant__ PbEntryParams prm) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < prm.n; e += stride)
+        prm.out[e] = pb_entry<DIM>(prm, prm.ij[2 * e], prm.ij[2 * e + 1]);
+}
+
+// all entries of the band pattern, rows of axis 0 in [row_begin,row_end): writes the MLB slab
+template <int DIM>
+__global__ void __launch_bounds__(128) pb_entries_mlb_kernel(const __grid_constant__ PbEntryParams prm,
+                                                             long long mu0_begin, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride)
+        prm.out[e] = pb_entry_mlb<DIM>(prm, mu0_begin, e);
+}
+#endif

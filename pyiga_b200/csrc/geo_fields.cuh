@@ -1,0 +1,214 @@
+// K2 — geometry Jacobian and per-Gauss-point coefficient fields, fused.
+//
+// Replaces, in one kernel, the reference's
+//   * `BSplineFunc.grid_eval / grid_jacobian` (pyiga/bspline.py:874-921): d (+1) sparse mode
+//     products of the control net with collocation matrices via `apply_tprod`
+//     (pyiga/tensor.py:97-128),
+//   * the NURBS quotient rule `_nurbs_jacobian` (pyiga/geometry.py:17-25, 116-123),
+//   * `precompute_fields` of the assembler classes (pyiga/assemblers.pyx:1389-1449 stiffness 3D,
+//     :1223-1249 mass 3D, :234-275 / :86-110 in 2D).
+// One thread per Gauss point (lanes along the last grid axis).  The Jacobian is built from the
+// compact 1D geometry tables (values / derivatives of the p_g+1 active geometry basis functions at
+// every node) and never stored; only the fields the form needs go to HBM, in SoA layout
+//     F[c][g0][g1][g2]
+// so that the contraction kernels read them coalesced.
+//
+// Conventions (same as the reference): J[i][j] = d geo_i / d xi_j, with xi_0 the *last* tensor axis.
+#pragma once
+#include "common.cuh"
+
+struct PbGeoDev {
+    int sdim, dim;          // parameter / physical dimension
+    int nc;                 // stored components = dim (+1 if rational: premultiplied coords + weight)
+    int rational;
+    int pg[PB_MAXDIM];      // degrees of the geometry basis
+    int Ng[PB_MAXDIM];      // control net size
+    const int* gfirst[PB_MAXDIM];   // [G_k]  first active geometry function at node g_k
+    const double* GV[PB_MAXDIM];    // [G_k][2][pg_k+1]
+    const double* coeffs;           // [Ng0][Ng1][Ng2][nc]
+};
+
+struct PbFieldParams {
+    int dim;
+    int G[PB_MAXDIM];
+    const double* gw[PB_MAXDIM];    // Gauss weights per axis
+    PbGeoDev geo;
+    const double* jac_in;           // optional: Jacobians evaluated by the caller, [pts][dim][dim]
+    const double* val_in;           // optional: geometry values, [pts][dim]
+    double* fields;                 // [nf][pts]
+    long long npts;
+    int nf;
+    const double* inputs[PB_MAXFIELDS];  // user-supplied input fields on the Gauss grid, [ncomp][pts]
+    const double* consts;                // parameters of the form
+};
+
+struct PbPoint {        // what a field program sees at one Gauss point
+    double J[3][3];
+    double x[3];        // physical coordinates
+    double gw;          // product of the 1D Gauss weights
+    long long idx;      // linear point index
+};
+
+// geometry value and Jacobian at the Gauss point (g0,g1,g2)
+template <int DIM>
+PB_HD void pb_geo_eval(const PbGeoDev& geo, const int* g, PbPoint& pt) {
+    double val[4] = {0, 0, 0, 0};
+    double dv[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // dv[c][k]: derivative along tensor axis k
+    const int nc = geo.nc;
+    const int f0 = geo.gfirst[0][g[0]], f1 = geo.gfirst[1][g[1]];
+    const double* T0 = geo.GV[0] + (long long)g[0] * 2 * (geo.pg[0] + 1);
+    const double* T1 = geo.GV[1] + (long long)g[1] * 2 * (geo.pg[1] + 1);
+    if constexpr (DIM == 2) {
+        for (int a0 = 0; a0 <= geo.pg[0]; ++a0) {
+            const double w0 = T0[a0], d0 = T0[geo.pg[0] + 1 + a0];
+            double sv[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0};
+            for (int a1 = 0; a1 <= geo.pg[1]; ++a1) {
+                const double w1 = T1[a1], d1 = T1[geo.pg[1] + 1 + a1];
+                const double* c = geo.coeffs + ((long long)(f0 + a0) * geo.Ng[1] + (f1 + a1)) * nc;
+                for (int k = 0; k < nc; ++k) { sv[k] = fma(c[k], w1, sv[k]); sd[k] = fma(c[k], d1, sd[k]); }
+            }
+            for (int k = 0; k < nc; ++k) {
+                val[k] = fma(w0, sv[k], val[k]);
+                dv[k][1] = fma(w0, sd[k], dv[k][1]);
+                dv[k][0] = fma(d0, sv[k], dv[k][0]);
+            }
+        }
+    } else {
+        const int f2 = geo.gfirst[2][g[2]];
+        const double* T2 = geo.GV[2] + (long long)g[2] * 2 * (geo.pg[2] + 1);
+        for (int a0 = 0; a0 <= geo.pg[0]; ++a0) {
+            const double w0 = T0[a0], d0 = T0[geo.pg[0] + 1 + a0];
+            for (int a1 = 0; a1 <= geo.pg[1]; ++a1) {
+                const double w1 = T1[a1], d1 = T1[geo.pg[1] + 1 + a1];
+                double sv[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0};
+                const double* c = geo.coeffs + (((long long)(f0 + a0) * geo.Ng[1] + (f1 + a1)) * geo.Ng[2] + f2) * nc;
+                for (int a2 = 0; a2 <= geo.pg[2]; ++a2) {
+                    const double w2 = T2[a2], d2 = T2[geo.pg[2] + 1 + a2];
+                    for (int k = 0; k < nc; ++k) {
+                        sv[k] = fma(c[a2 * nc + k], w2, sv[k]);
+                        sd[k] = fma(c[a2 * nc + k], d2, sd[k]);
+                    }
+                }
+                const double w01 = w0 * w1, w0d1 = w0 * d1, d0w1 = d0 * w1;
+                for (int k = 0; k < nc; ++k) {
+                    val[k] = fma(w01, sv[k], val[k]);
+                    dv[k][2] = fma(w01, sd[k], dv[k][2]);
+                    dv[k][1] = fma(w0d1, sv[k], dv[k][1]);
+                    dv[k][0] = fma(d0w1, sv[k], dv[k][0]);
+                }
+            }
+        }
+    }
+    // J[i][j], j = DIM-1-k  (x is the last tensor axis)
+    if (geo.rational) {
+        const double W = val[geo.dim];
+        const double iW2 = 1.0 / (W * W);
+        for (int i = 0; i < geo.dim; ++i) {
+            pt.x[i] = val[i] / W;
+            for (int k = 0; k < DIM; ++k)
+                pt.J[i][DIM - 1 - k] = (dv[i][k] * W - val[i] * dv[geo.dim][k]) * iW2;
+        }
+    } else {
+        for (int i = 0; i < geo.dim; ++i) {
+            pt.x[i] = val[i];
+            for (int k = 0; k < DIM; ++k) pt.J[i][DIM - 1 - k] = dv[i][k];
+        }
+    }
+}
+
+// ---- field programs ---------------------------------------------------------------------------
+template <int DIM> PB_HD double pb_det(const double (&J)[3][3]) {
+    if constexpr (DIM == 2) return J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    else return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1])
+              - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+              + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+}
+
+// inverse by cofactors, like the generated reference code (pyiga/assemblers.pyx:1430-1441)
+template <int DIM> PB_HD void pb_inv(const double (&J)[3][3], double det, double (&I)[3][3]) {
+    const double t = 1.0 / det;
+    if constexpr (DIM == 2) {
+        I[0][0] = t * J[1][1];  I[0][1] = -t * J[0][1];
+        I[1][0] = -t * J[1][0]; I[1][1] = t * J[0][0];
+    } else {
+        I[0][0] = t * (J[1][1] * J[2][2] - J[1][2] * J[2][1]);
+        I[0][1] = -t * (J[0][1] * J[2][2] - J[0][2] * J[2][1]);
+        I[0][2] = t * (J[0][1] * J[1][2] - J[0][2] * J[1][1]);
+        I[1][0] = -t * (J[1][0] * J[2][2] - J[1][2] * J[2][0]);
+        I[1][1] = t * (J[0][0] * J[2][2] - J[0][2] * J[2][0]);
+        I[1][2] = -t * (J[0][0] * J[1][2] - J[0][2] * J[1][0]);
+        I[2][0] = t * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        I[2][1] = -t * (J[0][0] * J[2][1] - J[0][1] * J[2][0]);
+        I[2][2] = t * (J[0][0] * J[1][1] - J[0][1] * J[1][0]);
+    }
+}
+
+// mass: W = GaussWeight * |det J|                      (pyiga/assemblers.pyx:1223-1249)
+template <int DIM> struct PbProgMass {
+    static constexpr int NF = 1;
+    static constexpr bool NEED_X = false;
+    PB_HD static void run(const PbFieldParams&, const PbPoint& pt, double* f) {
+        f[0] = pt.gw * fabs(pb_det<DIM>(pt.J));
+    }
+};
+
+// stiffness: B = W * J^-1 J^-T, symmetric-packed upper triangle, x,y,z index order
+//                                                      (pyiga/assemblers.pyx:1389-1449, vform.py:28-34)
+template <int DIM> struct PbProgStiffness {
+    static constexpr int NF = DIM * (DIM + 1) / 2;
+    static constexpr bool NEED_X = false;
+    PB_HD static void run(const PbFieldParams&, const PbPoint& pt, double* f) {
+        const double det = pb_det<DIM>(pt.J);
+        const double W = pt.gw * fabs(det);
+        double I[3][3];
+        pb_inv<DIM>(pt.J, det, I);
+        int k = 0;
+        for (int a = 0; a < DIM; ++a)
+            for (int b = a; b < DIM; ++b) {
+                double s = 0.0;
+                for (int m = 0; m < DIM; ++m) s += I[a][m] * I[b][m];
+                f[k++] = W * s;
+            }
+    }
+};
+
+// raw geometry data (debug / host callbacks): J row-major (DIM*DIM), then x (DIM)
+template <int DIM> struct PbProgGeoRaw {
+    static constexpr int NF = DIM * DIM + DIM;
+    static constexpr bool NEED_X = true;
+    PB_HD static void run(const PbFieldParams&, const PbPoint& pt, double* f) {
+        for (int i = 0; i < DIM; ++i)
+            for (int j = 0; j < DIM; ++j) f[i * DIM + j] = pt.J[i][j];
+        for (int i = 0; i < DIM; ++i) f[DIM * DIM + i] = pt.x[i];
+    }
+};
+
+template <int DIM, class Prog>
+PB_HD void pb_fields_point(const PbFieldParams& prm, long long idx) {
+    int g[3];
+    long long r = idx;
+    for (int k = DIM - 1; k >= 0; --k) { g[k] = (int)(r % prm.G[k]); r /= prm.G[k]; }
+    PbPoint pt;
+    pt.idx = idx;
+    pt.gw = 1.0;
+    for (int k = 0; k < DIM; ++k) pt.gw *= prm.gw[k][g[k]];
+    if (prm.jac_in) {
+        for (int i = 0; i < DIM; ++i)
+            for (int j = 0; j < DIM; ++j) pt.J[i][j] = prm.jac_in[(idx * DIM + i) * DIM + j];
+        for (int i = 0; i < DIM; ++i) pt.x[i] = prm.val_in ? prm.val_in[idx * DIM + i] : 0.0;
+    } else {
+        pb_geo_eval<DIM>(prm.geo, g, pt);
+    }
+    double f[Prog::NF];
+    Prog::run(prm, pt, f);
+    for (int c = 0; c < Prog::NF; ++c) prm.fields[(long long)c * prm.npts + idx] = f[c];
+}
+
+#if defined(__CUDACC__)
+template <int DIM, class Prog>
+__global__ void __launch_bounds__(256) pb_fields_kernel(const __grid_constant__ PbFieldParams prm) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < prm.npts; idx += stride)
+        pb_fields_point<DIM, Prog>(prm, idx);
+}
+#endif

@@ -1,0 +1,330 @@
+// Sum-factorised banded contraction along one tensor axis ("walk" stage).
+//
+// This is the core of the B200 assembly path.  The reference computes every matrix entry by a
+// full d-dimensional quadrature loop (pyiga/assemblers.pyx:1455-1540 `combine` + `entry_impl`,
+// driven by pyiga/genericasm.pxi:691-758).  Here the same sums are evaluated by *pairwise sum
+// factorisation*: the d-dimensional sum is split into d one-dimensional contractions, and each
+// contraction turns a Gauss-node axis (length n*q) into a band axis (the list of function pairs
+// (i,j) with joint support on that axis, in the order of `compute_sparsity_ij`,
+// pyiga/mlmatrix.py:420-440).
+//
+// One thread owns one "line" (all other indices fixed) and walks along the node axis span by span.
+// On span s exactly the p+1 consecutive functions first[s] .. first[s]+p are active, so the thread
+// keeps a (p+1)x(p+1) register window acc[a][b] of partial sums for the pairs
+// (f+a, f+b), f = window base.  Per node it performs a rank-1 style update
+//     acc[a][b] += D_ft[a] * D_fu[b] * x          (D_0 = values, D_1 = first derivatives)
+// factored as y[b] = D_fu[b]*x ; acc[a][b] += D_ft[a]*y[b]  (or the mirrored grouping), which needs
+// only 2(p+1) table values per node; those are warp-uniform and come from shared memory (staged by
+// a TMA bulk copy).  When the window base moves on, the pairs that lose their last span are
+// complete and are written out ("retired").
+//
+// Lanes of a warp own neighbouring lines, so the loads of x and the stores of retired entries are
+// coalesced whenever the walk axis is not the fastest one in memory.
+#pragma once
+#include "common.cuh"
+
+struct PbOp {       // acc[out] += D_ft (x) D_fu * in
+    int in;         // input term
+    int tr;         // read the input at the transposed (u, v) line
+    int ft;         // derivative order of the test function on this axis (0/1)
+    int fu;         // derivative order of the trial function on this axis (0/1)
+    int out;        // output term
+};
+
+#define PB_WALK_MAXOPS 8
+#define PB_WALK_MAXOUT 4
+
+struct PbWalkParams {
+    // ---- thread grid: tid -> (u, v, x),  x fastest -------------------------------------------
+    long long nthreads;
+    int X, V;
+    int u_begin;                    // absolute index of the first u line
+    int u_base_in, u_base_out;      // absolute u that sits in slot 0 of the in / out buffers
+    const int* tr_u;                // transposed-pair tables for the u / v coordinates (or null)
+    const int* tr_v;
+    const int* u_pair_i;            // (i,j) of band entry u, for the slab filter (or null)
+    const int* u_pair_j;
+    int u_mode, u_lo, u_hi;         // 0: all u;  1: keep i in [lo,hi);  2: keep i or j in [lo,hi)
+    // ---- input / output terms ---------------------------------------------------------------
+    const double* in[PB_WALK_MAXOPS];   // per op: base pointer of its input term
+    long long in_su, in_sv, in_sx, in_sc;   // strides (doubles) of u, v, x and of the node index
+    double* out[PB_WALK_MAXOUT];
+    long long out_su, out_sv, out_sx, out_smu;
+    int mu_base;                    // band index stored in slot 0 of the output band axis
+    // ---- walk axis ---------------------------------------------------------------------------
+    int s_begin, s_end;             // spans walked
+    int N;                          // number of functions on the axis
+    const int* first;               // [n]
+    const double* V2;               // [G][2][P+1]
+    const int* ret_mu;              // [N][2P+1]
+    int w_mode, w_lo, w_hi;         // retire filter on the walk-axis pair (i,j), as u_mode
+};
+
+template <int I> struct PbIC { static constexpr int value = I; };
+
+template <int B, int E, class F>
+PB_HD void pb_static_for(F&& f) {
+    if constexpr (B < E) {
+        f(PbIC<B>{});
+        pb_static_for<B + 1, E>(f);
+    }
+}
+
+// compile-time queries on a plan
+template <class Plan> constexpr int pb_count_ft(int out, int ft) {
+    int c = 0;
+    for (int i = 0; i < Plan::NOPS; ++i) c += (Plan::op(i).out == out && Plan::op(i).ft == ft) ? 1 : 0;
+    return c;
+}
+template <class Plan> constexpr int pb_count_fu(int out, int fu) {
+    int c = 0;
+    for (int i = 0; i < Plan::NOPS; ++i) c += (Plan::op(i).out == out && Plan::op(i).fu == fu) ? 1 : 0;
+    return c;
+}
+// first op of the group (out, flag) under the chosen grouping
+template <class Plan> constexpr int pb_first_in_group(int out, int fl, bool by_fu) {
+    for (int i = 0; i < Plan::NOPS; ++i)
+        if (Plan::op(i).out == out && (by_fu ? Plan::op(i).fu : Plan::op(i).ft) == fl) return i;
+    return -1;
+}
+// group the ops of an output by the trial flag when that gives fewer rank-1 updates
+template <class Plan> constexpr bool pb_group_by_fu(int out) {
+    int nft = (pb_count_ft<Plan>(out, 0) > 0) + (pb_count_ft<Plan>(out, 1) > 0);
+    int nfu = (pb_count_fu<Plan>(out, 0) > 0) + (pb_count_fu<Plan>(out, 1) > 0);
+    return nfu < nft;
+}
+
+// The body executed by one thread.  `Vt` points at the [G][2][P+1] table (shared or global).
+template <class Plan, int P, int Q>
+PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt) {
+    constexpr int P1 = P + 1;
+    constexpr int NOPS = Plan::NOPS, NOUT = Plan::NOUT;
+
+    // ---- decode the line ------------------------------------------------------------------
+    const int x = (int)(tid % prm.X);
+    const long long t2 = tid / prm.X;
+    const int v = (int)(t2 % prm.V);
+    const int u = (int)(t2 / prm.V) + prm.u_begin;
+    if (prm.u_mode != 0) {
+        const int ui = prm.u_pair_i[u], uj = prm.u_pair_j[u];
+        const bool ki = (ui >= prm.u_lo && ui < prm.u_hi);
+        const bool kj = (uj >= prm.u_lo && uj < prm.u_hi);
+        if (!(ki || (prm.u_mode == 2 && kj))) return;
+    }
+    const long long off_in = (long long)(u - prm.u_base_in) * prm.in_su + (long long)v * prm.in_sv
+                             + (long long)x * prm.in_sx;
+    long long off_in_tr = off_in;
+    if (Plan::HAS_TR) {
+        const int ut = prm.tr_u ? prm.tr_u[u] : u;
+        const int vt = prm.tr_v ? prm.tr_v[v] : v;
+        off_in_tr = (long long)(ut - prm.u_base_in) * prm.in_su + (long long)vt * prm.in_sv
+                    + (long long)x * prm.in_sx;
+    }
+    const long long off_out = (long long)(u - prm.u_base_out) * prm.out_su + (long long)v * prm.out_sv
+                              + (long long)x * prm.out_sx;
+
+    const double* src[NOPS];
+    pb_static_for<0, NOPS>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        src[i] = prm.in[i] + (Plan::op(i).tr ? off_in_tr : off_in);
+    });
+
+    double acc[NOUT][P1][P1];
+    pb_static_for<0, NOUT>([&](auto O) {
+        constexpr int o = decltype(O)::value;
+#pragma unroll
+        for (int a = 0; a < P1; ++a)
+#pragma unroll
+            for (int b = 0; b < P1; ++b) acc[o][a][b] = 0.0;
+    });
+
+    // retire the pairs that involve function f (first row / first column of the window), then
+    // slide the window down by one function
+    auto retire_shift = [&](int f) {
+        const int* rm = prm.ret_mu + (long long)f * (2 * P + 1);
+#pragma unroll
+        for (int k = 0; k <= 2 * P; ++k) {
+            const int mu = rm[k];
+            const int a = (k <= P) ? 0 : (k - P);
+            const int b = (k <= P) ? k : 0;
+            bool keep = (mu >= 0);
+            if (prm.w_mode != 0) {
+                const int i = f + a, j = f + b;
+                const bool ki = (i >= prm.w_lo && i < prm.w_hi);
+                const bool kj = (j >= prm.w_lo && j < prm.w_hi);
+                keep = keep && (ki || (prm.w_mode == 2 && kj));
+            }
+            if (keep) {
+                const long long o_off = off_out + (long long)(mu - prm.mu_base) * prm.out_smu;
+                pb_static_for<0, NOUT>([&](auto O) {
+                    constexpr int o = decltype(O)::value;
+                    prm.out[o][o_off] = acc[o][a][b];
+                });
+            }
+        }
+        pb_static_for<0, NOUT>([&](auto O) {
+            constexpr int o = decltype(O)::value;
+#pragma unroll
+            for (int a = 0; a < P; ++a)
+#pragma unroll
+                for (int b = 0; b < P; ++b) acc[o][a][b] = acc[o][a + 1][b + 1];
+#pragma unroll
+            for (int a = 0; a < P1; ++a) {
+                acc[o][a][P] = 0.0;
+                acc[o][P][a] = 0.0;
+            }
+        });
+    };
+
+    int f = prm.first[prm.s_begin];
+    double xq[Q][NOPS];         // inputs of the current span (loaded one span ahead of use)
+#pragma unroll
+    for (int gq = 0; gq < Q; ++gq)
+        pb_static_for<0, NOPS>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            xq[gq][i] = src[i][(long long)(prm.s_begin * Q + gq) * prm.in_sc];
+        });
+
+    for (int s = prm.s_begin; s < prm.s_end; ++s) {
+        const int fs = prm.first[s];
+        while (f < fs) { retire_shift(f); ++f; }
+
+        double xc[Q][NOPS];
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+            pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; xc[gq][i] = xq[gq][i]; });
+        if (s + 1 < prm.s_end) {
+#pragma unroll
+            for (int gq = 0; gq < Q; ++gq)
+                pb_static_for<0, NOPS>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    xq[gq][i] = src[i][(long long)((s + 1) * Q + gq) * prm.in_sc];
+                });
+        }
+
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq) {
+            const double* Vn = Vt + (long long)(s * Q + gq) * (2 * P1);
+            double D[2][P1];
+#pragma unroll
+            for (int a = 0; a < P1; ++a) { D[0][a] = Vn[a]; D[1][a] = Vn[P1 + a]; }
+
+            pb_static_for<0, NOUT>([&](auto O) {
+                constexpr int o = decltype(O)::value;
+                constexpr bool by_fu = pb_group_by_fu<Plan>(o);
+                pb_static_for<0, 2>([&](auto FL) {
+                    constexpr int fl = decltype(FL)::value;     // the flag shared by the group
+                    constexpr int cnt = by_fu ? pb_count_fu<Plan>(o, fl) : pb_count_ft<Plan>(o, fl);
+                    if constexpr (cnt > 0) {
+                        // y[c] = sum over the group's ops of D_other[c] * x
+                        double y[P1];
+                        constexpr int lead = pb_first_in_group<Plan>(o, fl, by_fu);
+                        pb_static_for<0, NOPS>([&](auto I) {
+                            constexpr int i = decltype(I)::value;
+                            constexpr PbOp op = Plan::op(i);
+                            if constexpr (op.out == o && (by_fu ? op.fu : op.ft) == fl) {
+                                constexpr int other = by_fu ? op.ft : op.fu;
+                                const double xv = xc[gq][i];
+                                if constexpr (i == lead) {
+#pragma unroll
+                                    for (int c = 0; c < P1; ++c) y[c] = D[other][c] * xv;
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < P1; ++c) y[c] = fma(D[other][c], xv, y[c]);
+                                }
+                            }
+                        });
+                        if constexpr (by_fu) {   // y indexed by the test function a
+#pragma unroll
+                            for (int a = 0; a < P1; ++a)
+#pragma unroll
+                                for (int b = 0; b < P1; ++b) acc[o][a][b] = fma(y[a], D[fl][b], acc[o][a][b]);
+                        } else {                 // y indexed by the trial function b
+#pragma unroll
+                            for (int a = 0; a < P1; ++a)
+#pragma unroll
+                                for (int b = 0; b < P1; ++b) acc[o][a][b] = fma(D[fl][a], y[b], acc[o][a][b]);
+                        }
+                    }
+                });
+            });
+        }
+    }
+    // flush: everything still in the window is complete now
+#pragma unroll 1
+    for (int k = 0; k < P1; ++k) {
+        if (f < prm.N) retire_shift(f);
+        ++f;
+    }
+}
+
+#if defined(__CUDACC__)
+// ---- TMA bulk copy of the 1D basis table into shared memory ---------------------------------
+PB_D uint32_t pb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+PB_D void pb_tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    // one elected thread: arm the barrier with the byte count and launch the bulk copy
+    const uint32_t b = pb_smem_u32(bar), d = pb_smem_u32(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+        "l"(gsrc), "r"(bytes), "r"(b)
+        : "memory");
+}
+PB_D void pb_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pb_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PB_D void pb_mbar_wait(uint64_t* bar, uint32_t phase) {
+    const uint32_t b = pb_smem_u32(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(b),
+        "r"(phase)
+        : "memory");
+}
+
+// Generic stage kernel.  Dynamic shared memory holds the walk-axis table slice
+// [s_begin*Q, s_end*Q) x 2 x (P+1) doubles when `use_smem` is set; otherwise the table is read
+// through the read-only path from global memory (axes too long for 227 KB).
+template <class Plan, int P, int Q, int MINB>
+__global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constant__ PbWalkParams prm, int use_smem) {
+    extern __shared__ __align__(128) unsigned char pb_smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const double* Vt = prm.V2;
+    if (use_smem) {
+        double* sV = reinterpret_cast<double*>(pb_smem_raw);
+        const long long first_node = (long long)prm.s_begin * Q;
+        const uint32_t bytes = (uint32_t)((long long)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double));
+        if (threadIdx.x == 0) {
+            pb_mbar_init(&bar, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // bulk copies are limited in size; issue in 32 KB pieces on the same barrier
+            const char* g = reinterpret_cast<const char*>(prm.V2 + first_node * 2 * (P + 1));
+            char* d = reinterpret_cast<char*>(sV);
+            uint32_t done = 0;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pb_smem_u32(&bar)), "r"(bytes)
+                         : "memory");
+            while (done < bytes) {
+                const uint32_t piece = (bytes - done) < 32768u ? (bytes - done) : 32768u;
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        pb_smem_u32(d + done)),
+                    "l"(g + done), "r"(piece), "r"(pb_smem_u32(&bar))
+                    : "memory");
+                done += piece;
+            }
+        }
+        pb_mbar_wait(&bar, 0);
+        Vt = sV - first_node * 2 * (P + 1);     // so that Vt[(s*Q+gq)*2*(P+1)] addresses the slice
+    }
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < prm.nthreads) pb_walk_line<Plan, P, Q>(prm, tid, Vt);
+}
+#endif

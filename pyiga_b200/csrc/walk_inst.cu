@@ -1,0 +1,45 @@
+// Instantiates the walk kernels of the built-in plans for one (degree, nodes-per-span) pair.
+// Compiled once per pair with -DPB_P=<p> -DPB_Q=<q>; each object registers its launchers.
+#include "backend.cuh"
+#include "plans.cuh"
+
+#ifndef PB_P
+#error "compile with -DPB_P=<degree> -DPB_Q=<nodes per span>"
+#endif
+
+namespace {
+
+template <class Plan>
+int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* stream) {
+#ifdef PB_EMULATE
+    (void)use_smem; (void)smem_bytes; (void)stream;
+    pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q>(*prm, tid, prm->V2); });
+    return 0;
+#else
+    auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, Plan::MINB>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const long long blocks = (prm->nthreads + 127) / 128;
+    if (blocks <= 0) return 0;
+    kern<<<(unsigned)blocks, 128, smem_bytes, (cudaStream_t)stream>>>(*prm, use_smem);
+    return (int)cudaGetLastError();
+#endif
+}
+
+struct Registrar {
+    Registrar() {
+        pb200_register_walk(PB_PLAN_COPY, PB_P, PB_Q, &launch<PbPlanCopy>);
+        pb200_register_walk(PB_PLAN_FINAL4, PB_P, PB_Q, &launch<PbPlanFinal4>);
+        pb200_register_walk(PB_PLAN_S1A, PB_P, PB_Q, &launch<PbPlanS1A>);
+        pb200_register_walk(PB_PLAN_S1B, PB_P, PB_Q, &launch<PbPlanS1B>);
+        pb200_register_walk(PB_PLAN_S2B, PB_P, PB_Q, &launch<PbPlanS2B>);
+        pb200_register_walk(PB_PLAN_S1_2D, PB_P, PB_Q, &launch<PbPlanS1_2D>);
+    }
+};
+Registrar registrar;
+
+}  // namespace

@@ -1,0 +1,150 @@
+"""Generates the committed golden fixtures from the REAL reference (c-f-h/pyiga).
+
+Run in the build container, where the reference is installed under oracle/_ref (see
+oracle/build_ref.py) and its test data lives under /root/reference/test:
+
+    python tests/golden/make_golden.py
+
+Outputs (all under tests/golden/):
+    pyiga_<name>.npz    the reference's own golden matrices test/poisson_neu_*.mtx.gz
+                        (test/test_assemble.py:138-168), re-encoded as CSR arrays
+    ref_cases.npz       inputs + outputs of the reference run on small cases: basis tables,
+                        Jacobians, band structures, mass/stiffness matrices, multi_entries samples,
+                        MLMatrix matvec, Kronecker matvec
+The GPU box has no /root/reference; tests only read these files.
+"""
+import gzip
+import os
+import sys
+
+import numpy as np
+import scipy.sparse
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'oracle', '_ref'))
+
+from pyiga import assemble, assemblers, bspline, geometry, mlmatrix, operators  # noqa: E402
+
+REFTEST = '/root/reference/test'
+
+
+def read_mtx(path):
+    with gzip.open(path, 'rt') as f:
+        m, n, nnz = (int(t) for t in f.readline().split())
+        raw = np.loadtxt(f)
+    A = scipy.sparse.coo_matrix((raw[:, 2], (raw[:, 0].astype(int) - 1, raw[:, 1].astype(int) - 1)), shape=(m, n))
+    return A.tocsr()
+
+
+def save_csr(name, A):
+    A = A.tocsr()
+    A.sort_indices()
+    np.savez_compressed(os.path.join(HERE, name), data=A.data, indices=A.indices.astype(np.int32),
+                        indptr=A.indptr.astype(np.int32), shape=np.array(A.shape))
+
+
+def geo_pack(prefix, geo, out):
+    out[prefix + '_rational'] = np.array(int(isinstance(geo, geometry.NurbsFunc)))
+    out[prefix + '_coeffs'] = np.asarray(geo.coeffs, dtype=float)
+    for k, kv in enumerate(geo.kvs):
+        out['%s_kv%d' % (prefix, k)] = kv.kv
+        out['%s_p%d' % (prefix, k)] = np.array(kv.p)
+    out[prefix + '_sdim'] = np.array(geo.sdim)
+
+
+def twisted_nurbs_box():
+    G = geometry.twisted_box()
+    i, j, k = np.meshgrid(np.arange(2), np.arange(4), np.arange(2), indexing='ij')
+    W = 1.0 + 0.25 * ((i + 2 * j + 3 * k) % 3)
+    return geometry.NurbsFunc(G.kvs, G.coeffs.copy(), W)
+
+
+def main():
+    # ---- 1. the reference's golden matrices ----------------------------------------------------
+    for name in ('d2_p3_n15_mass', 'd2_p3_n15_stiff', 'd3_p2_n10_mass', 'd3_p2_n10_stiff'):
+        save_csr('pyiga_%s.npz' % name, read_mtx(os.path.join(REFTEST, 'poisson_neu_%s.mtx.gz' % name)))
+
+    out = {}
+    # ---- 2. basis functions ----------------------------------------------------------------------
+    kv = bspline.make_knots(3, 0.0, 1.0, 5, mult=2)
+    nodes = np.concatenate((np.linspace(0, 1, 23), kv.mesh))
+    idx, vals = bspline.collocation_derivs_info(kv, nodes, derivs=2)
+    out['basis_kv'], out['basis_p'], out['basis_nodes'] = kv.kv, np.array(3), nodes
+    out['basis_first'], out['basis_vals'] = np.asarray(idx), np.asarray(vals)      # (derivs+1, n, p+1)
+
+    # ---- 3. geometry Jacobians ------------------------------------------------------------------
+    geos = {'tb': geometry.twisted_box(), 'tnb': twisted_nurbs_box(), 'qa': geometry.quarter_annulus(),
+            'bqa': geometry.bspline_quarter_annulus(),
+            'cyl': geometry.tensor_product(geometry.line_segment(0, 1), geometry.quarter_annulus())}
+    for name, geo in geos.items():
+        grid = tuple(np.linspace(0.03, 0.98, 4 + k) for k in range(geo.sdim))
+        geo_pack('geo_' + name, geo, out)
+        for k, g in enumerate(grid):
+            out['geo_%s_grid%d' % (name, k)] = g
+        out['geo_%s_val' % name] = geo.grid_eval(grid)
+        out['geo_%s_jac' % name] = geo.grid_jacobian(grid)
+
+    # ---- 4. assembled matrices --------------------------------------------------------------------
+    def space(ps, ns, mult=1):
+        return tuple(bspline.make_knots(p, 0.0, 1.0, n, mult=mult) for p, n in zip(ps, ns))
+
+    cases = {
+        'a2_qa': (space((2, 2), (4, 5)), geos['qa']),
+        'a2_mixed': (space((4, 3), (4, 5)), geos['bqa']),
+        'a3_tb': (space((2, 2, 2), (3, 4, 3)), geos['tb']),
+        'a3_mixed': (space((2, 3, 2), (4, 3, 3)), geos['tb']),
+        'a3_nurbs': (space((3, 3, 3), (4, 4, 4)), geos['tnb']),
+        'a3_mult': (space((2, 2, 2), (3, 3, 3), mult=2), geos['cyl']),
+        'a3_p1': (space((1, 1, 1), (4, 3, 5)), geos['tb']),
+        'a3_p4': (space((4, 4, 4), (2, 3, 2)), geos['tnb']),
+    }
+    rng = np.random.default_rng(1234)
+    for name, (kvs, geo) in cases.items():
+        out[name + '_geo'] = np.array([k for k, g in geos.items() if g is geo][0])
+        for k, kv in enumerate(kvs):
+            out['%s_kv%d' % (name, k)] = kv.kv
+            out['%s_p%d' % (name, k)] = np.array(kv.p)
+        out[name + '_dim'] = np.array(len(kvs))
+        S = mlmatrix.MLStructure.from_kvs(kvs, kvs)
+        for k in range(S.L):
+            out['%s_bidx%d' % (name, k)] = S.bidx[k]
+        for form, fn in (('mass', assemble.mass), ('stiff', assemble.stiffness)):
+            A = fn(kvs, geo).tocsr()
+            A.sort_indices()
+            I, J = S.nonzero()
+            data = np.asarray(A[I.astype(np.int64), J.astype(np.int64)]).ravel()
+            out['%s_%s_mlb' % (name, form)] = data.reshape([len(b) for b in S.bidx])
+            out['%s_%s_indptr' % (name, form)] = A.indptr
+            out['%s_%s_indices' % (name, form)] = A.indices
+        # multi_entries protocol: random pairs, many outside the pattern
+        cls = {2: assemblers.StiffnessAssembler2D, 3: assemblers.StiffnessAssembler3D}[len(kvs)]
+        asm = cls(kvs, geo)
+        n = S.shape[0]
+        ij = np.column_stack((rng.integers(0, n, 200), rng.integers(0, n, 200)))
+        I, J = S.nonzero()
+        pick = rng.integers(0, len(I), 200)
+        ij = np.vstack((ij, np.column_stack((I[pick], J[pick])))).astype(np.uint64)
+        out[name + '_me_ij'] = ij
+        out[name + '_me_val'] = asm.multi_entries(ij)
+
+    # ---- 5. MLMatrix matvec and Kronecker operator ----------------------------------------------
+    kvs, geo = cases['a3_mixed']
+    S = mlmatrix.MLStructure.from_kvs(kvs, kvs)
+    X = rng.standard_normal([len(b) for b in S.bidx])
+    x = rng.standard_normal(S.shape[1])
+    out['mv_data'], out['mv_x'] = X, x
+    out['mv_y'] = mlmatrix.MLMatrix(S, data=X).dot(x)
+    facs = [rng.standard_normal((3, 4)), rng.standard_normal((5, 2)), rng.standard_normal((4, 6))]
+    xk = rng.standard_normal(4 * 2 * 6)
+    for k, A in enumerate(facs):
+        out['kron_A%d' % k] = A
+    out['kron_x'] = xk
+    out['kron_y'] = operators.KroneckerOperator(*facs).dot(xk)
+
+    np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
+    print('wrote', len(out), 'arrays')
+
+
+if __name__ == '__main__':
+    main()

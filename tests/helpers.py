@@ -1,0 +1,63 @@
+"""Shared helpers of the parity tests."""
+import os
+
+import numpy as np
+import scipy.sparse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+CASES = ['a2_qa', 'a2_mixed', 'a3_tb', 'a3_mixed', 'a3_nurbs', 'a3_mult', 'a3_p1', 'a3_p4']
+GEOS = ['tb', 'tnb', 'qa', 'bqa', 'cyl']
+RTOL = 1e-12        # north-star tolerance: relative to the max-abs entry of the reference matrix
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, 'pyiga_%s.npz' % name))
+    return scipy.sparse.csr_matrix((z['data'], z['indices'], z['indptr']), shape=tuple(z['shape']))
+
+
+def geo_arrays(ref, name):
+    sdim = int(ref['geo_%s_sdim' % name])
+    kvs = [ref['geo_%s_kv%d' % (name, k)] for k in range(sdim)]
+    ps = [int(ref['geo_%s_p%d' % (name, k)]) for k in range(sdim)]
+    return kvs, ps, ref['geo_%s_coeffs' % name], bool(ref['geo_%s_rational' % name])
+
+
+def make_geo(ref, name):
+    """pyiga_b200 geometry object from the packed fixture arrays."""
+    from pyiga_b200 import bspline, geometry
+    kvs, ps, coeffs, rational = geo_arrays(ref, name)
+    kvs = tuple(bspline.KnotVector(kv, p) for kv, p in zip(kvs, ps))
+    if rational:
+        return geometry.NurbsFunc(kvs, coeffs.copy(), None, premultiplied=True)
+    return bspline.BSplineFunc(kvs, coeffs.copy())
+
+
+def case_space(ref, case):
+    dim = int(ref[case + '_dim'])
+    kvs = [ref['%s_kv%d' % (case, k)] for k in range(dim)]
+    ps = [int(ref['%s_p%d' % (case, k)]) for k in range(dim)]
+    return kvs, ps
+
+
+def make_space(ref, case):
+    from pyiga_b200 import bspline
+    kvs, ps = case_space(ref, case)
+    return tuple(bspline.KnotVector(kv, p) for kv, p in zip(kvs, ps))
+
+
+def ref_csr(ref, case, form):
+    mlb = ref['%s_%s_mlb' % (case, form)]
+    indptr, indices = ref['%s_%s_indptr' % (case, form)], ref['%s_%s_indices' % (case, form)]
+    n = len(indptr) - 1
+    # CSR values in canonical order = MLB values permuted; rebuild through the index lists
+    return indptr, indices, mlb
+
+
+def assert_close_rel(got, want, rtol=RTOL, what=''):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, '%s: shape %s != %s' % (what, got.shape, want.shape)
+    scale = np.abs(want).max()
+    err = np.abs(got - want).max()
+    assert err <= rtol * scale, '%s: max abs error %.3e > %.1e * max|ref| (%.3e)' % (what, err, rtol, scale)

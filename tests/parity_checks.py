@@ -1,0 +1,165 @@
+"""Parity checks of the pyiga_b200 path against reference fixtures, goldens and the oracle.
+
+The same functions are run twice: through the sequential host emulation of the kernels
+(tests/test_emulated.py, CPU) and through the CUDA library on the B200 (tests/test_gpu_parity.py).
+Tolerance: the north-star's 1e-12 relative to the max-abs entry of the reference matrix; index
+arrays bit-exact.
+"""
+import ctypes as C
+
+import numpy as np
+
+from helpers import RTOL, assert_close_rel, case_space, geo_arrays, load_golden, make_geo, make_space
+from oracle import pyiga_oracle as orc
+
+
+def check_basis(be, ref):
+    """K1 against bspline.collocation_derivs_info of the reference."""
+    kv, p, nodes = ref['basis_kv'], int(ref['basis_p']), ref['basis_nodes']
+    d_kv, d_nodes = be.from_host(kv), be.from_host(nodes)
+    m = len(nodes)
+    first = be.empty(m, np.int32)
+    vals = be.empty(m * 3 * (p + 1))
+    from pyiga_b200 import _device
+    _device.check(be.lib.pb200_basis_eval(be.ptr(d_kv), len(kv), p, be.ptr(d_nodes), m, 2, be.ptr(first),
+                                           be.ptr(vals), be.stream()))
+    be.synchronize()
+    assert np.array_equal(be.to_host(first), ref['basis_first'])
+    got = be.to_host(vals).reshape(m, 3, p + 1).transpose(1, 0, 2)      # -> (deriv, node, fn)
+    np.testing.assert_allclose(got, ref['basis_vals'], rtol=0, atol=1e-12 * np.abs(ref['basis_vals']).max())
+
+
+def check_geometry(ref, name):
+    """K2's geometry evaluation against grid_eval / grid_jacobian of the reference."""
+    geo = make_geo(ref, name)
+    grid = tuple(ref['geo_%s_grid%d' % (name, k)] for k in range(geo.sdim))
+    np.testing.assert_allclose(geo.grid_eval(grid), ref['geo_%s_val' % name], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(geo.grid_jacobian(grid), ref['geo_%s_jac' % name], rtol=0, atol=1e-13)
+
+
+def check_fields(ref, case, form):
+    """K2's coefficient fields against the oracle's restatement of precompute_fields."""
+    from pyiga_b200 import assemblers
+    kvs = make_space(ref, case)
+    geo = make_geo(ref, str(ref[case + '_geo']))
+    cls = getattr(assemblers, ('Mass' if form == 'mass' else 'Stiffness') + 'Assembler%dD' % len(kvs))
+    asm = cls(kvs, geo)
+    okvs, ops = case_space(ref, case)
+    gk, gp, gc, rational = geo_arrays(ref, str(ref[case + '_geo']))
+    prob = orc.Problem(okvs, ops, gk, gp, gc, rational)
+    want = (orc.fields_mass if form == 'mass' else orc.fields_stiffness)(prob.jac, prob.gw)
+    got = np.moveaxis(asm.dev.fields_host(), 0, -1)
+    assert_close_rel(got, want, what='fields %s %s' % (case, form))
+
+
+def check_case(ref, case, entrywise=False, rows=None):
+    """mass + stiffness of a fixture case: band structure, MLB values, CSR arrays."""
+    from pyiga_b200 import assemblers
+    from pyiga_b200.mlmatrix import MLStructure
+    kvs = make_space(ref, case)
+    dim = len(kvs)
+    geo = make_geo(ref, str(ref[case + '_geo']))
+    S = MLStructure.from_kvs(kvs, kvs)
+    for k in range(dim):
+        assert S.bidx[k].dtype == np.uint32
+        assert np.array_equal(S.bidx[k], ref['%s_bidx%d' % (case, k)])
+    for form, key in (('Mass', 'mass'), ('Stiffness', 'stiff')):
+        asm = getattr(assemblers, '%sAssembler%dD' % (form, dim))(kvs, geo)
+        for k in range(dim):    # the C library's structure must agree with the host one
+            assert np.array_equal(asm.dev.bidx(k), S.bidx[k])
+        want = ref['%s_%s_mlb' % (case, key)]
+        data = asm.dev.be.to_host(asm.dev.assemble_mlb(entrywise=entrywise)).reshape(want.shape)
+        assert_close_rel(data, want, what='%s %s mlb' % (case, key))
+        if entrywise:
+            continue
+        assert asm.dev.fast_path, 'no sum-factorised instantiation for ' + case
+        A = asm.assemble_csr()
+        assert A.indptr.dtype == np.int32 and A.indices.dtype == np.int32 and A.data.dtype == np.float64
+        assert np.array_equal(A.indptr, ref['%s_%s_indptr' % (case, key)])
+        assert np.array_equal(A.indices, ref['%s_%s_indices' % (case, key)])
+        B = orc.mlb_to_csr(want, [ref['%s_bidx%d' % (case, k)] for k in range(dim)], S.bs)
+        B.sort_indices()
+        assert_close_rel(A.data, B.data, what='%s %s csr' % (case, key))
+
+
+def check_slabs(ref, case, nslabs):
+    """row slabs of the first axis, assembled independently, concatenate to the full tensor
+    (multi-GPU parity with logical ranks on one device)."""
+    from pyiga_b200 import assemblers
+    from pyiga_b200.dist import partition_rows
+    kvs = make_space(ref, case)
+    geo = make_geo(ref, str(ref[case + '_geo']))
+    for form, key in (('Mass', 'mass'), ('Stiffness', 'stiff')):
+        asm = getattr(assemblers, '%sAssembler%dD' % (form, len(kvs)))(kvs, geo)
+        want = ref['%s_%s_mlb' % (case, key)]
+        parts = []
+        for (a, b) in partition_rows(asm.dev, nslabs):
+            parts.append(asm.dev.be.to_host(asm.dev.assemble_mlb(rows=(a, b))))
+        got = np.concatenate(parts).reshape(want.shape)
+        assert_close_rel(got, want, what='%s %s in %d slabs' % (case, key, nslabs))
+
+
+def check_chunked(ref, case):
+    """a tiny workspace budget forces the chunked pipeline"""
+    from pyiga_b200 import assemblers
+    kvs = make_space(ref, case)
+    geo = make_geo(ref, str(ref[case + '_geo']))
+    asm = assemblers.StiffnessAssembler3D(kvs, geo)
+    full = asm.dev.workspace_bytes()
+    one = max(asm.dev.workspace_bytes((r, r + 1)) for r in range(asm.dev.ndofs_test[0]))
+    assert one < full
+    budget = one
+    chunks = asm.dev.row_chunks(None, budget)
+    assert len(chunks) > 1
+    want = ref[case + '_stiff_mlb']
+    got = asm.dev.be.to_host(asm.dev.assemble_mlb(budget_bytes=budget)).reshape(want.shape)
+    assert_close_rel(got, want, what=case + ' chunked')
+
+
+def check_multi_entries(ref, case):
+    """the multi_entries protocol incl. pairs outside the pattern (-> exactly 0.0)"""
+    from pyiga_b200 import assemblers
+    kvs = make_space(ref, case)
+    geo = make_geo(ref, str(ref[case + '_geo']))
+    asm = getattr(assemblers, 'StiffnessAssembler%dD' % len(kvs))(kvs, geo)
+    ij, want = ref[case + '_me_ij'], ref[case + '_me_val']
+    got = asm.multi_entries(ij)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert_close_rel(got, want, what='multi_entries ' + case)
+    assert np.all(got[want == 0.0] == 0.0)
+    # iterable of pairs + scalar entry()
+    got2 = asm.multi_entries((int(i), int(j)) for i, j in ij[:5])
+    assert np.array_equal(got2, got[:5])
+    assert asm.entry(int(ij[200, 0]), int(ij[200, 1])) == got[200]
+    assert asm.arity == 2 and asm.kvs == (kvs, kvs)
+    assert asm.inputs() == {'geo': (len(kvs),)} and asm.parameters() == {}
+
+
+def check_golden(dim):
+    """the reference's golden matrices (test/test_assemble.py:138-168) through assemble.mass/stiffness"""
+    from pyiga_b200 import assemble, bspline, geometry
+    if dim == 2:
+        kvs = 2 * (bspline.make_knots(3, 0.0, 1.0, 15),)
+        geo, names = geometry.bspline_quarter_annulus(), ('d2_p3_n15_mass', 'd2_p3_n15_stiff')
+    else:
+        kvs = 3 * (bspline.make_knots(2, 0.0, 1.0, 10),)
+        geo, names = geometry.twisted_box(), ('d3_p2_n10_mass', 'd3_p2_n10_stiff')
+    for fn, name in zip((assemble.mass, assemble.stiffness), names):
+        A, G = fn(kvs, geo), load_golden(name)
+        assert A.format == 'csr' and A.shape == G.shape
+        scale = abs(G).max()
+        assert abs(A - G).max() <= RTOL * scale, name
+        assert abs(A - A.T).max() <= RTOL * scale
+
+
+def check_operators(ref):
+    from pyiga_b200.mlmatrix import MLMatrix, MLStructure
+    from pyiga_b200.operators import KroneckerOperator
+    kvs = make_space(ref, 'a3_mixed')
+    S = MLStructure.from_kvs(kvs, kvs)
+    M = MLMatrix(S, data=ref['mv_data'])
+    np.testing.assert_allclose(M.dot(ref['mv_x']), ref['mv_y'], rtol=1e-13, atol=1e-13)
+    A = M.asmatrix()
+    np.testing.assert_allclose(A @ ref['mv_x'], ref['mv_y'], rtol=1e-13, atol=1e-13)
+    facs = [ref['kron_A%d' % k] for k in range(3)]
+    np.testing.assert_allclose(KroneckerOperator(*facs).dot(ref['kron_x']), ref['kron_y'], rtol=1e-13, atol=1e-13)

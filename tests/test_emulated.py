@@ -1,0 +1,55 @@
+"""CPU run of the parity checks through the sequential host emulation of the kernels
+(tests/emu): covers the host logic of the package and the index logic of every kernel body.
+The numbers that count are produced by tests/test_gpu_parity.py on the B200."""
+import pytest
+
+import parity_checks as pc
+from helpers import CASES, GEOS
+
+
+def test_basis(emu, ref):
+    pc.check_basis(emu, ref)
+
+
+@pytest.mark.parametrize('name', GEOS)
+def test_geometry(emu, ref, name):
+    pc.check_geometry(ref, name)
+
+
+@pytest.mark.parametrize('case', ['a2_qa', 'a3_nurbs'])
+@pytest.mark.parametrize('form', ['mass', 'stiffness'])
+def test_fields(emu, ref, case, form):
+    pc.check_fields(ref, case, form)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_assemble_sum_factorised(emu, ref, case):
+    pc.check_case(ref, case)
+
+
+@pytest.mark.parametrize('case', ['a2_mixed', 'a3_mult'])
+def test_assemble_entrywise(emu, ref, case):
+    pc.check_case(ref, case, entrywise=True)
+
+
+@pytest.mark.parametrize('case,nslabs', [('a2_qa', 2), ('a3_tb', 2), ('a3_nurbs', 4), ('a3_mult', 3), ('a3_p1', 8)])
+def test_slabs(emu, ref, case, nslabs):
+    pc.check_slabs(ref, case, nslabs)
+
+
+def test_chunked(emu, ref):
+    pc.check_chunked(ref, 'a3_p1')
+
+
+@pytest.mark.parametrize('case', ['a2_qa', 'a3_mixed', 'a3_mult'])
+def test_multi_entries(emu, ref, case):
+    pc.check_multi_entries(ref, case)
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+def test_golden(emu, dim):
+    pc.check_golden(dim)
+
+
+def test_operators(emu, ref):
+    pc.check_operators(ref)

@@ -1,0 +1,103 @@
+"""Parity of the CUDA path on the B200 against reference fixtures, goldens and the oracle.
+Everything here calls through the C ABI of libpyiga_b200.so (ctypes) on cuda:0."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from helpers import CASES, GEOS, assert_close_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_loaded(cuda):
+    assert cuda.name == 'cuda'
+    assert cuda.lib.pb200_version() >= 100
+
+
+def test_basis(cuda, ref):
+    pc.check_basis(cuda, ref)
+
+
+@pytest.mark.parametrize('name', GEOS)
+def test_geometry(cuda, ref, name):
+    pc.check_geometry(ref, name)
+
+
+@pytest.mark.parametrize('case', ['a2_qa', 'a3_nurbs'])
+@pytest.mark.parametrize('form', ['mass', 'stiffness'])
+def test_fields(cuda, ref, case, form):
+    pc.check_fields(ref, case, form)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_assemble_sum_factorised(cuda, ref, case):
+    pc.check_case(ref, case)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_assemble_entrywise(cuda, ref, case):
+    pc.check_case(ref, case, entrywise=True)
+
+
+@pytest.mark.parametrize('case,nslabs', [('a2_qa', 2), ('a3_tb', 2), ('a3_nurbs', 4), ('a3_mult', 3), ('a3_p1', 8)])
+def test_slabs(cuda, ref, case, nslabs):
+    pc.check_slabs(ref, case, nslabs)
+
+
+def test_chunked(cuda, ref):
+    pc.check_chunked(ref, 'a3_p1')
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_multi_entries(cuda, ref, case):
+    pc.check_multi_entries(ref, case)
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+def test_golden(cuda, dim):
+    pc.check_golden(dim)
+
+
+def test_operators(cuda, ref):
+    pc.check_operators(ref)
+
+
+@pytest.mark.parametrize('p,n', [(2, 12), (3, 16), (4, 10)])
+@pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
+def test_vs_oracle_3d(cuda, p, n, form):
+    """sizes above the fixtures: sum-factorised kernels vs the oracle's closed form, and vs the
+    per-entry kernel (two independent device algorithms)"""
+    from oracle import pyiga_oracle as orc
+    from pyiga_b200 import assemblers, bspline, geometry
+    kvs = 3 * (bspline.make_knots(p, 0.0, 1.0, n),)
+    geo = geometry.twisted_nurbs_box()
+    asm = getattr(assemblers, form + 'Assembler3D')(kvs, geo)
+    got = cuda.to_host(asm.dev.assemble_mlb())
+    prob = orc.Problem([kv.kv for kv in kvs], [p] * 3, [kv.kv for kv in geo.kvs], [kv.p for kv in geo.kvs],
+                       geo.coeffs, True)
+    want = orc.assemble_mlb(prob, form.lower()).ravel()
+    assert_close_rel(got, want, what='%s p=%d n=%d' % (form, p, n))
+    ew = cuda.to_host(asm.dev.assemble_mlb(entrywise=True))
+    assert_close_rel(ew, want, what='entrywise %s p=%d n=%d' % (form, p, n))
+
+
+def test_properties_large(cuda):
+    """size-independent properties at a size the oracle cannot hold: symmetry of the MLB tensor
+    under the transposed band index, row sums of the stiffness matrix vanish (constants are in the
+    kernel of the gradient), mass matrix sums to the volume."""
+    from pyiga_b200 import assemblers, bspline, geometry
+    p, n = 3, 40
+    kvs = 3 * (bspline.make_knots(p, 0.0, 1.0, n),)
+    geo = geometry.twisted_box()
+    K = assemblers.StiffnessAssembler3D(kvs, geo)
+    M = assemblers.MassAssembler3D(kvs, geo)
+    Kd, Md = K.assemble_mlb(), M.assemble_mlb()
+    ones = np.ones(Kd.shape[1])
+    scale = np.abs(Kd.data).max()
+    assert np.abs(Kd.dot(ones)).max() <= 1e-10 * scale
+    vol_mass = float(ones @ Md.dot(ones))
+    vol_quad = float(M.dev.fields_host().sum())          # sum of W = GaussWeight * |det J|
+    assert abs(vol_mass - vol_quad) <= 1e-12 * abs(vol_quad)
+    tr = [np.lexsort((b[:, 0], b[:, 1])) for b in Kd.structure.bidx]
+    T = Kd.data[np.ix_(*tr)]
+    assert np.abs(T - Kd.data).max() <= 1e-12 * scale
