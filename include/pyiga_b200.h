@@ -105,6 +105,8 @@ typedef struct {
 
 PB200_API int pb200_version(void);
 PB200_API const char* pb200_last_error(void);
+/* number of kernels this library has launched so far (benchmark bookkeeping) */
+PB200_API long long pb200_launch_count(void);
 
 /* ---- assembler object -------------------------------------------------------------------------
  * Replaces the constructor of the assembler classes (pyiga/assemblers.pyx:1336-1383): builds the
@@ -127,6 +129,10 @@ PB200_API int pb200_asm_structure(const pb200_assembler* a, int axis, uint32_t* 
  * assemblers.pyx:1389-1449). */
 PB200_API int pb200_asm_bind_fields(pb200_assembler* a, double* d_fields);
 PB200_API int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc* geo, void* stream);
+/* same, restricted to the Gauss planes that the rows [row0_begin,row0_end) of the first axis see
+ * (slab-sharded assembly: every rank evaluates only its planes plus the p-span overlap) */
+PB200_API int pb200_asm_compute_fields_slab(pb200_assembler* a, const pb200_geo_desc* geo, int row0_begin,
+                                            int row0_end, void* stream);
 /* same, from Jacobians the caller evaluated on the Gauss grid (geometry objects that are not
  * splines): d_jac is [npoints][dim][dim] */
 PB200_API int pb200_asm_compute_fields_from_jacobian(pb200_assembler* a, const double* d_jac, void* stream);
@@ -150,6 +156,15 @@ PB200_API int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int row
  * configurations without a fast path) */
 PB200_API int pb200_asm_assemble_mlb_entrywise(pb200_assembler* a, int row0_begin, int row0_end, double* d_out,
                                      void* stream);
+
+/* Per-kernel timing of the pipeline (for the roofline report): when enabled, CUDA events are
+ * recorded on the launch stream around every stage of the next assemble call;
+ * pb200_asm_get_timing waits for them and returns the durations in ms and the ';'-joined names. */
+PB200_API int pb200_asm_set_timing(pb200_assembler* a, int enable);
+/* tuning / test switches: "force_walk" = 1 disables the warp-per-line kernels of the final stage */
+PB200_API int pb200_asm_set_option(pb200_assembler* a, const char* name, int value);
+PB200_API int pb200_asm_get_timing(pb200_assembler* a, int max_stages, float* ms, char* names, int names_len,
+                                   int* nstages);
 
 /* multi_entries(indices) (pyiga/genericasm.pxi:722-758): d_ij is n x 2 uint64 (row, column),
  * d_out n doubles; pairs outside the pattern give 0.0. */

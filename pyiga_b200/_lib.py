@@ -49,6 +49,7 @@ class Info(C.Structure):
 SIGNATURES = {
     'pb200_version': (C.c_int, []),
     'pb200_last_error': (C.c_char_p, []),
+    'pb200_launch_count': (C.c_longlong, []),
     'pb200_asm_create': (C.c_int, [C.POINTER(Desc), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     'pb200_asm_destroy': (C.c_int, [C.c_void_p]),
     'pb200_asm_info': (C.c_int, [C.c_void_p, C.POINTER(Info)]),
@@ -56,6 +57,7 @@ SIGNATURES = {
     'pb200_asm_structure': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'pb200_asm_bind_fields': (C.c_int, [C.c_void_p, C.c_void_p]),
     'pb200_asm_compute_fields': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_void_p]),
+    'pb200_asm_compute_fields_slab': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_int, C.c_int, C.c_void_p]),
     'pb200_asm_compute_fields_from_jacobian': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb200_geo_eval_grid': (C.c_int, [C.POINTER(GeoDesc), C.POINTER(C.c_int), C.POINTER(c_double_p),
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -63,6 +65,10 @@ SIGNATURES = {
     'pb200_asm_assemble_mlb': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
     'pb200_asm_assemble_mlb_entrywise': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    'pb200_asm_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    'pb200_asm_set_timing': (C.c_int, [C.c_void_p, C.c_int]),
+    'pb200_asm_get_timing': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_char_p, C.c_int,
+                                       C.POINTER(C.c_int)]),
     'pb200_asm_multi_entries': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     'pb200_asm_mlstruct': (C.c_void_p, [C.c_void_p]),
     'pb200_mlstruct_create': (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

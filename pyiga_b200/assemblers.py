@@ -119,12 +119,17 @@ class DeviceAssembler:
     def tabulate(self):
         _device.check(self.be.lib.pb200_asm_tabulate(self.handle, self.be.stream()))
 
-    def compute_fields(self, geo):
-        """K2: geometry Jacobian + form coefficients at every Gauss point."""
+    def compute_fields(self, geo, rows=None):
+        """K2: geometry Jacobian + form coefficients at every Gauss point (or only on the Gauss
+        planes seen by the rows `rows` of the first axis)."""
         be = self.be
         if _is_spline_geo(geo):
             desc, keep = _lib.make_geo_desc(geo)
-            _device.check(be.lib.pb200_asm_compute_fields(self.handle, C.byref(desc), be.stream()))
+            if rows is None:
+                _device.check(be.lib.pb200_asm_compute_fields(self.handle, C.byref(desc), be.stream()))
+            else:
+                _device.check(be.lib.pb200_asm_compute_fields_slab(self.handle, C.byref(desc), rows[0], rows[1],
+                                                                    be.stream()))
         else:
             # geometry given as an arbitrary Python object: evaluate its Jacobian on the host, as
             # the reference does for every geometry, and upload it
@@ -196,6 +201,21 @@ class DeviceAssembler:
             if workspace is None and ws is not None:
                 be.synchronize()    # the temporary workspace is released when `ws` goes out of scope
         return out
+
+    def set_option(self, name, value):
+        _device.check(self.be.lib.pb200_asm_set_option(self.handle, name.encode(), int(value)))
+
+    def set_timing(self, enable=True):
+        _device.check(self.be.lib.pb200_asm_set_timing(self.handle, int(enable)))
+
+    def stage_times(self):
+        """[(kernel name, ms)] of the last assemble call (needs set_timing(True))."""
+        ms = (C.c_float * 16)()
+        names = C.create_string_buffer(512)
+        n = C.c_int()
+        _device.check(self.be.lib.pb200_asm_get_timing(self.handle, 16, ms, names, 512, C.byref(n)))
+        labels = [t for t in names.value.decode().split(';') if t]
+        return [(labels[i], float(ms[i])) for i in range(min(n.value, len(labels)))]
 
     def multi_entries_device(self, ij):
         be = self.be

@@ -23,6 +23,7 @@
 // errors
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static long long g_launches = 0;       // kernels launched by this library (reported by the benchmark)
 
 static int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -45,6 +46,7 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 static void k_basis(const double* kv, int nk, int p, const double* nodes, int m, int nd, int* first, double* values,
                     pbStream st) {
+    ++g_launches;
 #ifdef PB_EMULATE
     pb_emu_for(m, [&](long long g) { pb_basis_node(kv, nk, p, nodes, nd, first, values, (int)g); });
 #else
@@ -54,11 +56,38 @@ static void k_basis(const double* kv, int nk, int p, const double* nodes, int m,
 
 template <int DIM, class Prog>
 static void k_fields(const PbFieldParams& prm, pbStream st) {
+    ++g_launches;
 #ifdef PB_EMULATE
-    pb_emu_for(prm.npts, [&](long long i) { pb_fields_point<DIM, Prog>(prm, i); });
+    pb_emu_for(prm.pt_end - prm.pt_begin, [&](long long i) { pb_fields_point<DIM, Prog>(prm, prm.pt_begin + i); });
 #else
-    const long long blocks = std::min<long long>((prm.npts + 255) / 256, 148LL * 32);
+    const long long blocks = std::min<long long>((prm.pt_end - prm.pt_begin + 255) / 256, 148LL * 32);
     pb_fields_kernel<DIM, Prog><<<(unsigned)blocks, 256, 0, st>>>(prm);
+#endif
+}
+
+// row-wise K2 for spline geometries: rows [row_begin, row_end) of the grid (row = g0 or (g0,g1))
+template <int DIM, int NC, class Prog>
+static int k_fields_rows(const PbFieldParams& prm, long long row_begin, long long row_end, pbStream st) {
+    const size_t ybytes = (size_t)prm.geo.Ng[DIM - 1] * NC * DIM * sizeof(double);
+    g_launches += (row_end - row_begin + (1LL << 30) - 1) >> 30;
+#ifdef PB_EMULATE
+    std::vector<double> Y(ybytes / sizeof(double));
+    pb_emu_for(row_end - row_begin, [&](long long r) { pb_fields_row_seq<DIM, NC, Prog>(prm, row_begin + r, Y.data()); });
+    (void)st;
+    return 0;
+#else
+    auto kern = pb_fields_row_kernel<DIM, NC, Prog>;
+    if (ybytes > 48 * 1024) {
+        if (ybytes > 200 * 1024) return fail(PB200_EUNSUPPORTED, "geometry control net too long on the last axis");
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ybytes));
+    }
+    long long done = row_begin;
+    while (done < row_end) {       // grid.x is limited to 2^31-1 blocks
+        const long long nb = std::min<long long>(row_end - done, 1LL << 30);
+        kern<<<(unsigned)nb, 128, ybytes, st>>>(prm, done);
+        done += nb;
+    }
+    return 0;
 #endif
 }
 
@@ -87,6 +116,7 @@ __global__ void pb_geo_grid_kernel(PbGeoDev geo, int G0, int G1, int G2, long lo
 #endif
 template <int DIM>
 static void k_geo_grid(const PbGeoDev& geo, const int* G, long long npts, double* values, double* jac, pbStream st) {
+    ++g_launches;
 #ifdef PB_EMULATE
     pb_emu_for(npts, [&](long long i) { pb_geo_grid_point<DIM>(geo, G, values, jac, i); });
 #else
@@ -97,6 +127,7 @@ static void k_geo_grid(const PbGeoDev& geo, const int* G, long long npts, double
 
 template <int DIM>
 static void k_entries(const PbEntryParams& prm, pbStream st) {
+    ++g_launches;
 #ifdef PB_EMULATE
     pb_emu_for(prm.n, [&](long long e) { prm.out[e] = pb_entry<DIM>(prm, prm.ij[2 * e], prm.ij[2 * e + 1]); });
 #else
@@ -106,6 +137,7 @@ static void k_entries(const PbEntryParams& prm, pbStream st) {
 }
 template <int DIM>
 static void k_entries_mlb(const PbEntryParams& prm, long long mu0_begin, long long count, pbStream st) {
+    ++g_launches;
 #ifdef PB_EMULATE
     pb_emu_for(count, [&](long long e) { prm.out[e] = pb_entry_mlb<DIM>(prm, mu0_begin, e); });
 #else
@@ -117,6 +149,7 @@ static void k_entries_mlb(const PbEntryParams& prm, long long mu0_begin, long lo
 template <class IdxT>
 static void k_csr(const PbMlbParams& p, long long nrows, long long count, IdxT* indptr, IdxT* indices, double* values,
                   pbStream st) {
+    g_launches += 2;
 #ifdef PB_EMULATE
     pb_emu_for(nrows + 1, [&](long long r) { pb_csr_indptr_row<IdxT>(p, nrows, indptr, r); });
     pb_emu_for(count, [&](long long e) { pb_csr_fill_elem<IdxT>(p, indices, values, e); });
@@ -129,6 +162,7 @@ static void k_csr(const PbMlbParams& p, long long nrows, long long count, IdxT* 
 }
 
 static void k_matvec(const PbMlbParams& p, long long nrows, const double* x, int x_j0, double* y, pbStream st) {
+    ++g_launches;
 #ifdef PB_EMULATE
     pb_emu_for(nrows, [&](long long r) { pb_mlb_matvec_row(p, x, x_j0, y, r); });
 #else
@@ -138,6 +172,7 @@ static void k_matvec(const PbMlbParams& p, long long nrows, const double* x, int
 
 static void k_modek(const double* A, int m, int n, const double* x, long long outer, long long inner, double* y,
                     pbStream st) {
+    ++g_launches;
     const long long total = outer * m * inner;
 #ifdef PB_EMULATE
     pb_emu_for(total, [&](long long e) { pb_modek_elem(A, m, n, x, inner, y, e); });
@@ -149,6 +184,7 @@ static void k_modek(const double* A, int m, int n, const double* x, long long ou
 
 extern "C" const char* pb200_last_error(void) { return g_err.c_str(); }
 extern "C" int pb200_version(void) { return 100; }
+extern "C" long long pb200_launch_count(void) { return g_launches; }
 
 // ------------------------------------------------------------------------------------------------
 // walk-kernel registry
@@ -304,7 +340,67 @@ struct pb200_assembler {
     void* geo_scratch = nullptr;
     long long npts = 0, nnz = 0;
     int fast = 0;
+    bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
+    bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
+    // optional per-kernel timing of the last assemble call (CUDA events on the launch stream)
+    bool timing = false;
+    std::vector<std::string> stage_names;
+#ifndef PB_EMULATE
+    std::vector<cudaEvent_t> stage_events;
+#endif
 };
+
+static void mark_stage(pb200_assembler* a, const char* name, pbStream st) {
+    if (!a->timing) return;
+#ifndef PB_EMULATE
+    const size_t i = a->stage_names.size();
+    if (a->stage_events.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        a->stage_events.push_back(e);
+    }
+    cudaEventRecord(a->stage_events[i], st);
+#else
+    (void)st;
+#endif
+    a->stage_names.push_back(name);
+}
+
+extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int value) {
+    if (!a || !name) return fail(PB200_EINVAL, "null argument");
+    if (!strcmp(name, "force_walk")) { a->force_walk = value != 0; return 0; }
+    return fail(PB200_EINVAL, "unknown option '%s'", name);
+}
+
+extern "C" int pb200_asm_set_timing(pb200_assembler* a, int enable) {
+    if (!a) return fail(PB200_EINVAL, "null handle");
+    a->timing = enable != 0;
+    a->stage_names.clear();
+    return 0;
+}
+
+// durations (ms) between consecutive marks of the last assemble call; names joined by ';'
+extern "C" int pb200_asm_get_timing(pb200_assembler* a, int max_stages, float* ms, char* names, int names_len, int* nstages) {
+    if (!a || !ms || !nstages) return fail(PB200_EINVAL, "null argument");
+    const int n = (int)a->stage_names.size() - 1;
+    *nstages = n > 0 ? n : 0;
+    std::string joined;
+    for (int i = 0; i < n && i < max_stages; ++i) {
+#ifndef PB_EMULATE
+        CK(cudaEventSynchronize(a->stage_events[i + 1]));
+        CK(cudaEventElapsedTime(&ms[i], a->stage_events[i], a->stage_events[i + 1]));
+#else
+        ms[i] = 0.f;
+#endif
+        joined += a->stage_names[i];
+        joined += ';';
+    }
+    if (names && names_len > 0) {
+        strncpy(names, joined.c_str(), names_len - 1);
+        names[names_len - 1] = 0;
+    }
+    return 0;
+}
 
 static bool have_plan(int plan, int P, int Q) { return pb_find_walk(plan, P, Q) != nullptr; }
 
@@ -403,6 +499,9 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
         }
         a->npts *= H.G;
         a->nnz *= H.M;
+        a->lane_ok[k] = H.same;
+        for (int s = 1; s < H.n; ++s)
+            if (H.U.first[s] != H.U.first[s - 1] + 1) a->lane_ok[k] = false;
     }
 
     if (desc->form == PB200_FORM_MASS) {
@@ -657,7 +756,8 @@ static int launch_fields(const PbFieldParams& prm, pbStream st) {
     return 0;
 }
 
-static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, const double* d_jac, pbStream st) {
+static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, const double* d_jac, pbStream st,
+                               int row0_begin = -1, int row0_end = -1) {
     if (!a) return fail(PB200_EINVAL, "null handle");
     if (!a->d_fields) return fail(PB200_EINVAL, "no field buffer bound (pb200_asm_bind_fields)");
     if (a->form == PB200_FORM_CUSTOM) return fail(PB200_EINVAL, "custom forms upload their fields");
@@ -674,6 +774,15 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
     }
     prm.fields = a->d_fields;
     prm.npts = a->npts;
+    prm.pt_begin = 0;
+    prm.pt_end = a->npts;
+    if (row0_begin >= 0) {      // only the Gauss planes in the support of the rows of the slab
+        const AxisHost& H0 = a->hax[0];
+        if (row0_end > H0.V.N() || row0_begin >= row0_end) return fail(PB200_EINVAL, "invalid row slab [%d,%d)", row0_begin, row0_end);
+        const long long plane = a->npts / H0.G;
+        prm.pt_begin = (long long)H0.V.supp[2 * row0_begin] * H0.q * plane;
+        prm.pt_end = (long long)H0.V.supp[2 * (row0_end - 1) + 1] * H0.q * plane;
+    }
     prm.nf = a->nfields;
     prm.jac_in = d_jac;
     GeoTables T;
@@ -684,13 +793,35 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
         a->geo_scratch = T.mem;
         prm.geo = T.dev;
     }
+    const bool mass = a->form == PB200_FORM_MASS;
+    if (!d_jac) {
+        // spline geometry: row-wise sum-factorised evaluation
+        const long long lastG = a->hax[a->dim - 1].G;
+        const long long r0 = prm.pt_begin / lastG, r1 = prm.pt_end / lastG;
+        const bool rat = prm.geo.rational != 0;
+        int rc;
+        if (a->dim == 2) {
+            if (mass) rc = rat ? k_fields_rows<2, 3, PbProgMass<2>>(prm, r0, r1, st) : k_fields_rows<2, 2, PbProgMass<2>>(prm, r0, r1, st);
+            else rc = rat ? k_fields_rows<2, 3, PbProgStiffness<2>>(prm, r0, r1, st) : k_fields_rows<2, 2, PbProgStiffness<2>>(prm, r0, r1, st);
+        } else {
+            if (mass) rc = rat ? k_fields_rows<3, 4, PbProgMass<3>>(prm, r0, r1, st) : k_fields_rows<3, 3, PbProgMass<3>>(prm, r0, r1, st);
+            else rc = rat ? k_fields_rows<3, 4, PbProgStiffness<3>>(prm, r0, r1, st) : k_fields_rows<3, 3, PbProgStiffness<3>>(prm, r0, r1, st);
+        }
+        if (rc) return rc;
+        CK(pbLastError());
+        return 0;
+    }
     if (a->dim == 2)
-        return a->form == PB200_FORM_MASS ? launch_fields<2, PbProgMass<2>>(prm, st) : launch_fields<2, PbProgStiffness<2>>(prm, st);
-    return a->form == PB200_FORM_MASS ? launch_fields<3, PbProgMass<3>>(prm, st) : launch_fields<3, PbProgStiffness<3>>(prm, st);
+        return mass ? launch_fields<2, PbProgMass<2>>(prm, st) : launch_fields<2, PbProgStiffness<2>>(prm, st);
+    return mass ? launch_fields<3, PbProgMass<3>>(prm, st) : launch_fields<3, PbProgStiffness<3>>(prm, st);
 }
 
 extern "C" int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc* geo, void* stream) {
     return compute_fields_impl(a, geo, nullptr, (pbStream)stream);
+}
+extern "C" int pb200_asm_compute_fields_slab(pb200_assembler* a, const pb200_geo_desc* geo, int row0_begin, int row0_end,
+                                             void* stream) {
+    return compute_fields_impl(a, geo, nullptr, (pbStream)stream, row0_begin, row0_end);
 }
 extern "C" int pb200_asm_compute_fields_from_jacobian(pb200_assembler* a, const double* d_jac, void* stream) {
     if (!d_jac) return fail(PB200_EINVAL, "null Jacobian array");
@@ -788,7 +919,9 @@ extern "C" int pb200_asm_workspace_bytes(const pb200_assembler* a, int row0_begi
     return 0;
 }
 
-static int run_stage(int plan, const pb200_assembler* a, int axis, PbWalkParams& prm, pbStream st) {
+static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, pbStream st, const char* name) {
+    mark_stage(a, name, st);
+    ++g_launches;
     const AxisHost& H = a->hax[axis];
     const PbAxis& D = a->dax[axis];
     const int P = H.U.p, Q = H.q;
@@ -798,6 +931,15 @@ static int run_stage(int plan, const pb200_assembler* a, int axis, PbWalkParams&
     prm.first = D.first_u;
     prm.V2 = D.Vu;
     prm.ret_mu = D.ret_mu;
+    // final stages (node axis contiguous, one output, single interior knots): warp-per-line kernel
+    if (prm.in_sc == 1 && prm.out_smu == 1 && prm.w_mode == 0 && a->lane_ok[axis] && !a->force_walk) {
+        PbWalkLaunch lane = pb_find_walk(PB_PLAN_LANE_BASE + plan, P, Q);
+        if (lane) {
+            int e = lane(&prm, 16, 0, st);
+            if (e) return fail(PB200_ECUDA, "lane-span kernel launch failed (plan %d, p=%d, q=%d): %s", plan, P, Q, pbErrorString((pbError)e));
+            return 0;
+        }
+    }
     const size_t smem = (size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double);
     const int use_smem = smem <= 160 * 1024;
     int e = fn(&prm, use_smem, use_smem ? smem : 0, st);
@@ -813,6 +955,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
     CK(pbSetDevice(a->device));
     pbStream st = (pbStream)stream;
     const bool stiff = a->form == PB200_FORM_STIFFNESS;
+    a->stage_names.clear();
     Slab S;
     int rc = make_slab(a, row0_begin, row0_end, uses_transposes(a), S);
     if (rc) return rc;
@@ -851,10 +994,10 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             if (stiff) {
                 p.in[0] = F + 2 * npts; p.in[1] = F + 1 * npts; p.in[2] = F;     // B11, B01, B00
                 for (int t = 0; t < 3; ++t) p.out[t] = X1 + t * s1;
-                rc = run_stage(PB_PLAN_S1_2D, a, 0, p, st);
+                rc = run_stage(PB_PLAN_S1_2D, a, 0, p, st, "s1_2d");
             } else {
                 p.in[0] = F; p.out[0] = X1;
-                rc = run_stage(PB_PLAN_COPY, a, 0, p, st);
+                rc = run_stage(PB_PLAN_COPY, a, 0, p, st, "s1_copy");
             }
             if (rc) return rc;
         }
@@ -870,11 +1013,12 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             p.out[0] = d_out;
             if (stiff) {
                 p.in[0] = X1; p.in[1] = X1 + s1; p.in[2] = X1 + s1; p.in[3] = X1 + 2 * s1;
-                rc = run_stage(PB_PLAN_FINAL4, a, 1, p, st);
+                rc = run_stage(PB_PLAN_FINAL4, a, 1, p, st, "s2_final4");
             } else {
                 p.in[0] = X1;
-                rc = run_stage(PB_PLAN_COPY, a, 1, p, st);
+                rc = run_stage(PB_PLAN_COPY, a, 1, p, st, "s2_copy");
             }
+            mark_stage(a, "end", st);
             return rc;
         }
     }
@@ -897,12 +1041,12 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             for (int t = 0; t < 3; ++t) pa.out[t] = X1 + t * s1;
             pb.in[0] = F + 3 * npts; pb.in[1] = F + 1 * npts; pb.in[2] = F;              // B11, B01, B00
             for (int t = 0; t < 3; ++t) pb.out[t] = X1 + (3 + t) * s1;
-            rc = run_stage(PB_PLAN_S1A, a, 0, pa, st);
+            rc = run_stage(PB_PLAN_S1A, a, 0, pa, st, "s1a");
             if (rc) return rc;
-            rc = run_stage(PB_PLAN_S1B, a, 0, pb, st);
+            rc = run_stage(PB_PLAN_S1B, a, 0, pb, st, "s1b");
         } else {
             p.in[0] = F; p.out[0] = X1;
-            rc = run_stage(PB_PLAN_COPY, a, 0, p, st);
+            rc = run_stage(PB_PLAN_COPY, a, 0, p, st, "s1_copy");
         }
         if (rc) return rc;
     }
@@ -923,12 +1067,12 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             pa.out[0] = X2;
             pb.in[0] = X1 + 2 * s1; pb.in[1] = X1 + 4 * s1; pb.in[2] = X1 + 5 * s1;
             pb.out[0] = X2 + s2; pb.out[1] = X2 + 2 * s2;
-            rc = run_stage(PB_PLAN_FINAL4, a, 1, pa, st);
+            rc = run_stage(PB_PLAN_FINAL4, a, 1, pa, st, "s2a_final4");
             if (rc) return rc;
-            rc = run_stage(PB_PLAN_S2B, a, 1, pb, st);
+            rc = run_stage(PB_PLAN_S2B, a, 1, pb, st, "s2b");
         } else {
             p.in[0] = X1; p.out[0] = X2;
-            rc = run_stage(PB_PLAN_COPY, a, 1, p, st);
+            rc = run_stage(PB_PLAN_COPY, a, 1, p, st, "s2_copy");
         }
         if (rc) return rc;
     }
@@ -944,13 +1088,14 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.out[0] = d_out;
         if (stiff) {
             p.in[0] = X2; p.in[1] = X2 + s2; p.in[2] = X2 + s2; p.in[3] = X2 + 2 * s2;
-            rc = run_stage(PB_PLAN_FINAL4, a, 2, p, st);
+            rc = run_stage(PB_PLAN_FINAL4, a, 2, p, st, "s3_final4");
         } else {
             p.in[0] = X2;
-            rc = run_stage(PB_PLAN_COPY, a, 2, p, st);
+            rc = run_stage(PB_PLAN_COPY, a, 2, p, st, "s3_copy");
         }
     }
     (void)H0;
+    mark_stage(a, "end", st);
     return rc;
 }
 

@@ -36,7 +36,8 @@ struct PbFieldParams {
     const double* jac_in;           // optional: Jacobians evaluated by the caller, [pts][dim][dim]
     const double* val_in;           // optional: geometry values, [pts][dim]
     double* fields;                 // [nf][pts]
-    long long npts;
+    long long npts;                 // points of the whole grid (stride between fields)
+    long long pt_begin, pt_end;     // linear range of points evaluated by this launch
     int nf;
     const double* inputs[PB_MAXFIELDS];  // user-supplied input fields on the Gauss grid, [ncomp][pts]
     const double* consts;                // parameters of the form
@@ -204,11 +205,147 @@ PB_HD void pb_fields_point(const PbFieldParams& prm, long long idx) {
     for (int c = 0; c < Prog::NF; ++c) prm.fields[(long long)c * prm.npts + idx] = f[c];
 }
 
+// ---- row-wise evaluation (the production path for spline geometries) --------------------------
+// All points of one grid row (fixed g0 [,g1]; the last axis runs) share the contraction of the
+// control net with the basis functions of the leading axes.  A block first reduces the net to
+//     Y[i_last][c][v] = sum_{a0[,a1]} coeffs[f0+a0][f1+a1][i_last][c] * w_v(a0, a1)
+// (v selects which leading axis carries the derivative: 0 = none, 1 = axis 0, 2 = axis 1) in shared
+// memory, then every thread finishes its point with p_last+1 terms.  This is the sum-factorised
+// form of `apply_tprod` (pyiga/tensor.py:97-128) for one row and makes K2 a streaming kernel.
+template <int DIM> struct PbRowVariants { static constexpr int NV = DIM; };
+
+// Y entry for (i_last, c): the NV = DIM variants
+template <int DIM>
+PB_HD void pb_geo_row_partial(const PbGeoDev& geo, const int* g, int i_last, int c, double* y) {
+    const int nc = geo.nc;
+    const int f0 = geo.gfirst[0][g[0]];
+    const double* T0 = geo.GV[0] + (long long)g[0] * 2 * (geo.pg[0] + 1);
+    if constexpr (DIM == 2) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int a0 = 0; a0 <= geo.pg[0]; ++a0) {
+            const double cv = geo.coeffs[((long long)(f0 + a0) * geo.Ng[1] + i_last) * nc + c];
+            s0 = fma(cv, T0[a0], s0);
+            s1 = fma(cv, T0[geo.pg[0] + 1 + a0], s1);
+        }
+        y[0] = s0; y[1] = s1;
+    } else {
+        const int f1 = geo.gfirst[1][g[1]];
+        const double* T1 = geo.GV[1] + (long long)g[1] * 2 * (geo.pg[1] + 1);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int a0 = 0; a0 <= geo.pg[0]; ++a0) {
+            const double w0 = T0[a0], d0 = T0[geo.pg[0] + 1 + a0];
+            double t0 = 0.0, t1 = 0.0;      // sum over a1 with value / derivative weights
+            for (int a1 = 0; a1 <= geo.pg[1]; ++a1) {
+                const double cv = geo.coeffs[(((long long)(f0 + a0) * geo.Ng[1] + (f1 + a1)) * geo.Ng[2] + i_last) * nc + c];
+                t0 = fma(cv, T1[a1], t0);
+                t1 = fma(cv, T1[geo.pg[1] + 1 + a1], t1);
+            }
+            s0 = fma(w0, t0, s0);       // no derivative on the leading axes
+            s1 = fma(d0, t0, s1);       // derivative on axis 0
+            s2 = fma(w0, t1, s2);       // derivative on axis 1
+        }
+        y[0] = s0; y[1] = s1; y[2] = s2;
+    }
+}
+
+// finish one point of the row from Y ([Ng_last][NC][DIM])
+template <int DIM, int NC, class Prog>
+PB_HD void pb_fields_row_point(const PbFieldParams& prm, const int* g, const double* Y) {
+    const PbGeoDev& geo = prm.geo;
+    const int L = DIM - 1;
+    const int gl = g[L];
+    const int fl = geo.gfirst[L][gl];
+    const double* TL = geo.GV[L] + (long long)gl * 2 * (geo.pg[L] + 1);
+    double val[NC], dv[NC][DIM];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        val[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) dv[c][k] = 0.0;
+    }
+    for (int a = 0; a <= geo.pg[L]; ++a) {
+        const double w = TL[a], d = TL[geo.pg[L] + 1 + a];
+        const double* y = Y + (long long)(fl + a) * NC * DIM;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            val[c] = fma(w, y[c * DIM + 0], val[c]);
+            dv[c][L] = fma(d, y[c * DIM + 0], dv[c][L]);        // derivative on the last axis
+            dv[c][0] = fma(w, y[c * DIM + 1], dv[c][0]);        // derivative on axis 0
+            if constexpr (DIM == 3) dv[c][1] = fma(w, y[c * DIM + 2], dv[c][1]);
+        }
+    }
+    PbPoint pt;
+    long long idx = 0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) idx = idx * prm.G[k] + g[k];
+    pt.idx = idx;
+    pt.gw = 1.0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) pt.gw *= prm.gw[k][g[k]];
+    constexpr int GD = DIM;     // square geometry maps: dim == sdim
+    if constexpr (NC == GD + 1) {
+        const double W = val[GD];
+        const double iW2 = 1.0 / (W * W);
+#pragma unroll
+        for (int i = 0; i < GD; ++i) {
+            pt.x[i] = val[i] / W;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) pt.J[i][DIM - 1 - k] = (dv[i][k] * W - val[i] * dv[GD][k]) * iW2;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < GD; ++i) {
+            pt.x[i] = val[i];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) pt.J[i][DIM - 1 - k] = dv[i][k];
+        }
+    }
+    double f[Prog::NF];
+    Prog::run(prm, pt, f);
+#pragma unroll
+    for (int c = 0; c < Prog::NF; ++c) prm.fields[(long long)c * prm.npts + idx] = f[c];
+}
+
+// one whole row, sequentially (host emulation) — `Y` is scratch of Ng_last*NC*DIM doubles
+template <int DIM, int NC, class Prog>
+PB_HD void pb_fields_row_seq(const PbFieldParams& prm, long long row, double* Y) {
+    int g[3] = {0, 0, 0};
+    if constexpr (DIM == 2) g[0] = (int)row;
+    else { g[0] = (int)(row / prm.G[1]); g[1] = (int)(row % prm.G[1]); }
+    const int NgL = prm.geo.Ng[DIM - 1];
+    for (int i = 0; i < NgL; ++i)
+        for (int c = 0; c < NC; ++c) pb_geo_row_partial<DIM>(prm.geo, g, i, c, Y + ((long long)i * NC + c) * DIM);
+    for (int gl = 0; gl < prm.G[DIM - 1]; ++gl) {
+        g[DIM - 1] = gl;
+        pb_fields_row_point<DIM, NC, Prog>(prm, g, Y);
+    }
+}
+
+#if defined(__CUDACC__)
+// one block per grid row; dynamic shared memory: Ng_last*NC*DIM doubles
+template <int DIM, int NC, class Prog>
+__global__ void __launch_bounds__(128) pb_fields_row_kernel(const __grid_constant__ PbFieldParams prm, long long row_begin) {
+    extern __shared__ double pb_Y[];
+    const long long row = row_begin + blockIdx.x;
+    int g[3] = {0, 0, 0};
+    if constexpr (DIM == 2) g[0] = (int)row;
+    else { g[0] = (int)(row / prm.G[1]); g[1] = (int)(row % prm.G[1]); }
+    const int NgL = prm.geo.Ng[DIM - 1];
+    for (int e = threadIdx.x; e < NgL * NC; e += blockDim.x)
+        pb_geo_row_partial<DIM>(prm.geo, g, e / NC, e % NC, pb_Y + (long long)e * DIM);
+    __syncthreads();
+    for (int gl = threadIdx.x; gl < prm.G[DIM - 1]; gl += blockDim.x) {
+        g[DIM - 1] = gl;
+        pb_fields_row_point<DIM, NC, Prog>(prm, g, pb_Y);
+    }
+}
+#endif
+
 #if defined(__CUDACC__)
 template <int DIM, class Prog>
 __global__ void __launch_bounds__(256) pb_fields_kernel(const __grid_constant__ PbFieldParams prm) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < prm.npts; idx += stride)
+    for (long long idx = prm.pt_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < prm.pt_end; idx += stride)
         pb_fields_point<DIM, Prog>(prm, idx);
 }
 #endif

@@ -30,7 +30,8 @@ enum PbPlanId {
     PB_PLAN_S1B = 3,
     PB_PLAN_S2B = 4,
     PB_PLAN_S1_2D = 5,  // 2D stiffness stage 1:  B11 [1,1]->(v,v)  B01 [1,0]->(v,d1)  B00 [0,0]->(d1,d1)
-    PB_PLAN_COUNT = 6
+    PB_PLAN_COUNT = 6,
+    PB_PLAN_LANE_BASE = 1000    // + plan id: the lane-per-span variant (second argument = lines per warp)
 };
 
 struct PbPlanCopy {

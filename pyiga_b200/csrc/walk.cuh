@@ -328,3 +328,215 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
     if (tid < prm.nthreads) pb_walk_line<Plan, P, Q>(prm, tid, Vt);
 }
 #endif
+
+// =================================================================================================
+// Final-stage variant: the walk axis is the fastest axis in memory ("lane per span").
+//
+// When the contracted node axis is contiguous (last tensor axis), the thread-per-line mapping of
+// pb_walk_kernel reads one 32-byte sector per lane and load instruction.  Here a WARP owns the line
+// instead: lane l takes span sb+l, loads its Q nodes (coalesced across the warp), and accumulates
+// the local (P+1)x(P+1) block L[a][b] of the pairs (s+a, s+b).  A band entry collects the blocks
+// of up to P+1 neighbouring spans; that sum is done with warp shuffles:
+//     out(m, m+d) = sum_{t=0..P-d} L_{span m-t}[t][t+d]          (shfl_up by t)
+// Lane l finishes the pairs "owned" by function m = f0 + l (the same retire set as in the walk
+// kernel), so ret_mu is reused.  Batches of 32 spans overlap by P spans because the first P lanes
+// of a batch lack their left neighbours.  Requires single interior knots (first[s+1] = first[s]+1).
+// =================================================================================================
+
+// local block of one span: L[a][b] = sum_gq sum_ops D_ft[a] D_fu[b] x   (single output plan)
+template <class Plan, int P, int Q>
+PB_HD void pb_span_block(const double (&x)[Q][Plan::NOPS], const double (&D)[Q][2][P + 1], double (&L)[P + 1][P + 1]) {
+    constexpr int P1 = P + 1;
+    constexpr int NOPS = Plan::NOPS;
+    constexpr bool by_fu = pb_group_by_fu<Plan>(0);
+#pragma unroll
+    for (int a = 0; a < P1; ++a)
+#pragma unroll
+        for (int b = 0; b < P1; ++b) L[a][b] = 0.0;
+#pragma unroll
+    for (int gq = 0; gq < Q; ++gq) {
+        pb_static_for<0, 2>([&](auto FL) {
+            constexpr int fl = decltype(FL)::value;
+            constexpr int cnt = by_fu ? pb_count_fu<Plan>(0, fl) : pb_count_ft<Plan>(0, fl);
+            if constexpr (cnt > 0) {
+                double y[P1];
+                constexpr int lead = pb_first_in_group<Plan>(0, fl, by_fu);
+                pb_static_for<0, NOPS>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    constexpr PbOp op = Plan::op(i);
+                    if constexpr ((by_fu ? op.fu : op.ft) == fl) {
+                        constexpr int other = by_fu ? op.ft : op.fu;
+                        const double xv = x[gq][i];
+                        if constexpr (i == lead) {
+#pragma unroll
+                            for (int c = 0; c < P1; ++c) y[c] = D[gq][other][c] * xv;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < P1; ++c) y[c] = fma(D[gq][other][c], xv, y[c]);
+                        }
+                    }
+                });
+                if constexpr (by_fu) {
+#pragma unroll
+                    for (int a = 0; a < P1; ++a)
+#pragma unroll
+                        for (int b = 0; b < P1; ++b) L[a][b] = fma(y[a], D[gq][fl][b], L[a][b]);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < P1; ++a)
+#pragma unroll
+                        for (int b = 0; b < P1; ++b) L[a][b] = fma(D[gq][fl][a], y[b], L[a][b]);
+                }
+            }
+        });
+    }
+}
+
+// line decode shared by the warp kernel and its emulation
+struct PbLineOffsets { long long in, in_tr, out; bool keep; };
+template <class Plan>
+PB_HD PbLineOffsets pb_decode_line(const PbWalkParams& prm, long long line) {
+    PbLineOffsets o;
+    const int x = (int)(line % prm.X);
+    const long long t2 = line / prm.X;
+    const int v = (int)(t2 % prm.V);
+    const int u = (int)(t2 / prm.V) + prm.u_begin;
+    o.keep = true;
+    if (prm.u_mode != 0) {
+        const int ui = prm.u_pair_i[u], uj = prm.u_pair_j[u];
+        const bool ki = (ui >= prm.u_lo && ui < prm.u_hi);
+        const bool kj = (uj >= prm.u_lo && uj < prm.u_hi);
+        o.keep = ki || (prm.u_mode == 2 && kj);
+    }
+    o.in = (long long)(u - prm.u_base_in) * prm.in_su + (long long)v * prm.in_sv + (long long)x * prm.in_sx;
+    o.in_tr = o.in;
+    if (Plan::HAS_TR) {
+        const int ut = prm.tr_u ? prm.tr_u[u] : u;
+        const int vt = prm.tr_v ? prm.tr_v[v] : v;
+        o.in_tr = (long long)(ut - prm.u_base_in) * prm.in_su + (long long)vt * prm.in_sv + (long long)x * prm.in_sx;
+    }
+    o.out = (long long)(u - prm.u_base_out) * prm.out_su + (long long)v * prm.out_sv + (long long)x * prm.out_sx;
+    return o;
+}
+
+PB_HD int pb_lane_batches(int nspans, int P) {
+    const int rest = nspans + P - 32;
+    return 1 + (rest > 0 ? (rest + (32 - P) - 1) / (32 - P) : 0);
+}
+
+// sequential emulation of one (line, batch) of the warp kernel
+template <class Plan, int P, int Q>
+PB_HD void pb_lane_span_seq(const PbWalkParams& prm, long long line, int batch) {
+    constexpr int P1 = P + 1, NOPS = Plan::NOPS;
+    const PbLineOffsets lo = pb_decode_line<Plan>(prm, line);
+    if (!lo.keep) return;
+    const int sb = prm.s_begin + batch * (32 - P);
+    const int f0 = prm.first[prm.s_begin];
+    double Ls[32][P1][P1];
+    for (int lane = 0; lane < 32; ++lane) {
+        const int s = sb + lane;
+        double x[Q][NOPS], D[Q][2][P1];
+        for (int gq = 0; gq < Q; ++gq) {
+            for (int i = 0; i < NOPS; ++i) x[gq][i] = 0.0;
+            for (int a = 0; a < P1; ++a) D[gq][0][a] = D[gq][1][a] = 0.0;
+        }
+        if (s < prm.s_end) {
+            for (int gq = 0; gq < Q; ++gq) {
+                pb_static_for<0, NOPS>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    x[gq][i] = prm.in[i][(Plan::op(i).tr ? lo.in_tr : lo.in) + (long long)(s * Q + gq)];
+                });
+                const double* Vn = prm.V2 + (long long)(s * Q + gq) * 2 * P1;
+                for (int a = 0; a < P1; ++a) { D[gq][0][a] = Vn[a]; D[gq][1][a] = Vn[P1 + a]; }
+            }
+        }
+        pb_span_block<Plan, P, Q>(x, D, Ls[lane]);
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+        if (batch > 0 && lane < P) continue;
+        const int m = f0 + (sb - prm.s_begin) + lane;
+        if (m >= prm.N) continue;
+        const int* rm = prm.ret_mu + (long long)m * (2 * P + 1);
+        for (int k = 0; k <= 2 * P; ++k) {
+            if (rm[k] < 0) continue;
+            const int d = (k <= P) ? k : k - P;
+            double sum = 0.0;
+            for (int t = 0; t <= P - d; ++t)
+                if (lane - t >= 0) sum += (k <= P) ? Ls[lane - t][t][t + d] : Ls[lane - t][t + d][t];
+            prm.out[0][lo.out + (long long)(rm[k] - prm.mu_base)] = sum;
+        }
+    }
+}
+
+#if defined(__CUDACC__)
+// grid.x: groups of `lines_per_warp` lines, 4 warps per block; grid.y: batch
+template <class Plan, int P, int Q>
+__global__ void __launch_bounds__(128) pb_lane_span_kernel(const __grid_constant__ PbWalkParams prm, int lines_per_warp) {
+    constexpr int P1 = P + 1, NOPS = Plan::NOPS;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int batch = blockIdx.y;
+    const long long line0 = warp * lines_per_warp;
+    if (line0 >= prm.nthreads) return;
+    const long long line1 = (line0 + lines_per_warp < prm.nthreads) ? line0 + lines_per_warp : prm.nthreads;
+
+    const int sb = prm.s_begin + batch * (32 - P);
+    const int s = sb + lane;
+    const bool active = s < prm.s_end;
+    const int m = prm.first[prm.s_begin] + (sb - prm.s_begin) + lane;
+    const bool writer = (batch == 0 || lane >= P) && m < prm.N;
+
+    double D[Q][2][P1];
+#pragma unroll
+    for (int gq = 0; gq < Q; ++gq) {
+        const double* Vn = prm.V2 + (long long)((active ? s : prm.s_begin) * Q + gq) * 2 * P1;
+#pragma unroll
+        for (int a = 0; a < P1; ++a) {
+            D[gq][0][a] = active ? __ldg(Vn + a) : 0.0;
+            D[gq][1][a] = active ? __ldg(Vn + P1 + a) : 0.0;
+        }
+    }
+    int mu[2 * P + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * P; ++k) mu[k] = writer ? __ldg(prm.ret_mu + (long long)m * (2 * P + 1) + k) : -1;
+
+    const long long node0 = (long long)(active ? s : prm.s_begin) * Q;
+    double xn[Q][NOPS];
+    auto load_line = [&](long long line, PbLineOffsets& lo) {
+        lo = pb_decode_line<Plan>(prm, line);
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+            pb_static_for<0, NOPS>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                xn[gq][i] = (active && lo.keep) ? prm.in[i][(Plan::op(i).tr ? lo.in_tr : lo.in) + node0 + gq] : 0.0;
+            });
+    };
+    PbLineOffsets lo_next;
+    load_line(line0, lo_next);
+    for (long long line = line0; line < line1; ++line) {
+        const PbLineOffsets lo = lo_next;
+        double x[Q][NOPS];
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+            pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; x[gq][i] = xn[gq][i]; });
+        if (line + 1 < line1) load_line(line + 1, lo_next);
+        if (!lo.keep) continue;             // warp-uniform
+        double L[P1][P1];
+        pb_span_block<Plan, P, Q>(x, D, L);
+        // gather the blocks of the left neighbours
+#pragma unroll
+        for (int k = 0; k <= 2 * P; ++k) {
+            const int d = (k <= P) ? k : k - P;
+            double sum = (k <= P) ? L[0][d] : L[d][0];
+#pragma unroll
+            for (int t = 1; t <= P; ++t) {
+                if (t <= P - d) {
+                    const double vsh = __shfl_up_sync(0xffffffffu, (k <= P) ? L[t][t + d] : L[t + d][t], t);
+                    if (lane >= t) sum += vsh;
+                }
+            }
+            if (mu[k] >= 0) prm.out[0][lo.out + (long long)(mu[k] - prm.mu_base)] = sum;
+        }
+    }
+}
+#endif

@@ -30,8 +30,28 @@ int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* strea
 #endif
 }
 
+template <class Plan>
+int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* stream) {
+    const int nb = pb_lane_batches(prm->s_end - prm->s_begin, PB_P);
+#ifdef PB_EMULATE
+    (void)stream; (void)lines_per_warp;
+    for (int b = 0; b < nb; ++b)
+        pb_emu_for(prm->nthreads, [&](long long line) { pb_lane_span_seq<Plan, PB_P, PB_Q>(*prm, line, b); });
+    return 0;
+#else
+    const long long warps = (prm->nthreads + lines_per_warp - 1) / lines_per_warp;
+    const long long blocks = (warps + 3) / 4;
+    if (blocks <= 0) return 0;
+    dim3 grid((unsigned)blocks, (unsigned)nb);
+    pb_lane_span_kernel<Plan, PB_P, PB_Q><<<grid, 128, 0, (cudaStream_t)stream>>>(*prm, lines_per_warp);
+    return (int)cudaGetLastError();
+#endif
+}
+
 struct Registrar {
     Registrar() {
+        pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_COPY, PB_P, PB_Q, &launch_lane<PbPlanCopy>);
+        pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_FINAL4, PB_P, PB_Q, &launch_lane<PbPlanFinal4>);
         pb200_register_walk(PB_PLAN_COPY, PB_P, PB_Q, &launch<PbPlanCopy>);
         pb200_register_walk(PB_PLAN_FINAL4, PB_P, PB_Q, &launch<PbPlanFinal4>);
         pb200_register_walk(PB_PLAN_S1A, PB_P, PB_Q, &launch<PbPlanS1A>);

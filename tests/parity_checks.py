@@ -163,3 +163,23 @@ def check_operators(ref):
     np.testing.assert_allclose(A @ ref['mv_x'], ref['mv_y'], rtol=1e-13, atol=1e-13)
     facs = [ref['kron_A%d' % k] for k in range(3)]
     np.testing.assert_allclose(KroneckerOperator(*facs).dot(ref['kron_x']), ref['kron_y'], rtol=1e-13, atol=1e-13)
+
+
+def check_vs_oracle(dim, ps, ns, form, geo_name='nurbs', mult=1, force_walk=False, rtol=RTOL):
+    """any space: the device pipeline against the oracle's closed form (the oracle is pinned to the
+    reference by tests/test_oracle.py)"""
+    from pyiga_b200 import assemblers, bspline, geometry
+    kvs = tuple(bspline.make_knots(p, 0.0, 1.0, n, mult=mult) for p, n in zip(ps, ns))
+    if dim == 2:
+        geo = geometry.quarter_annulus() if geo_name == 'nurbs' else geometry.bspline_quarter_annulus()
+    else:
+        geo = geometry.twisted_nurbs_box() if geo_name == 'nurbs' else geometry.twisted_box()
+    asm = getattr(assemblers, '%sAssembler%dD' % (form, dim))(kvs, geo)
+    if force_walk:
+        asm.dev.set_option('force_walk', 1)
+    got = asm.dev.be.to_host(asm.dev.assemble_mlb())
+    prob = orc.Problem([kv.kv for kv in kvs], list(ps), [kv.kv for kv in geo.kvs], [kv.p for kv in geo.kvs],
+                       geo.coeffs, geo._rational)
+    want = orc.assemble_mlb(prob, form.lower()).ravel()
+    assert_close_rel(got, want, rtol=rtol, what='%s %dD p=%s n=%s' % (form, dim, ps, ns))
+    return asm

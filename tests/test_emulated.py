@@ -53,3 +53,20 @@ def test_golden(emu, dim):
 
 def test_operators(emu, ref):
     pc.check_operators(ref)
+
+
+@pytest.mark.parametrize('force_walk', [False, True])
+@pytest.mark.parametrize('ps,ns', [((2, 2), (4, 70)), ((3, 1), (5, 33)), ((1, 4), (3, 29))])
+def test_long_last_axis_2d(emu, ps, ns, force_walk):
+    """more than one 32-span batch of the warp-per-line final stage (and the plain walk kernel)"""
+    pc.check_vs_oracle(2, ps, ns, 'Stiffness', force_walk=force_walk)
+    pc.check_vs_oracle(2, ps, ns, 'Mass', force_walk=force_walk)
+
+
+def test_long_last_axis_3d(emu):
+    pc.check_vs_oracle(3, (2, 2, 3), (2, 3, 31), 'Stiffness')
+
+
+def test_repeated_knots_use_walk_kernel(emu):
+    pc.check_vs_oracle(2, (3, 3), (4, 20), 'Stiffness', mult=2)
+    pc.check_vs_oracle(3, (2, 2, 2), (3, 2, 12), 'Mass', mult=2, geo_name='bspline')
