@@ -1,0 +1,98 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/pyiga_b200.h declares;
+host-only entry points work; the package refuses to run without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, 'include', 'pyiga_b200.h')).read()
+    return sorted(set(re.findall(r'PB200_API\s+[\w\s\*]+?\b(pb200_\w+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyiga_b200 import _lib
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.SIGNATURES) == names, 'ctypes prototypes out of sync with the header'
+    assert lib.pb200_version() >= 100
+
+
+def test_host_only_band_structure(ref):
+    from pyiga_b200 import _lib, bspline
+    from pyiga_b200.mlmatrix import compute_sparsity_ij
+    lib = _lib.load()
+    for p, n, mult in [(3, 7, 1), (2, 5, 2), (4, 3, 3), (1, 6, 1)]:
+        kv = bspline.make_knots(p, 0.0, 1.0, n, mult=mult)
+        cnt = C.c_int()
+        rc = lib.pb200_band_structure(_lib.as_double_p(kv.kv), kv.kv.size, p, None, 0, 0, None, C.byref(cnt))
+        assert rc == 0
+        out = np.empty((cnt.value, 2), dtype=np.uint32)
+        lib.pb200_band_structure(_lib.as_double_p(kv.kv), kv.kv.size, p, None, 0, 0, out.ctypes.data, C.byref(cnt))
+        assert np.array_equal(out, compute_sparsity_ij(kv, kv))
+    # two different spaces on one mesh (Petrov-Galerkin pattern)
+    ku, kv_ = bspline.make_knots(3, 0.0, 1.0, 6), bspline.make_knots(2, 0.0, 1.0, 6)
+    cnt = C.c_int()
+    lib.pb200_band_structure(_lib.as_double_p(ku.kv), ku.kv.size, 3, _lib.as_double_p(kv_.kv), kv_.kv.size, 2, None,
+                             C.byref(cnt))
+    out = np.empty((cnt.value, 2), dtype=np.uint32)
+    lib.pb200_band_structure(_lib.as_double_p(ku.kv), ku.kv.size, 3, _lib.as_double_p(kv_.kv), kv_.kv.size, 2,
+                             out.ctypes.data, C.byref(cnt))
+    assert np.array_equal(out, compute_sparsity_ij(ku, kv_))
+
+
+def test_error_reporting():
+    from pyiga_b200 import _lib
+    lib = _lib.load()
+    bad = np.array([0.0, 1.0, 0.5, 1.0])
+    rc = lib.pb200_band_structure(_lib.as_double_p(bad), 4, 1, None, 0, 0, None, None)
+    assert rc == -1 and b'increasing' in lib.pb200_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(lib, rc)
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device the product backend must refuse to start"""
+    import torch
+    from pyiga_b200 import _device
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    _device._backend = None
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        _device.backend()
+    from pyiga_b200 import assemble, bspline, geometry
+    kv = bspline.make_knots(2, 0.0, 1.0, 3)
+    with pytest.raises(RuntimeError):
+        assemble.mass((kv, kv), geometry.unit_square())
+
+
+def test_structures_match_reference(ref):
+    from helpers import CASES, make_space
+    from pyiga_b200.mlmatrix import MLStructure
+    for case in CASES:
+        kvs = make_space(ref, case)
+        S = MLStructure.from_kvs(kvs, kvs)
+        for k in range(S.L):
+            assert np.array_equal(S.bidx[k], ref['%s_bidx%d' % (case, k)])
+        I, J = S.nonzero()
+        assert I.dtype == np.uint64 and len(I) == np.prod([len(b) for b in S.bidx])
+        Il, Jl = S.nonzero(lower_tri=True)
+        assert np.all(Jl <= Il) and 2 * len(Il) - S.shape[0] == len(I)
+
+
+def test_knotvector_api():
+    from pyiga_b200 import bspline
+    kv = bspline.make_knots(3, 0.0, 1.0, 4, mult=2)
+    assert kv.numdofs == kv.kv.size - 4 and kv.numspans == 4
+    ms = kv.mesh_support_idx_all()
+    assert ms.shape == (kv.numdofs, 2) and ms[0, 0] == 0 and ms[-1, 1] == 4
+    assert kv.findspan(1.0) == kv.kv.size - 3 - 2 and kv.findspan(0.0) == 3
+    assert kv == kv.copy() and kv.refine().numspans == 8
