@@ -82,6 +82,12 @@ typedef struct {
  * slot 0 = function value, slot 1+k = derivative along tensor axis k (parametric). */
 typedef struct { int field, slot_test, slot_trial; } pb200_term;
 
+/* One physical coefficient term of a general first-order scalar form (see
+ * pb200_asm_compute_fields_general): slots 0 = value, 1+a = derivative w.r.t. physical coordinate a
+ * (x,y,z order); input = index of a coefficient array on the Gauss grid, or -1 for the constant 1;
+ * the coefficient is scale * input. */
+typedef struct { int slot_test, slot_trial, input; double scale; } pb200_phys_term;
+
 typedef struct {
     int dim;
     pb200_axis_desc axis[PB200_MAXDIM];
@@ -133,6 +139,18 @@ PB200_API int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc*
  * (slab-sharded assembly: every rank evaluates only its planes plus the p-span overlap) */
 PB200_API int pb200_asm_compute_fields_slab(pb200_assembler* a, const pb200_geo_desc* geo, int row0_begin,
                                             int row0_end, void* stream);
+/* Fields of a PB200_FORM_CUSTOM assembler for a general scalar form with at most first derivatives,
+ *     a(u,v) = int sum_t c_t(x) d^{slot_test} v d^{slot_trial} u dx   (physical derivatives),
+ * pulled back with J^-1 and weighted with GaussWeight*|det J| on the device; field f receives the
+ * coefficient of the parametric slot pair of the (unique) term that uses field f.  Replaces the
+ * generated precompute_fields of compiled vforms (pyiga/codegen/cython.py:673-701).  d_inputs are
+ * coefficient arrays on the full Gauss grid (user callables are evaluated on the host by the
+ * caller, exactly as pyiga does, pyiga/codegen/cython.py:465-484).  Give either `geo` or `d_jac`;
+ * row0_begin < 0 selects the whole grid. */
+PB200_API int pb200_asm_compute_fields_general(pb200_assembler* a, const pb200_geo_desc* geo, const double* d_jac,
+                                               int nphys, const pb200_phys_term* phys, int ninputs,
+                                               const double* const* d_inputs, int row0_begin, int row0_end,
+                                               void* stream);
 /* same, from Jacobians the caller evaluated on the Gauss grid (geometry objects that are not
  * splines): d_jac is [npoints][dim][dim] */
 PB200_API int pb200_asm_compute_fields_from_jacobian(pb200_assembler* a, const double* d_jac, void* stream);

@@ -33,6 +33,10 @@ class Term(C.Structure):
     _fields_ = [('field', C.c_int), ('slot_test', C.c_int), ('slot_trial', C.c_int)]
 
 
+class PhysTerm(C.Structure):
+    _fields_ = [('slot_test', C.c_int), ('slot_trial', C.c_int), ('input', C.c_int), ('scale', C.c_double)]
+
+
 class Desc(C.Structure):
     _fields_ = [('dim', C.c_int), ('axis', AxisDesc * MAXDIM), ('form', C.c_int),
                 ('nfields', C.c_int), ('nterms', C.c_int), ('terms', C.POINTER(Term)),
@@ -58,6 +62,9 @@ SIGNATURES = {
     'pb200_asm_bind_fields': (C.c_int, [C.c_void_p, C.c_void_p]),
     'pb200_asm_compute_fields': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_void_p]),
     'pb200_asm_compute_fields_slab': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_int, C.c_int, C.c_void_p]),
+    'pb200_asm_compute_fields_general': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_void_p, C.c_int,
+                                                   C.POINTER(PhysTerm), C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                                   C.c_int, C.c_void_p]),
     'pb200_asm_compute_fields_from_jacobian': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb200_geo_eval_grid': (C.c_int, [C.POINTER(GeoDesc), C.POINTER(C.c_int), C.POINTER(c_double_p),
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -115,7 +115,7 @@ def assemble(problem, kvs, args=None, bfuns=None, boundary=None, symmetric=False
     assembler class or assembler object (``pyiga/assemble.py:837-897``)."""
     args = dict() if args is None else args
     args.update(kwargs)
-    if hasattr(problem, 'arity') and not isinstance(problem, type):
+    if hasattr(problem, 'multi_entries') and not isinstance(problem, type):
         asm = problem
     else:
         asm = instantiate_assembler(problem, kvs, args, bfuns, boundary)

@@ -229,34 +229,10 @@ class DeviceAssembler:
         return out
 
 
-class _ScalarAssemblerBase:
-    """Protocol shared by the predefined scalar assemblers (``pyiga/genericasm.pxi:662-786``)."""
-    _form = None
-    _dim = None
+class _AssemblerProtocol:
+    """Methods every device assembler shares (``pyiga/genericasm.pxi:662-786``)."""
+    arity = 2
 
-    @classmethod
-    def inputs(cls):
-        return {'geo': (cls._dim,)}
-
-    @classmethod
-    def parameters(cls):
-        return {}
-
-    def __init__(self, kvs0, geo):
-        d = self._dim
-        assert geo.sdim == d, "Geometry has wrong source dimension"
-        assert geo.dim == d, "Geometry has wrong dimension"
-        kvs0 = tuple(kvs0)
-        assert len(kvs0) == d, "Assembler requires %d knot vectors" % d
-        self.arity = 2
-        self.nqp = max(kv.p for kv in kvs0) + 1
-        self._geo = geo
-        self.dev = DeviceAssembler(kvs0, kvs0, self._form, nqp=self.nqp)
-        self.dev.compute_fields(geo)
-        self.kvs = (kvs0, kvs0)
-        self.gaussgrid = self.dev.gaussgrid
-
-    # ---- reference protocol ------------------------------------------------------------------
     def entry(self, i, j):
         """A[i, j] = a(phi_j, phi_i): row index decoded in the test space, column in the trial space."""
         return float(self.multi_entries(np.array([[i, j]], dtype=np.uint64))[0])
@@ -290,6 +266,176 @@ class _ScalarAssemblerBase:
         """The whole matrix as ``scipy.sparse.csr_matrix`` (float64 data, int32 indices, sorted)."""
         data = self.dev.assemble_mlb(**kw)
         return self.dev.device_structure.to_csr(data)
+
+
+class _ScalarAssemblerBase(_AssemblerProtocol):
+    """The predefined scalar assemblers."""
+    _form = None
+    _dim = None
+
+    @classmethod
+    def inputs(cls):
+        return {'geo': (cls._dim,)}
+
+    @classmethod
+    def parameters(cls):
+        return {}
+
+    def __init__(self, kvs0, geo):
+        d = self._dim
+        assert geo.sdim == d, "Geometry has wrong source dimension"
+        assert geo.dim == d, "Geometry has wrong dimension"
+        kvs0 = tuple(kvs0)
+        assert len(kvs0) == d, "Assembler requires %d knot vectors" % d
+        self.arity = 2
+        self.nqp = max(kv.p for kv in kvs0) + 1
+        self._geo = geo
+        self.dev = DeviceAssembler(kvs0, kvs0, self._form, nqp=self.nqp)
+        self.dev.compute_fields(geo)
+        self.kvs = (kvs0, kvs0)
+        self.gaussgrid = self.dev.gaussgrid
+
+
+class GenericFormAssembler(_AssemblerProtocol):
+    """Assembler of a scalar bilinear form described by a :class:`~pyiga_b200.vform.VForm`
+    (base of the classes returned by :func:`~pyiga_b200.vform.compile_vform`).
+
+    Mirrors the generated assembler classes of the reference (``pyiga/codegen/cython.py:509-744``):
+    construction evaluates the input functions on the Gauss grid (physical callables at the mapped
+    points, spline functions on the parameter grid), ``update(name=func)`` re-evaluates one input.
+    """
+    _vf = None
+
+    def __init__(self, kvs, **args):
+        vf = self._vf
+        kvs = tuple(kvs)
+        d = vf.dim
+        assert len(kvs) == d, "Assembler requires %d knot vectors" % d
+        geo = args['geo']
+        assert geo.sdim == d, "Geometry has wrong source dimension"
+        assert geo.dim == d, "Geometry has wrong dimension"
+        self.arity = vf.arity
+        self.nqp = max(kv.p for kv in kvs) + 1
+        self.kvs = (kvs, kvs)
+        self._geo = geo
+        self._args = dict(args)
+        self.gaussgrid, _ = make_tensor_quadrature([kv.mesh for kv in kvs], self.nqp)
+        self._grid_shape = tuple(len(g) for g in self.gaussgrid)
+        self._X = None
+        self._env = {}
+        for name, shape, physical, _upd in vf.inputs:
+            self._env[name] = self._eval_input(args[name], shape, physical)
+        for name, shape in vf.params:
+            self._env[name] = np.asarray(args[name], dtype=float)
+        if any(_mentions_x(e) for e in vf.exprs):
+            X = self._physical_points()
+            self._env['@x'] = np.stack([X[..., i] for i in range(d)])
+        coefs = self._analyse()
+        self._keys = sorted(coefs)
+        pairs = set()
+        for (bt, bu) in self._keys:
+            for bp in ([0] if bt == 0 else range(1, d + 1)):
+                for ap in ([0] if bu == 0 else range(1, d + 1)):
+                    pairs.add((bp, ap))
+        self._pairs = sorted(pairs)
+        terms = [(f, bp, ap) for f, (bp, ap) in enumerate(self._pairs)]
+        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=self.nqp, terms=terms, nfields=len(terms))
+        self._compute_fields(coefs)
+
+    # ---- input evaluation (host side, like the reference) ------------------------------------
+    def _physical_points(self):
+        if self._X is None:
+            geo = self._geo
+            self._X = np.asarray(geo.grid_eval(self.gaussgrid))     # device evaluation for spline geometries
+        return self._X
+
+    def _eval_input(self, f, shape, physical):
+        from .vform import _grid_values
+        if not physical:        # spline function: parametric, evaluated on the Gauss grid
+            vals = np.asarray(f.grid_eval(self.gaussgrid))
+            return np.moveaxis(vals, tuple(range(len(self._grid_shape), vals.ndim)), tuple(range(len(shape)))) \
+                if shape else vals
+        X = self._physical_points()
+        coords = tuple(X[..., i] for i in range(X.shape[-1]))
+        vals = _grid_values(f, shape, coords, self._grid_shape)
+        if shape == ():
+            return np.ascontiguousarray(vals)
+        return np.stack([np.ascontiguousarray(v) for v in vals.ravel()]).reshape(shape + self._grid_shape)
+
+    def _analyse(self):
+        """evaluate the expression trees symbolically: {(test slot, trial slot): Coef}"""
+        total = None
+        for e in self._vf.exprs:
+            val = e.ev(self._env)[()]
+            total = val if total is None else total + val
+        coefs = {}
+        for (bt, bu), c in total.terms.items():
+            if bt is None or bu is None:
+                raise ValueError('the form must be linear in both u and v (term without %s)' % ('v' if bt is None else 'u'))
+            if not c.is_zero():
+                coefs[(bt, bu)] = c
+        if not coefs:
+            raise ValueError('the form is identically zero')
+        return coefs
+
+    def _compute_fields(self, coefs):
+        dev, be = self.dev, self.dev.be
+        if sorted(coefs) != self._keys:
+            raise RuntimeError('update() changed the structure of the form')
+        arrays, index = [], {}
+        phys = (_lib.PhysTerm * len(coefs))()
+        for t, key in enumerate(self._keys):
+            c = coefs[key]
+            inp = -1
+            if c.arr is not None:
+                if id(c.arr) not in index:
+                    index[id(c.arr)] = len(arrays)
+                    arr = np.ascontiguousarray(np.broadcast_to(c.arr, self._grid_shape), dtype=np.float64)
+                    arrays.append(be.from_host(arr.ravel()))
+                inp = index[id(c.arr)]
+            phys[t] = _lib.PhysTerm(key[0], key[1], inp, c.scale)
+        ptrs = (C.c_void_p * max(len(arrays), 1))(*[be.ptr(a) for a in arrays])
+        geo = self._geo
+        if _is_spline_geo(geo):
+            desc, keep = _lib.make_geo_desc(geo)
+            _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, C.byref(desc), None, len(coefs), phys,
+                                                                   len(arrays), ptrs, -1, -1, be.stream()))
+        else:
+            jac = np.ascontiguousarray(geo.grid_jacobian(self.gaussgrid), dtype=np.float64)
+            d_jac = be.from_host(jac.ravel())
+            _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, None, be.ptr(d_jac), len(coefs), phys,
+                                                                   len(arrays), ptrs, -1, -1, be.stream()))
+        be.synchronize()        # the uploaded coefficient arrays may be released now
+
+    def update(self, **kwargs):
+        """Re-evaluate the given input functions (``pyiga/codegen/cython.py:703-724``)."""
+        known = {name: (shape, physical) for name, shape, physical, _ in self._vf.inputs}
+        for name, f in kwargs.items():
+            if name == 'geo':
+                self._geo, self._X = f, None
+                self._args['geo'] = f
+                for n2, (shape, physical) in known.items():     # physical inputs move with the geometry
+                    if physical:
+                        self._env[n2] = self._eval_input(self._args[n2], shape, physical)
+                if '@x' in self._env:
+                    X = self._physical_points()
+                    self._env['@x'] = np.stack([X[..., i] for i in range(self._vf.dim)])
+                continue
+            if name not in known:
+                raise ValueError("unknown input '%s'" % name)
+            self._args[name] = f
+            self._env[name] = self._eval_input(f, *known[name])
+        self._compute_fields(self._analyse())
+
+    def update_params(self, **kwargs):
+        for name, v in kwargs.items():
+            self._env[name] = np.asarray(v, dtype=float)
+        self._compute_fields(self._analyse())
+
+
+def _mentions_x(expr):
+    from .vform import _mentions
+    return _mentions(expr, '@x')
 
 
 class MassAssembler2D(_ScalarAssemblerBase):

@@ -1,6 +1,7 @@
 // C ABI of pyiga_b200 (see include/pyiga_b200.h): host-side table construction, kernel launches.
 #include "backend.cuh"
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdarg>
@@ -337,6 +338,7 @@ struct pb200_assembler {
     Pool pool;
     double* d_fields = nullptr;
     std::vector<PbTerm> terms;
+    std::vector<std::pair<int, int>> field_slots;       // custom forms: (test slot, trial slot) of field f
     void* geo_scratch = nullptr;
     long long npts = 0, nnz = 0;
     int fast = 0;
@@ -413,6 +415,11 @@ static int detect_fast_path(const pb200_assembler* a) {
     if (a->form == PB200_FORM_MASS) {
         for (int k = 0; k < a->dim; ++k)
             if (!have_plan(PB_PLAN_COPY, P(k), Q)) return 0;
+        return 1;
+    }
+    if (a->form == PB200_FORM_CUSTOM) {
+        for (int k = 0; k < a->dim; ++k)
+            if (!have_plan(PB_PLAN_GEN4, P(k), Q) || !have_plan(PB_PLAN_COPY, P(k), Q)) return 0;
         return 1;
     }
     if (a->form == PB200_FORM_STIFFNESS) {
@@ -529,6 +536,17 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
                 return fail(PB200_EINVAL, "invalid term %d", t);
             a->terms.push_back(PbTerm{T.field, T.slot_test, T.slot_trial});
         }
+        a->field_slots.assign(a->nfields, std::make_pair(-1, -1));
+        for (const PbTerm& T : a->terms) {
+            if (a->field_slots[T.field].first >= 0) return fail(PB200_EINVAL, "field %d is used by more than one term", T.field);
+            a->field_slots[T.field] = std::make_pair(T.bt, T.bu);
+        }
+        for (int f = 0; f < a->nfields; ++f)
+            if (a->field_slots[f].first < 0) return fail(PB200_EINVAL, "field %d is not used by any term", f);
+        for (size_t i = 0; i < a->terms.size(); ++i)
+            for (size_t j = i + 1; j < a->terms.size(); ++j)
+                if (a->terms[i].bt == a->terms[j].bt && a->terms[i].bu == a->terms[j].bu)
+                    return fail(PB200_EINVAL, "duplicate term (slots %d,%d): merge the coefficients", a->terms[i].bt, a->terms[i].bu);
     }
 
     // ---- upload ---------------------------------------------------------------------------------
@@ -756,14 +774,38 @@ static int launch_fields(const PbFieldParams& prm, pbStream st) {
     return 0;
 }
 
+struct GeneralSpec {
+    int nphys = 0;
+    const pb200_phys_term* phys = nullptr;
+    int ninputs = 0;
+    const double* const* d_inputs = nullptr;
+};
+
 static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, const double* d_jac, pbStream st,
-                               int row0_begin = -1, int row0_end = -1) {
+                               int row0_begin = -1, int row0_end = -1, const GeneralSpec* gen = nullptr) {
     if (!a) return fail(PB200_EINVAL, "null handle");
     if (!a->d_fields) return fail(PB200_EINVAL, "no field buffer bound (pb200_asm_bind_fields)");
-    if (a->form == PB200_FORM_CUSTOM) return fail(PB200_EINVAL, "custom forms upload their fields");
+    if ((a->form == PB200_FORM_CUSTOM) != (gen != nullptr))
+        return fail(PB200_EINVAL, a->form == PB200_FORM_CUSTOM ? "custom forms need pb200_asm_compute_fields_general"
+                                                                : "built-in forms compute their own fields");
     CK(pbSetDevice(a->device));
     PbFieldParams prm;
     memset(&prm, 0, sizeof prm);
+    if (gen) {
+        if (gen->nphys < 1 || gen->nphys > PB_MAXFIELDS || !gen->phys) return fail(PB200_EINVAL, "invalid number of coefficient terms %d", gen->nphys);
+        if (gen->ninputs < 0 || gen->ninputs > PB_MAXFIELDS) return fail(PB200_EINVAL, "invalid number of input arrays %d", gen->ninputs);
+        prm.nphys = gen->nphys;
+        for (int t = 0; t < gen->nphys; ++t) {
+            const pb200_phys_term& T = gen->phys[t];
+            if (T.slot_test < 0 || T.slot_test > a->dim || T.slot_trial < 0 || T.slot_trial > a->dim || T.input >= gen->ninputs)
+                return fail(PB200_EINVAL, "invalid coefficient term %d", t);
+            prm.phys[t].bt = T.slot_test; prm.phys[t].bu = T.slot_trial;
+            prm.phys[t].input = T.input < 0 ? -1 : T.input;
+            prm.phys[t].scale = T.scale;
+        }
+        for (int i = 0; i < gen->ninputs; ++i) prm.inputs[i] = gen->d_inputs[i];
+        for (int c = 0; c < a->nfields; ++c) { prm.outmap[c].bp = a->field_slots[c].first; prm.outmap[c].ap = a->field_slots[c].second; }
+    }
     prm.dim = a->dim;
     const double* d_nodes[PB_MAXDIM] = {nullptr, nullptr, nullptr};
     int G[PB_MAXDIM] = {1, 1, 1};
@@ -794,6 +836,20 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
         prm.geo = T.dev;
     }
     const bool mass = a->form == PB200_FORM_MASS;
+    if (gen) {
+        if (!d_jac) {
+            const long long lastG = a->hax[a->dim - 1].G;
+            const long long r0 = prm.pt_begin / lastG, r1 = prm.pt_end / lastG;
+            const bool rat = prm.geo.rational != 0;
+            int rc;
+            if (a->dim == 2) rc = rat ? k_fields_rows<2, 3, PbProgGeneral<2>>(prm, r0, r1, st) : k_fields_rows<2, 2, PbProgGeneral<2>>(prm, r0, r1, st);
+            else rc = rat ? k_fields_rows<3, 4, PbProgGeneral<3>>(prm, r0, r1, st) : k_fields_rows<3, 3, PbProgGeneral<3>>(prm, r0, r1, st);
+            if (rc) return rc;
+            CK(pbLastError());
+            return 0;
+        }
+        return a->dim == 2 ? launch_fields<2, PbProgGeneral<2>>(prm, st) : launch_fields<3, PbProgGeneral<3>>(prm, st);
+    }
     if (!d_jac) {
         // spline geometry: row-wise sum-factorised evaluation
         const long long lastG = a->hax[a->dim - 1].G;
@@ -822,6 +878,14 @@ extern "C" int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc
 extern "C" int pb200_asm_compute_fields_slab(pb200_assembler* a, const pb200_geo_desc* geo, int row0_begin, int row0_end,
                                              void* stream) {
     return compute_fields_impl(a, geo, nullptr, (pbStream)stream, row0_begin, row0_end);
+}
+extern "C" int pb200_asm_compute_fields_general(pb200_assembler* a, const pb200_geo_desc* geo, const double* d_jac,
+                                                int nphys, const pb200_phys_term* phys, int ninputs,
+                                                const double* const* d_inputs, int row0_begin, int row0_end, void* stream) {
+    GeneralSpec g;
+    g.nphys = nphys; g.phys = phys; g.ninputs = ninputs; g.d_inputs = d_inputs;
+    if (!geo && !d_jac) return fail(PB200_EINVAL, "geometry missing");
+    return compute_fields_impl(a, d_jac ? nullptr : geo, d_jac, (pbStream)stream, row0_begin, row0_end, &g);
 }
 extern "C" int pb200_asm_compute_fields_from_jacobian(pb200_assembler* a, const double* d_jac, void* stream) {
     if (!d_jac) return fail(PB200_EINVAL, "null Jacobian array");
@@ -891,10 +955,51 @@ static int make_slab(const pb200_assembler* a, int ra, int rb, bool sym, Slab& S
 
 static bool uses_transposes(const pb200_assembler* a) { return a->form == PB200_FORM_STIFFNESS; }
 
+// generic forms: a term travels through the stages as (test slot, trial slot, buffer slot)
+struct GenTerm { int bt, bu, slot; };
+struct GenStage {
+    std::vector<GenTerm> out;                    // outputs (slot = index in the stage's output buffer)
+    std::vector<std::array<int, 4>> ops;         // per output: input slot for (ft,fu) = 00,01,10,11 or -1
+};
+// contract `axis`: derivative slot 1+axis turns into the value slot
+static GenStage plan_generic_stage(const std::vector<GenTerm>& in, int axis) {
+    GenStage S;
+    for (const GenTerm& t : in) {
+        const int ft = t.bt == 1 + axis, fu = t.bu == 1 + axis;
+        const int bt = ft ? 0 : t.bt, bu = fu ? 0 : t.bu;
+        size_t o = 0;
+        for (; o < S.out.size(); ++o)
+            if (S.out[o].bt == bt && S.out[o].bu == bu) break;
+        if (o == S.out.size()) {
+            S.out.push_back(GenTerm{bt, bu, (int)o});
+            S.ops.push_back({-1, -1, -1, -1});
+        }
+        S.ops[o][ft * 2 + fu] = t.slot;
+    }
+    return S;
+}
+static void generic_plan(const pb200_assembler* a, std::vector<GenStage>& stages) {
+    std::vector<GenTerm> cur;
+    for (const PbTerm& t : a->terms) cur.push_back(GenTerm{t.bt, t.bu, t.field});
+    for (int k = 0; k < a->dim; ++k) {
+        stages.push_back(plan_generic_stage(cur, k));
+        cur = stages.back().out;
+    }
+}
+
 static void stage_sizes(const pb200_assembler* a, const Slab& S, size_t& x1_terms, size_t& x1_stride, size_t& x2_terms,
                         size_t& x2_stride) {
     const size_t Mext = (size_t)(S.ext_hi - S.ext_lo);
     const bool st = a->form == PB200_FORM_STIFFNESS;
+    if (a->form == PB200_FORM_CUSTOM) {
+        std::vector<GenStage> stages;
+        generic_plan(a, stages);
+        x1_terms = stages[0].out.size();
+        x1_stride = Mext * a->hax[1].G * (a->dim == 3 ? a->hax[2].G : 1);
+        x2_terms = a->dim == 3 ? stages[1].out.size() : 0;
+        x2_stride = a->dim == 3 ? Mext * a->hax[1].M * a->hax[2].G : 0;
+        return;
+    }
     if (a->dim == 2) {
         x1_terms = st ? 3 : 1;
         x1_stride = Mext * a->hax[1].G;
@@ -981,6 +1086,60 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.V = 1; p.X = 1;
         return p;
     };
+
+    if (a->form == PB200_FORM_CUSTOM) {
+        // ---- generic scalar form: one GEN4 / COPY launch per output term of every stage -------
+        std::vector<GenStage> stages;
+        generic_plan(a, stages);
+        const int dim = a->dim;
+        const long long Glast = dim == 3 ? a->hax[2].G : 1;
+        for (int k = 0; k < dim; ++k) {
+            const GenStage& G = stages[k];
+            const bool last = (k == dim - 1);
+            for (size_t o = 0; o < G.out.size(); ++o) {
+                PbWalkParams p = base_params();
+                const double* inbase = (k == 0) ? F : (k == 1 ? X1 : X2);
+                const long long instride = (k == 0) ? npts : (k == 1 ? (long long)s1 : (long long)s2);
+                double* outbase = last ? d_out : (k == 0 ? X1 : X2);
+                const long long outstride = last ? 0 : (k == 0 ? (long long)s1 : (long long)s2);
+                for (int c = 0; c < 4; ++c) p.in[c] = G.ops[o][c] >= 0 ? inbase + (long long)G.ops[o][c] * instride : nullptr;
+                p.out[0] = outbase + (long long)o * outstride;
+                if (k == 0) {               // axis 0: lines are the points of the trailing grid axes
+                    p.X = (int)(G1 * Glast); p.nthreads = G1 * Glast;
+                    p.in_sx = 1; p.in_sc = G1 * Glast;
+                    p.out_sx = 1; p.out_smu = G1 * Glast; p.mu_base = S.mu_lo;
+                    p.s_begin = S.sa; p.s_end = S.sb;
+                    p.w_mode = 1; p.w_lo = S.ra; p.w_hi = S.rb;
+                } else if (k == 1 && dim == 3) {
+                    p.X = (int)Glast; p.nthreads = (long long)Mrows * Glast;
+                    p.u_begin = S.mu_lo; p.u_base_in = S.mu_lo; p.u_base_out = S.mu_lo;
+                    p.in_su = G1 * Glast; p.in_sx = 1; p.in_sc = Glast;
+                    p.out_su = M1 * Glast; p.out_sx = 1; p.out_smu = Glast; p.mu_base = 0;
+                    p.s_begin = 0; p.s_end = H1.n;
+                } else if (dim == 2) {      // final stage in 2D: axis 1
+                    p.nthreads = Mrows;
+                    p.u_begin = S.mu_lo; p.u_base_in = S.mu_lo; p.u_base_out = S.mu_lo;
+                    p.in_su = G1; p.in_sc = 1;
+                    p.out_su = M1; p.out_smu = 1; p.mu_base = 0;
+                    p.s_begin = 0; p.s_end = H1.n;
+                } else {                    // final stage in 3D: axis 2
+                    const long long M2g = a->hax[2].M;
+                    p.V = (int)M1; p.nthreads = (long long)Mrows * M1;
+                    p.u_begin = S.mu_lo; p.u_base_in = S.mu_lo; p.u_base_out = S.mu_lo;
+                    p.in_su = M1 * Glast; p.in_sv = Glast; p.in_sc = 1;
+                    p.out_su = M1 * M2g; p.out_sv = M2g; p.out_smu = 1; p.mu_base = 0;
+                    p.s_begin = 0; p.s_end = a->hax[2].n;
+                }
+                const bool copy_only = G.ops[o][1] < 0 && G.ops[o][2] < 0 && G.ops[o][3] < 0;
+                char nm[32];
+                snprintf(nm, sizeof nm, "g%d_%s%d", k + 1, copy_only ? "copy" : "gen", (int)o);
+                rc = run_stage(copy_only ? PB_PLAN_COPY : PB_PLAN_GEN4, a, k, p, st, nm);
+                if (rc) return rc;
+            }
+        }
+        mark_stage(a, "end", st);
+        return 0;
+    }
 
     if (a->dim == 2) {
         // stage 1: axis 0,  fields[f][g0][g1] -> X1[t][mu0 - ext_lo][g1]

@@ -39,8 +39,11 @@ struct PbFieldParams {
     long long npts;                 // points of the whole grid (stride between fields)
     long long pt_begin, pt_end;     // linear range of points evaluated by this launch
     int nf;
-    const double* inputs[PB_MAXFIELDS];  // user-supplied input fields on the Gauss grid, [ncomp][pts]
-    const double* consts;                // parameters of the form
+    // general first-order scalar forms (PbProgGeneral): physical coefficient terms and output map
+    const double* inputs[PB_MAXFIELDS];  // coefficient arrays on the Gauss grid (null: constant 1)
+    int nphys;
+    struct { int bt, bu, input; double scale; } phys[PB_MAXFIELDS];   // slots: 0 value, 1+a d/dx_a
+    struct { int bp, ap; } outmap[PB_MAXFIELDS];                      // parametric slots of field f
 };
 
 struct PbPoint {        // what a field program sees at one Gauss point
@@ -173,6 +176,37 @@ template <int DIM> struct PbProgStiffness {
     }
 };
 
+// General scalar bilinear form with at most first derivatives on u and v:
+//     a(u,v) = int sum_t c_t(x) d^{bt} v d^{bu} u dx,   slots: 0 = value, 1+a = d/dx_a (physical)
+// pulled back to the parameter domain: d/dx_a = sum_j Jinv[j][a] d/dxi_j, xi_j = tensor axis DIM-1-j.
+// Output field f holds the coefficient of the parametric slot pair outmap[f]:
+//     C[bp][ap] = W * sum_t c_t T[bt][bp] T[bu][ap],  T[0][0] = 1,  T[1+a][1+k] = Jinv[DIM-1-k][a].
+// This is what the reference's generated precompute_fields computes for such forms
+// (pyiga/codegen/cython.py:673-701 on the finalized VForm, pyiga/vform.py:705-731).
+template <int DIM> struct PbProgGeneral {
+    static constexpr int NF = PB_MAXFIELDS;
+    static constexpr bool NEED_X = false;
+    PB_HD static void run(const PbFieldParams& prm, const PbPoint& pt, double* f) {
+        const double det = pb_det<DIM>(pt.J);
+        const double W = pt.gw * fabs(det);
+        double I[3][3];
+        pb_inv<DIM>(pt.J, det, I);
+        double T[DIM + 1][DIM + 1];
+        for (int a = 0; a <= DIM; ++a)
+            for (int b = 0; b <= DIM; ++b) T[a][b] = 0.0;
+        T[0][0] = 1.0;
+        for (int a = 0; a < DIM; ++a)
+            for (int k = 0; k < DIM; ++k) T[1 + a][1 + k] = I[DIM - 1 - k][a];
+        for (int c = 0; c < prm.nf; ++c) f[c] = 0.0;
+        for (int t = 0; t < prm.nphys; ++t) {
+            const int in = prm.phys[t].input;
+            const double cv = W * prm.phys[t].scale * (in >= 0 ? prm.inputs[in][pt.idx] : 1.0);
+            for (int c = 0; c < prm.nf; ++c)
+                f[c] = fma(cv, T[prm.phys[t].bt][prm.outmap[c].bp] * T[prm.phys[t].bu][prm.outmap[c].ap], f[c]);
+        }
+    }
+};
+
 // raw geometry data (debug / host callbacks): J row-major (DIM*DIM), then x (DIM)
 template <int DIM> struct PbProgGeoRaw {
     static constexpr int NF = DIM * DIM + DIM;
@@ -202,7 +236,7 @@ PB_HD void pb_fields_point(const PbFieldParams& prm, long long idx) {
     }
     double f[Prog::NF];
     Prog::run(prm, pt, f);
-    for (int c = 0; c < Prog::NF; ++c) prm.fields[(long long)c * prm.npts + idx] = f[c];
+    for (int c = 0; c < Prog::NF && c < prm.nf; ++c) prm.fields[(long long)c * prm.npts + idx] = f[c];
 }
 
 // ---- row-wise evaluation (the production path for spline geometries) --------------------------
@@ -303,7 +337,8 @@ PB_HD void pb_fields_row_point(const PbFieldParams& prm, const int* g, const dou
     double f[Prog::NF];
     Prog::run(prm, pt, f);
 #pragma unroll
-    for (int c = 0; c < Prog::NF; ++c) prm.fields[(long long)c * prm.npts + idx] = f[c];
+    for (int c = 0; c < Prog::NF; ++c)
+        if (c < prm.nf) prm.fields[(long long)c * prm.npts + idx] = f[c];
 }
 
 // one whole row, sequentially (host emulation) — `Y` is scratch of Ng_last*NC*DIM doubles

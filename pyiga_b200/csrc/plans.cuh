@@ -30,7 +30,8 @@ enum PbPlanId {
     PB_PLAN_S1B = 3,
     PB_PLAN_S2B = 4,
     PB_PLAN_S1_2D = 5,  // 2D stiffness stage 1:  B11 [1,1]->(v,v)  B01 [1,0]->(v,d1)  B00 [0,0]->(d1,d1)
-    PB_PLAN_COUNT = 6,
+    PB_PLAN_GEN4 = 6,   // generic forms: [0,0] + [0,1] + [1,0] + [1,1] -> one output, no transposes, null = absent
+    PB_PLAN_COUNT = 7,
     PB_PLAN_LANE_BASE = 1000    // + plan id: the lane-per-span variant (second argument = lines per warp)
 };
 
@@ -44,6 +45,14 @@ struct PbPlanFinal4 {
     static constexpr bool HAS_TR = true;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {1, 1, 1, 0, 0}, {2, 0, 1, 1, 0}};
+        return t[i];
+    }
+};
+struct PbPlanGen4 {
+    static constexpr int NOPS = 4, NOUT = 1, MINB = 3;
+    static constexpr bool HAS_TR = false;
+    static constexpr PbOp op(int i) {
+        constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {2, 0, 1, 0, 0}, {3, 0, 1, 1, 0}};
         return t[i];
     }
 };

@@ -123,9 +123,12 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
     const long long off_out = (long long)(u - prm.u_base_out) * prm.out_su + (long long)v * prm.out_sv
                               + (long long)x * prm.out_sx;
 
+    // a null input pointer means "term absent" (generic forms): it reads as zero
     const double* src[NOPS];
+    bool has[NOPS];
     pb_static_for<0, NOPS>([&](auto I) {
         constexpr int i = decltype(I)::value;
+        has[i] = prm.in[i] != nullptr;
         src[i] = prm.in[i] + (Plan::op(i).tr ? off_in_tr : off_in);
     });
 
@@ -182,7 +185,7 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
     for (int gq = 0; gq < Q; ++gq)
         pb_static_for<0, NOPS>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            xq[gq][i] = src[i][(long long)(prm.s_begin * Q + gq) * prm.in_sc];
+            xq[gq][i] = has[i] ? src[i][(long long)(prm.s_begin * Q + gq) * prm.in_sc] : 0.0;
         });
 
     for (int s = prm.s_begin; s < prm.s_end; ++s) {
@@ -198,7 +201,7 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
             for (int gq = 0; gq < Q; ++gq)
                 pb_static_for<0, NOPS>([&](auto I) {
                     constexpr int i = decltype(I)::value;
-                    xq[gq][i] = src[i][(long long)((s + 1) * Q + gq) * prm.in_sc];
+                    xq[gq][i] = has[i] ? src[i][(long long)((s + 1) * Q + gq) * prm.in_sc] : 0.0;
                 });
         }
 
@@ -444,7 +447,7 @@ PB_HD void pb_lane_span_seq(const PbWalkParams& prm, long long line, int batch) 
             for (int gq = 0; gq < Q; ++gq) {
                 pb_static_for<0, NOPS>([&](auto I) {
                     constexpr int i = decltype(I)::value;
-                    x[gq][i] = prm.in[i][(Plan::op(i).tr ? lo.in_tr : lo.in) + (long long)(s * Q + gq)];
+                    x[gq][i] = prm.in[i] ? prm.in[i][(Plan::op(i).tr ? lo.in_tr : lo.in) + (long long)(s * Q + gq)] : 0.0;
                 });
                 const double* Vn = prm.V2 + (long long)(s * Q + gq) * 2 * P1;
                 for (int a = 0; a < P1; ++a) { D[gq][0][a] = Vn[a]; D[gq][1][a] = Vn[P1 + a]; }
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(128) pb_lane_span_kernel(const __grid_constant
         for (int gq = 0; gq < Q; ++gq)
             pb_static_for<0, NOPS>([&](auto I) {
                 constexpr int i = decltype(I)::value;
-                xn[gq][i] = (active && lo.keep) ? prm.in[i][(Plan::op(i).tr ? lo.in_tr : lo.in) + node0 + gq] : 0.0;
+                xn[gq][i] = (active && lo.keep && prm.in[i]) ? prm.in[i][(Plan::op(i).tr ? lo.in_tr : lo.in) + node0 + gq] : 0.0;
             });
     };
     PbLineOffsets lo_next;

@@ -52,6 +52,8 @@ struct Registrar {
     Registrar() {
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_COPY, PB_P, PB_Q, &launch_lane<PbPlanCopy>);
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_FINAL4, PB_P, PB_Q, &launch_lane<PbPlanFinal4>);
+        pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_GEN4, PB_P, PB_Q, &launch_lane<PbPlanGen4>);
+        pb200_register_walk(PB_PLAN_GEN4, PB_P, PB_Q, &launch<PbPlanGen4>);
         pb200_register_walk(PB_PLAN_COPY, PB_P, PB_Q, &launch<PbPlanCopy>);
         pb200_register_walk(PB_PLAN_FINAL4, PB_P, PB_Q, &launch<PbPlanFinal4>);
         pb200_register_walk(PB_PLAN_S1A, PB_P, PB_Q, &launch<PbPlanS1A>);

@@ -193,7 +193,9 @@ class MLMatrix(scipy.sparse.linalg.LinearOperator):
         assert data is None or matrix is None, 'Can only specify one of `data` and `matrix`'
         dtype = np.float64
         if data is not None:
-            if isinstance(data, np.ndarray):
+            from . import _device
+            on_device = _device._backend is not None and _device._backend.is_buffer(data)
+            if not on_device and isinstance(data, np.ndarray):
                 assert data.shape == self.datashape, 'Wrong shape of data tensor'
                 self._data = np.asarray(data, order='C')
                 dtype = self._data.dtype

@@ -1,0 +1,565 @@
+"""Variational forms for the device assembler: scalar bilinear forms with at most first derivatives.
+
+This is the front end that ``assemble.assemble("... * dx", kvs, geo=..., f=...)`` uses.  It plays
+the role of the reference's ``pyiga.vform`` + ``pyiga.codegen`` + ``pyiga.compile``
+(``pyiga/vform.py:162-735, 1804-1887``, ``pyiga/codegen/cython.py:748-805``,
+``pyiga/compile.py:120-132``) for the family of forms the device path implements
+
+    a(u, v) = int  sum_t c_t(x) * d^{bt} v * d^{bu} u  dx,      bt, bu in {value, d/dx_1..d/dx_d}
+
+(diffusion with scalar/matrix coefficients, convection, reaction, and their transposes).  Instead of
+generating and compiling source code per form, an expression is *analysed*: evaluating it with
+symbolic basis functions yields the coefficient ``c_t`` of every slot pair.  User callables are
+evaluated on the host at the (physical) Gauss points — as the reference does
+(``pyiga/codegen/cython.py:465-484``, ``pyiga/utils.py:33-52``) — uploaded, and the pull-back to the
+parameter domain (``J^-1``, ``|det J|``, Gauss weights) happens in the K2 kernel
+(``csrc/geo_fields.cuh: PbProgGeneral``).  The matrix itself comes from the same sum-factorised
+pipeline as mass and stiffness (``pb200_asm_assemble_mlb`` with a generic stage plan).
+
+Vector-valued basis functions, second derivatives, boundary integrals and arity-1 forms are not
+part of the device path; they raise ``NotImplementedError``.
+"""
+import re
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------
+# coefficients and slot-forms (the values expressions evaluate to)
+# ---------------------------------------------------------------------------------------------
+class Coef:
+    """scale * arr, where arr is an array on the Gauss grid or None (= 1)."""
+    __slots__ = ('scale', 'arr')
+
+    def __init__(self, scale=1.0, arr=None):
+        self.scale, self.arr = float(scale), arr
+
+    def value(self):
+        return self.scale if self.arr is None else self.scale * self.arr
+
+    def __mul__(self, o):
+        if self.arr is None:
+            return Coef(self.scale * o.scale, o.arr)
+        if o.arr is None:
+            return Coef(self.scale * o.scale, self.arr)
+        return Coef(self.scale * o.scale, self.arr * o.arr)
+
+    def __add__(self, o):
+        if self.arr is o.arr:
+            return Coef(self.scale + o.scale, self.arr)
+        return Coef(1.0, self.value() + o.value())
+
+    def is_zero(self):
+        return self.scale == 0.0
+
+
+class Form:
+    """Scalar value of an expression: {(test slot, trial slot): Coef}; slot None = no basis function,
+    0 = function value, 1+a = derivative with respect to physical coordinate a (x, y, z order)."""
+
+    def __init__(self, terms=None):
+        self.terms = dict(terms or {})
+
+    @staticmethod
+    def const(c, arr=None):
+        return Form({(None, None): Coef(c, arr)})
+
+    def is_coef(self):
+        return all(k == (None, None) for k in self.terms)
+
+    def coef(self):
+        assert self.is_coef()
+        return self.terms.get((None, None), Coef(0.0))
+
+    def __add__(self, o):
+        out = dict(self.terms)
+        for k, c in o.terms.items():
+            out[k] = out[k] + c if k in out else c
+        return Form(out)
+
+    def __neg__(self):
+        return Form({k: Coef(-c.scale, c.arr) for k, c in self.terms.items()})
+
+    def __sub__(self, o):
+        return self + (-o)
+
+    def __mul__(self, o):
+        out = {}
+        for (bt1, bu1), c1 in self.terms.items():
+            for (bt2, bu2), c2 in o.terms.items():
+                if (bt1 is not None and bt2 is not None) or (bu1 is not None and bu2 is not None):
+                    raise ValueError('expression is not linear in each basis function')
+                k = (bt1 if bt1 is not None else bt2, bu1 if bu1 is not None else bu2)
+                c = c1 * c2
+                out[k] = out[k] + c if k in out else c
+        return Form(out)
+
+    def __truediv__(self, o):
+        if not o.is_coef():
+            raise ValueError('cannot divide by an expression that contains basis functions')
+        c = o.coef()
+        inv = Coef(1.0 / c.scale, None if c.arr is None else 1.0 / c.arr)
+        return self * Form({(None, None): inv})
+
+    def apply(self, fn):
+        if not self.is_coef():
+            raise ValueError('functions can only be applied to coefficient expressions')
+        v = self.coef().value()
+        r = fn(v)
+        return Form.const(1.0, r) if isinstance(r, np.ndarray) else Form.const(float(r))
+
+
+def _obj(shape, items):
+    a = np.empty(shape, dtype=object)
+    a.ravel()[:] = list(items)
+    return a
+
+
+# ---------------------------------------------------------------------------------------------
+# lazy expression trees
+# ---------------------------------------------------------------------------------------------
+class Expr:
+    """Node of an expression tree; ``ev(env)`` returns a numpy object array of :class:`Form`."""
+    shape = ()
+
+    def __add__(self, o): return BinOp('+', self, as_expr(o))
+    def __radd__(self, o): return BinOp('+', as_expr(o), self)
+    def __sub__(self, o): return BinOp('-', self, as_expr(o))
+    def __rsub__(self, o): return BinOp('-', as_expr(o), self)
+    def __mul__(self, o): return BinOp('*', self, as_expr(o))
+    def __rmul__(self, o): return BinOp('*', as_expr(o), self)
+    def __truediv__(self, o): return BinOp('/', self, as_expr(o))
+    def __rtruediv__(self, o): return BinOp('/', as_expr(o), self)
+    def __neg__(self): return BinOp('-', as_expr(0.0), self)
+    def __pos__(self): return self
+
+    def __getitem__(self, idx):
+        return Index(self, idx)
+
+    def __len__(self):
+        if not self.shape:
+            raise TypeError('scalar expression has no length')
+        return self.shape[0]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def is_scalar(self): return self.shape == ()
+    def is_vector(self): return len(self.shape) == 1
+    def is_matrix(self): return len(self.shape) == 2
+
+    @property
+    def T(self):
+        return Transpose(self)
+
+    def dot(self, o):
+        return dot(self, o)
+
+
+class Const(Expr):
+    def __init__(self, v):
+        self.v = np.asarray(v, dtype=float)
+        self.shape = self.v.shape
+
+    def ev(self, env):
+        return _obj(self.shape, (Form.const(float(x)) for x in self.v.ravel()))
+
+
+class Literal(Expr):
+    """vector / matrix built from scalar expressions"""
+    def __init__(self, items, shape):
+        self.items, self.shape = [as_expr(i) for i in items], tuple(shape)
+        assert all(i.shape == () for i in self.items), 'components must be scalar'
+
+    def ev(self, env):
+        return _obj(self.shape, (i.ev(env)[()] for i in self.items))
+
+
+class BasisFun(Expr):
+    def __init__(self, name, role):
+        self.name, self.role = name, role       # role: 'trial' (u, columns) or 'test' (v, rows)
+
+    def ev(self, env):
+        return _obj((), [Form({((None, 0) if self.role == 'trial' else (0, None)): Coef(1.0)})])
+
+
+class Input(Expr):
+    """named input function or constant parameter; value supplied at instantiation"""
+    def __init__(self, name, shape):
+        self.name, self.shape = name, tuple(shape)
+
+    def ev(self, env):
+        vals = env[self.name]       # ndarray of shape self.shape (+ grid) or python floats
+        if self.shape == ():
+            return _obj((), [_coef_form(vals)])
+        return _obj(self.shape, (_coef_form(vals[idx]) for idx in np.ndindex(*self.shape)))
+
+
+def _coef_form(v):
+    if isinstance(v, np.ndarray) and v.ndim > 0:
+        return Form.const(1.0, v)
+    return Form.const(float(v))
+
+
+class Measure(Expr):
+    """dx: the factor |det J| * GaussWeight is applied on the device"""
+    def ev(self, env):
+        return _obj((), [Form.const(1.0)])
+
+
+class BinOp(Expr):
+    def __init__(self, op, a, b):
+        self.op, self.a, self.b = op, a, b
+        if op in '+-':
+            if a.shape != b.shape:
+                raise ValueError('incompatible shapes %s and %s' % (a.shape, b.shape))
+            self.shape = a.shape
+        elif op == '*':
+            if a.shape and b.shape:
+                if a.shape != b.shape:
+                    raise ValueError('elementwise product of shapes %s and %s' % (a.shape, b.shape))
+                self.shape = a.shape
+            else:
+                self.shape = a.shape or b.shape
+        else:
+            if b.shape:
+                raise ValueError('can only divide by scalars')
+            self.shape = a.shape
+
+    def ev(self, env):
+        A, B = self.a.ev(env), self.b.ev(env)
+        fn = {'+': lambda x, y: x + y, '-': lambda x, y: x - y, '*': lambda x, y: x * y,
+              '/': lambda x, y: x / y}[self.op]
+        if A.shape == B.shape:
+            return _obj(A.shape, (fn(x, y) for x, y in zip(A.ravel(), B.ravel())))
+        if A.shape == ():
+            return _obj(B.shape, (fn(A[()], y) for y in B.ravel()))
+        return _obj(A.shape, (fn(x, B[()]) for x in A.ravel()))
+
+
+class Index(Expr):
+    def __init__(self, e, idx):
+        if not e.shape:
+            raise TypeError('cannot index a scalar expression')
+        self.e, self.idx = e, idx
+        self.shape = np.shape(np.empty(e.shape)[idx])
+
+    def ev(self, env):
+        r = self.e.ev(env)[self.idx]
+        return r if isinstance(r, np.ndarray) else _obj((), [r])
+
+
+class Transpose(Expr):
+    def __init__(self, e):
+        self.e, self.shape = e, tuple(reversed(e.shape))
+
+    def ev(self, env):
+        return self.e.ev(env).T
+
+
+class Grad(Expr):
+    def __init__(self, e, dim):
+        if not isinstance(e, BasisFun):
+            raise NotImplementedError('grad() is implemented for the basis functions u and v only')
+        self.e, self.shape, self.dim = e, (dim,), dim
+
+    def ev(self, env):
+        trial = self.e.role == 'trial'
+        return _obj(self.shape, (Form({((None, 1 + a) if trial else (1 + a, None)): Coef(1.0)})
+                                 for a in range(self.dim)))
+
+
+class Contract(Expr):
+    """inner (full contraction) and dot (matrix/vector products)"""
+    def __init__(self, kind, a, b):
+        self.kind, self.a, self.b = kind, a, b
+        if kind == 'inner':
+            if a.shape != b.shape:
+                raise ValueError('incompatible shapes for inner product')
+            self.shape = ()
+        else:
+            if not a.shape or not b.shape or a.shape[-1] != b.shape[0]:
+                raise ValueError('incompatible shapes for dot product')
+            self.shape = a.shape[:-1] + b.shape[1:]
+
+    def ev(self, env):
+        A, B = self.a.ev(env), self.b.ev(env)
+        if self.kind == 'inner':
+            acc = None
+            for x, y in zip(A.ravel(), B.ravel()):
+                acc = x * y if acc is None else acc + x * y
+            return _obj((), [acc])
+        A2 = A.reshape(-1, A.shape[-1])
+        B2 = B.reshape(B.shape[0], -1)
+        out = []
+        for i in range(A2.shape[0]):
+            for j in range(B2.shape[1]):
+                acc = None
+                for k in range(A2.shape[1]):
+                    t = A2[i, k] * B2[k, j]
+                    acc = t if acc is None else acc + t
+                out.append(acc)
+        return _obj(self.shape, out)
+
+
+class Func(Expr):
+    def __init__(self, fn, e):
+        self.fn, self.e, self.shape = fn, e, e.shape
+
+    def ev(self, env):
+        A = self.e.ev(env)
+        return _obj(A.shape, (x.apply(self.fn) for x in A.ravel()))
+
+
+def as_expr(x):
+    if isinstance(x, Expr):
+        return x
+    if isinstance(x, (tuple, list)):
+        items = [as_expr(i) for i in x]
+        if all(i.shape == () for i in items):
+            return Literal(items, (len(items),))
+        if all(len(i.shape) == 1 for i in items):
+            flat = [c for i in items for c in i]
+            return Literal(flat, (len(items), len(items[0])))
+        raise ValueError('cannot convert nested sequence to an expression')
+    return Const(x)
+
+
+as_vector = as_expr
+as_matrix = as_expr
+
+# operators available in form strings (names as in pyiga/vform.py:1518-1733)
+
+
+def grad(e, dims=None, parametric=False):
+    if parametric or dims is not None:
+        raise NotImplementedError('parametric / partial gradients are not part of the device path')
+    e = as_expr(e)
+    return Grad(e, e._dim)
+
+
+def Dx(e, k, times=1, parametric=False):
+    if times != 1 or parametric:
+        raise NotImplementedError('only first physical derivatives are part of the device path')
+    return grad(e)[k]
+
+
+def inner(a, b):
+    return Contract('inner', as_expr(a), as_expr(b))
+
+
+def dot(a, b):
+    return Contract('dot', as_expr(a), as_expr(b))
+
+
+def tr(A):
+    A = as_expr(A)
+    assert A.is_matrix() and A.shape[0] == A.shape[1]
+    out = A[0, 0]
+    for i in range(1, A.shape[0]):
+        out = out + A[i, i]
+    return out
+
+
+def outer(a, b):
+    a, b = as_expr(a), as_expr(b)
+    return Literal([x * y for x in a for y in b], (len(a), len(b)))
+
+
+def norm(x):
+    return sqrt(inner(x, x))
+
+
+def sqrt(x): return Func(np.sqrt, as_expr(x))
+def exp(x): return Func(np.exp, as_expr(x))
+def log(x): return Func(np.log, as_expr(x))
+def sin(x): return Func(np.sin, as_expr(x))
+def cos(x): return Func(np.cos, as_expr(x))
+def tan(x): return Func(np.tan, as_expr(x))
+
+
+# ---------------------------------------------------------------------------------------------
+# VForm
+# ---------------------------------------------------------------------------------------------
+class VForm:
+    """Abstract description of a variational form (API after ``pyiga/vform.py:162-350``)."""
+
+    def __init__(self, dim, geo_dim=None, boundary=False, arity=2, spacetime=False):
+        if boundary or spacetime or (geo_dim is not None and geo_dim != dim):
+            raise NotImplementedError('boundary, surface and space-time forms are not part of the device path')
+        self.dim, self.arity = dim, arity
+        self.vec = False
+        self.exprs = []
+        self.inputs = []        # [(name, shape, physical, updatable)]
+        self.params = []        # [(name, shape)]
+        self.dx = Measure()
+        self.Geo = Input('@x', (dim,))
+        self._uses_x = False
+
+    def basisfuns(self, components=(None, None), spaces=(0, 0)):
+        if any(c not in (None, 1) for c in components):
+            raise NotImplementedError('vector-valued basis functions are not part of the device path')
+        if any(s != 0 for s in spaces):
+            raise NotImplementedError('forms over two different spaces are not part of the device path')
+        v = BasisFun('v', 'test')
+        v._dim = self.dim
+        if self.arity == 1:
+            return v
+        u = BasisFun('u', 'trial')
+        u._dim = self.dim
+        return u, v
+
+    def input(self, name, shape=(), physical=False, updatable=False):
+        self.inputs.append((name, tuple(shape), bool(physical), bool(updatable)))
+        return Input(name, shape)
+
+    def parameter(self, name, shape=()):
+        self.params.append((name, tuple(shape)))
+        return Input(name, shape)
+
+    def add(self, expr):
+        expr = as_expr(expr)
+        if expr.shape != ():
+            raise NotImplementedError('vector-valued forms are not part of the device path')
+        self.exprs.append(expr)
+
+    def num_spaces(self):
+        return 1
+
+
+def _mentions(expr, name):
+    stack, seen = [expr], set()
+    while stack:
+        e = stack.pop()
+        if id(e) in seen:
+            continue
+        seen.add(id(e))
+        if isinstance(e, Input) and e.name == name:
+            return True
+        for v in vars(e).values():
+            if isinstance(v, Expr):
+                stack.append(v)
+            elif isinstance(v, (list, tuple)):
+                stack.extend(x for x in v if isinstance(x, Expr))
+    return False
+
+
+def _check_input_field(kvs, f):
+    """(shape, physical): spline functions are parametric, other callables physical and probed at
+    the midpoint of the parameter box (``pyiga/vform.py:1791-1802``)."""
+    if hasattr(f, 'grid_eval') and hasattr(f, 'kvs'):
+        return tuple(f.output_shape()), False
+    mid = tuple(0.5 * (kv.support()[0] + kv.support()[1]) for kv in kvs)
+    return np.shape(f(*mid)), True
+
+
+def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
+    """Parse a form string like ``'(inner(c * grad(u), grad(v)) + inner(b, grad(u)) * v) * dx'``
+    (``pyiga/vform.py:1804-1887``)."""
+    if boundary:
+        raise NotImplementedError('boundary integrals are not part of the device path')
+    if not all(hasattr(kv, 'kv') for kv in kvs):
+        if all(hasattr(kv, 'kv') for kv in kvs[0]):
+            kvs = kvs[0]
+        else:
+            raise ValueError('expected a tensor product spline space in `kvs`')
+    dim = len(kvs)
+    words = set(re.findall(r"[^\d\W]\w*", expr))
+    if 'ds' in words:
+        raise NotImplementedError('surface integrals are not part of the device path')
+    if bfuns is None:
+        names = sorted(words & {'u', 'v'})
+    else:
+        names = []
+        for bf in bfuns:
+            bf = (bf,) if isinstance(bf, str) else tuple(bf)
+            if (len(bf) > 1 and bf[1] not in (None, 1)) or (len(bf) > 2 and bf[2] != 0):
+                raise NotImplementedError('vector-valued / multi-space basis functions are not part of the device path')
+            names.append(bf[0])
+    if len(names) not in (1, 2):
+        raise ValueError('arity should be 1 or 2')
+    vf = VForm(dim=dim, arity=len(names))
+    loc = {}
+    if vf.arity == 1:
+        loc[names[0]] = vf.basisfuns()
+    else:
+        u, v = vf.basisfuns()
+        loc[names[0]], loc[names[1]] = u, v
+    for name in sorted(set(args.keys()) & words):
+        if callable(args[name]):
+            shp, phys = _check_input_field(kvs, args[name])
+            loc[name] = vf.input(name, shape=shp, physical=phys, updatable=(name in updatable))
+        else:
+            loc[name] = vf.parameter(name, shape=np.shape(args[name]))
+    if 'x' in words and 'x' not in args:
+        loc['x'] = vf.Geo
+    ns = dict(globals())
+    ns['dx'] = vf.dx
+    ns.update(loc)
+    vf.add(eval(expr, ns))
+    vf.source = expr
+    return vf
+
+
+def mass_vf(dim):
+    vf = VForm(dim)
+    u, v = vf.basisfuns()
+    vf.add(u * v * vf.dx)
+    return vf
+
+
+def stiffness_vf(dim):
+    vf = VForm(dim)
+    u, v = vf.basisfuns()
+    vf.add(inner(grad(u), grad(v)) * vf.dx)
+    return vf
+
+
+# ---------------------------------------------------------------------------------------------
+# "compilation": VForm -> assembler class bound to the device pipeline
+# ---------------------------------------------------------------------------------------------
+def _grid_values(f, shape, coords, grid_shape):
+    """evaluate a callable at coordinate arrays (x, y, z order) and bring the result to
+    shape + grid_shape (``pyiga/utils.py:8-31`` _ensure_grid_shape)"""
+    vals = f(*coords)
+    if shape == ():
+        return np.broadcast_to(np.asarray(vals, dtype=float), grid_shape)
+    comps = np.empty(shape, dtype=object)
+    vals_arr = vals if isinstance(vals, np.ndarray) and vals.shape[:len(shape)] == shape else None
+    for idx in np.ndindex(*shape):
+        c = vals_arr[idx] if vals_arr is not None else _nested_get(vals, idx)
+        comps[idx] = np.broadcast_to(np.asarray(c, dtype=float), grid_shape)
+    return comps
+
+
+def _nested_get(v, idx):
+    for i in idx:
+        v = v[i]
+    return v
+
+
+def compile_vform(vf):
+    """Return an assembler *class* for the form, like ``pyiga.compile.compile_vform``
+    (``pyiga/compile.py:120-132``); no code is generated — the class analyses the form when it is
+    instantiated on a concrete space."""
+    if vf.arity != 2:
+        raise NotImplementedError('arity-1 forms (load vectors) are not part of the device path yet')
+    input_shapes = {'geo': (vf.dim,)}
+    input_shapes.update({name: shape for name, shape, _, _ in vf.inputs})
+    param_shapes = {name: shape for name, shape in vf.params}
+
+    from . import assemblers
+
+    class VFormAssembler(assemblers.GenericFormAssembler):
+        _vf = vf
+
+        @classmethod
+        def inputs(cls):
+            return dict(input_shapes)
+
+        @classmethod
+        def parameters(cls):
+            return dict(param_shapes)
+
+    VFormAssembler.__name__ = 'VFormAssembler%dD' % vf.dim
+    return VFormAssembler

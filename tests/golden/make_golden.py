@@ -142,6 +142,26 @@ def main():
     out['kron_x'] = xk
     out['kron_y'] = operators.KroneckerOperator(*facs).dot(xk)
 
+    # ---- 6. string vforms through the reference's JIT (pyiga/assemble.py:837, compile.py:120) -------
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers import VFORMS
+    for name, (form, inputs, case, gname) in VFORMS.items():
+        kvs, _ = cases[case]
+        A = assemble.assemble(form, kvs, geo=geos[gname], **inputs).tocsr()
+        A.sort_indices()
+        S = mlmatrix.MLStructure.from_kvs(kvs, kvs)
+        I, J = S.nonzero()
+        out['vf_%s_mlb' % name] = np.asarray(A[I.astype(np.int64), J.astype(np.int64)]).ravel().reshape(
+            [len(b) for b in S.bidx])
+    # Assembler with an updatable input (test/test_assemble.py:409-450 pattern)
+    kvs, _ = cases['a2_qa']
+    asm = assemble.Assembler('f * inner(grad(u), grad(v)) * dx', kvs, geo=geos['qa'], f=lambda x, y: 1.0 + x,
+                             updatable=['f'])
+    S = mlmatrix.MLStructure.from_kvs(kvs, kvs)
+    I, J = S.nonzero()
+    out['vf_upd_a'] = np.asarray(asm.assemble()[I.astype(np.int64), J.astype(np.int64)]).ravel()
+    out['vf_upd_b'] = np.asarray(asm.assemble(f=lambda x, y: 2.0 + y * y)[I.astype(np.int64), J.astype(np.int64)]).ravel()
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

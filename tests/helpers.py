@@ -61,3 +61,18 @@ def assert_close_rel(got, want, rtol=RTOL, what=''):
     scale = np.abs(want).max()
     err = np.abs(got - want).max()
     assert err <= rtol * scale, '%s: max abs error %.3e > %.1e * max|ref| (%.3e)' % (what, err, rtol, scale)
+
+
+# variational forms used by the vform parity tests: name -> (form string, inputs, space case, geometry)
+A3 = [[2.0, 0.3, 0.0], [-0.1, 1.5, 0.2], [0.4, 0.0, 1.0]]
+VFORMS = {
+    'cd3': ('(inner(diff_coeff * grad(u), grad(v)) + inner((x[1], -x[0], 1.0), grad(u)) * v) * dx',
+            {'diff_coeff': lambda x, y, z: 1.0 + x * y}, 'a3_mixed', 'tb'),
+    'cd2': ('(inner(grad(u), grad(v)) + inner(b, grad(u)) * v + 3.0 * u * v) * dx',
+            {'b': lambda x, y: (y, -x)}, 'a2_qa', 'qa'),
+    'aniso3': ('inner(dot(A, grad(u)), grad(v)) * dx', {'A': A3}, 'a3_tb', 'tnb'),
+    'react2': ('(c * u * v + inner(grad(v), w) * u) * dx',
+               {'c': lambda x, y: 2.0 + x - y * y, 'w': (0.5, -1.25)}, 'a2_mixed', 'bqa'),
+    'sqrt3': ('sqrt(kappa) * inner(grad(u), grad(v)) / (1.0 + x[2]) * dx',
+              {'kappa': lambda x, y, z: 1.0 + x * x + z}, 'a3_p1', 'tb'),
+}

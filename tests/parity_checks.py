@@ -183,3 +183,52 @@ def check_vs_oracle(dim, ps, ns, form, geo_name='nurbs', mult=1, force_walk=Fals
     want = orc.assemble_mlb(prob, form.lower()).ravel()
     assert_close_rel(got, want, rtol=rtol, what='%s %dD p=%s n=%s' % (form, dim, ps, ns))
     return asm
+
+
+def check_vform(ref, name):
+    """string vforms through assemble.assemble against the reference's JIT-compiled assemblers"""
+    from helpers import VFORMS
+    from pyiga_b200 import assemble
+    form, inputs, case, gname = VFORMS[name]
+    kvs = make_space(ref, case)
+    geo = make_geo(ref, gname)
+    want = ref['vf_%s_mlb' % name]
+    M = assemble.assemble(form, kvs, geo=geo, format='mlb', **inputs)
+    assert M.datashape == want.shape
+    assert_close_rel(M.data, want, what='vform ' + name)
+    A = assemble.assemble(form, kvs, args=dict(inputs, geo=geo))
+    B = orc.mlb_to_csr(want, [ref['%s_bidx%d' % (case, k)] for k in range(len(kvs))], M.structure.bs)
+    B.sort_indices()
+    assert np.array_equal(A.indices, B.indices) and np.array_equal(A.indptr, B.indptr)
+    assert_close_rel(A.data, B.data, what='vform csr ' + name)
+
+
+def check_vform_protocol(ref):
+    """Assembler with updatable inputs, error behaviour (test/test_assemble.py:409-450)"""
+    import pytest
+    from pyiga_b200 import assemble, vform
+    kvs = make_space(ref, 'a2_qa')
+    geo = make_geo(ref, 'qa')
+    asm = assemble.Assembler('f * inner(grad(u), grad(v)) * dx', kvs, geo=geo, f=lambda x, y: 1.0 + x,
+                             updatable=['f'])
+    S = asm.asm.dev.structure
+    I, J = (a.astype(np.int64) for a in S.nonzero())
+    A = asm.assemble()
+    assert_close_rel(np.asarray(A[I, J]).ravel(), ref['vf_upd_a'], what='Assembler')
+    B = asm.assemble(f=lambda x, y: 2.0 + y * y)
+    assert_close_rel(np.asarray(B[I, J]).ravel(), ref['vf_upd_b'], what='Assembler.update')
+    with pytest.raises(RuntimeError):
+        asm.update(geo=geo)             # not declared updatable
+    with pytest.raises(ValueError):
+        assemble.Assembler('f * u * v * dx', kvs, geo=geo, f=lambda x, y: x, updatable=['g'])
+    with pytest.raises(ValueError, match="required input parameter 'f' missing"):
+        assemble.assemble(vform.parse_vf('f * u * v * dx', kvs, args={'f': lambda x, y: x}), kvs, geo=geo)
+    with pytest.raises(TypeError):
+        assemble.assemble(42, kvs, geo=geo)
+    # class-level metadata of the compiled form
+    cls = vform.compile_vform(vform.parse_vf('c * u * v * dx', kvs, args={'c': 2.0}))
+    assert cls.inputs() == {'geo': (2,)} and cls.parameters() == {'c': ()}
+    # programmatic VForm equals the predefined stiffness assembler
+    K = assemble.assemble(vform.stiffness_vf(2), kvs, geo=geo)
+    K2 = assemble.stiffness(kvs, geo)
+    assert abs(K - K2).max() <= RTOL * abs(K2).max()

@@ -70,3 +70,12 @@ def test_long_last_axis_3d(emu):
 def test_repeated_knots_use_walk_kernel(emu):
     pc.check_vs_oracle(2, (3, 3), (4, 20), 'Stiffness', mult=2)
     pc.check_vs_oracle(3, (2, 2, 2), (3, 2, 12), 'Mass', mult=2, geo_name='bspline')
+
+
+@pytest.mark.parametrize('name', ['cd3', 'cd2', 'aniso3', 'react2', 'sqrt3'])
+def test_vform(emu, ref, name):
+    pc.check_vform(ref, name)
+
+
+def test_vform_protocol(emu, ref):
+    pc.check_vform_protocol(ref)

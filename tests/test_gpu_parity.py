@@ -62,6 +62,28 @@ def test_operators(cuda, ref):
     pc.check_operators(ref)
 
 
+@pytest.mark.parametrize('name', ['cd3', 'cd2', 'aniso3', 'react2', 'sqrt3'])
+def test_vform(cuda, ref, name):
+    pc.check_vform(ref, name)
+
+
+def test_vform_protocol(cuda, ref):
+    pc.check_vform_protocol(ref)
+
+
+@pytest.mark.parametrize('force_walk', [False, True])
+@pytest.mark.parametrize('ps,ns', [((2, 2), (4, 70)), ((3, 1), (5, 33)), ((3, 3), (40, 45))])
+def test_long_last_axis_2d(cuda, ps, ns, force_walk):
+    pc.check_vs_oracle(2, ps, ns, 'Stiffness', force_walk=force_walk)
+    pc.check_vs_oracle(2, ps, ns, 'Mass', force_walk=force_walk)
+
+
+def test_repeated_knots(cuda):
+    pc.check_vs_oracle(2, (3, 3), (4, 20), 'Stiffness', mult=2)
+    pc.check_vs_oracle(3, (2, 2, 2), (3, 2, 12), 'Mass', mult=2, geo_name='bspline')
+    pc.check_vs_oracle(3, (3, 3, 3), (5, 4, 6), 'Stiffness', mult=3)
+
+
 @pytest.mark.parametrize('p,n', [(2, 12), (3, 16), (4, 10)])
 @pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
 def test_vs_oracle_3d(cuda, p, n, form):
