@@ -7,6 +7,13 @@ import scipy.sparse
 from . import _device
 
 
+def _ptr(be, buf):
+    """device address of a backend buffer or of a torch view of one"""
+    if hasattr(buf, 'data_ptr'):
+        return buf.data_ptr()
+    return be.ptr(buf)
+
+
 class DeviceStructure:
     """Owns (or borrows, from an assembler) a ``pb200_mlstruct`` handle."""
 
@@ -75,12 +82,13 @@ class DeviceStructure:
         return A
 
     def matvec_device(self, d_data, d_x, d_y=None, row0=None, x_j0=0):
+        """y = A[rows] x on device buffers; `d_data` starts at the first band entry of row0[0]."""
         be = self.be
         ra, rb, nrows, _ = self._sizes(row0)
         if d_y is None:
             d_y = be.empty(nrows)
-        _device.check(be.lib.pb200_mlb_matvec(self.handle, ra, rb, be.ptr(d_data), be.ptr(d_x), int(x_j0),
-                                               be.ptr(d_y), be.stream()))
+        _device.check(be.lib.pb200_mlb_matvec(self.handle, ra, rb, _ptr(be, d_data), _ptr(be, d_x), int(x_j0),
+                                               _ptr(be, d_y), be.stream()))
         return d_y
 
     def matvec(self, d_data, x):

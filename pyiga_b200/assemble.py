@@ -26,6 +26,30 @@ def _default_geo(kvs):
     return geometry.identity(kvs)
 
 
+def _assemble_1d(kv, form):
+    """1D mass / stiffness matrix of a knot vector, computed on the device as a marginal of the 2D
+    matrix over (kv) x (one linear element): M2 = M_kv (x) M_1 and K2 = K_kv (x) M_1 + M_kv (x) K_1,
+    and the entries of M_1 sum to 1 while those of K_1 sum to 0.  Replaces ``bsp_mass_1d`` /
+    ``bsp_stiffness_1d`` (``pyiga/assemble.py:152-234``)."""
+    import scipy.sparse
+    unit = bspline.make_knots(1, 0.0, 1.0, 1)
+    kvs = (kv, unit)
+    cls = assemblers.MassAssembler2D if form == 'mass' else assemblers.StiffnessAssembler2D
+    M = cls(kvs, geometry.identity(kvs)).assemble_mlb()
+    vals = M.data.sum(axis=1)
+    b = M.structure.bidx[0]
+    n = kv.numdofs
+    return scipy.sparse.csr_matrix((vals, (b[:, 0].astype(np.int64), b[:, 1].astype(np.int64))), shape=(n, n))
+
+
+def bsp_mass_1d(knotvec):
+    return _assemble_1d(knotvec, 'mass')
+
+
+def bsp_stiffness_1d(knotvec):
+    return _assemble_1d(knotvec, 'stiffness')
+
+
 def assemble_entries(asm, symmetric=False, format='csr', layout='blocked'):
     """Assemble all entries of an assembler object (``pyiga/assemble.py:703-754``).
 
@@ -51,7 +75,8 @@ def mass(kvs, geo=None, format='csr'):
     if geo:
         assert geo.dim == dim, "Geometry has wrong dimension"
     if dim == 1:
-        raise NotImplementedError('1D assembling is a host-only path of the reference and is not part of pyiga_b200')
+        assert geo is None, "Geometry map not supported for 1D assembling"
+        return bsp_mass_1d(kvs).asformat(format)
     if geo is None:
         geo = _default_geo(kvs)
     cls = {2: assemblers.MassAssembler2D, 3: assemblers.MassAssembler3D}.get(dim)
@@ -65,7 +90,8 @@ def stiffness(kvs, geo=None, format='csr'):
     if geo:
         assert geo.dim == dim, "Geometry has wrong dimension"
     if dim == 1:
-        raise NotImplementedError('1D assembling is a host-only path of the reference and is not part of pyiga_b200')
+        assert geo is None, "Geometry map not supported for 1D assembling"
+        return bsp_stiffness_1d(kvs).asformat(format)
     if geo is None:
         geo = _default_geo(kvs)
     cls = {2: assemblers.StiffnessAssembler2D, 3: assemblers.StiffnessAssembler3D}.get(dim)

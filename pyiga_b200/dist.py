@@ -69,3 +69,177 @@ class SlabAssembly:
         if self.rows is None:
             return None
         return self.dev.device_structure.to_csr(self.assemble_mlb(), row0=self.rows)
+
+
+# ---------------------------------------------------------------------------------------------
+# slab-distributed operator: y_r = A_r x with a halo exchange, and CG on top of it
+# ---------------------------------------------------------------------------------------------
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+class SlabOperator:
+    """The rows [ra, rb) of the first tensor axis of a multi-level banded matrix, applied to a vector
+    that is distributed by the same slabs.  The band of the slab's rows reaches
+    `p` planes into the neighbouring slabs: those planes of x are received from their owners with
+    point-to-point messages (NCCL send/recv on NVLink) while the rows that need no halo are already
+    being multiplied.  With one rank it is a plain device matvec (``pyiga/mlmatrix_cy.pyx:295-325``)."""
+
+    def __init__(self, dev, mlb, rows=None, slabs=None, rank=0):
+        self.dev, self.mlb = dev, mlb
+        self.be = dev.be
+        n0 = dev.ndofs_test[0]
+        self.slabs = slabs if slabs is not None else [(0, n0)]
+        self.rank = rank
+        self.rows = rows if rows is not None else self.slabs[rank]
+        ra, rb = self.rows
+        b0 = dev.structure.bidx[0].astype(np.int64)
+        sel = (b0[:, 0] >= ra) & (b0[:, 0] < rb)
+        self.ha, self.hb = int(b0[sel, 1].min()), int(b0[sel, 1].max()) + 1     # trial planes touched
+        self.plane = int(np.prod(dev.ndofs_trial[1:], dtype=np.int64))
+        self.plane_rows = int(np.prod(dev.ndofs_test[1:], dtype=np.int64))
+        # rows whose band stays inside the slab can be multiplied before the halo arrives
+        rmin = np.full(n0, n0, dtype=np.int64)
+        rmax = np.zeros(n0, dtype=np.int64)
+        np.minimum.at(rmin, b0[:, 0], b0[:, 1])
+        np.maximum.at(rmax, b0[:, 0], b0[:, 1])
+        inner = [i for i in range(ra, rb) if rmin[i] >= ra and rmax[i] < rb]
+        self.inner = (inner[0], inner[-1] + 1) if inner else None
+        # message plan: (peer, first plane, last plane) to receive / to send
+        self.recv, self.send = [], []
+        for s, (sa, sb) in enumerate(self.slabs):
+            if s == rank:
+                continue
+            lo, hi = max(sa, self.ha), min(sb, self.hb)
+            if lo < hi:
+                self.recv.append((s, lo, hi))
+            sel_s = (b0[:, 0] >= sa) & (b0[:, 0] < sb)
+            if sel_s.any():
+                pa, pb = int(b0[sel_s, 1].min()), int(b0[sel_s, 1].max()) + 1
+                lo, hi = max(ra, pa), min(rb, pb)
+                if lo < hi:
+                    self.send.append((s, lo, hi))
+        self.x_ext = self.be.zeros((self.hb - self.ha) * self.plane)
+        self.local_size = (rb - ra) * self.plane_rows
+        self.halo_bytes = 8 * self.plane * sum(hi - lo for _, lo, hi in self.recv)
+
+    def _t(self, buf):
+        """torch view of a backend buffer (communication goes through torch.distributed)"""
+        import torch
+        return buf if isinstance(buf, torch.Tensor) else torch.from_numpy(np.asarray(buf))
+
+    def matvec(self, x_local, y_local=None):
+        be, dev = self.be, self.dev
+        ra, rb = self.rows
+        if y_local is None:
+            y_local = be.empty(self.local_size)
+        xe = self._t(self.x_ext)
+        xl = self._t(x_local)
+        xe[(ra - self.ha) * self.plane:(rb - self.ha) * self.plane].copy_(xl)
+        dist = _dist()
+        works = []
+        if dist is not None and (self.recv or self.send):
+            ops = []
+            for peer, lo, hi in self.recv:
+                ops.append(dist.P2POp(dist.irecv, xe[(lo - self.ha) * self.plane:(hi - self.ha) * self.plane], peer))
+            for peer, lo, hi in self.send:
+                ops.append(dist.P2POp(dist.isend, xl[(lo - ra) * self.plane:(hi - ra) * self.plane], peer))
+            works = dist.batch_isend_irecv(ops)
+        ds = dev.device_structure
+        yt = self._t(y_local)
+        if self.inner and works:
+            ia, ib = self.inner
+            ds.matvec_device(self._slab_ptr(ia), self.x_ext, yt[(ia - ra) * self.plane_rows:(ib - ra) * self.plane_rows],
+                             row0=(ia, ib), x_j0=self.ha)
+            for w in works:
+                w.wait()
+            for (a, b) in ((ra, ia), (ib, rb)):
+                if a < b:
+                    ds.matvec_device(self._slab_ptr(a), self.x_ext, yt[(a - ra) * self.plane_rows:(b - ra) * self.plane_rows],
+                                     row0=(a, b), x_j0=self.ha)
+        else:
+            for w in works:
+                w.wait()
+            ds.matvec_device(self.mlb, self.x_ext, y_local, row0=(ra, rb), x_j0=self.ha)
+        return y_local
+
+    def _slab_ptr(self, row):
+        """view of the MLB slab starting at row `row` of axis 0"""
+        rs = self.dev.row_start0()
+        inner = int(np.prod(self.dev.nband[1:], dtype=np.int64))
+        off = int(rs[row] - rs[self.rows[0]]) * inner
+        return self._t(self.mlb)[off:]
+
+
+def _allsum(t):
+    dist = _dist()
+    if dist is not None:
+        dist.all_reduce(t)
+    return t
+
+
+def cg(op, b, M=None, x0=None, rtol=1e-10, maxiter=200):
+    """Preconditioned conjugate gradients on slab-distributed torch vectors (same recurrences as
+    scipy.sparse.linalg.cg, which the reference uses, ``pyiga/approx.py:92-93``).  `op(x)` and
+    `M(r)` map local slabs to local slabs; dot products are all-reduced.  Returns
+    (x, iterations, [relative residual norms])."""
+    import torch
+    x = torch.zeros_like(b) if x0 is None else x0.clone()
+    r = b - op(x) if x0 is not None else b.clone()
+    bnorm = float(torch.sqrt(_allsum(torch.dot(b, b).reshape(1)))[0])
+    if bnorm == 0.0:
+        return x, 0, [0.0]
+    z = M(r) if M is not None else r
+    p = z.clone()
+    rz = _allsum(torch.dot(r, z).reshape(1))
+    hist = []
+    it = 0
+    for it in range(1, maxiter + 1):
+        Ap = op(p)
+        alpha = rz / _allsum(torch.dot(p, Ap).reshape(1))
+        x += alpha * p
+        r -= alpha * Ap
+        res = float(torch.sqrt(_allsum(torch.dot(r, r).reshape(1)))[0]) / bnorm
+        hist.append(res)
+        if res <= rtol:
+            break
+        z = M(r) if M is not None else r
+        rz_new = _allsum(torch.dot(r, z).reshape(1))
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, it, hist
+
+
+class GatheredKronecker:
+    """Kronecker-product preconditioner on a slab-distributed vector: the vector is a few MB, so it
+    is all-gathered, the mode products run redundantly on every rank, and the local slab is kept."""
+
+    def __init__(self, kron, slabs, rank, plane):
+        self.kron, self.slabs, self.rank, self.plane = kron, slabs, rank, plane
+
+    def __call__(self, r_local):
+        import torch
+        dist = _dist()
+        if dist is None or len(self.slabs) == 1:
+            full = r_local
+        else:
+            sizes = [(b - a) * self.plane for a, b in self.slabs]
+            parts = [torch.empty(s, dtype=r_local.dtype, device=r_local.device) for s in sizes]
+            dist.all_gather(parts, r_local) if len(set(sizes)) == 1 else self._gather_uneven(parts, r_local)
+            full = torch.cat(parts)
+        out = self.kron.matvec_device(full)
+        out = out if isinstance(out, torch.Tensor) else torch.from_numpy(np.asarray(out))
+        a, b = self.slabs[self.rank]
+        return out[a * self.plane:b * self.plane].clone()
+
+    def _gather_uneven(self, parts, r_local):
+        import torch
+        dist = _dist()
+        n = max(p.numel() for p in parts)
+        pad = torch.zeros(n, dtype=r_local.dtype, device=r_local.device)
+        pad[:r_local.numel()] = r_local
+        bufs = [torch.empty_like(pad) for _ in parts]
+        dist.all_gather(bufs, pad)
+        for p, b in zip(parts, bufs):
+            p.copy_(b[:p.numel()])

@@ -34,7 +34,11 @@ class EmuBackend:
         return np.array(buf, copy=True).view(np.ndarray)
 
     def ptr(self, buf):
-        return 0 if buf is None else buf.ctypes.data
+        if buf is None:
+            return 0
+        if hasattr(buf, 'data_ptr'):        # torch view of a host buffer
+            return buf.data_ptr()
+        return buf.ctypes.data
 
     def nbytes(self, buf):
         return buf.nbytes

@@ -232,3 +232,63 @@ def check_vform_protocol(ref):
     K = assemble.assemble(vform.stiffness_vf(2), kvs, geo=geo)
     K2 = assemble.stiffness(kvs, geo)
     assert abs(K - K2).max() <= RTOL * abs(K2).max()
+
+
+def check_kronecker_path(ref):
+    """geo=None: the reference takes the Kronecker shortcut over 1D matrices
+    (pyiga/assemble.py:236-282, test/test_assemble.py:83-100); here the same matrices come from the
+    device with the identity map, and the 1D factors from bsp_*_1d"""
+    import scipy.sparse
+    from pyiga_b200 import assemble, bspline
+    kvs = (bspline.make_knots(3, 0.0, 1.0, 4), bspline.make_knots(2, 0.0, 1.0, 5))
+    M1 = [assemble.mass(kv) for kv in kvs]
+    K1 = [assemble.stiffness(kv) for kv in kvs]
+    # literal 1D matrices of the reference's tests (test/test_assemble.py:10-40) for p=1 on 3 spans
+    kv = bspline.make_knots(1, 0.0, 1.0, 3)
+    np.testing.assert_allclose(assemble.mass(kv).toarray() * 18,
+                               [[2, 1, 0, 0], [1, 4, 1, 0], [0, 1, 4, 1], [0, 0, 1, 2]], atol=1e-13)
+    np.testing.assert_allclose(assemble.stiffness(kv).toarray() / 3,
+                               [[1, -1, 0, 0], [-1, 2, -1, 0], [0, -1, 2, -1], [0, 0, -1, 1]], atol=1e-13)
+    M = assemble.mass(kvs)
+    K = assemble.stiffness(kvs)
+    Mk = scipy.sparse.kron(M1[0], M1[1])
+    Kk = scipy.sparse.kron(K1[0], M1[1]) + scipy.sparse.kron(M1[0], K1[1])
+    assert abs(M - Mk).max() <= 1e-13 * abs(Mk).max()
+    assert abs(K - Kk).max() <= 1e-13 * abs(Kk).max()
+
+
+def check_slab_operator_and_cg(ref, world=1, rank=0):
+    """slab operator == MLMatrix matvec; CG with Kronecker preconditioner converges like scipy's"""
+    import scipy.sparse.linalg
+    import torch
+    from pyiga_b200 import assemble, bspline, geometry
+    from pyiga_b200.dist import GatheredKronecker, SlabAssembly, SlabOperator, cg
+    from pyiga_b200.operators import KroneckerOperator
+    kvs = (bspline.make_knots(2, 0.0, 1.0, 6), bspline.make_knots(3, 0.0, 1.0, 4), bspline.make_knots(2, 0.0, 1.0, 5))
+    geo = geometry.twisted_box()
+    sa = SlabAssembly(kvs, geo, 'mass', rank=rank, world=world)
+    be = sa.dev.be
+    mlb = sa.assemble_mlb()
+    op = SlabOperator(sa.dev, mlb, rows=sa.rows, slabs=sa.slabs, rank=rank)
+    full = SlabAssembly(kvs, geo, 'mass')
+    A = full.assemble_csr()
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(A.shape[1])
+    a, b = sa.rows
+    plane = kvs[1].numdofs * kvs[2].numdofs
+    to_t = lambda v: torch.from_numpy(np.ascontiguousarray(v)) if be.name == 'emu' else be.from_host(v)
+    y = op.matvec(be.from_host(x[a * plane:b * plane]))
+    np.testing.assert_allclose(be.to_host(y), (A @ x)[a * plane:b * plane], rtol=1e-12, atol=1e-14)
+    # CG as in pyiga/approx.py:82-93: Kronecker preconditioner from the inverses of the 1D mass matrices
+    Minv = [np.linalg.inv(assemble.mass(kv).toarray()) for kv in kvs]
+    prec = GatheredKronecker(KroneckerOperator(*Minv), sa.slabs, rank, plane)
+    rhs = A @ np.ones(A.shape[1])
+    bl = to_t(rhs[a * plane:b * plane])
+    xs, it, hist = cg(lambda v: op._t(op.matvec(v)).clone(), bl, M=prec, rtol=1e-10, maxiter=100)
+    xs = np.asarray(xs.cpu()) if hasattr(xs, 'cpu') else np.asarray(xs)
+    np.testing.assert_allclose(xs, 1.0, rtol=0, atol=1e-7)
+    it_ref = [0]
+    scipy.sparse.linalg.cg(A, rhs, rtol=1e-10, atol=0.0, maxiter=100, M=scipy.sparse.linalg.LinearOperator(
+        A.shape, matvec=lambda r: orc.kron_matvec(Minv, r)), callback=lambda xk: it_ref.__setitem__(0, it_ref[0] + 1))
+    assert abs(it - it_ref[0]) <= 1, (it, it_ref[0])
+    return it

@@ -71,3 +71,36 @@ def test_partition_balance(emu):
         sizes = [sa.dev.slab_size(s) for s in slabs]
         assert sum(sizes) == sa.dev.nnz
         assert max(sizes) <= 1.35 * sa.dev.nnz / len(slabs)
+
+
+def _worker_cg(rank, world, port, libpath, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from emu.emu_backend import EmuBackend
+        from pyiga_b200 import _device
+        import parity_checks as pc
+        _device._backend = EmuBackend(libpath)
+        ref = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_cases.npz'))
+        it = pc.check_slab_operator_and_cg(ref, world=world, rank=rank)
+        q.put((rank, it))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_halo_matvec_and_cg(emu_lib, world):
+    """distributed matvec with halo exchange (P2P) + CG with all-reduced dot products, gloo ranks"""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() + world) % 2000
+    procs = [ctx.Process(target=_worker_cg, args=(r, world, port, emu_lib, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    its = dict(q.get(timeout=10) for _ in range(world))
+    assert len(set(its.values())) == 1      # every rank ran the same number of iterations

@@ -79,3 +79,11 @@ def test_vform(emu, ref, name):
 
 def test_vform_protocol(emu, ref):
     pc.check_vform_protocol(ref)
+
+
+def test_kronecker_path_and_1d(emu, ref):
+    pc.check_kronecker_path(ref)
+
+
+def test_slab_operator_and_cg(emu, ref):
+    pc.check_slab_operator_and_cg(ref)

@@ -71,6 +71,14 @@ def test_vform_protocol(cuda, ref):
     pc.check_vform_protocol(ref)
 
 
+def test_kronecker_path_and_1d(cuda, ref):
+    pc.check_kronecker_path(ref)
+
+
+def test_slab_operator_and_cg(cuda, ref):
+    pc.check_slab_operator_and_cg(ref)
+
+
 @pytest.mark.parametrize('force_walk', [False, True])
 @pytest.mark.parametrize('ps,ns', [((2, 2), (4, 70)), ((3, 1), (5, 33)), ((3, 3), (40, 45))])
 def test_long_last_axis_2d(cuda, ps, ns, force_walk):
