@@ -42,6 +42,8 @@ class CudaBackend:
 
     def from_host(self, arr, pinned=False):
         arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:
+            arr = arr.copy()
         if arr.dtype == np.uint64:
             arr = arr.view(np.int64)
         t = self.torch.from_numpy(arr)
