@@ -78,8 +78,9 @@ typedef struct {
     const double* h_coeffs;
 } pb200_geo_desc;
 
-/* One term of a custom bilinear form:  integral of  C(field) * d^{slot_test} v * d^{slot_trial} u.
- * slot 0 = function value, slot 1+k = derivative along tensor axis k (parametric). */
+/* One term of a custom form:  integral of  C(field) * d^{slot_test} v * d^{slot_trial} u.
+ * slot 0 = function value, slot 1+k = derivative along tensor axis k (parametric).
+ * Linear forms (arity 1, load vectors) set slot_trial = -1 in every term. */
 typedef struct { int field, slot_test, slot_trial; } pb200_term;
 
 /* One physical coefficient term of a general first-order scalar form (see
@@ -183,6 +184,12 @@ PB200_API int pb200_asm_set_timing(pb200_assembler* a, int enable);
 PB200_API int pb200_asm_set_option(pb200_assembler* a, const char* name, int value);
 PB200_API int pb200_asm_get_timing(pb200_assembler* a, int max_stages, float* ms, char* names, int names_len,
                                    int* nstages);
+
+/* Linear forms (arity 1): the load vector, ndofs doubles in C order of the test space.  Replaces
+ * BaseAssembler*.assemble_vector (pyiga/genericasm.pxi:129-145, 762-778). */
+PB200_API int pb200_asm_vector_workspace_bytes(const pb200_assembler* a, size_t* bytes);
+PB200_API int pb200_asm_assemble_vector(pb200_assembler* a, double* d_out, void* d_work, size_t work_bytes,
+                                        void* stream);
 
 /* multi_entries(indices) (pyiga/genericasm.pxi:722-758): d_ij is n x 2 uint64 (row, column),
  * d_out n doubles; pairs outside the pattern give 0.0. */

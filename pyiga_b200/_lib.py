@@ -76,6 +76,8 @@ SIGNATURES = {
     'pb200_asm_set_timing': (C.c_int, [C.c_void_p, C.c_int]),
     'pb200_asm_get_timing': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_char_p, C.c_int,
                                        C.POINTER(C.c_int)]),
+    'pb200_asm_vector_workspace_bytes': (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    'pb200_asm_assemble_vector': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'pb200_asm_multi_entries': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     'pb200_asm_mlstruct': (C.c_void_p, [C.c_void_p]),
     'pb200_mlstruct_create': (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

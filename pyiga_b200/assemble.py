@@ -115,6 +115,18 @@ def bsp_stiffness_3d(knotvecs, geo=None, format='csr'):
     return stiffness(knotvecs, geo, format)
 
 
+def inner_products(kvs, f, f_physical=False, geo=None):
+    """L2 inner products of every basis function with `f` (``pyiga/assemble.py:288-340``): array of
+    shape ndofs.  `f` is a function of the parameter coordinates unless `f_physical`."""
+    dim, kvs = _detect_dim(kvs)
+    if dim == 1:
+        raise NotImplementedError('1D inner products are not part of the device path')
+    if geo is None:
+        geo = _default_geo(kvs)
+    name = 'L2FunctionalAssembler%s%dD' % ('Phys' if f_physical else '', dim)
+    return getattr(assemblers, name)(kvs, geo, f).assemble_vector()
+
+
 def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatable=[]):
     """Turn a problem description into an assembler object (``pyiga/assemble.py:914-956``)."""
     if boundary:

@@ -202,6 +202,17 @@ class DeviceAssembler:
                 be.synchronize()    # the temporary workspace is released when `ws` goes out of scope
         return out
 
+    def assemble_vector_device(self):
+        """load vector of a linear form as a flat device buffer (C order of the test space)"""
+        be = self.be
+        n = C.c_size_t()
+        _device.check(be.lib.pb200_asm_vector_workspace_bytes(self.handle, C.byref(n)))
+        ws = be.empty(n.value, np.uint8)
+        out = be.empty(int(np.prod(self.ndofs_test, dtype=np.int64)))
+        _device.check(be.lib.pb200_asm_assemble_vector(self.handle, be.ptr(out), be.ptr(ws), n.value, be.stream()))
+        be.synchronize()
+        return out
+
     def set_option(self, name, value):
         _device.check(self.be.lib.pb200_asm_set_option(self.handle, name.encode(), int(value)))
 
@@ -335,7 +346,7 @@ class GenericFormAssembler(_AssemblerProtocol):
         pairs = set()
         for (bt, bu) in self._keys:
             for bp in ([0] if bt == 0 else range(1, d + 1)):
-                for ap in ([0] if bu == 0 else range(1, d + 1)):
+                for ap in ([-1] if bu < 0 else [0] if bu == 0 else range(1, d + 1)):
                     pairs.add((bp, ap))
         self._pairs = sorted(pairs)
         terms = [(f, bp, ap) for f, (bp, ap) in enumerate(self._pairs)]
@@ -370,7 +381,11 @@ class GenericFormAssembler(_AssemblerProtocol):
             total = val if total is None else total + val
         coefs = {}
         for (bt, bu), c in total.terms.items():
-            if bt is None or bu is None:
+            if self.arity == 1:
+                if bt is None or bu is not None:
+                    raise ValueError('a linear form must be linear in its basis function')
+                bu = -1
+            elif bt is None or bu is None:
                 raise ValueError('the form must be linear in both u and v (term without %s)' % ('v' if bt is None else 'u'))
             if not c.is_zero():
                 coefs[(bt, bu)] = c
@@ -406,6 +421,30 @@ class GenericFormAssembler(_AssemblerProtocol):
             _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, None, be.ptr(d_jac), len(coefs), phys,
                                                                    len(arrays), ptrs, -1, -1, be.stream()))
         be.synchronize()        # the uploaded coefficient arrays may be released now
+
+    # ---- arity 1 ------------------------------------------------------------------------------
+    def assemble_vector(self):
+        """Load vector, shape = number of dofs per axis (``pyiga/genericasm.pxi:762-778``)."""
+        if self.arity != 1:
+            return None
+        return self.dev.be.to_host(self.dev.assemble_vector_device()).reshape(self.dev.ndofs_test)
+
+    def multi_entries(self, indices):
+        if self.arity == 1:
+            return self.multi_entries1(indices)
+        return super().multi_entries(indices)
+
+    def multi_entries1(self, indices):
+        if self.arity != 1:
+            return None
+        idx = np.asarray(indices if isinstance(indices, np.ndarray) else list(indices), dtype=np.int64)
+        return self.assemble_vector().ravel()[idx]
+
+    def entry1(self, i):
+        return float(self.multi_entries1([i])[0]) if self.arity == 1 else 0.0
+
+    def entry(self, i, j):
+        return super().entry(i, j) if self.arity == 2 else 0.0
 
     def update(self, **kwargs):
         """Re-evaluate the given input functions (``pyiga/codegen/cython.py:703-724``)."""
@@ -456,3 +495,57 @@ class MassAssembler3D(_ScalarAssemblerBase):
 class StiffnessAssembler3D(_ScalarAssemblerBase):
     """``inner(grad(u), grad(v)) * dx`` in 3D (``pyiga/assemblers.pyx:1324-1540``)."""
     _form, _dim = _lib.FORM_STIFFNESS, 3
+
+
+class _L2FunctionalBase(GenericFormAssembler):
+    """``f * v * dx`` — load vector of a function (``pyiga/assemblers.pyx:1959-2504``).  `f` lives on
+    the parameter domain (L2FunctionalAssembler) or on the physical domain (...Phys)."""
+    _physical = False
+    _dim = None
+
+    @classmethod
+    def inputs(cls):
+        return {'geo': (cls._dim,), 'f': ()}
+
+    @classmethod
+    def parameters(cls):
+        return {}
+
+    def __init__(self, kvs0, geo, f):
+        from . import vform
+        vf = vform.VForm(self._dim, arity=1)
+        v = vf.basisfuns()
+        fin = vf.input('f', shape=(), physical=self._physical)
+        vf.add(fin * v * vf.dx)
+        self._vf = vf
+        if not self._physical and not hasattr(f, 'grid_eval'):
+            f = _ParametricCallable(f)
+        super().__init__(kvs0, geo=geo, f=f)
+
+
+class _ParametricCallable:
+    """plain callable evaluated on the parameter grid (``pyiga/utils.py:33-41`` grid_eval)"""
+    def __init__(self, f):
+        self.f = f
+
+    def grid_eval(self, grid):
+        mesh = list(np.meshgrid(*grid, sparse=True, indexing='ij'))
+        mesh.reverse()
+        shape = tuple(len(g) for g in grid)
+        return np.broadcast_to(np.asarray(self.f(*mesh), dtype=float), shape)
+
+
+class L2FunctionalAssembler2D(_L2FunctionalBase):
+    _dim = 2
+
+
+class L2FunctionalAssembler3D(_L2FunctionalBase):
+    _dim = 3
+
+
+class L2FunctionalAssemblerPhys2D(_L2FunctionalBase):
+    _dim, _physical = 2, True
+
+
+class L2FunctionalAssemblerPhys3D(_L2FunctionalBase):
+    _dim, _physical = 3, True

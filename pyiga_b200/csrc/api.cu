@@ -19,6 +19,7 @@
 #include "geo_fields.cuh"
 #include "mlb.cuh"
 #include "plans.cuh"
+#include "walk1.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -203,6 +204,17 @@ PbWalkLaunch pb_find_walk(int plan_id, int P, int Q) {
     return it == registry().end() ? nullptr : it->second;
 }
 
+typedef std::map<std::pair<int, int>, PbWalk1Launch> Walk1Registry;
+static Walk1Registry& registry1() {
+    static Walk1Registry r;
+    return r;
+}
+extern "C" void pb200_register_walk1(int P, int Q, PbWalk1Launch fn) { registry1()[std::make_pair(P, Q)] = fn; }
+PbWalk1Launch pb_find_walk1(int P, int Q) {
+    auto it = registry1().find(std::make_pair(P, Q));
+    return it == registry1().end() ? nullptr : it->second;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side axis tables
 // ------------------------------------------------------------------------------------------------
@@ -332,6 +344,7 @@ struct pb200_assembler {
     int nfields = 0;
     bool symmetric = false;
     bool same_space = true;
+    int arity = 2;
     AxisHost hax[PB_MAXDIM];
     PbAxis dax[PB_MAXDIM];
     size_t off_knots_u[PB_MAXDIM], off_knots_v[PB_MAXDIM];
@@ -415,6 +428,11 @@ static int detect_fast_path(const pb200_assembler* a) {
     if (a->form == PB200_FORM_MASS) {
         for (int k = 0; k < a->dim; ++k)
             if (!have_plan(PB_PLAN_COPY, P(k), Q)) return 0;
+        return 1;
+    }
+    if (a->form == PB200_FORM_CUSTOM && a->arity == 1) {
+        for (int k = 0; k < a->dim; ++k)
+            if (!pb_find_walk1(P(k), Q)) return 0;
         return 1;
     }
     if (a->form == PB200_FORM_CUSTOM) {
@@ -530,12 +548,16 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
         if (desc->nterms < 1 || desc->nterms > PB_MAXTERMS || !desc->terms) return fail(PB200_EINVAL, "invalid number of terms %d", desc->nterms);
         a->nfields = desc->nfields;
         a->symmetric = desc->symmetric != 0;
+        int nlinear = 0;
         for (int t = 0; t < desc->nterms; ++t) {
             const pb200_term& T = desc->terms[t];
-            if (T.field < 0 || T.field >= a->nfields || T.slot_test < 0 || T.slot_test > dim || T.slot_trial < 0 || T.slot_trial > dim)
+            if (T.field < 0 || T.field >= a->nfields || T.slot_test < 0 || T.slot_test > dim || T.slot_trial < -1 || T.slot_trial > dim)
                 return fail(PB200_EINVAL, "invalid term %d", t);
+            nlinear += T.slot_trial < 0;
             a->terms.push_back(PbTerm{T.field, T.slot_test, T.slot_trial});
         }
+        if (nlinear != 0 && nlinear != desc->nterms) return fail(PB200_EINVAL, "terms mix linear and bilinear slots");
+        a->arity = nlinear ? 1 : 2;
         a->field_slots.assign(a->nfields, std::make_pair(-1, -1));
         for (const PbTerm& T : a->terms) {
             if (a->field_slots[T.field].first >= 0) return fail(PB200_EINVAL, "field %d is used by more than one term", T.field);
@@ -797,7 +819,8 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
         prm.nphys = gen->nphys;
         for (int t = 0; t < gen->nphys; ++t) {
             const pb200_phys_term& T = gen->phys[t];
-            if (T.slot_test < 0 || T.slot_test > a->dim || T.slot_trial < 0 || T.slot_trial > a->dim || T.input >= gen->ninputs)
+            const int lo = a->arity == 1 ? -1 : 0, hi = a->arity == 1 ? -1 : a->dim;
+            if (T.slot_test < 0 || T.slot_test > a->dim || T.slot_trial < lo || T.slot_trial > hi || T.input >= gen->ninputs)
                 return fail(PB200_EINVAL, "invalid coefficient term %d", t);
             prm.phys[t].bt = T.slot_test; prm.phys[t].bu = T.slot_trial;
             prm.phys[t].input = T.input < 0 ? -1 : T.input;
@@ -1014,7 +1037,7 @@ static void stage_sizes(const pb200_assembler* a, const Slab& S, size_t& x1_term
 
 extern "C" int pb200_asm_workspace_bytes(const pb200_assembler* a, int row0_begin, int row0_end, size_t* bytes) {
     if (!a || !bytes) return fail(PB200_EINVAL, "null argument");
-    if (!a->fast) { *bytes = 0; return 0; }
+    if (!a->fast || a->arity != 2) { *bytes = 0; return 0; }
     Slab S;
     int rc = make_slab(a, row0_begin, row0_end, uses_transposes(a), S);
     if (rc) return rc;
@@ -1052,9 +1075,103 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// linear forms: load vector by three single-function walks
+// ------------------------------------------------------------------------------------------------
+struct Gen1Stage { std::vector<int> out_slot; std::vector<std::array<int, 2>> ops; };   // per output: input for ft = 0 / 1
+
+static void plan_linear(const pb200_assembler* a, std::vector<Gen1Stage>& stages) {
+    std::vector<std::pair<int, int>> cur;       // (test slot, buffer slot)
+    for (const PbTerm& t : a->terms) cur.push_back(std::make_pair(t.bt, t.field));
+    for (int k = 0; k < a->dim; ++k) {
+        Gen1Stage S;
+        std::vector<std::pair<int, int>> next;
+        for (auto& t : cur) {
+            const int ft = t.first == 1 + k;
+            const int bt = ft ? 0 : t.first;
+            size_t o = 0;
+            for (; o < S.out_slot.size(); ++o)
+                if (S.out_slot[o] == bt) break;
+            if (o == S.out_slot.size()) { S.out_slot.push_back(bt); S.ops.push_back({-1, -1}); next.push_back(std::make_pair(bt, (int)o)); }
+            S.ops[o][ft] = t.second;
+        }
+        stages.push_back(S);
+        cur = next;
+    }
+}
+
+extern "C" int pb200_asm_vector_workspace_bytes(const pb200_assembler* a, size_t* bytes) {
+    if (!a || !bytes) return fail(PB200_EINVAL, "null argument");
+    if (a->arity != 1) return fail(PB200_EINVAL, "not a linear form");
+    size_t y1 = 1, y2 = 1;
+    y1 = (size_t)a->hax[0].V.N() * a->hax[1].G * (a->dim == 3 ? a->hax[2].G : 1);
+    y2 = a->dim == 3 ? (size_t)a->hax[0].V.N() * a->hax[1].V.N() * a->hax[2].G : 0;
+    *bytes = (y1 * (a->dim + 1) + y2 * a->dim) * sizeof(double) + 512;
+    return 0;
+}
+
+extern "C" int pb200_asm_assemble_vector(pb200_assembler* a, double* d_out, void* d_work, size_t work_bytes, void* stream) {
+    if (!a || !d_out) return fail(PB200_EINVAL, "null argument");
+    if (a->arity != 1) return fail(PB200_EINVAL, "assemble_vector needs a linear form (arity 1)");
+    if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
+    if (!a->fast) return fail(PB200_EUNSUPPORTED, "no vector kernels for these degrees");
+    CK(pbSetDevice(a->device));
+    pbStream st = (pbStream)stream;
+    size_t need = 0;
+    int rc = pb200_asm_vector_workspace_bytes(a, &need);
+    if (rc) return rc;
+    if (!d_work || work_bytes < need) return fail(PB200_ENOMEM, "workspace too small: need %zu bytes, have %zu", need, work_bytes);
+    const int dim = a->dim;
+    const long long N0 = a->hax[0].V.N(), N1 = a->hax[1].V.N(), G1 = a->hax[1].G;
+    const long long G2 = dim == 3 ? a->hax[2].G : 1, N2 = dim == 3 ? a->hax[2].V.N() : 1;
+    const size_t y1 = (size_t)N0 * G1 * G2, y2 = dim == 3 ? (size_t)N0 * N1 * G2 : 0;
+    double* Y1 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(d_work) + 255) & ~uintptr_t(255));
+    double* Y2 = Y1 + y1 * (dim + 1);
+    std::vector<Gen1Stage> stages;
+    plan_linear(a, stages);
+    for (int k = 0; k < dim; ++k) {
+        const AxisHost& H = a->hax[k];
+        PbWalk1Launch fn = pb_find_walk1(H.U.p, H.q);
+        if (!fn) return fail(PB200_EUNSUPPORTED, "no vector kernel for p=%d, q=%d", H.U.p, H.q);
+        const bool last = k == dim - 1;
+        const double* inbase = k == 0 ? a->d_fields : (k == 1 ? Y1 : Y2);
+        const long long instride = k == 0 ? a->npts : (k == 1 ? (long long)y1 : (long long)y2);
+        double* outbase = last ? d_out : (k == 0 ? Y1 : Y2);
+        const long long outstride = last ? 0 : (k == 0 ? (long long)y1 : (long long)y2);
+        for (size_t o = 0; o < stages[k].out_slot.size(); ++o) {
+            PbWalk1Params p;
+            memset(&p, 0, sizeof p);
+            p.in0 = stages[k].ops[o][0] >= 0 ? inbase + (long long)stages[k].ops[o][0] * instride : nullptr;
+            p.in1 = stages[k].ops[o][1] >= 0 ? inbase + (long long)stages[k].ops[o][1] * instride : nullptr;
+            p.out = outbase + (long long)o * outstride;
+            p.n = H.n; p.N = H.V.N();
+            p.first = a->dax[k].first_u; p.V2 = a->dax[k].Vu;
+            if (k == 0) {                           // F[g0][g1][g2] -> Y1[i0][g1][g2]
+                p.X = (int)(G1 * G2); p.nthreads = G1 * G2;
+                p.in_sx = 1; p.in_sc = G1 * G2; p.out_sx = 1; p.out_sf = G1 * G2;
+            } else if (k == 1 && dim == 3) {        // Y1[i0][g1][g2] -> Y2[i0][i1][g2]
+                p.X = (int)G2; p.nthreads = N0 * G2;
+                p.in_su = G1 * G2; p.in_sx = 1; p.in_sc = G2;
+                p.out_su = N1 * G2; p.out_sx = 1; p.out_sf = G2;
+            } else if (dim == 2) {                  // Y1[i0][g1] -> out[i0][i1]
+                p.X = 1; p.nthreads = N0;
+                p.in_su = G1; p.in_sc = 1; p.out_su = N1; p.out_sf = 1;
+            } else {                                // Y2[i0][i1][g2] -> out[i0][i1][i2]
+                p.X = 1; p.nthreads = N0 * N1;
+                p.in_su = G2; p.in_sc = 1; p.out_su = N2; p.out_sf = 1;
+            }
+            ++g_launches;
+            int e = fn(&p, st);
+            if (e) return fail(PB200_ECUDA, "vector kernel launch failed: %s", pbErrorString((pbError)e));
+        }
+    }
+    return 0;
+}
+
 extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int row0_end, double* d_out, void* d_work,
                                       size_t work_bytes, void* stream) {
     if (!a || !d_out) return fail(PB200_EINVAL, "null argument");
+    if (a->arity != 2) return fail(PB200_EINVAL, "matrix assembly needs a bilinear form (arity 2)");
     if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
     if (!a->fast) return pb200_asm_assemble_mlb_entrywise(a, row0_begin, row0_end, d_out, stream);
     CK(pbSetDevice(a->device));
@@ -1273,6 +1390,7 @@ static void fill_entry_params(const pb200_assembler* a, PbEntryParams& prm) {
 
 extern "C" int pb200_asm_multi_entries(pb200_assembler* a, const uint64_t* d_ij, size_t n, double* d_out, void* stream) {
     if (!a || (n && (!d_ij || !d_out))) return fail(PB200_EINVAL, "null argument");
+    if (a->arity != 2) return fail(PB200_EINVAL, "multi_entries needs a bilinear form (arity 2)");
     if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
     if (n == 0) return 0;
     CK(pbSetDevice(a->device));

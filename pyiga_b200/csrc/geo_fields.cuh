@@ -201,8 +201,11 @@ template <int DIM> struct PbProgGeneral {
         for (int t = 0; t < prm.nphys; ++t) {
             const int in = prm.phys[t].input;
             const double cv = W * prm.phys[t].scale * (in >= 0 ? prm.inputs[in][pt.idx] : 1.0);
-            for (int c = 0; c < prm.nf; ++c)
-                f[c] = fma(cv, T[prm.phys[t].bt][prm.outmap[c].bp] * T[prm.phys[t].bu][prm.outmap[c].ap], f[c]);
+            for (int c = 0; c < prm.nf; ++c) {
+                // linear forms have no trial function: slot -1 on both sides
+                const double tu = prm.outmap[c].ap < 0 ? 1.0 : T[prm.phys[t].bu][prm.outmap[c].ap];
+                f[c] = fma(cv, T[prm.phys[t].bt][prm.outmap[c].bp] * tu, f[c]);
+            }
         }
     }
 };

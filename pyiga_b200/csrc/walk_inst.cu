@@ -2,6 +2,7 @@
 // Compiled once per pair with -DPB_P=<p> -DPB_Q=<q>; each object registers its launchers.
 #include "backend.cuh"
 #include "plans.cuh"
+#include "walk1.cuh"
 
 #ifndef PB_P
 #error "compile with -DPB_P=<degree> -DPB_Q=<nodes per span>"
@@ -48,8 +49,22 @@ int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* strea
 #endif
 }
 
+int launch_walk1(const PbWalk1Params* prm, void* stream) {
+#ifdef PB_EMULATE
+    (void)stream;
+    pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk1_line<PB_P, PB_Q>(*prm, tid); });
+    return 0;
+#else
+    const long long blocks = (prm->nthreads + 127) / 128;
+    if (blocks <= 0) return 0;
+    pb_walk1_kernel<PB_P, PB_Q><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*prm);
+    return (int)cudaGetLastError();
+#endif
+}
+
 struct Registrar {
     Registrar() {
+        pb200_register_walk1(PB_P, PB_Q, &launch_walk1);
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_COPY, PB_P, PB_Q, &launch_lane<PbPlanCopy>);
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_FINAL4, PB_P, PB_Q, &launch_lane<PbPlanFinal4>);
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_GEN4, PB_P, PB_Q, &launch_lane<PbPlanGen4>);

@@ -16,8 +16,9 @@ parameter domain (``J^-1``, ``|det J|``, Gauss weights) happens in the K2 kernel
 (``csrc/geo_fields.cuh: PbProgGeneral``).  The matrix itself comes from the same sum-factorised
 pipeline as mass and stiffness (``pb200_asm_assemble_mlb`` with a generic stage plan).
 
-Vector-valued basis functions, second derivatives, boundary integrals and arity-1 forms are not
-part of the device path; they raise ``NotImplementedError``.
+Linear forms (arity 1, e.g. ``'f * v * dx'``) give load vectors through the same machinery.
+Vector-valued basis functions, second derivatives and boundary integrals are not part of the
+device path; they raise ``NotImplementedError``.
 """
 import re
 
@@ -542,8 +543,6 @@ def compile_vform(vf):
     """Return an assembler *class* for the form, like ``pyiga.compile.compile_vform``
     (``pyiga/compile.py:120-132``); no code is generated — the class analyses the form when it is
     instantiated on a concrete space."""
-    if vf.arity != 2:
-        raise NotImplementedError('arity-1 forms (load vectors) are not part of the device path yet')
     input_shapes = {'geo': (vf.dim,)}
     input_shapes.update({name: shape for name, shape, _, _ in vf.inputs})
     param_shapes = {name: shape for name, shape in vf.params}

@@ -162,6 +162,17 @@ def main():
     out['vf_upd_a'] = np.asarray(asm.assemble()[I.astype(np.int64), J.astype(np.int64)]).ravel()
     out['vf_upd_b'] = np.asarray(asm.assemble(f=lambda x, y: 2.0 + y * y)[I.astype(np.int64), J.astype(np.int64)]).ravel()
 
+    # ---- 7. linear forms: assemble_vector / inner_products (test/test_assemble.py:223-245) --------
+    from helpers import LFORMS
+    for name, (form, inputs, case, gname) in LFORMS.items():
+        kvs, _ = cases[case]
+        out['lf_%s' % name] = assemble.assemble(form, kvs, geo=geos[gname], **inputs)
+    kvs, _ = cases['a3_tb']
+    fpar = lambda x, y, z: x + 2 * y * z
+    out['ip_param'] = assemble.inner_products(kvs, fpar, geo=geos['tb'])
+    out['ip_phys'] = assemble.inner_products(kvs, fpar, f_physical=True, geo=geos['tnb'])
+    out['ip_nogeo'] = assemble.inner_products(kvs, fpar)
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

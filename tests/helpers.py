@@ -76,3 +76,10 @@ VFORMS = {
     'sqrt3': ('sqrt(kappa) * inner(grad(u), grad(v)) / (1.0 + x[2]) * dx',
               {'kappa': lambda x, y, z: 1.0 + x * x + z}, 'a3_p1', 'tb'),
 }
+
+# linear forms (arity 1): name -> (form string, inputs, space case, geometry)
+LFORMS = {
+    'lin3': ('(f * v + inner((1.0, x[0], -2.0), grad(v))) * dx', {'f': lambda x, y, z: x * y + z * z}, 'a3_mixed', 'tb'),
+    'lin2': ('g * v * dx', {'g': lambda x, y: x * y + 1.0}, 'a2_qa', 'qa'),
+    'lin3n': ('inner(b, grad(v)) * dx', {'b': lambda x, y, z: (y, 1.0 + x, z * x)}, 'a3_nurbs', 'tnb'),
+}

@@ -292,3 +292,25 @@ def check_slab_operator_and_cg(ref, world=1, rank=0):
         A.shape, matvec=lambda r: orc.kron_matvec(Minv, r)), callback=lambda xk: it_ref.__setitem__(0, it_ref[0] + 1))
     assert abs(it - it_ref[0]) <= 1, (it, it_ref[0])
     return it
+
+
+def check_linear_forms(ref):
+    """arity-1 forms: assemble_vector through assemble.assemble and inner_products"""
+    from helpers import LFORMS
+    from pyiga_b200 import assemble, assemblers
+    for name, (form, inputs, case, gname) in LFORMS.items():
+        kvs = make_space(ref, case)
+        got = assemble.assemble(form, kvs, geo=make_geo(ref, gname), **inputs)
+        want = ref['lf_%s' % name]
+        assert got.shape == want.shape == tuple(kv.numdofs for kv in kvs)
+        assert_close_rel(got, want, what='linear form ' + name)
+    kvs = make_space(ref, 'a3_tb')
+    fpar = lambda x, y, z: x + 2 * y * z
+    assert_close_rel(assemble.inner_products(kvs, fpar, geo=make_geo(ref, 'tb')), ref['ip_param'], what='inner_products')
+    assert_close_rel(assemble.inner_products(kvs, fpar, f_physical=True, geo=make_geo(ref, 'tnb')), ref['ip_phys'],
+                     what='inner_products physical')
+    assert_close_rel(assemble.inner_products(kvs, fpar), ref['ip_nogeo'], what='inner_products geo=None')
+    asm = assemblers.L2FunctionalAssemblerPhys3D(kvs, make_geo(ref, 'tnb'), fpar)
+    assert asm.arity == 1 and asm.entry(0, 0) == 0.0
+    vec = asm.assemble_vector()
+    assert np.array_equal(asm.multi_entries([0, 5, 7]), vec.ravel()[[0, 5, 7]])

@@ -87,3 +87,7 @@ def test_kronecker_path_and_1d(emu, ref):
 
 def test_slab_operator_and_cg(emu, ref):
     pc.check_slab_operator_and_cg(ref)
+
+
+def test_linear_forms(emu, ref):
+    pc.check_linear_forms(ref)

@@ -71,6 +71,10 @@ def test_vform_protocol(cuda, ref):
     pc.check_vform_protocol(ref)
 
 
+def test_linear_forms(cuda, ref):
+    pc.check_linear_forms(ref)
+
+
 def test_kronecker_path_and_1d(cuda, ref):
     pc.check_kronecker_path(ref)
 
