@@ -154,12 +154,19 @@ static void k_csr(const PbMlbParams& p, long long nrows, long long count, IdxT* 
     g_launches += 2;
 #ifdef PB_EMULATE
     pb_emu_for(nrows + 1, [&](long long r) { pb_csr_indptr_row<IdxT>(p, nrows, indptr, r); });
-    pb_emu_for(count, [&](long long e) { pb_csr_fill_elem<IdxT>(p, indices, values, e); });
+    pb_emu_for(nrows, [&](long long r) {
+        int i[3] = {0, 0, 0}, rs[3] = {0, 0, 0}, nb[3] = {1, 1, 1}, jm[3] = {0, 0, 0};
+        pb_csr_row_tables(p, r, i, rs, nb, jm);
+        const long long rowoff = pb_csr_row_offset(p, i);
+        for (int e = 0; e < nb[0] * nb[1] * nb[2]; ++e) pb_csr_fill_row_entry<IdxT>(p, i, rs, nb, jm, rowoff, e, indices, values);
+    });
+    (void)count;
 #else
     const unsigned b1 = (unsigned)((nrows + 1 + 255) / 256);
-    const unsigned b2 = (unsigned)std::min<long long>((count + 255) / 256, 148LL * 64);
+    const unsigned b2 = (unsigned)std::min<long long>((nrows + 7) / 8, 148LL * 32);
     pb_csr_indptr_kernel<IdxT><<<b1, 256, 0, st>>>(p, nrows, indptr);
-    pb_csr_fill_kernel<IdxT><<<b2, 256, 0, st>>>(p, count, indices, values);
+    pb_csr_fill_rows_kernel<IdxT><<<b2, 256, 0, st>>>(p, nrows, indices, values);
+    (void)count;
 #endif
 }
 
@@ -357,6 +364,7 @@ struct pb200_assembler {
     int fast = 0;
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
+    bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
     // optional per-kernel timing of the last assemble call (CUDA events on the launch stream)
     bool timing = false;
     std::vector<std::string> stage_names;
@@ -384,6 +392,7 @@ static void mark_stage(pb200_assembler* a, const char* name, pbStream st) {
 extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int value) {
     if (!a || !name) return fail(PB200_EINVAL, "null argument");
     if (!strcmp(name, "force_walk")) { a->force_walk = value != 0; return 0; }
+    if (!strcmp(name, "lane_v1")) { a->lane_v1 = value != 0; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
 }
 
@@ -1063,7 +1072,7 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     if (prm.in_sc == 1 && prm.out_smu == 1 && prm.w_mode == 0 && a->lane_ok[axis] && !a->force_walk) {
         PbWalkLaunch lane = pb_find_walk(PB_PLAN_LANE_BASE + plan, P, Q);
         if (lane) {
-            int e = lane(&prm, 16, 0, st);
+            int e = lane(&prm, a->lane_v1 ? -16 : 64, 0, st);
             if (e) return fail(PB200_ECUDA, "lane-span kernel launch failed (plan %d, p=%d, q=%d): %s", plan, P, Q, pbErrorString((pbError)e));
             return 0;
         }

@@ -70,6 +70,39 @@ PB_HD void pb_csr_fill_elem(const PbMlbParams& p, IdxT* indices, double* values,
     values[pos] = p.data[e];
 }
 
+// CSR export, one matrix row: entry e = (k0*nb1 + k1)*nb2 + k2 of row (i0,i1,i2) comes from
+// data[mu0 = rs0[i0]+k0][mu1 = rs1[i1]+k1][mu2 = rs2[i2]+k2].  Written so that consecutive e are
+// consecutive CSR slots (a warp fills a row with coalesced stores; the reads are runs of nb2).
+template <class IdxT>
+PB_HD void pb_csr_fill_row_entry(const PbMlbParams& p, const int* i, const int* rs, const int* nb, const int* jm,
+                                 long long rowoff, int e, IdxT* indices, double* values) {
+    const int mu0_base = p.row_start[0][p.row0_begin];
+    if (p.dim == 2) {
+        const int k1 = e % nb[1], k0 = e / nb[1];
+        const long long src = (long long)(rs[0] + k0 - mu0_base) * p.M[1] + rs[1] + k1;
+        indices[rowoff + e] = (IdxT)((long long)(jm[0] + k0) * p.Nu[1] + jm[1] + k1);
+        values[rowoff + e] = p.data[src];
+    } else {
+        const int k2 = e % nb[2], t = e / nb[2];
+        const int k1 = t % nb[1], k0 = t / nb[1];
+        const long long src = ((long long)(rs[0] + k0 - mu0_base) * p.M[1] + rs[1] + k1) * p.M[2] + rs[2] + k2;
+        indices[rowoff + e] = (IdxT)(((long long)(jm[0] + k0) * p.Nu[1] + jm[1] + k1) * p.Nu[2] + jm[2] + k2);
+        values[rowoff + e] = p.data[src];
+    }
+    (void)i;
+}
+
+PB_HD void pb_csr_row_tables(const PbMlbParams& p, long long r, int* i, int* rs, int* nb, int* jm) {
+    long long t = r;
+    for (int k = p.dim - 1; k >= 1; --k) { i[k] = (int)(t % p.Nv[k]); t /= p.Nv[k]; }
+    i[0] = (int)t + p.row0_begin;
+    for (int k = 0; k < p.dim; ++k) {
+        rs[k] = p.row_start[k][i[k]];
+        nb[k] = p.row_start[k][i[k] + 1] - rs[k];
+        jm[k] = p.jmin[k][i[k]];
+    }
+}
+
 // y[I] = sum_J A[I,J] x[J] for one row of the slab.  `x` starts at trial index j0 = x_j0_begin on
 // axis 0 (halo layout of the slab-distributed operator); y starts at row0_begin.
 PB_HD void pb_mlb_matvec_row(const PbMlbParams& p, const double* __restrict__ x, int x_j0_begin,
@@ -131,6 +164,20 @@ __global__ void pb_csr_fill_kernel(const __grid_constant__ PbMlbParams p, long l
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride)
         pb_csr_fill_elem<IdxT>(p, indices, values, e);
+}
+// one warp per matrix row
+template <class IdxT>
+__global__ void __launch_bounds__(256) pb_csr_fill_rows_kernel(const __grid_constant__ PbMlbParams p, long long nrows,
+                                                               IdxT* indices, double* values) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+        int i[3] = {0, 0, 0}, rs[3] = {0, 0, 0}, nb[3] = {1, 1, 1}, jm[3] = {0, 0, 0};
+        pb_csr_row_tables(p, r, i, rs, nb, jm);
+        const long long rowoff = pb_csr_row_offset(p, i);
+        const int len = nb[0] * nb[1] * nb[2];
+        for (int e = lane; e < len; e += 32) pb_csr_fill_row_entry<IdxT>(p, i, rs, nb, jm, rowoff, e, indices, values);
+    }
 }
 __global__ void __launch_bounds__(256) pb_mlb_matvec_kernel(const __grid_constant__ PbMlbParams p, long long nrows,
                                                             const double* __restrict__ x, int x_j0_begin,

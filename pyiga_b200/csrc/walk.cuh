@@ -542,4 +542,178 @@ __global__ void __launch_bounds__(128) pb_lane_span_kernel(const __grid_constant
         }
     }
 }
+// -------------------------------------------------------------------------------------------------
+// v2 of the warp-per-line kernel: asynchronous staging through shared memory.
+//   * loads: every line segment (32 spans x Q nodes per input term) is copied global -> shared with
+//     cp.async in 16-byte pieces (8-byte for odd Q) that are contiguous across the warp, NST line
+//     segments ahead of their use; no registers are tied up by data in flight.  For Q = 4 the
+//     16-byte pieces are XOR-swizzled so that the per-lane 32-byte reads are bank-conflict free.
+//   * stores: the 2P+1 finished entries of every lane are first placed at their band offset in a
+//     per-warp shared buffer and then written by consecutive lanes, i.e. as full 32-byte sectors.
+// -------------------------------------------------------------------------------------------------
+PB_D void pb_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pb_smem_u32(smem)), "l"(gmem) : "memory");
+}
+PB_D void pb_cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pb_smem_u32(smem)), "l"(gmem) : "memory");
+}
+PB_D void pb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PB_D void pb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int P, int Q> struct PbLaneCfg {
+    static constexpr int SEG = 32 * Q;                      // doubles per term and line segment
+    static constexpr int OUTSLOTS = (32 + P) * (2 * P + 1); // staging slots for finished entries
+    static constexpr int OUTPAD = (OUTSLOTS + 31) / 32 * 32;
+};
+
+template <class Plan, int P, int Q, int NST>
+__global__ void __launch_bounds__(128, 3) pb_lane_span_kernel_v2(const __grid_constant__ PbWalkParams prm, int lines_per_warp) {
+    constexpr int P1 = P + 1, NOPS = Plan::NOPS;
+    using Cfg = PbLaneCfg<P, Q>;
+    constexpr int SEG = Cfg::SEG;
+    constexpr bool VEC = (Q % 2 == 0);                      // 16-byte pieces
+    constexpr int STAGE = NOPS * SEG;                       // doubles per pipeline stage
+    extern __shared__ __align__(16) double pb_lane_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + Cfg::OUTPAD);
+    double* obuf = ring + NST * STAGE;
+
+    const long long warp = (long long)blockIdx.x * 4 + wib;
+    const int batch = blockIdx.y;
+    const long long line0 = warp * lines_per_warp;
+    if (line0 >= prm.nthreads) return;
+    const long long line1 = (line0 + lines_per_warp < prm.nthreads) ? line0 + lines_per_warp : prm.nthreads;
+
+    const int sb = prm.s_begin + batch * (32 - P);
+    const int s = sb + lane;
+    const bool active = s < prm.s_end;
+    const int m = prm.first[prm.s_begin] + (sb - prm.s_begin) + lane;
+    const bool writer = (batch == 0 || lane >= P) && m < prm.N;
+    const long long seg_node0 = (long long)sb * Q;                       // first node of the segment
+    const long long seg_nodes = (long long)(pb_min(prm.s_end, sb + 32) - sb) * Q;   // valid nodes in it
+
+    double D[Q][2][P1];
+#pragma unroll
+    for (int gq = 0; gq < Q; ++gq) {
+        const double* Vn = prm.V2 + (long long)((active ? s : prm.s_begin) * Q + gq) * 2 * P1;
+#pragma unroll
+        for (int a = 0; a < P1; ++a) {
+            D[gq][0][a] = active ? __ldg(Vn + a) : 0.0;
+            D[gq][1][a] = active ? __ldg(Vn + P1 + a) : 0.0;
+        }
+    }
+    // band offsets of this lane's entries relative to the smallest one written by the warp
+    int mu[2 * P + 1];
+    int mu_lo = 0x7fffffff, mu_hi = -1;
+#pragma unroll
+    for (int k = 0; k <= 2 * P; ++k) {
+        mu[k] = writer ? __ldg(prm.ret_mu + (long long)m * (2 * P + 1) + k) : -1;
+        if (mu[k] >= 0) { mu_lo = pb_min(mu_lo, mu[k]); mu_hi = pb_max(mu_hi, mu[k]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mu_lo = pb_min(mu_lo, __shfl_xor_sync(0xffffffffu, mu_lo, o));
+        mu_hi = pb_max(mu_hi, __shfl_xor_sync(0xffffffffu, mu_hi, o));
+    }
+    if (mu_hi < 0) return;                                              // nothing to write in this batch
+    const int nslots = mu_hi - mu_lo + 1;                               // <= OUTSLOTS
+    // which staging slots does this warp own?  (bit j of `mine`: slot lane + 32 j)
+    for (int t = lane; t < Cfg::OUTPAD; t += 32) obuf[t] = 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k <= 2 * P; ++k)
+        if (mu[k] >= 0) obuf[mu[k] - mu_lo] = 1.0;
+    __syncwarp();
+    unsigned mine = 0;
+#pragma unroll
+    for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
+        if (obuf[lane + 32 * j] != 0.0) mine |= 1u << j;
+    __syncwarp();
+
+    // asynchronous copy of one line segment into ring stage `st`
+    auto issue = [&](long long line, int st) {
+        const PbLineOffsets lo = pb_decode_line<Plan>(prm, line);
+        double* dst = ring + (size_t)st * STAGE;
+        if (lo.keep) {
+            pb_static_for<0, NOPS>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                if (prm.in[i]) {
+                    const double* src = prm.in[i] + (Plan::op(i).tr ? lo.in_tr : lo.in) + seg_node0;
+                    if constexpr (VEC) {
+#pragma unroll
+                        for (int c = lane; c < SEG / 2; c += 32) {
+                            if (2 * c < seg_nodes) {
+                                const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
+                                pb_cp_async16(dst + i * SEG + 2 * pc, src + 2 * c);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = lane; e < SEG; e += 32)
+                            if (e < seg_nodes) pb_cp_async8(dst + i * SEG + e, src + e);
+                    }
+                }
+            });
+        }
+        pb_cp_async_commit();
+    };
+
+#pragma unroll
+    for (int j = 0; j < NST - 1; ++j) {
+        if (line0 + j < line1) issue(line0 + j, j);
+        else pb_cp_async_commit();
+    }
+    int st = 0;
+    for (long long line = line0; line < line1; ++line) {
+        __syncwarp();                                   // everyone is done with the stage refilled below
+        if (line + NST - 1 < line1) issue(line + NST - 1, (st + NST - 1) % NST);
+        else pb_cp_async_commit();
+        pb_cp_async_wait<NST - 1>();
+        __syncwarp();
+        const PbLineOffsets lo = pb_decode_line<Plan>(prm, line);
+        if (lo.keep) {                                  // warp-uniform
+            const double* src = ring + (size_t)st * STAGE;
+            double x[Q][NOPS];
+            pb_static_for<0, NOPS>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                if constexpr (VEC) {
+#pragma unroll
+                    for (int h = 0; h < Q / 2; ++h) {
+                        const int c = lane * (Q / 2) + h;
+                        const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
+                        const double2 v = *reinterpret_cast<const double2*>(src + i * SEG + 2 * pc);
+                        x[2 * h][i] = (active && prm.in[i]) ? v.x : 0.0;
+                        x[2 * h + 1][i] = (active && prm.in[i]) ? v.y : 0.0;
+                    }
+                } else {
+#pragma unroll
+                    for (int gq = 0; gq < Q; ++gq)
+                        x[gq][i] = (active && prm.in[i]) ? src[i * SEG + lane * Q + gq] : 0.0;
+                }
+            });
+            double L[P1][P1];
+            pb_span_block<Plan, P, Q>(x, D, L);
+#pragma unroll
+            for (int k = 0; k <= 2 * P; ++k) {
+                const int d = (k <= P) ? k : k - P;
+                double sum = (k <= P) ? L[0][d] : L[d][0];
+#pragma unroll
+                for (int t = 1; t <= P; ++t) {
+                    if (t <= P - d) {
+                        const double vsh = __shfl_up_sync(0xffffffffu, (k <= P) ? L[t][t + d] : L[t + d][t], t);
+                        if (lane >= t) sum += vsh;
+                    }
+                }
+                if (mu[k] >= 0) obuf[mu[k] - mu_lo] = sum;
+            }
+            __syncwarp();
+            double* dst = prm.out[0] + lo.out + (long long)(mu_lo - prm.mu_base);
+#pragma unroll
+            for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
+                if ((mine >> j) & 1u) dst[lane + 32 * j] = obuf[lane + 32 * j];
+        }
+        st = (st + 1) % NST;
+    }
+    (void)nslots;
+}
 #endif

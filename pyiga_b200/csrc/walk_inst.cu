@@ -40,11 +40,27 @@ int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* strea
         pb_emu_for(prm->nthreads, [&](long long line) { pb_lane_span_seq<Plan, PB_P, PB_Q>(*prm, line, b); });
     return 0;
 #else
+    const bool v1 = lines_per_warp < 0;             // negative: the register-prefetch version (v1)
+    if (v1) lines_per_warp = -lines_per_warp;
     const long long warps = (prm->nthreads + lines_per_warp - 1) / lines_per_warp;
     const long long blocks = (warps + 3) / 4;
     if (blocks <= 0) return 0;
     dim3 grid((unsigned)blocks, (unsigned)nb);
-    pb_lane_span_kernel<Plan, PB_P, PB_Q><<<grid, 128, 0, (cudaStream_t)stream>>>(*prm, lines_per_warp);
+    if (v1) {
+        pb_lane_span_kernel<Plan, PB_P, PB_Q><<<grid, 128, 0, (cudaStream_t)stream>>>(*prm, lines_per_warp);
+        return (int)cudaGetLastError();
+    }
+    constexpr int NST = 4;
+    using Cfg = PbLaneCfg<PB_P, PB_Q>;
+    const size_t smem = 4 * (size_t)(NST * Plan::NOPS * Cfg::SEG + Cfg::OUTPAD) * sizeof(double);
+    auto kern = pb_lane_span_kernel_v2<Plan, PB_P, PB_Q, NST>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    kern<<<grid, 128, smem, (cudaStream_t)stream>>>(*prm, lines_per_warp);
     return (int)cudaGetLastError();
 #endif
 }
