@@ -187,6 +187,10 @@ def stage_bytes(name, dev, rows_mu, ext_mu):
     G = dev.nnodes
     M = dev.nband
     d = 8.0
+    if name.startswith('s1_one') or name.startswith('s1_copy') and name != 's1_copy':
+        return d * (G[0] * G[1] * G[2] + ext_mu * G[1] * G[2])
+    if name == 's2_pairt':
+        return d * (2 * ext_mu * G[1] * G[2] + ext_mu * M[1] * G[2])
     if name in ('s1a', 's1b'):
         return d * (3 * G[0] * G[1] * G[2] + 3 * ext_mu * G[1] * G[2])
     if name == 's1_copy':

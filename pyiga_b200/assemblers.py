@@ -80,6 +80,11 @@ class DeviceAssembler:
         self._structure = None
         self._dstruct = None
         self._row_start0 = None
+        # tuning switches for experiments, e.g. PB200_OPTS="fused_plans=1,lane_v1=1"
+        import os
+        for item in filter(None, os.environ.get('PB200_OPTS', '').split(',')):
+            k, _, v = item.partition('=')
+            self.set_option(k.strip(), int(v or 1))
 
     def __del__(self):
         try:

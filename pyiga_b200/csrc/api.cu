@@ -365,6 +365,7 @@ struct pb200_assembler {
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
     bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
+    bool fused_plans = false;                           // multi-output stage kernels (S1A/S1B/S2B) instead of one launch per output
     // optional per-kernel timing of the last assemble call (CUDA events on the launch stream)
     bool timing = false;
     std::vector<std::string> stage_names;
@@ -393,6 +394,7 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!a || !name) return fail(PB200_EINVAL, "null argument");
     if (!strcmp(name, "force_walk")) { a->force_walk = value != 0; return 0; }
     if (!strcmp(name, "lane_v1")) { a->lane_v1 = value != 0; return 0; }
+    if (!strcmp(name, "fused_plans")) { a->fused_plans = value != 0; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
 }
 
@@ -453,7 +455,8 @@ static int detect_fast_path(const pb200_assembler* a) {
         if (a->dim == 2)
             return have_plan(PB_PLAN_S1_2D, P(0), Q) && have_plan(PB_PLAN_FINAL4, P(1), Q);
         return have_plan(PB_PLAN_S1A, P(0), Q) && have_plan(PB_PLAN_S1B, P(0), Q) && have_plan(PB_PLAN_FINAL4, P(1), Q)
-               && have_plan(PB_PLAN_S2B, P(1), Q) && have_plan(PB_PLAN_FINAL4, P(2), Q);
+               && have_plan(PB_PLAN_S2B, P(1), Q) && have_plan(PB_PLAN_FINAL4, P(2), Q) && have_plan(PB_PLAN_ONE11, P(0), Q)
+               && have_plan(PB_PLAN_PAIRT, P(1), Q);
     }
     return 0;
 }
@@ -1276,10 +1279,20 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             p.out_sx = 1; p.out_smu = G1; p.mu_base = S.ext_lo;
             p.s_begin = S.sa; p.s_end = S.sb;
             p.w_mode = keep_mode; p.w_lo = S.ra; p.w_hi = S.rb;
-            if (stiff) {
+            if (stiff && a->fused_plans) {
                 p.in[0] = F + 2 * npts; p.in[1] = F + 1 * npts; p.in[2] = F;     // B11, B01, B00
                 for (int t = 0; t < 3; ++t) p.out[t] = X1 + t * s1;
                 rc = run_stage(PB_PLAN_S1_2D, a, 0, p, st, "s1_2d");
+            } else if (stiff) {
+                // one launch per output: every field is read by exactly one of them
+                const int plan[3] = {PB_PLAN_ONE11, PB_PLAN_ONE10, PB_PLAN_COPY};
+                const int field[3] = {2, 1, 0};                                 // B11, B01, B00
+                const char* nm[3] = {"s1_one11", "s1_one10", "s1_copy"};
+                for (int t = 0; t < 3 && !rc; ++t) {
+                    PbWalkParams q = p;
+                    q.in[0] = F + field[t] * npts; q.out[0] = X1 + t * s1;
+                    rc = run_stage(plan[t], a, 0, q, st, nm[t]);
+                }
             } else {
                 p.in[0] = F; p.out[0] = X1;
                 rc = run_stage(PB_PLAN_COPY, a, 0, p, st, "s1_copy");
@@ -1320,7 +1333,16 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.out_sx = 1; p.out_smu = G1 * G2; p.mu_base = S.ext_lo;
         p.s_begin = S.sa; p.s_end = S.sb;
         p.w_mode = keep_mode; p.w_lo = S.ra; p.w_hi = S.rb;
-        if (stiff) {
+        if (stiff && !a->fused_plans) {
+            const int plan[6] = {PB_PLAN_ONE11, PB_PLAN_ONE10, PB_PLAN_ONE10, PB_PLAN_COPY, PB_PLAN_COPY, PB_PLAN_COPY};
+            const int field[6] = {5, 4, 2, 3, 1, 0};                            // B22, B12, B02, B11, B01, B00
+            const char* nm[6] = {"s1_one11", "s1_one10a", "s1_one10b", "s1_copya", "s1_copyb", "s1_copyc"};
+            for (int t = 0; t < 6 && !rc; ++t) {
+                PbWalkParams q = p;
+                q.in[0] = F + field[t] * npts; q.out[0] = X1 + t * s1;
+                rc = run_stage(plan[t], a, 0, q, st, nm[t]);
+            }
+        } else if (stiff) {
             PbWalkParams pa = p, pb = p;
             pa.in[0] = F + 5 * npts; pa.in[1] = F + 4 * npts; pa.in[2] = F + 2 * npts;   // B22, B12, B02
             for (int t = 0; t < 3; ++t) pa.out[t] = X1 + t * s1;
@@ -1354,7 +1376,16 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             pb.out[0] = X2 + s2; pb.out[1] = X2 + 2 * s2;
             rc = run_stage(PB_PLAN_FINAL4, a, 1, pa, st, "s2a_final4");
             if (rc) return rc;
-            rc = run_stage(PB_PLAN_S2B, a, 1, pb, st, "s2b");
+            if (a->fused_plans) {
+                rc = run_stage(PB_PLAN_S2B, a, 1, pb, st, "s2b");
+            } else {
+                PbWalkParams pc = p, pd = p;
+                pc.in[0] = X1 + 2 * s1; pc.in[1] = X1 + 4 * s1; pc.out[0] = X2 + s2;    // (v,d2)[0,0] + (d1,d2)[1,0]
+                pd.in[0] = X1 + 5 * s1; pd.out[0] = X2 + 2 * s2;                          // (d2,d2)[0,0]
+                rc = run_stage(PB_PLAN_PAIRT, a, 1, pc, st, "s2_pairt");
+                if (rc) return rc;
+                rc = run_stage(PB_PLAN_COPY, a, 1, pd, st, "s2_copy");
+            }
         } else {
             p.in[0] = X1; p.out[0] = X2;
             rc = run_stage(PB_PLAN_COPY, a, 1, p, st, "s2_copy");

@@ -31,17 +31,38 @@ enum PbPlanId {
     PB_PLAN_S2B = 4,
     PB_PLAN_S1_2D = 5,  // 2D stiffness stage 1:  B11 [1,1]->(v,v)  B01 [1,0]->(v,d1)  B00 [0,0]->(d1,d1)
     PB_PLAN_GEN4 = 6,   // generic forms: [0,0] + [0,1] + [1,0] + [1,1] -> one output, no transposes, null = absent
-    PB_PLAN_COUNT = 7,
+    PB_PLAN_ONE11 = 7,  // one term, test and trial derivative on this axis
+    PB_PLAN_ONE10 = 8,  // one term, test derivative on this axis
+    PB_PLAN_PAIRT = 9,  // [0,0] + [1,0] -> one output
+    PB_PLAN_COUNT = 10,
     PB_PLAN_LANE_BASE = 1000    // + plan id: the lane-per-span variant (second argument = lines per warp)
 };
 
 struct PbPlanCopy {
-    static constexpr int NOPS = 1, NOUT = 1, MINB = 4;
+    static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int) { return PbOp{0, 0, 0, 0, 0}; }
 };
+struct PbPlanOne11 {
+    static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
+    static constexpr bool HAS_TR = false;
+    static constexpr PbOp op(int) { return PbOp{0, 0, 1, 1, 0}; }
+};
+struct PbPlanOne10 {
+    static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
+    static constexpr bool HAS_TR = false;
+    static constexpr PbOp op(int) { return PbOp{0, 0, 1, 0, 0}; }
+};
+struct PbPlanPairT {
+    static constexpr int NOPS = 2, NOUT = 1, MINB = 4, NPF = 3;
+    static constexpr bool HAS_TR = false;
+    static constexpr PbOp op(int i) {
+        constexpr PbOp t[2] = {{0, 0, 0, 0, 0}, {1, 0, 1, 0, 0}};
+        return t[i];
+    }
+};
 struct PbPlanFinal4 {
-    static constexpr int NOPS = 4, NOUT = 1, MINB = 3;
+    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 1;
     static constexpr bool HAS_TR = true;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {1, 1, 1, 0, 0}, {2, 0, 1, 1, 0}};
@@ -49,7 +70,7 @@ struct PbPlanFinal4 {
     }
 };
 struct PbPlanGen4 {
-    static constexpr int NOPS = 4, NOUT = 1, MINB = 3;
+    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 1;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {2, 0, 1, 0, 0}, {3, 0, 1, 1, 0}};
@@ -57,7 +78,7 @@ struct PbPlanGen4 {
     }
 };
 struct PbPlanS1A {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 1;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 1, 0, 2}};
@@ -65,7 +86,7 @@ struct PbPlanS1A {
     }
 };
 struct PbPlanS1B {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 1;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 0, 0, 1}, {2, 0, 0, 0, 2}};
@@ -73,7 +94,7 @@ struct PbPlanS1B {
     }
 };
 struct PbPlanS2B {
-    static constexpr int NOPS = 3, NOUT = 2, MINB = 2;
+    static constexpr int NOPS = 3, NOUT = 2, MINB = 2, NPF = 1;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 1, 0, 0}, {2, 0, 0, 0, 1}};
@@ -81,7 +102,7 @@ struct PbPlanS2B {
     }
 };
 struct PbPlanS1_2D {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 1;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 0, 0, 2}};

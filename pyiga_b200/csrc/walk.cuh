@@ -95,7 +95,8 @@ template <class Plan> constexpr bool pb_group_by_fu(int out) {
 }
 
 // The body executed by one thread.  `Vt` points at the [G][2][P+1] table (shared or global).
-template <class Plan, int P, int Q>
+// NPF = number of spans whose inputs are in flight (in registers) ahead of the span being contracted.
+template <class Plan, int P, int Q, int NPF = 1>
 PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt) {
     constexpr int P1 = P + 1;
     constexpr int NOPS = Plan::NOPS, NOUT = Plan::NOUT;
@@ -180,13 +181,17 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
     };
 
     int f = prm.first[prm.s_begin];
-    double xq[Q][NOPS];         // inputs of the current span (loaded one span ahead of use)
+    double xq[NPF][Q][NOPS];    // inputs of the next NPF spans (loaded ahead of use)
 #pragma unroll
-    for (int gq = 0; gq < Q; ++gq)
-        pb_static_for<0, NOPS>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            xq[gq][i] = has[i] ? src[i][(long long)(prm.s_begin * Q + gq) * prm.in_sc] : 0.0;
-        });
+    for (int k = 0; k < NPF; ++k) {
+        const bool ok = prm.s_begin + k < prm.s_end;
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+            pb_static_for<0, NOPS>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                xq[k][gq][i] = (ok && has[i]) ? src[i][(long long)((prm.s_begin + k) * Q + gq) * prm.in_sc] : 0.0;
+            });
+    }
 
     for (int s = prm.s_begin; s < prm.s_end; ++s) {
         const int fs = prm.first[s];
@@ -195,13 +200,18 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
         double xc[Q][NOPS];
 #pragma unroll
         for (int gq = 0; gq < Q; ++gq)
-            pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; xc[gq][i] = xq[gq][i]; });
-        if (s + 1 < prm.s_end) {
+            pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; xc[gq][i] = xq[0][gq][i]; });
+#pragma unroll
+        for (int k = 0; k + 1 < NPF; ++k)
+#pragma unroll
+            for (int gq = 0; gq < Q; ++gq)
+                pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; xq[k][gq][i] = xq[k + 1][gq][i]; });
+        if (s + NPF < prm.s_end) {
 #pragma unroll
             for (int gq = 0; gq < Q; ++gq)
                 pb_static_for<0, NOPS>([&](auto I) {
                     constexpr int i = decltype(I)::value;
-                    xq[gq][i] = has[i] ? src[i][(long long)((s + 1) * Q + gq) * prm.in_sc] : 0.0;
+                    xq[NPF - 1][gq][i] = has[i] ? src[i][(long long)((s + NPF) * Q + gq) * prm.in_sc] : 0.0;
                 });
         }
 
@@ -294,7 +304,7 @@ PB_D void pb_mbar_wait(uint64_t* bar, uint32_t phase) {
 // Generic stage kernel.  Dynamic shared memory holds the walk-axis table slice
 // [s_begin*Q, s_end*Q) x 2 x (P+1) doubles when `use_smem` is set; otherwise the table is read
 // through the read-only path from global memory (axes too long for 227 KB).
-template <class Plan, int P, int Q, int MINB>
+template <class Plan, int P, int Q, int MINB, int NPF>
 __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constant__ PbWalkParams prm, int use_smem) {
     extern __shared__ __align__(128) unsigned char pb_smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
         Vt = sV - first_node * 2 * (P + 1);     // so that Vt[(s*Q+gq)*2*(P+1)] addresses the slice
     }
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid < prm.nthreads) pb_walk_line<Plan, P, Q>(prm, tid, Vt);
+    if (tid < prm.nthreads) pb_walk_line<Plan, P, Q, NPF>(prm, tid, Vt);
 }
 #endif
 
@@ -567,7 +577,7 @@ template <int P, int Q> struct PbLaneCfg {
 };
 
 template <class Plan, int P, int Q, int NST>
-__global__ void __launch_bounds__(128, 3) pb_lane_span_kernel_v2(const __grid_constant__ PbWalkParams prm, int lines_per_warp) {
+__global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(const __grid_constant__ PbWalkParams prm, int lines_per_warp) {
     constexpr int P1 = P + 1, NOPS = Plan::NOPS;
     using Cfg = PbLaneCfg<P, Q>;
     constexpr int SEG = Cfg::SEG;

@@ -14,10 +14,10 @@ template <class Plan>
 int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* stream) {
 #ifdef PB_EMULATE
     (void)use_smem; (void)smem_bytes; (void)stream;
-    pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q>(*prm, tid, prm->V2); });
+    pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q, Plan::NPF>(*prm, tid, prm->V2); });
     return 0;
 #else
-    auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, Plan::MINB>;
+    auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, Plan::MINB, Plan::NPF>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -85,6 +85,9 @@ struct Registrar {
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_FINAL4, PB_P, PB_Q, &launch_lane<PbPlanFinal4>);
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_GEN4, PB_P, PB_Q, &launch_lane<PbPlanGen4>);
         pb200_register_walk(PB_PLAN_GEN4, PB_P, PB_Q, &launch<PbPlanGen4>);
+        pb200_register_walk(PB_PLAN_ONE11, PB_P, PB_Q, &launch<PbPlanOne11>);
+        pb200_register_walk(PB_PLAN_ONE10, PB_P, PB_Q, &launch<PbPlanOne10>);
+        pb200_register_walk(PB_PLAN_PAIRT, PB_P, PB_Q, &launch<PbPlanPairT>);
         pb200_register_walk(PB_PLAN_COPY, PB_P, PB_Q, &launch<PbPlanCopy>);
         pb200_register_walk(PB_PLAN_FINAL4, PB_P, PB_Q, &launch<PbPlanFinal4>);
         pb200_register_walk(PB_PLAN_S1A, PB_P, PB_Q, &launch<PbPlanS1A>);
