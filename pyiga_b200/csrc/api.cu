@@ -1081,7 +1081,7 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
         }
     }
     const size_t smem = (size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double);
-    const int use_smem = smem <= 160 * 1024;
+    const int use_smem = smem <= 64 * 1024;     // longer axes read the table through L1 (keeps occupancy)
     int e = fn(&prm, use_smem, use_smem ? smem : 0, st);
     if (e) return fail(PB200_ECUDA, "walk kernel launch failed (plan %d, p=%d, q=%d): %s", plan, P, Q, pbErrorString((pbError)e));
     return 0;

@@ -62,7 +62,7 @@ struct PbPlanPairT {
     }
 };
 struct PbPlanFinal4 {
-    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 1;
+    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 3;
     static constexpr bool HAS_TR = true;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {1, 1, 1, 0, 0}, {2, 0, 1, 1, 0}};
@@ -70,7 +70,7 @@ struct PbPlanFinal4 {
     }
 };
 struct PbPlanGen4 {
-    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 1;
+    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 3;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {2, 0, 1, 0, 0}, {3, 0, 1, 1, 0}};
@@ -78,7 +78,7 @@ struct PbPlanGen4 {
     }
 };
 struct PbPlanS1A {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 1;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 1, 0, 2}};
@@ -86,7 +86,7 @@ struct PbPlanS1A {
     }
 };
 struct PbPlanS1B {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 1;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 0, 0, 1}, {2, 0, 0, 0, 2}};
@@ -94,7 +94,7 @@ struct PbPlanS1B {
     }
 };
 struct PbPlanS2B {
-    static constexpr int NOPS = 3, NOUT = 2, MINB = 2, NPF = 1;
+    static constexpr int NOPS = 3, NOUT = 2, MINB = 2, NPF = 3;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 1, 0, 0}, {2, 0, 0, 0, 1}};
@@ -102,7 +102,7 @@ struct PbPlanS2B {
     }
 };
 struct PbPlanS1_2D {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 1;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 0, 0, 2}};

@@ -95,9 +95,47 @@ template <class Plan> constexpr bool pb_group_by_fu(int out) {
 }
 
 // The body executed by one thread.  `Vt` points at the [G][2][P+1] table (shared or global).
-// NPF = number of spans whose inputs are in flight (in registers) ahead of the span being contracted.
+// Input staging policies of the walk: how the Q*NOPS inputs of a span reach the registers.
+//  * PbRegLoader: plain loads one span ahead into registers (host emulation, fall-back).
+//  * PbAsyncLoader (device): cp.async into a per-thread ring in shared memory, NST-1 spans ahead;
+//    data in flight holds no registers and needs no register moves, so the lead is really NST-1.
+template <class Plan, int Q>
+struct PbRegLoader {
+    static constexpr int NOPS = Plan::NOPS;
+    const double* src[NOPS];
+    bool has[NOPS];
+    long long sc;
+    int s_end;
+    double xq[Q][NOPS];
+    PB_HD void load(int s) {
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+            pb_static_for<0, NOPS>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                xq[gq][i] = has[i] ? src[i][(long long)(s * Q + gq) * sc] : 0.0;
+            });
+    }
+    PB_HD void prime(int s_begin) { load(s_begin); }
+    // hand out the inputs of span s and start fetching a later span
+    PB_HD void next(int s, double (&xc)[Q][NOPS]) {
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+            pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; xc[gq][i] = xq[gq][i]; });
+        if (s + 1 < s_end) load(s + 1);
+    }
+};
+
+template <class Plan, int P, int Q, class Loader>
+PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt, Loader& ld);
+
 template <class Plan, int P, int Q, int NPF = 1>
 PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt) {
+    PbRegLoader<Plan, Q> ld;
+    pb_walk_line_impl<Plan, P, Q>(prm, tid, Vt, ld);
+}
+
+template <class Plan, int P, int Q, class Loader>
+PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt, Loader& ld) {
     constexpr int P1 = P + 1;
     constexpr int NOPS = Plan::NOPS, NOUT = Plan::NOUT;
 
@@ -125,13 +163,13 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
                               + (long long)x * prm.out_sx;
 
     // a null input pointer means "term absent" (generic forms): it reads as zero
-    const double* src[NOPS];
-    bool has[NOPS];
     pb_static_for<0, NOPS>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        has[i] = prm.in[i] != nullptr;
-        src[i] = prm.in[i] + (Plan::op(i).tr ? off_in_tr : off_in);
+        ld.has[i] = prm.in[i] != nullptr;
+        ld.src[i] = prm.in[i] + (Plan::op(i).tr ? off_in_tr : off_in);
     });
+    ld.sc = prm.in_sc;
+    ld.s_end = prm.s_end;
 
     double acc[NOUT][P1][P1];
     pb_static_for<0, NOUT>([&](auto O) {
@@ -181,39 +219,14 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
     };
 
     int f = prm.first[prm.s_begin];
-    double xq[NPF][Q][NOPS];    // inputs of the next NPF spans (loaded ahead of use)
-#pragma unroll
-    for (int k = 0; k < NPF; ++k) {
-        const bool ok = prm.s_begin + k < prm.s_end;
-#pragma unroll
-        for (int gq = 0; gq < Q; ++gq)
-            pb_static_for<0, NOPS>([&](auto I) {
-                constexpr int i = decltype(I)::value;
-                xq[k][gq][i] = (ok && has[i]) ? src[i][(long long)((prm.s_begin + k) * Q + gq) * prm.in_sc] : 0.0;
-            });
-    }
+    ld.prime(prm.s_begin);
 
     for (int s = prm.s_begin; s < prm.s_end; ++s) {
         const int fs = prm.first[s];
         while (f < fs) { retire_shift(f); ++f; }
 
         double xc[Q][NOPS];
-#pragma unroll
-        for (int gq = 0; gq < Q; ++gq)
-            pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; xc[gq][i] = xq[0][gq][i]; });
-#pragma unroll
-        for (int k = 0; k + 1 < NPF; ++k)
-#pragma unroll
-            for (int gq = 0; gq < Q; ++gq)
-                pb_static_for<0, NOPS>([&](auto I) { constexpr int i = decltype(I)::value; xq[k][gq][i] = xq[k + 1][gq][i]; });
-        if (s + NPF < prm.s_end) {
-#pragma unroll
-            for (int gq = 0; gq < Q; ++gq)
-                pb_static_for<0, NOPS>([&](auto I) {
-                    constexpr int i = decltype(I)::value;
-                    xq[NPF - 1][gq][i] = has[i] ? src[i][(long long)((s + NPF) * Q + gq) * prm.in_sc] : 0.0;
-                });
-        }
+        ld.next(s, xc);
 
 #pragma unroll
         for (int gq = 0; gq < Q; ++gq) {
@@ -284,6 +297,14 @@ PB_D void pb_tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint6
         "l"(gsrc), "r"(bytes), "r"(b)
         : "memory");
 }
+PB_D void pb_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pb_smem_u32(smem)), "l"(gmem) : "memory");
+}
+PB_D void pb_cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pb_smem_u32(smem)), "l"(gmem) : "memory");
+}
+PB_D void pb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PB_D void pb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 PB_D void pb_mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pb_smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -300,6 +321,44 @@ PB_D void pb_mbar_wait(uint64_t* bar, uint32_t phase) {
         "r"(phase)
         : "memory");
 }
+
+template <class Plan, int Q, int NST>
+struct PbAsyncLoader {
+    static constexpr int NOPS = Plan::NOPS;
+    const double* src[NOPS];
+    bool has[NOPS];
+    long long sc;
+    int s_end;
+    double* ring;       // this thread's column of the block ring: [NST][Q][NOPS][blockDim.x]
+    int nthr, st;
+    PB_D void issue(int s, int stage) {
+        if (s < s_end) {
+#pragma unroll
+            for (int gq = 0; gq < Q; ++gq)
+                pb_static_for<0, NOPS>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    if (has[i]) pb_cp_async8(ring + ((stage * Q + gq) * NOPS + i) * nthr, src[i] + (long long)(s * Q + gq) * sc);
+                });
+        }
+        pb_cp_async_commit();
+    }
+    PB_D void prime(int s_begin) {
+        st = 0;
+#pragma unroll
+        for (int k = 0; k < NST - 1; ++k) issue(s_begin + k, k);
+    }
+    PB_D void next(int s, double (&xc)[Q][NOPS]) {
+        issue(s + NST - 1, (st + NST - 1) % NST);
+        pb_cp_async_wait<NST - 1>();
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+            pb_static_for<0, NOPS>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                xc[gq][i] = has[i] ? ring[((st * Q + gq) * NOPS + i) * nthr] : 0.0;
+            });
+        st = (st + 1) % NST;
+    }
+};
 
 // Generic stage kernel.  Dynamic shared memory holds the walk-axis table slice
 // [s_begin*Q, s_end*Q) x 2 x (P+1) doubles when `use_smem` is set; otherwise the table is read
@@ -338,7 +397,18 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
         Vt = sV - first_node * 2 * (P + 1);     // so that Vt[(s*Q+gq)*2*(P+1)] addresses the slice
     }
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid < prm.nthreads) pb_walk_line<Plan, P, Q, NPF>(prm, tid, Vt);
+    if (tid < prm.nthreads) {
+        if constexpr (NPF >= 2) {
+            // NPF doubles as the ring depth of the asynchronous loader
+            const size_t vbytes = use_smem ? ((size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double) + 127) & ~size_t(127) : 0;
+            PbAsyncLoader<Plan, Q, NPF> ld;
+            ld.ring = reinterpret_cast<double*>(pb_smem_raw + vbytes) + threadIdx.x;
+            ld.nthr = blockDim.x;
+            pb_walk_line_impl<Plan, P, Q>(prm, tid, Vt, ld);
+        } else {
+            pb_walk_line<Plan, P, Q>(prm, tid, Vt);
+        }
+    }
 }
 #endif
 
@@ -561,14 +631,6 @@ __global__ void __launch_bounds__(128) pb_lane_span_kernel(const __grid_constant
 //   * stores: the 2P+1 finished entries of every lane are first placed at their band offset in a
 //     per-warp shared buffer and then written by consecutive lanes, i.e. as full 32-byte sectors.
 // -------------------------------------------------------------------------------------------------
-PB_D void pb_cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pb_smem_u32(smem)), "l"(gmem) : "memory");
-}
-PB_D void pb_cp_async8(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pb_smem_u32(smem)), "l"(gmem) : "memory");
-}
-PB_D void pb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> PB_D void pb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int P, int Q> struct PbLaneCfg {
     static constexpr int SEG = 32 * Q;                      // doubles per term and line segment

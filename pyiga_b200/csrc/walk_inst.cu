@@ -14,7 +14,7 @@ template <class Plan>
 int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* stream) {
 #ifdef PB_EMULATE
     (void)use_smem; (void)smem_bytes; (void)stream;
-    pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q, Plan::NPF>(*prm, tid, prm->V2); });
+    pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q>(*prm, tid, prm->V2); });
     return 0;
 #else
     auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, Plan::MINB, Plan::NPF>;
@@ -26,7 +26,10 @@ int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* strea
     }
     const long long blocks = (prm->nthreads + 127) / 128;
     if (blocks <= 0) return 0;
-    kern<<<(unsigned)blocks, 128, smem_bytes, (cudaStream_t)stream>>>(*prm, use_smem);
+    // the asynchronous loader's ring (plans with NPF >= 2) sits behind the table slice
+    const size_t ring = Plan::NPF >= 2 ? (size_t)Plan::NPF * PB_Q * Plan::NOPS * 128 * sizeof(double) : 0;
+    const size_t vpad = use_smem ? (smem_bytes + 127) & ~size_t(127) : 0;
+    kern<<<(unsigned)blocks, 128, vpad + ring, (cudaStream_t)stream>>>(*prm, use_smem);
     return (int)cudaGetLastError();
 #endif
 }
