@@ -1068,6 +1068,8 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     PbWalkLaunch fn = pb_find_walk(plan, P, Q);
     if (!fn) return fail(PB200_EUNSUPPORTED, "no walk kernel for plan %d, p=%d, q=%d", plan, P, Q);
     prm.N = H.V.N();
+    prm.f_lo = H.U.first[prm.s_begin];
+    prm.f_hi = std::min(H.V.N(), H.U.first[prm.s_end - 1] + P + 1);
     prm.first = D.first_u;
     prm.V2 = D.Vu;
     prm.ret_mu = D.ret_mu;
@@ -1081,7 +1083,8 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
         }
     }
     const size_t smem = (size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double);
-    const int use_smem = smem <= 64 * 1024;     // longer axes read the table through L1 (keeps occupancy)
+    const size_t ismem = ((size_t)(prm.s_end - prm.s_begin + 4) + (size_t)(prm.f_hi - prm.f_lo) * (2 * P + 1)) * sizeof(int);
+    const int use_smem = smem + ismem <= 64 * 1024;     // longer axes read the table through L1 (keeps occupancy)
     int e = fn(&prm, use_smem, use_smem ? smem : 0, st);
     if (e) return fail(PB200_ECUDA, "walk kernel launch failed (plan %d, p=%d, q=%d): %s", plan, P, Q, pbErrorString((pbError)e));
     return 0;

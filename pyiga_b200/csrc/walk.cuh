@@ -58,6 +58,7 @@ struct PbWalkParams {
     const double* V2;               // [G][2][P+1]
     const int* ret_mu;              // [N][2P+1]
     int w_mode, w_lo, w_hi;         // retire filter on the walk-axis pair (i,j), as u_mode
+    int f_lo, f_hi;                 // functions retired by this walk: [first[s_begin], min(N, first[s_end-1]+P+1))
 };
 
 template <int I> struct PbIC { static constexpr int value = I; };
@@ -125,17 +126,25 @@ struct PbRegLoader {
     }
 };
 
+struct PbWalkTables {       // where the thread finds the walk-axis tables (shared or global memory)
+    const double* V;        // indexed by absolute node
+    const int* first;       // indexed by absolute span
+    const int* ret_mu;      // indexed by absolute function * (2P+1)
+};
 template <class Plan, int P, int Q, class Loader>
-PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt, Loader& ld);
+PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWalkTables& tb, Loader& ld);
 
 template <class Plan, int P, int Q, int NPF = 1>
 PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt) {
     PbRegLoader<Plan, Q> ld;
-    pb_walk_line_impl<Plan, P, Q>(prm, tid, Vt, ld);
+    PbWalkTables tb;
+    tb.V = Vt; tb.first = prm.first; tb.ret_mu = prm.ret_mu;
+    pb_walk_line_impl<Plan, P, Q>(prm, tid, tb, ld);
 }
 
 template <class Plan, int P, int Q, class Loader>
-PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt, Loader& ld) {
+PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWalkTables& tb, Loader& ld) {
+    const double* __restrict__ Vt = tb.V;
     constexpr int P1 = P + 1;
     constexpr int NOPS = Plan::NOPS, NOUT = Plan::NOUT;
 
@@ -183,7 +192,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const doubl
     // retire the pairs that involve function f (first row / first column of the window), then
     // slide the window down by one function
     auto retire_shift = [&](int f) {
-        const int* rm = prm.ret_mu + (long long)f * (2 * P + 1);
+        const int* rm = tb.ret_mu + (long long)f * (2 * P + 1);
 #pragma unroll
         for (int k = 0; k <= 2 * P; ++k) {
             const int mu = rm[k];
@@ -218,11 +227,11 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const doubl
         });
     };
 
-    int f = prm.first[prm.s_begin];
+    int f = tb.first[prm.s_begin];
     ld.prime(prm.s_begin);
 
     for (int s = prm.s_begin; s < prm.s_end; ++s) {
-        const int fs = prm.first[s];
+        const int fs = tb.first[s];
         while (f < fs) { retire_shift(f); ++f; }
 
         double xc[Q][NOPS];
@@ -396,17 +405,39 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
         pb_mbar_wait(&bar, 0);
         Vt = sV - first_node * 2 * (P + 1);     // so that Vt[(s*Q+gq)*2*(P+1)] addresses the slice
     }
+    // the small integer tables (first active function per span, retire table) go to shared memory
+    // as well: every span of every thread reads them, and with most of the L1 carved out as shared
+    // memory they would otherwise be re-fetched from L2 inside the dependent chain of the walk
+    const size_t vbytes = use_smem ? ((size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double) + 127) & ~size_t(127) : 0;
+    const int nsp = prm.s_end - prm.s_begin;
+    const int f_lo = prm.f_lo, f_hi = prm.f_hi;                            // functions retired by this walk
+    int* s_first = reinterpret_cast<int*>(pb_smem_raw + vbytes);
+    int* s_ret = s_first + ((nsp + 3) & ~3);
+    const size_t ibytes = (((size_t)((nsp + 3) & ~3) + (size_t)(f_hi - f_lo) * (2 * P + 1)) * sizeof(int) + 127) & ~size_t(127);
+    PbWalkTables tb;
+    tb.V = Vt;
+    if (use_smem) {
+        for (int t = threadIdx.x; t < nsp; t += blockDim.x) s_first[t] = prm.first[prm.s_begin + t];
+        for (int t = threadIdx.x; t < (f_hi - f_lo) * (2 * P + 1); t += blockDim.x)
+            s_ret[t] = prm.ret_mu[(long long)f_lo * (2 * P + 1) + t];
+        __syncthreads();
+        tb.first = s_first - prm.s_begin;
+        tb.ret_mu = s_ret - (long long)f_lo * (2 * P + 1);
+    } else {
+        tb.first = prm.first;
+        tb.ret_mu = prm.ret_mu;
+    }
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < prm.nthreads) {
         if constexpr (NPF >= 2) {
             // NPF doubles as the ring depth of the asynchronous loader
-            const size_t vbytes = use_smem ? ((size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double) + 127) & ~size_t(127) : 0;
             PbAsyncLoader<Plan, Q, NPF> ld;
-            ld.ring = reinterpret_cast<double*>(pb_smem_raw + vbytes) + threadIdx.x;
+            ld.ring = reinterpret_cast<double*>(pb_smem_raw + vbytes + (use_smem ? ibytes : 0)) + threadIdx.x;
             ld.nthr = blockDim.x;
-            pb_walk_line_impl<Plan, P, Q>(prm, tid, Vt, ld);
+            pb_walk_line_impl<Plan, P, Q>(prm, tid, tb, ld);
         } else {
-            pb_walk_line<Plan, P, Q>(prm, tid, Vt);
+            PbRegLoader<Plan, Q> ld;
+            pb_walk_line_impl<Plan, P, Q>(prm, tid, tb, ld);
         }
     }
 }

@@ -29,7 +29,10 @@ int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* strea
     // the asynchronous loader's ring (plans with NPF >= 2) sits behind the table slice
     const size_t ring = Plan::NPF >= 2 ? (size_t)Plan::NPF * PB_Q * Plan::NOPS * 128 * sizeof(double) : 0;
     const size_t vpad = use_smem ? (smem_bytes + 127) & ~size_t(127) : 0;
-    kern<<<(unsigned)blocks, 128, vpad + ring, (cudaStream_t)stream>>>(*prm, use_smem);
+    // integer tables behind the V slice: spans (padded to 4) + at most (spans + P + 1) functions x (2P+1)
+    const int nsp = prm->s_end - prm->s_begin;
+    const size_t ipad = use_smem ? ((((size_t)((nsp + 3) & ~3) + (size_t)(prm->f_hi - prm->f_lo) * (2 * PB_P + 1)) * sizeof(int) + 127) & ~size_t(127)) : 0;
+    kern<<<(unsigned)blocks, 128, vpad + ipad + ring, (cudaStream_t)stream>>>(*prm, use_smem);
     return (int)cudaGetLastError();
 #endif
 }
