@@ -62,7 +62,7 @@ struct PbPlanPairT {
     }
 };
 struct PbPlanFinal4 {
-    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 3;
+    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 2;
     static constexpr bool HAS_TR = true;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {1, 1, 1, 0, 0}, {2, 0, 1, 1, 0}};
@@ -70,7 +70,7 @@ struct PbPlanFinal4 {
     }
 };
 struct PbPlanGen4 {
-    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 3;
+    static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 2;
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {2, 0, 1, 0, 0}, {3, 0, 1, 1, 0}};

@@ -667,6 +667,7 @@ template <int P, int Q> struct PbLaneCfg {
     static constexpr int SEG = 32 * Q;                      // doubles per term and line segment
     static constexpr int OUTSLOTS = (32 + P) * (2 * P + 1); // staging slots for finished entries
     static constexpr int OUTPAD = (OUTSLOTS + 31) / 32 * 32;
+    static constexpr int LOSLOTS = 16;      // per warp: decoded offsets of the lines in flight (<= 4 stages x 4 words)
 };
 
 template <class Plan, int P, int Q, int NST>
@@ -678,8 +679,9 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
     constexpr int STAGE = NOPS * SEG;                       // doubles per pipeline stage
     extern __shared__ __align__(16) double pb_lane_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + Cfg::OUTPAD);
+    double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + Cfg::OUTPAD + Cfg::LOSLOTS);
     double* obuf = ring + NST * STAGE;
+    long long* lo_ring = reinterpret_cast<long long*>(obuf + Cfg::OUTPAD);
 
     const long long warp = (long long)blockIdx.x * 4 + wib;
     const int batch = blockIdx.y;
@@ -733,9 +735,18 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
         if (obuf[lane + 32 * j] != 0.0) mine |= 1u << j;
     __syncwarp();
 
+    // regions of the ring that no copy ever writes (spans past the end of the axis, absent terms)
+    // must read as zero
+    for (int t = lane; t < NST * STAGE; t += 32) ring[t] = 0.0;
+    __syncwarp();
+
     // asynchronous copy of one line segment into ring stage `st`
     auto issue = [&](long long line, int st) {
         const PbLineOffsets lo = pb_decode_line<Plan>(prm, line);
+        if (lane == 0) {
+            lo_ring[4 * st + 0] = lo.out;
+            lo_ring[4 * st + 1] = lo.keep ? 1 : 0;
+        }
         double* dst = ring + (size_t)st * STAGE;
         if (lo.keep) {
             pb_static_for<0, NOPS>([&](auto I) {
@@ -773,7 +784,9 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
         else pb_cp_async_commit();
         pb_cp_async_wait<NST - 1>();
         __syncwarp();
-        const PbLineOffsets lo = pb_decode_line<Plan>(prm, line);
+        PbLineOffsets lo;
+        lo.out = lo_ring[4 * st + 0];
+        lo.keep = lo_ring[4 * st + 1] != 0;
         if (lo.keep) {                                  // warp-uniform
             const double* src = ring + (size_t)st * STAGE;
             double x[Q][NOPS];
@@ -785,13 +798,12 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
                         const int c = lane * (Q / 2) + h;
                         const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
                         const double2 v = *reinterpret_cast<const double2*>(src + i * SEG + 2 * pc);
-                        x[2 * h][i] = (active && prm.in[i]) ? v.x : 0.0;
-                        x[2 * h + 1][i] = (active && prm.in[i]) ? v.y : 0.0;
+                        x[2 * h][i] = v.x;
+                        x[2 * h + 1][i] = v.y;
                     }
                 } else {
 #pragma unroll
-                    for (int gq = 0; gq < Q; ++gq)
-                        x[gq][i] = (active && prm.in[i]) ? src[i * SEG + lane * Q + gq] : 0.0;
+                    for (int gq = 0; gq < Q; ++gq) x[gq][i] = src[i * SEG + lane * Q + gq];
                 }
             });
             double L[P1][P1];
