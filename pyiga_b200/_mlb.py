@@ -60,16 +60,21 @@ class DeviceStructure:
         count = int(rs0[1] - rs0[0]) * int(np.prod([len(b) for b in S.bidx[1:]], dtype=np.int64))
         return ra, rb, nrows, count
 
-    def csr_arrays(self, d_data, row0=None):
-        """Device CSR arrays (indptr, indices, values) of the slab; int32 unless nnz >= 2^31."""
+    def csr_arrays(self, d_data, row0=None, out=None, idt=None):
+        """Device CSR arrays (indptr, indices, values) of the slab; int32 unless nnz >= 2^31.
+        `out` may hold preallocated (indptr, indices, values) buffers at least as large."""
         be = self.be
         ra, rb, nrows, count = self._sizes(row0)
-        idt = np.int32 if count < 2 ** 31 else np.int64
-        indptr = be.empty(nrows + 1, idt)
-        indices = be.empty(count, idt)
-        values = be.empty(count, np.float64)
-        _device.check(be.lib.pb200_mlb_to_csr(self.handle, ra, rb, be.ptr(d_data), be.ptr(indptr), be.ptr(indices),
-                                               be.ptr(values), np.dtype(idt).itemsize, be.stream()))
+        if idt is None:
+            idt = np.int32 if count < 2 ** 31 else np.int64
+        if out is not None:
+            indptr, indices, values = (o[:n] for o, n in zip(out, (nrows + 1, count, count)))
+        else:
+            indptr = be.empty(nrows + 1, idt)
+            indices = be.empty(count, idt)
+            values = be.empty(count, np.float64)
+        _device.check(be.lib.pb200_mlb_to_csr(self.handle, ra, rb, _ptr(be, d_data), _ptr(be, indptr), _ptr(be, indices),
+                                               _ptr(be, values), np.dtype(idt).itemsize, be.stream()))
         return indptr, indices, values
 
     def to_csr(self, d_data, row0=None):

@@ -365,7 +365,7 @@ struct pb200_assembler {
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
     bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
-    bool fused_plans = false;                           // multi-output stage kernels (S1A/S1B/S2B) instead of one launch per output
+    bool fused_plans = true;                            // multi-output stage kernels (S1A/S1B/S2B); false: one launch per output
     // optional per-kernel timing of the last assemble call (CUDA events on the launch stream)
     bool timing = false;
     std::vector<std::string> stage_names;

@@ -70,6 +70,67 @@ class SlabAssembly:
             return None
         return self.dev.device_structure.to_csr(self.assemble_mlb(), row0=self.rows)
 
+    def csr_sizes(self):
+        """(local rows, local nnz, index dtype) of the CSR arrays of this slab"""
+        ra, rb = self.rows
+        nrows = (rb - ra) * int(np.prod(self.dev.ndofs_test[1:], dtype=np.int64))
+        nnz = self.local_nnz
+        return nrows, nnz, (np.int32 if nnz < 2 ** 31 else np.int64)
+
+    def assemble_csr_host(self, host=None, nchunks=8, workspace=None):
+        """Assemble the local rows and deliver the CSR arrays (indptr, indices, data) in host memory,
+        overlapping the device->host copy of one row chunk with the assembly of the next (CUDA
+        backend only).  `host` may hold three preallocated pinned torch tensors; returns them."""
+        be, dev = self.dev.be, self.dev
+        torch = be.torch
+        nrows, nnz, idt = self.csr_sizes()
+        tdt = torch.int32 if idt == np.int32 else torch.int64
+        if host is None:
+            host = [torch.empty(nrows + 1, dtype=tdt, pin_memory=True), torch.empty(nnz, dtype=tdt, pin_memory=True),
+                    torch.empty(nnz, dtype=torch.float64, pin_memory=True)]
+        dev.compute_fields(self.geo, rows=self.rows)
+        ra, rb = self.rows
+        rs = dev.row_start0()
+        inner_b = int(np.prod(dev.nband[1:], dtype=np.int64))
+        inner_r = int(np.prod(dev.ndofs_test[1:], dtype=np.int64))
+        # chunks of rows balanced by band count
+        targets = np.linspace(rs[ra], rs[rb], max(1, min(nchunks, rb - ra)) + 1)
+        cuts = sorted(set(int(np.clip(np.searchsorted(rs, t), ra, rb)) for t in targets) | {ra, rb})
+        chunks = [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
+        cmax_nnz = max(int(rs[b] - rs[a]) * inner_b for a, b in chunks)
+        cmax_rows = max((b - a) * inner_r for a, b in chunks)
+        if workspace is None:
+            workspace = be.empty(max(dev.workspace_bytes(c) for c in chunks), np.uint8)
+        mlb = be.empty(cmax_nnz)
+        stage = [(be.empty(cmax_rows + 1, idt), be.empty(cmax_nnz, idt), be.empty(cmax_nnz)) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=be.device)
+        main = torch.cuda.current_stream(be.device)
+        freed = [None, None]
+        row_off, nnz_off = 0, 0
+        for k, (a, b) in enumerate(chunks):
+            cn = int(rs[b] - rs[a]) * inner_b
+            cr = (b - a) * inner_r
+            if freed[k % 2] is not None:
+                main.wait_event(freed[k % 2])           # the staging buffers are free again
+            dev.assemble_mlb(rows=(a, b), out=mlb, workspace=workspace)
+            ip, ix, vv = dev.device_structure.csr_arrays(mlb, row0=(a, b), out=stage[k % 2], idt=idt)
+            if nnz_off:
+                ip += nnz_off
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                host[0][row_off:row_off + cr + 1].copy_(ip, non_blocking=True)
+                host[1][nnz_off:nnz_off + cn].copy_(ix, non_blocking=True)
+                host[2][nnz_off:nnz_off + cn].copy_(vv, non_blocking=True)
+                freed[k % 2] = torch.cuda.Event()
+                freed[k % 2].record(copy_stream)
+            row_off += cr
+            nnz_off += cn
+        copy_stream.synchronize()
+        main.synchronize()
+        return host
+
 
 # ---------------------------------------------------------------------------------------------
 # slab-distributed operator: y_r = A_r x with a halo exchange, and CG on top of it

@@ -135,3 +135,17 @@ def test_properties_large(cuda):
     tr = [np.lexsort((b[:, 0], b[:, 1])) for b in Kd.structure.bidx]
     T = Kd.data[np.ix_(*tr)]
     assert np.abs(T - Kd.data).max() <= 1e-12 * scale
+
+
+def test_pipelined_csr_host(cuda):
+    """chunked assembly with overlapped device->host copies gives the same CSR arrays"""
+    from pyiga_b200 import bspline, geometry
+    from pyiga_b200.dist import SlabAssembly
+    kvs = 3 * (bspline.make_knots(3, 0.0, 1.0, 14),)
+    geo = geometry.twisted_nurbs_box()
+    for world, rank in ((1, 0), (3, 1)):
+        sa = SlabAssembly(kvs, geo, 'stiffness', rank=rank, world=world)
+        A = sa.assemble_csr()
+        ip, ix, vv = sa.assemble_csr_host(nchunks=4)
+        assert np.array_equal(ip.numpy(), A.indptr) and np.array_equal(ix.numpy(), A.indices)
+        assert np.array_equal(vv.numpy(), A.data)
