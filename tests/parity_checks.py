@@ -314,3 +314,51 @@ def check_linear_forms(ref):
     assert asm.arity == 1 and asm.entry(0, 0) == 0.0
     vec = asm.assemble_vector()
     assert np.array_equal(asm.multi_entries([0, 5, 7]), vec.ravel()[[0, 5, 7]])
+
+
+def check_edge_cases(ref):
+    """degenerate and unusual inputs the reference accepts"""
+    import pytest
+    from pyiga_b200 import assemble, assemblers, bspline, geometry
+    # one span per axis, degree higher than the number of spans
+    pc_kvs = (bspline.make_knots(3, 0.0, 1.0, 1), bspline.make_knots(2, 0.0, 1.0, 1))
+    check_vs_oracle(2, (3, 2), (1, 1), 'Stiffness')
+    check_vs_oracle(3, (2, 1, 3), (1, 2, 1), 'Mass')
+    # degree without a sum-factorised instantiation: falls back to the per-entry kernel on the device
+    asm = check_vs_oracle(2, (5, 5), (3, 4), 'Stiffness')
+    assert not asm.dev.fast_path
+    # empty request
+    asm = assemblers.MassAssembler2D(pc_kvs, geometry.unit_square())
+    assert asm.multi_entries(np.empty((0, 2), dtype=np.uint64)).shape == (0,)
+    assert asm.multi_entries([]).shape == (0,)
+    # indices far outside the matrix give 0 like the reference's out-of-pattern pairs
+    assert asm.multi_entries(np.array([[0, 10 ** 9]], dtype=np.uint64))[0] == 0.0
+    # argument checks with the reference's messages (pyiga/assemblers.pyx:1174-1185)
+    with pytest.raises(AssertionError, match='Geometry has wrong source dimension'):
+        assemblers.MassAssembler2D(pc_kvs, geometry.twisted_box())
+    with pytest.raises(AssertionError, match='Assembler requires 3 knot vectors'):
+        assemblers.StiffnessAssembler3D(pc_kvs, geometry.twisted_box())
+    with pytest.raises(AssertionError, match='Geometry has wrong dimension'):
+        assemble.mass(pc_kvs, geometry.twisted_box())
+    with pytest.raises(ValueError, match='not open'):
+        from pyiga_b200 import _lib
+        bad = bspline.KnotVector(np.array([0.0, 0.0, 0.5, 1.0, 1.0, 1.0]), 2)
+        assemblers.MassAssembler2D((bad, bad), geometry.unit_square())
+
+    # a geometry that is not a spline object: Jacobian evaluated on the host and uploaded
+    class Shear:
+        sdim = dim = 2
+
+        def grid_jacobian(self, grid):
+            g0, g1 = np.meshgrid(*grid, indexing='ij')
+            J = np.empty(g0.shape + (2, 2))
+            J[..., 0, 0], J[..., 0, 1], J[..., 1, 0], J[..., 1, 1] = 1.0 + g0, 0.5, 0.25 * g1, 2.0
+            return J
+
+    kvs = (bspline.make_knots(2, 0.0, 1.0, 4), bspline.make_knots(3, 0.0, 1.0, 3))
+    asm = assemblers.StiffnessAssembler2D(kvs, Shear())
+    got = asm.dev.be.to_host(asm.dev.assemble_mlb())
+    prob = orc.Problem([kv.kv for kv in kvs], [2, 3], [kv.kv for kv in geometry.unit_square().kvs], [1, 1],
+                       geometry.unit_square().coeffs)
+    prob.jac = Shear().grid_jacobian(prob.grid)
+    assert_close_rel(got, orc.assemble_mlb(prob, 'stiffness').ravel(), what='host-evaluated geometry')

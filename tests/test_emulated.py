@@ -91,3 +91,7 @@ def test_slab_operator_and_cg(emu, ref):
 
 def test_linear_forms(emu, ref):
     pc.check_linear_forms(ref)
+
+
+def test_edge_cases(emu, ref):
+    pc.check_edge_cases(ref)
