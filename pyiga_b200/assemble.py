@@ -64,9 +64,32 @@ def assemble_entries(asm, symmetric=False, format='csr', layout='blocked'):
         return result
     if not hasattr(asm, 'assemble_mlb'):
         raise TypeError('assemble_entries needs a pyiga_b200 device assembler, got %r' % type(asm))
+    if hasattr(asm, 'num_components'):
+        return assemble_entries_vec(asm, symmetric=symmetric, format=format, layout=layout)
     if format == 'mlb':
         return asm.assemble_mlb()
     return asm.assemble_csr().asformat(format)
+
+
+def assemble_entries_vec(asm, symmetric=False, format='csr', layout='blocked'):
+    """Vector-valued forms (``pyiga/assemble.py:761-810``).  `layout='blocked'`: a k_test x k_trial
+    block matrix of scalar matrices; `'packed'`: every scalar entry becomes a small k_test x k_trial
+    block (`format='bsr'` gives the BSR matrix directly).  `format='mlb'` returns the MLMatrix with
+    the dense component level."""
+    assert layout in ('packed', 'blocked')
+    if format == 'mlb':
+        return asm.assemble_mlb(layout=layout)
+    return asm.assemble_csr(layout=layout, format=format)
+
+
+def divdiv(kvs, geo=None, layout='blocked', format='csr'):
+    """``div(u) div(v)`` matrix for vector-valued functions (``pyiga/assemble.py:1051-1061``)."""
+    dim, kvs = _detect_dim(kvs)
+    if geo is None:
+        geo = geometry.unit_cube(dim=dim)
+    cls = {2: assemblers.DivDivAssembler2D, 3: assemblers.DivDivAssembler3D}.get(dim)
+    assert cls is not None, 'dimension %d not implemented' % dim
+    return assemble_entries_vec(cls(kvs, geo), symmetric=True, layout=layout, format=format)
 
 
 def mass(kvs, geo=None, format='csr'):

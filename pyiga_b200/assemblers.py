@@ -312,13 +312,61 @@ class _ScalarAssemblerBase(_AssemblerProtocol):
         self.gaussgrid = self.dev.gaussgrid
 
 
+class _FormBlock:
+    """One scalar form  sum_t c_t d^bt v d^bu u  on the device: tables, coefficient upload, fields."""
+
+    def __init__(self, kvs, nqp, dim, arity, coefs, geo, gaussgrid):
+        self.dim, self.arity, self.kvs = dim, arity, kvs
+        self.gaussgrid = gaussgrid
+        self._grid_shape = tuple(len(g) for g in gaussgrid)
+        self.keys = sorted(coefs)
+        pairs = set()
+        for (bt, bu) in self.keys:
+            for bp in ([0] if bt == 0 else range(1, dim + 1)):
+                for ap in ([-1] if bu < 0 else [0] if bu == 0 else range(1, dim + 1)):
+                    pairs.add((bp, ap))
+        terms = [(f, bp, ap) for f, (bp, ap) in enumerate(sorted(pairs))]
+        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms))
+        self.compute_fields(coefs, geo)
+
+    def compute_fields(self, coefs, geo):
+        dev, be = self.dev, self.dev.be
+        if sorted(coefs) != self.keys:
+            raise RuntimeError('update() changed the structure of the form')
+        arrays, index = [], {}
+        phys = (_lib.PhysTerm * len(coefs))()
+        for t, key in enumerate(self.keys):
+            c = coefs[key]
+            inp = -1
+            if c.arr is not None:
+                if id(c.arr) not in index:
+                    index[id(c.arr)] = len(arrays)
+                    arr = np.ascontiguousarray(np.broadcast_to(c.arr, self._grid_shape), dtype=np.float64)
+                    arrays.append(be.from_host(arr.ravel()))
+                inp = index[id(c.arr)]
+            phys[t] = _lib.PhysTerm(key[0], key[1], inp, c.scale)
+        ptrs = (C.c_void_p * max(len(arrays), 1))(*[be.ptr(a) for a in arrays])
+        if _is_spline_geo(geo):
+            desc, keep = _lib.make_geo_desc(geo)
+            _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, C.byref(desc), None, len(coefs), phys,
+                                                                   len(arrays), ptrs, -1, -1, be.stream()))
+        else:
+            jac = np.ascontiguousarray(geo.grid_jacobian(self.gaussgrid), dtype=np.float64)
+            d_jac = be.from_host(jac.ravel())
+            _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, None, be.ptr(d_jac), len(coefs), phys,
+                                                                   len(arrays), ptrs, -1, -1, be.stream()))
+        be.synchronize()        # the uploaded coefficient arrays may be released now
+
+
 class GenericFormAssembler(_AssemblerProtocol):
-    """Assembler of a scalar bilinear form described by a :class:`~pyiga_b200.vform.VForm`
+    """Assembler of a bilinear or linear form described by a :class:`~pyiga_b200.vform.VForm`
     (base of the classes returned by :func:`~pyiga_b200.vform.compile_vform`).
 
     Mirrors the generated assembler classes of the reference (``pyiga/codegen/cython.py:509-744``):
     construction evaluates the input functions on the Gauss grid (physical callables at the mapped
     points, spline functions on the parameter grid), ``update(name=func)`` re-evaluates one input.
+    Vector-valued forms (``pyiga/genericasm.pxi:790-958``) are assembled block by block: the pair
+    (test component, trial component) is one scalar form.
     """
     _vf = None
 
@@ -346,17 +394,16 @@ class GenericFormAssembler(_AssemblerProtocol):
         if any(_mentions_x(e) for e in vf.exprs):
             X = self._physical_points()
             self._env['@x'] = np.stack([X[..., i] for i in range(d)])
-        coefs = self._analyse()
-        self._keys = sorted(coefs)
-        pairs = set()
-        for (bt, bu) in self._keys:
-            for bp in ([0] if bt == 0 else range(1, d + 1)):
-                for ap in ([-1] if bu < 0 else [0] if bu == 0 else range(1, d + 1)):
-                    pairs.add((bp, ap))
-        self._pairs = sorted(pairs)
-        terms = [(f, bp, ap) for f, (bp, ap) in enumerate(self._pairs)]
-        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=self.nqp, terms=terms, nfields=len(terms))
-        self._compute_fields(coefs)
+        nc_u, nc_v = vf.numcomp
+        self._vec = bool(vf.vec)
+        self._nc = (nc_u or 1, nc_v or 1)          # (trial, test) components
+        if self._vec:
+            self.num_components = lambda: self._nc
+        self.blocks = {}
+        for blk, coefs in self._analyse().items():
+            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid)
+        first = next(iter(self.blocks.values()))
+        self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
 
     # ---- input evaluation (host side, like the reference) ------------------------------------
     def _physical_points(self):
@@ -379,60 +426,103 @@ class GenericFormAssembler(_AssemblerProtocol):
         return np.stack([np.ascontiguousarray(v) for v in vals.ravel()]).reshape(shape + self._grid_shape)
 
     def _analyse(self):
-        """evaluate the expression trees symbolically: {(test slot, trial slot): Coef}"""
+        """evaluate the expression trees symbolically:
+        {(test comp, trial comp): {(test deriv slot, trial deriv slot): Coef}}"""
         total = None
         for e in self._vf.exprs:
             val = e.ev(self._env)[()]
             total = val if total is None else total + val
-        coefs = {}
-        for (bt, bu), c in total.terms.items():
+        blocks = {}
+        for (st, su), c in total.terms.items():
             if self.arity == 1:
-                if bt is None or bu is not None:
+                if st is None or su is not None:
                     raise ValueError('a linear form must be linear in its basis function')
-                bu = -1
-            elif bt is None or bu is None:
-                raise ValueError('the form must be linear in both u and v (term without %s)' % ('v' if bt is None else 'u'))
+                blk, key = (st[0], None), (st[1], -1)
+            else:
+                if st is None or su is None:
+                    raise ValueError('the form must be linear in both u and v (term without %s)' % ('v' if st is None else 'u'))
+                blk, key = (st[0], su[0]), (st[1], su[1])
             if not c.is_zero():
-                coefs[(bt, bu)] = c
-        if not coefs:
+                blocks.setdefault(blk, {})[key] = c
+        if not blocks:
             raise ValueError('the form is identically zero')
-        return coefs
+        return blocks
 
-    def _compute_fields(self, coefs):
-        dev, be = self.dev, self.dev.be
-        if sorted(coefs) != self._keys:
+    def _recompute(self):
+        blocks = self._analyse()
+        if sorted(blocks, key=str) != sorted(self.blocks, key=str):
             raise RuntimeError('update() changed the structure of the form')
-        arrays, index = [], {}
-        phys = (_lib.PhysTerm * len(coefs))()
-        for t, key in enumerate(self._keys):
-            c = coefs[key]
-            inp = -1
-            if c.arr is not None:
-                if id(c.arr) not in index:
-                    index[id(c.arr)] = len(arrays)
-                    arr = np.ascontiguousarray(np.broadcast_to(c.arr, self._grid_shape), dtype=np.float64)
-                    arrays.append(be.from_host(arr.ravel()))
-                inp = index[id(c.arr)]
-            phys[t] = _lib.PhysTerm(key[0], key[1], inp, c.scale)
-        ptrs = (C.c_void_p * max(len(arrays), 1))(*[be.ptr(a) for a in arrays])
-        geo = self._geo
-        if _is_spline_geo(geo):
-            desc, keep = _lib.make_geo_desc(geo)
-            _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, C.byref(desc), None, len(coefs), phys,
-                                                                   len(arrays), ptrs, -1, -1, be.stream()))
-        else:
-            jac = np.ascontiguousarray(geo.grid_jacobian(self.gaussgrid), dtype=np.float64)
-            d_jac = be.from_host(jac.ravel())
-            _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, None, be.ptr(d_jac), len(coefs), phys,
-                                                                   len(arrays), ptrs, -1, -1, be.stream()))
-        be.synchronize()        # the uploaded coefficient arrays may be released now
+        for blk, coefs in blocks.items():
+            self.blocks[blk].compute_fields(coefs, self._geo)
+
+    # ---- vector-valued forms -----------------------------------------------------------------
+    def _block_mlb(self):
+        """device MLB tensors of all blocks: {(ct, cu): buffer}"""
+        return {blk: b.dev.assemble_mlb() for blk, b in self.blocks.items()}
+
+    def multi_blocks(self, indices):
+        """blocks[k][ct][cu] = A[(i_k, ct), (j_k, cu)] (``pyiga/genericasm.pxi:815-850``)"""
+        if not isinstance(indices, np.ndarray):
+            indices = np.array(list(indices), dtype=np.uint64)
+        indices = np.asarray(indices, dtype=np.uint64).reshape(-1, 2)
+        nc_u, nc_v = self._nc
+        out = np.zeros((indices.shape[0], nc_v, nc_u))
+        for (ct, cu), b in self.blocks.items():
+            out[:, ct, cu] = b.dev.be.to_host(b.dev.multi_entries_device(indices))
+        return out
+
+    def assemble_mlb(self, layout='packed', **kw):
+        if not self._vec:
+            return super().assemble_mlb(**kw)
+        dev = self.dev
+        S_base = dev.structure
+        nc_u, nc_v = self._nc
+        from .mlmatrix import MLStructure
+        S = S_base.join(MLStructure.dense((nc_v, nc_u)))
+        data = np.zeros(tuple(len(b) for b in S_base.bidx) + (nc_v * nc_u,))
+        for (ct, cu), buf in self._block_mlb().items():
+            data[..., ct * nc_u + cu] = dev.be.to_host(buf).reshape(data.shape[:-1])
+        X = MLMatrix(structure=S, data=data)
+        if layout == 'blocked':
+            L = S.L
+            X = X.reorder((L - 1,) + tuple(range(L - 1)))
+        return X
+
+    def assemble_csr(self, layout='blocked', format='csr', **kw):
+        if not self._vec:
+            return super().assemble_csr(**kw)
+        import scipy.sparse
+        nc_u, nc_v = self._nc
+        ds = self.dev.device_structure
+        mats = {}
+        for blk, buf in self._block_mlb().items():
+            mats[blk] = ds.to_csr(buf)
+        ref = next(iter(mats.values()))
+        if layout == 'packed':
+            data = np.zeros((ref.nnz, nc_v, nc_u))
+            for (ct, cu), A in mats.items():
+                data[:, ct, cu] = A.data
+            n = ref.shape[0]
+            A = scipy.sparse.bsr_matrix((data, ref.indices, ref.indptr), shape=(n * nc_v, ref.shape[1] * nc_u),
+                                        blocksize=(nc_v, nc_u))
+            return A.asformat(format)
+        zero = scipy.sparse.csr_matrix(ref.shape)
+        rows = [[mats.get((ct, cu), zero) for cu in range(nc_u)] for ct in range(nc_v)]
+        return scipy.sparse.bmat(rows, format='csr').asformat(format)
 
     # ---- arity 1 ------------------------------------------------------------------------------
     def assemble_vector(self):
-        """Load vector, shape = number of dofs per axis (``pyiga/genericasm.pxi:762-778``)."""
+        """Load vector, shape = number of dofs per axis (+ a trailing component axis for
+        vector-valued forms) (``pyiga/genericasm.pxi:762-778, 852-868``)."""
         if self.arity != 1:
             return None
-        return self.dev.be.to_host(self.dev.assemble_vector_device()).reshape(self.dev.ndofs_test)
+        be = self.dev.be
+        if not self._vec:
+            return be.to_host(self.dev.assemble_vector_device()).reshape(self.dev.ndofs_test)
+        out = np.zeros(self.dev.ndofs_test + (self._nc[1],))
+        for (ct, _), b in self.blocks.items():
+            out[..., ct] = be.to_host(b.dev.assemble_vector_device()).reshape(self.dev.ndofs_test)
+        return out
 
     def multi_entries(self, indices):
         if self.arity == 1:
@@ -469,12 +559,12 @@ class GenericFormAssembler(_AssemblerProtocol):
                 raise ValueError("unknown input '%s'" % name)
             self._args[name] = f
             self._env[name] = self._eval_input(f, *known[name])
-        self._compute_fields(self._analyse())
+        self._recompute()
 
     def update_params(self, **kwargs):
         for name, v in kwargs.items():
             self._env[name] = np.asarray(v, dtype=float)
-        self._compute_fields(self._analyse())
+        self._recompute()
 
 
 def _mentions_x(expr):
@@ -554,3 +644,29 @@ class L2FunctionalAssemblerPhys2D(_L2FunctionalBase):
 
 class L2FunctionalAssemblerPhys3D(_L2FunctionalBase):
     _dim, _physical = 3, True
+
+
+class _DivDivBase(GenericFormAssembler):
+    """``div(u) * div(v) * dx`` for vector-valued u, v (``pyiga/assemblers.pyx:692-881``)."""
+    _dim = None
+
+    @classmethod
+    def inputs(cls):
+        return {'geo': (cls._dim,)}
+
+    @classmethod
+    def parameters(cls):
+        return {}
+
+    def __init__(self, kvs0, geo):
+        from . import vform
+        self._vf = vform.divdiv_vf(self._dim)
+        super().__init__(kvs0, geo=geo)
+
+
+class DivDivAssembler2D(_DivDivBase):
+    _dim = 2
+
+
+class DivDivAssembler3D(_DivDivBase):
+    _dim = 3

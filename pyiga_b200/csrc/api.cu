@@ -71,7 +71,7 @@ static void k_fields(const PbFieldParams& prm, pbStream st) {
 template <int DIM, int NC, class Prog>
 static int k_fields_rows(const PbFieldParams& prm, long long row_begin, long long row_end, pbStream st) {
     const size_t ybytes = (size_t)prm.geo.Ng[DIM - 1] * NC * DIM * sizeof(double);
-    g_launches += (row_end - row_begin + (1LL << 30) - 1) >> 30;
+    g_launches += 1;
 #ifdef PB_EMULATE
     std::vector<double> Y(ybytes / sizeof(double));
     pb_emu_for(row_end - row_begin, [&](long long r) { pb_fields_row_seq<DIM, NC, Prog>(prm, row_begin + r, Y.data()); });
@@ -79,16 +79,13 @@ static int k_fields_rows(const PbFieldParams& prm, long long row_begin, long lon
     return 0;
 #else
     auto kern = pb_fields_row_kernel<DIM, NC, Prog>;
-    if (ybytes > 48 * 1024) {
-        if (ybytes > 200 * 1024) return fail(PB200_EUNSUPPORTED, "geometry control net too long on the last axis");
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ybytes));
+    const size_t gbytes = ybytes * PB_K2_ROWS;
+    if (gbytes > 48 * 1024) {
+        if (gbytes > 200 * 1024) return fail(PB200_EUNSUPPORTED, "geometry control net too long on the last axis");
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gbytes));
     }
-    long long done = row_begin;
-    while (done < row_end) {       // grid.x is limited to 2^31-1 blocks
-        const long long nb = std::min<long long>(row_end - done, 1LL << 30);
-        kern<<<(unsigned)nb, 128, ybytes, st>>>(prm, done);
-        done += nb;
-    }
+    const long long groups = (row_end - row_begin + PB_K2_ROWS - 1) / PB_K2_ROWS;
+    if (groups > 0) kern<<<(unsigned)groups, 128, gbytes, st>>>(prm, row_begin, row_end);
     return 0;
 #endif
 }

@@ -360,21 +360,36 @@ PB_HD void pb_fields_row_seq(const PbFieldParams& prm, long long row, double* Y)
 }
 
 #if defined(__CUDACC__)
-// one block per grid row; dynamic shared memory: Ng_last*NC*DIM doubles
+// One block per group of PB_K2_ROWS consecutive grid rows (same g0 in 3D); dynamic shared memory:
+// PB_K2_ROWS * Ng_last*NC*DIM doubles.  Threads own fixed positions on the last axis and visit the
+// rows of the group one after the other, so the block synchronises once per group.
+#define PB_K2_ROWS 8
 template <int DIM, int NC, class Prog>
-__global__ void __launch_bounds__(128) pb_fields_row_kernel(const __grid_constant__ PbFieldParams prm, long long row_begin) {
+__global__ void __launch_bounds__(128) pb_fields_row_kernel(const __grid_constant__ PbFieldParams prm, long long row_begin,
+                                                            long long row_end) {
     extern __shared__ double pb_Y[];
-    const long long row = row_begin + blockIdx.x;
-    int g[3] = {0, 0, 0};
-    if constexpr (DIM == 2) g[0] = (int)row;
-    else { g[0] = (int)(row / prm.G[1]); g[1] = (int)(row % prm.G[1]); }
+    const long long row0 = row_begin + (long long)blockIdx.x * PB_K2_ROWS;
+    const int nrows = (int)((row_end - row0) < PB_K2_ROWS ? (row_end - row0) : PB_K2_ROWS);
     const int NgL = prm.geo.Ng[DIM - 1];
-    for (int e = threadIdx.x; e < NgL * NC; e += blockDim.x)
-        pb_geo_row_partial<DIM>(prm.geo, g, e / NC, e % NC, pb_Y + (long long)e * DIM);
+    const int ysz = NgL * NC * DIM;
+    for (int e = threadIdx.x; e < nrows * NgL * NC; e += blockDim.x) {
+        const int r = e / (NgL * NC), t = e % (NgL * NC);
+        const long long row = row0 + r;
+        int g[3] = {0, 0, 0};
+        if constexpr (DIM == 2) g[0] = (int)row;
+        else { g[0] = (int)(row / prm.G[1]); g[1] = (int)(row % prm.G[1]); }
+        pb_geo_row_partial<DIM>(prm.geo, g, t / NC, t % NC, pb_Y + (long long)r * ysz + (long long)t * DIM);
+    }
     __syncthreads();
-    for (int gl = threadIdx.x; gl < prm.G[DIM - 1]; gl += blockDim.x) {
-        g[DIM - 1] = gl;
-        pb_fields_row_point<DIM, NC, Prog>(prm, g, pb_Y);
+    for (int r = 0; r < nrows; ++r) {
+        const long long row = row0 + r;
+        int g[3] = {0, 0, 0};
+        if constexpr (DIM == 2) g[0] = (int)row;
+        else { g[0] = (int)(row / prm.G[1]); g[1] = (int)(row % prm.G[1]); }
+        for (int gl = threadIdx.x; gl < prm.G[DIM - 1]; gl += blockDim.x) {
+            g[DIM - 1] = gl;
+            pb_fields_row_point<DIM, NC, Prog>(prm, g, pb_Y + (long long)r * ysz);
+        }
     }
 }
 #endif

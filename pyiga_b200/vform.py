@@ -16,9 +16,11 @@ parameter domain (``J^-1``, ``|det J|``, Gauss weights) happens in the K2 kernel
 (``csrc/geo_fields.cuh: PbProgGeneral``).  The matrix itself comes from the same sum-factorised
 pipeline as mass and stiffness (``pb200_asm_assemble_mlb`` with a generic stage plan).
 
-Linear forms (arity 1, e.g. ``'f * v * dx'``) give load vectors through the same machinery.
-Vector-valued basis functions, second derivatives and boundary integrals are not part of the
-device path; they raise ``NotImplementedError``.
+Linear forms (arity 1, e.g. ``'f * v * dx'``) give load vectors through the same machinery, and
+vector-valued basis functions (``bfuns=[('u', 2), ('v', 2)]``) are handled block by block: every
+pair of components is one scalar form of the family above.  Second derivatives, boundary
+integrals and forms over two different spaces are not part of the device path; they
+raise ``NotImplementedError``.
 """
 import re
 
@@ -55,8 +57,9 @@ class Coef:
 
 
 class Form:
-    """Scalar value of an expression: {(test slot, trial slot): Coef}; slot None = no basis function,
-    0 = function value, 1+a = derivative with respect to physical coordinate a (x, y, z order)."""
+    """Scalar value of an expression: {(test slot, trial slot): Coef}.  A slot is None (no basis
+    function) or (component, deriv) with deriv 0 = function value, 1+a = derivative with respect to
+    physical coordinate a (x, y, z order); scalar basis functions have component 0."""
 
     def __init__(self, terms=None):
         self.terms = dict(terms or {})
@@ -177,11 +180,19 @@ class Literal(Expr):
 
 
 class BasisFun(Expr):
-    def __init__(self, name, role):
+    def __init__(self, name, role, numcomp=None):
         self.name, self.role = name, role       # role: 'trial' (u, columns) or 'test' (v, rows)
+        self.numcomp = numcomp                  # None: scalar; k: vector-valued with k components
+        self.shape = () if numcomp is None else (numcomp,)
+
+    def _form(self, comp, deriv):
+        slot = (comp, deriv)
+        return Form({((None, slot) if self.role == 'trial' else (slot, None)): Coef(1.0)})
 
     def ev(self, env):
-        return _obj((), [Form({((None, 0) if self.role == 'trial' else (0, None)): Coef(1.0)})])
+        if self.numcomp is None:
+            return _obj((), [self._form(0, 0)])
+        return _obj(self.shape, (self._form(c, 0) for c in range(self.numcomp)))
 
 
 class Input(Expr):
@@ -259,15 +270,23 @@ class Transpose(Expr):
 
 
 class Grad(Expr):
+    """gradient of a basis function: vector for scalar functions, Jacobian (rows = components) for
+    vector-valued ones"""
     def __init__(self, e, dim):
-        if not isinstance(e, BasisFun):
+        if isinstance(e, Index) and isinstance(e.e, BasisFun) and isinstance(e.idx, int):
+            self.e, self.comp = e.e, e.idx          # gradient of one component of a vector function
+        elif isinstance(e, BasisFun):
+            self.e, self.comp = e, None
+        else:
             raise NotImplementedError('grad() is implemented for the basis functions u and v only')
-        self.e, self.shape, self.dim = e, (dim,), dim
+        self.dim = dim
+        vec = self.e.numcomp is not None and self.comp is None
+        self.shape = (self.e.numcomp, dim) if vec else (dim,)
 
     def ev(self, env):
-        trial = self.e.role == 'trial'
-        return _obj(self.shape, (Form({((None, 1 + a) if trial else (1 + a, None)): Coef(1.0)})
-                                 for a in range(self.dim)))
+        if len(self.shape) == 2:
+            return _obj(self.shape, (self.e._form(c, 1 + a) for c in range(self.shape[0]) for a in range(self.dim)))
+        return _obj(self.shape, (self.e._form(self.comp or 0, 1 + a) for a in range(self.dim)))
 
 
 class Contract(Expr):
@@ -332,11 +351,20 @@ as_matrix = as_expr
 # operators available in form strings (names as in pyiga/vform.py:1518-1733)
 
 
+def _bfun_dim(e):
+    return (e.e if isinstance(e, Index) else e)._dim
+
+
 def grad(e, dims=None, parametric=False):
     if parametric or dims is not None:
         raise NotImplementedError('parametric / partial gradients are not part of the device path')
     e = as_expr(e)
-    return Grad(e, e._dim)
+    return Grad(e, _bfun_dim(e))
+
+
+def div(e, parametric=False):
+    """divergence of a vector-valued basis function"""
+    return tr(grad(e, parametric=parametric))
 
 
 def Dx(e, k, times=1, parametric=False):
@@ -395,18 +423,25 @@ class VForm:
         self.params = []        # [(name, shape)]
         self.dx = Measure()
         self.Geo = Input('@x', (dim,))
-        self._uses_x = False
+        self.numcomp = (None, None)
 
     def basisfuns(self, components=(None, None), spaces=(0, 0)):
-        if any(c not in (None, 1) for c in components):
-            raise NotImplementedError('vector-valued basis functions are not part of the device path')
         if any(s != 0 for s in spaces):
             raise NotImplementedError('forms over two different spaces are not part of the device path')
-        v = BasisFun('v', 'test')
+        components = tuple(components)
+        if self.arity == 1:
+            components = components[-1:]
+        if all(c in (None, 1) for c in components):
+            components = len(components) * (None,)      # scalar assembler
+        else:
+            components = tuple(1 if c is None else int(c) for c in components)
+            self.vec = True
+        v = BasisFun('v', 'test', components[-1])
         v._dim = self.dim
+        self.numcomp = (components[0] if self.arity == 2 else None, components[-1])   # (trial, test)
         if self.arity == 1:
             return v
-        u = BasisFun('u', 'trial')
+        u = BasisFun('u', 'trial', components[0])
         u._dim = self.dim
         return u, v
 
@@ -421,7 +456,7 @@ class VForm:
     def add(self, expr):
         expr = as_expr(expr)
         if expr.shape != ():
-            raise NotImplementedError('vector-valued forms are not part of the device path')
+            raise ValueError('the integrand must be scalar (use inner() / dot() to contract vectors)')
         self.exprs.append(expr)
 
     def num_spaces(self):
@@ -469,22 +504,23 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
     if 'ds' in words:
         raise NotImplementedError('surface integrals are not part of the device path')
     if bfuns is None:
-        names = sorted(words & {'u', 'v'})
+        names, comps = sorted(words & {'u', 'v'}), None
     else:
-        names = []
+        names, comps = [], []
         for bf in bfuns:
             bf = (bf,) if isinstance(bf, str) else tuple(bf)
-            if (len(bf) > 1 and bf[1] not in (None, 1)) or (len(bf) > 2 and bf[2] != 0):
-                raise NotImplementedError('vector-valued / multi-space basis functions are not part of the device path')
+            if len(bf) > 2 and bf[2] != 0:
+                raise NotImplementedError('multi-space basis functions are not part of the device path')
             names.append(bf[0])
+            comps.append(bf[1] if len(bf) > 1 else 1)
     if len(names) not in (1, 2):
         raise ValueError('arity should be 1 or 2')
     vf = VForm(dim=dim, arity=len(names))
     loc = {}
     if vf.arity == 1:
-        loc[names[0]] = vf.basisfuns()
+        loc[names[0]] = vf.basisfuns(components=tuple(comps) if comps else (None,))
     else:
-        u, v = vf.basisfuns()
+        u, v = vf.basisfuns(components=tuple(comps) if comps else (None, None))
         loc[names[0]], loc[names[1]] = u, v
     for name in sorted(set(args.keys()) & words):
         if callable(args[name]):
@@ -506,6 +542,13 @@ def mass_vf(dim):
     vf = VForm(dim)
     u, v = vf.basisfuns()
     vf.add(u * v * vf.dx)
+    return vf
+
+
+def divdiv_vf(dim):
+    vf = VForm(dim)
+    u, v = vf.basisfuns(components=(dim, dim))
+    vf.add(div(u) * div(v) * vf.dx)
     return vf
 
 

@@ -173,6 +173,18 @@ def main():
     out['ip_phys'] = assemble.inner_products(kvs, fpar, f_physical=True, geo=geos['tnb'])
     out['ip_nogeo'] = assemble.inner_products(kvs, fpar)
 
+    # ---- 8. vector-valued forms (test/test_assemble.py:170-181, 452-472) ----------------------------
+    from helpers import VECFORMS
+    for name, (form, bfuns, inputs, case, gname) in VECFORMS.items():
+        kvs, _ = cases[case]
+        X = assemble.assemble(form, kvs, geo=geos[gname], bfuns=bfuns, format='mlb', layout='packed', **inputs)
+        out['vv_%s_mlb' % name] = X.data
+        asm = assemble.instantiate_assembler(form, kvs, dict(inputs, geo=geos[gname]), bfuns)
+        out['vv_%s_blocks' % name] = np.array(asm.multi_blocks([(0, 0), (0, 1), (2, 1), (5, 5)]))
+    kvs, _ = cases['a2_qa']
+    out['vv_divdiv2_bsr'] = assemble.divdiv(kvs, geos['bqa'], layout='packed', format='bsr').toarray()
+    out['vv_rhs2'] = assemble.assemble('inner(g, v) * dx', kvs, geo=geos['qa'], bfuns=[('v', 2)], g=lambda x, y: (x, -y))
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

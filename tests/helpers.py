@@ -83,3 +83,12 @@ LFORMS = {
     'lin2': ('g * v * dx', {'g': lambda x, y: x * y + 1.0}, 'a2_qa', 'qa'),
     'lin3n': ('inner(b, grad(v)) * dx', {'b': lambda x, y, z: (y, 1.0 + x, z * x)}, 'a3_nurbs', 'tnb'),
 }
+
+# vector-valued forms: name -> (form, bfuns, inputs, space case, geometry)
+VECFORMS = {
+    'nonsym2': ('inner(as_matrix([[2,1],[0,0]]).dot(u), v) * dx', [('u', 2), ('v', 2)], {}, 'a2_qa', 'qa'),
+    'elast3': ('(2.0*inner(0.5*(grad(u)+grad(u).T), grad(v)) + lam*div(u)*div(v)) * dx', [('u', 3), ('v', 3)],
+               {'lam': 1.5}, 'a3_tb', 'tb'),
+    'stokes_like2': ('(inner(grad(u), grad(v)) + c * inner(u, v)) * dx', [('u', 2), ('v', 2)],
+                     {'c': lambda x, y: 1.0 + x * y}, 'a2_mixed', 'bqa'),
+}

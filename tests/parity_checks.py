@@ -362,3 +362,38 @@ def check_edge_cases(ref):
                        geometry.unit_square().coeffs)
     prob.jac = Shear().grid_jacobian(prob.grid)
     assert_close_rel(got, orc.assemble_mlb(prob, 'stiffness').ravel(), what='host-evaluated geometry')
+
+
+def check_vector_forms(ref):
+    """vector-valued basis functions: layouts 'packed'/'blocked', formats csr/bsr/mlb, multi_blocks"""
+    from helpers import VECFORMS
+    from pyiga_b200 import assemble
+    for name, (form, bfuns, inputs, case, gname) in VECFORMS.items():
+        kvs = make_space(ref, case)
+        geo = make_geo(ref, gname)
+        want = ref['vv_%s_mlb' % name]
+        X = assemble.assemble(form, kvs, geo=geo, bfuns=bfuns, format='mlb', layout='packed', **inputs)
+        assert X.data.shape == want.shape
+        assert_close_rel(X.data, want, what='vector form %s (mlb)' % name)
+        nc = bfuns[0][1]
+        n = int(np.prod([kv.numdofs for kv in kvs]))
+        P = assemble.assemble(form, kvs, geo=geo, bfuns=bfuns, layout='packed', format='bsr', **inputs)
+        assert P.format == 'bsr' and P.blocksize == (nc, nc) and P.shape == (n * nc, n * nc)
+        B = assemble.assemble(form, kvs, geo=geo, bfuns=bfuns, layout='blocked', **inputs)
+        # blocked = packed with dofs regrouped by component
+        perm = np.arange(n * nc).reshape(n, nc).T.ravel()
+        Pd = P.toarray()
+        assert abs(B.toarray() - Pd[np.ix_(perm, perm)]).max() <= RTOL * abs(Pd).max()
+        # reference matrix from the MLB fixture
+        S = X.structure
+        I, J = (a.astype(np.int64) for a in S.nonzero())
+        assert abs(Pd[I, J] - want.ravel()).max() <= RTOL * abs(want).max()
+        asm = assemble.instantiate_assembler(form, kvs, dict(inputs, geo=geo), bfuns)
+        assert asm.num_components() == (nc, nc)
+        blocks = asm.multi_blocks([(0, 0), (0, 1), (2, 1), (5, 5)])
+        assert_close_rel(blocks, ref['vv_%s_blocks' % name], what='multi_blocks ' + name)
+    kvs = make_space(ref, 'a2_qa')
+    A = assemble.divdiv(kvs, make_geo(ref, 'bqa'), layout='packed', format='bsr')
+    assert_close_rel(A.toarray(), ref['vv_divdiv2_bsr'], what='divdiv')
+    f = assemble.assemble('inner(g, v) * dx', kvs, geo=make_geo(ref, 'qa'), bfuns=[('v', 2)], g=lambda x, y: (x, -y))
+    assert_close_rel(f, ref['vv_rhs2'], what='vector-valued load vector')

@@ -95,3 +95,7 @@ def test_linear_forms(emu, ref):
 
 def test_edge_cases(emu, ref):
     pc.check_edge_cases(ref)
+
+
+def test_vector_forms(emu, ref):
+    pc.check_vector_forms(ref)

@@ -71,6 +71,10 @@ def test_vform_protocol(cuda, ref):
     pc.check_vform_protocol(ref)
 
 
+def test_vector_forms(cuda, ref):
+    pc.check_vector_forms(ref)
+
+
 def test_edge_cases(cuda, ref):
     pc.check_edge_cases(ref)
 

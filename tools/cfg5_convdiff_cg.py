@@ -24,6 +24,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from pyiga_b200 import _device, assemble, bspline, geometry, vform
     from pyiga_b200.dist import GatheredKronecker, SlabAssembly, SlabOperator, cg, partition_rows
@@ -91,6 +92,7 @@ def main():
     out['matvec_ms'] = mv_ms
     out['matvec_GBps_local'] = 8.0 * sa.local_nnz / (mv_ms * 1e-3) / 1e9
     out['halo_bytes'] = op.halo_bytes
+    cg(lambda v: op.matvec(v).clone(), b, M=prec, rtol=1e-10, maxiter=2)     # warm up the collectives
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     x, it, hist = cg(lambda v: op.matvec(v).clone(), b, M=prec, rtol=1e-10, maxiter=100)
