@@ -362,6 +362,7 @@ struct pb200_assembler {
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
     bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
+    bool mirror_opt = true;                             // symmetric forms: compute the upper half of the final stage, mirror the rest
     bool fused_plans = true;                            // multi-output stage kernels (S1A/S1B/S2B); false: one launch per output
     // optional per-kernel timing of the last assemble call (CUDA events on the launch stream)
     bool timing = false;
@@ -392,6 +393,7 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!strcmp(name, "force_walk")) { a->force_walk = value != 0; return 0; }
     if (!strcmp(name, "lane_v1")) { a->lane_v1 = value != 0; return 0; }
     if (!strcmp(name, "fused_plans")) { a->fused_plans = value != 0; return 0; }
+    if (!strcmp(name, "mirror")) { a->mirror_opt = value != 0; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
 }
 
@@ -1071,7 +1073,9 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     prm.V2 = D.Vu;
     prm.ret_mu = D.ret_mu;
     // final stages (node axis contiguous, one output, single interior knots): warp-per-line kernel
-    if (prm.in_sc == 1 && prm.out_smu == 1 && prm.w_mode == 0 && a->lane_ok[axis] && !a->force_walk) {
+    bool nofilter = true;
+    for (int o = 0; o < PB_WALK_MAXOUT; ++o) nofilter = nofilter && prm.w_mode[o] == 0;
+    if (prm.in_sc == 1 && prm.out_smu == 1 && nofilter && a->lane_ok[axis] && !a->force_walk) {
         PbWalkLaunch lane = pb_find_walk(PB_PLAN_LANE_BASE + plan, P, Q);
         if (lane) {
             int e = lane(&prm, a->lane_v1 ? -16 : 64, 0, st);
@@ -1202,7 +1206,18 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
     double* X2 = X1 + t1 * s1;
     const long long npts = a->npts;
     const double* F = a->d_fields;
-    const int keep_mode = uses_transposes(a) ? 2 : 1;
+    // slab filters (see walk.cuh): terms that are read through the transposed band index must exist
+    // for every pair with i or j in the slab (2); terms that are only read directly are needed for
+    // the lines the final stage computes: rows of the slab (1), or - when the final stage mirrors
+    // the symmetric half - only their "upper" part (3)
+    const int last_axis = a->dim - 1;
+    const int final_plan = stiff ? PB_PLAN_FINAL4 : PB_PLAN_COPY;
+    const bool mirror = a->mirror_opt && a->symmetric && a->same_space && a->form != PB200_FORM_CUSTOM
+                        && a->lane_ok[last_axis] && !a->force_walk
+                        && pb_find_walk(PB_PLAN_LANE_BASE + final_plan, a->hax[last_axis].U.p, a->hax[last_axis].q) != nullptr;
+    const int m_tr = uses_transposes(a) ? 2 : 1;        // terms read directly and transposed
+    const int m_dir = mirror ? 3 : 1;                   // terms read directly only
+    auto set_modes = [](int* dst, std::initializer_list<int> m) { int k = 0; for (int v : m) dst[k++] = v; };
 
     const AxisHost &H0 = a->hax[0], &H1 = a->hax[1];
     const PbAxis &D0 = a->dax[0], &D1 = a->dax[1];
@@ -1238,7 +1253,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                     p.in_sx = 1; p.in_sc = G1 * Glast;
                     p.out_sx = 1; p.out_smu = G1 * Glast; p.mu_base = S.mu_lo;
                     p.s_begin = S.sa; p.s_end = S.sb;
-                    p.w_mode = 1; p.w_lo = S.ra; p.w_hi = S.rb;
+                    p.w_mode[0] = 1; p.w_lo = S.ra; p.w_hi = S.rb;
                 } else if (k == 1 && dim == 3) {
                     p.X = (int)Glast; p.nthreads = (long long)Mrows * Glast;
                     p.u_begin = S.mu_lo; p.u_base_in = S.mu_lo; p.u_base_out = S.mu_lo;
@@ -1278,10 +1293,11 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             p.in_sx = 1; p.in_sc = G1;
             p.out_sx = 1; p.out_smu = G1; p.mu_base = S.ext_lo;
             p.s_begin = S.sa; p.s_end = S.sb;
-            p.w_mode = keep_mode; p.w_lo = S.ra; p.w_hi = S.rb;
+            p.w_lo = S.ra; p.w_hi = S.rb;
+            const int modes2d[3] = {m_dir, m_tr, m_dir};                        // (v,v), (v,d1), (d1,d1)
             if (stiff && a->fused_plans) {
                 p.in[0] = F + 2 * npts; p.in[1] = F + 1 * npts; p.in[2] = F;     // B11, B01, B00
-                for (int t = 0; t < 3; ++t) p.out[t] = X1 + t * s1;
+                for (int t = 0; t < 3; ++t) { p.out[t] = X1 + t * s1; p.w_mode[t] = modes2d[t]; }
                 rc = run_stage(PB_PLAN_S1_2D, a, 0, p, st, "s1_2d");
             } else if (stiff) {
                 // one launch per output: every field is read by exactly one of them
@@ -1290,11 +1306,11 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                 const char* nm[3] = {"s1_one11", "s1_one10", "s1_copy"};
                 for (int t = 0; t < 3 && !rc; ++t) {
                     PbWalkParams q = p;
-                    q.in[0] = F + field[t] * npts; q.out[0] = X1 + t * s1;
+                    q.in[0] = F + field[t] * npts; q.out[0] = X1 + t * s1; q.w_mode[0] = modes2d[t];
                     rc = run_stage(plan[t], a, 0, q, st, nm[t]);
                 }
             } else {
-                p.in[0] = F; p.out[0] = X1;
+                p.in[0] = F; p.out[0] = X1; p.w_mode[0] = m_dir;
                 rc = run_stage(PB_PLAN_COPY, a, 0, p, st, "s1_copy");
             }
             if (rc) return rc;
@@ -1309,6 +1325,11 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             p.out_su = M1; p.out_smu = 1; p.mu_base = 0;
             p.s_begin = 0; p.s_end = H1.n;
             p.out[0] = d_out;
+            if (mirror) {
+                p.u_pair_i = D0.pair_i; p.u_pair_j = D0.pair_j;
+                p.u_mode[0] = 1; p.u_lo = S.ra; p.u_hi = S.rb;
+                p.mirror = 1;
+            }
             if (stiff) {
                 p.in[0] = X1; p.in[1] = X1 + s1; p.in[2] = X1 + s1; p.in[3] = X1 + 2 * s1;
                 rc = run_stage(PB_PLAN_FINAL4, a, 1, p, st, "s2_final4");
@@ -1332,18 +1353,21 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.in_sx = 1; p.in_sc = G1 * G2;
         p.out_sx = 1; p.out_smu = G1 * G2; p.mu_base = S.ext_lo;
         p.s_begin = S.sa; p.s_end = S.sb;
-        p.w_mode = keep_mode; p.w_lo = S.ra; p.w_hi = S.rb;
+        p.w_lo = S.ra; p.w_hi = S.rb;
+        // X1 terms (v,v) (v,d1) (v,d2) (d1,d1) (d1,d2) (d2,d2): which are read through a transposed index?
+        const int modes1[6] = {m_dir, m_tr, m_tr, m_dir, m_tr, m_dir};
         if (stiff && !a->fused_plans) {
             const int plan[6] = {PB_PLAN_ONE11, PB_PLAN_ONE10, PB_PLAN_ONE10, PB_PLAN_COPY, PB_PLAN_COPY, PB_PLAN_COPY};
             const int field[6] = {5, 4, 2, 3, 1, 0};                            // B22, B12, B02, B11, B01, B00
             const char* nm[6] = {"s1_one11", "s1_one10a", "s1_one10b", "s1_copya", "s1_copyb", "s1_copyc"};
             for (int t = 0; t < 6 && !rc; ++t) {
                 PbWalkParams q = p;
-                q.in[0] = F + field[t] * npts; q.out[0] = X1 + t * s1;
+                q.in[0] = F + field[t] * npts; q.out[0] = X1 + t * s1; q.w_mode[0] = modes1[t];
                 rc = run_stage(plan[t], a, 0, q, st, nm[t]);
             }
         } else if (stiff) {
             PbWalkParams pa = p, pb = p;
+            for (int t = 0; t < 3; ++t) { pa.w_mode[t] = modes1[t]; pb.w_mode[t] = modes1[3 + t]; }
             pa.in[0] = F + 5 * npts; pa.in[1] = F + 4 * npts; pa.in[2] = F + 2 * npts;   // B22, B12, B02
             for (int t = 0; t < 3; ++t) pa.out[t] = X1 + t * s1;
             pb.in[0] = F + 3 * npts; pb.in[1] = F + 1 * npts; pb.in[2] = F;              // B11, B01, B00
@@ -1352,7 +1376,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             if (rc) return rc;
             rc = run_stage(PB_PLAN_S1B, a, 0, pb, st, "s1b");
         } else {
-            p.in[0] = F; p.out[0] = X1;
+            p.in[0] = F; p.out[0] = X1; p.w_mode[0] = m_dir;
             rc = run_stage(PB_PLAN_COPY, a, 0, p, st, "s1_copy");
         }
         if (rc) return rc;
@@ -1364,16 +1388,19 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.u_begin = S.ext_lo; p.u_base_in = S.ext_lo; p.u_base_out = S.ext_lo;
         p.tr_u = D0.tr;
         p.u_pair_i = D0.pair_i; p.u_pair_j = D0.pair_j;
-        p.u_mode = keep_mode; p.u_lo = S.ra; p.u_hi = S.rb;
+        p.u_lo = S.ra; p.u_hi = S.rb;
+        // X2 terms (v,v) (v,d2) (d2,d2): only (v,d2) is read through the transposed index
+        const int modes2[3] = {m_dir, m_tr, m_dir};
         p.in_su = G1 * G2; p.in_sx = 1; p.in_sc = G2;
         p.out_su = M1 * G2; p.out_sx = 1; p.out_smu = G2; p.mu_base = 0;
         p.s_begin = 0; p.s_end = H1.n;
         if (stiff) {
             PbWalkParams pa = p, pb = p;
             pa.in[0] = X1; pa.in[1] = X1 + s1; pa.in[2] = X1 + s1; pa.in[3] = X1 + 3 * s1;
-            pa.out[0] = X2;
+            pa.out[0] = X2; pa.u_mode[0] = modes2[0];
             pb.in[0] = X1 + 2 * s1; pb.in[1] = X1 + 4 * s1; pb.in[2] = X1 + 5 * s1;
             pb.out[0] = X2 + s2; pb.out[1] = X2 + 2 * s2;
+            pb.u_mode[0] = modes2[1]; pb.u_mode[1] = modes2[2];
             rc = run_stage(PB_PLAN_FINAL4, a, 1, pa, st, "s2a_final4");
             if (rc) return rc;
             if (a->fused_plans) {
@@ -1382,12 +1409,13 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                 PbWalkParams pc = p, pd = p;
                 pc.in[0] = X1 + 2 * s1; pc.in[1] = X1 + 4 * s1; pc.out[0] = X2 + s2;    // (v,d2)[0,0] + (d1,d2)[1,0]
                 pd.in[0] = X1 + 5 * s1; pd.out[0] = X2 + 2 * s2;                          // (d2,d2)[0,0]
+                pc.u_mode[0] = modes2[1]; pd.u_mode[0] = modes2[2];
                 rc = run_stage(PB_PLAN_PAIRT, a, 1, pc, st, "s2_pairt");
                 if (rc) return rc;
                 rc = run_stage(PB_PLAN_COPY, a, 1, pd, st, "s2_copy");
             }
         } else {
-            p.in[0] = X1; p.out[0] = X2;
+            p.in[0] = X1; p.out[0] = X2; p.u_mode[0] = m_dir;
             rc = run_stage(PB_PLAN_COPY, a, 1, p, st, "s2_copy");
         }
         if (rc) return rc;
@@ -1402,6 +1430,13 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.out_su = M1 * M2; p.out_sv = M2; p.out_smu = 1; p.mu_base = 0;
         p.s_begin = 0; p.s_end = H2.n;
         p.out[0] = d_out;
+        if (mirror) {
+            p.u_pair_i = D0.pair_i; p.u_pair_j = D0.pair_j;
+            p.v_pair_i = D1.pair_i; p.v_pair_j = D1.pair_j;
+            p.u_mode[0] = 1; p.u_lo = S.ra; p.u_hi = S.rb;
+            p.tr_u = D0.tr; p.tr_v = D1.tr;
+            p.mirror = 1;
+        }
         if (stiff) {
             p.in[0] = X2; p.in[1] = X2 + s2; p.in[2] = X2 + s2; p.in[3] = X2 + 2 * s2;
             rc = run_stage(PB_PLAN_FINAL4, a, 2, p, st, "s3_final4");

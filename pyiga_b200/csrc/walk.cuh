@@ -44,7 +44,14 @@ struct PbWalkParams {
     const int* tr_v;
     const int* u_pair_i;            // (i,j) of band entry u, for the slab filter (or null)
     const int* u_pair_j;
-    int u_mode, u_lo, u_hi;         // 0: all u;  1: keep i in [lo,hi);  2: keep i or j in [lo,hi)
+    // line filter on the band entry u = (i,j) of axis 0, per output term:
+    //   0: all u;  1: i in [lo,hi);  2: i or j in [lo,hi);
+    //   3: i in [lo,hi) and (i <= j or j outside [lo,hi))   ("upper half": the rest is mirrored)
+    // a line runs if any output wants it; inputs that only feed unwanted outputs are not loaded
+    int u_mode[PB_WALK_MAXOUT], u_lo, u_hi;
+    const int* v_pair_i;            // (i,j) of band entry v (final stage with mirroring)
+    const int* v_pair_j;
+    int mirror;                     // final stage: also write the transposed line (symmetric forms)
     // ---- input / output terms ---------------------------------------------------------------
     const double* in[PB_WALK_MAXOPS];   // per op: base pointer of its input term
     long long in_su, in_sv, in_sx, in_sc;   // strides (doubles) of u, v, x and of the node index
@@ -57,9 +64,14 @@ struct PbWalkParams {
     const int* first;               // [n]
     const double* V2;               // [G][2][P+1]
     const int* ret_mu;              // [N][2P+1]
-    int w_mode, w_lo, w_hi;         // retire filter on the walk-axis pair (i,j), as u_mode
+    int w_mode[PB_WALK_MAXOUT], w_lo, w_hi;     // retire filter on the walk-axis pair (i,j), as u_mode
     int f_lo, f_hi;                 // functions retired by this walk: [first[s_begin], min(N, first[s_end-1]+P+1))
 };
+
+PB_HD bool pb_keep(int mode, int i, int j, int lo, int hi) {
+    const bool ki = (i >= lo && i < hi), kj = (j >= lo && j < hi);
+    return mode == 0 || (mode == 1 && ki) || (mode == 2 && (ki || kj)) || (mode == 3 && ki && (i <= j || !kj));
+}
 
 template <int I> struct PbIC { static constexpr int value = I; };
 
@@ -153,11 +165,17 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
     const long long t2 = tid / prm.X;
     const int v = (int)(t2 % prm.V);
     const int u = (int)(t2 / prm.V) + prm.u_begin;
-    if (prm.u_mode != 0) {
-        const int ui = prm.u_pair_i[u], uj = prm.u_pair_j[u];
-        const bool ki = (ui >= prm.u_lo && ui < prm.u_hi);
-        const bool kj = (uj >= prm.u_lo && uj < prm.u_hi);
-        if (!(ki || (prm.u_mode == 2 && kj))) return;
+    bool want[NOUT];
+    {
+        bool any = false;
+        const bool filt = prm.u_pair_i != nullptr;
+        const int ui = filt ? prm.u_pair_i[u] : 0, uj = filt ? prm.u_pair_j[u] : 0;
+        pb_static_for<0, NOUT>([&](auto O) {
+            constexpr int o = decltype(O)::value;
+            want[o] = !filt || pb_keep(prm.u_mode[o], ui, uj, prm.u_lo, prm.u_hi);
+            any = any || want[o];
+        });
+        if (!any) return;
     }
     const long long off_in = (long long)(u - prm.u_base_in) * prm.in_su + (long long)v * prm.in_sv
                              + (long long)x * prm.in_sx;
@@ -174,7 +192,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
     // a null input pointer means "term absent" (generic forms): it reads as zero
     pb_static_for<0, NOPS>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        ld.has[i] = prm.in[i] != nullptr;
+        ld.has[i] = prm.in[i] != nullptr && want[Plan::op(i).out];
         ld.src[i] = prm.in[i] + (Plan::op(i).tr ? off_in_tr : off_in);
     });
     ld.sc = prm.in_sc;
@@ -198,18 +216,11 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
             const int mu = rm[k];
             const int a = (k <= P) ? 0 : (k - P);
             const int b = (k <= P) ? k : 0;
-            bool keep = (mu >= 0);
-            if (prm.w_mode != 0) {
-                const int i = f + a, j = f + b;
-                const bool ki = (i >= prm.w_lo && i < prm.w_hi);
-                const bool kj = (j >= prm.w_lo && j < prm.w_hi);
-                keep = keep && (ki || (prm.w_mode == 2 && kj));
-            }
-            if (keep) {
+            if (mu >= 0) {
                 const long long o_off = off_out + (long long)(mu - prm.mu_base) * prm.out_smu;
                 pb_static_for<0, NOUT>([&](auto O) {
                     constexpr int o = decltype(O)::value;
-                    prm.out[o][o_off] = acc[o][a][b];
+                    if (want[o] && pb_keep(prm.w_mode[o], f + a, f + b, prm.w_lo, prm.w_hi)) prm.out[o][o_off] = acc[o][a][b];
                 });
             }
         }
@@ -507,7 +518,7 @@ PB_HD void pb_span_block(const double (&x)[Q][Plan::NOPS], const double (&D)[Q][
 }
 
 // line decode shared by the warp kernel and its emulation
-struct PbLineOffsets { long long in, in_tr, out; bool keep; };
+struct PbLineOffsets { long long in, in_tr, out, out_tr; bool keep, mirror; };
 template <class Plan>
 PB_HD PbLineOffsets pb_decode_line(const PbWalkParams& prm, long long line) {
     PbLineOffsets o;
@@ -516,11 +527,21 @@ PB_HD PbLineOffsets pb_decode_line(const PbWalkParams& prm, long long line) {
     const int v = (int)(t2 % prm.V);
     const int u = (int)(t2 / prm.V) + prm.u_begin;
     o.keep = true;
-    if (prm.u_mode != 0) {
+    o.mirror = false;
+    if (prm.u_pair_i != nullptr) {
         const int ui = prm.u_pair_i[u], uj = prm.u_pair_j[u];
-        const bool ki = (ui >= prm.u_lo && ui < prm.u_hi);
-        const bool kj = (uj >= prm.u_lo && uj < prm.u_hi);
-        o.keep = ki || (prm.u_mode == 2 && kj);
+        o.keep = pb_keep(prm.u_mode[0], ui, uj, prm.u_lo, prm.u_hi);
+        if (prm.mirror) {
+            // symmetric form: of a line and its transposed partner only the "upper" one is computed
+            // (if the partner row belongs to this slab) and its result is written to both
+            const bool partner_owned = (uj >= prm.u_lo && uj < prm.u_hi);
+            int vi = 0, vj = 0;
+            if (prm.v_pair_i != nullptr) { vi = prm.v_pair_i[v]; vj = prm.v_pair_j[v]; }
+            const bool upper = ui < uj || (ui == uj && vi <= vj);
+            const bool self = (ui == uj && vi == vj);
+            o.keep = o.keep && (!partner_owned || upper);
+            o.mirror = partner_owned && upper && !self;
+        }
     }
     o.in = (long long)(u - prm.u_base_in) * prm.in_su + (long long)v * prm.in_sv + (long long)x * prm.in_sx;
     o.in_tr = o.in;
@@ -530,6 +551,12 @@ PB_HD PbLineOffsets pb_decode_line(const PbWalkParams& prm, long long line) {
         o.in_tr = (long long)(ut - prm.u_base_in) * prm.in_su + (long long)vt * prm.in_sv + (long long)x * prm.in_sx;
     }
     o.out = (long long)(u - prm.u_base_out) * prm.out_su + (long long)v * prm.out_sv + (long long)x * prm.out_sx;
+    o.out_tr = o.out;
+    if (o.mirror) {
+        const int ut = prm.tr_u ? prm.tr_u[u] : u;
+        const int vt = prm.tr_v ? prm.tr_v[v] : v;
+        o.out_tr = (long long)(ut - prm.u_base_out) * prm.out_su + (long long)vt * prm.out_sv + (long long)x * prm.out_sx;
+    }
     return o;
 }
 
@@ -578,6 +605,10 @@ PB_HD void pb_lane_span_seq(const PbWalkParams& prm, long long line, int batch) 
             for (int t = 0; t <= P - d; ++t)
                 if (lane - t >= 0) sum += (k <= P) ? Ls[lane - t][t][t + d] : Ls[lane - t][t + d][t];
             prm.out[0][lo.out + (long long)(rm[k] - prm.mu_base)] = sum;
+            if (lo.mirror) {        // entry (i,j) of this line is entry (j,i) of the transposed line
+                const int kt = (k == 0) ? 0 : (k <= P ? k + P : k - P);
+                prm.out[0][lo.out_tr + (long long)(rm[kt] - prm.mu_base)] = sum;
+            }
         }
     }
 }
@@ -679,9 +710,10 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
     constexpr int STAGE = NOPS * SEG;                       // doubles per pipeline stage
     extern __shared__ __align__(16) double pb_lane_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + Cfg::OUTPAD + Cfg::LOSLOTS);
+    double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + 2 * Cfg::OUTPAD + Cfg::LOSLOTS);
     double* obuf = ring + NST * STAGE;
-    long long* lo_ring = reinterpret_cast<long long*>(obuf + Cfg::OUTPAD);
+    double* obuf_t = obuf + Cfg::OUTPAD;                // entries of the transposed line (mirroring)
+    long long* lo_ring = reinterpret_cast<long long*>(obuf_t + Cfg::OUTPAD);
 
     const long long warp = (long long)blockIdx.x * 4 + wib;
     const int batch = blockIdx.y;
@@ -745,7 +777,8 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
         const PbLineOffsets lo = pb_decode_line<Plan>(prm, line);
         if (lane == 0) {
             lo_ring[4 * st + 0] = lo.out;
-            lo_ring[4 * st + 1] = lo.keep ? 1 : 0;
+            lo_ring[4 * st + 1] = (lo.keep ? 1 : 0) | (lo.mirror ? 2 : 0);
+            lo_ring[4 * st + 2] = lo.out_tr;
         }
         double* dst = ring + (size_t)st * STAGE;
         if (lo.keep) {
@@ -786,7 +819,9 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
         __syncwarp();
         PbLineOffsets lo;
         lo.out = lo_ring[4 * st + 0];
-        lo.keep = lo_ring[4 * st + 1] != 0;
+        lo.keep = (lo_ring[4 * st + 1] & 1) != 0;
+        lo.mirror = (lo_ring[4 * st + 1] & 2) != 0;
+        lo.out_tr = lo_ring[4 * st + 2];
         if (lo.keep) {                                  // warp-uniform
             const double* src = ring + (size_t)st * STAGE;
             double x[Q][NOPS];
@@ -819,13 +854,25 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
                         if (lane >= t) sum += vsh;
                     }
                 }
-                if (mu[k] >= 0) obuf[mu[k] - mu_lo] = sum;
+                if (mu[k] >= 0) {
+                    obuf[mu[k] - mu_lo] = sum;
+                    // entry (i,j) of this line is entry (j,i) of the transposed line
+                    constexpr int dummy = 0; (void)dummy;
+                    const int kt = (k == 0) ? 0 : (k <= P ? k + P : k - P);
+                    if (lo.mirror) obuf_t[mu[kt] - mu_lo] = sum;
+                }
             }
             __syncwarp();
             double* dst = prm.out[0] + lo.out + (long long)(mu_lo - prm.mu_base);
 #pragma unroll
             for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
                 if ((mine >> j) & 1u) dst[lane + 32 * j] = obuf[lane + 32 * j];
+            if (lo.mirror) {
+                double* dst_t = prm.out[0] + lo.out_tr + (long long)(mu_lo - prm.mu_base);
+#pragma unroll
+                for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
+                    if ((mine >> j) & 1u) dst_t[lane + 32 * j] = obuf_t[lane + 32 * j];
+            }
         }
         st = (st + 1) % NST;
     }
