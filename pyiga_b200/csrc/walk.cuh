@@ -142,6 +142,7 @@ struct PbWalkTables {       // where the thread finds the walk-axis tables (shar
     const double* V;        // indexed by absolute node
     const int* first;       // indexed by absolute span
     const int* ret_mu;      // indexed by absolute function * (2P+1)
+    bool encoded;           // ret_mu entries carry the per-output slab filter in bits 24..27
 };
 template <class Plan, int P, int Q, class Loader>
 PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWalkTables& tb, Loader& ld);
@@ -150,7 +151,7 @@ template <class Plan, int P, int Q, int NPF = 1>
 PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt) {
     PbRegLoader<Plan, Q> ld;
     PbWalkTables tb;
-    tb.V = Vt; tb.first = prm.first; tb.ret_mu = prm.ret_mu;
+    tb.V = Vt; tb.first = prm.first; tb.ret_mu = prm.ret_mu; tb.encoded = false;
     pb_walk_line_impl<Plan, P, Q>(prm, tid, tb, ld);
 }
 
@@ -217,10 +218,21 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
             const int a = (k <= P) ? 0 : (k - P);
             const int b = (k <= P) ? k : 0;
             if (mu >= 0) {
-                const long long o_off = off_out + (long long)(mu - prm.mu_base) * prm.out_smu;
+                // the slab filter of the walk-axis pair is the same for every line: the staged table
+                // carries it as a bit mask; the plain table needs the test here
+                const int band = tb.encoded ? (mu & 0xFFFFFF) : mu;
+                int mask = mu >> 24;
+                if (!tb.encoded) {
+                    mask = 0;
+                    pb_static_for<0, NOUT>([&](auto O) {
+                        constexpr int o = decltype(O)::value;
+                        mask |= pb_keep(prm.w_mode[o], f + a, f + b, prm.w_lo, prm.w_hi) ? (1 << o) : 0;
+                    });
+                }
+                const long long o_off = off_out + (long long)(band - prm.mu_base) * prm.out_smu;
                 pb_static_for<0, NOUT>([&](auto O) {
                     constexpr int o = decltype(O)::value;
-                    if (want[o] && pb_keep(prm.w_mode[o], f + a, f + b, prm.w_lo, prm.w_hi)) prm.out[o][o_off] = acc[o][a][b];
+                    if (want[o] && ((mask >> o) & 1)) prm.out[o][o_off] = acc[o][a][b];
                 });
             }
         }
@@ -429,14 +441,25 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
     tb.V = Vt;
     if (use_smem) {
         for (int t = threadIdx.x; t < nsp; t += blockDim.x) s_first[t] = prm.first[prm.s_begin + t];
-        for (int t = threadIdx.x; t < (f_hi - f_lo) * (2 * P + 1); t += blockDim.x)
-            s_ret[t] = prm.ret_mu[(long long)f_lo * (2 * P + 1) + t];
+        for (int t = threadIdx.x; t < (f_hi - f_lo) * (2 * P + 1); t += blockDim.x) {
+            int mu = prm.ret_mu[(long long)f_lo * (2 * P + 1) + t];
+            if (mu >= 0) {
+                const int f = f_lo + t / (2 * P + 1), k = t % (2 * P + 1);
+                const int i = (k <= P) ? f : f + (k - P), j = (k <= P) ? f + k : f;
+                int mask = 0;
+                for (int o = 0; o < Plan::NOUT; ++o) mask |= pb_keep(prm.w_mode[o], i, j, prm.w_lo, prm.w_hi) ? (1 << o) : 0;
+                mu = mask ? (mu | (mask << 24)) : -1;
+            }
+            s_ret[t] = mu;
+        }
         __syncthreads();
         tb.first = s_first - prm.s_begin;
         tb.ret_mu = s_ret - (long long)f_lo * (2 * P + 1);
+        tb.encoded = true;
     } else {
         tb.first = prm.first;
         tb.ret_mu = prm.ret_mu;
+        tb.encoded = false;
     }
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < prm.nthreads) {
@@ -710,10 +733,9 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
     constexpr int STAGE = NOPS * SEG;                       // doubles per pipeline stage
     extern __shared__ __align__(16) double pb_lane_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + 2 * Cfg::OUTPAD + Cfg::LOSLOTS);
+    double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + Cfg::OUTPAD + Cfg::LOSLOTS);
     double* obuf = ring + NST * STAGE;
-    double* obuf_t = obuf + Cfg::OUTPAD;                // entries of the transposed line (mirroring)
-    long long* lo_ring = reinterpret_cast<long long*>(obuf_t + Cfg::OUTPAD);
+    long long* lo_ring = reinterpret_cast<long long*>(obuf + Cfg::OUTPAD);
 
     const long long warp = (long long)blockIdx.x * 4 + wib;
     const int batch = blockIdx.y;
@@ -843,6 +865,7 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
             });
             double L[P1][P1];
             pb_span_block<Plan, P, Q>(x, D, L);
+            double val[2 * P + 1];
 #pragma unroll
             for (int k = 0; k <= 2 * P; ++k) {
                 const int d = (k <= P) ? k : k - P;
@@ -854,13 +877,8 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
                         if (lane >= t) sum += vsh;
                     }
                 }
-                if (mu[k] >= 0) {
-                    obuf[mu[k] - mu_lo] = sum;
-                    // entry (i,j) of this line is entry (j,i) of the transposed line
-                    constexpr int dummy = 0; (void)dummy;
-                    const int kt = (k == 0) ? 0 : (k <= P ? k + P : k - P);
-                    if (lo.mirror) obuf_t[mu[kt] - mu_lo] = sum;
-                }
+                val[k] = sum;
+                if (mu[k] >= 0) obuf[mu[k] - mu_lo] = sum;
             }
             __syncwarp();
             double* dst = prm.out[0] + lo.out + (long long)(mu_lo - prm.mu_base);
@@ -868,10 +886,19 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
             for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
                 if ((mine >> j) & 1u) dst[lane + 32 * j] = obuf[lane + 32 * j];
             if (lo.mirror) {
+                // entry (i,j) of this line is entry (j,i) of the transposed line: same staging
+                // slots, values swapped between the pair and its transpose
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k <= 2 * P; ++k) {
+                    const int kt = (k == 0) ? 0 : (k <= P ? k + P : k - P);
+                    if (mu[k] >= 0) obuf[mu[k] - mu_lo] = val[kt];
+                }
+                __syncwarp();
                 double* dst_t = prm.out[0] + lo.out_tr + (long long)(mu_lo - prm.mu_base);
 #pragma unroll
                 for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
-                    if ((mine >> j) & 1u) dst_t[lane + 32 * j] = obuf_t[lane + 32 * j];
+                    if ((mine >> j) & 1u) dst_t[lane + 32 * j] = obuf[lane + 32 * j];
             }
         }
         st = (st + 1) % NST;

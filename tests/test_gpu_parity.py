@@ -156,4 +156,6 @@ def test_pipelined_csr_host(cuda):
         A = sa.assemble_csr()
         ip, ix, vv = sa.assemble_csr_host(nchunks=4)
         assert np.array_equal(ip.numpy(), A.indptr) and np.array_equal(ix.numpy(), A.indices)
-        assert np.array_equal(vv.numpy(), A.data)
+        # values agree to rounding: which half of a symmetric pair is computed and which is mirrored
+        # depends on the row chunking
+        assert np.abs(vv.numpy() - A.data).max() <= 1e-13 * np.abs(A.data).max()
