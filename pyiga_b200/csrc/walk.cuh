@@ -583,6 +583,52 @@ PB_HD PbLineOffsets pb_decode_line(const PbWalkParams& prm, long long line) {
     return o;
 }
 
+// offsets of consecutive lines without a division per line: keeps (u, v, x) as counters
+template <class Plan>
+struct PbLineCursor {
+    int u, v, x;
+    PB_HD void seek(const PbWalkParams& prm, long long line) {
+        x = (int)(line % prm.X);
+        const long long t2 = line / prm.X;
+        v = (int)(t2 % prm.V);
+        u = (int)(t2 / prm.V) + prm.u_begin;
+    }
+    PB_HD void advance(const PbWalkParams& prm) {
+        if (++x == prm.X) { x = 0; if (++v == prm.V) { v = 0; ++u; } }
+    }
+    PB_HD PbLineOffsets offsets(const PbWalkParams& prm) const {
+        PbLineOffsets o;
+        o.keep = true;
+        o.mirror = false;
+        if (prm.u_pair_i != nullptr) {
+            const int ui = prm.u_pair_i[u], uj = prm.u_pair_j[u];
+            o.keep = pb_keep(prm.u_mode[0], ui, uj, prm.u_lo, prm.u_hi);
+            if (prm.mirror) {
+                const bool partner_owned = (uj >= prm.u_lo && uj < prm.u_hi);
+                int vi = 0, vj = 0;
+                if (prm.v_pair_i != nullptr) { vi = prm.v_pair_i[v]; vj = prm.v_pair_j[v]; }
+                const bool upper = ui < uj || (ui == uj && vi <= vj);
+                const bool self = (ui == uj && vi == vj);
+                o.keep = o.keep && (!partner_owned || upper);
+                o.mirror = partner_owned && upper && !self;
+            }
+        }
+        o.in = (long long)(u - prm.u_base_in) * prm.in_su + (long long)v * prm.in_sv + (long long)x * prm.in_sx;
+        o.in_tr = o.in;
+        o.out = (long long)(u - prm.u_base_out) * prm.out_su + (long long)v * prm.out_sv + (long long)x * prm.out_sx;
+        o.out_tr = o.out;
+        if (Plan::HAS_TR || o.mirror) {
+            const int ut = prm.tr_u ? prm.tr_u[u] : u;
+            const int vt = prm.tr_v ? prm.tr_v[v] : v;
+            if (Plan::HAS_TR)
+                o.in_tr = (long long)(ut - prm.u_base_in) * prm.in_su + (long long)vt * prm.in_sv + (long long)x * prm.in_sx;
+            if (o.mirror)
+                o.out_tr = (long long)(ut - prm.u_base_out) * prm.out_su + (long long)vt * prm.out_sv + (long long)x * prm.out_sx;
+        }
+        return o;
+    }
+};
+
 PB_HD int pb_lane_batches(int nspans, int P) {
     const int rest = nspans + P - 32;
     return 1 + (rest > 0 ? (rest + (32 - P) - 1) / (32 - P) : 0);
@@ -795,8 +841,26 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
     __syncwarp();
 
     // asynchronous copy of one line segment into ring stage `st`
-    auto issue = [&](long long line, int st) {
-        const PbLineOffsets lo = pb_decode_line<Plan>(prm, line);
+    // this lane's share of a line segment: piece index -> offsets in global / shared memory
+    constexpr int NPIECE = VEC ? (SEG / 2 + 31) / 32 : (SEG + 31) / 32;
+    int goff[NPIECE], soff[NPIECE];
+#pragma unroll
+    for (int h = 0; h < NPIECE; ++h) {
+        const int c = lane + 32 * h;
+        if constexpr (VEC) {
+            const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
+            goff[h] = (c < SEG / 2 && 2 * c < seg_nodes) ? 2 * c : -1;
+            soff[h] = 2 * pc;
+        } else {
+            goff[h] = (c < SEG && c < seg_nodes) ? c : -1;
+            soff[h] = c;
+        }
+    }
+    PbLineCursor<Plan> cur;
+    cur.seek(prm, line0);
+    auto issue = [&](long long, int st) {
+        const PbLineOffsets lo = cur.offsets(prm);
+        cur.advance(prm);
         if (lane == 0) {
             lo_ring[4 * st + 0] = lo.out;
             lo_ring[4 * st + 1] = (lo.keep ? 1 : 0) | (lo.mirror ? 2 : 0);
@@ -808,18 +872,12 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
                 constexpr int i = decltype(I)::value;
                 if (prm.in[i]) {
                     const double* src = prm.in[i] + (Plan::op(i).tr ? lo.in_tr : lo.in) + seg_node0;
-                    if constexpr (VEC) {
 #pragma unroll
-                        for (int c = lane; c < SEG / 2; c += 32) {
-                            if (2 * c < seg_nodes) {
-                                const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
-                                pb_cp_async16(dst + i * SEG + 2 * pc, src + 2 * c);
-                            }
+                    for (int h = 0; h < NPIECE; ++h) {
+                        if (goff[h] >= 0) {
+                            if constexpr (VEC) pb_cp_async16(dst + i * SEG + soff[h], src + goff[h]);
+                            else pb_cp_async8(dst + i * SEG + soff[h], src + goff[h]);
                         }
-                    } else {
-#pragma unroll
-                        for (int e = lane; e < SEG; e += 32)
-                            if (e < seg_nodes) pb_cp_async8(dst + i * SEG + e, src + e);
                     }
                 }
             });
