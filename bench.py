@@ -181,31 +181,44 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def stage_bytes(name, dev, rows_mu, ext_mu):
-    """Algorithmic HBM bytes of one pipeline kernel (each input term read once, each output written
-    once)."""
-    G = dev.nnodes
-    M = dev.nband
+def pipeline_bytes(dev, rows, form, p, mirror=True):
+    """Algorithmic HBM bytes of every pipeline kernel for the row slab `rows` (each input element a
+    kernel needs is read once, each output element written once).  With mirroring the
+    final stage computes only the upper half of each symmetric pair of lines, and the earlier
+    stages only the terms those lines need (slab filter modes 1/2/3 of csrc/walk.cuh)."""
+    import numpy as np
+    ra, rb = rows
+    G, M = dev.nnodes, dev.nband
+    S = dev.structure
+    b0 = S.bidx[0].astype(np.int64)
+    b1 = S.bidx[1].astype(np.int64)
+    i0, j0 = b0[:, 0], b0[:, 1]
+    ini, inj = (i0 >= ra) & (i0 < rb), (j0 >= ra) & (j0 < rb)
+    c1 = int(ini.sum())
+    c2 = int((ini | inj).sum())
+    c3 = int((ini & ((i0 <= j0) | ~inj)).sum()) if mirror else c1
+    upper1 = int((b1[:, 0] <= b1[:, 1]).sum())
+    if mirror:
+        lines = int((ini & inj & (i0 < j0)).sum()) * M[1] + int((ini & (i0 == j0)).sum()) * upper1 \
+            + int((ini & ~inj).sum()) * M[1]
+    else:
+        lines = c1 * M[1]
+    msi = np.asarray(dev.kvs[0][0].mesh_support_idx_all())
+    planes = int(msi[rb - 1, 1] - msi[ra, 0]) * (p + 1)
+    plane = G[1] * G[2]
     d = 8.0
-    if name.startswith('s1_one') or name.startswith('s1_copy') and name != 's1_copy':
-        return d * (G[0] * G[1] * G[2] + ext_mu * G[1] * G[2])
-    if name == 's2_pairt':
-        return d * (2 * ext_mu * G[1] * G[2] + ext_mu * M[1] * G[2])
-    if name in ('s1a', 's1b'):
-        return d * (3 * G[0] * G[1] * G[2] + 3 * ext_mu * G[1] * G[2])
-    if name == 's1_copy':
-        return d * (G[0] * G[1] * G[2] + ext_mu * G[1] * G[2])
-    if name == 's2a_final4':
-        return d * (4 * ext_mu * G[1] * G[2] + ext_mu * M[1] * G[2])
-    if name == 's2b':
-        return d * (3 * ext_mu * G[1] * G[2] + 2 * ext_mu * M[1] * G[2])
-    if name == 's2_copy':
-        return d * (ext_mu * G[1] * G[2] + ext_mu * M[1] * G[2])
-    if name == 's3_final4':
-        return d * (4 * rows_mu * M[1] * G[2] + rows_mu * M[1] * M[2])
-    if name == 's3_copy':
-        return d * (rows_mu * M[1] * G[2] + rows_mu * M[1] * M[2])
-    return None
+    out = {'k2_fields': d * dev.nfields * planes * plane}
+    if form == 'stiffness':
+        out['s1a'] = d * (3 * planes * plane + (c3 + 2 * c2) * plane)
+        out['s1b'] = d * (3 * planes * plane + (2 * c3 + c2) * plane)
+        out['s2a_final4'] = d * (4 * c3 * plane + c3 * M[1] * G[2])
+        out['s2b'] = d * ((2 * c2 + c3) * plane + (c2 + c3) * M[1] * G[2])
+        out['s3_final4'] = d * (4 * lines * G[2] + c1 * M[1] * M[2])
+    else:
+        out['s1_copy'] = d * (planes * plane + c3 * plane)
+        out['s2_copy'] = d * (c3 * plane + c3 * M[1] * G[2])
+        out['s3_copy'] = d * (lines * G[2] + c1 * M[1] * M[2])
+    return out
 
 
 def run_ours(a):
@@ -346,22 +359,24 @@ def run_ours(a):
         roof = None
         if stages:
             dom = max(stages, key=stages.get)
-            ext = dev.row_start0()
-            rows_mu = int(rs[sa.rows[1]] - rs[sa.rows[0]])
-            P = a.p
-            ea, eb = max(0, sa.rows[0] - P), min(dev.ndofs_test[0], sa.rows[1] + P)
-            ext_mu = int(ext[eb] - ext[ea]) if a.form == 'stiffness' else rows_mu
-            if dom == 'k2_fields':
-                planes = (kvs[0].mesh_support_idx_all()[sa.rows[1] - 1, 1] - kvs[0].mesh_support_idx_all()[sa.rows[0], 0]) * (a.p + 1)
-                byts = 8.0 * dev.nfields * planes * dev.nnodes[1] * dev.nnodes[2]
-            else:
-                byts = stage_bytes(dom, dev, rows_mu, ext_mu)
+            pbytes = pipeline_bytes(dev, sa.rows, a.form, a.p)
+            byts = pbytes.get(dom)
+            kernel_gbs = {k: round(pbytes[k] / (stages[k] * 1e-3) / 1e9, 1) for k in stages if k in pbytes}
+            traffic = None
+            try:    # DRAM bytes per launch from the committed ncu --set full capture of the same workload
+                t = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+                if t.get('workload') == workload_name(a) and world == 1:
+                    traffic = t['dram_bytes_per_launch'].get(dom)
+            except Exception:
+                pass
             if byts:
                 ach = byts / (stages[dom] * 1e-3) / 1e9
                 roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                        'frac': ach / hbm_peak, 'traffic': None, 'bytes_per_launch': byts,
+                        'frac': ach / hbm_peak, 'traffic': traffic, 'bytes_per_launch': byts,
                         'ms_per_launch': stages[dom], 'peak_source': hbm_src,
-                        'share_of_step': stages[dom] / sum(stages.values())}
+                        'share_of_step': stages[dom] / sum(stages.values()),
+                        'all_kernels_GBps': kernel_gbs, 'step_bytes': sum(pbytes.values()),
+                        'step_GBps': sum(pbytes.values()) / (ms * 1e-3) / 1e9}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
