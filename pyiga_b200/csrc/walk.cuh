@@ -583,52 +583,6 @@ PB_HD PbLineOffsets pb_decode_line(const PbWalkParams& prm, long long line) {
     return o;
 }
 
-// offsets of consecutive lines without a division per line: keeps (u, v, x) as counters
-template <class Plan>
-struct PbLineCursor {
-    int u, v, x;
-    PB_HD void seek(const PbWalkParams& prm, long long line) {
-        x = (int)(line % prm.X);
-        const long long t2 = line / prm.X;
-        v = (int)(t2 % prm.V);
-        u = (int)(t2 / prm.V) + prm.u_begin;
-    }
-    PB_HD void advance(const PbWalkParams& prm) {
-        if (++x == prm.X) { x = 0; if (++v == prm.V) { v = 0; ++u; } }
-    }
-    PB_HD PbLineOffsets offsets(const PbWalkParams& prm) const {
-        PbLineOffsets o;
-        o.keep = true;
-        o.mirror = false;
-        if (prm.u_pair_i != nullptr) {
-            const int ui = prm.u_pair_i[u], uj = prm.u_pair_j[u];
-            o.keep = pb_keep(prm.u_mode[0], ui, uj, prm.u_lo, prm.u_hi);
-            if (prm.mirror) {
-                const bool partner_owned = (uj >= prm.u_lo && uj < prm.u_hi);
-                int vi = 0, vj = 0;
-                if (prm.v_pair_i != nullptr) { vi = prm.v_pair_i[v]; vj = prm.v_pair_j[v]; }
-                const bool upper = ui < uj || (ui == uj && vi <= vj);
-                const bool self = (ui == uj && vi == vj);
-                o.keep = o.keep && (!partner_owned || upper);
-                o.mirror = partner_owned && upper && !self;
-            }
-        }
-        o.in = (long long)(u - prm.u_base_in) * prm.in_su + (long long)v * prm.in_sv + (long long)x * prm.in_sx;
-        o.in_tr = o.in;
-        o.out = (long long)(u - prm.u_base_out) * prm.out_su + (long long)v * prm.out_sv + (long long)x * prm.out_sx;
-        o.out_tr = o.out;
-        if (Plan::HAS_TR || o.mirror) {
-            const int ut = prm.tr_u ? prm.tr_u[u] : u;
-            const int vt = prm.tr_v ? prm.tr_v[v] : v;
-            if (Plan::HAS_TR)
-                o.in_tr = (long long)(ut - prm.u_base_in) * prm.in_su + (long long)vt * prm.in_sv + (long long)x * prm.in_sx;
-            if (o.mirror)
-                o.out_tr = (long long)(ut - prm.u_base_out) * prm.out_su + (long long)vt * prm.out_sv + (long long)x * prm.out_sx;
-        }
-        return o;
-    }
-};
-
 PB_HD int pb_lane_batches(int nspans, int P) {
     const int rest = nspans + P - 32;
     return 1 + (rest > 0 ? (rest + (32 - P) - 1) / (32 - P) : 0);
@@ -767,7 +721,8 @@ template <int P, int Q> struct PbLaneCfg {
     static constexpr int SEG = 32 * Q;                      // doubles per term and line segment
     static constexpr int OUTSLOTS = (32 + P) * (2 * P + 1); // staging slots for finished entries
     static constexpr int OUTPAD = (OUTSLOTS + 31) / 32 * 32;
-    static constexpr int LOSLOTS = 16;      // per warp: decoded offsets of the lines in flight (<= 4 stages x 4 words)
+    static constexpr int DQ = 64;           // per warp: decoded lines (<= lines per warp)
+    static constexpr int LOSLOTS = 4 * DQ;  // in, in_tr, out, out_tr offsets of the decoded lines
 };
 
 template <class Plan, int P, int Q, int NST>
@@ -781,7 +736,7 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* ring = pb_lane_smem + (size_t)wib * (NST * STAGE + Cfg::OUTPAD + Cfg::LOSLOTS);
     double* obuf = ring + NST * STAGE;
-    long long* lo_ring = reinterpret_cast<long long*>(obuf + Cfg::OUTPAD);
+    long long* dq = reinterpret_cast<long long*>(obuf + Cfg::OUTPAD);
 
     const long long warp = (long long)blockIdx.x * 4 + wib;
     const int batch = blockIdx.y;
@@ -856,108 +811,115 @@ __global__ void __launch_bounds__(128, (P >= 4 ? 2 : 3)) pb_lane_span_kernel_v2(
             soff[h] = c;
         }
     }
-    PbLineCursor<Plan> cur;
-    cur.seek(prm, line0);
-    auto issue = [&](long long, int st) {
-        const PbLineOffsets lo = cur.offsets(prm);
-        cur.advance(prm);
-        if (lane == 0) {
-            lo_ring[4 * st + 0] = lo.out;
-            lo_ring[4 * st + 1] = (lo.keep ? 1 : 0) | (lo.mirror ? 2 : 0);
-            lo_ring[4 * st + 2] = lo.out_tr;
-        }
-        double* dst = ring + (size_t)st * STAGE;
+    // Lines of this warp: decoded 32 at a time, one line per lane, so that the table look-ups of the
+    // decode (pair tables, transposed indices) cost one memory latency per 32 lines instead of a
+    // dependent chain per line; lines that are filtered out (slab filter, mirrored half of a
+    // symmetric form) are dropped here and never enter the copy pipeline.
+    int nkept = 0;
+    for (long long base = line0; base < line1; base += 32) {
+        const long long ln = base + lane;
+        PbLineOffsets lo;
+        lo.keep = false;
+        if (ln < line1) lo = pb_decode_line<Plan>(prm, ln);
+        const unsigned bal = __ballot_sync(0xffffffffu, lo.keep);
         if (lo.keep) {
-            pb_static_for<0, NOPS>([&](auto I) {
-                constexpr int i = decltype(I)::value;
-                if (prm.in[i]) {
-                    const double* src = prm.in[i] + (Plan::op(i).tr ? lo.in_tr : lo.in) + seg_node0;
+            const int slot = nkept + __popc(bal & ((1u << lane) - 1u));
+            dq[slot] = lo.in;
+            dq[Cfg::DQ + slot] = lo.in_tr;
+            dq[2 * Cfg::DQ + slot] = lo.out;
+            dq[3 * Cfg::DQ + slot] = lo.mirror ? lo.out_tr : -1;
+        }
+        nkept += __popc(bal);
+    }
+    __syncwarp();
+    if (nkept == 0) return;
+
+    auto issue = [&](int k, int st) {
+        const long long in = dq[k], in_tr = dq[Cfg::DQ + k];
+        double* dst = ring + (size_t)st * STAGE;
+        pb_static_for<0, NOPS>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if (prm.in[i]) {
+                const double* src = prm.in[i] + (Plan::op(i).tr ? in_tr : in) + seg_node0;
 #pragma unroll
-                    for (int h = 0; h < NPIECE; ++h) {
-                        if (goff[h] >= 0) {
-                            if constexpr (VEC) pb_cp_async16(dst + i * SEG + soff[h], src + goff[h]);
-                            else pb_cp_async8(dst + i * SEG + soff[h], src + goff[h]);
-                        }
+                for (int h = 0; h < NPIECE; ++h) {
+                    if (goff[h] >= 0) {
+                        if constexpr (VEC) pb_cp_async16(dst + i * SEG + soff[h], src + goff[h]);
+                        else pb_cp_async8(dst + i * SEG + soff[h], src + goff[h]);
                     }
                 }
-            });
-        }
+            }
+        });
         pb_cp_async_commit();
     };
 
 #pragma unroll
     for (int j = 0; j < NST - 1; ++j) {
-        if (line0 + j < line1) issue(line0 + j, j);
+        if (j < nkept) issue(j, j);
         else pb_cp_async_commit();
     }
     int st = 0;
-    for (long long line = line0; line < line1; ++line) {
+    for (int k = 0; k < nkept; ++k) {
         __syncwarp();                                   // everyone is done with the stage refilled below
-        if (line + NST - 1 < line1) issue(line + NST - 1, (st + NST - 1) % NST);
+        if (k + NST - 1 < nkept) issue(k + NST - 1, (st + NST - 1) % NST);
         else pb_cp_async_commit();
         pb_cp_async_wait<NST - 1>();
         __syncwarp();
-        PbLineOffsets lo;
-        lo.out = lo_ring[4 * st + 0];
-        lo.keep = (lo_ring[4 * st + 1] & 1) != 0;
-        lo.mirror = (lo_ring[4 * st + 1] & 2) != 0;
-        lo.out_tr = lo_ring[4 * st + 2];
-        if (lo.keep) {                                  // warp-uniform
-            const double* src = ring + (size_t)st * STAGE;
-            double x[Q][NOPS];
-            pb_static_for<0, NOPS>([&](auto I) {
-                constexpr int i = decltype(I)::value;
-                if constexpr (VEC) {
+        const long long out = dq[2 * Cfg::DQ + k], out_tr = dq[3 * Cfg::DQ + k];
+        const double* src = ring + (size_t)st * STAGE;
+        double x[Q][NOPS];
+        pb_static_for<0, NOPS>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if constexpr (VEC) {
 #pragma unroll
-                    for (int h = 0; h < Q / 2; ++h) {
-                        const int c = lane * (Q / 2) + h;
-                        const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
-                        const double2 v = *reinterpret_cast<const double2*>(src + i * SEG + 2 * pc);
-                        x[2 * h][i] = v.x;
-                        x[2 * h + 1][i] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int gq = 0; gq < Q; ++gq) x[gq][i] = src[i * SEG + lane * Q + gq];
+                for (int h = 0; h < Q / 2; ++h) {
+                    const int c = lane * (Q / 2) + h;
+                    const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
+                    const double2 v = *reinterpret_cast<const double2*>(src + i * SEG + 2 * pc);
+                    x[2 * h][i] = v.x;
+                    x[2 * h + 1][i] = v.y;
                 }
-            });
-            double L[P1][P1];
-            pb_span_block<Plan, P, Q>(x, D, L);
-            double val[2 * P + 1];
+            } else {
 #pragma unroll
-            for (int k = 0; k <= 2 * P; ++k) {
-                const int d = (k <= P) ? k : k - P;
-                double sum = (k <= P) ? L[0][d] : L[d][0];
+                for (int gq = 0; gq < Q; ++gq) x[gq][i] = src[i * SEG + lane * Q + gq];
+            }
+        });
+        double L[P1][P1];
+        pb_span_block<Plan, P, Q>(x, D, L);
+        double val[2 * P + 1];
 #pragma unroll
-                for (int t = 1; t <= P; ++t) {
-                    if (t <= P - d) {
-                        const double vsh = __shfl_up_sync(0xffffffffu, (k <= P) ? L[t][t + d] : L[t + d][t], t);
-                        if (lane >= t) sum += vsh;
-                    }
+        for (int kk = 0; kk <= 2 * P; ++kk) {
+            const int d = (kk <= P) ? kk : kk - P;
+            double sum = (kk <= P) ? L[0][d] : L[d][0];
+#pragma unroll
+            for (int t = 1; t <= P; ++t) {
+                if (t <= P - d) {
+                    const double vsh = __shfl_up_sync(0xffffffffu, (kk <= P) ? L[t][t + d] : L[t + d][t], t);
+                    if (lane >= t) sum += vsh;
                 }
-                val[k] = sum;
-                if (mu[k] >= 0) obuf[mu[k] - mu_lo] = sum;
+            }
+            val[kk] = sum;
+            if (mu[kk] >= 0) obuf[mu[kk] - mu_lo] = sum;
+        }
+        __syncwarp();
+        double* dst = prm.out[0] + out + (long long)(mu_lo - prm.mu_base);
+#pragma unroll
+        for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
+            if ((mine >> j) & 1u) dst[lane + 32 * j] = obuf[lane + 32 * j];
+        if (out_tr >= 0) {                              // warp-uniform
+            // entry (i,j) of this line is entry (j,i) of the transposed line: same staging
+            // slots, values swapped between the pair and its transpose
+            __syncwarp();
+#pragma unroll
+            for (int kk = 0; kk <= 2 * P; ++kk) {
+                const int kt = (kk == 0) ? 0 : (kk <= P ? kk + P : kk - P);
+                if (mu[kk] >= 0) obuf[mu[kk] - mu_lo] = val[kt];
             }
             __syncwarp();
-            double* dst = prm.out[0] + lo.out + (long long)(mu_lo - prm.mu_base);
+            double* dst_t = prm.out[0] + out_tr + (long long)(mu_lo - prm.mu_base);
 #pragma unroll
             for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
-                if ((mine >> j) & 1u) dst[lane + 32 * j] = obuf[lane + 32 * j];
-            if (lo.mirror) {
-                // entry (i,j) of this line is entry (j,i) of the transposed line: same staging
-                // slots, values swapped between the pair and its transpose
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k <= 2 * P; ++k) {
-                    const int kt = (k == 0) ? 0 : (k <= P ? k + P : k - P);
-                    if (mu[k] >= 0) obuf[mu[k] - mu_lo] = val[kt];
-                }
-                __syncwarp();
-                double* dst_t = prm.out[0] + lo.out_tr + (long long)(mu_lo - prm.mu_base);
-#pragma unroll
-                for (int j = 0; j < Cfg::OUTPAD / 32; ++j)
-                    if ((mine >> j) & 1u) dst_t[lane + 32 * j] = obuf[lane + 32 * j];
-            }
+                if ((mine >> j) & 1u) dst_t[lane + 32 * j] = obuf[lane + 32 * j];
         }
         st = (st + 1) % NST;
     }

@@ -57,6 +57,7 @@ int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* strea
         return (int)cudaGetLastError();
     }
     constexpr int NST = 4;
+    if (lines_per_warp > PbLaneCfg<PB_P, PB_Q>::DQ) return (int)cudaErrorInvalidValue;
     using Cfg = PbLaneCfg<PB_P, PB_Q>;
     const size_t smem = 4 * (size_t)(NST * Plan::NOPS * Cfg::SEG + Cfg::OUTPAD + Cfg::LOSLOTS) * sizeof(double);
     auto kern = pb_lane_span_kernel_v2<Plan, PB_P, PB_Q, NST>;
