@@ -362,6 +362,7 @@ struct pb200_assembler {
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
     bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
+    int lane_lines = 64;                                // lines per warp of the lane-span kernel (<= PbLaneCfg::DQ)
     bool mirror_opt = true;                             // symmetric forms: compute the upper half of the final stage, mirror the rest
     bool fused_plans = true;                            // multi-output stage kernels (S1A/S1B/S2B); false: one launch per output
     // optional per-kernel timing of the last assemble call (CUDA events on the launch stream)
@@ -392,6 +393,7 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!a || !name) return fail(PB200_EINVAL, "null argument");
     if (!strcmp(name, "force_walk")) { a->force_walk = value != 0; return 0; }
     if (!strcmp(name, "lane_v1")) { a->lane_v1 = value != 0; return 0; }
+    if (!strcmp(name, "lane_lines")) { if (value < 1 || value > 64) return fail(PB200_EINVAL, "lane_lines must be in 1..64"); a->lane_lines = value; return 0; }
     if (!strcmp(name, "fused_plans")) { a->fused_plans = value != 0; return 0; }
     if (!strcmp(name, "mirror")) { a->mirror_opt = value != 0; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
@@ -1078,7 +1080,7 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     if (prm.in_sc == 1 && prm.out_smu == 1 && nofilter && a->lane_ok[axis] && !a->force_walk) {
         PbWalkLaunch lane = pb_find_walk(PB_PLAN_LANE_BASE + plan, P, Q);
         if (lane) {
-            int e = lane(&prm, a->lane_v1 ? -16 : 64, 0, st);
+            int e = lane(&prm, a->lane_v1 ? -16 : a->lane_lines, 0, st);
             if (e) return fail(PB200_ECUDA, "lane-span kernel launch failed (plan %d, p=%d, q=%d): %s", plan, P, Q, pbErrorString((pbError)e));
             return 0;
         }
