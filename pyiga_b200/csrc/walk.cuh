@@ -141,21 +141,21 @@ struct PbRegLoader {
 struct PbWalkTables {       // where the thread finds the walk-axis tables (shared or global memory)
     const double* V;        // indexed by absolute node
     const int* first;       // indexed by absolute span
-    const int* ret_mu;      // indexed by absolute function * (2P+1)
-    bool encoded;           // ret_mu entries carry the per-output slab filter in bits 24..27
+    const int* ret_mu;      // indexed by absolute function * (2P+1); the staged copy (template flag ENC
+                            // of the walk) carries the per-output slab filter in bits 24..27
 };
-template <class Plan, int P, int Q, class Loader>
+template <class Plan, int P, int Q, bool ENC, class Loader>
 PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWalkTables& tb, Loader& ld);
 
 template <class Plan, int P, int Q, int NPF = 1>
 PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt) {
     PbRegLoader<Plan, Q> ld;
     PbWalkTables tb;
-    tb.V = Vt; tb.first = prm.first; tb.ret_mu = prm.ret_mu; tb.encoded = false;
-    pb_walk_line_impl<Plan, P, Q>(prm, tid, tb, ld);
+    tb.V = Vt; tb.first = prm.first; tb.ret_mu = prm.ret_mu;
+    pb_walk_line_impl<Plan, P, Q, false>(prm, tid, tb, ld);
 }
 
-template <class Plan, int P, int Q, class Loader>
+template <class Plan, int P, int Q, bool ENC, class Loader>
 PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWalkTables& tb, Loader& ld) {
     const double* __restrict__ Vt = tb.V;
     constexpr int P1 = P + 1;
@@ -208,6 +208,17 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
             for (int b = 0; b < P1; ++b) acc[o][a][b] = 0.0;
     });
 
+    // per-thread output bases and the set of outputs this line feeds; the band stride fits 32 bits
+    // (checked on the host), so the offset of a band entry is one widening multiply-add
+    double* outp[NOUT];
+    int wantbits = 0;
+    pb_static_for<0, NOUT>([&](auto O) {
+        constexpr int o = decltype(O)::value;
+        outp[o] = prm.out[o] + off_out;
+        wantbits |= want[o] ? (1 << o) : 0;
+    });
+    const int smu = (int)prm.out_smu, mu_base = prm.mu_base;
+
     // retire the pairs that involve function f (first row / first column of the window), then
     // slide the window down by one function
     auto retire_shift = [&](int f) {
@@ -220,19 +231,21 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
             if (mu >= 0) {
                 // the slab filter of the walk-axis pair is the same for every line: the staged table
                 // carries it as a bit mask; the plain table needs the test here
-                const int band = tb.encoded ? (mu & 0xFFFFFF) : mu;
-                int mask = mu >> 24;
-                if (!tb.encoded) {
-                    mask = 0;
+                int band = mu, mask = 0;
+                if constexpr (ENC) {
+                    band = mu & 0xFFFFFF;
+                    mask = mu >> 24;
+                } else {
                     pb_static_for<0, NOUT>([&](auto O) {
                         constexpr int o = decltype(O)::value;
                         mask |= pb_keep(prm.w_mode[o], f + a, f + b, prm.w_lo, prm.w_hi) ? (1 << o) : 0;
                     });
                 }
-                const long long o_off = off_out + (long long)(band - prm.mu_base) * prm.out_smu;
+                mask &= wantbits;
+                const long long boff = (long long)(band - mu_base) * (long long)smu;
                 pb_static_for<0, NOUT>([&](auto O) {
                     constexpr int o = decltype(O)::value;
-                    if (want[o] && ((mask >> o) & 1)) prm.out[o][o_off] = acc[o][a][b];
+                    if (mask & (1 << o)) outp[o][boff] = acc[o][a][b];
                 });
             }
         }
@@ -354,39 +367,65 @@ PB_D void pb_mbar_wait(uint64_t* bar, uint32_t phase) {
         : "memory");
 }
 
-template <class Plan, int Q, int NST>
+template <int OFF> PB_D void pb_cp_async8_at(uint32_t smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0 + %2], [%1], 8;" ::"r"(smem), "l"(gmem), "n"(OFF) : "memory");
+}
+
+// spans are issued in order, so the global addresses are running pointers (no multiply per copy)
+// and the shared-memory destinations are a stage base plus compile-time offsets
+template <class Plan, int Q, int NST, int NTHR = 128>
 struct PbAsyncLoader {
     static constexpr int NOPS = Plan::NOPS;
+    static constexpr int STAGE = Q * NOPS * NTHR;       // doubles per stage of the block ring
     const double* src[NOPS];
     bool has[NOPS];
     long long sc;
     int s_end;
-    double* ring;       // this thread's column of the block ring: [NST][Q][NOPS][blockDim.x]
-    int nthr, st;
-    PB_D void issue(int s, int stage) {
-        if (s < s_end) {
-#pragma unroll
-            for (int gq = 0; gq < Q; ++gq)
-                pb_static_for<0, NOPS>([&](auto I) {
-                    constexpr int i = decltype(I)::value;
-                    if (has[i]) pb_cp_async8(ring + ((stage * Q + gq) * NOPS + i) * nthr, src[i] + (long long)(s * Q + gq) * sc);
-                });
+    double* ring;       // this thread's column of the block ring: [NST][Q][NOPS][NTHR]
+    int st, s_next;
+    uint32_t ring_u32;
+    long long scb;
+    const char* p[NOPS];
+    PB_D void issue(int stage) {
+        if (s_next < s_end) {
+            const uint32_t d = ring_u32 + (uint32_t)stage * (uint32_t)(STAGE * sizeof(double));
+            pb_static_for<0, NOPS>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                if (has[i]) {
+                    const char* a = p[i];
+                    pb_static_for<0, Q>([&](auto GQ) {
+                        constexpr int gq = decltype(GQ)::value;
+                        pb_cp_async8_at<(gq * NOPS + i) * NTHR * (int)sizeof(double)>(d, a);
+                        a += scb;
+                    });
+                    p[i] = a;
+                }
+            });
         }
+        ++s_next;
         pb_cp_async_commit();
     }
     PB_D void prime(int s_begin) {
         st = 0;
+        s_next = s_begin;
+        scb = sc * (long long)sizeof(double);
+        ring_u32 = pb_smem_u32(ring);
+        pb_static_for<0, NOPS>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            p[i] = reinterpret_cast<const char*>(src[i]) + (long long)s_begin * Q * scb;
+        });
 #pragma unroll
-        for (int k = 0; k < NST - 1; ++k) issue(s_begin + k, k);
+        for (int k = 0; k < NST - 1; ++k) issue(k);
     }
-    PB_D void next(int s, double (&xc)[Q][NOPS]) {
-        issue(s + NST - 1, (st + NST - 1) % NST);
+    PB_D void next(int, double (&xc)[Q][NOPS]) {
+        issue((st + NST - 1) % NST);
         pb_cp_async_wait<NST - 1>();
+        const double* r = ring + st * STAGE;
 #pragma unroll
         for (int gq = 0; gq < Q; ++gq)
             pb_static_for<0, NOPS>([&](auto I) {
                 constexpr int i = decltype(I)::value;
-                xc[gq][i] = has[i] ? ring[((st * Q + gq) * NOPS + i) * nthr] : 0.0;
+                xc[gq][i] = has[i] ? r[(gq * NOPS + i) * NTHR] : 0.0;
             });
         st = (st + 1) % NST;
     }
@@ -455,11 +494,9 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
         __syncthreads();
         tb.first = s_first - prm.s_begin;
         tb.ret_mu = s_ret - (long long)f_lo * (2 * P + 1);
-        tb.encoded = true;
     } else {
         tb.first = prm.first;
         tb.ret_mu = prm.ret_mu;
-        tb.encoded = false;
     }
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < prm.nthreads) {
@@ -467,11 +504,12 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
             // NPF doubles as the ring depth of the asynchronous loader
             PbAsyncLoader<Plan, Q, NPF> ld;
             ld.ring = reinterpret_cast<double*>(pb_smem_raw + vbytes + (use_smem ? ibytes : 0)) + threadIdx.x;
-            ld.nthr = blockDim.x;
-            pb_walk_line_impl<Plan, P, Q>(prm, tid, tb, ld);
+            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, tid, tb, ld);
+            else pb_walk_line_impl<Plan, P, Q, false>(prm, tid, tb, ld);
         } else {
             PbRegLoader<Plan, Q> ld;
-            pb_walk_line_impl<Plan, P, Q>(prm, tid, tb, ld);
+            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, tid, tb, ld);
+            else pb_walk_line_impl<Plan, P, Q, false>(prm, tid, tb, ld);
         }
     }
 }

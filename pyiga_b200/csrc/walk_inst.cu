@@ -26,6 +26,7 @@ int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* strea
     }
     const long long blocks = (prm->nthreads + 127) / 128;
     if (blocks <= 0) return 0;
+    if (prm->out_smu >= (1LL << 31)) return (int)cudaErrorInvalidValue;   // band stride is used as a 32-bit factor
     // the asynchronous loader's ring (plans with NPF >= 2) sits behind the table slice
     const size_t ring = Plan::NPF >= 2 ? (size_t)Plan::NPF * PB_Q * Plan::NOPS * 128 * sizeof(double) : 0;
     const size_t vpad = use_smem ? (smem_bytes + 127) & ~size_t(127) : 0;

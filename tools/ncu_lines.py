@@ -1,5 +1,5 @@
 """Aggregate the warp-stall samples of an .ncu-rep per CUDA source line (needs -lineinfo and
---import-source on):  python tools/ncu_lines.py report.ncu-rep [top]"""
+--import-source on):  python tools/ncu_lines.py report.ncu-rep [top] [kernel-name substring]"""
 import csv
 import subprocess
 import sys
@@ -8,6 +8,8 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    want = sys.argv[3] if len(sys.argv) > 3 else ''
+    func = ''
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'],
                          capture_output=True, text=True).stdout
     cur, hdr, acc = None, None, []
@@ -16,9 +18,11 @@ def main():
             continue
         if r[0] == 'File Path':
             cur = r[1].split('/')[-1]
+        elif r[0] == 'Function Name':
+            func = r[1]
         elif r[0] == 'Line No':
             hdr = r
-        elif hdr and r[0] not in ('', 'Function Name') and len(r) > 5:
+        elif hdr and r[0] != '' and len(r) > 5 and want in func:
             try:
                 acc.append((float(r[4]), cur, r[0], r[1][:120]))
             except ValueError:
