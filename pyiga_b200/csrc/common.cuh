@@ -12,6 +12,7 @@
 #include <cmath>
 using std::fma;
 using std::fabs;
+struct alignas(16) double2 { double x, y; };     // host build of the shared kernel bodies
 #endif
 
 #if defined(__CUDACC__)

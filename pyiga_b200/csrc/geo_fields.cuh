@@ -46,8 +46,11 @@ struct PbFieldParams {
     struct { int bp, ap; } outmap[PB_MAXFIELDS];                      // parametric slots of field f
 };
 
+template <int I> struct PbInt { static constexpr int value = I; };
+
 struct PbPoint {        // what a field program sees at one Gauss point
-    double J[3][3];
+    double J[3][3];     // Jacobian numerators: the Jacobian is J / jden
+    double jden;        // 1 unless the producer leaves the quotient rule's 1/W^2 to the program (RAT)
     double x[3];        // physical coordinates
     double gw;          // product of the 1D Gauss weights
     long long idx;      // linear point index
@@ -147,12 +150,47 @@ template <int DIM> PB_HD void pb_inv(const double (&J)[3][3], double det, double
     }
 }
 
+// adjugate (transposed cofactors): inverse = A / det
+template <int DIM> PB_HD void pb_adj(const double (&J)[3][3], double (&A)[3][3]) {
+    if constexpr (DIM == 2) {
+        A[0][0] = J[1][1];  A[0][1] = -J[0][1];
+        A[1][0] = -J[1][0]; A[1][1] = J[0][0];
+    } else {
+        A[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        A[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+        A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+        A[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+        A[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+        A[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+        A[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        A[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+        A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    }
+}
+
+// programs are instantiated with RAT = true where the point carries an unnormalised Jacobian
+// (J / jden, rational geometries on the row path) and fold the denominator into their own scaling
+template <int DIM, bool RAT> PB_HD void pb_point_normalize(PbPoint& pt) {
+    if constexpr (RAT) {
+        const double r = 1.0 / pt.jden;
+        for (int i = 0; i < DIM; ++i)
+            for (int j = 0; j < DIM; ++j) pt.J[i][j] *= r;
+        pt.jden = 1.0;
+    }
+}
+
 // mass: W = GaussWeight * |det J|                      (pyiga/assemblers.pyx:1223-1249)
 template <int DIM> struct PbProgMass {
     static constexpr int NF = 1;
     static constexpr bool NEED_X = false;
-    PB_HD static void run(const PbFieldParams&, const PbPoint& pt, double* f) {
-        f[0] = pt.gw * fabs(pb_det<DIM>(pt.J));
+    template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) {
+        const double d = pt.gw * fabs(pb_det<DIM>(pt.J));
+        if constexpr (RAT) {
+            const double r = 1.0 / pt.jden;
+            f[0] = d * (DIM == 2 ? r * r : r * r * r);
+        } else {
+            f[0] = d;
+        }
     }
 };
 
@@ -161,17 +199,19 @@ template <int DIM> struct PbProgMass {
 template <int DIM> struct PbProgStiffness {
     static constexpr int NF = DIM * (DIM + 1) / 2;
     static constexpr bool NEED_X = false;
-    PB_HD static void run(const PbFieldParams&, const PbPoint& pt, double* f) {
+    template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) {
+        // with J = N / jden:  W J^-1 J^-T = gw jden^(2-DIM) / |det N| * adj(N) adj(N)^T  -- one division
         const double det = pb_det<DIM>(pt.J);
-        const double W = pt.gw * fabs(det);
-        double I[3][3];
-        pb_inv<DIM>(pt.J, det, I);
+        double A[3][3];
+        pb_adj<DIM>(pt.J, A);
+        const double den = (RAT && DIM == 3) ? pt.jden * fabs(det) : fabs(det);
+        const double sc = pt.gw / den;
         int k = 0;
         for (int a = 0; a < DIM; ++a)
             for (int b = a; b < DIM; ++b) {
-                double s = 0.0;
-                for (int m = 0; m < DIM; ++m) s += I[a][m] * I[b][m];
-                f[k++] = W * s;
+                double s = A[a][0] * A[b][0];
+                for (int m = 1; m < DIM; ++m) s = fma(A[a][m], A[b][m], s);
+                f[k++] = sc * s;
             }
     }
 };
@@ -186,7 +226,8 @@ template <int DIM> struct PbProgStiffness {
 template <int DIM> struct PbProgGeneral {
     static constexpr int NF = PB_MAXFIELDS;
     static constexpr bool NEED_X = false;
-    PB_HD static void run(const PbFieldParams& prm, const PbPoint& pt, double* f) {
+    template <bool RAT> PB_HD static void run(const PbFieldParams& prm, PbPoint& pt, double* f) {
+        pb_point_normalize<DIM, RAT>(pt);
         const double det = pb_det<DIM>(pt.J);
         const double W = pt.gw * fabs(det);
         double I[3][3];
@@ -214,7 +255,8 @@ template <int DIM> struct PbProgGeneral {
 template <int DIM> struct PbProgGeoRaw {
     static constexpr int NF = DIM * DIM + DIM;
     static constexpr bool NEED_X = true;
-    PB_HD static void run(const PbFieldParams&, const PbPoint& pt, double* f) {
+    template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) {
+        pb_point_normalize<DIM, RAT>(pt);
         for (int i = 0; i < DIM; ++i)
             for (int j = 0; j < DIM; ++j) f[i * DIM + j] = pt.J[i][j];
         for (int i = 0; i < DIM; ++i) f[DIM * DIM + i] = pt.x[i];
@@ -228,6 +270,7 @@ PB_HD void pb_fields_point(const PbFieldParams& prm, long long idx) {
     for (int k = DIM - 1; k >= 0; --k) { g[k] = (int)(r % prm.G[k]); r /= prm.G[k]; }
     PbPoint pt;
     pt.idx = idx;
+    pt.jden = 1.0;
     pt.gw = 1.0;
     for (int k = 0; k < DIM; ++k) pt.gw *= prm.gw[k][g[k]];
     if (prm.jac_in) {
@@ -238,7 +281,7 @@ PB_HD void pb_fields_point(const PbFieldParams& prm, long long idx) {
         pb_geo_eval<DIM>(prm.geo, g, pt);
     }
     double f[Prog::NF];
-    Prog::run(prm, pt, f);
+    Prog::template run<false>(prm, pt, f);
     for (int c = 0; c < Prog::NF && c < prm.nf; ++c) prm.fields[(long long)c * prm.npts + idx] = f[c];
 }
 
@@ -285,14 +328,16 @@ PB_HD void pb_geo_row_partial(const PbGeoDev& geo, const int* g, int i_last, int
     }
 }
 
-// finish one point of the row from Y ([Ng_last][NC][DIM])
-template <int DIM, int NC, class Prog>
-PB_HD void pb_fields_row_point(const PbFieldParams& prm, const int* g, const double* Y) {
+// finish one point of the row from Y ([Ng_last][NC][DIM]).  PGL: degree of the geometry on the last
+// axis when known at compile time (unrolled), -1 for a run-time loop.  `row_idx`: linear index of the
+// row's first point, `gw_row`: product of the Gauss weights of the leading axes.
+template <int DIM, int NC, class Prog, int PGL>
+PB_HD void pb_fields_row_point(const PbFieldParams& prm, int gl, const double* Y, long long row_idx, double gw_row) {
     const PbGeoDev& geo = prm.geo;
-    const int L = DIM - 1;
-    const int gl = g[L];
+    constexpr int L = DIM - 1;
+    const int pgl = PGL >= 0 ? PGL : geo.pg[L];
     const int fl = geo.gfirst[L][gl];
-    const double* TL = geo.GV[L] + (long long)gl * 2 * (geo.pg[L] + 1);
+    const double* TL = geo.GV[L] + (long long)gl * 2 * (pgl + 1);
     double val[NC], dv[NC][DIM];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -300,9 +345,21 @@ PB_HD void pb_fields_row_point(const PbFieldParams& prm, const int* g, const dou
 #pragma unroll
         for (int k = 0; k < DIM; ++k) dv[c][k] = 0.0;
     }
-    for (int a = 0; a <= geo.pg[L]; ++a) {
-        const double w = TL[a], d = TL[geo.pg[L] + 1 + a];
-        const double* y = Y + (long long)(fl + a) * NC * DIM;
+    auto term = [&](int a) {
+        const double w = TL[a], d = TL[pgl + 1 + a];
+        const double* yp = Y + (long long)(fl + a) * NC * DIM;
+        double y[NC * DIM];
+        if constexpr ((NC * DIM) % 2 == 0) {        // 16-byte aligned entries: vector loads
+#pragma unroll
+            for (int h = 0; h < NC * DIM / 2; ++h) {
+                const double2 v = *reinterpret_cast<const double2*>(yp + 2 * h);
+                y[2 * h] = v.x;
+                y[2 * h + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < NC * DIM; ++h) y[h] = yp[h];
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             val[c] = fma(w, y[c * DIM + 0], val[c]);
@@ -310,26 +367,31 @@ PB_HD void pb_fields_row_point(const PbFieldParams& prm, const int* g, const dou
             dv[c][0] = fma(w, y[c * DIM + 1], dv[c][0]);        // derivative on axis 0
             if constexpr (DIM == 3) dv[c][1] = fma(w, y[c * DIM + 2], dv[c][1]);
         }
+    };
+    if constexpr (PGL >= 0) {
+#pragma unroll
+        for (int a = 0; a <= PGL; ++a) term(a);
+    } else {
+        for (int a = 0; a <= pgl; ++a) term(a);
     }
     PbPoint pt;
-    long long idx = 0;
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) idx = idx * prm.G[k] + g[k];
+    const long long idx = row_idx + gl;
     pt.idx = idx;
-    pt.gw = 1.0;
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) pt.gw *= prm.gw[k][g[k]];
+    pt.gw = gw_row * prm.gw[L][gl];
     constexpr int GD = DIM;     // square geometry maps: dim == sdim
-    if constexpr (NC == GD + 1) {
+    constexpr bool RAT = (NC == GD + 1);
+    if constexpr (RAT) {
+        // quotient rule without the division: J = (V' W - V W') / W^2, the program folds 1 / W^2 in
         const double W = val[GD];
-        const double iW2 = 1.0 / (W * W);
+        pt.jden = W * W;
 #pragma unroll
         for (int i = 0; i < GD; ++i) {
-            pt.x[i] = val[i] / W;
+            if constexpr (Prog::NEED_X) pt.x[i] = val[i] / W;
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) pt.J[i][DIM - 1 - k] = (dv[i][k] * W - val[i] * dv[GD][k]) * iW2;
+            for (int k = 0; k < DIM; ++k) pt.J[i][DIM - 1 - k] = dv[i][k] * W - val[i] * dv[GD][k];
         }
     } else {
+        pt.jden = 1.0;
 #pragma unroll
         for (int i = 0; i < GD; ++i) {
             pt.x[i] = val[i];
@@ -338,25 +400,42 @@ PB_HD void pb_fields_row_point(const PbFieldParams& prm, const int* g, const dou
         }
     }
     double f[Prog::NF];
-    Prog::run(prm, pt, f);
+    Prog::template run<RAT>(prm, pt, f);
+    double* o = prm.fields + idx;
+    const int nf = prm.nf;
 #pragma unroll
-    for (int c = 0; c < Prog::NF; ++c)
-        if (c < prm.nf) prm.fields[(long long)c * prm.npts + idx] = f[c];
+    for (int c = 0; c < Prog::NF; ++c) {
+        if (c < nf) *o = f[c];
+        o += prm.npts;
+    }
+}
+
+// linear index of the first point of a row and the Gauss weight of its leading axes
+template <int DIM>
+PB_HD void pb_row_origin(const PbFieldParams& prm, long long row, int* g, long long& row_idx, double& gw_row) {
+    g[0] = g[1] = g[2] = 0;
+    if constexpr (DIM == 2) {
+        g[0] = (int)row;
+        gw_row = prm.gw[0][g[0]];
+    } else {
+        g[0] = (int)(row / prm.G[1]);
+        g[1] = (int)(row % prm.G[1]);
+        gw_row = prm.gw[0][g[0]] * prm.gw[1][g[1]];
+    }
+    row_idx = row * prm.G[DIM - 1];
 }
 
 // one whole row, sequentially (host emulation) — `Y` is scratch of Ng_last*NC*DIM doubles
 template <int DIM, int NC, class Prog>
 PB_HD void pb_fields_row_seq(const PbFieldParams& prm, long long row, double* Y) {
-    int g[3] = {0, 0, 0};
-    if constexpr (DIM == 2) g[0] = (int)row;
-    else { g[0] = (int)(row / prm.G[1]); g[1] = (int)(row % prm.G[1]); }
+    int g[3];
+    long long row_idx;
+    double gw_row;
+    pb_row_origin<DIM>(prm, row, g, row_idx, gw_row);
     const int NgL = prm.geo.Ng[DIM - 1];
     for (int i = 0; i < NgL; ++i)
         for (int c = 0; c < NC; ++c) pb_geo_row_partial<DIM>(prm.geo, g, i, c, Y + ((long long)i * NC + c) * DIM);
-    for (int gl = 0; gl < prm.G[DIM - 1]; ++gl) {
-        g[DIM - 1] = gl;
-        pb_fields_row_point<DIM, NC, Prog>(prm, g, Y);
-    }
+    for (int gl = 0; gl < prm.G[DIM - 1]; ++gl) pb_fields_row_point<DIM, NC, Prog, -1>(prm, gl, Y, row_idx, gw_row);
 }
 
 #if defined(__CUDACC__)
@@ -367,7 +446,7 @@ PB_HD void pb_fields_row_seq(const PbFieldParams& prm, long long row, double* Y)
 template <int DIM, int NC, class Prog>
 __global__ void __launch_bounds__(128) pb_fields_row_kernel(const __grid_constant__ PbFieldParams prm, long long row_begin,
                                                             long long row_end) {
-    extern __shared__ double pb_Y[];
+    extern __shared__ __align__(16) double pb_Y[];
     const long long row0 = row_begin + (long long)blockIdx.x * PB_K2_ROWS;
     const int nrows = (int)((row_end - row0) < PB_K2_ROWS ? (row_end - row0) : PB_K2_ROWS);
     const int NgL = prm.geo.Ng[DIM - 1];
@@ -381,15 +460,25 @@ __global__ void __launch_bounds__(128) pb_fields_row_kernel(const __grid_constan
         pb_geo_row_partial<DIM>(prm.geo, g, t / NC, t % NC, pb_Y + (long long)r * ysz + (long long)t * DIM);
     }
     __syncthreads();
-    for (int r = 0; r < nrows; ++r) {
-        const long long row = row0 + r;
-        int g[3] = {0, 0, 0};
-        if constexpr (DIM == 2) g[0] = (int)row;
-        else { g[0] = (int)(row / prm.G[1]); g[1] = (int)(row % prm.G[1]); }
-        for (int gl = threadIdx.x; gl < prm.G[DIM - 1]; gl += blockDim.x) {
-            g[DIM - 1] = gl;
-            pb_fields_row_point<DIM, NC, Prog>(prm, g, pb_Y + (long long)r * ysz);
+    const int GL = prm.G[DIM - 1];
+    auto rows = [&](auto PGLc) {
+        constexpr int PGL = decltype(PGLc)::value;
+        for (int r = 0; r < nrows; ++r) {
+            int g[3];
+            long long row_idx;
+            double gw_row;
+            pb_row_origin<DIM>(prm, row0 + r, g, row_idx, gw_row);
+            const double* Y = pb_Y + (long long)r * ysz;
+            for (int gl = threadIdx.x; gl < GL; gl += blockDim.x)
+                pb_fields_row_point<DIM, NC, Prog, PGL>(prm, gl, Y, row_idx, gw_row);
         }
+    };
+    // the loop over the geometry's basis functions of the last axis is unrolled for the usual degrees
+    switch (prm.geo.pg[DIM - 1]) {
+        case 1: rows(PbInt<1>{}); break;
+        case 2: rows(PbInt<2>{}); break;
+        case 3: rows(PbInt<3>{}); break;
+        default: rows(PbInt<-1>{}); break;
     }
 }
 #endif

@@ -40,21 +40,25 @@ enum PbPlanId {
 
 struct PbPlanCopy {
     static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
+    static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int) { return PbOp{0, 0, 0, 0, 0}; }
 };
 struct PbPlanOne11 {
     static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
+    static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int) { return PbOp{0, 0, 1, 1, 0}; }
 };
 struct PbPlanOne10 {
     static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
+    static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int) { return PbOp{0, 0, 1, 0, 0}; }
 };
 struct PbPlanPairT {
     static constexpr int NOPS = 2, NOUT = 1, MINB = 4, NPF = 3;
+    static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[2] = {{0, 0, 0, 0, 0}, {1, 0, 1, 0, 0}};
@@ -63,6 +67,7 @@ struct PbPlanPairT {
 };
 struct PbPlanFinal4 {
     static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 2;
+    static constexpr int MINB4 = 3;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = true;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {1, 1, 1, 0, 0}, {2, 0, 1, 1, 0}};
@@ -71,6 +76,7 @@ struct PbPlanFinal4 {
 };
 struct PbPlanGen4 {
     static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 2;
+    static constexpr int MINB4 = 3;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {2, 0, 1, 0, 0}, {3, 0, 1, 1, 0}};
@@ -79,6 +85,7 @@ struct PbPlanGen4 {
 };
 struct PbPlanS1A {
     static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
+    static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 1, 0, 2}};
@@ -87,6 +94,7 @@ struct PbPlanS1A {
 };
 struct PbPlanS1B {
     static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
+    static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 0, 0, 1}, {2, 0, 0, 0, 2}};
@@ -94,7 +102,8 @@ struct PbPlanS1B {
     }
 };
 struct PbPlanS2B {
-    static constexpr int NOPS = 3, NOUT = 2, MINB = 2, NPF = 3;
+    static constexpr int NOPS = 3, NOUT = 2, MINB = 3, NPF = 3;
+    static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 1, 0, 0}, {2, 0, 0, 0, 1}};
@@ -103,6 +112,7 @@ struct PbPlanS2B {
 };
 struct PbPlanS1_2D {
     static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
+    static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 0, 0, 2}};

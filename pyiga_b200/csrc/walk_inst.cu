@@ -17,7 +17,7 @@ int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* strea
     pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q>(*prm, tid, prm->V2); });
     return 0;
 #else
-    auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, Plan::MINB, Plan::NPF>;
+    auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, (PB_P >= 4 ? Plan::MINB4 : Plan::MINB), Plan::NPF>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
