@@ -217,6 +217,30 @@ PB200_API int pb200_mlb_matvec(const pb200_mlstruct* s, int row0_begin, int row0
 PB200_API int pb200_kron_matvec(int d, const double* const* d_factors, const int* rows, const int* cols,
                       const double* d_x, double* d_y, double* d_tmp, void* stream);
 
+/* ---- elimination of constrained dofs on device CSR arrays ----------------------------------------
+ * Replaces the selection-matrix products of RestrictedLinearSystem (pyiga/assemble.py:575-652):
+ *   A_r = R_free_v A R_free^T  (restrict_matrix, :632-637),  b_r = R_free_v (b - A R_elim^T values) (:616).
+ * d_rows: old row index of every kept row (nrows_new, increasing); d_colmap: new column index of every
+ * old column or -1 if eliminated.  idx_bytes (4 or 8) is the integer width of all CSR index arrays.
+ * Phase 1 writes the new indptr (nrows_new+1 entries; the last one is the new nnz, read it back to
+ * size the outputs); phase 2 compacts indices and values.  Order inside rows is preserved. */
+PB200_API int pb200_csr_restrict_workspace(long long nrows_new, int idx_bytes, size_t* bytes);
+PB200_API int pb200_csr_restrict_count(long long nrows_new, const int32_t* d_rows, const void* d_indptr,
+                             const void* d_indices, int idx_bytes, const int32_t* d_colmap,
+                             void* d_indptr_new, void* d_work, size_t work_bytes, void* stream);
+PB200_API int pb200_csr_restrict_fill(long long nrows_new, const int32_t* d_rows, const void* d_indptr,
+                            const void* d_indices, const double* d_values, int idx_bytes,
+                            const int32_t* d_colmap, const void* d_indptr_new, void* d_indices_new,
+                            double* d_values_new, void* stream);
+/* y_out = (d_y_in ? y_in : 0) + alpha * A x for device CSR arrays (the rhs update above; scipy's
+ * csr_matrix.dot on the reference side) */
+PB200_API int pb200_csr_matvec(long long nrows, const void* d_indptr, const void* d_indices, const double* d_values,
+                     int idx_bytes, const double* d_x, const double* d_y_in, double alpha, double* d_y_out,
+                     void* stream);
+/* out[k] = in[idx[k]] / out[idx[k]] = in[k]  (restrict, extend, complete; pyiga/assemble.py:618-652) */
+PB200_API int pb200_vec_gather(long long n, const int32_t* d_idx, const double* d_in, double* d_out, void* stream);
+PB200_API int pb200_vec_scatter(long long n, const int32_t* d_idx, const double* d_in, double* d_out, void* stream);
+
 /* K1 stand-alone (replaces bspline.active_deriv / collocation_derivs_info,
  * pyiga/bspline_cy.pyx:126-145, pyiga/bspline.py:648-660): d_first m int32, d_values [m][nderiv+1][p+1] */
 PB200_API int pb200_basis_eval(const double* d_knots, int nknots, int p, const double* d_nodes, int m, int nderiv,

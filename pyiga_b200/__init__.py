@@ -6,4 +6,4 @@ See DESIGN.md.
 """
 __version__ = '0.1.0'
 
-from . import bspline, geometry, quadrature, mlmatrix, assemblers, assemble, operators  # noqa: F401
+from . import bspline, geometry, quadrature, mlmatrix, assemblers, assemble, operators, utils, approx  # noqa: F401

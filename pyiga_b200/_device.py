@@ -60,6 +60,12 @@ class CudaBackend:
     def nbytes(self, buf):
         return buf.numel() * buf.element_size()
 
+    def size(self, buf):
+        return int(buf.numel())
+
+    def itemsize(self, buf):
+        return int(buf.element_size())
+
     def stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 

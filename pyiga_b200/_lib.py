@@ -89,6 +89,15 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     'pb200_kron_matvec': (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pb200_csr_restrict_workspace': (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_size_t)]),
+    'pb200_csr_restrict_count': (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'pb200_csr_restrict_fill': (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pb200_csr_matvec': (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_double, C.c_void_p, C.c_void_p]),
+    'pb200_vec_gather': (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pb200_vec_scatter': (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb200_basis_eval': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb200_probe_fp64': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),

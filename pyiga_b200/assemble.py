@@ -143,11 +143,188 @@ def inner_products(kvs, f, f_physical=False, geo=None):
     shape ndofs.  `f` is a function of the parameter coordinates unless `f_physical`."""
     dim, kvs = _detect_dim(kvs)
     if dim == 1:
-        raise NotImplementedError('1D inner products are not part of the device path')
+        # marginal of the 2D functional on (kv) x (one linear element), as in _assemble_1d: the two
+        # functions of the dummy axis sum to 1, and f only sees the first coordinate
+        assert geo is None, "Geometry map not supported for 1D inner products"
+        unit = bspline.make_knots(1, 0.0, 1.0, 1)
+        kvs2 = (kvs, unit)
+        v = assemblers.L2FunctionalAssembler2D(kvs2, geometry.identity(kvs2), lambda x, y: f(y)).assemble_vector()
+        return np.asarray(v).sum(axis=1)
     if geo is None:
         geo = _default_geo(kvs)
     name = 'L2FunctionalAssembler%s%dD' % ('Phys' if f_physical else '', dim)
     return getattr(assemblers, name)(kvs, geo, f).assemble_vector()
+
+
+################################################################################
+# Incorporating essential boundary conditions (pyiga/assemble.py:342-652)
+################################################################################
+
+def slice_indices(ax, idx, shape, ravel=False, flip=None):
+    """Dof indices of the slice `idx` across axis `ax` of a tensor-product basis of size `shape`:
+    an ``N x dim`` array of multi-indices or, with `ravel`, raveled indices
+    (``pyiga/assemble.py:346-368``)."""
+    shape = tuple(shape)
+    if idx < 0:
+        idx += shape[ax]
+    axdofs = [np.arange(n) for n in shape]
+    if flip is not None:
+        flip = tuple(flip)
+        flip = flip[:ax] + (False,) + flip[ax:]
+        axdofs = [a[::-1] if flp else a for a, flp in zip(axdofs, flip)]
+    axdofs[ax] = np.array([idx])
+    grids = np.meshgrid(*axdofs, indexing='ij')
+    multi = np.stack([g.ravel() for g in grids], axis=1)
+    if ravel:
+        return np.ravel_multi_index(multi.T, shape)
+    return multi
+
+
+def boundary_dofs(kvs, bdspec, ravel=False, flip=None):
+    """Indices of the dofs on one side of the boundary (``pyiga/assemble.py:370-377``)."""
+    bdax, bdside = bspline._parse_bdspec(bdspec, len(kvs))
+    N = tuple(kv.numdofs for kv in kvs)
+    return slice_indices(bdax, 0 if bdside == 0 else -1, N, ravel=ravel, flip=flip)
+
+
+def boundary_cells(kvs, bdspec, ravel=False):
+    """Indices of the cells on one side of the boundary (``pyiga/assemble.py:379-386``)."""
+    bdax, bdside = bspline._parse_bdspec(bdspec, len(kvs))
+    N = tuple(kv.numspans for kv in kvs)
+    return slice_indices(bdax, 0 if bdside == 0 else -1, N, ravel=ravel)
+
+
+def _drop_nans(indices, values):
+    keep = ~np.isnan(values)
+    return (indices, values) if keep.all() else (indices[keep], values[keep])
+
+
+def combine_bcs(bcs):
+    """Merge ``(indices, values)`` pairs; a dof that occurs more than once takes its value from
+    its first occurrence (``pyiga/assemble.py:553-566``)."""
+    bcs = list(bcs)
+    indices = np.concatenate([ind for ind, _ in bcs])
+    values = np.concatenate([val for _, val in bcs])
+    assert indices.shape == values.shape, 'Inconsistent BC sizes'
+    uidx, lookup = np.unique(indices, return_index=True)
+    return uidx, values[lookup]
+
+
+def compute_dirichlet_bc(kvs, geo, bdspec, dir_func):
+    """Indices and values of a Dirichlet condition on one side, by interpolation of `dir_func`
+    (given in physical coordinates; scalars mean constants) on the boundary face
+    (``pyiga/assemble.py:395-461``)."""
+    from .approx import interpolate
+    bdspec = bspline._parse_bdspec(bdspec, len(kvs))
+    bdax, bdside = bdspec
+    bdbasis = list(kvs)
+    assert len(bdbasis) == geo.sdim, 'Invalid dimension of geometry'
+    del bdbasis[bdax]
+    bdgeo = geo.boundary(bdspec)
+    if np.isscalar(dir_func):
+        const_value = dir_func
+        dir_func = lambda *x: const_value
+    dircoeffs = interpolate(bdbasis, dir_func, geo=bdgeo)
+    N = tuple(kv.numdofs for kv in kvs)
+    bdindices = slice_indices(bdax, 0 if bdside == 0 else -1, N, ravel=True)
+    extra_dims = dircoeffs.ndim - len(bdbasis)
+    if extra_dims == 0:
+        return _drop_nans(bdindices, dircoeffs.ravel())
+    if extra_dims == 1:       # vector function, blocked vector discretization
+        NN = int(np.prod(N))
+        idx, val = combine_bcs((bdindices + j * NN, dircoeffs[..., j].ravel()) for j in range(dircoeffs.shape[-1]))
+        return _drop_nans(idx, val)
+    raise ValueError('invalid dimension of Dirichlet coefficients: %s' % (dircoeffs.shape,))
+
+
+def compute_dirichlet_bcs(kvs, geo, bdconds):
+    """Dirichlet conditions on several sides; ``('all', g)`` means every side
+    (``pyiga/assemble.py:463-489``)."""
+    if len(bdconds) == 2 and isinstance(bdconds[0], str) and bdconds[0] == 'all':
+        dir_func = bdconds[1]
+        bdconds = [((ax, bd), dir_func) for ax in range(len(kvs)) for bd in (0, 1)]
+    return combine_bcs(compute_dirichlet_bc(kvs, geo, bdspec, g) for (bdspec, g) in bdconds)
+
+
+class RestrictedLinearSystem:
+    """Linear system with some dofs eliminated (``pyiga/assemble.py:568-652``).
+
+    `A` may be a scipy sparse matrix, an :class:`MLMatrix` whose values are still on the GPU, or a
+    :class:`~pyiga_b200._csr.DeviceCSR`.  The reference multiplies with 0/1 selection matrices; here
+    the kept rows/columns are compacted by two passes over the device CSR arrays and the right-hand
+    side is updated by one device matvec.  ``A`` (scipy CSR, fetched on first use), ``b``,
+    ``restrict``, ``restrict_rhs``, ``restrict_matrix``, ``extend`` and ``complete`` behave like the
+    reference; ``A_device`` is the restricted matrix as device CSR.
+    """
+
+    def __init__(self, A, b, bcs, elim_rows=None):
+        from ._csr import DeviceCSR
+        indices, values = bcs
+        indices = np.asarray(list(indices), dtype=np.int64)
+        Ad = DeviceCSR.wrap(A)
+        nrows, ncols = Ad.shape
+        if np.isscalar(b):
+            b = np.broadcast_to(b, nrows)
+        if np.isscalar(values):
+            values = np.broadcast_to(values, indices.shape[0])
+        self.values = np.asarray(values, dtype=np.float64)
+
+        mask = np.ones(ncols, dtype=bool)
+        mask[indices] = False
+        self._free = np.nonzero(mask)[0]
+        self._elim = np.nonzero(~mask)[0]
+        # R_elim lists the eliminated dofs in increasing order; like the reference, `values` is
+        # taken in that order
+        self._colmap = np.full(ncols, -1, dtype=np.int32)
+        self._colmap[self._free] = np.arange(self._free.size, dtype=np.int32)
+        if elim_rows is not None:
+            maskv = np.ones(nrows, dtype=bool)
+            maskv[sorted(elim_rows)] = False
+            self._free_v = np.nonzero(maskv)[0]
+        else:
+            self._free_v = self._free
+
+        be = Ad.be
+        self.A_device = Ad.restrict(self._free_v, self._colmap, self._free.size)
+        self._A = None
+        # b - A (R_elim^T values), restricted to the kept rows
+        x_elim = np.zeros(ncols)
+        x_elim[self._elim] = self.values
+        t = Ad.matvec_device(be.from_host(x_elim), be.from_host(np.ascontiguousarray(b, dtype=np.float64)), alpha=-1.0)
+        from . import _csr
+        self.b = be.to_host(_csr.gather(t, self._free_v))
+
+    @property
+    def A(self):
+        if self._A is None:
+            self._A = self.A_device.to_scipy()
+        return self._A
+
+    def restrict(self, u):
+        """Restriction of a vector of all dofs to the free dofs."""
+        return np.asarray(u)[self._free]
+
+    def restrict_rhs(self, f):
+        """Restriction of a right-hand side to the non-eliminated rows."""
+        return np.asarray(f)[self._free_v]
+
+    def restrict_matrix(self, B):
+        """Restriction of a matrix which operates on all dofs to the free dofs (scipy CSR)."""
+        from ._csr import DeviceCSR
+        return DeviceCSR.wrap(B).restrict(self._free_v, self._colmap, self._free.size).to_scipy()
+
+    def extend(self, u):
+        """Pad a vector of the free dofs with zeros to all dofs."""
+        u = np.asarray(u)
+        out = np.zeros((self._colmap.size,) + u.shape[1:], dtype=np.result_type(u, np.float64))
+        out[self._free] = u
+        return out
+
+    def complete(self, u):
+        """Solution of the original system from a solution `u` of the restricted one."""
+        out = self.extend(u)
+        out[self._elim] += self.values.reshape((-1,) + (1,) * (out.ndim - 1))
+        return out
 
 
 def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatable=[]):

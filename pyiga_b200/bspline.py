@@ -129,6 +129,18 @@ class KnotVector:
         return abs(self.kv[-1] - self.kv[0]) / self.numspans
 
 
+def _parse_bdspec(bdspec, dim):
+    """``(axis, side)`` of a boundary given as pair or by name (``pyiga/bspline.py:13-33``)."""
+    names = {'left': (dim - 1, 0), 'right': (dim - 1, 1), 'bottom': (dim - 2, 0), 'top': (dim - 2, 1),
+             'front': (dim - 3, 0), 'back': (dim - 3, 1)}
+    bd = names.get(bdspec, bdspec) if isinstance(bdspec, str) else bdspec
+    if isinstance(bd, str) or not (len(bd) == 2 and bd[1] in (0, 1)):
+        raise ValueError('invalid bdspec ' + str(bd))
+    if bd[0] < 0 or bd[0] >= dim:
+        raise ValueError('invalid bdspec %s for space of dimension %d' % (bdspec, dim))
+    return tuple(bd)
+
+
 def make_knots(p, a, b, n, mult=1):
     """Open knot vector of degree `p` on `(a,b)` with `n` equal spans and interior
     multiplicity `mult` (reference: ``pyiga/bspline.py:192-213``; the interior
@@ -150,6 +162,67 @@ def _as_kv_tuple(kvs):
     if hasattr(kvs, 'kv') and hasattr(kvs, 'p'):
         return (kvs,)
     return tuple(kvs)
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluation of the active basis functions (K1 of the device library)
+# ---------------------------------------------------------------------------------------------
+
+def _basis_eval(kv, u, numderiv):
+    """first active function per node (int32, n) and values [n][numderiv+1][p+1], from the GPU"""
+    import ctypes as C
+    from . import _device
+    be = _device.backend()
+    u = np.ascontiguousarray(np.atleast_1d(u), dtype=np.float64).ravel()
+    m = u.size
+    d_kv, d_u = be.from_host(kv.kv), be.from_host(u)
+    d_first = be.empty(m, np.int32)
+    d_vals = be.empty(m * (numderiv + 1) * (kv.p + 1))
+    _device.check(be.lib.pb200_basis_eval(be.ptr(d_kv), kv.kv.size, kv.p, be.ptr(d_u), m, numderiv,
+                                          be.ptr(d_first), be.ptr(d_vals), be.stream()))
+    return be.to_host(d_first), be.to_host(d_vals).reshape(m, numderiv + 1, kv.p + 1)
+
+
+def active_deriv(kv, u, numderiv):
+    """Values and derivatives up to `numderiv` of the p+1 active B-splines at the points `u`:
+    array ``(numderiv+1, p+1, n)`` (or without the last axis for scalar `u`), computed by the K1
+    kernel (``pyiga/bspline_cy.pyx:126-145``)."""
+    _, vals = _basis_eval(kv, u, numderiv)
+    out = np.ascontiguousarray(vals.transpose(1, 2, 0))
+    return out[..., 0] if np.isscalar(u) else out
+
+
+def active_ev(kv, u):
+    """Values of the active B-splines: ``(p+1, n)`` (``pyiga/bspline_cy.pyx:116-124``)."""
+    return active_deriv(kv, u, 0)[0]
+
+
+def collocation_derivs_info(kv, nodes, derivs=1):
+    """First active function per node and coefficient rows ``(derivs+1, n, p+1)``
+    (``pyiga/bspline.py:649-660``)."""
+    first, vals = _basis_eval(kv, nodes, derivs)
+    return first.astype(np.int64), np.ascontiguousarray(vals.transpose(1, 0, 2))
+
+
+def collocation_info(kv, nodes):
+    first, vals = collocation_derivs_info(kv, nodes, 0)
+    return first, vals[0]
+
+
+def collocation_derivs(kv, nodes, derivs=1):
+    """List of derivs+1 CSR collocation matrices ``(len(nodes), numdofs)`` (``pyiga/bspline.py:629-647``)."""
+    import scipy.sparse
+    nodes = np.asarray(nodes)
+    m, n, p = nodes.size, kv.numdofs, kv.p
+    first, vals = collocation_derivs_info(kv, nodes, derivs)
+    I = np.repeat(np.arange(m), p + 1)
+    J = (first[:, None] + np.arange(p + 1)[None, :]).ravel()
+    return [scipy.sparse.coo_matrix((vals[d].ravel(), (I, J)), shape=(m, n)).tocsr() for d in range(derivs + 1)]
+
+
+def collocation(kv, nodes):
+    """CSR collocation matrix: entry (i, j) = B_j(nodes[i]) (``pyiga/bspline.py:591-612``)."""
+    return collocation_derivs(kv, nodes, 0)[0]
 
 
 class _SplineFuncBase:
@@ -249,3 +322,13 @@ class BSplineFunc(_SplineFuncBase):
         assert self.dim == 2, 'Must be 2D vector function'
         c, s = np.cos(angle), np.sin(angle)
         return self.apply_matrix([[c, -s], [s, c]])
+
+    def boundary(self, bdspec):
+        """One side of the boundary as a :class:`BSplineFunc` with one parameter less
+        (``pyiga/bspline.py:1017-1036``; open knot vectors make the boundary interpolatory)."""
+        axis, side = _parse_bdspec(bdspec, self.sdim)
+        slices = self.sdim * [slice(None)]
+        slices[axis] = 0 if side == 0 else -1
+        kvs = list(self.kvs)
+        del kvs[axis]
+        return BSplineFunc(kvs, self.coeffs[tuple(slices)])

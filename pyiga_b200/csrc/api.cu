@@ -18,6 +18,7 @@
 #include "entries.cuh"
 #include "geo_fields.cuh"
 #include "mlb.cuh"
+#include "csr.cuh"
 #include "plans.cuh"
 #include "walk1.cuh"
 
@@ -1551,6 +1552,153 @@ extern "C" int pb200_mlb_matvec(const pb200_mlstruct* a, int ra, int rb, const d
     for (int k = 1; k < a->dim; ++k) nrows *= p.Nv[k];
     k_matvec(p, nrows, d_x, x_j0_begin, d_y, (pbStream)stream);
     CK(pbLastError());
+    return 0;
+}
+
+// ---- CSR utilities (csr.cuh) ---------------------------------------------------------------------
+extern "C" int pb200_csr_restrict_workspace(long long nrows_new, int idx_bytes, size_t* bytes) {
+    if (!bytes || nrows_new < 0 || (idx_bytes != 4 && idx_bytes != 8)) return fail(PB200_EINVAL, "invalid argument");
+#ifdef PB_EMULATE
+    *bytes = 8;
+#else
+    *bytes = (size_t)((nrows_new + PB_SCAN_BLOCK - 1) / PB_SCAN_BLOCK + 1) * (size_t)idx_bytes;
+#endif
+    return 0;
+}
+
+template <class IT>
+static int csr_restrict_count(long long n, const int* rows, const IT* indptr, const IT* indices, const int* colmap,
+                              IT* indptr_new, IT* work, pbStream st) {
+#ifdef PB_EMULATE
+    (void)work; (void)st;
+    indptr_new[0] = 0;
+    for (long long r = 0; r < n; ++r) indptr_new[r + 1] = indptr_new[r] + (IT)pb_csr_count_row<IT>(indptr, indices, colmap, rows[r]);
+    g_launches += 1;
+#else
+    CK(cudaMemsetAsync(indptr_new, 0, sizeof(IT), st));
+    if (n > 0) {
+        const unsigned b = (unsigned)std::min<long long>((n + 7) / 8, 148LL * 32);
+        const unsigned nb = (unsigned)((n + PB_SCAN_BLOCK - 1) / PB_SCAN_BLOCK);
+        pb_csr_restrict_count_kernel<IT><<<b, 256, 0, st>>>(n, rows, indptr, indices, colmap, indptr_new + 1);
+        pb_scan_sums_kernel<IT><<<nb, 256, 0, st>>>(indptr_new + 1, n, work);
+        pb_scan_top_kernel<IT><<<1, 256, 0, st>>>(work, nb);
+        pb_scan_apply_kernel<IT><<<nb, 256, 0, st>>>(indptr_new + 1, n, work);
+        g_launches += 4;
+    }
+    CK(pbLastError());
+#endif
+    return 0;
+}
+
+extern "C" int pb200_csr_restrict_count(long long nrows_new, const int32_t* d_rows, const void* d_indptr,
+                                        const void* d_indices, int idx_bytes, const int32_t* d_colmap,
+                                        void* d_indptr_new, void* d_work, size_t work_bytes, void* stream) {
+    if (nrows_new < 0 || !d_indptr || !d_colmap || !d_indptr_new || (nrows_new > 0 && !d_rows))
+        return fail(PB200_EINVAL, "null argument");
+    size_t need = 0;
+    int rc = pb200_csr_restrict_workspace(nrows_new, idx_bytes, &need);
+    if (rc) return rc;
+    if (!d_work || work_bytes < need) return fail(PB200_EINVAL, "workspace too small: %zu < %zu bytes", work_bytes, need);
+    pbStream st = (pbStream)stream;
+    if (idx_bytes == 4)
+        return csr_restrict_count<int>(nrows_new, d_rows, (const int*)d_indptr, (const int*)d_indices, d_colmap,
+                                       (int*)d_indptr_new, (int*)d_work, st);
+    return csr_restrict_count<long long>(nrows_new, d_rows, (const long long*)d_indptr, (const long long*)d_indices,
+                                         d_colmap, (long long*)d_indptr_new, (long long*)d_work, st);
+}
+
+template <class IT>
+static int csr_restrict_fill(long long n, const int* rows, const IT* indptr, const IT* indices, const double* values,
+                             const int* colmap, const IT* indptr_new, IT* indices_new, double* values_new, pbStream st) {
+    ++g_launches;
+#ifdef PB_EMULATE
+    (void)st;
+    for (long long r = 0; r < n; ++r)
+        pb_csr_fill_row<IT>(indptr, indices, values, colmap, rows[r], indptr_new[r], indices_new, values_new);
+#else
+    if (n > 0) {
+        const unsigned b = (unsigned)std::min<long long>((n + 7) / 8, 148LL * 32);
+        pb_csr_restrict_fill_kernel<IT><<<b, 256, 0, st>>>(n, rows, indptr, indices, values, colmap, indptr_new, indices_new,
+                                                          values_new);
+    }
+    CK(pbLastError());
+#endif
+    return 0;
+}
+
+extern "C" int pb200_csr_restrict_fill(long long nrows_new, const int32_t* d_rows, const void* d_indptr,
+                                       const void* d_indices, const double* d_values, int idx_bytes,
+                                       const int32_t* d_colmap, const void* d_indptr_new, void* d_indices_new,
+                                       double* d_values_new, void* stream) {
+    if (nrows_new < 0 || !d_indptr || !d_colmap || !d_indptr_new) return fail(PB200_EINVAL, "null argument");
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
+    pbStream st = (pbStream)stream;
+    if (idx_bytes == 4)
+        return csr_restrict_fill<int>(nrows_new, d_rows, (const int*)d_indptr, (const int*)d_indices, d_values, d_colmap,
+                                      (const int*)d_indptr_new, (int*)d_indices_new, d_values_new, st);
+    return csr_restrict_fill<long long>(nrows_new, d_rows, (const long long*)d_indptr, (const long long*)d_indices, d_values,
+                                        d_colmap, (const long long*)d_indptr_new, (long long*)d_indices_new, d_values_new, st);
+}
+
+template <class IT>
+static int csr_matvec(long long n, const IT* indptr, const IT* indices, const double* values, const double* x,
+                      const double* y_in, double alpha, double* y_out, pbStream st) {
+    ++g_launches;
+#ifdef PB_EMULATE
+    (void)st;
+    for (long long r = 0; r < n; ++r)
+        y_out[r] = (y_in ? y_in[r] : 0.0) + alpha * pb_csr_row_dot<IT>(indptr, indices, values, x, r);
+#else
+    if (n > 0) {
+        const unsigned b = (unsigned)std::min<long long>((n + 7) / 8, 148LL * 32);
+        pb_csr_matvec_kernel<IT><<<b, 256, 0, st>>>(n, indptr, indices, values, x, y_in, alpha, y_out);
+    }
+    CK(pbLastError());
+#endif
+    return 0;
+}
+
+extern "C" int pb200_csr_matvec(long long nrows, const void* d_indptr, const void* d_indices, const double* d_values,
+                                int idx_bytes, const double* d_x, const double* d_y_in, double alpha, double* d_y_out,
+                                void* stream) {
+    if (nrows < 0 || !d_indptr || !d_x || !d_y_out) return fail(PB200_EINVAL, "null argument");
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
+    pbStream st = (pbStream)stream;
+    if (idx_bytes == 4)
+        return csr_matvec<int>(nrows, (const int*)d_indptr, (const int*)d_indices, d_values, d_x, d_y_in, alpha, d_y_out, st);
+    return csr_matvec<long long>(nrows, (const long long*)d_indptr, (const long long*)d_indices, d_values, d_x, d_y_in,
+                                 alpha, d_y_out, st);
+}
+
+extern "C" int pb200_vec_gather(long long n, const int32_t* d_idx, const double* d_in, double* d_out, void* stream) {
+    if (n < 0 || (n > 0 && (!d_idx || !d_in || !d_out))) return fail(PB200_EINVAL, "null argument");
+    ++g_launches;
+#ifdef PB_EMULATE
+    (void)stream;
+    for (long long k = 0; k < n; ++k) d_out[k] = d_in[d_idx[k]];
+#else
+    if (n > 0) {
+        const unsigned b = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 32);
+        pb_gather_kernel<<<b, 256, 0, (pbStream)stream>>>(n, d_idx, d_in, d_out);
+    }
+    CK(pbLastError());
+#endif
+    return 0;
+}
+
+extern "C" int pb200_vec_scatter(long long n, const int32_t* d_idx, const double* d_in, double* d_out, void* stream) {
+    if (n < 0 || (n > 0 && (!d_idx || !d_in || !d_out))) return fail(PB200_EINVAL, "null argument");
+    ++g_launches;
+#ifdef PB_EMULATE
+    (void)stream;
+    for (long long k = 0; k < n; ++k) d_out[d_idx[k]] = d_in[k];
+#else
+    if (n > 0) {
+        const unsigned b = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 32);
+        pb_scatter_kernel<<<b, 256, 0, (pbStream)stream>>>(n, d_idx, d_in, d_out);
+    }
+    CK(pbLastError());
+#endif
     return 0;
 }
 

@@ -51,6 +51,16 @@ class NurbsFunc(_SplineFuncBase):
     def output_shape(self):
         return () if self._isscalar else (self.dim,)
 
+    def boundary(self, bdspec):
+        """One side of the boundary as a :class:`NurbsFunc` (``pyiga/geometry.py:188-209``)."""
+        from .bspline import _parse_bdspec
+        axis, side = _parse_bdspec(bdspec, self.sdim)
+        slices = self.sdim * [slice(None)]
+        slices[axis] = 0 if side == 0 else -1
+        kvs = list(self.kvs)
+        del kvs[axis]
+        return NurbsFunc(kvs, self.coeffs[tuple(slices)], weights=None, premultiplied=True)
+
     def coeffs_weights(self):
         """Non-premultiplied coefficients and the weights."""
         W = self.coeffs[..., -1]

@@ -43,6 +43,12 @@ class EmuBackend:
     def nbytes(self, buf):
         return buf.nbytes
 
+    def size(self, buf):
+        return int(buf.size)
+
+    def itemsize(self, buf):
+        return int(buf.itemsize)
+
     def stream(self):
         return 0
 

@@ -19,6 +19,7 @@ import sys
 
 import numpy as np
 import scipy.sparse
+import scipy.sparse.linalg
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
@@ -42,6 +43,13 @@ def save_csr(name, A):
     A.sort_indices()
     np.savez_compressed(os.path.join(HERE, name), data=A.data, indices=A.indices.astype(np.int32),
                         indptr=A.indptr.astype(np.int32), shape=np.array(A.shape))
+
+
+def save_csr_into(out, name, A):
+    A = scipy.sparse.csr_matrix(A)
+    A.sort_indices()
+    out[name + '_indptr'], out[name + '_indices'], out[name + '_data'] = A.indptr, A.indices, A.data
+    out[name + '_shape'] = np.array(A.shape)
 
 
 def geo_pack(prefix, geo, out):
@@ -184,6 +192,60 @@ def main():
     kvs, _ = cases['a2_qa']
     out['vv_divdiv2_bsr'] = assemble.divdiv(kvs, geos['bqa'], layout='packed', format='bsr').toarray()
     out['vv_rhs2'] = assemble.assemble('inner(g, v) * dx', kvs, geo=geos['qa'], bfuns=[('v', 2)], g=lambda x, y: (x, -y))
+
+    # ---- 9. essential boundary conditions (test/test_assemble.py:251-281,497-505, test/test_solve.py) ---
+    from pyiga import approx
+    kvs2 = (bspline.make_knots(3, 0.0, 1.0, 5), bspline.make_knots(2, 0.0, 1.0, 8))
+    out['bc_bd_bottom'] = assemble.boundary_dofs(kvs2, 'bottom', ravel=True)
+    out['bc_bd_right'] = assemble.boundary_dofs(kvs2, 'right')
+    out['bc_bd_left_flip'] = assemble.boundary_dofs(kvs2, 'left', ravel=True, flip=(True,))
+    kvs3b = (bspline.make_knots(2, 0.0, 1.0, 3), bspline.make_knots(3, 0.0, 1.0, 4), bspline.make_knots(2, 0.0, 1.0, 2))
+    out['bc_bd3_front'] = assemble.boundary_dofs(kvs3b, 'front', ravel=True)
+    out['bc_bd3_top'] = assemble.boundary_dofs(kvs3b, (1, 1))
+    out['bc_cells3_back'] = assemble.boundary_cells(kvs3b, 'back', ravel=True)
+    # Poisson on the NURBS quarter annulus, Dirichlet data on all sides (test/test_solve.py)
+    kvsP = 2 * (bspline.make_knots(3, 0.0, 1.0, 10),)
+    geoP = geometry.quarter_annulus()
+    gP = lambda x, y: np.cos(x + y) + np.exp(y - x)
+    fP = lambda x, y: 2 * (np.cos(x + y) - np.exp(y - x))
+    idx, val = assemble.compute_dirichlet_bcs(kvsP, geoP, ('all', gP))
+    out['bc_p2_idx'], out['bc_p2_val'] = idx, val
+    i1, v1 = assemble.compute_dirichlet_bc(kvsP, geoP, 'top', gP)
+    out['bc_p2_top_idx'], out['bc_p2_top_val'] = i1, v1
+    rhs = assemble.inner_products(kvsP, fP, f_physical=True, geo=geoP).ravel()
+    A = assemble.stiffness(kvsP, geo=geoP)
+    LS = assemble.RestrictedLinearSystem(A, rhs, (idx, val))
+    save_csr_into(out, 'bc_p2_A', LS.A)
+    out['bc_p2_b'] = LS.b
+    u = LS.complete(scipy.sparse.linalg.spsolve(LS.A.tocsc(), LS.b))
+    out['bc_p2_u'] = u
+    out['bc_p2_uex'] = approx.interpolate(kvsP, gP, geo=geoP)
+    # 3D, two sides, vector-valued Dirichlet data for a blocked 3-component system, elim_rows
+    kvs3, _ = cases['a3_tb']
+    g3 = geos['tnb']
+    i3, v3 = assemble.compute_dirichlet_bcs(kvs3, g3, [('front', lambda x, y, z: x * y + z), ((2, 1), 1.5)])
+    out['bc_3d_idx'], out['bc_3d_val'] = i3, v3
+    iv, vv = assemble.compute_dirichlet_bc(kvs3, g3, 'bottom', lambda x, y, z: (x, y * z, 1.0 + z))
+    out['bc_3d_vec_idx'], out['bc_3d_vec_val'] = iv, vv
+    A3 = assemble.stiffness(kvs3, geo=g3) + assemble.mass(kvs3, geo=g3)
+    b3 = np.cos(np.arange(A3.shape[0]) * 0.37)
+    LS3 = assemble.RestrictedLinearSystem(A3, b3, (i3, v3))
+    save_csr_into(out, 'bc_3d_A', LS3.A)
+    out['bc_3d_b'] = LS3.b
+    elim_rows = np.arange(3, A3.shape[0], 7)[:i3.size]
+    LS3e = assemble.RestrictedLinearSystem(A3, 0.5, (i3, 2.0), elim_rows=elim_rows)
+    save_csr_into(out, 'bc_3de_A', LS3e.A)
+    out['bc_3de_b'], out['bc_3de_rows'] = LS3e.b, elim_rows
+    xf = np.sin(np.arange(LS3.A.shape[0]) * 0.11)
+    out['bc_3d_complete'] = LS3.complete(xf)
+    out['bc_3d_extend'] = LS3.extend(xf)
+    out['bc_3d_restrict'] = LS3.restrict(b3)
+    save_csr_into(out, 'bc_3d_restrM', LS3.restrict_matrix(assemble.mass(kvs3, geo=g3)))
+    # 1D model problem (test/test_assemble.py:497-505)
+    kv1 = bspline.make_knots(2, 0.0, 1.0, 10)
+    out['bc_1d_f'] = assemble.inner_products(kv1, lambda x: 1.0 + x)
+    out['bc_1d_interp'] = approx.interpolate(kv1, lambda x: 0.5 * x * (3 - x))
+    out['bc_interp3'] = approx.interpolate(kvs3, lambda x, y, z: np.sin(x) * y + z * z, geo=g3)
 
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')

@@ -397,3 +397,113 @@ def check_vector_forms(ref):
     assert_close_rel(A.toarray(), ref['vv_divdiv2_bsr'], what='divdiv')
     f = assemble.assemble('inner(g, v) * dx', kvs, geo=make_geo(ref, 'qa'), bfuns=[('v', 2)], g=lambda x, y: (x, -y))
     assert_close_rel(f, ref['vv_rhs2'], what='vector-valued load vector')
+
+
+def _ref_csr_named(ref, name):
+    import scipy.sparse
+    return scipy.sparse.csr_matrix((ref[name + '_data'], ref[name + '_indices'], ref[name + '_indptr']),
+                                   shape=tuple(ref[name + '_shape']))
+
+
+def _assert_csr_equal(A, R, what, rtol=RTOL):
+    A = A.tocsr()
+    assert A.shape == R.shape, what
+    assert A.has_sorted_indices or True
+    assert np.array_equal(A.indptr, R.indptr), what + ': indptr'
+    assert np.array_equal(A.indices, R.indices), what + ': indices'
+    assert_close_rel(A.data, R.data, rtol=rtol, what=what)
+
+
+def check_boundary_conditions(ref):
+    """boundary dofs, Dirichlet data by interpolation, RestrictedLinearSystem
+    (reference: pyiga/assemble.py:342-652; tests test_assemble.py:251-281,497-505, test_solve.py)"""
+    import scipy.sparse.linalg
+    from pyiga_b200 import approx, assemble, bspline, geometry
+    kvs2 = (bspline.make_knots(3, 0.0, 1.0, 5), bspline.make_knots(2, 0.0, 1.0, 8))
+    assert np.array_equal(assemble.boundary_dofs(kvs2, 'bottom', ravel=True), ref['bc_bd_bottom'])
+    assert np.array_equal(assemble.boundary_dofs(kvs2, 'bottom', ravel=True), np.arange(10))
+    assert np.array_equal(assemble.boundary_dofs(kvs2, 'right'), ref['bc_bd_right'])
+    assert np.array_equal(assemble.boundary_dofs(kvs2, 'left', ravel=True, flip=(True,)), ref['bc_bd_left_flip'])
+    kvs3b = (bspline.make_knots(2, 0.0, 1.0, 3), bspline.make_knots(3, 0.0, 1.0, 4), bspline.make_knots(2, 0.0, 1.0, 2))
+    assert np.array_equal(assemble.boundary_dofs(kvs3b, 'front', ravel=True), ref['bc_bd3_front'])
+    assert np.array_equal(assemble.boundary_dofs(kvs3b, (1, 1)), ref['bc_bd3_top'])
+    assert np.array_equal(assemble.boundary_cells(kvs3b, 'back', ravel=True), ref['bc_cells3_back'])
+    for bad in [(3, 0), (0, 2), 'nowhere']:
+        try:
+            assemble.boundary_dofs(kvs3b, bad)
+        except (ValueError, TypeError):
+            pass
+        else:
+            raise AssertionError('invalid bdspec accepted: %r' % (bad,))
+
+    # the identity-map case of the reference's own test (test_assemble.py:264-281)
+    kvs = (bspline.make_knots(3, 0.0, 1.0, 5), bspline.make_knots(2, 0.0, 1.0, 3))
+    geo = geometry.identity(kvs)
+    ny, nx = (kv.numdofs for kv in kvs)
+    one = lambda x, y: 1.0
+    for bd, want in [((0, 0), range(nx)), ((0, 1), range((ny - 1) * nx, ny * nx)), ((1, 0), range(0, ny * nx, nx)),
+                     ((1, 1), range(nx - 1, nx - 1 + ny * nx, nx))]:
+        idx, val = assemble.compute_dirichlet_bc(kvs, geo, bd, one)
+        assert np.array_equal(idx, list(want)) and np.allclose(val, 1.0, rtol=0, atol=1e-13)
+
+    # Poisson on the quarter annulus (test_solve.py)
+    kvsP = 2 * (bspline.make_knots(3, 0.0, 1.0, 10),)
+    geoP = geometry.quarter_annulus()
+    gP = lambda x, y: np.cos(x + y) + np.exp(y - x)
+    fP = lambda x, y: 2 * (np.cos(x + y) - np.exp(y - x))
+    idx, val = assemble.compute_dirichlet_bcs(kvsP, geoP, ('all', gP))
+    assert np.array_equal(idx, ref['bc_p2_idx'])
+    assert_close_rel(val, ref['bc_p2_val'], what='Dirichlet values (all sides)')
+    i1, v1 = assemble.compute_dirichlet_bc(kvsP, geoP, 'top', gP)
+    assert np.array_equal(i1, ref['bc_p2_top_idx'])
+    assert_close_rel(v1, ref['bc_p2_top_val'], what='Dirichlet values (top)')
+    assert_close_rel(approx.interpolate(kvsP, gP, geo=geoP), ref['bc_p2_uex'], what='interpolate 2D')
+    rhs = assemble.inner_products(kvsP, fP, f_physical=True, geo=geoP).ravel()
+    for fmt in ('csr', 'mlb'):          # host CSR input and device-resident MLMatrix input
+        A = assemble.stiffness(kvsP, geo=geoP, format=fmt)
+        LS = assemble.RestrictedLinearSystem(A, rhs, (idx, val))
+        _assert_csr_equal(LS.A, _ref_csr_named(ref, 'bc_p2_A'), 'restricted stiffness (%s input)' % fmt)
+        assert_close_rel(LS.b, ref['bc_p2_b'], what='restricted rhs')
+    u = LS.complete(scipy.sparse.linalg.spsolve(LS.A.tocsc(), LS.b))
+    assert_close_rel(u, ref['bc_p2_u'], rtol=1e-10, what='Poisson solution')
+    assert np.sqrt(np.mean((u - ref['bc_p2_uex'].ravel()) ** 2)) < 2e-4
+
+    # 3D: two sides, constants, vector-valued data, elim_rows, helper methods
+    kvs3 = make_space(ref, 'a3_tb')
+    g3 = make_geo(ref, 'tnb')
+    i3, v3 = assemble.compute_dirichlet_bcs(kvs3, g3, [('front', lambda x, y, z: x * y + z), ((2, 1), 1.5)])
+    assert np.array_equal(i3, ref['bc_3d_idx'])
+    assert_close_rel(v3, ref['bc_3d_val'], what='3D Dirichlet values')
+    iv, vv = assemble.compute_dirichlet_bc(kvs3, g3, 'bottom', lambda x, y, z: (x, y * z, 1.0 + z))
+    assert np.array_equal(iv, ref['bc_3d_vec_idx'])
+    assert_close_rel(vv, ref['bc_3d_vec_val'], what='3D vector Dirichlet values')
+    K, M = assemble.stiffness(kvs3, geo=g3), assemble.mass(kvs3, geo=g3)
+    A3 = K + M
+    b3 = np.cos(np.arange(A3.shape[0]) * 0.37)
+    LS3 = assemble.RestrictedLinearSystem(A3, b3, (i3, v3))
+    _assert_csr_equal(LS3.A, _ref_csr_named(ref, 'bc_3d_A'), 'restricted 3D matrix')
+    assert_close_rel(LS3.b, ref['bc_3d_b'], what='restricted 3D rhs')
+    LS3e = assemble.RestrictedLinearSystem(A3, 0.5, (i3, 2.0), elim_rows=ref['bc_3de_rows'])
+    _assert_csr_equal(LS3e.A, _ref_csr_named(ref, 'bc_3de_A'), 'restricted 3D matrix, elim_rows')
+    assert_close_rel(LS3e.b, ref['bc_3de_b'], what='restricted 3D rhs, elim_rows')
+    xf = np.sin(np.arange(LS3.A.shape[0]) * 0.11)
+    assert_close_rel(LS3.complete(xf), ref['bc_3d_complete'], what='complete')
+    assert np.array_equal(LS3.extend(xf), ref['bc_3d_extend'])
+    assert np.array_equal(LS3.restrict(b3), ref['bc_3d_restrict'])
+    assert np.array_equal(LS3.restrict_rhs(b3), ref['bc_3d_restrict'])
+    _assert_csr_equal(LS3.restrict_matrix(M), _ref_csr_named(ref, 'bc_3d_restrM'), 'restrict_matrix')
+    # restricted operator == restriction of the operator (property, any size)
+    y = LS3.A_device.dot(xf)
+    assert_close_rel(y, LS3.restrict_rhs(A3 @ LS3.extend(xf)), what='restricted matvec')
+
+    # 1D model problem -u'' = 1, u(0) = 0, u(1) = 1 (test_assemble.py:497-505)
+    kv1 = bspline.make_knots(2, 0.0, 1.0, 10)
+    assert_close_rel(assemble.inner_products(kv1, lambda x: 1.0 + x), ref['bc_1d_f'], what='1D inner products')
+    assert_close_rel(approx.interpolate(kv1, lambda x: 0.5 * x * (3 - x)), ref['bc_1d_interp'], what='1D interpolate')
+    A1 = assemble.stiffness(kv1)
+    f1 = assemble.inner_products(kv1, lambda x: 1.0)
+    LS1 = assemble.RestrictedLinearSystem(A1, f1, [(0, kv1.numdofs - 1), (0.0, 1.0)])
+    u1 = LS1.complete(np.linalg.solve(LS1.A.toarray(), LS1.b))
+    assert np.linalg.norm(u1 - ref['bc_1d_interp']) < 1e-12
+    assert_close_rel(approx.interpolate(kvs3, lambda x, y, z: np.sin(x) * y + z * z, geo=g3), ref['bc_interp3'],
+                     what='3D interpolate')

@@ -99,3 +99,7 @@ def test_edge_cases(emu, ref):
 
 def test_vector_forms(emu, ref):
     pc.check_vector_forms(ref)
+
+
+def test_boundary_conditions(emu, ref):
+    pc.check_boundary_conditions(ref)

@@ -159,3 +159,7 @@ def test_pipelined_csr_host(cuda):
         # values agree to rounding: which half of a symmetric pair is computed and which is mirrored
         # depends on the row chunking
         assert np.abs(vv.numpy() - A.data).max() <= 1e-13 * np.abs(A.data).max()
+
+
+def test_boundary_conditions(cuda, ref):
+    pc.check_boundary_conditions(ref)
