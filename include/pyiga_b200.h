@@ -217,6 +217,16 @@ PB200_API int pb200_mlb_matvec(const pb200_mlstruct* s, int row0_begin, int row0
 PB200_API int pb200_kron_matvec(int d, const double* const* d_factors, const int* rows, const int* cols,
                       const double* d_x, double* d_y, double* d_tmp, void* stream);
 
+/* ---- partial-row assembly --------------------------------------------------------------------------
+ * Replaces _assemble_partial_rows (pyiga/_hdiscr.py:5-12): MLStructure.nonzeros_for_rows
+ * (pyiga/mlmatrix.py:150-185) + multi_entries + COO->CSR for a list of matrix rows (hierarchical /
+ * adaptive callers).  Phase 1 (host, integer closed form): h_indptr[0..n] = prefix sums of the
+ * pattern sizes of the rows.  Phase 2 (device): sorted column indices and per-entry quadrature
+ * values of every row; d_indptr is the uploaded phase-1 result in the chosen integer width. */
+PB200_API int pb200_asm_rows_count(const pb200_assembler* a, const int64_t* h_rows, long long n, int64_t* h_indptr);
+PB200_API int pb200_asm_rows_fill(pb200_assembler* a, const int64_t* d_rows, long long n, const void* d_indptr,
+                        void* d_indices, double* d_values, int idx_bytes, void* stream);
+
 /* ---- elimination of constrained dofs on device CSR arrays ----------------------------------------
  * Replaces the selection-matrix products of RestrictedLinearSystem (pyiga/assemble.py:575-652):
  *   A_r = R_free_v A R_free^T  (restrict_matrix, :632-637),  b_r = R_free_v (b - A R_elim^T values) (:616).

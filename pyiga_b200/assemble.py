@@ -71,6 +71,32 @@ def assemble_entries(asm, symmetric=False, format='csr', layout='blocked'):
     return asm.assemble_csr().asformat(format)
 
 
+def assemble_partial_rows(asm, row_indices, restrict=False):
+    """Submatrix which contains only the given rows (``_assemble_partial_rows``,
+    ``pyiga/_hdiscr.py:5-12``): CSR matrix of the full shape whose other rows are empty or, with
+    `restrict`, of shape ``(len(row_indices), ncols)`` with the rows in the given order.  The pattern
+    of a row is a closed form of the per-axis band tables, so no index lists are built on the host;
+    the values come from the per-entry quadrature kernel."""
+    import scipy.sparse
+    if not hasattr(asm, 'dev'):
+        raise TypeError('assemble_partial_rows needs a pyiga_b200 device assembler, got %r' % type(asm))
+    rows = np.asarray(row_indices, dtype=np.int64).ravel()
+    shape = tuple(int(np.prod([kv.numdofs for kv in kvs], dtype=np.int64)) for kvs in (asm.kvs[1], asm.kvs[0]))
+    if not restrict:
+        rows = np.unique(rows)
+    be = asm.dev.be
+    indptr, indices, values = (be.to_host(x) for x in asm.dev.rows_csr_device(rows))
+    if restrict:
+        A = scipy.sparse.csr_matrix((values, indices, indptr), shape=(rows.size, shape[1]))
+    else:
+        counts = np.zeros(shape[0], dtype=indptr.dtype)
+        counts[rows] = np.diff(indptr)
+        full = np.concatenate(([0], np.cumsum(counts))).astype(indptr.dtype)
+        A = scipy.sparse.csr_matrix((values, indices, full), shape=shape)
+    A.has_sorted_indices = True
+    return A
+
+
 def assemble_entries_vec(asm, symmetric=False, format='csr', layout='blocked'):
     """Vector-valued forms (``pyiga/assemble.py:761-810``).  `layout='blocked'`: a k_test x k_trial
     block matrix of scalar matrices; `'packed'`: every scalar entry becomes a small k_test x k_trial

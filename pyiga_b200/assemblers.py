@@ -233,6 +233,26 @@ class DeviceAssembler:
         labels = [t for t in names.value.decode().split(';') if t]
         return [(labels[i], float(ms[i])) for i in range(min(n.value, len(labels)))]
 
+    def rows_csr_device(self, rows):
+        """Device CSR arrays (indptr, indices, values) of the given matrix rows, values by per-entry
+        quadrature (``pb200_asm_rows_count`` / ``pb200_asm_rows_fill``)."""
+        be = self.be
+        rows = np.ascontiguousarray(rows, dtype=np.int64).ravel()
+        n = rows.size
+        h_indptr = np.zeros(n + 1, dtype=np.int64)
+        _device.check(be.lib.pb200_asm_rows_count(self.handle, rows.ctypes.data, n, h_indptr.ctypes.data))
+        nnz = int(h_indptr[-1])
+        ncols = int(np.prod([kv.numdofs for kv in self.kvs[0]], dtype=np.int64))
+        idt = np.int32 if max(nnz, ncols) < 2 ** 31 else np.int64
+        d_indptr = be.from_host(h_indptr.astype(idt))
+        d_indices, d_values = be.empty(nnz, idt), be.empty(nnz)
+        if n:
+            d_rows = be.from_host(rows)
+            _device.check(be.lib.pb200_asm_rows_fill(self.handle, be.ptr(d_rows), n, be.ptr(d_indptr), be.ptr(d_indices),
+                                                     be.ptr(d_values), np.dtype(idt).itemsize, be.stream()))
+            be.synchronize()
+        return d_indptr, d_indices, d_values
+
     def multi_entries_device(self, ij):
         be = self.be
         ij = np.ascontiguousarray(ij, dtype=np.uint64).reshape(-1, 2)

@@ -1483,6 +1483,64 @@ extern "C" int pb200_asm_multi_entries(pb200_assembler* a, const uint64_t* d_ij,
     return 0;
 }
 
+extern "C" int pb200_asm_rows_count(const pb200_assembler* a, const int64_t* h_rows, long long n, int64_t* h_indptr) {
+    if (!a || n < 0 || !h_indptr || (n > 0 && !h_rows)) return fail(PB200_EINVAL, "null argument");
+    if (a->arity != 2) return fail(PB200_EINVAL, "partial-row assembly needs a bilinear form (arity 2)");
+    long long nrows_total = 1;
+    for (int k = 0; k < a->dim; ++k) nrows_total *= a->ml.Nv[k];
+    h_indptr[0] = 0;
+    for (long long r = 0; r < n; ++r) {
+        long long I = h_rows[r];
+        if (I < 0 || I >= nrows_total) return fail(PB200_EINVAL, "row index %lld out of range [0,%lld)", I, nrows_total);
+        long long cnt = 1;
+        for (int k = a->dim - 1; k >= 0; --k) {
+            const int i = (int)(I % a->ml.Nv[k]);
+            I /= a->ml.Nv[k];
+            cnt *= a->hax[k].row_start[i + 1] - a->hax[k].row_start[i];
+        }
+        h_indptr[r + 1] = h_indptr[r] + cnt;
+    }
+    return 0;
+}
+
+template <int DIM, class IdxT>
+static void k_rows_fill(const PbEntryParams& prm, const long long* rows, long long n, const IdxT* indptr, IdxT* indices,
+                        double* values, pbStream st) {
+    ++g_launches;
+#ifdef PB_EMULATE
+    (void)st;
+    for (long long r = 0; r < n; ++r)
+        for (long long e = 0; e < (long long)(indptr[r + 1] - indptr[r]); ++e)
+            pb_row_entry<DIM, IdxT>(prm, (unsigned long long)rows[r], (long long)indptr[r], (int)e, indices, values);
+#else
+    const unsigned blocks = (unsigned)std::min<long long>(n, 148LL * 64);
+    pb_rows_fill_kernel<DIM, IdxT><<<blocks, 128, 0, st>>>(prm, rows, indptr, n, indices, values);
+#endif
+}
+
+extern "C" int pb200_asm_rows_fill(pb200_assembler* a, const int64_t* d_rows, long long n, const void* d_indptr,
+                                   void* d_indices, double* d_values, int idx_bytes, void* stream) {
+    if (!a || n < 0 || (n > 0 && (!d_rows || !d_indptr))) return fail(PB200_EINVAL, "null argument");
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
+    if (a->arity != 2) return fail(PB200_EINVAL, "partial-row assembly needs a bilinear form (arity 2)");
+    if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
+    if (n == 0) return 0;
+    CK(pbSetDevice(a->device));
+    PbEntryParams prm;
+    fill_entry_params(a, prm);
+    pbStream st = (pbStream)stream;
+    const long long* rows = reinterpret_cast<const long long*>(d_rows);
+    if (a->dim == 2) {
+        if (idx_bytes == 4) k_rows_fill<2, int>(prm, rows, n, (const int*)d_indptr, (int*)d_indices, d_values, st);
+        else k_rows_fill<2, long long>(prm, rows, n, (const long long*)d_indptr, (long long*)d_indices, d_values, st);
+    } else {
+        if (idx_bytes == 4) k_rows_fill<3, int>(prm, rows, n, (const int*)d_indptr, (int*)d_indices, d_values, st);
+        else k_rows_fill<3, long long>(prm, rows, n, (const long long*)d_indptr, (long long*)d_indices, d_values, st);
+    }
+    CK(pbLastError());
+    return 0;
+}
+
 extern "C" int pb200_asm_assemble_mlb_entrywise(pb200_assembler* a, int row0_begin, int row0_end, double* d_out, void* stream) {
     if (!a || !d_out) return fail(PB200_EINVAL, "null argument");
     if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");

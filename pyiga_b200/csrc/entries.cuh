@@ -111,7 +111,46 @@ PB_HD double pb_entry_mlb(const PbEntryParams& prm, long long mu0_begin, long lo
     return pb_entry<DIM>(prm, I, J);
 }
 
+// Partial-row assembly: entry e of requested row I.  The row's pattern is the Cartesian product of
+// the per-axis column ranges [jmin_k[i_k], jmin_k[i_k] + nb_k), enumerated with the last axis
+// fastest, i.e. in increasing column order (what MLStructure.nonzeros_for_rows lists row by row,
+// pyiga/mlmatrix.py:150-185); the value is the same per-entry quadrature as multi_entries.
+template <int DIM, class IdxT>
+PB_HD void pb_row_entry(const PbEntryParams& prm, unsigned long long I, long long base, int e, IdxT* indices, double* values) {
+    int i[3] = {0, 0, 0}, nb[3] = {1, 1, 1}, jm[3] = {0, 0, 0};
+    unsigned long long r = I;
+    for (int k = DIM - 1; k >= 0; --k) {
+        i[k] = (int)(r % (unsigned long long)prm.ax[k].Nv);
+        r /= (unsigned long long)prm.ax[k].Nv;
+        nb[k] = prm.ax[k].row_start[i[k] + 1] - prm.ax[k].row_start[i[k]];
+        jm[k] = prm.ax[k].jmin[i[k]];
+    }
+    int t = e;
+    unsigned long long J = 0, mul = 1;
+    for (int k = DIM - 1; k >= 0; --k) {
+        J += mul * (unsigned long long)(jm[k] + t % nb[k]);
+        t /= nb[k];
+        mul *= (unsigned long long)prm.ax[k].Nu;
+    }
+    indices[base + e] = (IdxT)J;
+    values[base + e] = pb_entry<DIM>(prm, I, J);
+}
+
 #if defined(__CUDACC__)
+// one block per requested row
+template <int DIM, class IdxT>
+__global__ void __launch_bounds__(128) pb_rows_fill_kernel(const __grid_constant__ PbEntryParams prm,
+                                                           const long long* __restrict__ rows,
+                                                           const IdxT* __restrict__ indptr, long long nrows,
+                                                           IdxT* __restrict__ indices, double* __restrict__ values) {
+    for (long long r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const long long base = (long long)indptr[r];
+        const int cnt = (int)((long long)indptr[r + 1] - base);
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x)
+            pb_row_entry<DIM, IdxT>(prm, (unsigned long long)rows[r], base, e, indices, values);
+    }
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(128) pb_entries_kernel(const __grid_constant__ PbEntryParams prm) {
     const long long stride = (long long)gridDim.x * blockDim.x;

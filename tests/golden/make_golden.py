@@ -247,6 +247,16 @@ def main():
     out['bc_1d_interp'] = approx.interpolate(kv1, lambda x: 0.5 * x * (3 - x))
     out['bc_interp3'] = approx.interpolate(kvs3, lambda x, y, z: np.sin(x) * y + z * z, geo=g3)
 
+    # ---- 10. partial-row assembly (pyiga/_hdiscr.py:5-12) ----------------------------------------------
+    from pyiga import _hdiscr
+    for case, cls in [('a3_mixed', assemblers.StiffnessAssembler3D), ('a2_mixed', assemblers.MassAssembler2D)]:
+        kvs, geo = cases[case]
+        asm = cls(kvs, geo)
+        n = int(np.prod([kv.numdofs for kv in kvs]))
+        rows = np.unique((np.arange(17) * 7919 + 3) % n)
+        out['pr_%s_rows' % case] = rows
+        save_csr_into(out, 'pr_%s' % case, _hdiscr._assemble_partial_rows(asm, rows))
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

@@ -507,3 +507,31 @@ def check_boundary_conditions(ref):
     assert np.linalg.norm(u1 - ref['bc_1d_interp']) < 1e-12
     assert_close_rel(approx.interpolate(kvs3, lambda x, y, z: np.sin(x) * y + z * z, geo=g3), ref['bc_interp3'],
                      what='3D interpolate')
+
+
+def check_partial_rows(ref):
+    """submatrix of a subset of rows (reference: pyiga/_hdiscr.py:5-12)"""
+    from pyiga_b200 import assemble, assemblers
+    for case, cls, gname in [('a3_mixed', assemblers.StiffnessAssembler3D, 'tb'), ('a2_mixed', assemblers.MassAssembler2D, 'bqa')]:
+        kvs = make_space(ref, case)
+        asm = cls(kvs, make_geo(ref, gname))
+        rows = ref['pr_%s_rows' % case]
+        R = _ref_csr_named(ref, 'pr_%s' % case)
+        A = assemble.assemble_partial_rows(asm, rows)
+        _assert_csr_equal(A, R, 'partial rows ' + case)
+        # restricted variant keeps the order (and duplicates) of the request
+        perm = np.concatenate((rows[::-1], rows[:2]))
+        B = assemble.assemble_partial_rows(asm, perm, restrict=True)
+        assert B.shape == (perm.size, R.shape[1])
+        assert abs(B - R[perm]).max() <= RTOL * abs(R).max()
+        # against the full matrix of the fast path
+        full = asm.assemble_csr()
+        assert abs(A[rows] - full[rows]).max() <= RTOL * abs(full).max()
+        E = assemble.assemble_partial_rows(asm, [])
+        assert E.shape == R.shape and E.nnz == 0
+        try:
+            assemble.assemble_partial_rows(asm, [R.shape[0]])
+        except ValueError:
+            pass
+        else:
+            raise AssertionError('out-of-range row accepted')

@@ -103,3 +103,7 @@ def test_vector_forms(emu, ref):
 
 def test_boundary_conditions(emu, ref):
     pc.check_boundary_conditions(ref)
+
+
+def test_partial_rows(emu, ref):
+    pc.check_partial_rows(ref)

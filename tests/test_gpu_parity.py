@@ -163,3 +163,7 @@ def test_pipelined_csr_host(cuda):
 
 def test_boundary_conditions(cuda, ref):
     pc.check_boundary_conditions(ref)
+
+
+def test_partial_rows(cuda, ref):
+    pc.check_partial_rows(ref)
