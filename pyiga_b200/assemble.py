@@ -355,16 +355,16 @@ class RestrictedLinearSystem:
 
 def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatable=[]):
     """Turn a problem description into an assembler object (``pyiga/assemble.py:914-956``)."""
-    if boundary:
-        raise NotImplementedError('boundary integrals are not part of the device path')
     if isinstance(problem, str):
         from . import vform
-        problem = vform.parse_vf(problem, kvs, args=args, bfuns=bfuns, updatable=updatable)
+        problem = vform.parse_vf(problem, kvs, args=args, bfuns=bfuns, boundary=bool(boundary), updatable=updatable)
     from . import vform as _vf
     if isinstance(problem, _vf.VForm):
         problem = _vf.compile_vform(problem)
     if isinstance(problem, type):
         used = {}
+        if boundary:
+            used['boundary'] = bspline._parse_bdspec(boundary, len(kvs))
         for name in list(problem.inputs().keys()) + list(problem.parameters().keys()):
             if name not in args:
                 raise ValueError("required input parameter '%s' missing" % name)

@@ -28,7 +28,9 @@ def _is_spline_geo(geo):
 class DeviceAssembler:
     """Handle on a ``pb200_assembler``: tables, fields and kernels for one (spaces, form, geometry)."""
 
-    def __init__(self, kvs0, kvs1, form, nqp=None, terms=None, nfields=0, symmetric=False):
+    def __init__(self, kvs0, kvs1, form, nqp=None, terms=None, nfields=0, symmetric=False, quad=None):
+        """`quad`: optional ``{axis: (nodes, weights, nodes_per_span)}`` replacing the Gauss rule of
+        an axis (boundary integrals: a single node on the boundary, ``pyiga/quadrature.py:23-31``)."""
         self.be = be = _device.backend()
         kvs0 = tuple(kvs0)
         kvs1 = tuple(kvs1) if kvs1 is not None else kvs0
@@ -39,6 +41,12 @@ class DeviceAssembler:
         self.nqp = int(nqp) if nqp else max(kv.p for kv in kvs0) + 1
         meshes = [kv.mesh for kv in kvs0]
         self.gaussgrid, self.gaussweights = make_tensor_quadrature(meshes, self.nqp)
+        nq_axis = [self.nqp] * dim
+        if quad:
+            grid, wts = list(self.gaussgrid), list(self.gaussweights)
+            for k, (nodes, weights, nq) in quad.items():
+                grid[k], wts[k], nq_axis[k] = np.asarray(nodes, dtype=float), np.asarray(weights, dtype=float), int(nq)
+            self.gaussgrid, self.gaussweights = tuple(grid), tuple(wts)
         self.same_space = all(a is b or a == b for a, b in zip(kvs0, kvs1))
 
         desc = _lib.Desc()
@@ -57,7 +65,7 @@ class DeviceAssembler:
             nodes = np.ascontiguousarray(self.gaussgrid[k], dtype=np.float64)
             weights = np.ascontiguousarray(self.gaussweights[k], dtype=np.float64)
             keep += [nodes, weights]
-            ax.nq, ax.h_nodes, ax.h_weights = self.nqp, _lib.as_double_p(nodes), _lib.as_double_p(weights)
+            ax.nq, ax.h_nodes, ax.h_weights = nq_axis[k], _lib.as_double_p(nodes), _lib.as_double_p(weights)
         if form == _lib.FORM_CUSTOM:
             tarr = (_lib.Term * len(terms))(*[_lib.Term(*t) for t in terms])
             keep.append(tarr)
@@ -335,7 +343,7 @@ class _ScalarAssemblerBase(_AssemblerProtocol):
 class _FormBlock:
     """One scalar form  sum_t c_t d^bt v d^bu u  on the device: tables, coefficient upload, fields."""
 
-    def __init__(self, kvs, nqp, dim, arity, coefs, geo, gaussgrid):
+    def __init__(self, kvs, nqp, dim, arity, coefs, geo, gaussgrid, quad=None):
         self.dim, self.arity, self.kvs = dim, arity, kvs
         self.gaussgrid = gaussgrid
         self._grid_shape = tuple(len(g) for g in gaussgrid)
@@ -346,7 +354,7 @@ class _FormBlock:
                 for ap in ([-1] if bu < 0 else [0] if bu == 0 else range(1, dim + 1)):
                     pairs.add((bp, ap))
         terms = [(f, bp, ap) for f, (bp, ap) in enumerate(sorted(pairs))]
-        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms))
+        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
         self.compute_fields(coefs, geo)
 
     def compute_fields(self, coefs, geo):
@@ -404,9 +412,15 @@ class GenericFormAssembler(_AssemblerProtocol):
         self._geo = geo
         self._args = dict(args)
         self.gaussgrid, _ = make_tensor_quadrature([kv.mesh for kv in kvs], self.nqp)
+        quad = None
+        self._bd = None
+        if getattr(vf, 'boundary', False):
+            kvs, quad = self._setup_boundary(kvs, args.get('boundary'))
         self._grid_shape = tuple(len(g) for g in self.gaussgrid)
         self._X = None
         self._env = {}
+        if self._bd is not None:
+            self._boundary_fields()
         for name, shape, physical, _upd in vf.inputs:
             self._env[name] = self._eval_input(args[name], shape, physical)
         for name, shape in vf.params:
@@ -421,9 +435,70 @@ class GenericFormAssembler(_AssemblerProtocol):
             self.num_components = lambda: self._nc
         self.blocks = {}
         for blk, coefs in self._analyse().items():
-            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid)
+            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid, quad=quad)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
+
+    # ---- boundary integrals --------------------------------------------------------------------
+    def _setup_boundary(self, kvs, boundary):
+        """Integrals over one side of the patch (``pyiga/codegen/cython.py:549-590``,
+        ``quadrature.py:23-31``): the Gauss rule of the normal axis is the single boundary point with
+        weight 1 and only the basis function that does not vanish there takes part.  The device
+        tables get a stand-in for the normal axis — a linear one-span knot vector whose boundary
+        function has the same value (1) and derivative at the boundary point — and the results are
+        sliced down to that function afterwards."""
+        from . import bspline
+        assert boundary is not None, "a boundary integral needs the `boundary` argument"
+        bdax, bdside = bspline._parse_bdspec(boundary, len(kvs))
+        kvn = kvs[bdax]
+        a, b = kvn.support()
+        pt = a if bdside == 0 else b
+        d1 = bspline.active_deriv(kvn, float(pt), 1)[1]
+        slope = abs(d1[0] if bdside == 0 else d1[-1])
+        if slope == 0.0:            # degree 0: constant function, any length will do
+            slope = 1.0 / (b - a)
+        L = 1.0 / slope
+        fake = bspline.KnotVector(np.array([a, a, a + L, a + L] if bdside == 0 else [b - L, b - L, b, b]), 1)
+        self._bd = (bdax, bdside)
+        self.kvs = tuple(tuple(kv for k, kv in enumerate(kvs) if k != bdax) for _ in range(2))
+        grid = list(self.gaussgrid)
+        grid[bdax] = np.array([pt], dtype=float)
+        self.gaussgrid = tuple(grid)
+        quad = {bdax: (grid[bdax], np.ones(1), 1)}
+        return kvs[:bdax] + (fake,) + kvs[bdax + 1:], quad
+
+    def _boundary_fields(self):
+        """surface measure relative to the volume measure, and the outer unit normal, on the face
+        grid: with g = J^-T e_n (the physical gradient of the normal parameter),
+        ds = |det J| |g| dxi_tangential and n = -+ g / |g|."""
+        d = self._vf.dim
+        bdax, bdside = self._bd
+        J = np.asarray(self._geo.grid_jacobian(self.gaussgrid), dtype=float)    # grid + (d, d), xi_0 = last axis
+        g = np.linalg.inv(J)[..., d - 1 - bdax, :]
+        norm = np.sqrt((g * g).sum(axis=-1))
+        self._env['@ds'] = np.ascontiguousarray(norm)
+        sign = -1.0 if bdside == 0 else 1.0
+        self._env['@n'] = np.stack([np.ascontiguousarray(sign * g[..., i] / norm) for i in range(d)])
+
+    def _bd_select(self, arr, arity):
+        """slice the band / dof axis of the stand-in normal axis down to the boundary function"""
+        bdax, bdside = self._bd
+        idx = [slice(None)] * arr.ndim
+        if arity == 2:
+            idx[bdax] = 0 if bdside == 0 else 3     # band entries of the 2 x 2 dense level: (0,0) ... (1,1)
+        else:
+            idx[bdax] = slice(0, 1) if bdside == 0 else slice(1, 2)
+        return np.ascontiguousarray(arr[tuple(idx)])
+
+    def _bd_structure(self):
+        from .mlmatrix import MLStructure
+        return MLStructure.from_kvs(self.kvs[0], self.kvs[1])
+
+    def _bd_matrix(self, b):
+        """MLMatrix over the boundary space of one scalar block"""
+        be = b.dev.be
+        full = be.to_host(b.dev.assemble_mlb()).reshape(tuple(len(x) for x in b.dev.structure.bidx))
+        return MLMatrix(structure=self._bd_structure(), data=self._bd_select(full, 2))
 
     # ---- input evaluation (host side, like the reference) ------------------------------------
     def _physical_points(self):
@@ -492,6 +567,10 @@ class GenericFormAssembler(_AssemblerProtocol):
         return out
 
     def assemble_mlb(self, layout='packed', **kw):
+        if self._bd is not None:
+            if self._vec:
+                raise NotImplementedError('vector-valued boundary forms in MLB format')
+            return self._bd_matrix(self.blocks[(0, 0)])
         if not self._vec:
             return super().assemble_mlb(**kw)
         dev = self.dev
@@ -509,14 +588,19 @@ class GenericFormAssembler(_AssemblerProtocol):
         return X
 
     def assemble_csr(self, layout='blocked', format='csr', **kw):
+        if self._bd is not None and not self._vec:
+            return self._bd_matrix(self.blocks[(0, 0)]).asmatrix('csr')
         if not self._vec:
             return super().assemble_csr(**kw)
         import scipy.sparse
         nc_u, nc_v = self._nc
         ds = self.dev.device_structure
         mats = {}
-        for blk, buf in self._block_mlb().items():
-            mats[blk] = ds.to_csr(buf)
+        if self._bd is not None:
+            mats = {blk: self._bd_matrix(b).asmatrix('csr') for blk, b in self.blocks.items()}
+        else:
+            for blk, buf in self._block_mlb().items():
+                mats[blk] = ds.to_csr(buf)
         ref = next(iter(mats.values()))
         if layout == 'packed':
             data = np.zeros((ref.nnz, nc_v, nc_u))
@@ -537,16 +621,33 @@ class GenericFormAssembler(_AssemblerProtocol):
         if self.arity != 1:
             return None
         be = self.dev.be
+        sel = (lambda a: a) if self._bd is None else (lambda a: self._bd_select(a, 1))
         if not self._vec:
-            return be.to_host(self.dev.assemble_vector_device()).reshape(self.dev.ndofs_test)
-        out = np.zeros(self.dev.ndofs_test + (self._nc[1],))
+            return sel(be.to_host(self.dev.assemble_vector_device()).reshape(self.dev.ndofs_test))
+        out = None
         for (ct, _), b in self.blocks.items():
-            out[..., ct] = be.to_host(b.dev.assemble_vector_device()).reshape(self.dev.ndofs_test)
+            part = sel(be.to_host(b.dev.assemble_vector_device()).reshape(self.dev.ndofs_test))
+            if out is None:
+                out = np.zeros(part.shape + (self._nc[1],))
+            out[..., ct] = part
         return out
+
+    def _bd_lift(self, idx):
+        """raveled indices of the boundary space -> raveled indices of the stand-in full space"""
+        bdax, bdside = self._bd
+        nb = tuple(kv.numdofs for kv in self.kvs[0])
+        multi = list(np.unravel_index(np.asarray(idx, dtype=np.int64), nb)) if nb else []
+        multi.insert(bdax, np.full(np.shape(idx), 0 if bdside == 0 else 1, dtype=np.int64))
+        return np.ravel_multi_index(tuple(multi), self.dev.ndofs_test)
 
     def multi_entries(self, indices):
         if self.arity == 1:
             return self.multi_entries1(indices)
+        if self._bd is not None:
+            if not isinstance(indices, np.ndarray):
+                indices = np.array(list(indices), dtype=np.int64)
+            indices = np.asarray(indices, dtype=np.int64).reshape(-1, 2)
+            indices = np.column_stack((self._bd_lift(indices[:, 0]), self._bd_lift(indices[:, 1])))
         return super().multi_entries(indices)
 
     def multi_entries1(self, indices):

@@ -434,6 +434,11 @@ static bool have_plan(int plan, int P, int Q) { return pb_find_walk(plan, P, Q) 
 
 static int detect_fast_path(const pb200_assembler* a) {
     if (!a->same_space) return 0;
+    if (a->form == PB200_FORM_CUSTOM && a->arity == 1) {    // every axis is contracted on its own
+        for (int k = 0; k < a->dim; ++k)
+            if (!pb_find_walk1(a->hax[k].U.p, a->hax[k].q)) return 0;
+        return 1;
+    }
     const int Q = a->hax[0].q;
     for (int k = 0; k < a->dim; ++k)
         if (a->hax[k].q != Q) return 0;

@@ -20,6 +20,10 @@ OBJ = os.path.join(HERE, '_obj')
 # reference's rule for equal degrees; the other pairs cover mixed-degree spaces (q = max p + 1).
 PQ = [(1, 2), (2, 3), (3, 4), (4, 5), (1, 3), (2, 4), (3, 5), (1, 4), (2, 5)]
 
+# pairs instantiated for linear forms only: the stand-in normal axis of boundary integrals (degree 1,
+# one node) and its companions
+PQ1 = [(1, 1)]
+
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
          '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
@@ -58,6 +62,9 @@ def build(force=False, verbose=False):
     for p, q in PQ:
         jobs.append(('walk_inst.cu', os.path.join(OBJ, 'walk_%d_%d_%s.o' % (p, q, tag)),
                      ['-DPB_P=%d' % p, '-DPB_Q=%d' % q]))
+    for p, q in PQ1:
+        jobs.append(('walk_inst.cu', os.path.join(OBJ, 'walk1_%d_%d_%s.o' % (p, q, tag)),
+                     ['-DPB_P=%d' % p, '-DPB_Q=%d' % q, '-DPB_WALK1_ONLY']))
     if force:
         for _, o, _ in jobs:
             if os.path.exists(o):

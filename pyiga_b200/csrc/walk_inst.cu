@@ -89,6 +89,7 @@ int launch_walk1(const PbWalk1Params* prm, void* stream) {
 struct Registrar {
     Registrar() {
         pb200_register_walk1(PB_P, PB_Q, &launch_walk1);
+#ifndef PB_WALK1_ONLY       // pairs that only occur in linear forms (the one-node axis of boundary integrals)
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_COPY, PB_P, PB_Q, &launch_lane<PbPlanCopy>);
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_FINAL4, PB_P, PB_Q, &launch_lane<PbPlanFinal4>);
         pb200_register_walk(PB_PLAN_LANE_BASE + PB_PLAN_GEN4, PB_P, PB_Q, &launch_lane<PbPlanGen4>);
@@ -102,6 +103,7 @@ struct Registrar {
         pb200_register_walk(PB_PLAN_S1B, PB_P, PB_Q, &launch<PbPlanS1B>);
         pb200_register_walk(PB_PLAN_S2B, PB_P, PB_Q, &launch<PbPlanS2B>);
         pb200_register_walk(PB_PLAN_S1_2D, PB_P, PB_Q, &launch<PbPlanS1_2D>);
+#endif
     }
 };
 Registrar registrar;

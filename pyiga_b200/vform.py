@@ -214,8 +214,14 @@ def _coef_form(v):
 
 
 class Measure(Expr):
-    """dx: the factor |det J| * GaussWeight is applied on the device"""
+    """dx: the factor |det J| * GaussWeight is applied on the device.  ds (boundary integrals): the
+    same factor times the ratio surface / volume measure, which the assembler supplies as '@ds'."""
+    def __init__(self, surface=False):
+        self.surface = surface
+
     def ev(self, env):
+        if self.surface:
+            return _obj((), [Form.const(1.0, env['@ds'])])
         return _obj((), [Form.const(1.0)])
 
 
@@ -414,9 +420,12 @@ class VForm:
     """Abstract description of a variational form (API after ``pyiga/vform.py:162-350``)."""
 
     def __init__(self, dim, geo_dim=None, boundary=False, arity=2, spacetime=False):
-        if boundary or spacetime or (geo_dim is not None and geo_dim != dim):
-            raise NotImplementedError('boundary, surface and space-time forms are not part of the device path')
+        if spacetime or (geo_dim is not None and geo_dim != dim):
+            raise NotImplementedError('surface and space-time forms are not part of the device path')
         self.dim, self.arity = dim, arity
+        self.boundary = bool(boundary)
+        self.ds = Measure(surface=True)         # boundary forms: integrate with `* ds`
+        self.normal = Input('@n', (dim,))       # outer unit normal (boundary forms)
         self.vec = False
         self.exprs = []
         self.inputs = []        # [(name, shape, physical, updatable)]
@@ -492,8 +501,6 @@ def _check_input_field(kvs, f):
 def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
     """Parse a form string like ``'(inner(c * grad(u), grad(v)) + inner(b, grad(u)) * v) * dx'``
     (``pyiga/vform.py:1804-1887``)."""
-    if boundary:
-        raise NotImplementedError('boundary integrals are not part of the device path')
     if not all(hasattr(kv, 'kv') for kv in kvs):
         if all(hasattr(kv, 'kv') for kv in kvs[0]):
             kvs = kvs[0]
@@ -502,7 +509,10 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
     dim = len(kvs)
     words = set(re.findall(r"[^\d\W]\w*", expr))
     if 'ds' in words:
-        raise NotImplementedError('surface integrals are not part of the device path')
+        if 'dx' in words:
+            raise RuntimeError("got both 'dx' and 'ds' - is this a volume or a surface integral?")
+        if not boundary:
+            raise NotImplementedError('surface integrals (manifolds) are not part of the device path')
     if bfuns is None:
         names, comps = sorted(words & {'u', 'v'}), None
     else:
@@ -515,7 +525,7 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
             comps.append(bf[1] if len(bf) > 1 else 1)
     if len(names) not in (1, 2):
         raise ValueError('arity should be 1 or 2')
-    vf = VForm(dim=dim, arity=len(names))
+    vf = VForm(dim=dim, boundary=bool(boundary), arity=len(names))
     loc = {}
     if vf.arity == 1:
         loc[names[0]] = vf.basisfuns(components=tuple(comps) if comps else (None,))
@@ -530,8 +540,11 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
             loc[name] = vf.parameter(name, shape=np.shape(args[name]))
     if 'x' in words and 'x' not in args:
         loc['x'] = vf.Geo
+    if 'n' in words and 'n' not in args:
+        loc['n'] = vf.normal
     ns = dict(globals())
     ns['dx'] = vf.dx
+    ns['ds'] = vf.ds
     ns.update(loc)
     vf.add(eval(expr, ns))
     vf.source = expr

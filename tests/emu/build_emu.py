@@ -50,6 +50,7 @@ def build():
     jobs = [('api.cu', os.path.join(OUT, 'api.o'), [])]
     jobs += [('walk_inst.cu', os.path.join(OUT, 'walk_%d_%d.o' % pq), ['-DPB_P=%d' % pq[0], '-DPB_Q=%d' % pq[1]])
              for pq in PQ]
+    jobs += [('walk_inst.cu', os.path.join(OUT, 'walk1_1_1.o'), ['-DPB_P=1', '-DPB_Q=1', '-DPB_WALK1_ONLY'])]
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(_cc, jobs))
     r = subprocess.run([CXX, '-shared', '-o', LIB] + objs, capture_output=True, text=True)

@@ -257,6 +257,16 @@ def main():
         out['pr_%s_rows' % case] = rows
         save_csr_into(out, 'pr_%s' % case, _hdiscr._assemble_partial_rows(asm, rows))
 
+    # ---- 11. boundary integrals (pyiga/assemble.py:899-940, codegen/cython.py:549-590) -----------------
+    from helpers import BFORMS
+    for name, (form, bfuns, inputs, case, gname, bd) in BFORMS.items():
+        kvs, _ = cases[case]
+        R = assemble.assemble(form, kvs, geo=geos[gname], bfuns=bfuns, boundary=bd, **inputs)
+        if scipy.sparse.issparse(R):
+            save_csr_into(out, 'bf_%s' % name, R)
+        else:
+            out['bf_%s' % name] = np.asarray(R)
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

@@ -92,3 +92,15 @@ VECFORMS = {
     'stokes_like2': ('(inner(grad(u), grad(v)) + c * inner(u, v)) * dx', [('u', 2), ('v', 2)],
                      {'c': lambda x, y: 1.0 + x * y}, 'a2_mixed', 'bqa'),
 }
+
+# boundary integrals: name -> (form, bfuns or None, inputs, space case, geometry, bdspec)
+BFORMS = {
+    'robin2_left': ('u * v * ds', None, {}, 'a2_qa', 'qa', 'left'),
+    'robin2_top': ('c * u * v * ds', None, {'c': lambda x, y: 1.0 + x * y}, 'a2_mixed', 'bqa', 'top'),
+    'neumann2': ('g * v * ds', None, {'g': lambda x, y: x + y}, 'a2_qa', 'qa', (0, 1)),
+    'flux2': ('inner(grad(u), n) * v * ds', None, {}, 'a2_qa', 'qa', 'right'),
+    'flux3_front': ('inner(grad(u), n) * v * ds', None, {}, 'a3_mixed', 'tb', 'front'),
+    'nitsche3': ('(inner(grad(u), n) * v + inner(grad(v), n) * u + 3.0 * u * v) * ds', None, {}, 'a3_nurbs', 'tnb', (1, 1)),
+    'neumann3': ('inner(g, n) * v * ds', None, {'g': lambda x, y, z: (x, y * z, 1.0)}, 'a3_tb', 'tnb', 'left'),
+    'traction2': ('inner(g, v) * ds', [('v', 2)], {'g': lambda x, y: (x, -y)}, 'a2_qa', 'qa', 'bottom'),
+}

@@ -535,3 +535,32 @@ def check_partial_rows(ref):
             pass
         else:
             raise AssertionError('out-of-range row accepted')
+
+
+def check_boundary_forms(ref):
+    """SURVEY 8(f) rank 4: integrals over one side of the patch (`boundary=` of assemble.assemble;
+    reference: pyiga/assemble.py:899-940, pyiga/codegen/cython.py:549-590, quadrature.py:23-31)"""
+    import scipy.sparse
+    from helpers import BFORMS
+    from pyiga_b200 import assemble
+    for name, (form, bfuns, inputs, case, gname, bd) in BFORMS.items():
+        kvs = make_space(ref, case)
+        got = assemble.assemble(form, kvs, geo=make_geo(ref, gname), bfuns=bfuns, boundary=bd, **inputs)
+        if 'bf_%s_indptr' % name in ref:
+            R = _ref_csr_named(ref, 'bf_%s' % name)
+            assert scipy.sparse.issparse(got) and got.shape == R.shape, name
+            assert abs(got - R).max() <= RTOL * abs(R).max(), 'boundary form %s: %.3e' % (name, abs(got - R).max())
+            # entries the reference stores are the pattern of the boundary space
+            G = got.tocsr(); G.sort_indices()
+            assert np.array_equal(G.indptr, R.indptr) and np.array_equal(G.indices, R.indices), name
+        else:
+            assert_close_rel(got, ref['bf_%s' % name], what='boundary form ' + name)
+    # the protocol on a boundary assembler: kvs without the normal axis, entries of the face space
+    form, bfuns, inputs, case, gname, bd = BFORMS['flux3_front']
+    kvs = make_space(ref, case)
+    asm = assemble.instantiate_assembler(form, kvs, dict(inputs, geo=make_geo(ref, gname)), bfuns, boundary=bd)
+    assert len(asm.kvs[0]) == 2 and asm.kvs[0] == tuple(kvs[1:])
+    R = _ref_csr_named(ref, 'bf_flux3_front')
+    ij = np.array([(0, 0), (3, 4), (R.shape[0] - 1, R.shape[0] - 2), (0, R.shape[0] - 1)])
+    want = np.asarray(R[ij[:, 0], ij[:, 1]]).ravel()
+    assert np.abs(asm.multi_entries(ij) - want).max() <= RTOL * abs(R).max()

@@ -107,3 +107,7 @@ def test_boundary_conditions(emu, ref):
 
 def test_partial_rows(emu, ref):
     pc.check_partial_rows(ref)
+
+
+def test_boundary_forms(emu, ref):
+    pc.check_boundary_forms(ref)

@@ -167,3 +167,7 @@ def test_boundary_conditions(cuda, ref):
 
 def test_partial_rows(cuda, ref):
     pc.check_partial_rows(ref)
+
+
+def test_boundary_forms(cuda, ref):
+    pc.check_boundary_forms(ref)
