@@ -359,7 +359,9 @@ def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatab
         from . import vform
         problem = vform.parse_vf(problem, kvs, args=args, bfuns=bfuns, boundary=bool(boundary), updatable=updatable)
     from . import vform as _vf
+    num_spaces = 1
     if isinstance(problem, _vf.VForm):
+        num_spaces = problem.num_spaces()
         problem = _vf.compile_vform(problem)
     if isinstance(problem, type):
         used = {}
@@ -369,7 +371,10 @@ def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatab
             if name not in args:
                 raise ValueError("required input parameter '%s' missing" % name)
             used[name] = args[name]
-        return problem(kvs, **used)
+        if num_spaces <= 1:
+            return problem(kvs, **used)
+        assert num_spaces == 2, 'no more than two spaces allowed'
+        return problem(kvs[0], kvs[1], **used)
     raise TypeError("invalid type for 'problem': {}".format(type(problem)))
 
 

@@ -343,7 +343,7 @@ class _ScalarAssemblerBase(_AssemblerProtocol):
 class _FormBlock:
     """One scalar form  sum_t c_t d^bt v d^bu u  on the device: tables, coefficient upload, fields."""
 
-    def __init__(self, kvs, nqp, dim, arity, coefs, geo, gaussgrid, quad=None):
+    def __init__(self, kvs, nqp, dim, arity, coefs, geo, gaussgrid, quad=None, kvs_test=None):
         self.dim, self.arity, self.kvs = dim, arity, kvs
         self.gaussgrid = gaussgrid
         self._grid_shape = tuple(len(g) for g in gaussgrid)
@@ -354,7 +354,7 @@ class _FormBlock:
                 for ap in ([-1] if bu < 0 else [0] if bu == 0 else range(1, dim + 1)):
                     pairs.add((bp, ap))
         terms = [(f, bp, ap) for f, (bp, ap) in enumerate(sorted(pairs))]
-        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
+        self.dev = DeviceAssembler(kvs, kvs_test or kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
         self.compute_fields(coefs, geo)
 
     def compute_fields(self, coefs, geo):
@@ -398,23 +398,33 @@ class GenericFormAssembler(_AssemblerProtocol):
     """
     _vf = None
 
-    def __init__(self, kvs, **args):
+    def __init__(self, kvs, kvs_test=None, **args):
         vf = self._vf
         kvs = tuple(kvs)
         d = vf.dim
         assert len(kvs) == d, "Assembler requires %d knot vectors" % d
+        if vf.num_spaces() == 2:
+            # Petrov-Galerkin: trial functions in `kvs` (space 0, columns), test functions in
+            # `kvs_test` (space 1, rows), on the same mesh (``pyiga/assemble.py:947-951``)
+            assert kvs_test is not None and len(kvs_test) == d, "Assembler requires %d knot vectors" % d
+            kvs_test = tuple(kvs_test)
+            assert all(np.array_equal(a.mesh, b.mesh) for a, b in zip(kvs, kvs_test)), 'both spaces must share the mesh'
+        else:
+            kvs_test = None
         geo = args['geo']
         assert geo.sdim == d, "Geometry has wrong source dimension"
         assert geo.dim == d, "Geometry has wrong dimension"
         self.arity = vf.arity
-        self.nqp = max(kv.p for kv in kvs) + 1
-        self.kvs = (kvs, kvs)
+        self.nqp = max(kv.p for kv in kvs + (kvs_test or ())) + 1
+        self.kvs = (kvs, kvs_test or kvs)
         self._geo = geo
         self._args = dict(args)
         self.gaussgrid, _ = make_tensor_quadrature([kv.mesh for kv in kvs], self.nqp)
         quad = None
         self._bd = None
         if getattr(vf, 'boundary', False):
+            if kvs_test is not None:
+                raise NotImplementedError('boundary integrals over two different spaces')
             kvs, quad = self._setup_boundary(kvs, args.get('boundary'))
         self._grid_shape = tuple(len(g) for g in self.gaussgrid)
         self._X = None
@@ -435,7 +445,7 @@ class GenericFormAssembler(_AssemblerProtocol):
             self.num_components = lambda: self._nc
         self.blocks = {}
         for blk, coefs in self._analyse().items():
-            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid, quad=quad)
+            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid, quad=quad, kvs_test=kvs_test)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
 

@@ -435,8 +435,13 @@ class VForm:
         self.numcomp = (None, None)
 
     def basisfuns(self, components=(None, None), spaces=(0, 0)):
-        if any(s != 0 for s in spaces):
-            raise NotImplementedError('forms over two different spaces are not part of the device path')
+        spaces = tuple(spaces)
+        if self.arity == 2 and spaces not in ((0, 0), (0, 1)):
+            # the reference's generator only compiles trial functions in space 0 / test functions in space 1
+            raise NotImplementedError('two-space forms need the trial function in space 0 and the test function in space 1')
+        if self.arity == 1 and any(s != 0 for s in spaces[-1:]):
+            raise NotImplementedError('linear forms over the second space are not part of the device path')
+        self.spaces = spaces if self.arity == 2 else (0, 0)
         components = tuple(components)
         if self.arity == 1:
             components = components[-1:]
@@ -469,7 +474,7 @@ class VForm:
         self.exprs.append(expr)
 
     def num_spaces(self):
-        return 1
+        return 2 if getattr(self, 'spaces', (0, 0)) == (0, 1) else 1
 
 
 def _mentions(expr, name):
@@ -513,16 +518,16 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
             raise RuntimeError("got both 'dx' and 'ds' - is this a volume or a surface integral?")
         if not boundary:
             raise NotImplementedError('surface integrals (manifolds) are not part of the device path')
+    spaces = None
     if bfuns is None:
         names, comps = sorted(words & {'u', 'v'}), None
     else:
-        names, comps = [], []
+        names, comps, spaces = [], [], []
         for bf in bfuns:
             bf = (bf,) if isinstance(bf, str) else tuple(bf)
-            if len(bf) > 2 and bf[2] != 0:
-                raise NotImplementedError('multi-space basis functions are not part of the device path')
             names.append(bf[0])
             comps.append(bf[1] if len(bf) > 1 else 1)
+            spaces.append(bf[2] if len(bf) > 2 else 0)
     if len(names) not in (1, 2):
         raise ValueError('arity should be 1 or 2')
     vf = VForm(dim=dim, boundary=bool(boundary), arity=len(names))
@@ -530,7 +535,8 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
     if vf.arity == 1:
         loc[names[0]] = vf.basisfuns(components=tuple(comps) if comps else (None,))
     else:
-        u, v = vf.basisfuns(components=tuple(comps) if comps else (None, None))
+        u, v = vf.basisfuns(components=tuple(comps) if comps else (None, None),
+                            spaces=tuple(spaces) if spaces else (0, 0))
         loc[names[0]], loc[names[1]] = u, v
     for name in sorted(set(args.keys()) & words):
         if callable(args[name]):

@@ -267,6 +267,13 @@ def main():
         else:
             out['bf_%s' % name] = np.asarray(R)
 
+    # ---- 12. two spaces (Petrov-Galerkin), pyiga/assemble.py:947-951 -----------------------------------
+    from helpers import PGFORMS
+    for name, (form, bfuns, inputs, p0, p1, ns, gname) in PGFORMS.items():
+        kvs0 = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(p0, ns))
+        kvs1 = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(p1, ns))
+        save_csr_into(out, 'pg_%s' % name, assemble.assemble(form, (kvs0, kvs1), geo=geos[gname], bfuns=bfuns, **inputs))
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

@@ -104,3 +104,11 @@ BFORMS = {
     'neumann3': ('inner(g, n) * v * ds', None, {'g': lambda x, y, z: (x, y * z, 1.0)}, 'a3_tb', 'tnb', 'left'),
     'traction2': ('inner(g, v) * ds', [('v', 2)], {'g': lambda x, y: (x, -y)}, 'a2_qa', 'qa', 'bottom'),
 }
+
+# Petrov-Galerkin forms: trial space = degrees `p0`, test space = degrees `p1` on the mesh of a space case
+# name -> (form, bfuns, inputs, dim, trial degrees, test degrees, spans, geometry)
+PGFORMS = {
+    'pg2': ('inner(grad(u), grad(v)) * dx', [('u', 1, 0), ('v', 1, 1)], {}, (2, 2), (3, 3), (3, 4), 'qa'),
+    'pg3': ('(c * u * v + inner(b, grad(u)) * v) * dx', [('u', 1, 0), ('v', 1, 1)],
+            {'c': lambda x, y, z: 1.0 + x * z, 'b': lambda x, y, z: (y, -x, 1.0)}, (3, 2, 2), (2, 3, 3), (3, 2, 4), 'tnb'),
+}

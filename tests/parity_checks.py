@@ -564,3 +564,30 @@ def check_boundary_forms(ref):
     ij = np.array([(0, 0), (3, 4), (R.shape[0] - 1, R.shape[0] - 2), (0, R.shape[0] - 1)])
     want = np.asarray(R[ij[:, 0], ij[:, 1]]).ravel()
     assert np.abs(asm.multi_entries(ij) - want).max() <= RTOL * abs(R).max()
+
+
+def check_two_spaces(ref):
+    """Petrov-Galerkin forms: trial functions in space 0 (columns), test functions in space 1 (rows)
+    (reference: pyiga/assemble.py:947-951, generated __init__(kvs0, kvs1, ...))"""
+    from helpers import PGFORMS
+    from pyiga_b200 import assemble, bspline
+    for name, (form, bfuns, inputs, p0, p1, ns, gname) in PGFORMS.items():
+        kvs0 = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(p0, ns))
+        kvs1 = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(p1, ns))
+        R = _ref_csr_named(ref, 'pg_%s' % name)
+        A = assemble.assemble(form, (kvs0, kvs1), geo=make_geo(ref, gname), bfuns=bfuns, **inputs)
+        _assert_csr_equal(A, R, 'two-space form ' + name)
+        M = assemble.assemble(form, (kvs0, kvs1), geo=make_geo(ref, gname), bfuns=bfuns, format='mlb', **inputs)
+        x = np.cos(np.arange(R.shape[1]) * 0.3)
+        assert_close_rel(M.dot(x), R @ x, what='two-space MLB matvec ' + name)
+        asm = assemble.instantiate_assembler(form, (kvs0, kvs1), dict(inputs, geo=make_geo(ref, gname)), bfuns)
+        assert asm.kvs == (kvs0, kvs1)
+        ij = np.array([(0, 0), (R.shape[0] - 1, R.shape[1] - 1), (5, 3), (R.shape[0] - 1, 0)])
+        want = np.asarray(R[ij[:, 0], ij[:, 1]]).ravel()
+        assert np.abs(asm.multi_entries(ij) - want).max() <= RTOL * abs(R).max()
+    try:
+        assemble.assemble('u * v * dx', (kvs0, kvs1), geo=make_geo(ref, 'tnb'), bfuns=[('u', 1, 1), ('v', 1, 0)])
+    except NotImplementedError:
+        pass
+    else:
+        raise AssertionError('unsupported space assignment accepted')

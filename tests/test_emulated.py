@@ -111,3 +111,7 @@ def test_partial_rows(emu, ref):
 
 def test_boundary_forms(emu, ref):
     pc.check_boundary_forms(ref)
+
+
+def test_two_spaces(emu, ref):
+    pc.check_two_spaces(ref)

@@ -171,3 +171,7 @@ def test_partial_rows(cuda, ref):
 
 def test_boundary_forms(cuda, ref):
     pc.check_boundary_forms(ref)
+
+
+def test_two_spaces(cuda, ref):
+    pc.check_two_spaces(ref)
