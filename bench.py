@@ -318,7 +318,7 @@ def run_ours(a):
                 pinned = [torch.empty(nrows_l + 1, dtype=tdt, pin_memory=True), torch.empty(nnz_l, dtype=tdt, pin_memory=True),
                           torch.empty(nnz_l, dtype=torch.float64, pin_memory=True)]
             sl.assemble_csr_host(host=pinned, workspace=ws)               # chunked: D2H overlaps the next chunk
-            d2h = sum(t.numel() * t.element_size() for t in pinned)
+            d2h = pinned[2].numel() * pinned[2].element_size()              # values only; see e2e.what
             h2d = sum(8 * (kv.kv.size + 2 * g.size) for kv, g in zip(kvs, sl.dev.gaussgrid)) + geo.coeffs.nbytes \
                 + sum(8 * kv.kv.size for kv in geo.kvs)
         barrier()
@@ -392,7 +392,8 @@ def run_ours(a):
             'roofline': roof, 'path_roofline': path, 'clocks': clocks,
             'e2e': {'value': total_nnz / (e2e_ms * 1e-3) if e2e_ms else None, 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'what': 'SlabAssembly(kvs, geo).assemble_csr_host(): tables H2D, K1+K2+K3 in row chunks, CSR export, D2H of (indptr, indices, data) into pinned host memory overlapped chunk by chunk'},
+                    'host_index_bytes_per_step': int(sum(t.numel() * t.element_size() for t in pinned[:2])) if pinned else 0,
+                    'what': 'SlabAssembly(kvs, geo).assemble_csr_host(): tables H2D, K1+K2+K3 in row chunks, CSR value permutation, D2H of the values into pinned host memory overlapped chunk by chunk; indptr/indices (closed form of the band tables) are written into the pinned host arrays by host threads meanwhile (pb200_csr_pattern_host)'},
         }
         if world == 1 and not a.no_cpu_baseline:
             try:

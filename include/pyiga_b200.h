@@ -205,9 +205,20 @@ PB200_API int pb200_mlstruct_create(int nlevels, const int* rows, const int* col
                                     const uint32_t* const* h_bidx, int device, pb200_mlstruct** out);
 PB200_API int pb200_mlstruct_destroy(pb200_mlstruct* s);
 /* CSR export of a slab (replaces ml_nonzero_* + COO->CSR, pyiga/mlmatrix_cy.pyx:189-289,
- * pyiga/assemble.py:745): idx_bytes is 4 or 8; d_indptr has nrows+1 entries relative to the slab. */
+ * pyiga/assemble.py:745): idx_bytes is 4 or 8; d_indptr has nrows+1 entries relative to the slab.
+ * d_indptr and d_indices may both be NULL: only the values are permuted. */
 PB200_API int pb200_mlb_to_csr(const pb200_mlstruct* s, int row0_begin, int row0_end, const double* d_mlb,
                      void* d_indptr, void* d_indices, double* d_values, int idx_bytes, void* stream);
+/* host-only helper (no CUDA call, `nthreads` host threads): the CSR pattern (indptr with nrows+1
+ * entries, first entry = indptr_offset; sorted column indices) of the same slab, from the per-level
+ * row tables (row_start[m+1], jmin[m]).  It is the closed form of ml_nonzero_* + COO->CSR
+ * (pyiga/mlmatrix_cy.pyx:189-289, pyiga/assemble.py:745) and lets a caller who wants the matrix in
+ * host memory produce the integer arrays there while the values (pb200_mlb_to_csr with null
+ * d_indptr / d_indices) are still being computed and copied: 8 instead of 12 B/nnz cross PCIe. */
+PB200_API int pb200_csr_pattern_host(int nlevels, const int* rows, const int* cols, const int* nband,
+                           const int* const* h_row_start, const int* const* h_jmin, int row0_begin,
+                           int row0_end, void* h_indptr, void* h_indices, int idx_bytes,
+                           long long indptr_offset, int nthreads);
 /* y = A x for the slab rows (replaces ml_matvec_2d/3d, pyiga/mlmatrix_cy.pyx:224-325).  d_x starts
  * at trial index x_j0_begin on axis 0 (use 0 for a full vector). */
 PB200_API int pb200_mlb_matvec(const pb200_mlstruct* s, int row0_begin, int row0_end, const double* d_mlb,

@@ -92,6 +92,9 @@ SIGNATURES = {
     'pb200_asm_rows_count': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     'pb200_asm_rows_fill': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_void_p]),
+    'pb200_csr_pattern_host': (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int]),
     'pb200_csr_restrict_workspace': (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_size_t)]),
     'pb200_csr_restrict_count': (C.c_int, [C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

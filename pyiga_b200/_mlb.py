@@ -77,6 +77,44 @@ class DeviceStructure:
                                                _ptr(be, values), np.dtype(idt).itemsize, be.stream()))
         return indptr, indices, values
 
+    def csr_values(self, d_data, row0=None, out=None):
+        """Only the CSR-ordered values of the slab (device buffer); the pattern comes from
+        :meth:`csr_pattern_host`."""
+        be = self.be
+        ra, rb, nrows, count = self._sizes(row0)
+        values = be.empty(count, np.float64) if out is None else out[:count]
+        idb = 4 if count < 2 ** 31 else 8
+        _device.check(be.lib.pb200_mlb_to_csr(self.handle, ra, rb, _ptr(be, d_data), 0, 0, _ptr(be, values), idb, be.stream()))
+        return values
+
+    def csr_pattern_host(self, h_indptr, h_indices, row0=None, indptr_offset=0, nthreads=None):
+        """Fill the host arrays `h_indptr` (nrows+1) and `h_indices` (count) — numpy arrays or pinned
+        torch tensors of int32 / int64 — with the CSR pattern of the slab, using `nthreads` host
+        threads.  No device work."""
+        import os
+        S = self.structure
+        L = S.L
+        tabs = [S._row_tables(k) for k in range(L)]
+        ra, rb, nrows, count = self._sizes(row0)
+        rows = (C.c_int * L)(*[b[0] for b in S.bs])
+        cols = (C.c_int * L)(*[b[1] for b in S.bs])
+        nband = (C.c_int * L)(*[len(b) for b in S.bidx])
+        rs = [np.ascontiguousarray(t[0], dtype=np.int32) for t in tabs]
+        jm = [np.ascontiguousarray(t[1], dtype=np.int32) for t in tabs]
+        p_rs = (C.c_void_p * L)(*[a.ctypes.data for a in rs])
+        p_jm = (C.c_void_p * L)(*[a.ctypes.data for a in jm])
+
+        def addr(a):
+            return a.data_ptr() if hasattr(a, 'data_ptr') else a.ctypes.data
+
+        def itemsize(a):
+            return a.element_size() if hasattr(a, 'element_size') else a.itemsize
+        assert itemsize(h_indptr) == itemsize(h_indices)
+        nthreads = nthreads or max(1, (os.cpu_count() or 2) - 1)
+        _device.check(self.be.lib.pb200_csr_pattern_host(L, rows, cols, nband, p_rs, p_jm, ra, rb, addr(h_indptr),
+                                                         addr(h_indices), itemsize(h_indptr), int(indptr_offset),
+                                                         int(nthreads)))
+
     def to_csr(self, d_data, row0=None):
         be = self.be
         indptr, indices, values = self.csr_arrays(d_data, row0)

@@ -10,6 +10,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -151,7 +152,7 @@ static void k_csr(const PbMlbParams& p, long long nrows, long long count, IdxT* 
                   pbStream st) {
     g_launches += 2;
 #ifdef PB_EMULATE
-    pb_emu_for(nrows + 1, [&](long long r) { pb_csr_indptr_row<IdxT>(p, nrows, indptr, r); });
+    if (indptr) pb_emu_for(nrows + 1, [&](long long r) { pb_csr_indptr_row<IdxT>(p, nrows, indptr, r); });
     pb_emu_for(nrows, [&](long long r) {
         int i[3] = {0, 0, 0}, rs[3] = {0, 0, 0}, nb[3] = {1, 1, 1}, jm[3] = {0, 0, 0};
         pb_csr_row_tables(p, r, i, rs, nb, jm);
@@ -162,7 +163,7 @@ static void k_csr(const PbMlbParams& p, long long nrows, long long count, IdxT* 
 #else
     const unsigned b1 = (unsigned)((nrows + 1 + 255) / 256);
     const unsigned b2 = (unsigned)std::min<long long>((nrows + 7) / 8, 148LL * 32);
-    pb_csr_indptr_kernel<IdxT><<<b1, 256, 0, st>>>(p, nrows, indptr);
+    if (indptr) pb_csr_indptr_kernel<IdxT><<<b1, 256, 0, st>>>(p, nrows, indptr);
     pb_csr_fill_rows_kernel<IdxT><<<b2, 256, 0, st>>>(p, nrows, indices, values);
     (void)count;
 #endif
@@ -1588,7 +1589,9 @@ static int fill_mlb_params(const pb200_mlstruct* a, int ra, int rb, const double
 
 extern "C" int pb200_mlb_to_csr(const pb200_mlstruct* a, int ra, int rb, const double* d_mlb, void* d_indptr,
                                 void* d_indices, double* d_values, int idx_bytes, void* stream) {
-    if (!a || !d_mlb || !d_indptr || !d_indices || !d_values) return fail(PB200_EINVAL, "null argument");
+    // d_indptr / d_indices may be null: values only (the pattern can be produced on the host by
+    // pb200_csr_pattern_host while the values are still being computed and copied)
+    if (!a || !d_mlb || !d_values) return fail(PB200_EINVAL, "null argument");
     if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
     CK(pbSetDevice(a->device));
     PbMlbParams p;
@@ -1615,6 +1618,72 @@ extern "C" int pb200_mlb_matvec(const pb200_mlstruct* a, int ra, int rb, const d
     for (int k = 1; k < a->dim; ++k) nrows *= p.Nv[k];
     k_matvec(p, nrows, d_x, x_j0_begin, d_y, (pbStream)stream);
     CK(pbLastError());
+    return 0;
+}
+
+// host-only: CSR pattern of the rows [row0_begin, row0_end) of axis 0 of a multi-level banded structure
+template <class IT>
+static void csr_pattern_rows(int L, const int* Nv, const int* Nu, const int* const* rs, const int* const* jm, const int* M,
+                             int ra, long long r_begin, long long r_end, IT* indptr, IT* indices, long long off0) {
+    const long long m1 = L > 1 ? M[1] : 1, m2 = L > 2 ? M[2] : 1;
+    const long long inner = (long long)(L > 1 ? Nv[1] : 1) * (L > 2 ? Nv[2] : 1);
+    for (long long r = r_begin; r < r_end; ++r) {
+        int i[3] = {0, 0, 0};
+        long long t = r;
+        for (int k = L - 1; k >= 1; --k) { i[k] = (int)(t % Nv[k]); t /= Nv[k]; }
+        i[0] = (int)t + ra;
+        int nb[3] = {1, 1, 1}, j0[3] = {0, 0, 0};
+        for (int k = 0; k < L; ++k) { nb[k] = rs[k][i[k] + 1] - rs[k][i[k]]; j0[k] = jm[k][i[k]]; }
+        long long off = (long long)(rs[0][i[0]] - rs[0][ra]) * m1 * m2;
+        if (L == 2) off += (long long)nb[0] * rs[1][i[1]];
+        if (L == 3) off += (long long)nb[0] * ((long long)rs[1][i[1]] * m2 + (long long)nb[1] * rs[2][i[2]]);
+        indptr[r] = (IT)(off0 + off);
+        IT* out = indices + off;
+        if (L == 2) {
+            for (int k0 = 0; k0 < nb[0]; ++k0) {
+                const long long base = (long long)(j0[0] + k0) * Nu[1] + j0[1];
+                for (int k1 = 0; k1 < nb[1]; ++k1) *out++ = (IT)(base + k1);
+            }
+        } else {
+            for (int k0 = 0; k0 < nb[0]; ++k0)
+                for (int k1 = 0; k1 < nb[1]; ++k1) {
+                    const long long base = ((long long)(j0[0] + k0) * Nu[1] + j0[1] + k1) * Nu[2] + j0[2];
+                    for (int k2 = 0; k2 < nb[2]; ++k2) *out++ = (IT)(base + k2);
+                }
+        }
+    }
+    (void)inner;
+}
+
+extern "C" int pb200_csr_pattern_host(int nlevels, const int* rows, const int* cols, const int* nband,
+                                      const int* const* h_row_start, const int* const* h_jmin, int row0_begin,
+                                      int row0_end, void* h_indptr, void* h_indices, int idx_bytes,
+                                      long long indptr_offset, int nthreads) {
+    if (!rows || !cols || !nband || !h_row_start || !h_jmin || !h_indptr || !h_indices) return fail(PB200_EINVAL, "null argument");
+    if (nlevels < 2 || nlevels > 3) return fail(PB200_EUNSUPPORTED, "2 or 3 levels (got %d)", nlevels);
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
+    if (row0_begin < 0 || row0_end > rows[0] || row0_begin > row0_end) return fail(PB200_EINVAL, "invalid row slab");
+    long long nrows = row0_end - row0_begin;
+    for (int k = 1; k < nlevels; ++k) nrows *= rows[k];
+    long long count = (long long)(h_row_start[0][row0_end] - h_row_start[0][row0_begin]);
+    for (int k = 1; k < nlevels; ++k) count *= nband[k];
+    nthreads = std::max(1, std::min(nthreads, 256));
+    auto work = [&](long long a, long long b) {
+        if (idx_bytes == 4)
+            csr_pattern_rows<int>(nlevels, rows, cols, h_row_start, h_jmin, nband, row0_begin, a, b, (int*)h_indptr,
+                                  (int*)h_indices, indptr_offset);
+        else
+            csr_pattern_rows<long long>(nlevels, rows, cols, h_row_start, h_jmin, nband, row0_begin, a, b,
+                                        (long long*)h_indptr, (long long*)h_indices, indptr_offset);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        const long long a = nrows * t / nthreads, b = nrows * (t + 1) / nthreads;
+        if (b > a) pool.emplace_back(work, a, b);
+    }
+    for (auto& th : pool) th.join();
+    if (idx_bytes == 4) ((int*)h_indptr)[nrows] = (int)(indptr_offset + count);
+    else ((long long*)h_indptr)[nrows] = indptr_offset + count;
     return 0;
 }
 

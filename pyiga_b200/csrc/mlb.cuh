@@ -80,13 +80,13 @@ PB_HD void pb_csr_fill_row_entry(const PbMlbParams& p, const int* i, const int* 
     if (p.dim == 2) {
         const int k1 = e % nb[1], k0 = e / nb[1];
         const long long src = (long long)(rs[0] + k0 - mu0_base) * p.M[1] + rs[1] + k1;
-        indices[rowoff + e] = (IdxT)((long long)(jm[0] + k0) * p.Nu[1] + jm[1] + k1);
+        if (indices) indices[rowoff + e] = (IdxT)((long long)(jm[0] + k0) * p.Nu[1] + jm[1] + k1);
         values[rowoff + e] = p.data[src];
     } else {
         const int k2 = e % nb[2], t = e / nb[2];
         const int k1 = t % nb[1], k0 = t / nb[1];
         const long long src = ((long long)(rs[0] + k0 - mu0_base) * p.M[1] + rs[1] + k1) * p.M[2] + rs[2] + k2;
-        indices[rowoff + e] = (IdxT)(((long long)(jm[0] + k0) * p.Nu[1] + jm[1] + k1) * p.Nu[2] + jm[2] + k2);
+        if (indices) indices[rowoff + e] = (IdxT)(((long long)(jm[0] + k0) * p.Nu[1] + jm[1] + k1) * p.Nu[2] + jm[2] + k2);
         values[rowoff + e] = p.data[src];
     }
     (void)i;

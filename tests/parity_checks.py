@@ -591,3 +591,27 @@ def check_two_spaces(ref):
         pass
     else:
         raise AssertionError('unsupported space assignment accepted')
+
+
+def check_csr_pattern_host(ref):
+    """host-side closed form of the CSR pattern (pb200_csr_pattern_host) == the reference's
+    MLStructure.nonzero + COO->CSR pattern, for whole matrices and row slabs, int32 and int64"""
+    from pyiga_b200 import assemblers
+    for case, cls, gname in [('a3_mixed', assemblers.StiffnessAssembler3D, 'tb'), ('a2_mixed', assemblers.MassAssembler2D, 'bqa'),
+                             ('a3_mult', assemblers.MassAssembler3D, 'cyl')]:
+        kvs = make_space(ref, case)
+        asm = cls(kvs, make_geo(ref, gname))
+        ds = asm.dev.device_structure
+        key = 'stiff' if 'Stiff' in cls.__name__ else 'mass'
+        indptr, indices = ref['%s_%s_indptr' % (case, key)], ref['%s_%s_indices' % (case, key)]
+        n0 = kvs[0].numdofs
+        inner = int(np.prod([kv.numdofs for kv in kvs[1:]]))
+        for (ra, rb), idt, nthr in [((0, n0), np.int32, 1), ((0, n0), np.int64, 3), ((1, n0 - 2), np.int32, 4), ((2, 3), np.int64, 7)]:
+            r0, r1 = ra * inner, rb * inner
+            want_ptr = indptr[r0:r1 + 1] - indptr[r0]
+            want_idx = indices[indptr[r0]:indptr[r1]]
+            got_ptr = np.full(want_ptr.size, -7, dtype=idt)
+            got_idx = np.full(want_idx.size, -7, dtype=idt)
+            ds.csr_pattern_host(got_ptr, got_idx, row0=(ra, rb), indptr_offset=5, nthreads=nthr)
+            assert np.array_equal(got_ptr, want_ptr + 5), (case, ra, rb)
+            assert np.array_equal(got_idx, want_idx), (case, ra, rb)

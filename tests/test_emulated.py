@@ -115,3 +115,7 @@ def test_boundary_forms(emu, ref):
 
 def test_two_spaces(emu, ref):
     pc.check_two_spaces(ref)
+
+
+def test_csr_pattern_host(emu, ref):
+    pc.check_csr_pattern_host(ref)

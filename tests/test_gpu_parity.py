@@ -154,11 +154,12 @@ def test_pipelined_csr_host(cuda):
     for world, rank in ((1, 0), (3, 1)):
         sa = SlabAssembly(kvs, geo, 'stiffness', rank=rank, world=world)
         A = sa.assemble_csr()
-        ip, ix, vv = sa.assemble_csr_host(nchunks=4)
-        assert np.array_equal(ip.numpy(), A.indptr) and np.array_equal(ix.numpy(), A.indices)
-        # values agree to rounding: which half of a symmetric pair is computed and which is mirrored
-        # depends on the row chunking
-        assert np.abs(vv.numpy() - A.data).max() <= 1e-13 * np.abs(A.data).max()
+        for pattern in ('host', 'device'):
+            ip, ix, vv = sa.assemble_csr_host(nchunks=4, pattern=pattern)
+            assert np.array_equal(ip.numpy(), A.indptr) and np.array_equal(ix.numpy(), A.indices), pattern
+            # values agree to rounding: which half of a symmetric pair is computed and which is mirrored
+            # depends on the row chunking
+            assert np.abs(vv.numpy() - A.data).max() <= 1e-13 * np.abs(A.data).max()
 
 
 def test_boundary_conditions(cuda, ref):
@@ -175,3 +176,7 @@ def test_boundary_forms(cuda, ref):
 
 def test_two_spaces(cuda, ref):
     pc.check_two_spaces(ref)
+
+
+def test_csr_pattern_host(cuda, ref):
+    pc.check_csr_pattern_host(ref)
