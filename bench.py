@@ -232,7 +232,8 @@ def run_ours(a):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: one JSON line only
+        # keep NCCL's version banner / debug output off stdout: rank 0 prints one JSON line only
+        os.environ['NCCL_DEBUG_FILE'] = os.path.join(tempfile.gettempdir(), 'nccl_bench_%h_%p.log')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     from pyiga_b200 import _device, bspline, geometry

@@ -365,6 +365,8 @@ struct pb200_assembler {
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
     bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
     int lane_lines = 64;                                // lines per warp of the lane-span kernel (<= PbLaneCfg::DQ)
+    int walk_split = 0;                                 // pieces of the walk axis: 0 = choose by occupancy, 1 = never, K = always K
+    int sm_count = 0;                                   // multiprocessors of the device
     bool mirror_opt = true;                             // symmetric forms: compute the upper half of the final stage, mirror the rest
     bool fused_plans = true;                            // multi-output stage kernels (S1A/S1B/S2B); false: one launch per output
     // optional per-kernel timing of the last assemble call (CUDA events on the launch stream)
@@ -395,6 +397,7 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!a || !name) return fail(PB200_EINVAL, "null argument");
     if (!strcmp(name, "force_walk")) { a->force_walk = value != 0; return 0; }
     if (!strcmp(name, "lane_v1")) { a->lane_v1 = value != 0; return 0; }
+    if (!strcmp(name, "walk_split")) { if (value < 0 || value > PB_WALK_MAXSPLIT) return fail(PB200_EINVAL, "walk_split must be in 0..%d", PB_WALK_MAXSPLIT); a->walk_split = value; return 0; }
     if (!strcmp(name, "lane_lines")) { if (value < 1 || value > 64) return fail(PB200_EINVAL, "lane_lines must be in 1..64"); a->lane_lines = value; return 0; }
     if (!strcmp(name, "fused_plans")) { a->fused_plans = value != 0; return 0; }
     if (!strcmp(name, "mirror")) { a->mirror_opt = value != 0; return 0; }
@@ -491,6 +494,9 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
         return fail(PB200_EINVAL, "unknown form id %d", desc->form);
     std::unique_ptr<pb200_assembler> a(new pb200_assembler);
     a->device = device;
+#ifndef PB_EMULATE
+    cudaDeviceGetAttribute(&a->sm_count, cudaDevAttrMultiProcessorCount, device);
+#endif
     a->dim = desc->dim;
     a->form = desc->form;
     const int dim = desc->dim;
@@ -1095,6 +1101,41 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     const size_t smem = (size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double);
     const size_t ismem = ((size_t)(prm.s_end - prm.s_begin + 4) + (size_t)(prm.f_hi - prm.f_lo) * (2 * P + 1)) * sizeof(int);
     const int use_smem = smem + ismem <= 64 * 1024;     // longer axes read the table through L1 (keeps occupancy)
+    // Tail effect: a stage whose blocks fill the GPU 1.x times spends the second wave almost idle.
+    // Cut the walk axis into K pieces (grid.y) when that shortens the sum of the waves; the pieces
+    // overlap by p spans.  Needs a stage without a walk-axis filter of its own.
+    prm.nsplit = 0;
+    const int rows_w = prm.w_hi > prm.w_lo ? 0 : H.V.N();       // only unfiltered stages: all rows of the axis
+    if (nofilter && rows_w > 0 && a->walk_split != 1 && prm.s_begin == 0 && prm.s_end == H.n) {
+        int K = 1;
+        if (a->walk_split > 1) {
+            K = a->walk_split;
+        } else {
+            const int occ = fn(&prm, -1, use_smem ? smem + ismem + 256 : 0, st);
+            if (occ > 0 && a->sm_count > 0) {
+                const long long B = (prm.nthreads + 127) / 128, slots = (long long)a->sm_count * occ;
+                double best = (double)((B + slots - 1) / slots) * H.n;
+                for (int k = 2; k <= PB_WALK_MAXSPLIT; ++k) {
+                    if (H.n / k < 4 * (P + 1)) break;                  // pieces too short to pay for the overlap
+                    const double cost = (double)((k * B + slots - 1) / slots) * ((double)H.n / k + P);
+                    if (cost < 0.93 * best) { best = cost; K = k; }
+                }
+            }
+        }
+        K = std::min(K, std::min(PB_WALK_MAXSPLIT, rows_w));
+        if (K > 1 && getenv("PB200_DEBUG_SPLIT")) fprintf(stderr, "[pb200] stage %s: walk axis cut into %d pieces\n", name, K);
+        if (K > 1) {
+            prm.nsplit = K;
+            for (int y = 0; y < K; ++y) {
+                const int lo = (int)((long long)rows_w * y / K), hi = (int)((long long)rows_w * (y + 1) / K);
+                prm.sp_w_lo[y] = lo; prm.sp_w_hi[y] = hi;
+                prm.sp_s_begin[y] = H.V.supp[2 * lo];
+                prm.sp_s_end[y] = H.V.supp[2 * (hi - 1) + 1];
+                prm.sp_f_lo[y] = H.U.first[prm.sp_s_begin[y]];
+                prm.sp_f_hi[y] = std::min(H.V.N(), H.U.first[prm.sp_s_end[y] - 1] + P + 1);
+            }
+        }
+    }
     int e = fn(&prm, use_smem, use_smem ? smem : 0, st);
     if (e) return fail(PB200_ECUDA, "walk kernel launch failed (plan %d, p=%d, q=%d): %s", plan, P, Q, pbErrorString((pbError)e));
     return 0;

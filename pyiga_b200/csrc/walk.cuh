@@ -32,6 +32,7 @@ struct PbOp {       // acc[out] += D_ft (x) D_fu * in
 };
 
 #define PB_WALK_MAXOPS 8
+#define PB_WALK_MAXSPLIT 4
 #define PB_WALK_MAXOUT 4
 
 struct PbWalkParams {
@@ -66,7 +67,34 @@ struct PbWalkParams {
     const int* ret_mu;              // [N][2P+1]
     int w_mode[PB_WALK_MAXOUT], w_lo, w_hi;     // retire filter on the walk-axis pair (i,j), as u_mode
     int f_lo, f_hi;                 // functions retired by this walk: [first[s_begin], min(N, first[s_end-1]+P+1))
+    // ---- optional split of the walk axis (grid.y pieces) --------------------------------------
+    // A stage whose lines fill the GPU only 1.x times is cut into `nsplit` pieces along the walk
+    // axis: piece y retires the pairs whose row lies in [sp_w_lo[y], sp_w_hi[y]) and walks only the
+    // spans those rows see, so that the tail wave is shorter (the pieces overlap by p spans).
+    // Only for stages without a walk-axis filter of their own (w_mode all 0).
+    int nsplit;
+    int sp_s_begin[PB_WALK_MAXSPLIT], sp_s_end[PB_WALK_MAXSPLIT];
+    int sp_w_lo[PB_WALK_MAXSPLIT], sp_w_hi[PB_WALK_MAXSPLIT];
+    int sp_f_lo[PB_WALK_MAXSPLIT], sp_f_hi[PB_WALK_MAXSPLIT];
 };
+
+// the part of the walk axis one thread block (or emulated piece) works on
+struct PbWalkRange { int s_begin, s_end, w_lo, w_hi, f_lo, f_hi; bool split; };
+PB_HD PbWalkRange pb_walk_range(const PbWalkParams& prm, int y) {
+    PbWalkRange r;
+    r.split = prm.nsplit > 1;
+    if (r.split) {
+        r.s_begin = prm.sp_s_begin[y]; r.s_end = prm.sp_s_end[y];
+        r.w_lo = prm.sp_w_lo[y]; r.w_hi = prm.sp_w_hi[y];
+        r.f_lo = prm.sp_f_lo[y]; r.f_hi = prm.sp_f_hi[y];
+    } else {
+        r.s_begin = prm.s_begin; r.s_end = prm.s_end;
+        r.w_lo = prm.w_lo; r.w_hi = prm.w_hi;
+        r.f_lo = prm.f_lo; r.f_hi = prm.f_hi;
+    }
+    return r;
+}
+PB_HD int pb_walk_wmode(const PbWalkParams& prm, const PbWalkRange& rg, int o) { return rg.split ? 1 : prm.w_mode[o]; }
 
 PB_HD bool pb_keep(int mode, int i, int j, int lo, int hi) {
     const bool ki = (i >= lo && i < hi), kj = (j >= lo && j < hi);
@@ -145,18 +173,19 @@ struct PbWalkTables {       // where the thread finds the walk-axis tables (shar
                             // of the walk) carries the per-output slab filter in bits 24..27
 };
 template <class Plan, int P, int Q, bool ENC, class Loader>
-PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWalkTables& tb, Loader& ld);
+PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, long long tid, const PbWalkTables& tb, Loader& ld);
 
 template <class Plan, int P, int Q, int NPF = 1>
-PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt) {
+PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __restrict__ Vt, int piece = 0) {
     PbRegLoader<Plan, Q> ld;
     PbWalkTables tb;
     tb.V = Vt; tb.first = prm.first; tb.ret_mu = prm.ret_mu;
-    pb_walk_line_impl<Plan, P, Q, false>(prm, tid, tb, ld);
+    const PbWalkRange rg = pb_walk_range(prm, piece);
+    pb_walk_line_impl<Plan, P, Q, false>(prm, rg, tid, tb, ld);
 }
 
 template <class Plan, int P, int Q, bool ENC, class Loader>
-PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWalkTables& tb, Loader& ld) {
+PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, long long tid, const PbWalkTables& tb, Loader& ld) {
     const double* __restrict__ Vt = tb.V;
     constexpr int P1 = P + 1;
     constexpr int NOPS = Plan::NOPS, NOUT = Plan::NOUT;
@@ -197,7 +226,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
         ld.src[i] = prm.in[i] + (Plan::op(i).tr ? off_in_tr : off_in);
     });
     ld.sc = prm.in_sc;
-    ld.s_end = prm.s_end;
+    ld.s_end = rg.s_end;
 
     double acc[NOUT][P1][P1];
     pb_static_for<0, NOUT>([&](auto O) {
@@ -238,7 +267,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
                 } else {
                     pb_static_for<0, NOUT>([&](auto O) {
                         constexpr int o = decltype(O)::value;
-                        mask |= pb_keep(prm.w_mode[o], f + a, f + b, prm.w_lo, prm.w_hi) ? (1 << o) : 0;
+                        mask |= pb_keep(pb_walk_wmode(prm, rg, o), f + a, f + b, rg.w_lo, rg.w_hi) ? (1 << o) : 0;
                     });
                 }
                 mask &= wantbits;
@@ -263,10 +292,10 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, long long tid, const PbWal
         });
     };
 
-    int f = tb.first[prm.s_begin];
-    ld.prime(prm.s_begin);
+    int f = tb.first[rg.s_begin];
+    ld.prime(rg.s_begin);
 
-    for (int s = prm.s_begin; s < prm.s_end; ++s) {
+    for (int s = rg.s_begin; s < rg.s_end; ++s) {
         const int fs = tb.first[s];
         while (f < fs) { retire_shift(f); ++f; }
 
@@ -439,10 +468,11 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
     extern __shared__ __align__(128) unsigned char pb_smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const double* Vt = prm.V2;
+    const PbWalkRange rg = pb_walk_range(prm, blockIdx.y);
     if (use_smem) {
         double* sV = reinterpret_cast<double*>(pb_smem_raw);
-        const long long first_node = (long long)prm.s_begin * Q;
-        const uint32_t bytes = (uint32_t)((long long)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double));
+        const long long first_node = (long long)rg.s_begin * Q;
+        const uint32_t bytes = (uint32_t)((long long)(rg.s_end - rg.s_begin) * Q * 2 * (P + 1) * sizeof(double));
         if (threadIdx.x == 0) {
             pb_mbar_init(&bar, 1);
         }
@@ -470,29 +500,29 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
     // the small integer tables (first active function per span, retire table) go to shared memory
     // as well: every span of every thread reads them, and with most of the L1 carved out as shared
     // memory they would otherwise be re-fetched from L2 inside the dependent chain of the walk
-    const size_t vbytes = use_smem ? ((size_t)(prm.s_end - prm.s_begin) * Q * 2 * (P + 1) * sizeof(double) + 127) & ~size_t(127) : 0;
-    const int nsp = prm.s_end - prm.s_begin;
-    const int f_lo = prm.f_lo, f_hi = prm.f_hi;                            // functions retired by this walk
+    const size_t vbytes = use_smem ? ((size_t)(rg.s_end - rg.s_begin) * Q * 2 * (P + 1) * sizeof(double) + 127) & ~size_t(127) : 0;
+    const int nsp = rg.s_end - rg.s_begin;
+    const int f_lo = rg.f_lo, f_hi = rg.f_hi;                            // functions retired by this walk
     int* s_first = reinterpret_cast<int*>(pb_smem_raw + vbytes);
     int* s_ret = s_first + ((nsp + 3) & ~3);
     const size_t ibytes = (((size_t)((nsp + 3) & ~3) + (size_t)(f_hi - f_lo) * (2 * P + 1)) * sizeof(int) + 127) & ~size_t(127);
     PbWalkTables tb;
     tb.V = Vt;
     if (use_smem) {
-        for (int t = threadIdx.x; t < nsp; t += blockDim.x) s_first[t] = prm.first[prm.s_begin + t];
+        for (int t = threadIdx.x; t < nsp; t += blockDim.x) s_first[t] = prm.first[rg.s_begin + t];
         for (int t = threadIdx.x; t < (f_hi - f_lo) * (2 * P + 1); t += blockDim.x) {
             int mu = prm.ret_mu[(long long)f_lo * (2 * P + 1) + t];
             if (mu >= 0) {
                 const int f = f_lo + t / (2 * P + 1), k = t % (2 * P + 1);
                 const int i = (k <= P) ? f : f + (k - P), j = (k <= P) ? f + k : f;
                 int mask = 0;
-                for (int o = 0; o < Plan::NOUT; ++o) mask |= pb_keep(prm.w_mode[o], i, j, prm.w_lo, prm.w_hi) ? (1 << o) : 0;
+                for (int o = 0; o < Plan::NOUT; ++o) mask |= pb_keep(pb_walk_wmode(prm, rg, o), i, j, rg.w_lo, rg.w_hi) ? (1 << o) : 0;
                 mu = mask ? (mu | (mask << 24)) : -1;
             }
             s_ret[t] = mu;
         }
         __syncthreads();
-        tb.first = s_first - prm.s_begin;
+        tb.first = s_first - rg.s_begin;
         tb.ret_mu = s_ret - (long long)f_lo * (2 * P + 1);
     } else {
         tb.first = prm.first;
@@ -504,12 +534,12 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
             // NPF doubles as the ring depth of the asynchronous loader
             PbAsyncLoader<Plan, Q, NPF> ld;
             ld.ring = reinterpret_cast<double*>(pb_smem_raw + vbytes + (use_smem ? ibytes : 0)) + threadIdx.x;
-            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, tid, tb, ld);
-            else pb_walk_line_impl<Plan, P, Q, false>(prm, tid, tb, ld);
+            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, rg, tid, tb, ld);
+            else pb_walk_line_impl<Plan, P, Q, false>(prm, rg, tid, tb, ld);
         } else {
             PbRegLoader<Plan, Q> ld;
-            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, tid, tb, ld);
-            else pb_walk_line_impl<Plan, P, Q, false>(prm, tid, tb, ld);
+            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, rg, tid, tb, ld);
+            else pb_walk_line_impl<Plan, P, Q, false>(prm, rg, tid, tb, ld);
         }
     }
 }

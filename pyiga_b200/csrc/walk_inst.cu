@@ -1,5 +1,6 @@
 // Instantiates the walk kernels of the built-in plans for one (degree, nodes-per-span) pair.
 // Compiled once per pair with -DPB_P=<p> -DPB_Q=<q>; each object registers its launchers.
+#include <algorithm>
 #include "backend.cuh"
 #include "plans.cuh"
 #include "walk1.cuh"
@@ -14,7 +15,8 @@ template <class Plan>
 int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* stream) {
 #ifdef PB_EMULATE
     (void)use_smem; (void)smem_bytes; (void)stream;
-    pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q>(*prm, tid, prm->V2); });
+    for (int y = 0; y < std::max(1, prm->nsplit); ++y)
+        pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_line<Plan, PB_P, PB_Q>(*prm, tid, prm->V2, y); });
     return 0;
 #else
     auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, (PB_P >= 4 ? Plan::MINB4 : Plan::MINB), Plan::NPF>;
@@ -24,16 +26,30 @@ int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* strea
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
+    // the asynchronous loader's ring (plans with NPF >= 2) sits behind the table slice
+    const size_t ring = Plan::NPF >= 2 ? (size_t)Plan::NPF * PB_Q * Plan::NOPS * 128 * sizeof(double) : 0;
+    if (use_smem < 0) {
+        // query: resident blocks per SM with `smem_bytes` of table staging (tables + integer tables)
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, smem_bytes + ring);
+        return e == cudaSuccess ? nb : 0;
+    }
     const long long blocks = (prm->nthreads + 127) / 128;
     if (blocks <= 0) return 0;
     if (prm->out_smu >= (1LL << 31)) return (int)cudaErrorInvalidValue;   // band stride is used as a 32-bit factor
-    // the asynchronous loader's ring (plans with NPF >= 2) sits behind the table slice
-    const size_t ring = Plan::NPF >= 2 ? (size_t)Plan::NPF * PB_Q * Plan::NOPS * 128 * sizeof(double) : 0;
-    const size_t vpad = use_smem ? (smem_bytes + 127) & ~size_t(127) : 0;
-    // integer tables behind the V slice: spans (padded to 4) + at most (spans + P + 1) functions x (2P+1)
-    const int nsp = prm->s_end - prm->s_begin;
-    const size_t ipad = use_smem ? ((((size_t)((nsp + 3) & ~3) + (size_t)(prm->f_hi - prm->f_lo) * (2 * PB_P + 1)) * sizeof(int) + 127) & ~size_t(127)) : 0;
-    kern<<<(unsigned)blocks, 128, vpad + ipad + ring, (cudaStream_t)stream>>>(*prm, use_smem);
+    // table slice and integer tables (spans padded to 4 + retired functions x (2P+1)) of the largest piece
+    const int ny = std::max(1, prm->nsplit);
+    size_t vpad = 0, ipad = 0;
+    for (int y = 0; y < ny; ++y) {
+        const PbWalkRange rg = pb_walk_range(*prm, y);
+        const int nsp = rg.s_end - rg.s_begin;
+        vpad = std::max(vpad, ((size_t)nsp * PB_Q * 2 * (PB_P + 1) * sizeof(double) + 127) & ~size_t(127));
+        ipad = std::max(ipad, (((size_t)((nsp + 3) & ~3) + (size_t)(rg.f_hi - rg.f_lo) * (2 * PB_P + 1)) * sizeof(int) + 127) & ~size_t(127));
+    }
+    if (!use_smem) vpad = ipad = 0;
+    (void)smem_bytes;
+    dim3 grid((unsigned)blocks, (unsigned)ny);
+    kern<<<grid, 128, vpad + ipad + ring, (cudaStream_t)stream>>>(*prm, use_smem);
     return (int)cudaGetLastError();
 #endif
 }

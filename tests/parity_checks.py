@@ -165,7 +165,7 @@ def check_operators(ref):
     np.testing.assert_allclose(KroneckerOperator(*facs).dot(ref['kron_x']), ref['kron_y'], rtol=1e-13, atol=1e-13)
 
 
-def check_vs_oracle(dim, ps, ns, form, geo_name='nurbs', mult=1, force_walk=False, rtol=RTOL):
+def check_vs_oracle(dim, ps, ns, form, geo_name='nurbs', mult=1, force_walk=False, rtol=RTOL, walk_split=None):
     """any space: the device pipeline against the oracle's closed form (the oracle is pinned to the
     reference by tests/test_oracle.py)"""
     from pyiga_b200 import assemblers, bspline, geometry
@@ -177,6 +177,8 @@ def check_vs_oracle(dim, ps, ns, form, geo_name='nurbs', mult=1, force_walk=Fals
     asm = getattr(assemblers, '%sAssembler%dD' % (form, dim))(kvs, geo)
     if force_walk:
         asm.dev.set_option('force_walk', 1)
+    if walk_split is not None:
+        asm.dev.set_option('walk_split', walk_split)
     got = asm.dev.be.to_host(asm.dev.assemble_mlb())
     prob = orc.Problem([kv.kv for kv in kvs], list(ps), [kv.kv for kv in geo.kvs], [kv.p for kv in geo.kvs],
                        geo.coeffs, geo._rational)

@@ -119,3 +119,12 @@ def test_two_spaces(emu, ref):
 
 def test_csr_pattern_host(emu, ref):
     pc.check_csr_pattern_host(ref)
+
+
+@pytest.mark.parametrize('k', [2, 3, 4])
+def test_walk_axis_split(emu, k):
+    """stages cut into k pieces along the walk axis (tail-wave balancing) give the same matrices"""
+    pc.check_vs_oracle(3, (3, 2, 2), (3, 9, 4), 'Stiffness', walk_split=k)
+    pc.check_vs_oracle(3, (2, 3, 1), (2, 7, 3), 'Mass', walk_split=k, geo_name='bspline')
+    pc.check_vs_oracle(2, (3, 3), (11, 5), 'Stiffness', walk_split=k)
+    pc.check_vs_oracle(3, (2, 2, 2), (2, 6, 3), 'Stiffness', walk_split=k, mult=2)

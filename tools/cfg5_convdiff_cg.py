@@ -24,7 +24,8 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'
+        import tempfile
+        os.environ['NCCL_DEBUG_FILE'] = os.path.join(tempfile.gettempdir(), 'nccl_cfg5_%h_%p.log')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from pyiga_b200 import _device, assemble, bspline, geometry, vform
     from pyiga_b200.dist import GatheredKronecker, SlabAssembly, SlabOperator, cg, partition_rows
