@@ -119,7 +119,7 @@ def run_reference(a, quiet=False):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     if not quiet:
-        print(json.dumps(line), flush=True)
+        emit(line)
     return line
 
 
@@ -232,8 +232,6 @@ def run_ours(a):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        # keep NCCL's version banner / debug output off stdout: rank 0 prints one JSON line only
-        os.environ['NCCL_DEBUG_FILE'] = os.path.join(tempfile.gettempdir(), 'nccl_bench_%h_%p.log')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     from pyiga_b200 import _device, bspline, geometry
@@ -407,14 +405,34 @@ def run_ours(a):
             except Exception as exc:    # the baseline is informational; never lose the GPU line over it
                 line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'unavailable',
                                         'sample': 'failed: %r' % (exc,)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the process's real stdout"""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse_args()
+    # Libraries write banners to the C-level stdout (NCCL prints its version there when NCCL_DEBUG is
+    # set in the environment): route file descriptor 1 to stderr for the whole run and keep the real
+    # stdout for the result line only.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == 'reference':
         run_reference(a)
     else:
