@@ -1105,8 +1105,10 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     // Cut the walk axis into K pieces (grid.y) when that shortens the sum of the waves; the pieces
     // overlap by p spans.  Needs a stage without a walk-axis filter of its own.
     prm.nsplit = 0;
-    const int rows_w = prm.w_hi > prm.w_lo ? 0 : H.V.N();       // only unfiltered stages: all rows of the axis
-    if (nofilter && rows_w > 0 && a->walk_split != 1 && prm.s_begin == 0 && prm.s_end == H.n) {
+    // rows the pieces partition: all rows of the axis, or the (extended) slab of a filtered stage
+    const int r_lo = nofilter ? 0 : prm.w_ext_lo, r_hi = nofilter ? H.V.N() : prm.w_ext_hi;
+    if (r_hi > r_lo && a->walk_split != 1) {
+        const int nsp = prm.s_end - prm.s_begin;
         int K = 1;
         if (a->walk_split > 1) {
             K = a->walk_split;
@@ -1114,25 +1116,29 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
             const int occ = fn(&prm, -1, use_smem ? smem + ismem + 256 : 0, st);
             if (occ > 0 && a->sm_count > 0) {
                 const long long B = (prm.nthreads + 127) / 128, slots = (long long)a->sm_count * occ;
-                double best = (double)((B + slots - 1) / slots) * H.n;
+                double best = (double)((B + slots - 1) / slots) * nsp;
                 for (int k = 2; k <= PB_WALK_MAXSPLIT; ++k) {
-                    if (H.n / k < 4 * (P + 1)) break;                  // pieces too short to pay for the overlap
-                    const double cost = (double)((k * B + slots - 1) / slots) * ((double)H.n / k + P);
+                    if (nsp / k < 4 * (P + 1)) break;                  // pieces too short to pay for the overlap
+                    // measured on B200 (3D p=3 n=128, stage 2): two pieces are ~10 % faster than the wave
+                    // count alone predicts (shorter-lived blocks balance better), hence the 0.9
+                    const double cost = 0.9 * (double)((k * B + slots - 1) / slots) * ((double)nsp / k + P);
                     if (cost < 0.93 * best) { best = cost; K = k; }
                 }
             }
         }
-        K = std::min(K, std::min(PB_WALK_MAXSPLIT, rows_w));
+        K = std::min(K, std::min(PB_WALK_MAXSPLIT, r_hi - r_lo));
         if (K > 1 && getenv("PB200_DEBUG_SPLIT")) fprintf(stderr, "[pb200] stage %s: walk axis cut into %d pieces\n", name, K);
         if (K > 1) {
             prm.nsplit = K;
             for (int y = 0; y < K; ++y) {
-                const int lo = (int)((long long)rows_w * y / K), hi = (int)((long long)rows_w * (y + 1) / K);
+                const int lo = r_lo + (int)((long long)(r_hi - r_lo) * y / K), hi = r_lo + (int)((long long)(r_hi - r_lo) * (y + 1) / K);
                 prm.sp_w_lo[y] = lo; prm.sp_w_hi[y] = hi;
-                prm.sp_s_begin[y] = H.V.supp[2 * lo];
-                prm.sp_s_end[y] = H.V.supp[2 * (hi - 1) + 1];
-                prm.sp_f_lo[y] = H.U.first[prm.sp_s_begin[y]];
-                prm.sp_f_hi[y] = std::min(H.V.N(), H.U.first[prm.sp_s_end[y] - 1] + P + 1);
+                // spans the rows of the piece see, inside the span range of the stage
+                int sb = std::max(prm.s_begin, H.V.supp[2 * lo]), se = std::min(prm.s_end, H.V.supp[2 * (hi - 1) + 1]);
+                if (se <= sb) { sb = prm.s_begin; se = prm.s_begin + 1; }      // nothing to do: walk one span, retire nothing new
+                prm.sp_s_begin[y] = sb; prm.sp_s_end[y] = se;
+                prm.sp_f_lo[y] = H.U.first[sb];
+                prm.sp_f_hi[y] = std::min(H.V.N(), H.U.first[se - 1] + P + 1);
             }
         }
     }
@@ -1303,7 +1309,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                     p.in_sx = 1; p.in_sc = G1 * Glast;
                     p.out_sx = 1; p.out_smu = G1 * Glast; p.mu_base = S.mu_lo;
                     p.s_begin = S.sa; p.s_end = S.sb;
-                    p.w_mode[0] = 1; p.w_lo = S.ra; p.w_hi = S.rb;
+                    p.w_mode[0] = 1; p.w_lo = S.ra; p.w_hi = S.rb; p.w_ext_lo = S.ra; p.w_ext_hi = S.rb;
                 } else if (k == 1 && dim == 3) {
                     p.X = (int)Glast; p.nthreads = (long long)Mrows * Glast;
                     p.u_begin = S.mu_lo; p.u_base_in = S.mu_lo; p.u_base_out = S.mu_lo;
@@ -1343,7 +1349,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             p.in_sx = 1; p.in_sc = G1;
             p.out_sx = 1; p.out_smu = G1; p.mu_base = S.ext_lo;
             p.s_begin = S.sa; p.s_end = S.sb;
-            p.w_lo = S.ra; p.w_hi = S.rb;
+            p.w_lo = S.ra; p.w_hi = S.rb; p.w_ext_lo = S.ea; p.w_ext_hi = S.eb;
             const int modes2d[3] = {m_dir, m_tr, m_dir};                        // (v,v), (v,d1), (d1,d1)
             if (stiff && a->fused_plans) {
                 p.in[0] = F + 2 * npts; p.in[1] = F + 1 * npts; p.in[2] = F;     // B11, B01, B00
@@ -1403,7 +1409,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.in_sx = 1; p.in_sc = G1 * G2;
         p.out_sx = 1; p.out_smu = G1 * G2; p.mu_base = S.ext_lo;
         p.s_begin = S.sa; p.s_end = S.sb;
-        p.w_lo = S.ra; p.w_hi = S.rb;
+        p.w_lo = S.ra; p.w_hi = S.rb; p.w_ext_lo = S.ea; p.w_ext_hi = S.eb;
         // X1 terms (v,v) (v,d1) (v,d2) (d1,d1) (d1,d2) (d2,d2): which are read through a transposed index?
         const int modes1[6] = {m_dir, m_tr, m_tr, m_dir, m_tr, m_dir};
         if (stiff && !a->fused_plans) {

@@ -71,34 +71,38 @@ struct PbWalkParams {
     // A stage whose lines fill the GPU only 1.x times is cut into `nsplit` pieces along the walk
     // axis: piece y retires the pairs whose row lies in [sp_w_lo[y], sp_w_hi[y]) and walks only the
     // spans those rows see, so that the tail wave is shorter (the pieces overlap by p spans).
-    // Only for stages without a walk-axis filter of their own (w_mode all 0).
-    int nsplit;
+    // The piece filter is applied on top of the stage's own walk-axis filter; `w_ext_lo/hi` is the
+    // row range the pieces partition (all rows for unfiltered stages).
+    int nsplit, w_ext_lo, w_ext_hi;
     int sp_s_begin[PB_WALK_MAXSPLIT], sp_s_end[PB_WALK_MAXSPLIT];
     int sp_w_lo[PB_WALK_MAXSPLIT], sp_w_hi[PB_WALK_MAXSPLIT];
     int sp_f_lo[PB_WALK_MAXSPLIT], sp_f_hi[PB_WALK_MAXSPLIT];
 };
 
+PB_HD bool pb_keep(int mode, int i, int j, int lo, int hi) {
+    const bool ki = (i >= lo && i < hi), kj = (j >= lo && j < hi);
+    return mode == 0 || (mode == 1 && ki) || (mode == 2 && (ki || kj)) || (mode == 3 && ki && (i <= j || !kj));
+}
+
 // the part of the walk axis one thread block (or emulated piece) works on
-struct PbWalkRange { int s_begin, s_end, w_lo, w_hi, f_lo, f_hi; bool split; };
+struct PbWalkRange { int s_begin, s_end, p_lo, p_hi, f_lo, f_hi; bool split; };
 PB_HD PbWalkRange pb_walk_range(const PbWalkParams& prm, int y) {
     PbWalkRange r;
     r.split = prm.nsplit > 1;
     if (r.split) {
         r.s_begin = prm.sp_s_begin[y]; r.s_end = prm.sp_s_end[y];
-        r.w_lo = prm.sp_w_lo[y]; r.w_hi = prm.sp_w_hi[y];
+        r.p_lo = prm.sp_w_lo[y]; r.p_hi = prm.sp_w_hi[y];
         r.f_lo = prm.sp_f_lo[y]; r.f_hi = prm.sp_f_hi[y];
     } else {
         r.s_begin = prm.s_begin; r.s_end = prm.s_end;
-        r.w_lo = prm.w_lo; r.w_hi = prm.w_hi;
+        r.p_lo = 0; r.p_hi = 0x7fffffff;
         r.f_lo = prm.f_lo; r.f_hi = prm.f_hi;
     }
     return r;
 }
-PB_HD int pb_walk_wmode(const PbWalkParams& prm, const PbWalkRange& rg, int o) { return rg.split ? 1 : prm.w_mode[o]; }
-
-PB_HD bool pb_keep(int mode, int i, int j, int lo, int hi) {
-    const bool ki = (i >= lo && i < hi), kj = (j >= lo && j < hi);
-    return mode == 0 || (mode == 1 && ki) || (mode == 2 && (ki || kj)) || (mode == 3 && ki && (i <= j || !kj));
+// retire filter of output o for the pair (i, j) of the walk axis: the stage's own filter and the piece
+PB_HD bool pb_walk_keep(const PbWalkParams& prm, const PbWalkRange& rg, int o, int i, int j) {
+    return pb_keep(prm.w_mode[o], i, j, prm.w_lo, prm.w_hi) && i >= rg.p_lo && i < rg.p_hi;
 }
 
 template <int I> struct PbIC { static constexpr int value = I; };
@@ -267,7 +271,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                 } else {
                     pb_static_for<0, NOUT>([&](auto O) {
                         constexpr int o = decltype(O)::value;
-                        mask |= pb_keep(pb_walk_wmode(prm, rg, o), f + a, f + b, rg.w_lo, rg.w_hi) ? (1 << o) : 0;
+                        mask |= pb_walk_keep(prm, rg, o, f + a, f + b) ? (1 << o) : 0;
                     });
                 }
                 mask &= wantbits;
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
                 const int f = f_lo + t / (2 * P + 1), k = t % (2 * P + 1);
                 const int i = (k <= P) ? f : f + (k - P), j = (k <= P) ? f + k : f;
                 int mask = 0;
-                for (int o = 0; o < Plan::NOUT; ++o) mask |= pb_keep(pb_walk_wmode(prm, rg, o), i, j, rg.w_lo, rg.w_hi) ? (1 << o) : 0;
+                for (int o = 0; o < Plan::NOUT; ++o) mask |= pb_walk_keep(prm, rg, o, i, j) ? (1 << o) : 0;
                 mu = mask ? (mu | (mask << 24)) : -1;
             }
             s_ret[t] = mu;

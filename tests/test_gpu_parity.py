@@ -189,3 +189,14 @@ def test_walk_axis_split(cuda, k):
     pc.check_vs_oracle(3, (2, 3, 1), (2, 7, 3), 'Mass', walk_split=k, geo_name='bspline')
     pc.check_vs_oracle(2, (3, 3), (11, 5), 'Stiffness', walk_split=k)
     pc.check_vs_oracle(3, (2, 2, 2), (2, 6, 3), 'Stiffness', walk_split=k, mult=2)
+
+
+@pytest.mark.parametrize('k', [2, 3])
+def test_walk_axis_split_with_slabs(cuda, ref, monkeypatch, k):
+    monkeypatch.setenv('PB200_OPTS', 'walk_split=%d' % k)
+    pc.check_case(ref, 'a3_nurbs')
+    pc.check_case(ref, 'a2_mixed')
+    pc.check_slabs(ref, 'a3_mixed', 3)
+    pc.check_slabs(ref, 'a2_qa', 2)
+    pc.check_chunked(ref, 'a3_p1')
+    pc.check_vform(ref, 'cd3')
