@@ -9,6 +9,10 @@
 #error "compile with -DPB_P=<degree> -DPB_Q=<nodes per span>"
 #endif
 
+#ifndef PB_LANE_NST
+#define PB_LANE_NST 4     // ring depth of the lane-span kernel (3 stages = 3 resident blocks per SM measured the same)
+#endif
+
 namespace {
 
 template <class Plan>
@@ -73,7 +77,7 @@ int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* strea
         pb_lane_span_kernel<Plan, PB_P, PB_Q><<<grid, 128, 0, (cudaStream_t)stream>>>(*prm, lines_per_warp);
         return (int)cudaGetLastError();
     }
-    constexpr int NST = 4;
+    constexpr int NST = PB_LANE_NST;
     if (lines_per_warp > PbLaneCfg<PB_P, PB_Q>::DQ) return (int)cudaErrorInvalidValue;
     using Cfg = PbLaneCfg<PB_P, PB_Q>;
     const size_t smem = 4 * (size_t)(NST * Plan::NOPS * Cfg::SEG + Cfg::OUTPAD + Cfg::LOSLOTS) * sizeof(double);
