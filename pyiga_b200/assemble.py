@@ -353,6 +353,44 @@ class RestrictedLinearSystem:
         return out
 
 
+################################################################################
+# Integration (pyiga/assemble.py:658-696)
+################################################################################
+
+def integrate(kvs, f, f_physical=False, geo=None):
+    """Integral of `f` over the geometry `geo` or the parameter domain, with the Gauss rule of the
+    spline space (``pyiga/assemble.py:658-696``).  The B-splines sum to one, so the integral is the
+    sum of the L2 inner products of `f` with all basis functions — the load vector of the device
+    path; vector-valued `f` is integrated component by component."""
+    from . import utils
+    dim, kvs_n = _detect_dim(kvs)
+    kvs_t = (kvs_n,) if dim == 1 else tuple(kvs_n)
+    if f_physical:
+        assert geo is not None, 'integrate in physical domain requires geometry'
+    if hasattr(f, 'grid_eval'):
+        raise NotImplementedError('integrate() of spline function objects: pass a callable')
+    # number of components: evaluate once at the centre of the parameter domain
+    mid = [np.array([0.5 * (kv.support()[0] + kv.support()[1])]) for kv in kvs_t]
+    probe = np.asarray(utils.grid_eval_transformed(f, mid, geo) if f_physical else utils.grid_eval(f, mid))
+    extra = probe.shape[dim:]
+    if extra == ():
+        return float(np.sum(inner_products(kvs, f, f_physical=f_physical, geo=geo)))
+
+    def component(idx):
+        def fc(*x):
+            v = f(*x)
+            if isinstance(v, tuple):        # tuple of component arrays (stacked on the last axis by grid_eval)
+                for i in idx:
+                    v = v[i]
+                return v
+            return np.asarray(v)[(Ellipsis,) + idx]
+        return fc
+    out = np.empty(extra)
+    for idx in np.ndindex(*extra):
+        out[idx] = np.sum(inner_products(kvs, component(idx), f_physical=f_physical, geo=geo))
+    return out
+
+
 def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatable=[]):
     """Turn a problem description into an assembler object (``pyiga/assemble.py:914-956``)."""
     if isinstance(problem, str):

@@ -274,6 +274,16 @@ def main():
         kvs1 = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(p1, ns))
         save_csr_into(out, 'pg_%s' % name, assemble.assemble(form, (kvs0, kvs1), geo=geos[gname], bfuns=bfuns, **inputs))
 
+    # ---- 13. integrate (pyiga/assemble.py:658-696; test/test_assemble.py:483-495) -----------------------
+    kvsI = (bspline.make_knots(3, 0.0, 1.0, 4), bspline.make_knots(2, 0.0, 1.0, 5))
+    out['int_qa_one'] = np.array(assemble.integrate(kvsI, lambda x, y: 1.0, geo=geometry.quarter_annulus()))
+    out['int_qa_phys'] = np.array(assemble.integrate(kvsI, lambda x, y: x * y + np.cos(x), f_physical=True, geo=geometry.quarter_annulus()))
+    out['int_par'] = np.array(assemble.integrate(kvsI, lambda x, y: x * x + y))
+    out['int_vec'] = np.array(assemble.integrate(kvsI, lambda x, y: (x, y * x)))     # vector f: parameter domain only in the reference
+    kvs3, _ = cases['a3_tb']
+    out['int_3d'] = np.array(assemble.integrate(kvs3, lambda x, y, z: x + y * z, f_physical=True, geo=geos['tnb']))
+    out['int_1d'] = np.array(assemble.integrate(bspline.make_knots(3, 0.0, 2.0, 5), lambda x: x * x))
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

@@ -318,6 +318,25 @@ def check_linear_forms(ref):
     assert np.array_equal(asm.multi_entries([0, 5, 7]), vec.ravel()[[0, 5, 7]])
 
 
+def check_integrate(ref):
+    """assemble.integrate (pyiga/assemble.py:658-696)"""
+    from pyiga_b200 import assemble, bspline, geometry
+    kvsI = (bspline.make_knots(3, 0.0, 1.0, 4), bspline.make_knots(2, 0.0, 1.0, 5))
+    qa = geometry.quarter_annulus()
+    tol = 1e-12
+    assert abs(assemble.integrate(kvsI, lambda x, y: 1.0, geo=qa) - ref['int_qa_one']) <= tol * abs(ref['int_qa_one'])
+    assert abs(3 * np.pi / 4 - assemble.integrate(kvsI, lambda x, y: 1.0, geo=qa)) < 1e-8
+    got = assemble.integrate(kvsI, lambda x, y: x * y + np.cos(x), f_physical=True, geo=qa)
+    assert abs(got - ref['int_qa_phys']) <= tol * abs(ref['int_qa_phys'])
+    assert abs(assemble.integrate(kvsI, lambda x, y: x * x + y) - ref['int_par']) <= tol * abs(ref['int_par'])
+    assert_close_rel(assemble.integrate(kvsI, lambda x, y: (x, y * x)), ref['int_vec'], what='integrate vector')
+    kvs3 = make_space(ref, 'a3_tb')
+    got = assemble.integrate(kvs3, lambda x, y, z: x + y * z, f_physical=True, geo=make_geo(ref, 'tnb'))
+    assert abs(got - ref['int_3d']) <= tol * abs(ref['int_3d'])
+    got = assemble.integrate(bspline.make_knots(3, 0.0, 2.0, 5), lambda x: x * x)
+    assert abs(got - ref['int_1d']) <= tol * abs(ref['int_1d'])
+
+
 def check_edge_cases(ref):
     """degenerate and unusual inputs the reference accepts"""
     import pytest

@@ -140,3 +140,7 @@ def test_walk_axis_split_with_slabs(emu, ref, monkeypatch, k):
     pc.check_slabs(ref, 'a2_qa', 2)
     pc.check_chunked(ref, 'a3_p1')
     pc.check_vform(ref, 'cd3')
+
+
+def test_integrate(emu, ref):
+    pc.check_integrate(ref)

@@ -200,3 +200,7 @@ def test_walk_axis_split_with_slabs(cuda, ref, monkeypatch, k):
     pc.check_slabs(ref, 'a2_qa', 2)
     pc.check_chunked(ref, 'a3_p1')
     pc.check_vform(ref, 'cd3')
+
+
+def test_integrate(cuda, ref):
+    pc.check_integrate(ref)
