@@ -1674,6 +1674,9 @@ static void csr_pattern_rows(int L, const int* Nv, const int* Nu, const int* con
                              int ra, long long r_begin, long long r_end, IT* indptr, IT* indices, long long off0) {
     const long long m1 = L > 1 ? M[1] : 1, m2 = L > 2 ? M[2] : 1;
     const long long inner = (long long)(L > 1 ? Nv[1] : 1) * (L > 2 ? Nv[2] : 1);
+    const IT* prev = nullptr;
+    long long prev_r = -2;
+    int prev_nb = 0, prev_j0 = 0, prev_len = 0;
     for (long long r = r_begin; r < r_end; ++r) {
         int i[3] = {0, 0, 0};
         long long t = r;
@@ -1686,18 +1689,27 @@ static void csr_pattern_rows(int L, const int* Nv, const int* Nu, const int* con
         if (L == 3) off += (long long)nb[0] * ((long long)rs[1][i[1]] * m2 + (long long)nb[1] * rs[2][i[2]]);
         indptr[r] = (IT)(off0 + off);
         IT* out = indices + off;
-        if (L == 2) {
+        const int len = nb[0] * nb[1] * nb[2];
+        // interior rows: the pattern of (.., i_last + 1) is the pattern of (.., i_last) shifted by one column
+        if (prev != nullptr && r == prev_r + 1 && i[L - 1] > 0 && nb[L - 1] == prev_nb && j0[L - 1] == prev_j0 + 1 && len == prev_len) {
+            const IT* __restrict src = prev;
+            IT* __restrict dst = out;
+            for (int e = 0; e < len; ++e) dst[e] = src[e] + 1;
+        } else if (L == 2) {
+            IT* o = out;
             for (int k0 = 0; k0 < nb[0]; ++k0) {
                 const long long base = (long long)(j0[0] + k0) * Nu[1] + j0[1];
-                for (int k1 = 0; k1 < nb[1]; ++k1) *out++ = (IT)(base + k1);
+                for (int k1 = 0; k1 < nb[1]; ++k1) *o++ = (IT)(base + k1);
             }
         } else {
+            IT* o = out;
             for (int k0 = 0; k0 < nb[0]; ++k0)
                 for (int k1 = 0; k1 < nb[1]; ++k1) {
                     const long long base = ((long long)(j0[0] + k0) * Nu[1] + j0[1] + k1) * Nu[2] + j0[2];
-                    for (int k2 = 0; k2 < nb[2]; ++k2) *out++ = (IT)(base + k2);
+                    for (int k2 = 0; k2 < nb[2]; ++k2) *o++ = (IT)(base + k2);
                 }
         }
+        prev = out; prev_r = r; prev_nb = nb[L - 1]; prev_j0 = j0[L - 1]; prev_len = len;
     }
     (void)inner;
 }
