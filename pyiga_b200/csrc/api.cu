@@ -365,6 +365,7 @@ struct pb200_assembler {
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
     bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
     int lane_lines = 64;                                // lines per warp of the lane-span kernel (<= PbLaneCfg::DQ)
+    bool walk_rot = true;                               // rotating-window walk on regular axes (no register shifts)
     int walk_split = 0;                                 // pieces of the walk axis: 0 = choose by occupancy, 1 = never, K = always K
     int sm_count = 0;                                   // multiprocessors of the device
     bool mirror_opt = true;                             // symmetric forms: compute the upper half of the final stage, mirror the rest
@@ -397,6 +398,7 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!a || !name) return fail(PB200_EINVAL, "null argument");
     if (!strcmp(name, "force_walk")) { a->force_walk = value != 0; return 0; }
     if (!strcmp(name, "lane_v1")) { a->lane_v1 = value != 0; return 0; }
+    if (!strcmp(name, "walk_rot")) { a->walk_rot = value != 0; return 0; }
     if (!strcmp(name, "walk_split")) { if (value < 0 || value > PB_WALK_MAXSPLIT) return fail(PB200_EINVAL, "walk_split must be in 0..%d", PB_WALK_MAXSPLIT); a->walk_split = value; return 0; }
     if (!strcmp(name, "lane_lines")) { if (value < 1 || value > 64) return fail(PB200_EINVAL, "lane_lines must be in 1..64"); a->lane_lines = value; return 0; }
     if (!strcmp(name, "fused_plans")) { a->fused_plans = value != 0; return 0; }
@@ -1087,6 +1089,7 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     prm.first = D.first_u;
     prm.V2 = D.Vu;
     prm.ret_mu = D.ret_mu;
+    prm.regular = (a->lane_ok[axis] && a->walk_rot) ? 1 : 0;
     // final stages (node axis contiguous, one output, single interior knots): warp-per-line kernel
     bool nofilter = true;
     for (int o = 0; o < PB_WALK_MAXOUT; ++o) nofilter = nofilter && prm.w_mode[o] == 0;

@@ -74,6 +74,7 @@ struct PbWalkParams {
     // The piece filter is applied on top of the stage's own walk-axis filter; `w_ext_lo/hi` is the
     // row range the pieces partition (all rows for unfiltered stages).
     int nsplit, w_ext_lo, w_ext_hi;
+    int regular;                    // every span advances `first` by one: the rotating-window walk may be used
     int sp_s_begin[PB_WALK_MAXSPLIT], sp_s_end[PB_WALK_MAXSPLIT];
     int sp_w_lo[PB_WALK_MAXSPLIT], sp_w_hi[PB_WALK_MAXSPLIT];
     int sp_f_lo[PB_WALK_MAXSPLIT], sp_f_hi[PB_WALK_MAXSPLIT];
@@ -176,7 +177,7 @@ struct PbWalkTables {       // where the thread finds the walk-axis tables (shar
     const int* ret_mu;      // indexed by absolute function * (2P+1); the staged copy (template flag ENC
                             // of the walk) carries the per-output slab filter in bits 24..27
 };
-template <class Plan, int P, int Q, bool ENC, class Loader>
+template <class Plan, int P, int Q, bool ENC, bool ROT, class Loader>
 PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, long long tid, const PbWalkTables& tb, Loader& ld);
 
 template <class Plan, int P, int Q, int NPF = 1>
@@ -185,10 +186,11 @@ PB_HD void pb_walk_line(const PbWalkParams& prm, long long tid, const double* __
     PbWalkTables tb;
     tb.V = Vt; tb.first = prm.first; tb.ret_mu = prm.ret_mu;
     const PbWalkRange rg = pb_walk_range(prm, piece);
-    pb_walk_line_impl<Plan, P, Q, false>(prm, rg, tid, tb, ld);
+    if (prm.regular) pb_walk_line_impl<Plan, P, Q, false, true>(prm, rg, tid, tb, ld);
+    else pb_walk_line_impl<Plan, P, Q, false, false>(prm, rg, tid, tb, ld);
 }
 
-template <class Plan, int P, int Q, bool ENC, class Loader>
+template <class Plan, int P, int Q, bool ENC, bool ROT, class Loader>
 PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, long long tid, const PbWalkTables& tb, Loader& ld) {
     const double* __restrict__ Vt = tb.V;
     constexpr int P1 = P + 1;
@@ -298,6 +300,116 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
 
     int f = tb.first[rg.s_begin];
     ld.prime(rg.s_begin);
+
+    if constexpr (ROT) {
+        // Regular axis (every span advances the first active function by one): the window is not
+        // shifted but ROTATED.  On the k-th span of the walk the pair (f+a, f+b) lives in
+        // acc[(a+k) % (P+1)][(b+k) % (P+1)]; the span loop is unrolled P+1 times so that all indices
+        // are compile-time constants and no register moves are needed.  The row / column that
+        // enters the window is not cleared either: its first contribution of the span assigns.
+        auto retire_rot = [&](auto RC, int fr) {            // RC: phase in which function fr is row/column 0
+            constexpr int R = decltype(RC)::value;
+            const int* rm = tb.ret_mu + (long long)fr * (2 * P + 1);
+#pragma unroll
+            for (int k = 0; k <= 2 * P; ++k) {
+                const int mu = rm[k];
+                const int a = (k <= P) ? 0 : (k - P);
+                const int b = (k <= P) ? k : 0;
+                if (mu >= 0) {
+                    int band = mu, mask = 0;
+                    if constexpr (ENC) {
+                        band = mu & 0xFFFFFF;
+                        mask = mu >> 24;
+                    } else {
+                        pb_static_for<0, NOUT>([&](auto O) {
+                            constexpr int o = decltype(O)::value;
+                            mask |= pb_walk_keep(prm, rg, o, fr + a, fr + b) ? (1 << o) : 0;
+                        });
+                    }
+                    mask &= wantbits;
+                    const long long boff = (long long)(band - mu_base) * (long long)smu;
+                    pb_static_for<0, NOUT>([&](auto O) {
+                        constexpr int o = decltype(O)::value;
+                        if (mask & (1 << o)) outp[o][boff] = acc[o][(a + R) % P1][(b + R) % P1];
+                    });
+                }
+            }
+        };
+        auto node = [&](auto RC, auto GQ, const double (&xc)[Q][NOPS], int s) {
+            constexpr int R = decltype(RC)::value, gq = decltype(GQ)::value;
+            const double* Vn = Vt + (long long)(s * Q + gq) * (2 * P1);
+            double D[2][P1];
+#pragma unroll
+            for (int a = 0; a < P1; ++a) { D[0][a] = Vn[a]; D[1][a] = Vn[P1 + a]; }
+            pb_static_for<0, NOUT>([&](auto O) {
+                constexpr int o = decltype(O)::value;
+                constexpr bool by_fu = pb_group_by_fu<Plan>(o);
+                constexpr int fl_first = ((by_fu ? pb_count_fu<Plan>(o, 0) : pb_count_ft<Plan>(o, 0)) > 0) ? 0 : 1;
+                pb_static_for<0, 2>([&](auto FL) {
+                    constexpr int fl = decltype(FL)::value;
+                    constexpr int cnt = by_fu ? pb_count_fu<Plan>(o, fl) : pb_count_ft<Plan>(o, fl);
+                    if constexpr (cnt > 0) {
+                        double y[P1];
+                        constexpr int lead = pb_first_in_group<Plan>(o, fl, by_fu);
+                        pb_static_for<0, NOPS>([&](auto I) {
+                            constexpr int i = decltype(I)::value;
+                            constexpr PbOp op = Plan::op(i);
+                            if constexpr (op.out == o && (by_fu ? op.fu : op.ft) == fl) {
+                                constexpr int other = by_fu ? op.ft : op.fu;
+                                const double xv = xc[gq][i];
+                                if constexpr (i == lead) {
+#pragma unroll
+                                    for (int c = 0; c < P1; ++c) y[c] = D[other][c] * xv;
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < P1; ++c) y[c] = fma(D[other][c], xv, y[c]);
+                                }
+                            }
+                        });
+                        constexpr bool assign_new = (gq == 0 && fl == fl_first);    // first contribution of the span
+#pragma unroll
+                        for (int a = 0; a < P1; ++a)
+#pragma unroll
+                            for (int b = 0; b < P1; ++b) {
+                                const double l = by_fu ? y[a] : D[fl][a], r = by_fu ? D[fl][b] : y[b];
+                                double& dst = acc[o][(a + R) % P1][(b + R) % P1];
+                                if (assign_new && (a == P || b == P)) dst = l * r;
+                                else dst = fma(l, r, dst);
+                            }
+                    }
+                });
+            });
+        };
+        int s = rg.s_begin;
+        while (s < rg.s_end) {
+            pb_static_for<0, P1>([&](auto RC) {
+                constexpr int R = decltype(RC)::value;
+                if (s < rg.s_end) {
+                    if (s > rg.s_begin) {       // the function that left the span range: row/column 0 of the previous phase
+                        retire_rot(PbIC<(R + P) % P1>{}, f);
+                        ++f;
+                    }
+                    double xc[Q][NOPS];
+                    ld.next(s, xc);
+                    pb_static_for<0, Q>([&](auto GQ) { node(RC, GQ, xc, s); });
+                    ++s;
+                }
+            });
+        }
+        // flush: the functions still in the window, starting in the phase of the last span
+        const int last_phase = (rg.s_end - rg.s_begin - 1) % P1;
+        pb_static_for<0, P1>([&](auto PH) {
+            constexpr int ph = decltype(PH)::value;
+            if (ph == last_phase) {
+                pb_static_for<0, P1>([&](auto T) {
+                    constexpr int t = decltype(T)::value;
+                    if (f < prm.N) retire_rot(PbIC<(ph + t) % P1>{}, f);
+                    ++f;
+                });
+            }
+        });
+        return;
+    }
 
     for (int s = rg.s_begin; s < rg.s_end; ++s) {
         const int fs = tb.first[s];
@@ -538,12 +650,13 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_kernel(const __grid_constan
             // NPF doubles as the ring depth of the asynchronous loader
             PbAsyncLoader<Plan, Q, NPF> ld;
             ld.ring = reinterpret_cast<double*>(pb_smem_raw + vbytes + (use_smem ? ibytes : 0)) + threadIdx.x;
-            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, rg, tid, tb, ld);
-            else pb_walk_line_impl<Plan, P, Q, false>(prm, rg, tid, tb, ld);
+            if (use_smem && prm.regular) pb_walk_line_impl<Plan, P, Q, true, true>(prm, rg, tid, tb, ld);
+            else if (use_smem) pb_walk_line_impl<Plan, P, Q, true, false>(prm, rg, tid, tb, ld);
+            else pb_walk_line_impl<Plan, P, Q, false, false>(prm, rg, tid, tb, ld);
         } else {
             PbRegLoader<Plan, Q> ld;
-            if (use_smem) pb_walk_line_impl<Plan, P, Q, true>(prm, rg, tid, tb, ld);
-            else pb_walk_line_impl<Plan, P, Q, false>(prm, rg, tid, tb, ld);
+            if (use_smem) pb_walk_line_impl<Plan, P, Q, true, false>(prm, rg, tid, tb, ld);
+            else pb_walk_line_impl<Plan, P, Q, false, false>(prm, rg, tid, tb, ld);
         }
     }
 }
