@@ -84,7 +84,7 @@ struct PbPlanGen4 {
     }
 };
 struct PbPlanS1A {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 3, NPF = 3;
     static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
@@ -93,7 +93,7 @@ struct PbPlanS1A {
     }
 };
 struct PbPlanS1B {
-    static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
+    static constexpr int NOPS = 3, NOUT = 3, MINB = 3, NPF = 3;
     static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
     static constexpr PbOp op(int i) {
