@@ -416,7 +416,7 @@ def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatab
     raise TypeError("invalid type for 'problem': {}".format(type(problem)))
 
 
-def assemble(problem, kvs, args=None, bfuns=None, boundary=None, symmetric=False, format='csr',
+def assemble(problem, kvs=None, args=None, bfuns=None, boundary=None, symmetric=False, format='csr',
              layout='blocked', **kwargs):
     """Assemble a matrix or vector for a variational form given as string, :class:`VForm`,
     assembler class or assembler object (``pyiga/assemble.py:837-897``)."""

@@ -556,6 +556,16 @@ def check_partial_rows(ref):
             pass
         else:
             raise AssertionError('out-of-range row accepted')
+    # a compiled variational form (what HDiscretization._assemble_level hands over, pyiga/_hdiscr.py:36-57)
+    from helpers import VFORMS
+    form, inputs, case, gname = VFORMS['cd3']
+    kvs = make_space(ref, case)
+    asm = assemble.instantiate_assembler(form, kvs, dict(inputs, geo=make_geo(ref, gname)))
+    full = assemble.assemble(asm).tocsr()
+    rows = np.array([0, 7, full.shape[0] // 2, full.shape[0] - 1])
+    part = assemble.assemble_partial_rows(asm, rows)
+    assert abs(part[rows] - full[rows]).max() <= RTOL * abs(full).max()
+    assert part.nnz == full[rows].nnz
 
 
 def check_boundary_forms(ref):
