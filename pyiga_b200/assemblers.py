@@ -343,8 +343,9 @@ class _ScalarAssemblerBase(_AssemblerProtocol):
 class _FormBlock:
     """One scalar form  sum_t c_t d^bt v d^bu u  on the device: tables, coefficient upload, fields."""
 
-    def __init__(self, kvs, nqp, dim, arity, coefs, geo, gaussgrid, quad=None, kvs_test=None):
+    def __init__(self, kvs, nqp, dim, arity, coefs, geo, gaussgrid, quad=None, kvs_test=None, host_pullback=False):
         self.dim, self.arity, self.kvs = dim, arity, kvs
+        self.host_pullback = host_pullback
         self.gaussgrid = gaussgrid
         self._grid_shape = tuple(len(g) for g in gaussgrid)
         self.keys = sorted(coefs)
@@ -354,13 +355,50 @@ class _FormBlock:
                 for ap in ([-1] if bu < 0 else [0] if bu == 0 else range(1, dim + 1)):
                     pairs.add((bp, ap))
         terms = [(f, bp, ap) for f, (bp, ap) in enumerate(sorted(pairs))]
+        self.terms = terms
         self.dev = DeviceAssembler(kvs, kvs_test or kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
         self.compute_fields(coefs, geo)
+
+    def _compute_fields_host(self, coefs, geo):
+        """Pull the physical terms back to the parameter domain with numpy and upload the fields:
+            C[bp][ap] = gw * sqrt(det J^T J) * sum_t c_t T[bt][bp] T[bu][ap],
+        T[0][0] = 1, T[1+a][1+k] = G[a][d-1-k], G = J (J^T J)^-1 (the tangential gradient is G grad_xi).
+        Used for manifolds (J is (d+1) x d); the square case runs on the device (PbProgGeneral)."""
+        dev, be = self.dev, self.dev.be
+        d = self.dim
+        J = np.asarray(geo.grid_jacobian(self.gaussgrid), dtype=float)          # grid + (gd, d), xi_0 = last axis
+        gd = J.shape[-2]
+        JtJ = np.einsum('...ai,...aj->...ij', J, J)
+        G = np.einsum('...ai,...ij->...aj', J, np.linalg.inv(JtJ))
+        W = np.sqrt(np.linalg.det(JtJ))
+        for k in range(d):
+            shp = [1] * d
+            shp[k] = -1
+            W = W * np.asarray(dev.gaussweights[k]).reshape(shp)
+        T = np.zeros(self._grid_shape + (gd + 1, d + 1))
+        T[..., 0, 0] = 1.0
+        for a in range(gd):
+            for k in range(d):
+                T[..., 1 + a, 1 + k] = G[..., a, d - 1 - k]
+        fields = np.zeros((len(self.terms),) + self._grid_shape)
+        for f, bp, ap in self.terms:
+            acc = 0.0
+            for (bt, bu) in self.keys:
+                c = coefs[(bt, bu)]
+                cv = c.scale * (np.broadcast_to(c.arr, self._grid_shape) if c.arr is not None else 1.0)
+                tu = 1.0 if ap < 0 else T[..., bu, ap]
+                acc = acc + cv * T[..., bt, bp] * tu
+            fields[f] = W * acc
+        buf = be.from_host(np.ascontiguousarray(fields).ravel())
+        dev.fields = buf
+        _device.check(be.lib.pb200_asm_bind_fields(dev.handle, be.ptr(buf)))
 
     def compute_fields(self, coefs, geo):
         dev, be = self.dev, self.dev.be
         if sorted(coefs) != self.keys:
             raise RuntimeError('update() changed the structure of the form')
+        if self.host_pullback:
+            return self._compute_fields_host(coefs, geo)
         arrays, index = [], {}
         phys = (_lib.PhysTerm * len(coefs))()
         for t, key in enumerate(self.keys):
@@ -413,7 +451,8 @@ class GenericFormAssembler(_AssemblerProtocol):
             kvs_test = None
         geo = args['geo']
         assert geo.sdim == d, "Geometry has wrong source dimension"
-        assert geo.dim == d, "Geometry has wrong dimension"
+        assert geo.dim == getattr(vf, 'geo_dim', d), "Geometry has wrong dimension"
+        self._surface = geo.dim != d            # manifold in R^(d+1): fields are pulled back on the host
         self.arity = vf.arity
         self.nqp = max(kv.p for kv in kvs + (kvs_test or ())) + 1
         self.kvs = (kvs, kvs_test or kvs)
@@ -431,13 +470,15 @@ class GenericFormAssembler(_AssemblerProtocol):
         self._env = {}
         if self._bd is not None:
             self._boundary_fields()
+        if self._surface:
+            self._surface_fields()
         for name, shape, physical, _upd in vf.inputs:
             self._env[name] = self._eval_input(args[name], shape, physical)
         for name, shape in vf.params:
             self._env[name] = np.asarray(args[name], dtype=float)
         if any(_mentions_x(e) for e in vf.exprs):
             X = self._physical_points()
-            self._env['@x'] = np.stack([X[..., i] for i in range(d)])
+            self._env['@x'] = np.stack([X[..., i] for i in range(X.shape[-1])])
         nc_u, nc_v = vf.numcomp
         self._vec = bool(vf.vec)
         self._nc = (nc_u or 1, nc_v or 1)          # (trial, test) components
@@ -445,7 +486,7 @@ class GenericFormAssembler(_AssemblerProtocol):
             self.num_components = lambda: self._nc
         self.blocks = {}
         for blk, coefs in self._analyse().items():
-            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid, quad=quad, kvs_test=kvs_test)
+            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid, quad=quad, kvs_test=kvs_test, host_pullback=self._surface)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
 
@@ -489,6 +530,21 @@ class GenericFormAssembler(_AssemblerProtocol):
         self._env['@ds'] = np.ascontiguousarray(norm)
         sign = -1.0 if bdside == 0 else 1.0
         self._env['@n'] = np.stack([np.ascontiguousarray(sign * g[..., i] / norm) for i in range(d)])
+
+    def _surface_fields(self):
+        """surface integrals over a manifold (`ds` without `boundary`, geo: R^d -> R^(d+1)): the measure
+        sqrt(det J^T J) is applied by the host pullback of the fields; the unit normal (surfaces in
+        R^3, curves in R^2) is a coefficient field (``pyiga/vform.py:202-211``)."""
+        J = np.asarray(self._geo.grid_jacobian(self.gaussgrid), dtype=float)    # grid + (d+1, d)
+        self._env['@ds'] = 1.0
+        if J.shape[-2:] == (3, 2):
+            nrm = np.cross(J[..., :, 0], J[..., :, 1])
+        elif J.shape[-2:] == (2, 1):
+            nrm = np.stack([J[..., 1, 0], -J[..., 0, 0]], axis=-1)
+        else:
+            return
+        nrm = nrm / np.sqrt((nrm * nrm).sum(axis=-1, keepdims=True))
+        self._env['@n'] = np.stack([np.ascontiguousarray(nrm[..., i]) for i in range(nrm.shape[-1])])
 
     def _bd_select(self, arr, arity):
         """slice the band / dof axis of the stand-in normal axis down to the boundary function"""

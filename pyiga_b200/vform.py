@@ -401,6 +401,14 @@ def outer(a, b):
     return Literal([x * y for x in a for y in b], (len(a), len(b)))
 
 
+def cross(a, b):
+    """cross product of two 3-vectors (``pyiga/vform.py`` cross)"""
+    a, b = as_expr(a), as_expr(b)
+    if a.shape != (3,) or b.shape != (3,):
+        raise ValueError('cross() needs two vectors of length 3')
+    return Literal([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], (3,))
+
+
 def norm(x):
     return sqrt(inner(x, x))
 
@@ -420,18 +428,24 @@ class VForm:
     """Abstract description of a variational form (API after ``pyiga/vform.py:162-350``)."""
 
     def __init__(self, dim, geo_dim=None, boundary=False, arity=2, spacetime=False):
-        if spacetime or (geo_dim is not None and geo_dim != dim):
-            raise NotImplementedError('surface and space-time forms are not part of the device path')
+        if spacetime:
+            raise NotImplementedError('space-time forms are not part of the device path')
         self.dim, self.arity = dim, arity
+        # integrals over a dim-dimensional manifold in R^(dim+1): `geo` maps R^dim -> R^geo_dim
+        self.geo_dim = dim if geo_dim is None else int(geo_dim)
+        if self.geo_dim not in (dim, dim + 1):
+            raise ValueError('geo_dim must be dim (volume) or dim + 1 (surface integral)')
+        if boundary and self.geo_dim != dim:
+            raise NotImplementedError('boundary integrals of surface forms')
         self.boundary = bool(boundary)
         self.ds = Measure(surface=True)         # boundary forms: integrate with `* ds`
-        self.normal = Input('@n', (dim,))       # outer unit normal (boundary forms)
+        self.normal = Input('@n', (self.geo_dim,))      # outer unit normal (boundary forms) / surface normal
         self.vec = False
         self.exprs = []
         self.inputs = []        # [(name, shape, physical, updatable)]
         self.params = []        # [(name, shape)]
         self.dx = Measure()
-        self.Geo = Input('@x', (dim,))
+        self.Geo = Input('@x', (self.geo_dim,))
         self.numcomp = (None, None)
 
     def basisfuns(self, components=(None, None), spaces=(0, 0)):
@@ -451,12 +465,12 @@ class VForm:
             components = tuple(1 if c is None else int(c) for c in components)
             self.vec = True
         v = BasisFun('v', 'test', components[-1])
-        v._dim = self.dim
+        v._dim = self.geo_dim                       # number of physical coordinates = length of grad()
         self.numcomp = (components[0] if self.arity == 2 else None, components[-1])   # (trial, test)
         if self.arity == 1:
             return v
         u = BasisFun('u', 'trial', components[0])
-        u._dim = self.dim
+        u._dim = self.geo_dim
         return u, v
 
     def input(self, name, shape=(), physical=False, updatable=False):
@@ -500,7 +514,11 @@ def _check_input_field(kvs, f):
     if hasattr(f, 'grid_eval') and hasattr(f, 'kvs'):
         return tuple(f.output_shape()), False
     mid = tuple(0.5 * (kv.support()[0] + kv.support()[1]) for kv in kvs)
-    return np.shape(f(*mid)), True
+    try:
+        return np.shape(f(*mid)), True
+    except TypeError:
+        # a function of the physical coordinates of a surface form takes one argument more
+        return np.shape(f(*(mid + (mid[-1],)))), True
 
 
 def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
@@ -516,8 +534,6 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
     if 'ds' in words:
         if 'dx' in words:
             raise RuntimeError("got both 'dx' and 'ds' - is this a volume or a surface integral?")
-        if not boundary:
-            raise NotImplementedError('surface integrals (manifolds) are not part of the device path')
     spaces = None
     if bfuns is None:
         names, comps = sorted(words & {'u', 'v'}), None
@@ -530,7 +546,8 @@ def parse_vf(expr, kvs, args=dict(), bfuns=None, boundary=False, updatable=[]):
             spaces.append(bf[2] if len(bf) > 2 else 0)
     if len(names) not in (1, 2):
         raise ValueError('arity should be 1 or 2')
-    vf = VForm(dim=dim, boundary=bool(boundary), arity=len(names))
+    geo_dim = dim + 1 if ('ds' in words and not boundary) else dim
+    vf = VForm(dim=dim, geo_dim=geo_dim, boundary=bool(boundary), arity=len(names))
     loc = {}
     if vf.arity == 1:
         loc[names[0]] = vf.basisfuns(components=tuple(comps) if comps else (None,))
@@ -605,7 +622,7 @@ def compile_vform(vf):
     """Return an assembler *class* for the form, like ``pyiga.compile.compile_vform``
     (``pyiga/compile.py:120-132``); no code is generated — the class analyses the form when it is
     instantiated on a concrete space."""
-    input_shapes = {'geo': (vf.dim,)}
+    input_shapes = {'geo': (vf.geo_dim,)}
     input_shapes.update({name: shape for name, shape, _, _ in vf.inputs})
     param_shapes = {name: shape for name, shape in vf.params}
 

@@ -284,6 +284,17 @@ def main():
     out['int_3d'] = np.array(assemble.integrate(kvs3, lambda x, y, z: x + y * z, f_physical=True, geo=geos['tnb']))
     out['int_1d'] = np.array(assemble.integrate(bspline.make_knots(3, 0.0, 2.0, 5), lambda x: x * x))
 
+    # ---- 14. surface integrals over manifolds (test/test_assemble.py:314-334) --------------------------
+    from helpers import SFORMS
+    cyl3 = geometry.tensor_product(geometry.line_segment(0.0, 1.0), geometry.quarter_annulus())
+    for name, (form, bfuns, inputs, ps, ns, side) in SFORMS.items():
+        kvsS = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(ps, ns))
+        R = assemble.assemble(form, kvsS, geo=cyl3.boundary(side), bfuns=bfuns, **inputs)
+        if scipy.sparse.issparse(R):
+            save_csr_into(out, 'sf_%s' % name, R)
+        else:
+            out['sf_%s' % name] = np.asarray(R)
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

@@ -112,3 +112,12 @@ PGFORMS = {
     'pg3': ('(c * u * v + inner(b, grad(u)) * v) * dx', [('u', 1, 0), ('v', 1, 1)],
             {'c': lambda x, y, z: 1.0 + x * z, 'b': lambda x, y, z: (y, -x, 1.0)}, (3, 2, 2), (2, 3, 3), (3, 2, 4), 'tnb'),
 }
+
+# surface integrals over a manifold (geo: R^2 -> R^3; the reference supports them without derivatives
+# of the basis functions only, and probes input callables with 2 arguments before calling them with 3): name -> (form, bfuns, inputs, (degrees), (spans), side of the 3D cylinder)
+SFORMS = {
+    'area': ('v * ds', None, {}, (3, 2), (4, 5), 'right'),
+    'smass': ('u * v * ds', None, {}, (2, 3), (3, 4), 'left'),
+    'sflux': ('inner(g, n) * v * ds', None, {'g': lambda *X: (X[0], X[1] * X[-1], 1.0 + X[0])}, (2, 2), (3, 3), 'back'),
+    'sreact': ('c * u * v * ds', None, {'c': lambda *X: 1.0 + X[0] * X[1] + X[-1]}, (2, 2), (4, 4), 'left'),
+}

@@ -646,3 +646,80 @@ def check_csr_pattern_host(ref):
             ds.csr_pattern_host(got_ptr, got_idx, row0=(ra, rb), indptr_offset=5, nthreads=nthr)
             assert np.array_equal(got_ptr, want_ptr + 5), (case, ra, rb)
             assert np.array_equal(got_idx, want_idx), (case, ra, rb)
+
+
+def check_boundary_reference_tests():
+    """the reference's own boundary-integral tests with analytic answers
+    (test/test_assemble.py:336-400: test_assemble_boundary_vector, test_assemble_boundary_matrix)"""
+    from pyiga_b200 import bspline, geometry
+    from pyiga_b200.assemble import assemble, stiffness
+    kvs = 3 * (bspline.make_knots(3, 0.0, 1.0, 3),)
+    geo_3d = geometry.tensor_product(geometry.line_segment(0.0, 1.0), geometry.quarter_annulus())
+    f = assemble('v * ds', kvs, geo=geo_3d, boundary='left')
+    assert f.shape == (6, 6, 1)
+    assert np.allclose(f.sum(), (2 * 1 * np.pi) / 4)
+    assert np.allclose(assemble('v * ds', kvs, geo=geo_3d, boundary='right').sum(), (2 * 2 * np.pi) / 4)
+    assert np.allclose(assemble('v * ds', kvs, geo=geo_3d, boundary='bottom').sum(), 1.0)
+    assert np.allclose(assemble('v * ds', kvs, geo=geo_3d, boundary='top').sum(), 1.0)
+    assert np.allclose(assemble('v * ds', kvs, geo=geo_3d, boundary='front').sum(), (2 ** 2 - 1 ** 2) * np.pi / 4)
+    assert np.allclose(assemble('v * ds', kvs, geo=geo_3d, boundary='back').sum(), (2 ** 2 - 1 ** 2) * np.pi / 4)
+    ann = (2 ** 2 - 1 ** 2) * np.pi / 4
+    for bd, want in [('left', [-1, -1, 0]), ('right', [2, 2, 0]), ('bottom', [0, -1, 0]), ('top', [-1, 0, 0]),
+                     ('front', [0, 0, -ann]), ('back', [0, 0, ann])]:
+        nv = assemble('inner(v, n) * ds', kvs, bfuns=[('v', 3)], geo=geo_3d, boundary=bd, layout='packed')
+        assert np.allclose(nv.sum(axis=(0, 1, 2)), want), (bd, nv.sum(axis=(0, 1, 2)))
+    kvs2 = 2 * (bspline.make_knots(3, 0.0, 1.0, 3),)
+    sq = geometry.unit_square()
+    for bd, want in [('left', [-1, 0]), ('right', [1, 0]), ('bottom', [0, -1]), ('top', [0, 1])]:
+        nv = assemble('inner(v, n) * ds', kvs2, bfuns=[('v', 2)], geo=sq, boundary=bd, layout='packed')
+        assert np.allclose(nv.sum(axis=(0, 1)), want), (bd, nv.sum(axis=(0, 1)))
+    kvs = (bspline.make_knots(3, 0.0, 1.0, 3), bspline.make_knots(3, 0.0, 1.0, 4), bspline.make_knots(3, 0.0, 1.0, 5))
+    A = assemble('inner(grad(u), grad(v)) * ds', kvs, geo=geo_3d, boundary='left')
+    assert A.shape == (6 * 7, 6 * 7)
+    A = assemble('inner(grad(u), grad(v)) * ds', kvs, geo=geo_3d, boundary='top')
+    assert A.shape == (6 * 8, 6 * 8)
+    # tangential components only: the 2D Laplacian of the plane face 'front'
+    A = assemble('inner(cross(n, grad(u)), cross(n, grad(v))) * ds', kvs, geo=geo_3d, boundary='front')
+    assert A.shape == (7 * 8, 7 * 8)
+    A2 = stiffness(kvs[1:], geo=geometry.quarter_annulus())
+    assert np.allclose(A.toarray(), A2.toarray())
+
+
+def check_surface_forms(ref):
+    """integrals over a 2D manifold in R^3 (`ds` without `boundary`; reference: pyiga/vform.py:171-236,
+    test/test_assemble.py:314-334)"""
+    import scipy.sparse
+    from helpers import SFORMS
+    from pyiga_b200 import assemble, bspline, geometry
+    from pyiga_b200.vform import VForm
+    cyl3 = geometry.tensor_product(geometry.line_segment(0.0, 1.0), geometry.quarter_annulus())
+    for name, (form, bfuns, inputs, ps, ns, side) in SFORMS.items():
+        kvs = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(ps, ns))
+        got = assemble.assemble(form, kvs, geo=cyl3.boundary(side), bfuns=bfuns, **inputs)
+        if 'sf_%s_indptr' % name in ref:
+            R = _ref_csr_named(ref, 'sf_%s' % name)
+            _assert_csr_equal(got, R, 'surface form ' + name)
+        else:
+            assert_close_rel(got, ref['sf_%s' % name], what='surface form ' + name)
+    # the reference's own test: surface area of the cylinder mantles through a VForm object
+    vf = VForm(2, geo_dim=3, arity=1)
+    v = vf.basisfuns()
+    vf.add(v * vf.ds)
+    kvs = 2 * (bspline.make_knots(3, 0.0, 1.0, 10),)
+    f = assemble.assemble(vf, kvs, geo=cyl3.boundary('left'))
+    assert np.allclose(f.sum(), (2 * 1 * np.pi) / 4)
+    f = assemble.assemble(vf, kvs, geo=cyl3.boundary('right'))
+    assert np.allclose(f.sum(), (2 * 2 * np.pi) / 4)
+    # callables of the three physical coordinates are accepted as well
+    kvs = 2 * (bspline.make_knots(2, 0.0, 1.0, 4),)
+    a = assemble.assemble('c * u * v * ds', kvs, geo=cyl3.boundary('left'), c=lambda x, y, z: 1.0 + x * y + z)
+    _assert_csr_equal(a, _ref_csr_named(ref, 'sf_sreact'), 'surface form with f(x, y, z)')
+    # Laplace-Beltrami (beyond the reference, whose generator cannot invert the 3 x 2 Jacobian):
+    # symmetric, constants in the kernel, and the energy of the axial coordinate z = xi_0 is the area
+    kvs = (bspline.make_knots(2, 0.0, 1.0, 4), bspline.make_knots(3, 0.0, 1.0, 5))
+    K = assemble.assemble('inner(grad(u), grad(v)) * ds', kvs, geo=cyl3.boundary('right'))
+    assert abs(K - K.T).max() <= 1e-12 * abs(K).max()
+    assert np.abs(K @ np.ones(K.shape[0])).max() <= 1e-11 * abs(K).max()
+    from pyiga_b200 import approx
+    z = approx.interpolate(kvs, lambda x, y: 0.0 * x + y).ravel()      # first parameter = axis of the cylinder
+    assert np.allclose(z @ (K @ z), (2 * 2 * np.pi) / 4)

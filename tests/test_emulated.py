@@ -144,3 +144,11 @@ def test_walk_axis_split_with_slabs(emu, ref, monkeypatch, k):
 
 def test_integrate(emu, ref):
     pc.check_integrate(ref)
+
+
+def test_boundary_reference_tests(emu):
+    pc.check_boundary_reference_tests()
+
+
+def test_surface_forms(emu, ref):
+    pc.check_surface_forms(ref)

@@ -204,3 +204,11 @@ def test_walk_axis_split_with_slabs(cuda, ref, monkeypatch, k):
 
 def test_integrate(cuda, ref):
     pc.check_integrate(ref)
+
+
+def test_boundary_reference_tests(cuda):
+    pc.check_boundary_reference_tests()
+
+
+def test_surface_forms(cuda, ref):
+    pc.check_surface_forms(ref)
