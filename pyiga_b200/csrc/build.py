@@ -55,7 +55,7 @@ def _compile(job):
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     tag = _deps_hash()
-    stamp = os.path.join(OBJ, 'stamp')
+    stamp = LIB + '.stamp'         # next to the library: the object cache does not travel to the GPU box
     if (not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == tag):
         return LIB
     jobs = [('api.cu', os.path.join(OBJ, 'api_%s.o' % tag), [])]
