@@ -77,7 +77,7 @@ class SlabAssembly:
         nnz = self.local_nnz
         return nrows, nnz, (np.int32 if nnz < 2 ** 31 else np.int64)
 
-    def assemble_csr_host(self, host=None, nchunks=8, workspace=None, pattern='host'):
+    def assemble_csr_host(self, host=None, nchunks=8, workspace=None, pattern='host', pattern_threads=None):
         """Assemble the local rows and deliver the CSR arrays (indptr, indices, data) in host memory,
         overlapping the device->host copy of one row chunk with the assembly of the next (CUDA
         backend only).  `host` may hold three preallocated pinned torch tensors; returns them.
@@ -119,7 +119,7 @@ class SlabAssembly:
 
             def fill():
                 try:
-                    dev.device_structure.csr_pattern_host(host[0], host[1], row0=(ra, rb))
+                    dev.device_structure.csr_pattern_host(host[0], host[1], row0=(ra, rb), nthreads=pattern_threads)
                 except Exception as exc:        # surfaced after the join
                     err.append(exc)
             worker = threading.Thread(target=fill)

@@ -44,6 +44,15 @@ def main():
         t2 = time.perf_counter()
         sl.assemble_csr_host(host=pinned, pattern='device')
         t3 = time.perf_counter()
+    for thr in (2, 4, 8, 12, 15):
+        for nch in (8, 16):
+            ts = []
+            for rep in range(3):
+                torch.cuda.synchronize()
+                t4 = time.perf_counter()
+                sl.assemble_csr_host(host=pinned, pattern='host', pattern_threads=thr, nchunks=nch)
+                ts.append(time.perf_counter() - t4)
+            out['csr_host_%dthr_%dchunks_ms' % (thr, nch)] = 1e3 * min(ts)
     out['constructor_ms'] = 1e3 * (t1 - t0)
     out['assemble_csr_host_pattern_host_ms'] = 1e3 * (t2 - t1)
     out['assemble_csr_host_pattern_device_ms'] = 1e3 * (t3 - t2)
