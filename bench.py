@@ -320,9 +320,13 @@ def run_ours(a):
             d2h = pinned[2].numel() * pinned[2].element_size()              # values only; see e2e.what
             h2d = sum(8 * (kv.kv.size + 2 * g.size) for kv, g in zip(kvs, sl.dev.gaussgrid)) + geo.coeffs.nbytes \
                 + sum(8 * kv.kv.size for kv in geo.kvs)
+        t_call = time.perf_counter() - t0
         barrier()
         if it > 0:
             e2e_times.append(time.perf_counter() - t0)
+        if os.environ.get('PB200_BENCH_DEBUG'):
+            sys.stderr.write('[e2e rank %d it %d] call %.1f ms, with barrier %.1f ms, phases %s\n'
+                             % (rank, it, 1e3 * t_call, 1e3 * (time.perf_counter() - t0), getattr(sl, 'last_timings', None)))
         del sl
     e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times) if e2e_times else None
 

@@ -86,6 +86,9 @@ class SlabAssembly:
         host threads write them straight into `host[0:2]` while the GPU computes and ships the values,
         so only 8 of the 12 B/nnz cross PCIe; ``pattern='device'`` produces and copies them from
         the GPU as well."""
+        import time
+        tm = self.last_timings = {}
+        t_start = time.perf_counter()
         be, dev = self.dev.be, self.dev
         torch = be.torch
         nrows, nnz, idt = self.csr_sizes()
@@ -113,6 +116,7 @@ class SlabAssembly:
         freed = [None, None]
         row_off, nnz_off = 0, 0
         worker = None
+        tm['setup_ms'] = 1e3 * (time.perf_counter() - t_start)
         if pattern == 'host':
             import threading
             err = []
@@ -148,12 +152,15 @@ class SlabAssembly:
                 freed[k % 2].record(copy_stream)
             row_off += cr
             nnz_off += cn
+        tm['enqueue_ms'] = 1e3 * (time.perf_counter() - t_start) - tm['setup_ms']
         copy_stream.synchronize()
         main.synchronize()
+        tm['device_done_ms'] = 1e3 * (time.perf_counter() - t_start)
         if worker is not None:
             worker.join()
             if err:
                 raise err[0]
+        tm['total_ms'] = 1e3 * (time.perf_counter() - t_start)
         return host
 
 
