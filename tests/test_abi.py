@@ -96,3 +96,47 @@ def test_knotvector_api():
     assert ms.shape == (kv.numdofs, 2) and ms[0, 0] == 0 and ms[-1, 1] == 4
     assert kv.findspan(1.0) == kv.kv.size - 3 - 2 and kv.findspan(0.0) == 3
     assert kv == kv.copy() and kv.refine().numspans == 8
+
+
+def test_host_only_csr_pattern(ref):
+    """pb200_csr_pattern_host is a host-only entry point of the PRODUCT library: callable without a GPU"""
+    from helpers import make_space
+    from pyiga_b200 import _lib
+    from pyiga_b200.mlmatrix import MLStructure
+    lib = _lib.load()
+    kvs = make_space(ref, 'a3_mixed')
+    S = MLStructure.from_kvs(kvs, kvs)
+    L = S.L
+    tabs = [S._row_tables(k) for k in range(L)]
+    rows = (C.c_int * L)(*[b[0] for b in S.bs])
+    cols = (C.c_int * L)(*[b[1] for b in S.bs])
+    nband = (C.c_int * L)(*[len(b) for b in S.bidx])
+    rs = [np.ascontiguousarray(t[0], dtype=np.int32) for t in tabs]
+    jm = [np.ascontiguousarray(t[1], dtype=np.int32) for t in tabs]
+    p_rs = (C.c_void_p * L)(*[a.ctypes.data for a in rs])
+    p_jm = (C.c_void_p * L)(*[a.ctypes.data for a in jm])
+    want_ptr, want_idx = ref['a3_mixed_stiff_indptr'], ref['a3_mixed_stiff_indices']
+    ip = np.empty(want_ptr.size, dtype=np.int32)
+    ix = np.empty(want_idx.size, dtype=np.int32)
+    rc = lib.pb200_csr_pattern_host(L, rows, cols, nband, p_rs, p_jm, 0, S.bs[0][0], ip.ctypes.data, ix.ctypes.data, 4, 0, 3)
+    assert rc == 0
+    assert np.array_equal(ip, want_ptr) and np.array_equal(ix, want_idx)
+    # argument checks
+    assert lib.pb200_csr_pattern_host(L, rows, cols, nband, p_rs, p_jm, 0, S.bs[0][0] + 1, ip.ctypes.data, ix.ctypes.data, 4, 0, 1) == -1
+    assert lib.pb200_csr_pattern_host(L, rows, cols, nband, p_rs, p_jm, 0, 1, ip.ctypes.data, ix.ctypes.data, 3, 0, 1) == -1
+    assert lib.pb200_csr_pattern_host(1, rows, cols, nband, p_rs, p_jm, 0, 1, ip.ctypes.data, ix.ctypes.data, 4, 0, 1) != 0
+
+
+def test_argument_checks_of_device_entry_points():
+    """invalid arguments are rejected before any CUDA call"""
+    from pyiga_b200 import _lib
+    lib = _lib.load()
+    n = C.c_size_t()
+    assert lib.pb200_csr_restrict_workspace(10, 5, C.byref(n)) == -1
+    assert lib.pb200_csr_restrict_workspace(-1, 4, C.byref(n)) == -1
+    assert lib.pb200_csr_restrict_workspace(10 ** 7, 8, C.byref(n)) == 0 and n.value > 0
+    assert lib.pb200_csr_restrict_count(5, None, None, None, 4, None, None, None, 0, None) == -1
+    assert lib.pb200_csr_matvec(3, None, None, None, 4, None, None, 1.0, None, None) == -1
+    assert lib.pb200_vec_gather(3, None, None, None, None) == -1
+    assert lib.pb200_asm_rows_count(None, None, 0, None) == -1
+    assert b'null' in lib.pb200_last_error()
