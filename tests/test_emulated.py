@@ -152,3 +152,10 @@ def test_boundary_reference_tests(emu):
 
 def test_surface_forms(emu, ref):
     pc.check_surface_forms(ref)
+
+
+def test_long_first_axis_unstaged_tables(emu):
+    """axis 0 so long that its tables do not fit the shared-memory budget: the walk reads them
+    through L1 (no staged retire table, no rotating window)"""
+    pc.check_vs_oracle(2, (3, 3), (300, 4), 'Stiffness')
+    pc.check_vs_oracle(2, (3, 2), (300, 3), 'Mass', geo_name='bspline')
