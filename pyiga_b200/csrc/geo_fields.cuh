@@ -201,9 +201,11 @@ template <int DIM> struct PbProgStiffness {
     static constexpr bool NEED_X = false;
     template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) {
         // with J = N / jden:  W J^-1 J^-T = gw jden^(2-DIM) / |det N| * adj(N) adj(N)^T  -- one division
-        const double det = pb_det<DIM>(pt.J);
         double A[3][3];
         pb_adj<DIM>(pt.J, A);
+        // Laplace expansion along the first row with the cofactors that are already there
+        double det = pt.J[0][0] * A[0][0];
+        for (int m = 1; m < DIM; ++m) det = fma(pt.J[0][m], A[m][0], det);
         const double den = (RAT && DIM == 3) ? pt.jden * fabs(det) : fabs(det);
         const double sc = pt.gw / den;
         int k = 0;
