@@ -24,11 +24,14 @@ int launch(const PbWalkParams* prm, int use_smem, size_t smem_bytes, void* strea
     return 0;
 #else
     auto kern = pb_walk_kernel<Plan, PB_P, PB_Q, (PB_P >= 4 ? Plan::MINB4 : Plan::MINB), Plan::NPF>;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to large dynamic shared memory is a per-device function attribute
+    static unsigned long long configured = 0;       // bit d: done on device d
+    int devno = 0;
+    cudaGetDevice(&devno);
+    if (devno >= 64 || !((configured >> devno) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        if (devno < 64) configured |= 1ull << devno;
     }
     // the asynchronous loader's ring (plans with NPF >= 2) sits behind the table slice
     const size_t ring = Plan::NPF >= 2 ? (size_t)Plan::NPF * PB_Q * Plan::NOPS * 128 * sizeof(double) : 0;
@@ -82,11 +85,13 @@ int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* strea
     using Cfg = PbLaneCfg<PB_P, PB_Q>;
     const size_t smem = 4 * (size_t)(NST * Plan::NOPS * Cfg::SEG + Cfg::OUTPAD + Cfg::LOSLOTS) * sizeof(double);
     auto kern = pb_lane_span_kernel_v2<Plan, PB_P, PB_Q, NST>;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;       // bit d: done on device d (per-device attribute)
+    int devno = 0;
+    cudaGetDevice(&devno);
+    if (devno >= 64 || !((configured >> devno) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        if (devno < 64) configured |= 1ull << devno;
     }
     kern<<<grid, 128, smem, (cudaStream_t)stream>>>(*prm, lines_per_warp);
     return (int)cudaGetLastError();
