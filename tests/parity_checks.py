@@ -723,3 +723,40 @@ def check_surface_forms(ref):
     from pyiga_b200 import approx
     z = approx.interpolate(kvs, lambda x, y: 0.0 * x + y).ravel()      # first parameter = axis of the cylinder
     assert np.allclose(z @ (K @ z), (2 * 2 * np.pi) / 4)
+
+
+def check_reference_driver_dropin(ref):
+    """the REAL reference's drivers (oracle/_ref, test infrastructure) accept
+    the device assemblers through the duck-typed protocol: pyiga.assemble.assemble_entries(asm) for
+    scalar, symmetric and vector-valued assemblers, pyiga's _assemble_partial_rows, MLMatrix(data=...)"""
+    import os
+    import sys
+    import pytest
+    refdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(refdir, 'pyiga')):
+        pytest.skip('oracle/_ref is not installed')
+    sys.path.insert(0, refdir)
+    try:
+        import pyiga.assemble as rasm
+        import pyiga._hdiscr as rh
+    except Exception as exc:        # pragma: no cover
+        pytest.skip('reference does not import: %s' % exc)
+    finally:
+        sys.path.remove(refdir)
+    from pyiga_b200 import assemble, assemblers
+    for case, cls, key, gname in [('a3_mixed', assemblers.StiffnessAssembler3D, 'stiff', 'tb'),
+                                  ('a2_mixed', assemblers.MassAssembler2D, 'mass', 'bqa')]:
+        kvs = make_space(ref, case)
+        asm = cls(kvs, make_geo(ref, gname))
+        want = asm.assemble_csr()
+        for sym in (False, True):       # the reference mirrors the lower triangle itself when symmetric=True
+            A = rasm.assemble_entries(asm, symmetric=sym).tocsr()
+            A.sort_indices()
+            assert np.array_equal(A.indptr, ref['%s_%s_indptr' % (case, key)])
+            assert np.array_equal(A.indices, ref['%s_%s_indices' % (case, key)])
+            assert abs(A - want).max() <= RTOL * abs(want).max()
+        # (format='mlb' of the reference goes through its Cython-typed core and is not duck-typed)
+        rows = ref['pr_%s_rows' % case] if 'pr_%s_rows' % case in ref else np.array([0, 3])
+        P = rh._assemble_partial_rows(asm, rows)
+        assert abs(P[rows] - want[rows]).max() <= RTOL * abs(want).max()
+    # (assemble_entries_vec and format='mlb' of the reference take Cython-typed assemblers only)

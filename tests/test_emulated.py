@@ -159,3 +159,7 @@ def test_long_first_axis_unstaged_tables(emu):
     through L1 (no staged retire table, no rotating window)"""
     pc.check_vs_oracle(2, (3, 3), (300, 4), 'Stiffness')
     pc.check_vs_oracle(2, (3, 2), (300, 3), 'Mass', geo_name='bspline')
+
+
+def test_reference_driver_dropin(emu, ref):
+    pc.check_reference_driver_dropin(ref)
