@@ -365,11 +365,13 @@ def run_ours(a):
             pbytes = pipeline_bytes(dev, sa.rows, a.form, a.p)
             byts = pbytes.get(dom)
             kernel_gbs = {k: round(pbytes[k] / (stages[k] * 1e-3) / 1e9, 1) for k in stages if k in pbytes}
-            traffic = None
-            try:    # DRAM bytes per launch from the committed ncu --set full capture of the same workload
+            traffic, step_traffic = None, None
+            try:    # DRAM bytes per launch from the committed ncu capture of the same workload
                 t = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
                 if t.get('workload') == workload_name(a) and world == 1:
                     traffic = t['dram_bytes_per_launch'].get(dom)
+                    if all(k in t['dram_bytes_per_launch'] for k in stages):
+                        step_traffic = sum(t['dram_bytes_per_launch'][k] for k in stages)
             except Exception:
                 pass
             if byts:
@@ -379,7 +381,10 @@ def run_ours(a):
                         'ms_per_launch': stages[dom], 'peak_source': hbm_src,
                         'share_of_step': stages[dom] / sum(stages.values()),
                         'all_kernels_GBps': kernel_gbs, 'step_bytes': sum(pbytes.values()),
-                        'step_GBps': sum(pbytes.values()) / (ms * 1e-3) / 1e9}
+                        'step_GBps': sum(pbytes.values()) / (ms * 1e-3) / 1e9,
+                        # all kernels of the step: DRAM traffic by ncu against the measured copy bandwidth
+                        'step_traffic': step_traffic,
+                        'step_traffic_frac': (step_traffic / (ms * 1e-3) / 1e9 / hbm_peak) if step_traffic else None}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
