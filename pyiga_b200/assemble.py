@@ -42,12 +42,59 @@ def _assemble_1d(kv, form):
     return scipy.sparse.csr_matrix((vals, (b[:, 0].astype(np.int64), b[:, 1].astype(np.int64))), shape=(n, n))
 
 
-def bsp_mass_1d(knotvec):
+def bsp_mixed_deriv_biform_1d_asym(knotvec1, knotvec2, du, dv, quadgrid=None, nqp=None):
+    """Matrix of ``a(u, v) = (u^(du), v^(dv))`` between two B-spline bases on one mesh: trial functions
+    in `knotvec1` (columns), test functions in `knotvec2` (rows), derivative orders 0 or 1
+    (``pyiga/assemble.py:192-222``).  Computed on the device as the marginal of the lifted 2D
+    Petrov-Galerkin form over (kv) x (one linear element), see :func:`_assemble_1d`; the Gauss rule
+    has max(p)+1 points per span, which is exact for these polynomial integrands like the reference's."""
+    import scipy.sparse
+    if quadgrid is not None or nqp is not None:
+        raise NotImplementedError('custom quadrature grids are not part of the device path')
+    if du not in (0, 1) or dv not in (0, 1):
+        raise NotImplementedError('derivative orders above 1 are not part of the device path')
+    unit = bspline.make_knots(1, 0.0, 1.0, 1)
+    kvs0, kvs1 = (knotvec1, unit), (knotvec2, unit)
+    eu = 'Dx(u, 1)' if du else 'u'          # axis 0 of the lifted space is the y coordinate
+    ev = 'Dx(v, 1)' if dv else 'v'
+    same = knotvec1 == knotvec2
+    if same:
+        M = assemble('%s * %s * dx' % (eu, ev), kvs0, geo=geometry.identity(kvs0), format='mlb')
+    else:
+        M = assemble('%s * %s * dx' % (eu, ev), (kvs0, kvs1), geo=geometry.identity(kvs0),
+                     bfuns=[('u', 1, 0), ('v', 1, 1)], format='mlb')
+    vals = M.data.sum(axis=1)
+    b = M.structure.bidx[0]
+    return scipy.sparse.csr_matrix((vals, (b[:, 0].astype(np.int64), b[:, 1].astype(np.int64))),
+                                   shape=(knotvec2.numdofs, knotvec1.numdofs))
+
+
+def bsp_mixed_deriv_biform_1d(knotvec, du, dv, nqp=None, weightfunc=None):
+    """``a(u, v) = (u^(du), v^(dv))`` on one knot vector (``pyiga/assemble.py:179-190``)."""
+    if weightfunc is not None:
+        raise NotImplementedError('weight functions in the 1D helpers are not part of the device path '
+                                  "(use assemble('w * u * v * dx', ...) on a 2D/3D space)")
+    return bsp_mixed_deriv_biform_1d_asym(knotvec, knotvec, du, dv, nqp=nqp)
+
+
+def bsp_mass_1d(knotvec, weightfunc=None):
+    if weightfunc is not None:
+        return bsp_mixed_deriv_biform_1d(knotvec, 0, 0, weightfunc=weightfunc)
     return _assemble_1d(knotvec, 'mass')
 
 
-def bsp_stiffness_1d(knotvec):
+def bsp_stiffness_1d(knotvec, weightfunc=None):
+    if weightfunc is not None:
+        return bsp_mixed_deriv_biform_1d(knotvec, 1, 1, weightfunc=weightfunc)
     return _assemble_1d(knotvec, 'stiffness')
+
+
+def bsp_mass_1d_asym(knotvec1, knotvec2, quadgrid=None):
+    return bsp_mixed_deriv_biform_1d_asym(knotvec1, knotvec2, 0, 0, quadgrid=quadgrid)
+
+
+def bsp_stiffness_1d_asym(knotvec1, knotvec2, quadgrid=None):
+    return bsp_mixed_deriv_biform_1d_asym(knotvec1, knotvec2, 1, 1, quadgrid=quadgrid)
 
 
 def assemble_entries(asm, symmetric=False, format='csr', layout='blocked'):
@@ -427,6 +474,13 @@ def assemble(problem, kvs=None, args=None, bfuns=None, boundary=None, symmetric=
     else:
         asm = instantiate_assembler(problem, kvs, args, bfuns, boundary)
     return assemble_entries(asm, symmetric=symmetric, format=format, layout=layout)
+
+
+def assemble_vf(vf, kvs, symmetric=False, format='csr', layout='blocked', args=None, **kwargs):
+    """Assemble a :class:`~pyiga_b200.vform.VForm` (``pyiga/assemble.py:812-822``)."""
+    args = dict() if args is None else args
+    args.update(kwargs)
+    return assemble(vf, kvs, symmetric=symmetric, format=format, layout=layout, args=args)
 
 
 class Assembler:

@@ -295,6 +295,12 @@ def main():
         else:
             out['sf_%s' % name] = np.asarray(R)
 
+    # ---- 15. 1D helpers (pyiga/assemble.py:165-230) -------------------------------------------------------
+    kvA, kvB = bspline.make_knots(3, 0.0, 2.0, 7), bspline.make_knots(2, 0.0, 2.0, 7)
+    for du, dv in [(0, 1), (1, 0), (1, 1), (0, 0)]:
+        out['b1d_%d%d' % (du, dv)] = assemble.bsp_mixed_deriv_biform_1d(kvA, du, dv).toarray()
+        out['b1d_asym_%d%d' % (du, dv)] = assemble.bsp_mixed_deriv_biform_1d_asym(kvA, kvB, du, dv).toarray()
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

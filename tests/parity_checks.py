@@ -337,6 +337,22 @@ def check_integrate(ref):
     assert abs(got - ref['int_1d']) <= tol * abs(ref['int_1d'])
 
 
+def check_1d_helpers(ref):
+    """1D bilinear forms through the lifted 2D device path (pyiga/assemble.py:165-230)"""
+    from pyiga_b200 import assemble, bspline
+    kvA, kvB = bspline.make_knots(3, 0.0, 2.0, 7), bspline.make_knots(2, 0.0, 2.0, 7)
+    for du, dv in [(0, 1), (1, 0), (1, 1), (0, 0)]:
+        got = assemble.bsp_mixed_deriv_biform_1d(kvA, du, dv).toarray()
+        want = ref['b1d_%d%d' % (du, dv)]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (du, dv)
+        got = assemble.bsp_mixed_deriv_biform_1d_asym(kvA, kvB, du, dv).toarray()
+        want = ref['b1d_asym_%d%d' % (du, dv)]
+        assert got.shape == want.shape == (kvB.numdofs, kvA.numdofs)
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), ('asym', du, dv)
+    assert np.abs(assemble.bsp_mass_1d_asym(kvA, kvB).toarray() - ref['b1d_asym_00']).max() <= 1e-12
+    assert np.abs(assemble.bsp_stiffness_1d(kvA).toarray() - ref['b1d_11']).max() <= 1e-12 * np.abs(ref['b1d_11']).max()
+
+
 def check_edge_cases(ref):
     """degenerate and unusual inputs the reference accepts"""
     import pytest

@@ -163,3 +163,7 @@ def test_long_first_axis_unstaged_tables(emu):
 
 def test_reference_driver_dropin(emu, ref):
     pc.check_reference_driver_dropin(ref)
+
+
+def test_1d_helpers(emu, ref):
+    pc.check_1d_helpers(ref)

@@ -223,3 +223,7 @@ def test_long_first_axis_unstaged_tables(cuda):
 
 def test_reference_driver_dropin(cuda, ref):
     pc.check_reference_driver_dropin(ref)
+
+
+def test_1d_helpers(cuda, ref):
+    pc.check_1d_helpers(ref)
