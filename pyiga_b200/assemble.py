@@ -319,6 +319,31 @@ def compute_dirichlet_bcs(kvs, geo, bdconds):
     return combine_bcs(compute_dirichlet_bc(kvs, geo, bdspec, g) for (bdspec, g) in bdconds)
 
 
+def compute_initial_condition_01(kvs, geo, bdspec, g0, g1, physical=True):
+    """Indices and values which prescribe function value (`g0`) and normal derivative (`g1`) on one
+    face of a space-time cylinder with time-independent geometry, by interpolation on the face and
+    a 2 x 2 collocation solve for the two layers of boundary coefficients
+    (``pyiga/assemble.py:492-552``)."""
+    from .approx import interpolate
+    bdspec = bspline._parse_bdspec(bdspec, len(kvs))
+    bdax, bdside = bdspec
+    bdbasis = list(kvs)
+    del bdbasis[bdax]
+    bdgeo = geo.boundary(bdspec) if physical else None
+    coeffs01 = np.stack((interpolate(bdbasis, g0, geo=bdgeo).ravel(), interpolate(bdbasis, g1, geo=bdgeo).ravel()))
+    a, b = kvs[bdax].support()
+    if bdside == 0:
+        bdcolloc = bspline.active_deriv(kvs[bdax], float(a), 1)[:2, :2]      # first two basis functions
+    else:
+        bdcolloc = bspline.active_deriv(kvs[bdax], float(b), 1)[:2, -2:]     # last two basis functions
+    coll_coeffs = np.linalg.solve(bdcolloc, coeffs01)
+    N = tuple(kv.numdofs for kv in kvs)
+    firstidx = 0 if bdside == 0 else -2
+    bdindices = np.concatenate((slice_indices(bdax, firstidx, N, ravel=True),
+                                slice_indices(bdax, firstidx + 1, N, ravel=True)))
+    return bdindices, coll_coeffs.ravel()
+
+
 class RestrictedLinearSystem:
     """Linear system with some dofs eliminated (``pyiga/assemble.py:568-652``).
 

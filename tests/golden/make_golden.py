@@ -301,6 +301,13 @@ def main():
         out['b1d_%d%d' % (du, dv)] = assemble.bsp_mixed_deriv_biform_1d(kvA, du, dv).toarray()
         out['b1d_asym_%d%d' % (du, dv)] = assemble.bsp_mixed_deriv_biform_1d_asym(kvA, kvB, du, dv).toarray()
 
+    # ---- 16. space-time initial conditions (pyiga/assemble.py:492-552) -----------------------------------
+    kvsT = (bspline.make_knots(2, 0.0, 1.0, 4), bspline.make_knots(3, 0.0, 1.0, 3), bspline.make_knots(2, 0.0, 1.0, 5))
+    geoT = geometry.tensor_product(geometry.line_segment(0.0, 1.0), geometry.quarter_annulus())
+    for side in (0, 1):
+        i01, v01 = assemble.compute_initial_condition_01(kvsT, geoT, (0, side), lambda x, y, t: x * y, lambda x, y, t: x - y)
+        out['ic01_idx%d' % side], out['ic01_val%d' % side] = i01, v01
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

@@ -337,6 +337,17 @@ def check_integrate(ref):
     assert abs(got - ref['int_1d']) <= tol * abs(ref['int_1d'])
 
 
+def check_initial_condition(ref):
+    """space-time initial conditions (pyiga/assemble.py:492-552)"""
+    from pyiga_b200 import assemble, bspline, geometry
+    kvsT = (bspline.make_knots(2, 0.0, 1.0, 4), bspline.make_knots(3, 0.0, 1.0, 3), bspline.make_knots(2, 0.0, 1.0, 5))
+    geoT = geometry.tensor_product(geometry.line_segment(0.0, 1.0), geometry.quarter_annulus())
+    for side in (0, 1):
+        idx, val = assemble.compute_initial_condition_01(kvsT, geoT, (0, side), lambda x, y, t: x * y, lambda x, y, t: x - y)
+        assert np.array_equal(idx, ref['ic01_idx%d' % side])
+        assert_close_rel(val, ref['ic01_val%d' % side], what='initial condition, side %d' % side)
+
+
 def check_1d_helpers(ref):
     """1D bilinear forms through the lifted 2D device path (pyiga/assemble.py:165-230)"""
     from pyiga_b200 import assemble, bspline

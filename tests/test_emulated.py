@@ -167,3 +167,7 @@ def test_reference_driver_dropin(emu, ref):
 
 def test_1d_helpers(emu, ref):
     pc.check_1d_helpers(ref)
+
+
+def test_initial_condition(emu, ref):
+    pc.check_initial_condition(ref)

@@ -227,3 +227,7 @@ def test_reference_driver_dropin(cuda, ref):
 
 def test_1d_helpers(cuda, ref):
     pc.check_1d_helpers(ref)
+
+
+def test_initial_condition(cuda, ref):
+    pc.check_initial_condition(ref)
