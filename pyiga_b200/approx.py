@@ -35,3 +35,44 @@ def interpolate(kvs, f, geo=None, nodes=None):
     for k, kv in enumerate(kvs):
         X = _solve_along(bspline.collocation(kv, nodes[k]), X, k)
     return X
+
+
+def project_L2(kvs, f, f_physical=False, geo=None, rtol=1e-14, maxiter=500):
+    """Coefficients of the L2 projection of `f` onto the tensor-product spline space, optionally on
+    the physical domain `geo` (``pyiga/approx.py:62-95``).  The mass matrix stays on the device as a
+    multi-level banded tensor; ``M x = rhs`` is solved by conjugate gradients with the device matvec
+    and the Kronecker product of the inverse 1D mass matrices as preconditioner (the reference
+    factorises M with a sparse direct solver; `rtol` is the relative residual CG stops at)."""
+    import torch
+    from . import assemble
+    from .dist import GatheredKronecker, SlabAssembly, SlabOperator, cg
+    from .operators import KroneckerOperator
+    if isinstance(kvs, bspline.KnotVector):
+        kvs = (kvs,)
+    kvs = tuple(kvs)
+    if len(kvs) == 1:
+        M = assemble.bsp_mass_1d(kvs[0])
+        rhs = assemble.inner_products(kvs[0], f)
+        return scipy.sparse.linalg.spsolve(M.tocsc(), rhs)
+    if f_physical:
+        assert geo is not None, 'projection in physical coordinates requires a geometry'
+    rhs = np.asarray(assemble.inner_products(kvs, f, f_physical=f_physical, geo=geo), dtype=np.float64)
+    extra = rhs.shape[len(kvs):]
+    from . import geometry
+    sa = SlabAssembly(kvs, geo if geo is not None else geometry.identity(kvs), 'mass')
+    be = sa.dev.be
+    op = SlabOperator(sa.dev, sa.assemble_mlb(), rows=sa.rows, slabs=sa.slabs, rank=0)
+    plane = int(np.prod([kv.numdofs for kv in kvs[1:]], dtype=np.int64))
+    Minv = [np.linalg.inv(assemble.bsp_mass_1d(kv).toarray()) for kv in kvs]
+    prec = GatheredKronecker(KroneckerOperator(*Minv), sa.slabs, 0, plane)
+    to_t = (lambda v: torch.from_numpy(np.ascontiguousarray(v))) if be.name == 'emu' else be.from_host
+
+    def solve(b):
+        x, _it, _hist = cg(lambda v: op._t(op.matvec(v)).clone(), to_t(b.ravel()), M=prec, rtol=rtol, maxiter=maxiter)
+        return (np.asarray(x.cpu()) if hasattr(x, 'cpu') else np.asarray(x)).reshape(b.shape)
+    if extra == ():
+        return solve(rhs)
+    out = np.empty_like(rhs)
+    for idx in np.ndindex(*extra):
+        out[(Ellipsis,) + idx] = solve(np.ascontiguousarray(rhs[(Ellipsis,) + idx]))
+    return out

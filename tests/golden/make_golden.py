@@ -308,6 +308,12 @@ def main():
         i01, v01 = assemble.compute_initial_condition_01(kvsT, geoT, (0, side), lambda x, y, t: x * y, lambda x, y, t: x - y)
         out['ic01_idx%d' % side], out['ic01_val%d' % side] = i01, v01
 
+    # ---- 17. L2 projection (pyiga/approx.py:62-95; used by test/test_solve.py) ----------------------------
+    out['pl2_2d'] = approx.project_L2(kvsP, gP, f_physical=True, geo=geoP)
+    out['pl2_3d'] = approx.project_L2(kvs3, lambda x, y, z: np.sin(x) * y + z * z, f_physical=True, geo=g3)
+    out['pl2_par'] = approx.project_L2(kvs3, lambda x, y, z: x * y - z)
+    out['pl2_1d'] = approx.project_L2(kv1, lambda x: np.cos(3 * x))
+
     np.savez_compressed(os.path.join(HERE, 'ref_cases.npz'), **out)
     print('wrote', len(out), 'arrays')
 

@@ -348,6 +348,24 @@ def check_initial_condition(ref):
         assert_close_rel(val, ref['ic01_val%d' % side], what='initial condition, side %d' % side)
 
 
+def check_project_L2(ref):
+    """L2 projection: device mass matrix + preconditioned CG vs the reference's direct solve
+    (pyiga/approx.py:62-95); the tolerance is the conditioning of the mass matrix times the CG residual"""
+    from pyiga_b200 import approx, bspline, geometry
+    kvsP = 2 * (bspline.make_knots(3, 0.0, 1.0, 10),)
+    gP = lambda x, y: np.cos(x + y) + np.exp(y - x)
+    got = approx.project_L2(kvsP, gP, f_physical=True, geo=geometry.quarter_annulus())
+    assert_close_rel(got, ref['pl2_2d'], rtol=1e-9, what='project_L2 2D physical')
+    kvs3 = make_space(ref, 'a3_tb')
+    g3 = make_geo(ref, 'tnb')
+    got = approx.project_L2(kvs3, lambda x, y, z: np.sin(x) * y + z * z, f_physical=True, geo=g3)
+    assert_close_rel(got, ref['pl2_3d'], rtol=1e-9, what='project_L2 3D physical')
+    got = approx.project_L2(kvs3, lambda x, y, z: x * y - z)
+    assert_close_rel(got, ref['pl2_par'], rtol=1e-9, what='project_L2 parametric')
+    kv1 = bspline.make_knots(2, 0.0, 1.0, 10)
+    assert_close_rel(approx.project_L2(kv1, lambda x: np.cos(3 * x)), ref['pl2_1d'], rtol=1e-9, what='project_L2 1D')
+
+
 def check_1d_helpers(ref):
     """1D bilinear forms through the lifted 2D device path (pyiga/assemble.py:165-230)"""
     from pyiga_b200 import assemble, bspline

@@ -171,3 +171,7 @@ def test_1d_helpers(emu, ref):
 
 def test_initial_condition(emu, ref):
     pc.check_initial_condition(ref)
+
+
+def test_project_L2(emu, ref):
+    pc.check_project_L2(ref)

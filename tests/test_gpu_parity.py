@@ -231,3 +231,7 @@ def test_1d_helpers(cuda, ref):
 
 def test_initial_condition(cuda, ref):
     pc.check_initial_condition(ref)
+
+
+def test_project_L2(cuda, ref):
+    pc.check_project_L2(ref)
