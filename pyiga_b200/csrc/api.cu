@@ -359,6 +359,7 @@ struct pb200_assembler {
     std::vector<PbTerm> terms;
     std::vector<std::pair<int, int>> field_slots;       // custom forms: (test slot, trial slot) of field f
     void* geo_scratch = nullptr;
+    size_t geo_scratch_bytes = 0;
     long long npts = 0, nnz = 0;
     int fast = 0;
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
@@ -770,8 +771,12 @@ struct GeoTables {
 };
 
 // uploads knots + control net and evaluates the 1D geometry tables at the given device nodes
+// `reuse` / `reuse_bytes`: an earlier allocation of the caller that is used again when it is large
+// enough (work already queued on `st` that reads it is ordered before the new copies); otherwise it
+// is released after a stream synchronisation and replaced.
 static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, const double* const* d_nodes,
-                            pbStream st, GeoTables& T, bool square = true) {
+                            pbStream st, GeoTables& T, bool square = true, void** reuse = nullptr,
+                            size_t* reuse_bytes = nullptr) {
     if (!geo) return fail(PB200_EINVAL, "geometry missing");
     if (geo->sdim != dim) return fail(PB200_EINVAL, "Geometry has wrong source dimension");
     if (square && geo->dim != dim) return fail(PB200_EINVAL, "Geometry has wrong dimension");
@@ -791,7 +796,13 @@ static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, co
         ncoef *= geo->nknots[k] - geo->p[k] - 1;
     }
     off_c = reserve(sizeof(double) * ncoef * nc);
-    CK(pbMalloc(&T.mem, bytes + 256));
+    if (reuse && *reuse && *reuse_bytes >= bytes + 256) {
+        T.mem = *reuse;
+    } else {
+        if (reuse && *reuse) { CK(pbStreamSync(st)); CK(pbFree(*reuse)); *reuse = nullptr; *reuse_bytes = 0; }
+        CK(pbMalloc(&T.mem, bytes + 256));
+        if (reuse) { *reuse = T.mem; *reuse_bytes = bytes + 256; }
+    }
     char* b = (char*)T.mem;
     PbGeoDev& D = T.dev;
     D.sdim = dim; D.dim = geo->dim; D.nc = nc; D.rational = geo->rational ? 1 : 0;
@@ -880,10 +891,10 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
     prm.jac_in = d_jac;
     GeoTables T;
     if (!d_jac) {
-        if (a->geo_scratch) { CK(pbStreamSync(st)); CK(pbFree(a->geo_scratch)); a->geo_scratch = nullptr; }
-        int rc = build_geo_tables(geo, a->dim, G, d_nodes, st, T);
-        if (rc) { if (T.mem) pbFree(T.mem); return rc; }
-        a->geo_scratch = T.mem;
+        // the tables live in a scratch buffer of the assembler that is kept between calls: no
+        // allocation, release or synchronisation in the steady state
+        int rc = build_geo_tables(geo, a->dim, G, d_nodes, st, T, true, &a->geo_scratch, &a->geo_scratch_bytes);
+        if (rc) return rc;
         prm.geo = T.dev;
     }
     const bool mass = a->form == PB200_FORM_MASS;
