@@ -58,6 +58,31 @@ static void k_basis(const double* kv, int nk, int p, const double* nodes, int m,
 #endif
 }
 
+struct BasisJobs {
+    PbBasisBatch b;
+    BasisJobs() { memset(&b, 0, sizeof b); }
+    void add(const double* kv, int nk, int p, const double* nodes, int m, int nd, int* first, double* values) {
+        const int j = b.njobs++;
+        b.kv[j] = kv; b.nk[j] = nk; b.p[j] = p; b.nodes[j] = nodes; b.m[j] = m; b.nd[j] = nd; b.first[j] = first; b.values[j] = values;
+    }
+};
+static void k_basis_batch(const BasisJobs& J, pbStream st) {
+    if (J.b.njobs == 0) return;
+    ++g_launches;
+#ifdef PB_EMULATE
+    (void)st;
+    for (int j = 0; j < J.b.njobs; ++j)
+        pb_emu_for(J.b.m[j], [&](long long g) {
+            pb_basis_node(J.b.kv[j], J.b.nk[j], J.b.p[j], J.b.nodes[j], J.b.nd[j], J.b.first[j], J.b.values[j], (int)g);
+        });
+#else
+    int mmax = 0;
+    for (int j = 0; j < J.b.njobs; ++j) mmax = std::max(mmax, J.b.m[j]);
+    dim3 grid((unsigned)((mmax + 127) / 128), (unsigned)J.b.njobs);
+    pb_basis_batch_kernel<<<grid, 128, 0, st>>>(J.b);
+#endif
+}
+
 template <int DIM, class Prog>
 static void k_fields(const PbFieldParams& prm, pbStream st) {
     ++g_launches;
@@ -476,16 +501,18 @@ static int detect_fast_path(const pb200_assembler* a) {
 }
 
 static int run_basis(pb200_assembler* a, pbStream st) {
+    BasisJobs J;        // all axes (and both spaces) in one launch
     for (int k = 0; k < a->dim; ++k) {
         AxisHost& H = a->hax[k];
         PbAxis& D = a->dax[k];
         const double* dku = reinterpret_cast<const double*>(a->pool.dev + a->off_knots_u[k]);
-        k_basis(dku, (int)H.U.kv.size(), H.U.p, D.nodes, H.G, D.nd, nullptr, const_cast<double*>(D.Vu), st);
+        J.add(dku, (int)H.U.kv.size(), H.U.p, D.nodes, H.G, D.nd, nullptr, const_cast<double*>(D.Vu));
         if (!H.same) {
             const double* dkv = reinterpret_cast<const double*>(a->pool.dev + a->off_knots_v[k]);
-            k_basis(dkv, (int)H.V.kv.size(), H.V.p, D.nodes, H.G, D.nd, nullptr, const_cast<double*>(D.Vv), st);
+            J.add(dkv, (int)H.V.kv.size(), H.V.p, D.nodes, H.G, D.nd, nullptr, const_cast<double*>(D.Vv));
         }
     }
+    k_basis_batch(J, st);
     CK(pbLastError());
     return 0;
 }
@@ -806,15 +833,17 @@ static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, co
     char* b = (char*)T.mem;
     PbGeoDev& D = T.dev;
     D.sdim = dim; D.dim = geo->dim; D.nc = nc; D.rational = geo->rational ? 1 : 0;
+    BasisJobs J;
     for (int k = 0; k < dim; ++k) {
         D.pg[k] = geo->p[k];
         D.Ng[k] = geo->nknots[k] - geo->p[k] - 1;
         CK(pbMemcpyH2D(b + off_k[k], geo->h_knots[k], sizeof(double) * geo->nknots[k], st));
         D.gfirst[k] = (const int*)(b + off_f[k]);
         D.GV[k] = (const double*)(b + off_v[k]);
-        k_basis((const double*)(b + off_k[k]), geo->nknots[k], geo->p[k], d_nodes[k], G[k], 2, (int*)(b + off_f[k]),
-                (double*)(b + off_v[k]), st);
+        J.add((const double*)(b + off_k[k]), geo->nknots[k], geo->p[k], d_nodes[k], G[k], 2, (int*)(b + off_f[k]),
+              (double*)(b + off_v[k]));
     }
+    k_basis_batch(J, st);
     for (int k = dim; k < PB_MAXDIM; ++k) { D.pg[k] = 0; D.Ng[k] = 1; D.gfirst[k] = nullptr; D.GV[k] = nullptr; }
     CK(pbMemcpyH2D(b + off_c, geo->h_coeffs, sizeof(double) * ncoef * nc, st));
     D.coeffs = (const double*)(b + off_c);

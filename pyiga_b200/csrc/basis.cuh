@@ -84,7 +84,25 @@ PB_HD void pb_basis_node(const double* kv, int nk, int p, const double* nodes, i
     for (int k = 0; k < nd * (p + 1); ++k) values[(long long)g * nd * (p + 1) + k] = buf[k];
 }
 
+// several independent K1 jobs (the axes of a space, the axes of a geometry) in one launch
+#define PB_BASIS_MAXJOBS 6
+struct PbBasisBatch {
+    int njobs;
+    const double* kv[PB_BASIS_MAXJOBS];
+    int nk[PB_BASIS_MAXJOBS], p[PB_BASIS_MAXJOBS];
+    const double* nodes[PB_BASIS_MAXJOBS];
+    int m[PB_BASIS_MAXJOBS], nd[PB_BASIS_MAXJOBS];
+    int* first[PB_BASIS_MAXJOBS];
+    double* values[PB_BASIS_MAXJOBS];
+};
+
 #if defined(__CUDACC__)
+__global__ void pb_basis_batch_kernel(const __grid_constant__ PbBasisBatch b) {
+    const int j = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < b.m[j]) pb_basis_node(b.kv[j], b.nk[j], b.p[j], b.nodes[j], b.nd[j], b.first[j], b.values[j], g);
+}
+
 __global__ void pb_basis_kernel(const double* __restrict__ kv, int nk, int p, const double* __restrict__ nodes,
                                 int m, int nd, int* __restrict__ first, double* __restrict__ values) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
