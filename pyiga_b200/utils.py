@@ -1,38 +1,45 @@
-"""Evaluation of user functions on tensor grids (``pyiga/utils.py:9-52``).  Python callables cannot
-run on the device; like the reference they are evaluated with numpy on grids whose geometry
-transform comes from the GPU (``grid_eval`` of the spline functions)."""
+"""Evaluation of user functions on tensor grids (the behaviour of ``pyiga/utils.py:9-52``).
+
+Python callables cannot run on the device; like the reference they are evaluated with numpy, on
+grids whose geometry transform comes from the GPU (``grid_eval`` of the spline function objects).
+Axes are ordered z, y, x; user functions take their arguments in x, y, z order.
+"""
 import numpy as np
 
 
-def _broadcast_to_grid(X, grid_shape):
-    num_dims = len(grid_shape)
-    X = np.asanyarray(X)
-    if X.ndim == 0:
-        X = np.broadcast_to(X, grid_shape)
-    # input might be a higher-dimensional tensor: only the leading grid axes are broadcast
-    if X.shape[:num_dims] != tuple(grid_shape):
-        X = np.broadcast_to(X, tuple(grid_shape) + X.shape[num_dims:])
-    return X
+def _on_grid(values, shape):
+    """Bring the result of a user function to an array whose leading axes are the grid: tuples are
+    vector components (stacked last), scalars and partially broadcast results are expanded."""
+    nd = len(shape)
+
+    def expand(v):
+        v = np.asanyarray(v)
+        if v.ndim == 0 or v.shape[:nd] != shape:
+            tail = v.shape[nd:] if v.ndim > nd else ()
+            v = np.broadcast_to(v, shape + tail)
+        return v
+
+    if isinstance(values, tuple):
+        return np.stack([expand(c) for c in values], axis=-1)
+    return expand(values)
 
 
 def _ensure_grid_shape(values, grid):
-    grid_shape = tuple(len(g) for g in grid)
-    if isinstance(values, tuple):       # vector-valued function given as a tuple of components
-        values = np.stack(tuple(_broadcast_to_grid(v, grid_shape) for v in values), axis=-1)
-    return _broadcast_to_grid(values, grid_shape)
+    return _on_grid(values, tuple(len(g) for g in grid))
 
 
 def grid_eval(f, grid):
-    """Evaluate `f` over the tensor grid `grid` (axes in z,y,x order; `f` takes x,y,z)."""
-    if hasattr(f, 'grid_eval'):
-        return f.grid_eval(grid)
-    mesh = list(np.meshgrid(*grid, sparse=True, indexing='ij'))
-    mesh.reverse()
-    return _ensure_grid_shape(f(*mesh), grid)
+    """`f` on the tensor grid `grid`; objects with their own ``grid_eval`` (spline functions) are
+    asked directly."""
+    own = getattr(f, 'grid_eval', None)
+    if own is not None:
+        return own(grid)
+    open_axes = np.ix_(*[np.asarray(g, dtype=float) for g in grid])     # broadcastable coordinate arrays, z..x
+    return _on_grid(f(*open_axes[::-1]), tuple(len(g) for g in grid))
 
 
 def grid_eval_transformed(f, grid, geo):
-    """Evaluate `f`, given in physical coordinates, on the image of the grid under `geo`."""
-    trf = grid_eval(geo, grid)
-    X = tuple(trf[..., i] for i in range(trf.shape[-1]))
-    return _ensure_grid_shape(f(*X), grid)
+    """`f`, given in physical coordinates, on the image of the tensor grid under `geo`."""
+    pts = grid_eval(geo, grid)
+    coords = [pts[..., k] for k in range(pts.shape[-1])]
+    return _on_grid(f(*coords), tuple(len(g) for g in grid))
