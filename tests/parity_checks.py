@@ -805,3 +805,19 @@ def check_reference_driver_dropin(ref):
         P = rh._assemble_partial_rows(asm, rows)
         assert abs(P[rows] - want[rows]).max() <= RTOL * abs(want).max()
     # (assemble_entries_vec and format='mlb' of the reference take Cython-typed assemblers only)
+
+
+def check_poisson_end_to_end():
+    """the whole flow of test/test_solve.py in 3D on the rational twisted box: the discretisation
+    error falls with the mesh width at the rate of the spline degree"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('poisson_demo', os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'tools', 'poisson_demo.py'))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    r1 = demo.solve(2, 4)
+    r2 = demo.solve(2, 8)
+    assert r1['cg_info'] == 0 and r2['cg_info'] == 0
+    assert r2['rms_error_vs_interpolant'] < 0.3 * r1['rms_error_vs_interpolant'], (r1, r2)
+    assert r2['rms_error_vs_interpolant'] < 1e-3, r2

@@ -175,3 +175,7 @@ def test_initial_condition(emu, ref):
 
 def test_project_L2(emu, ref):
     pc.check_project_L2(ref)
+
+
+def test_poisson_end_to_end(emu):
+    pc.check_poisson_end_to_end()

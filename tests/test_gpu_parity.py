@@ -235,3 +235,7 @@ def test_initial_condition(cuda, ref):
 
 def test_project_L2(cuda, ref):
     pc.check_project_L2(ref)
+
+
+def test_poisson_end_to_end(cuda):
+    pc.check_poisson_end_to_end()
