@@ -1170,7 +1170,8 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
             }
         }
         K = std::min(K, std::min(PB_WALK_MAXSPLIT, r_hi - r_lo));
-        if (K > 1 && getenv("PB200_DEBUG_SPLIT")) fprintf(stderr, "[pb200] stage %s: walk axis cut into %d pieces\n", name, K);
+        static const bool debug_split = getenv("PB200_DEBUG_SPLIT") != nullptr;
+        if (K > 1 && debug_split) fprintf(stderr, "[pb200] stage %s: walk axis cut into %d pieces\n", name, K);
         if (K > 1) {
             prm.nsplit = K;
             for (int y = 0; y < K; ++y) {
