@@ -436,9 +436,10 @@ class GenericFormAssembler(_AssemblerProtocol):
     """
     _vf = None
 
-    def __init__(self, kvs, kvs_test=None, **args):
+    def __init__(self, kvs, kvs_test=None, bbox=None, **args):
         vf = self._vf
         kvs = tuple(kvs)
+        self.bbox = bbox            # on-demand box of the reference's generated classes: not needed here
         d = vf.dim
         assert len(kvs) == d, "Assembler requires %d knot vectors" % d
         if vf.num_spaces() == 2:

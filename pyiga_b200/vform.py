@@ -618,10 +618,13 @@ def _nested_get(v, idx):
     return v
 
 
-def compile_vform(vf):
+def compile_vform(vf, on_demand=False, verbose=False):
     """Return an assembler *class* for the form, like ``pyiga.compile.compile_vform``
     (``pyiga/compile.py:120-132``); no code is generated — the class analyses the form when it is
-    instantiated on a concrete space."""
+    instantiated on a concrete space.  `on_demand` assemblers of the reference evaluate their fields
+    lazily inside a bounding box of cells (``bbox=`` of the constructor, used by
+    ``HDiscretization._assemble_level``); here the fields of the whole patch are one K2 launch, so the
+    flag and the box are accepted and every entry stays valid."""
     input_shapes = {'geo': (vf.geo_dim,)}
     input_shapes.update({name: shape for name, shape, _, _ in vf.inputs})
     param_shapes = {name: shape for name, shape in vf.params}

@@ -611,6 +611,12 @@ def check_partial_rows(ref):
     part = assemble.assemble_partial_rows(asm, rows)
     assert abs(part[rows] - full[rows]).max() <= RTOL * abs(full).max()
     assert part.nnz == full[rows].nnz
+    # the call HDiscretization._assemble_level makes: on-demand class, bounding box of cells
+    from pyiga_b200 import vform as vfm
+    cls = vfm.compile_vform(vfm.parse_vf(form, kvs, args=inputs), on_demand=True)
+    asm2 = cls(kvs, geo=make_geo(ref, gname), bbox=tuple((0, kv.numspans) for kv in kvs), **inputs)
+    part2 = assemble.assemble_partial_rows(asm2, rows)
+    assert abs(part2 - part).max() <= 1e-14 * abs(full).max()
 
 
 def check_boundary_forms(ref):
