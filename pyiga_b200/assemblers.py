@@ -736,6 +736,11 @@ class GenericFormAssembler(_AssemblerProtocol):
             if name == 'geo':
                 self._geo, self._X = f, None
                 self._args['geo'] = f
+                # surface measure and normal are functions of the geometry as well
+                if self._bd is not None:
+                    self._boundary_fields()
+                if self._surface:
+                    self._surface_fields()
                 for n2, (shape, physical) in known.items():     # physical inputs move with the geometry
                     if physical:
                         self._env[n2] = self._eval_input(self._args[n2], shape, physical)

@@ -120,38 +120,64 @@ class MLStructure:
         return I, J
 
     def sequential_bidx(self):
-        return [self.bs[j][0] * self.bidx[j][:, 0] + self.bidx[j][:, 1] for j in range(self.L)]
+        """per level: the nonzero positions as C-order offsets into the (m_k x n_k) block"""
+        return [bx[:, 0] * np.uint32(m) + bx[:, 1] for bx, (m, _) in zip(self.bidx, self.bs)]
 
-    def _level_rowwise_interactions(self, k):
+    def _level_csr(self, k):
+        """columns of level k grouped by row: (start[m+1], cols) — a CSR view of ``bidx[k]``"""
         bx = self.bidx[k]
         order = np.argsort(bx[:, 0], kind='stable')
-        rows = bx[order, 0]
-        cuts = np.searchsorted(rows, np.arange(self.bs[k][0] + 1))
-        cols = bx[order, 1].astype(np.int64)
-        return [cols[cuts[i]:cuts[i + 1]] for i in range(self.bs[k][0])]
+        start = np.searchsorted(bx[order, 0], np.arange(self.bs[k][0] + 1)).astype(np.int64)
+        return start, bx[order, 1].astype(np.int64)
 
     def nonzeros_for_rows(self, row_indices, renumber_rows=False):
-        """Nonzero positions restricted to the given rows (``pyiga/mlmatrix.py:150-185``)."""
-        row_indices = np.asarray(row_indices, dtype=np.int64)
-        if row_indices.size == 0:
+        """Nonzero positions restricted to the given rows (``pyiga/mlmatrix.py:150-185``): for row
+        ``(i_0,..,i_{L-1})`` the columns are the Cartesian product of the per-level column lists,
+        last level fastest.  Vectorised over all rows: entry t of a row is decomposed in the mixed
+        radix of the row's per-level counts."""
+        rows = np.asarray(row_indices, dtype=np.int64).ravel()
+        if rows.size == 0:
             e = np.empty(0, dtype=int)
             return (e, e, e) if renumber_rows else (e, e)
-        lvia = [self._level_rowwise_interactions(k) for k in range(self.L)]
-        bs_I = tuple(b[0] for b in self.bs)
-        bs_J = tuple(b[1] for b in self.bs)
-        ix = np.column_stack(np.unravel_index(row_indices, bs_I))
-        Js, counts = [], []
-        for r in range(ix.shape[0]):
-            J = np.zeros(1, dtype=np.int64)
-            for k in range(self.L):
-                J = (J[:, None] * bs_J[k] + lvia[k][ix[r, k]][None, :]).ravel()
-            Js.append(J)
-            counts.append(J.size)
-        Is = np.repeat(row_indices, counts)
-        Js = np.concatenate(Js) if Js else np.empty(0, dtype=int)
+        level = [self._level_csr(k) for k in range(self.L)]
+        multi = np.unravel_index(rows, tuple(b[0] for b in self.bs))
+        first = [level[k][0][multi[k]] for k in range(self.L)]                  # start of the column list
+        count = [level[k][0][multi[k] + 1] - first[k] for k in range(self.L)]   # its length
+        per_row = np.prod(count, axis=0)
+        which = np.repeat(np.arange(rows.size), per_row)
+        t = np.arange(per_row.sum()) - np.repeat(np.cumsum(per_row) - per_row, per_row)
+        digits = [None] * self.L
+        for k in range(self.L - 1, -1, -1):
+            ck = count[k][which]
+            digits[k] = t % np.maximum(ck, 1)
+            t = t // np.maximum(ck, 1)
+        Js = np.zeros(which.size, dtype=np.int64)
+        for k in range(self.L):
+            Js = Js * self.bs[k][1] + level[k][1][first[k][which] + digits[k]]
+        Is = rows[which]
         if renumber_rows:
-            return Is, Js, np.repeat(np.arange(len(row_indices)), counts)
+            return Is, Js, which
         return Is, Js
+
+    def positions(self, I, J):
+        """Flat position in the value tensor of the entries (I, J), or -1 for pairs outside the
+        pattern (for which ``multi_entries`` returns 0, ``pyiga/genericasm.pxi:722-758``).  Needs
+        contiguous per-row column ranges on every level (all spline patterns)."""
+        I = np.array(I, dtype=np.int64).ravel()
+        J = np.array(J, dtype=np.int64).ravel()
+        pos = np.zeros(I.shape, dtype=np.int64)
+        ok = np.ones(I.shape, dtype=bool)
+        ik = np.unravel_index(I, tuple(b[0] for b in self.bs))
+        jk = np.unravel_index(J, tuple(b[1] for b in self.bs))
+        for k in range(self.L):
+            tabs = self._row_tables(k)
+            assert tabs is not None, 'level %d has no contiguous row pattern' % k
+            row_start, jmin = (t.astype(np.int64) for t in tabs)
+            d = jk[k] - jmin[ik[k]]
+            ok &= (d >= 0) & (d < row_start[ik[k] + 1] - row_start[ik[k]])
+            pos = pos * len(self.bidx[k]) + row_start[ik[k]] + np.where(ok, d, 0)
+        pos[~ok] = -1
+        return pos
 
     def nonzeros_for_columns(self, col_indices):
         J, I = self.transpose().nonzeros_for_rows(col_indices)

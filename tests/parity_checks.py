@@ -646,6 +646,15 @@ def check_boundary_forms(ref):
     ij = np.array([(0, 0), (3, 4), (R.shape[0] - 1, R.shape[0] - 2), (0, R.shape[0] - 1)])
     want = np.asarray(R[ij[:, 0], ij[:, 1]]).ravel()
     assert np.abs(asm.multi_entries(ij) - want).max() <= RTOL * abs(R).max()
+    # updating the geometry of a boundary form refreshes the surface measure and the normal too:
+    # same matrix as a freshly built assembler
+    kvs = make_space(ref, 'a2_qa')
+    g1, g2 = make_geo(ref, 'qa'), make_geo(ref, 'bqa')
+    for form in ('u * v * ds', 'inner(grad(u), n) * v * ds'):
+        upd = assemble.Assembler(form, kvs, geo=g1, boundary='left', updatable=['geo'])
+        fresh = assemble.assemble(form, kvs, geo=g2, boundary='left')
+        got = upd.assemble(geo=g2)
+        assert abs(got - fresh).max() <= 1e-14 * abs(fresh).max(), form
 
 
 def check_two_spaces(ref):
@@ -827,3 +836,112 @@ def check_poisson_end_to_end():
     assert r1['cg_info'] == 0 and r2['cg_info'] == 0
     assert r2['rms_error_vs_interpolant'] < 0.3 * r1['rms_error_vs_interpolant'], (r1, r2)
     assert r2['rms_error_vs_interpolant'] < 1e-3, r2
+
+
+# ---------------------------------------------------------------------------------------------
+# benchmark-scale parity against sampled entries of the real reference
+# (tests/golden/large_*.npz, made by tests/golden/make_golden_large.py)
+# ---------------------------------------------------------------------------------------------
+LARGE_CONVDIFF = '(inner(diff_coeff * grad(u), grad(v)) + inner((x[1], -x[0], 1.0), grad(u)) * v) * dx'
+
+
+def load_large(name):
+    import os
+    from helpers import GOLDEN
+    return np.load(os.path.join(GOLDEN, 'large_%s.npz' % name))
+
+
+def large_assembler(z):
+    """the device assembler of a large fixture: (asm, kvs, geo)"""
+    from pyiga_b200 import assemble, assemblers, bspline, geometry
+    form, p, n = str(z['form']), int(z['p']), int(z['n'])
+    kvs = 3 * (bspline.make_knots(p, 0.0, 1.0, n),)
+    geo = geometry.twisted_nurbs_box() if str(z['geo']) == 'tnb' else geometry.twisted_box()
+    if form == 'stiffness':
+        asm = assemblers.StiffnessAssembler3D(kvs, geo)
+    elif form == 'mass':
+        asm = assemblers.MassAssembler3D(kvs, geo)
+    else:
+        asm = assemble.instantiate_assembler(LARGE_CONVDIFF, kvs, {'geo': geo, 'diff_coeff': lambda x, y, z: 1.0 + x * y}, None)
+    return asm, kvs, geo
+
+
+def sample_errors(dev, d_data, rows, z, pos=None):
+    """max |ours - reference| over the sampled entries whose row lies in the first-axis row slab
+    `rows`, read out of the device MLB buffer `d_data` of that slab; also checks that pairs for
+    which the reference returned 0 outside the pattern are outside ours.  Returns (max abs error,
+    number of entries compared)."""
+    be = dev.be
+    ij = z['ij'].astype(np.int64)
+    want = z['val']
+    S = dev.structure
+    if pos is None:
+        pos = S.positions(ij[:, 0], ij[:, 1])
+    nout = int(z['nout'])
+    assert np.all(pos[len(pos) - nout:] == -1), 'pairs outside the reference pattern are inside ours'
+    assert np.all(pos[:len(pos) - nout] >= 0), 'pairs inside the reference pattern are outside ours'
+    plane_rows = int(np.prod(dev.ndofs_test[1:], dtype=np.int64))
+    i0 = ij[:, 0] // plane_rows
+    rs = dev.row_start0()
+    inner = int(np.prod(dev.nband[1:], dtype=np.int64))
+    sel = (pos >= 0) & (i0 >= rows[0]) & (i0 < rows[1])
+    if not sel.any():
+        return 0.0, 0
+    local = pos[sel] - int(rs[rows[0]]) * inner
+    assert local.min() >= 0 and local.max() < dev.slab_size(rows)
+    got = be.to_host(d_data[be.from_host(local)])
+    return float(np.abs(got - want[sel]).max()), int(sel.sum())
+
+
+def check_large(name, nslabs=1):
+    """sum-factorised assembly at a benchmarked size against the reference's sampled entries, as one
+    slab or as `nslabs` independent row slabs (the multi-GPU sharding on one device)"""
+    from pyiga_b200.dist import partition_rows
+    z = load_large(name)
+    asm, kvs, geo = large_assembler(z)
+    dev = asm.dev
+    assert dev.fast_path
+    scale = float(z['full_maxabs']) if 'full_maxabs' in z else float(z['sample_maxabs'])
+    ij = z['ij'].astype(np.int64)
+    pos = dev.structure.positions(ij[:, 0], ij[:, 1])
+    slabs = partition_rows(dev, nslabs) if nslabs > 1 else [(0, dev.ndofs_test[0])]
+    worst, count = 0.0, 0
+    for rows in slabs:
+        if nslabs > 1:
+            if hasattr(asm, 'compute_fields_rows'):
+                asm.compute_fields_rows(rows)
+            else:
+                dev.compute_fields(geo, rows=rows)
+        data = dev.assemble_mlb(rows=rows)
+        err, cnt = sample_errors(dev, data, rows, z, pos)
+        worst, count = max(worst, err), count + cnt
+        del data
+    assert count == len(pos) - int(z['nout']), 'every sampled entry belongs to exactly one slab'
+    assert worst <= RTOL * scale, '%s in %d slabs: max abs error %.3e > %.1e * max|A_ref| (%.3e)' % (name, nslabs, worst, RTOL, scale)
+    return worst / scale
+
+
+def check_large_full(name):
+    """p=3 n=64: whole-matrix checks against the reference's full assembly — nnz, sum of all entries,
+    sum of absolute values, max|A| and a strided matvec checksum (A x)[::stride]"""
+    z = load_large(name)
+    asm, kvs, geo = large_assembler(z)
+    M = asm.assemble_mlb()
+    d = M.data                  # host copy of the device tensor (0.76 GB at n=64)
+    scale = float(z['full_maxabs'])
+    nnz = int(z['full_nnz'])
+    assert M.nnz == nnz
+    assert abs(float(np.abs(d).max()) - scale) <= RTOL * scale
+    # sums of 9.5e7 terms: compare with the rounding of the summation, not of a single entry
+    assert abs(float(d.sum()) - float(z['full_sum'])) <= 1e-12 * float(z['full_abs_sum'])
+    assert abs(float(np.abs(d).sum()) - float(z['full_abs_sum'])) <= 1e-12 * float(z['full_abs_sum'])
+    x = np.cos(float(z['mv_freq']) * np.arange(M.shape[1]) + float(z['mv_phase']))
+    y = M.dot(x)[::int(z['mv_stride'])]
+    rowmax = (2 * int(z['p']) + 1) ** 3 * scale     # at most (2p+1)^3 entries per row
+    assert np.abs(y - z['mv_y']).max() <= RTOL * rowmax
+    # CSR through the public driver: int32, sorted, and the same values at the sampled pairs
+    A = asm.assemble_csr()
+    assert A.nnz == nnz and A.indices.dtype == np.int32 and A.has_sorted_indices
+    ij = z['ij'].astype(np.int64)
+    got = np.asarray(A[ij[:, 0], ij[:, 1]]).ravel()
+    assert np.abs(got - z['val']).max() <= RTOL * scale

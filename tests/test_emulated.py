@@ -179,3 +179,13 @@ def test_project_L2(emu, ref):
 
 def test_poisson_end_to_end(emu):
     pc.check_poisson_end_to_end()
+
+
+@pytest.mark.parametrize('name,nslabs', [('tiny_stiff_p2_n6', 1), ('tiny_stiff_p2_n6', 3), ('tiny_mass_p3_n5', 2)])
+def test_large_fixture_logic(emu, name, nslabs):
+    """the benchmark-scale parity check (sampled reference entries) on a tiny copy of its fixture"""
+    pc.check_large(name, nslabs)
+
+
+def test_large_full_logic(emu):
+    pc.check_large_full('tiny_stiff_p2_n6')

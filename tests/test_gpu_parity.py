@@ -239,3 +239,26 @@ def test_project_L2(cuda, ref):
 
 def test_poisson_end_to_end(cuda):
     pc.check_poisson_end_to_end()
+
+
+# ---- benchmark-scale parity against the real reference (sampled multi_entries fixtures) ------------
+LARGE = ['stiff_p3_n64', 'mass_p3_n64', 'stiff_p3_n128', 'mass_p3_n128', 'stiff_p4_n96', 'mass_p4_n96']
+
+
+@pytest.mark.parametrize('nslabs', [1, 8])
+@pytest.mark.parametrize('name', LARGE)
+def test_large_vs_reference(cuda, name, nslabs):
+    """the sizes that are benchmarked, against ~1e5 entries per case computed by the reference's
+    multi_entries (complete corner / edge / slab-seam / interior rows, random entries, pairs outside
+    the pattern); 1e-12 relative to max|A_ref|"""
+    pc.check_large(name, nslabs)
+
+
+@pytest.mark.parametrize('name', ['stiff_p3_n64', 'mass_p3_n64'])
+def test_large_full_matrix_checks(cuda, name):
+    pc.check_large_full(name)
+
+
+def test_large_convdiff_vs_reference(cuda):
+    """config 5's form at p=3 n=96 against the reference's JIT-compiled assembler"""
+    pc.check_large('convdiff_p3_n96', 1)
