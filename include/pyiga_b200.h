@@ -135,6 +135,15 @@ PB200_API int pb200_asm_structure(const pb200_assembler* a, int axis, uint32_t* 
  * geo.grid_jacobian + precompute_fields (pyiga/bspline.py:897-921, geometry.py:116-123,
  * assemblers.pyx:1389-1449). */
 PB200_API int pb200_asm_bind_fields(pb200_assembler* a, double* d_fields);
+/* Bind a spline geometry WITHOUT evaluating the fields: control net and knots are uploaded and the
+ * 1D geometry basis tables are evaluated at the Gauss nodes (K1).  For 3D mass / stiffness the
+ * fused stage 1 of pb200_asm_assemble_mlb then evaluates grid_jacobian + precompute_fields
+ * (same reference code as above) in registers, point by point, while it contracts the first axis
+ * — the field array is never materialised.  pb200_asm_uses_fused_fields tells whether the next
+ * pb200_asm_assemble_mlb takes that path (1) or needs pb200_asm_compute_fields* first (0);
+ * after pb200_asm_set_geometry the latter may be called with geo = NULL. */
+PB200_API int pb200_asm_set_geometry(pb200_assembler* a, const pb200_geo_desc* geo, void* stream);
+PB200_API int pb200_asm_uses_fused_fields(const pb200_assembler* a);
 PB200_API int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc* geo, void* stream);
 /* same, restricted to the Gauss planes that the rows [row0_begin,row0_end) of the first axis see
  * (slab-sharded assembly: every rank evaluates only its planes plus the p-span overlap) */

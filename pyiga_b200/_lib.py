@@ -60,6 +60,8 @@ SIGNATURES = {
     'pb200_asm_tabulate': (C.c_int, [C.c_void_p, C.c_void_p]),
     'pb200_asm_structure': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'pb200_asm_bind_fields': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'pb200_asm_set_geometry': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_void_p]),
+    'pb200_asm_uses_fused_fields': (C.c_int, [C.c_void_p]),
     'pb200_asm_compute_fields': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_void_p]),
     'pb200_asm_compute_fields_slab': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_int, C.c_int, C.c_void_p]),
     'pb200_asm_compute_fields_general': (C.c_int, [C.c_void_p, C.POINTER(GeoDesc), C.c_void_p, C.c_int,

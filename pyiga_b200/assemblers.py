@@ -83,8 +83,9 @@ class DeviceAssembler:
         self.fast_path = bool(info.fast_path)
         self.nnz = int(info.nnz)
         self.npoints = int(info.npoints)
-        self.fields = be.empty(self.nfields * self.npoints)
-        _device.check(be.lib.pb200_asm_bind_fields(h, be.ptr(self.fields)))
+        self._fields = None         # allocated when a kernel needs the field array (see `fields`)
+        self._geo_bound = None      # spline geometry bound on the device, fields not evaluated yet
+        self._fields_rows = None    # rows of axis 0 whose Gauss planes hold current fields ('all' or (ra, rb))
         self._structure = None
         self._dstruct = None
         self._row_start0 = None
@@ -129,6 +130,43 @@ class DeviceAssembler:
         return self._row_start0
 
     # ---- fields ------------------------------------------------------------------------------
+    @property
+    def fields(self):
+        """the coefficient-field array F[c][g0][g1][g2] on the device, allocated on first use: the
+        fused 3D mass / stiffness pipeline never needs it"""
+        if self._fields is None:
+            self._fields = self.be.empty(self.nfields * self.npoints)
+            _device.check(self.be.lib.pb200_asm_bind_fields(self.handle, self.be.ptr(self._fields)))
+        return self._fields
+
+    @fields.setter
+    def fields(self, buf):
+        self._fields = buf
+        self._fields_rows = 'all'
+
+    def uses_fused_fields(self):
+        """True if assemble_mlb evaluates geometry and fields inside its first stage (no K2)"""
+        return bool(self.be.lib.pb200_asm_uses_fused_fields(self.handle))
+
+    def need_fields(self, rows=None):
+        """make sure the field array holds the fields of the bound geometry on the Gauss planes the
+        rows `rows` of the first axis see (K2 runs now if it has not yet)"""
+        if self._geo_bound is None:
+            if self._fields_rows is None:
+                raise RuntimeError('fields have not been computed')
+            return
+        have = self._fields_rows
+        if have == 'all' or (have is not None and rows is not None and have[0] <= rows[0] and rows[1] <= have[1]):
+            return
+        be = self.be
+        self.fields
+        if rows is None:
+            _device.check(be.lib.pb200_asm_compute_fields(self.handle, None, be.stream()))
+            self._fields_rows = 'all'
+        else:
+            _device.check(be.lib.pb200_asm_compute_fields_slab(self.handle, None, rows[0], rows[1], be.stream()))
+            self._fields_rows = tuple(rows)
+
     def tabulate(self):
         _device.check(self.be.lib.pb200_asm_tabulate(self.handle, self.be.stream()))
 
@@ -137,22 +175,26 @@ class DeviceAssembler:
         planes seen by the rows `rows` of the first axis)."""
         be = self.be
         if _is_spline_geo(geo):
+            # bind the geometry; K2 itself runs only if a kernel asks for the field array
+            # (`need_fields`): the fused first stage of the 3D pipeline evaluates the fields itself
             desc, keep = _lib.make_geo_desc(geo)
-            if rows is None:
-                _device.check(be.lib.pb200_asm_compute_fields(self.handle, C.byref(desc), be.stream()))
-            else:
-                _device.check(be.lib.pb200_asm_compute_fields_slab(self.handle, C.byref(desc), rows[0], rows[1],
-                                                                    be.stream()))
+            _device.check(be.lib.pb200_asm_set_geometry(self.handle, C.byref(desc), be.stream()))
+            self._geo_bound, self._fields_rows = geo, None
+            if not self.uses_fused_fields():
+                self.need_fields(rows)
         else:
             # geometry given as an arbitrary Python object: evaluate its Jacobian on the host, as
             # the reference does for every geometry, and upload it
             jac = np.ascontiguousarray(geo.grid_jacobian(self.gaussgrid), dtype=np.float64)
             assert jac.shape == self.nnodes + (self.dim, self.dim), 'geo.grid_jacobian returned a wrong shape'
             d_jac = be.from_host(jac.ravel())
+            self.fields
             _device.check(be.lib.pb200_asm_compute_fields_from_jacobian(self.handle, be.ptr(d_jac), be.stream()))
             be.synchronize()
+            self._geo_bound, self._fields_rows = None, 'all'
 
     def fields_host(self):
+        self.need_fields()
         return self.be.to_host(self.fields).reshape((self.nfields,) + self.nnodes)
 
     # ---- assembly ----------------------------------------------------------------------------
@@ -198,8 +240,11 @@ class DeviceAssembler:
         rs = self.row_start0()
         inner = int(np.prod(self.nband[1:], dtype=np.int64))
         if entrywise:
+            self.need_fields()
             _device.check(be.lib.pb200_asm_assemble_mlb_entrywise(self.handle, ra, rb, be.ptr(out), be.stream()))
             return out
+        if not self.uses_fused_fields():
+            self.need_fields((ra, rb))
         if budget_bytes is None and workspace is None:
             budget_bytes = max(be.free_bytes() - (1 << 30), 1 << 28) if self.fast_path else None
         elif workspace is not None:
@@ -218,6 +263,7 @@ class DeviceAssembler:
     def assemble_vector_device(self):
         """load vector of a linear form as a flat device buffer (C order of the test space)"""
         be = self.be
+        self.need_fields()
         n = C.c_size_t()
         _device.check(be.lib.pb200_asm_vector_workspace_bytes(self.handle, C.byref(n)))
         ws = be.empty(n.value, np.uint8)
@@ -245,6 +291,7 @@ class DeviceAssembler:
         """Device CSR arrays (indptr, indices, values) of the given matrix rows, values by per-entry
         quadrature (``pb200_asm_rows_count`` / ``pb200_asm_rows_fill``)."""
         be = self.be
+        self.need_fields()
         rows = np.ascontiguousarray(rows, dtype=np.int64).ravel()
         n = rows.size
         h_indptr = np.zeros(n + 1, dtype=np.int64)
@@ -263,6 +310,7 @@ class DeviceAssembler:
 
     def multi_entries_device(self, ij):
         be = self.be
+        self.need_fields()
         ij = np.ascontiguousarray(ij, dtype=np.uint64).reshape(-1, 2)
         n = ij.shape[0]
         out = be.empty(n)
@@ -391,6 +439,7 @@ class _FormBlock:
             fields[f] = W * acc
         buf = be.from_host(np.ascontiguousarray(fields).ravel())
         dev.fields = buf
+        dev._geo_bound = None
         _device.check(be.lib.pb200_asm_bind_fields(dev.handle, be.ptr(buf)))
 
     def compute_fields(self, coefs, geo):
@@ -412,6 +461,8 @@ class _FormBlock:
                 inp = index[id(c.arr)]
             phys[t] = _lib.PhysTerm(key[0], key[1], inp, c.scale)
         ptrs = (C.c_void_p * max(len(arrays), 1))(*[be.ptr(a) for a in arrays])
+        dev.fields                  # allocate and bind the field array
+        dev._geo_bound, dev._fields_rows = None, 'all'
         if _is_spline_geo(geo):
             desc, keep = _lib.make_geo_desc(geo)
             _device.check(be.lib.pb200_asm_compute_fields_general(dev.handle, C.byref(desc), None, len(coefs), phys,

@@ -22,6 +22,8 @@
 #include "csr.cuh"
 #include "plans.cuh"
 #include "walk1.cuh"
+#include "walk_geo.cuh"
+#include "fused23.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -241,6 +243,16 @@ static Walk1Registry& registry1() {
     return r;
 }
 extern "C" void pb200_register_walk1(int P, int Q, PbWalk1Launch fn) { registry1()[std::make_pair(P, Q)] = fn; }
+typedef std::map<std::tuple<int, int, int>, PbS32Launch> S32Registry;
+static S32Registry& registry_s32() {
+    static S32Registry r;
+    return r;
+}
+extern "C" void pb200_register_s32(int form, int P, int Q, PbS32Launch fn) { registry_s32()[std::make_tuple(form, P, Q)] = fn; }
+PbS32Launch pb_find_s32(int form, int P, int Q) {
+    auto it = registry_s32().find(std::make_tuple(form, P, Q));
+    return it == registry_s32().end() ? nullptr : it->second;
+}
 PbWalk1Launch pb_find_walk1(int P, int Q) {
     auto it = registry1().find(std::make_pair(P, Q));
     return it == registry1().end() ? nullptr : it->second;
@@ -385,6 +397,11 @@ struct pb200_assembler {
     std::vector<std::pair<int, int>> field_slots;       // custom forms: (test slot, trial slot) of field f
     void* geo_scratch = nullptr;
     size_t geo_scratch_bytes = 0;
+    PbGeoDev geo_dev;                                   // device tables of the bound spline geometry (in geo_scratch)
+    bool geo_valid = false;                             // geo_dev describes the current geometry
+    bool fields_valid = false;                          // d_fields holds the fields of the current geometry
+    bool fuse = true;                                   // 3D mass / stiffness: fused stage 1 (geometry + fields + axis 0, walk_geo.cuh)
+    bool fuse23 = true;                                 // 3D mass / stiffness: fused stages 2 + 3 (fused23.cuh), no X2 in HBM
     long long npts = 0, nnz = 0;
     int fast = 0;
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
@@ -429,6 +446,8 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!strcmp(name, "lane_lines")) { if (value < 1 || value > 64) return fail(PB200_EINVAL, "lane_lines must be in 1..64"); a->lane_lines = value; return 0; }
     if (!strcmp(name, "fused_plans")) { a->fused_plans = value != 0; return 0; }
     if (!strcmp(name, "mirror")) { a->mirror_opt = value != 0; return 0; }
+    if (!strcmp(name, "fuse")) { a->fuse = value != 0; return 0; }
+    if (!strcmp(name, "fuse23")) { a->fuse23 = value != 0; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
 }
 
@@ -854,7 +873,31 @@ static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, co
 extern "C" int pb200_asm_bind_fields(pb200_assembler* a, double* d_fields) {
     if (!a) return fail(PB200_EINVAL, "null handle");
     a->d_fields = d_fields;
+    a->fields_valid = d_fields != nullptr;      // the caller's buffer is taken as the fields until a new geometry is bound
     return 0;
+}
+
+// upload the spline geometry and tabulate its 1D basis functions at the Gauss nodes; the tables stay
+// in a scratch buffer of the assembler that is kept between calls (no allocation, release or
+// synchronisation in the steady state)
+static int bind_geometry(pb200_assembler* a, const pb200_geo_desc* geo, pbStream st) {
+    const double* d_nodes[PB_MAXDIM] = {nullptr, nullptr, nullptr};
+    int G[PB_MAXDIM] = {1, 1, 1};
+    for (int k = 0; k < a->dim; ++k) { G[k] = a->hax[k].G; d_nodes[k] = a->dax[k].nodes; }
+    GeoTables T;
+    a->geo_valid = false;
+    int rc = build_geo_tables(geo, a->dim, G, d_nodes, st, T, true, &a->geo_scratch, &a->geo_scratch_bytes);
+    if (rc) return rc;
+    a->geo_dev = T.dev;
+    a->geo_valid = true;
+    a->fields_valid = false;
+    return 0;
+}
+
+extern "C" int pb200_asm_set_geometry(pb200_assembler* a, const pb200_geo_desc* geo, void* stream) {
+    if (!a || !geo) return fail(PB200_EINVAL, "null argument");
+    CK(pbSetDevice(a->device));
+    return bind_geometry(a, geo, (pbStream)stream);
 }
 
 template <int DIM, class Prog>
@@ -918,14 +961,19 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
     }
     prm.nf = a->nfields;
     prm.jac_in = d_jac;
-    GeoTables T;
     if (!d_jac) {
-        // the tables live in a scratch buffer of the assembler that is kept between calls: no
-        // allocation, release or synchronisation in the steady state
-        int rc = build_geo_tables(geo, a->dim, G, d_nodes, st, T, true, &a->geo_scratch, &a->geo_scratch_bytes);
-        if (rc) return rc;
-        prm.geo = T.dev;
+        if (geo) {
+            int rc = bind_geometry(a, geo, st);
+            if (rc) return rc;
+        } else if (!a->geo_valid) {
+            return fail(PB200_EINVAL, "geometry missing");
+        }
+        prm.geo = a->geo_dev;
+    } else {
+        a->geo_valid = false;
     }
+    (void)d_nodes;
+    a->fields_valid = true;     // the launches below are ordered before any consumer on the stream
     const bool mass = a->form == PB200_FORM_MASS;
     if (gen) {
         if (!d_jac) {
@@ -963,6 +1011,7 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
     return mass ? launch_fields<3, PbProgMass<3>>(prm, st) : launch_fields<3, PbProgStiffness<3>>(prm, st);
 }
 
+// `geo` may be null in the two calls below when a geometry has been bound with pb200_asm_set_geometry
 extern "C" int pb200_asm_compute_fields(pb200_assembler* a, const pb200_geo_desc* geo, void* stream) {
     return compute_fields_impl(a, geo, nullptr, (pbStream)stream);
 }
@@ -1046,6 +1095,53 @@ static int make_slab(const pb200_assembler* a, int ra, int rb, bool sym, Slab& S
 
 static bool uses_transposes(const pb200_assembler* a) { return a->form == PB200_FORM_STIFFNESS; }
 
+// 3D mass / stiffness on a bound spline geometry: stage 1 evaluates geometry and fields itself
+// (walk_geo.cuh) — no K2 launch, no field buffer
+static bool fused_stage1(const pb200_assembler* a) {
+    if (!a->fuse || a->dim != 3 || !a->geo_valid || a->arity != 2 || !a->fast || a->force_walk) return false;
+    if (a->form != PB200_FORM_STIFFNESS && a->form != PB200_FORM_MASS) return false;
+    if (!a->lane_ok[0] || !a->walk_rot) return false;           // rotating-window walk on axis 0
+    const PbGeoDev& g = a->geo_dev;
+    if (g.dim != 3 || g.sdim != 3 || g.Ng[0] * g.nc * 3 > PB_GEO_ZMAX) return false;
+    const AxisHost& H = a->hax[0];
+    const int P = H.U.p, Q = H.q;
+    if (!have_plan(a->form == PB200_FORM_STIFFNESS ? PB_PLAN_S1F : PB_PLAN_S1F_MASS, P, Q)) return false;
+    // staged tables of the whole axis (slabs and pieces are shorter) next to the Z columns
+    const size_t nodes = (size_t)H.G;
+    const size_t smem = nodes * 2 * (P + 1) * 8 + ((size_t)H.n + 4 + (size_t)H.V.N() * (2 * P + 1)) * 4
+                        + nodes * (2 * (g.pg[0] + 1) + 1) * 8 + nodes * 4 + ((size_t)g.Ng[0] * g.nc * 3 + (size_t)std::max(Q * 6, (P + 1) * 6)) * 128 * 8 + 1024;
+    return smem <= 113 * 1024;
+}
+
+extern "C" int pb200_asm_uses_fused_fields(const pb200_assembler* a) { return a && fused_stage1(a) ? 1 : 0; }
+
+// 3D mass / stiffness with equal degrees and single interior knots on axes 1 and 2: stages 2 and 3 run
+// as one kernel (fused23.cuh); X2 is never written
+static void fill_s32_axes(const pb200_assembler* a, PbS32Params& p) {
+    const AxisHost &H1 = a->hax[1], &H2 = a->hax[2];
+    const PbAxis &D0 = a->dax[0], &D1 = a->dax[1], &D2 = a->dax[2];
+    p.pair_i0 = D0.pair_i; p.pair_j0 = D0.pair_j; p.tr0 = D0.tr;
+    p.G1 = H1.G; p.G2 = H2.G; p.n1 = H1.n; p.n2 = H2.n;
+    p.N1 = H1.V.N(); p.N2 = H2.V.N(); p.M1 = H1.M; p.M2 = H2.M;
+    p.first1 = D1.first_u; p.V1 = D1.Vu; p.ret_mu1 = D1.ret_mu; p.tr1 = D1.tr;
+    p.first2 = D2.first_u; p.V2 = D2.Vu; p.ret_mu2 = D2.ret_mu; p.tr2 = D2.tr;
+}
+static bool fused_stage23(const pb200_assembler* a) {
+    if (!a->fuse23 || a->dim != 3 || a->arity != 2 || !a->fast || a->force_walk) return false;
+    if (a->form != PB200_FORM_STIFFNESS && a->form != PB200_FORM_MASS) return false;
+    if (!(a->mirror_opt && a->symmetric && a->same_space)) return false;
+    if (!a->lane_ok[1] || !a->lane_ok[2] || !a->walk_rot) return false;
+    const AxisHost &H1 = a->hax[1], &H2 = a->hax[2];
+    if (H1.U.p != H2.U.p || H1.q != H2.q) return false;
+    if ((long long)H1.M * H2.M >= (1LL << 31)) return false;
+    PbS32Launch fn = pb_find_s32(a->form, H1.U.p, H1.q);
+    if (!fn) return false;
+    PbS32Params q;
+    memset(&q, 0, sizeof q);
+    fill_s32_axes(a, q);
+    return fn(&q, nullptr) == 0;        // query: shared memory of this configuration fits
+}
+
 // generic forms: a term travels through the stages as (test slot, trial slot, buffer slot)
 struct GenTerm { int bt, bu, slot; };
 struct GenStage {
@@ -1100,6 +1196,7 @@ static void stage_sizes(const pb200_assembler* a, const Slab& S, size_t& x1_term
         x1_stride = Mext * a->hax[1].G * a->hax[2].G;
         x2_terms = st ? 3 : 1;
         x2_stride = Mext * a->hax[1].M * a->hax[2].G;
+        if (fused_stage23(a)) { x2_terms = 0; x2_stride = 0; }
     }
 }
 
@@ -1288,7 +1385,9 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                                       size_t work_bytes, void* stream) {
     if (!a || !d_out) return fail(PB200_EINVAL, "null argument");
     if (a->arity != 2) return fail(PB200_EINVAL, "matrix assembly needs a bilinear form (arity 2)");
-    if (!a->d_fields) return fail(PB200_EINVAL, "fields have not been computed");
+    const bool fuse1 = fused_stage1(a);
+    const bool fuse23 = fused_stage23(a);
+    if (!fuse1 && (!a->d_fields || !a->fields_valid)) return fail(PB200_EINVAL, "fields have not been computed");
     if (!a->fast) return pb200_asm_assemble_mlb_entrywise(a, row0_begin, row0_end, d_out, stream);
     CK(pbSetDevice(a->device));
     pbStream st = (pbStream)stream;
@@ -1316,7 +1415,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                         && a->lane_ok[last_axis] && !a->force_walk
                         && pb_find_walk(PB_PLAN_LANE_BASE + final_plan, a->hax[last_axis].U.p, a->hax[last_axis].q) != nullptr;
     const int m_tr = uses_transposes(a) ? 2 : 1;        // terms read directly and transposed
-    const int m_dir = mirror ? 3 : 1;                   // terms read directly only
+    const int m_dir = (mirror || fuse23) ? 3 : 1;       // terms read directly only
     auto set_modes = [](int* dst, std::initializer_list<int> m) { int k = 0; for (int v : m) dst[k++] = v; };
 
     const AxisHost &H0 = a->hax[0], &H1 = a->hax[1];
@@ -1455,8 +1554,22 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         p.s_begin = S.sa; p.s_end = S.sb;
         p.w_lo = S.ra; p.w_hi = S.rb; p.w_ext_lo = S.ea; p.w_ext_hi = S.eb;
         // X1 terms (v,v) (v,d1) (v,d2) (d1,d1) (d1,d2) (d2,d2): which are read through a transposed index?
-        const int modes1[6] = {m_dir, m_tr, m_tr, m_dir, m_tr, m_dir};
-        if (stiff && !a->fused_plans) {
+        // (with the fused stages 2 + 3 the term (d1,d2) is only read directly)
+        const int modes1[6] = {m_dir, m_tr, m_tr, m_dir, fuse23 ? m_dir : m_tr, m_dir};
+        PbGeoLineParams gl;
+        if (fuse1) {
+            gl.geo = a->geo_dev;
+            for (int k = 0; k < 3; ++k) gl.gw[k] = a->dax[k].weights;
+            gl.G1 = (int)G1; gl.G2 = (int)G2;
+            p.geo_line = &gl;
+            if (stiff) {
+                for (int t = 0; t < 6; ++t) { p.out[t] = X1 + t * s1; p.w_mode[t] = modes1[t]; }
+                rc = run_stage(PB_PLAN_S1F, a, 0, p, st, "s1f");
+            } else {
+                p.out[0] = X1; p.w_mode[0] = m_dir;
+                rc = run_stage(PB_PLAN_S1F_MASS, a, 0, p, st, "s1f_mass");
+            }
+        } else if (stiff && !a->fused_plans) {
             const int plan[6] = {PB_PLAN_ONE11, PB_PLAN_ONE10, PB_PLAN_ONE10, PB_PLAN_COPY, PB_PLAN_COPY, PB_PLAN_COPY};
             const int field[6] = {5, 4, 2, 3, 1, 0};                            // B22, B12, B02, B11, B01, B00
             const char* nm[6] = {"s1_one11", "s1_one10a", "s1_one10b", "s1_copya", "s1_copyb", "s1_copyc"};
@@ -1480,6 +1593,24 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             rc = run_stage(PB_PLAN_COPY, a, 0, p, st, "s1_copy");
         }
         if (rc) return rc;
+    }
+    if (fuse23) {
+        // stages 2 + 3 in one kernel: X1[t][mu0][g1][g2] -> out[mu0 - mu_lo][mu1][mu2]
+        PbS32Params q;
+        memset(&q, 0, sizeof q);
+        fill_s32_axes(a, q);
+        q.X1 = X1; q.x1_stride = (long long)s1; q.x1_mu_base = S.ext_lo;
+        q.mu0_begin = S.mu_lo; q.mu0_count = Mrows;
+        q.u_lo = S.ra; q.u_hi = S.rb;
+        q.symmetric = 1;
+        q.out = d_out; q.out_mu_base = S.mu_lo;
+        q.nbatch = pb_lane_batches(H2.n, H2.U.p);
+        mark_stage(a, stiff ? "s23" : "s23_mass", st);
+        ++g_launches;
+        int e = pb_find_s32(a->form, H1.U.p, H1.q)(&q, st);
+        if (e) return fail(PB200_ECUDA, "fused stage 2+3 launch failed: %s", pbErrorString((pbError)e));
+        mark_stage(a, "end", st);
+        return 0;
     }
     // stage 2: axis 1,  X1[t][mu0][g1][g2] -> X2[t][mu0][mu1][g2]
     {

@@ -183,7 +183,8 @@ template <int DIM, bool RAT> PB_HD void pb_point_normalize(PbPoint& pt) {
 template <int DIM> struct PbProgMass {
     static constexpr int NF = 1;
     static constexpr bool NEED_X = false;
-    template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) {
+    template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) { point<RAT>(pt, f); }
+    template <bool RAT> PB_HD static void point(PbPoint& pt, double* f) {
         const double d = pt.gw * fabs(pb_det<DIM>(pt.J));
         if constexpr (RAT) {
             const double r = 1.0 / pt.jden;
@@ -199,7 +200,8 @@ template <int DIM> struct PbProgMass {
 template <int DIM> struct PbProgStiffness {
     static constexpr int NF = DIM * (DIM + 1) / 2;
     static constexpr bool NEED_X = false;
-    template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) {
+    template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) { point<RAT>(pt, f); }
+    template <bool RAT> PB_HD static void point(PbPoint& pt, double* f) {
         // with J = N / jden:  W J^-1 J^-T = gw jden^(2-DIM) / |det N| * adj(N) adj(N)^T  -- one division
         double A[3][3];
         pb_adj<DIM>(pt.J, A);

@@ -34,7 +34,9 @@ enum PbPlanId {
     PB_PLAN_ONE11 = 7,  // one term, test and trial derivative on this axis
     PB_PLAN_ONE10 = 8,  // one term, test derivative on this axis
     PB_PLAN_PAIRT = 9,  // [0,0] + [1,0] -> one output
-    PB_PLAN_COUNT = 10,
+    PB_PLAN_S1F = 10,       // fused stage 1 of 3D stiffness: geometry + fields in registers -> all six X1 terms (walk_geo.cuh)
+    PB_PLAN_S1F_MASS = 11,  // fused stage 1 of 3D mass
+    PB_PLAN_COUNT = 12,
     PB_PLAN_LANE_BASE = 1000    // + plan id: the lane-per-span variant (second argument = lines per warp)
 };
 
@@ -42,24 +44,28 @@ struct PbPlanCopy {
     static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
     static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int) { return PbOp{0, 0, 0, 0, 0}; }
 };
 struct PbPlanOne11 {
     static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
     static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int) { return PbOp{0, 0, 1, 1, 0}; }
 };
 struct PbPlanOne10 {
     static constexpr int NOPS = 1, NOUT = 1, MINB = 4, NPF = 4;
     static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int) { return PbOp{0, 0, 1, 0, 0}; }
 };
 struct PbPlanPairT {
     static constexpr int NOPS = 2, NOUT = 1, MINB = 4, NPF = 3;
     static constexpr int MINB4 = 4;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int i) {
         constexpr PbOp t[2] = {{0, 0, 0, 0, 0}, {1, 0, 1, 0, 0}};
         return t[i];
@@ -69,6 +75,7 @@ struct PbPlanFinal4 {
     static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 2;
     static constexpr int MINB4 = 3;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = true;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {1, 1, 1, 0, 0}, {2, 0, 1, 1, 0}};
         return t[i];
@@ -78,6 +85,7 @@ struct PbPlanGen4 {
     static constexpr int NOPS = 4, NOUT = 1, MINB = 3, NPF = 2;
     static constexpr int MINB4 = 3;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int i) {
         constexpr PbOp t[4] = {{0, 0, 0, 0, 0}, {1, 0, 0, 1, 0}, {2, 0, 1, 0, 0}, {3, 0, 1, 1, 0}};
         return t[i];
@@ -87,6 +95,7 @@ struct PbPlanS1A {
     static constexpr int NOPS = 3, NOUT = 3, MINB = 3, NPF = 3;
     static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 1, 0, 2}};
         return t[i];
@@ -96,6 +105,7 @@ struct PbPlanS1B {
     static constexpr int NOPS = 3, NOUT = 3, MINB = 3, NPF = 3;
     static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 0, 0, 1}, {2, 0, 0, 0, 2}};
         return t[i];
@@ -105,6 +115,7 @@ struct PbPlanS2B {
     static constexpr int NOPS = 3, NOUT = 2, MINB = 3, NPF = 3;
     static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 0, 0, 0}, {1, 0, 1, 0, 0}, {2, 0, 0, 0, 1}};
         return t[i];
@@ -114,10 +125,37 @@ struct PbPlanS1_2D {
     static constexpr int NOPS = 3, NOUT = 3, MINB = 2, NPF = 3;
     static constexpr int MINB4 = 2;   // resident blocks asked for when P >= 4 (bigger windows)
     static constexpr bool HAS_TR = false;
+    static constexpr bool sym(int) { return false; }
     static constexpr PbOp op(int i) {
         constexpr PbOp t[3] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 0, 0, 2}};
         return t[i];
     }
+};
+
+// Fused stage 1 (walk_geo.cuh): the inputs are not read but evaluated from the geometry; `field(i)`
+// is the index of op i's input in the output of the field program.  Outputs whose op has ft == fu
+// have a symmetric window (10 instead of 16 accumulators for p = 3).
+struct PbPlanS1F {
+    static constexpr int NOPS = 6, NOUT = 6, MINB = 2, NPF = 1;
+    static constexpr int MINB4 = 1;
+    static constexpr bool HAS_TR = false;
+    static constexpr PbOp op(int i) {
+        constexpr PbOp t[6] = {{0, 0, 1, 1, 0}, {1, 0, 1, 0, 1}, {2, 0, 1, 0, 2}, {3, 0, 0, 0, 3}, {4, 0, 0, 0, 4}, {5, 0, 0, 0, 5}};
+        return t[i];
+    }
+    static constexpr int field(int i) {     // B22, B12, B02, B11, B01, B00 of the symmetric-packed B
+        constexpr int f[6] = {5, 4, 2, 3, 1, 0};
+        return f[i];
+    }
+    static constexpr bool sym(int o) { return o == 0 || o >= 3; }
+};
+struct PbPlanS1FMass {
+    static constexpr int NOPS = 1, NOUT = 1, MINB = 3, NPF = 1;
+    static constexpr int MINB4 = 2;
+    static constexpr bool HAS_TR = false;
+    static constexpr PbOp op(int) { return PbOp{0, 0, 0, 0, 0}; }
+    static constexpr int field(int) { return 0; }
+    static constexpr bool sym(int) { return true; }
 };
 
 // launcher registry (filled by the per-(P,Q) translation units and by JIT-compiled form modules)

@@ -33,7 +33,7 @@ struct PbOp {       // acc[out] += D_ft (x) D_fu * in
 
 #define PB_WALK_MAXOPS 8
 #define PB_WALK_MAXSPLIT 4
-#define PB_WALK_MAXOUT 4
+#define PB_WALK_MAXOUT 6
 
 struct PbWalkParams {
     // ---- thread grid: tid -> (u, v, x),  x fastest -------------------------------------------
@@ -78,6 +78,8 @@ struct PbWalkParams {
     int sp_s_begin[PB_WALK_MAXSPLIT], sp_s_end[PB_WALK_MAXSPLIT];
     int sp_w_lo[PB_WALK_MAXSPLIT], sp_w_hi[PB_WALK_MAXSPLIT];
     int sp_f_lo[PB_WALK_MAXSPLIT], sp_f_hi[PB_WALK_MAXSPLIT];
+    // ---- fused stage 1 (walk_geo.cuh): host pointer to the PbGeoLineParams of the launch ---------
+    const void* geo_line;
 };
 
 PB_HD bool pb_keep(int mode, int i, int j, int lo, int hi) {
@@ -148,6 +150,7 @@ template <class Plan> constexpr bool pb_group_by_fu(int out) {
 template <class Plan, int Q>
 struct PbRegLoader {
     static constexpr int NOPS = Plan::NOPS;
+    static constexpr bool ROLLED = false;
     const double* src[NOPS];
     bool has[NOPS];
     long long sc;
@@ -330,7 +333,9 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                     const long long boff = (long long)(band - mu_base) * (long long)smu;
                     pb_static_for<0, NOUT>([&](auto O) {
                         constexpr int o = decltype(O)::value;
-                        if (mask & (1 << o)) outp[o][boff] = acc[o][(a + R) % P1][(b + R) % P1];
+                        // outputs with a symmetric window keep only the labels lo <= hi (see node())
+                        const int la = (a + R) % P1, lb = (b + R) % P1;
+                        if (mask & (1 << o)) outp[o][boff] = Plan::sym(o) ? acc[o][la < lb ? la : lb][la < lb ? lb : la] : acc[o][la][lb];
                     });
                 }
             }
@@ -371,8 +376,13 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                         for (int a = 0; a < P1; ++a)
 #pragma unroll
                             for (int b = 0; b < P1; ++b) {
+                                // Outputs whose ops all have ft == fu have a symmetric window
+                                // (acc[a][b] == acc[b][a]): only a <= b is accumulated, under the
+                                // ordered pair of rotated labels, and the retire reads it from there.
+                                if (Plan::sym(o) && a > b) continue;
                                 const double l = by_fu ? y[a] : D[fl][a], r = by_fu ? D[fl][b] : y[b];
-                                double& dst = acc[o][(a + R) % P1][(b + R) % P1];
+                                const int la = (a + R) % P1, lb = (b + R) % P1;
+                                double& dst = Plan::sym(o) ? acc[o][la < lb ? la : lb][la < lb ? lb : la] : acc[o][la][lb];
                                 if (assign_new && (a == P || b == P)) dst = l * r;
                                 else dst = fma(l, r, dst);
                             }
@@ -381,6 +391,157 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
             });
         };
         int s = rg.s_begin;
+        if constexpr (Loader::ROLLED) {
+            // Compact variant for loaders that stage the inputs of a span themselves (fused stage 1,
+            // walk_geo.cuh): the node loop is NOT unrolled — the loader hands out the input of
+            // (node, op) on request — and the row / column entering the window is cleared instead of
+            // being assigned by its first contribution, so that all nodes run the same code.  The
+            // unrolled body exceeds the instruction caches there (ncu: 21 % no_instructions stalls).
+            auto node_rolled = [&](auto RC, int gq, int sp) {
+                constexpr int R = decltype(RC)::value;
+                const double* Vn = Vt + (long long)(sp * Q + gq) * (2 * P1);
+                double D[2][P1];
+#pragma unroll
+                for (int a = 0; a < P1; ++a) { D[0][a] = Vn[a]; D[1][a] = Vn[P1 + a]; }
+                pb_static_for<0, NOUT>([&](auto O) {
+                    constexpr int o = decltype(O)::value;
+                    constexpr bool by_fu = pb_group_by_fu<Plan>(o);
+                    pb_static_for<0, 2>([&](auto FL) {
+                        constexpr int fl = decltype(FL)::value;
+                        constexpr int cnt = by_fu ? pb_count_fu<Plan>(o, fl) : pb_count_ft<Plan>(o, fl);
+                        if constexpr (cnt > 0) {
+                            double y[P1];
+                            constexpr int lead = pb_first_in_group<Plan>(o, fl, by_fu);
+                            pb_static_for<0, NOPS>([&](auto I) {
+                                constexpr int i = decltype(I)::value;
+                                constexpr PbOp op = Plan::op(i);
+                                if constexpr (op.out == o && (by_fu ? op.fu : op.ft) == fl) {
+                                    constexpr int other = by_fu ? op.ft : op.fu;
+                                    const double xv = ld.template get<i>(gq);
+                                    if constexpr (i == lead) {
+#pragma unroll
+                                        for (int c = 0; c < P1; ++c) y[c] = D[other][c] * xv;
+                                    } else {
+#pragma unroll
+                                        for (int c = 0; c < P1; ++c) y[c] = fma(D[other][c], xv, y[c]);
+                                    }
+                                }
+                            });
+#pragma unroll
+                            for (int a = 0; a < P1; ++a)
+#pragma unroll
+                                for (int b = 0; b < P1; ++b) {
+                                    if (Plan::sym(o) && a > b) continue;
+                                    const double l = by_fu ? y[a] : D[fl][a], r = by_fu ? D[fl][b] : y[b];
+                                    const int la = (a + R) % P1, lb = (b + R) % P1;
+                                    double& dst = Plan::sym(o) ? acc[o][la < lb ? la : lb][la < lb ? lb : la] : acc[o][la][lb];
+                                    dst = fma(l, r, dst);
+                                }
+                        }
+                    });
+                });
+            };
+            auto clear_entering = [&](auto RC) {        // row P and column P of the window in phase R
+                constexpr int R = decltype(RC)::value;
+                pb_static_for<0, NOUT>([&](auto O) {
+                    constexpr int o = decltype(O)::value;
+#pragma unroll
+                    for (int a = 0; a < P1; ++a) {
+                        const int la = (a + R) % P1, lp = (P + R) % P1;
+                        acc[o][la < lp ? la : lp][la < lp ? lp : la] = 0.0;
+                        if (!Plan::sym(o)) acc[o][la < lp ? lp : la][la < lp ? la : lp] = 0.0;
+                    }
+                });
+            };
+            // finished pairs go through the loader's staging column (thread-private shared memory):
+            // the phase-specific code only copies registers there, one rolled loop stores them
+            // (in two halves — row 0, then column 0 — to keep the staging column short)
+            auto stage_rot = [&](auto RC, auto HALF) {  // RC: phase in which the leaving function is row/column 0
+                constexpr int R = decltype(RC)::value;
+                constexpr int k0 = decltype(HALF)::value == 0 ? 0 : P + 1, k1 = decltype(HALF)::value == 0 ? P + 1 : 2 * P + 1;
+#pragma unroll
+                for (int k = k0; k < k1; ++k) {
+                    const int a = (k <= P) ? 0 : (k - P);
+                    const int b = (k <= P) ? k : 0;
+                    const int la = (a + R) % P1, lb = (b + R) % P1;
+                    pb_static_for<0, NOUT>([&](auto O) {
+                        constexpr int o = decltype(O)::value;
+                        ld.stage_put((k - k0) * NOUT + o, Plan::sym(o) ? acc[o][la < lb ? la : lb][la < lb ? lb : la] : acc[o][la][lb]);
+                    });
+                }
+            };
+            auto store_staged = [&](int fr, int k0, int k1) {
+                const int* rm = tb.ret_mu + (long long)fr * (2 * P + 1);
+                // unrolled (P+1 entries at most): the table look-ups and staged values of all entries
+                // are in flight together instead of one dependent chain per entry
+#pragma unroll
+                for (int k = k0; k < k0 + P + 1; ++k) {
+                    if (k >= k1) break;
+                    const int mu = rm[k];
+                    if (mu < 0) continue;
+                    int band = mu, mask = 0;
+                    if constexpr (ENC) {
+                        band = mu & 0xFFFFFF;
+                        mask = mu >> 24;
+                    } else {
+                        const int a = (k <= P) ? 0 : (k - P), b = (k <= P) ? k : 0;
+                        pb_static_for<0, NOUT>([&](auto O) {
+                            constexpr int o = decltype(O)::value;
+                            mask |= pb_walk_keep(prm, rg, o, fr + a, fr + b) ? (1 << o) : 0;
+                        });
+                    }
+                    mask &= wantbits;
+                    const long long boff = (long long)(band - mu_base) * (long long)smu;
+                    pb_static_for<0, NOUT>([&](auto O) {
+                        constexpr int o = decltype(O)::value;
+                        if (mask & (1 << o)) outp[o][boff] = ld.stage_get((k - k0) * NOUT + o);
+                    });
+                }
+            };
+            int phase = 0;
+            for (; s < rg.s_end; ++s) {
+                if (s > rg.s_begin) {           // the function that left the span range
+                    pb_static_for<0, P1>([&](auto RC) {
+                        constexpr int R = decltype(RC)::value;
+                        if (phase == R) stage_rot(PbIC<(R + P) % P1>{}, PbIC<0>{});
+                    });
+                    store_staged(f, 0, P + 1);
+                    pb_static_for<0, P1>([&](auto RC) {
+                        constexpr int R = decltype(RC)::value;
+                        if (phase == R) { stage_rot(PbIC<(R + P) % P1>{}, PbIC<1>{}); clear_entering(RC); }
+                    });
+                    store_staged(f, P + 1, 2 * P + 1);
+                    ++f;
+                }
+                ld.begin_span(s);
+                pb_static_for<0, P1>([&](auto RC) {
+                    constexpr int R = decltype(RC)::value;
+                    if (phase == R) {
+#pragma unroll 1
+                        for (int gq = 0; gq < Q; ++gq) node_rolled(RC, gq, s);
+                    }
+                });
+                phase = (phase + 1 == P1) ? 0 : phase + 1;
+            }
+            // flush: the functions still in the window, starting in the phase of the last span
+            const int last_ph = (rg.s_end - rg.s_begin - 1) % P1;
+            for (int t = 0; t < P1; ++t) {
+                if (f < prm.N) {
+                    pb_static_for<0, P1>([&](auto PH) {
+                        constexpr int ph = decltype(PH)::value;
+                        if ((last_ph + t) % P1 == ph) stage_rot(PH, PbIC<0>{});
+                    });
+                    store_staged(f, 0, P + 1);
+                    pb_static_for<0, P1>([&](auto PH) {
+                        constexpr int ph = decltype(PH)::value;
+                        if ((last_ph + t) % P1 == ph) stage_rot(PH, PbIC<1>{});
+                    });
+                    store_staged(f, P + 1, 2 * P + 1);
+                }
+                ++f;
+            }
+            return;
+        } else {
         while (s < rg.s_end) {
             pb_static_for<0, P1>([&](auto RC) {
                 constexpr int R = decltype(RC)::value;
@@ -395,6 +556,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                     ++s;
                 }
             });
+        }
         }
         // flush: the functions still in the window, starting in the phase of the last span
         const int last_phase = (rg.s_end - rg.s_begin - 1) % P1;
@@ -521,6 +683,7 @@ template <int OFF> PB_D void pb_cp_async8_at(uint32_t smem, const void* gmem) {
 template <class Plan, int Q, int NST, int NTHR = 128>
 struct PbAsyncLoader {
     static constexpr int NOPS = Plan::NOPS;
+    static constexpr bool ROLLED = false;
     static constexpr int STAGE = Q * NOPS * NTHR;       // doubles per stage of the block ring
     const double* src[NOPS];
     bool has[NOPS];

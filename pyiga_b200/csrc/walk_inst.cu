@@ -1,9 +1,13 @@
 // Instantiates the walk kernels of the built-in plans for one (degree, nodes-per-span) pair.
 // Compiled once per pair with -DPB_P=<p> -DPB_Q=<q>; each object registers its launchers.
 #include <algorithm>
+#include <cstring>
+#include <vector>
 #include "backend.cuh"
 #include "plans.cuh"
 #include "walk1.cuh"
+#include "walk_geo.cuh"
+#include "fused23.cuh"
 
 #ifndef PB_P
 #error "compile with -DPB_P=<degree> -DPB_Q=<nodes per span>"
@@ -98,6 +102,86 @@ int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* strea
 #endif
 }
 
+// fused stage 1 (walk_geo.cuh): geometry and fields are evaluated by the walk itself
+template <class Plan, class Prog, int NC>
+int launch_geo_nc(const PbWalkParams* prm, const PbGeoLineParams& gp, int use_smem, void* stream) {
+#ifdef PB_EMULATE
+    (void)use_smem; (void)stream;
+    for (int y = 0; y < std::max(1, prm->nsplit); ++y)
+        pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_geo_line<Plan, PB_P, PB_Q, NC, Prog>(*prm, gp, tid, y); });
+    return 0;
+#else
+    auto kern = pb_walk_geo_kernel<Plan, PB_P, PB_Q, NC, Prog, (PB_P >= 4 ? Plan::MINB4 : Plan::MINB)>;
+    static unsigned long long configured = 0;       // bit d: done on device d
+    int devno = 0;
+    cudaGetDevice(&devno);
+    if (devno >= 64 || !((configured >> devno) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        if (devno < 64) configured |= 1ull << devno;
+    }
+    const int ny = std::max(1, prm->nsplit);
+    size_t smem = 0;
+    for (int y = 0; y < ny; ++y) {
+        size_t vb, ib, gb, zb;
+        pb_walk_geo_smem<PB_P, PB_Q>(pb_walk_range(*prm, y), gp.geo.pg[0], gp.geo.Ng[0] * NC * 3 + PbGeoLoader<Plan, PB_Q, NC, Prog>::stage_doubles(PB_P), vb, ib, gb, zb);
+        smem = std::max(smem, vb + ib + gb + zb);
+    }
+    if (use_smem < 0) {     // query: resident blocks per SM
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, smem);
+        return e == cudaSuccess ? nb : 0;
+    }
+    const long long blocks = (prm->nthreads + 127) / 128;
+    if (blocks <= 0) return 0;
+    if (prm->out_smu >= (1LL << 31)) return (int)cudaErrorInvalidValue;
+    dim3 grid((unsigned)blocks, (unsigned)ny);
+    kern<<<grid, 128, smem, (cudaStream_t)stream>>>(*prm, gp);
+    return (int)cudaGetLastError();
+#endif
+}
+
+template <class Plan, class Prog>
+int launch_geo(const PbWalkParams* prm, int use_smem, size_t, void* stream) {
+    const PbGeoLineParams* gp = static_cast<const PbGeoLineParams*>(prm->geo_line);
+    if (!gp || gp->geo.Ng[0] * gp->geo.nc * 3 > PB_GEO_ZMAX) return 1;      // cudaErrorInvalidValue
+    return gp->geo.nc == 4 ? launch_geo_nc<Plan, Prog, 4>(prm, *gp, use_smem, stream)
+                           : launch_geo_nc<Plan, Prog, 3>(prm, *gp, use_smem, stream);
+}
+
+// fused stages 2 + 3 (fused23.cuh); prm->out == nullptr: query, 0 if the configuration can be launched
+template <class Form>
+int launch_s32(const PbS32Params* prm, void* stream) {
+#ifdef PB_EMULATE
+    (void)stream;
+    if (!prm->out) return 0;
+    std::vector<double> T((size_t)prm->G1 * Form::NT * PbS32Cfg<PB_P>::TPAD);
+    for (int u = 0; u < prm->mu0_count; ++u)
+        for (int b = 0; b < prm->nbatch; ++b) {
+            std::fill(T.begin(), T.end(), 0.0);
+            pb_s32_seq<Form, PB_P, PB_Q>(*prm, prm->mu0_begin + u, b, T.data());
+        }
+    return 0;
+#else
+    const PbS32Smem<Form, PB_P, PB_Q> lay(prm->G1, prm->N1);
+    if (lay.total > 227 * 1024) return 1;
+    if (!prm->out) return 0;
+    auto kern = pb_s32_kernel<Form, PB_P, PB_Q>;
+    static unsigned long long configured = 0;       // bit d: done on device d
+    int devno = 0;
+    cudaGetDevice(&devno);
+    if (devno >= 64 || !((configured >> devno) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        if (devno < 64) configured |= 1ull << devno;
+    }
+    const long long blocks = (long long)prm->mu0_count * prm->nbatch;
+    if (blocks <= 0) return 0;
+    kern<<<(unsigned)blocks, (PB_Q * PbS32Split<Form>::NH + PbS32Cfg<PB_P>::NCW) * 32, lay.total, (cudaStream_t)stream>>>(*prm);
+    return (int)cudaGetLastError();
+#endif
+}
+
 int launch_walk1(const PbWalk1Params* prm, void* stream) {
 #ifdef PB_EMULATE
     (void)stream;
@@ -128,6 +212,12 @@ struct Registrar {
         pb200_register_walk(PB_PLAN_S1B, PB_P, PB_Q, &launch<PbPlanS1B>);
         pb200_register_walk(PB_PLAN_S2B, PB_P, PB_Q, &launch<PbPlanS2B>);
         pb200_register_walk(PB_PLAN_S1_2D, PB_P, PB_Q, &launch<PbPlanS1_2D>);
+#if PB_Q == PB_P + 1 && PB_P <= 3
+        pb200_register_s32(2 /* PB200_FORM_STIFFNESS */, PB_P, PB_Q, &launch_s32<PbS32Stiffness>);
+        pb200_register_s32(1 /* PB200_FORM_MASS */, PB_P, PB_Q, &launch_s32<PbS32Mass>);
+#endif
+        pb200_register_walk(PB_PLAN_S1F, PB_P, PB_Q, &launch_geo<PbPlanS1F, PbProgStiffness<3>>);
+        pb200_register_walk(PB_PLAN_S1F_MASS, PB_P, PB_Q, &launch_geo<PbPlanS1FMass, PbProgMass<3>>);
 #endif
     }
 };
