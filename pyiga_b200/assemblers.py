@@ -355,9 +355,15 @@ class _AssemblerProtocol:
         return M
 
     def assemble_csr(self, **kw):
-        """The whole matrix as ``scipy.sparse.csr_matrix`` (float64 data, int32 indices, sorted)."""
-        data = self.dev.assemble_mlb(**kw)
-        return self.dev.device_structure.to_csr(data)
+        """The whole matrix as ``scipy.sparse.csr_matrix`` (float64 data, int32 indices unless
+        nnz >= 2^31, sorted).  On the GPU the sum-factorised path delivers it chunk by chunk with the
+        device->host copies overlapped (:mod:`pyiga_b200._hostcsr`)."""
+        dev = self.dev
+        if not kw and dev.fast_path and dev.be.name == 'cuda' and dev.dim >= 2:
+            from ._hostcsr import assemble_csr_matrix
+            return assemble_csr_matrix(dev)
+        data = dev.assemble_mlb(**kw)
+        return dev.device_structure.to_csr(data)
 
 
 class _ScalarAssemblerBase(_AssemblerProtocol):

@@ -1105,6 +1105,7 @@ static bool fused_stage1(const pb200_assembler* a) {
     if (g.dim != 3 || g.sdim != 3 || g.Ng[0] * g.nc * 3 > PB_GEO_ZMAX) return false;
     const AxisHost& H = a->hax[0];
     const int P = H.U.p, Q = H.q;
+    if (P > 3) return false;        // the 6 x (p+1)^2 window of degree 4 does not fit the register file (ptxas: spills)
     if (!have_plan(a->form == PB200_FORM_STIFFNESS ? PB_PLAN_S1F : PB_PLAN_S1F_MASS, P, Q)) return false;
     // staged tables of the whole axis (slabs and pieces are shorter) next to the Z columns
     const size_t nodes = (size_t)H.G;

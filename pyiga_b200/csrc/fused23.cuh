@@ -200,8 +200,15 @@ PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, double* Trow /
 // (terms / input streams of "half" 0 and 1) so that a producer warp carries about as many FP64
 // instructions per span as a consumer warp — the block synchronises once per span and the slowest
 // warp sets the pace (ncu: with one warp per row the consumers waited 12 % of the time).
+// Measured on B200 (3D p=3 n=128 stiffness): one warp per row with the lane's basis values in
+// registers 4.9 ms; two warps per row with the values in shared memory (512 threads need <= 128
+// registers) 5.6 ms — the extra shared-memory reads (32 per term and row) cost more than the better
+// balance gains.  PB_S32_SPLIT selects the two-warp variant.
+#ifndef PB_S32_SPLIT
+#define PB_S32_SPLIT 0
+#endif
 template <class Form> struct PbS32Split {
-    static constexpr int NH = Form::NT > 1 ? 2 : 1;
+    static constexpr int NH = (PB_S32_SPLIT && Form::NT > 1) ? 2 : 1;
     static constexpr int NSTR = Form::NIN / NH;                 // input streams per half
     static constexpr int half_of_term(int t) { return (NH == 1 || t == 0) ? 0 : 1; }
 };
@@ -314,6 +321,15 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
         const int prow = warp / NH, half = warp % NH;
         double* ring = sRing + (size_t)warp * NST * STAGE;
         const double* sDl = sD + lane;
+#if !PB_S32_SPLIT
+        double Dreg[Q][2][P1];          // basis values of this lane's span
+#pragma unroll
+        for (int gq = 0; gq < Q; ++gq)
+#pragma unroll
+            for (int fl = 0; fl < 2; ++fl)
+#pragma unroll
+                for (int a = 0; a < P1; ++a) Dreg[gq][fl][a] = sDl[((gq * 2 + fl) * P1 + a) * 32];
+#endif
         // slot offsets of this lane's entries in a T row (-1: not a writer)
         int tpos[2 * P + 1];
 #pragma unroll
@@ -389,7 +405,11 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
                 }
             });
             double L[P1][P1];
+#if PB_S32_SPLIT
             pb_span_block_sd<TP, P, Q>(xt, sDl, L);
+#else
+            pb_span_block<TP, P, Q>(xt, Dreg, L);
+#endif
 #pragma unroll
             for (int kk = 0; kk <= 2 * P; ++kk) {
                 const int d = (kk <= P) ? kk : kk - P;

@@ -72,96 +72,26 @@ class SlabAssembly:
 
     def csr_sizes(self):
         """(local rows, local nnz, index dtype) of the CSR arrays of this slab"""
-        ra, rb = self.rows
-        nrows = (rb - ra) * int(np.prod(self.dev.ndofs_test[1:], dtype=np.int64))
-        nnz = self.local_nnz
+        from ._hostcsr import csr_sizes
+        nrows, nnz, _ = csr_sizes(self.dev, self.rows)
         return nrows, nnz, (np.int32 if nnz < 2 ** 31 else np.int64)
 
     def assemble_csr_host(self, host=None, nchunks=8, workspace=None, pattern='host', pattern_threads=None):
         """Assemble the local rows and deliver the CSR arrays (indptr, indices, data) in host memory,
         overlapping the device->host copy of one row chunk with the assembly of the next (CUDA
-        backend only).  `host` may hold three preallocated pinned torch tensors; returns them.
+        backend only; see :mod:`pyiga_b200._hostcsr`).  `host` may hold three preallocated pinned torch
+        tensors; returns them.
 
         The integer arrays are a closed form of the band tables: with ``pattern='host'`` (default)
         host threads write them straight into `host[0:2]` while the GPU computes and ships the values,
         so only 8 of the 12 B/nnz cross PCIe; ``pattern='device'`` produces and copies them from
         the GPU as well."""
-        import time
-        tm = self.last_timings = {}
-        t_start = time.perf_counter()
-        be, dev = self.dev.be, self.dev
-        torch = be.torch
-        nrows, nnz, idt = self.csr_sizes()
-        tdt = torch.int32 if idt == np.int32 else torch.int64
-        if host is None:
-            host = [torch.empty(nrows + 1, dtype=tdt, pin_memory=True), torch.empty(nnz, dtype=tdt, pin_memory=True),
-                    torch.empty(nnz, dtype=torch.float64, pin_memory=True)]
-        dev.compute_fields(self.geo, rows=self.rows)
-        ra, rb = self.rows
-        rs = dev.row_start0()
-        inner_b = int(np.prod(dev.nband[1:], dtype=np.int64))
-        inner_r = int(np.prod(dev.ndofs_test[1:], dtype=np.int64))
-        # chunks of rows balanced by band count
-        targets = np.linspace(rs[ra], rs[rb], max(1, min(nchunks, rb - ra)) + 1)
-        cuts = sorted(set(int(np.clip(np.searchsorted(rs, t), ra, rb)) for t in targets) | {ra, rb})
-        chunks = [(a, b) for a, b in zip(cuts, cuts[1:]) if b > a]
-        cmax_nnz = max(int(rs[b] - rs[a]) * inner_b for a, b in chunks)
-        cmax_rows = max((b - a) * inner_r for a, b in chunks)
-        if workspace is None:
-            workspace = be.empty(max(dev.workspace_bytes(c) for c in chunks), np.uint8)
-        mlb = be.empty(cmax_nnz)
-        stage = [(be.empty(cmax_rows + 1, idt), be.empty(cmax_nnz, idt), be.empty(cmax_nnz)) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=be.device)
-        main = torch.cuda.current_stream(be.device)
-        freed = [None, None]
-        row_off, nnz_off = 0, 0
-        worker = None
-        tm['setup_ms'] = 1e3 * (time.perf_counter() - t_start)
-        if pattern == 'host':
-            import threading
-            err = []
-
-            def fill():
-                try:
-                    dev.device_structure.csr_pattern_host(host[0], host[1], row0=(ra, rb), nthreads=pattern_threads)
-                except Exception as exc:        # surfaced after the join
-                    err.append(exc)
-            worker = threading.Thread(target=fill)
-            worker.start()
-        for k, (a, b) in enumerate(chunks):
-            cn = int(rs[b] - rs[a]) * inner_b
-            cr = (b - a) * inner_r
-            if freed[k % 2] is not None:
-                main.wait_event(freed[k % 2])           # the staging buffers are free again
-            dev.assemble_mlb(rows=(a, b), out=mlb, workspace=workspace)
-            if worker is not None:
-                vv = dev.device_structure.csr_values(mlb, row0=(a, b), out=stage[k % 2][2])
-            else:
-                ip, ix, vv = dev.device_structure.csr_arrays(mlb, row0=(a, b), out=stage[k % 2], idt=idt)
-                if nnz_off:
-                    ip += nnz_off
-            ready = torch.cuda.Event()
-            ready.record(main)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ready)
-                if worker is None:
-                    host[0][row_off:row_off + cr + 1].copy_(ip, non_blocking=True)
-                    host[1][nnz_off:nnz_off + cn].copy_(ix, non_blocking=True)
-                host[2][nnz_off:nnz_off + cn].copy_(vv, non_blocking=True)
-                freed[k % 2] = torch.cuda.Event()
-                freed[k % 2].record(copy_stream)
-            row_off += cr
-            nnz_off += cn
-        tm['enqueue_ms'] = 1e3 * (time.perf_counter() - t_start) - tm['setup_ms']
-        copy_stream.synchronize()
-        main.synchronize()
-        tm['device_done_ms'] = 1e3 * (time.perf_counter() - t_start)
-        if worker is not None:
-            worker.join()
-            if err:
-                raise err[0]
-        tm['total_ms'] = 1e3 * (time.perf_counter() - t_start)
-        return host
+        from ._hostcsr import assemble_csr_host
+        self.dev.compute_fields(self.geo, rows=self.rows)
+        self.last_timings = {}
+        tensors, _ = assemble_csr_host(self.dev, self.rows, host=host, nchunks=nchunks, workspace=workspace, pattern=pattern,
+                                       pattern_threads=pattern_threads, timings=self.last_timings)
+        return tensors
 
 
 # ---------------------------------------------------------------------------------------------
