@@ -286,6 +286,33 @@ PB200_API int pb200_band_structure(const double* h_knots_trial, int nknots_trial
                          const double* h_knots_test, int nknots_test, int p_test,
                          uint32_t* h_bidx, int* nband);
 
+/* ---- slab-distributed preconditioned CG (csrc/distcg.cuh) ------------------------------------------------
+ * Replaces scipy.sparse.linalg.cg(M, b, M=KroneckerOperator(*Minvs)) of pyiga/approx.py:82-96 with the operator
+ * of pyiga/mlmatrix_cy.pyx:295-325 and the preconditioner of pyiga/kronecker.py:15-34, for a matrix whose rows
+ * of the first tensor axis are sharded over the GPUs of one node.  All ranks of the solve share WINDOWS of
+ * device memory (CUDA IPC: peer loads / stores over NVLink); halo planes, dot products and the gathered
+ * preconditioner input travel through them inside the kernels — no NCCL call, no host in the iteration. */
+typedef struct pb200_comm pb200_comm;
+typedef struct pb200_cg pb200_cg;
+PB200_API int pb200_comm_create(int device, int rank, int world, size_t bytes, pb200_comm** out);
+PB200_API int pb200_comm_handle(pb200_comm* c, void* handle64);              /* 64 bytes, to be sent to the peers */
+PB200_API int pb200_comm_open_peers(pb200_comm* c, const void* handles);     /* world x 64 bytes in rank order */
+PB200_API int pb200_comm_destroy(pb200_comm* c);
+/* window size of a solver: cuts[world+1] = row slabs of the first axis, halo = planes the band reaches into a
+ * neighbouring slab (the degree for spline spaces) */
+PB200_API int pb200_cg_window_bytes(const pb200_mlstruct* S, int world, const int* cuts, int halo, size_t* bytes);
+/* d_mlb: value tensor of the local slab; d_Ainv[3]: dense row-major inverses of the Kronecker factors (device);
+ * comm: window with the peers opened (NULL with world == 1) */
+PB200_API int pb200_cg_create(const pb200_mlstruct* S, int rank, int world, const int* cuts, int halo,
+                              const double* d_mlb, const double* const* d_Ainv, pb200_comm* comm, pb200_cg** out);
+PB200_API int pb200_cg_destroy(pb200_cg* g);
+/* x0 = 0; stops when ||r|| <= rtol ||b||; the host looks at the device-side flag every check_every iterations
+ * (one CUDA graph launch per batch) */
+PB200_API int pb200_cg_solve(pb200_cg* g, const double* d_b_local, double* d_x_local, double rtol, int maxiter,
+                             int check_every, int* iters, double* relres, void* stream);
+/* y_local = A_slab p: the halo-exchanging matvec alone (ml_matvec_3d of pyiga/mlmatrix_cy.pyx:295-325) */
+PB200_API int pb200_cg_matvec(pb200_cg* g, const double* d_p_local, double* d_y_local, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,17 @@ SIGNATURES = {
     'pb200_basis_eval': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb200_probe_fp64': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    'pb200_comm_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    'pb200_comm_handle': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'pb200_comm_open_peers': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'pb200_comm_destroy': (C.c_int, [C.c_void_p]),
+    'pb200_cg_window_bytes': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_size_t)]),
+    'pb200_cg_create': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p,
+                                  C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_void_p)]),
+    'pb200_cg_destroy': (C.c_int, [C.c_void_p]),
+    'pb200_cg_solve': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                 C.POINTER(C.c_double), C.c_void_p]),
+    'pb200_cg_matvec': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb200_band_structure': (C.c_int, [c_double_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int,
                                        C.c_void_p, C.POINTER(C.c_int)]),
 }

@@ -2157,3 +2157,5 @@ extern "C" int pb200_probe_fp64(int device, int iters, double* gflops) {
     return 0;
 #endif
 }
+
+#include "distcg_api.inl"

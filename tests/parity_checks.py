@@ -945,3 +945,55 @@ def check_large_full(name):
     ij = z['ij'].astype(np.int64)
     got = np.asarray(A[ij[:, 0], ij[:, 1]]).ravel()
     assert np.abs(got - z['val']).max() <= RTOL * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# native slab-distributed CG (csrc/distcg.cuh): halo, dot products and the preconditioner's gather
+# through peer-mapped windows
+# ---------------------------------------------------------------------------------------------
+def check_native_distributed_cg(world=1, rank=0, p=2, n=(7, 4, 5), rtol=1e-11):
+    """mass matrix on the rational twisted box, b = M x*, Kronecker preconditioner of the inverse 1D
+    mass matrices (pyiga/approx.py:82-93): the distributed matvec equals the slab of M p, the solve
+    recovers x* and runs as many iterations as scipy's cg on the assembled matrix (+-1)."""
+    import scipy.sparse.linalg
+    from pyiga_b200 import assemble, assemblers, bspline, geometry
+    from pyiga_b200.dist import partition_rows
+    from pyiga_b200.distcg import DistributedCG
+    kvs = tuple(bspline.make_knots(p, 0.0, 1.0, nk) for nk in n)
+    geo = geometry.twisted_nurbs_box()
+    asm = assemblers.MassAssembler3D(kvs, geo)
+    dev = asm.dev
+    be = dev.be
+    slabs = partition_rows(dev, world)
+    assert len(slabs) == world
+    rows = slabs[rank]
+    mlb = dev.assemble_mlb(rows=rows)
+    Ainv = [np.linalg.inv(assemble.bsp_mass_1d(kv).toarray()) for kv in kvs]
+    cg = DistributedCG(dev.device_structure, mlb, slabs, rank, Ainv)
+    # reference on the host: the whole matrix (every rank assembles it; small)
+    A = asm.assemble_csr()
+    N = A.shape[0]
+    plane = kvs[1].numdofs * kvs[2].numdofs
+    lo, hi = rows[0] * plane, rows[1] * plane
+    rng = np.random.default_rng(5)
+    pvec = rng.standard_normal(N)
+    y = be.to_host(cg.matvec(be.from_host(pvec[lo:hi])))
+    want = (A @ pvec)[lo:hi]
+    assert np.abs(y - want).max() <= 1e-13 * np.abs(want).max(), 'distributed matvec'
+    xstar = np.cos(0.3 * np.arange(N))
+    b = A @ xstar
+    x, its, res = cg.solve(be.from_host(b[lo:hi]), rtol=rtol, maxiter=300, check_every=7)
+    x = be.to_host(x)
+    assert res <= rtol
+    assert np.abs(x - xstar[lo:hi]).max() <= 1e-7 * np.abs(xstar).max(), np.abs(x - xstar[lo:hi]).max()
+    # scipy's cg with the same preconditioner
+    Minv = scipy.sparse.linalg.LinearOperator((N, N), matvec=lambda v: np.einsum(
+        'ia,jb,kc,abc->ijk', Ainv[0], Ainv[1], Ainv[2], v.reshape([kv.numdofs for kv in kvs])).ravel())
+    count = [0]
+    xs, info = scipy.sparse.linalg.cg(A, b, rtol=rtol, atol=0.0, maxiter=300, M=Minv, callback=lambda _: count.__setitem__(0, count[0] + 1))
+    assert info == 0 and abs(count[0] - its) <= 1, (count[0], its)
+    # a second solve on the same object (stamps keep increasing)
+    x2, its2, _ = cg.solve(be.from_host(2.0 * b[lo:hi]), rtol=rtol, maxiter=300, check_every=3)
+    assert its2 == its and np.abs(be.to_host(x2) - 2.0 * xstar[lo:hi]).max() <= 2e-7 * np.abs(xstar).max()
+    cg.close()
+    return its

@@ -104,3 +104,40 @@ def test_halo_matvec_and_cg(emu_lib, world):
         assert p.exitcode == 0
     its = dict(q.get(timeout=10) for _ in range(world))
     assert len(set(its.values())) == 1      # every rank ran the same number of iterations
+
+
+def test_native_cg_single_rank(emu):
+    import parity_checks as pc
+    pc.check_native_distributed_cg()
+
+
+def _worker_native_cg(rank, world, port, libpath, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from emu.emu_backend import EmuBackend
+        from pyiga_b200 import _device
+        import parity_checks as pc
+        _device._backend = EmuBackend(libpath)
+        q.put((rank, pc.check_native_distributed_cg(world=world, rank=rank)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_native_cg_peer_windows(emu_lib, world):
+    """the device-resident distributed CG with its windows in POSIX shared memory (the emulation build's
+    stand-in for CUDA IPC): halo pushes, flag waits, rank-ordered all-reduce, gathered preconditioner"""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33000 + (os.getpid() + world) % 2000
+    procs = [ctx.Process(target=_worker_native_cg, args=(r, world, port, emu_lib, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    its = dict(q.get(timeout=10) for _ in range(world))
+    assert len(set(its.values())) == 1

@@ -262,3 +262,9 @@ def test_large_full_matrix_checks(cuda, name):
 def test_large_convdiff_vs_reference(cuda):
     """config 5's form at p=3 n=96 against the reference's JIT-compiled assembler"""
     pc.check_large('convdiff_p3_n96', 1)
+
+
+def test_native_cg_single_gpu(cuda):
+    """device-resident CG (CUDA graph batches, device-side convergence flag) on one GPU; the multi-GPU
+    path of the same code runs in tests/test_dist_cpu.py (shared-memory windows) and tools/dist_cg_bench.py"""
+    pc.check_native_distributed_cg(p=3, n=(9, 6, 7))
