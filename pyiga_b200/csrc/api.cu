@@ -2158,4 +2158,4 @@ extern "C" int pb200_probe_fp64(int device, int iters, double* gflops) {
 #endif
 }
 
-#include "distcg_api.inl"
+#include "distcg_api.cuh"

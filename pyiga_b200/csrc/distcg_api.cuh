@@ -113,7 +113,8 @@ struct pb200_cg {
     cudaGraphExec_t graph = nullptr;
     int graph_iters = 0;
     const double* graph_x = nullptr;
-    cudaStream_t graph_stream = nullptr;
+    cudaStream_t own_stream = nullptr;      // the solve runs on a stream of its own (the caller's may be the legacy
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;     // default stream, which cannot be captured), ordered by events
 #endif
 };
 
@@ -209,6 +210,9 @@ extern "C" int pb200_cg_destroy(pb200_cg* g) {
     if (!g) return 0;
 #ifndef PB_EMULATE
     if (g->graph) cudaGraphExecDestroy(g->graph);
+    if (g->own_stream) cudaStreamDestroy(g->own_stream);
+    if (g->ev_in) cudaEventDestroy(g->ev_in);
+    if (g->ev_out) cudaEventDestroy(g->ev_out);
 #endif
     if (g->mem) pbFree(g->mem);
     if (g->own_comm) pb200_comm_destroy(g->comm);
@@ -337,6 +341,15 @@ extern "C" int pb200_cg_solve(pb200_cg* g, const double* d_b, double* d_x, doubl
     return 0;
 #else
     CK(pbSetDevice(g->comm->device));
+    if (!g->own_stream) {
+        CK(cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g->ev_out, cudaEventDisableTiming));
+    }
+    cudaStream_t caller = st;
+    CK(cudaEventRecord(g->ev_in, caller));
+    st = g->own_stream;
+    CK(cudaStreamWaitEvent(st, g->ev_in, 0));
     // control words: done = 0, iterations = 0, tolerance; the epoch advances by one (fresh stamps)
     long long h_ctl[2] = {0, 0};
     CK(cudaMemcpyAsync(d.ctl, h_ctl, sizeof h_ctl, cudaMemcpyHostToDevice, st));
@@ -352,7 +365,7 @@ extern "C" int pb200_cg_solve(pb200_cg* g, const double* d_b, double* d_x, doubl
     CK(pbLastError());
     // a batch of `check_every` iterations as one graph (re-captured when the batch size or x changes)
     const double*& graph_x = g->graph_x;
-    if (!g->graph || g->graph_iters != check_every || g->graph_stream != st || graph_x != d_x) {
+    if (!g->graph || g->graph_iters != check_every || graph_x != d_x) {
         if (g->graph) { cudaGraphExecDestroy(g->graph); g->graph = nullptr; }
         cudaGraph_t gr = nullptr;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -360,7 +373,7 @@ extern "C" int pb200_cg_solve(pb200_cg* g, const double* d_b, double* d_x, doubl
         CK(cudaStreamEndCapture(st, &gr));
         CK(cudaGraphInstantiate(&g->graph, gr, 0));
         cudaGraphDestroy(gr);
-        g->graph_iters = check_every; g->graph_stream = st; graph_x = d_x;
+        g->graph_iters = check_every; graph_x = d_x;
     }
     long long h[2] = {0, 0};
     double h_s[6];
@@ -373,6 +386,8 @@ extern "C" int pb200_cg_solve(pb200_cg* g, const double* d_b, double* d_x, doubl
     CK(cudaMemcpyAsync(h, d.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_s, d.scal, sizeof h_s, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(g->ev_out, st));
+    CK(cudaStreamWaitEvent(caller, g->ev_out, 0));
     if (iters) *iters = (int)h[1];
     if (relres) *relres = h_s[5] > 0 ? std::sqrt(h_s[4] / h_s[5]) : 0.0;
     return 0;
@@ -405,9 +420,7 @@ extern "C" int pb200_cg_matvec(pb200_cg* g, const double* d_p, double* d_y, void
     }
 #else
     CK(pbSetDevice(g->comm->device));
-    long long zero = 0;
-    CK(cudaMemcpyAsync(d.ctl, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaMemsetAsync(d.ctl, 0, sizeof(long long), st));       // done = 0
     pb_cg_bump_epoch_kernel<<<1, 1, 0, st>>>(d);
     pb_cg_direction_kernel<<<g->nblocks, 256, 0, st>>>(d, 1);
     pb_cg_matvec_kernel<<<g->nblocks, 256, 0, st>>>(d, g->mp, g->nb_lo, g->nb_hi);

@@ -1,7 +1,7 @@
 """Device-resident distributed CG (pyiga_b200.distcg) on the geometry mass matrix, Kronecker
 preconditioner of the inverse 1D mass matrices as in pyiga/approx.py:82-93.  Run with python (1 GPU)
 or torchrun (N GPUs of one node):
-    python tools/dist_cg_bench.py [--p 3 --n 128 --geo nurbs|bspline]
+    python tools/dist_cg_bench.py [--degree 3 --spans 128 --geo nurbs|bspline]
 Prints one JSON line: local matvec bandwidth (halo exchange through peer windows), CG time and
 iterations, error against the known solution."""
 import argparse
@@ -18,8 +18,8 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--p', type=int, default=3)
-    ap.add_argument('--n', type=int, default=128)
+    ap.add_argument('--degree', dest='p', type=int, default=3)
+    ap.add_argument('--spans', dest='n', type=int, default=128)
     ap.add_argument('--geo', default='nurbs')
     ap.add_argument('--check-every', type=int, default=10)
     a = ap.parse_args()
