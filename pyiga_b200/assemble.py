@@ -468,9 +468,9 @@ def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatab
     if isinstance(problem, str):
         from . import vform
         problem = vform.parse_vf(problem, kvs, args=args, bfuns=bfuns, boundary=bool(boundary), updatable=updatable)
-    from . import vform as _vf
+    from . import refvform, vform as _vf
     num_spaces = 1
-    if isinstance(problem, _vf.VForm):
+    if isinstance(problem, _vf.VForm) or refvform.is_reference_vform(problem):
         num_spaces = problem.num_spaces()
         problem = _vf.compile_vform(problem)
     if isinstance(problem, type):

@@ -346,6 +346,34 @@ class _AssemblerProtocol:
     def assemble_vector(self):
         return None     # arity 2
 
+    def entry_func_ptr(self):
+        """PyCapsule named ``"entryfunc"`` holding a C function ``double (*)(size_t i, size_t j, void* self)``
+        (``pyiga/genericasm.pxi:780-786``, consumed by the low-rank assembler
+        ``pyiga/fast_assemble_cy.pyx:99-113``, which passes the assembler object itself as `self`).
+        A per-entry callback cannot be served from the GPU entry by entry, so the first call assembles
+        the matrix once on the device; the callback then reads the host CSR copy."""
+        import ctypes as C_
+        if getattr(self, '_entry_capsule', None) is None:
+            A = self._entry_matrix()
+            indptr, indices, data = A.indptr, A.indices, A.data
+
+            def lookup(i, j, _self):
+                a, b = indptr[i], indptr[i + 1]
+                k = a + np.searchsorted(indices[a:b], j)
+                return float(data[k]) if k < b and indices[k] == j else 0.0
+            proto = C_.CFUNCTYPE(C_.c_double, C_.c_size_t, C_.c_size_t, C_.c_void_p)
+            self._entry_cfunc = proto(lookup)          # keeps the trampoline alive
+            new = C_.pythonapi.PyCapsule_New
+            new.restype, new.argtypes = C_.py_object, [C_.c_void_p, C_.c_char_p, C_.c_void_p]
+            self._entry_capsule_name = b'entryfunc'
+            self._entry_capsule = new(C_.cast(self._entry_cfunc, C_.c_void_p), self._entry_capsule_name, None)
+        return self._entry_capsule
+
+    def _entry_matrix(self):
+        A = self.assemble_csr()
+        A.sort_indices()
+        return A
+
     # ---- fast path ---------------------------------------------------------------------------
     def assemble_mlb(self, **kw):
         """The whole matrix as an :class:`~pyiga_b200.mlmatrix.MLMatrix` whose values stay on the device."""

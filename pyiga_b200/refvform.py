@@ -1,0 +1,335 @@
+"""CUDA backend for the reference's ``VForm`` objects (``pyiga.vform.VForm``).
+
+The reference compiles a variational form in two steps: ``VForm.finalize()`` rewrites the expression
+tree into scalar expressions over *parametric* derivatives of the basis functions and named
+variables (``pyiga/vform.py:705-731``), and ``AsmGenerator`` prints them as Cython source
+(``pyiga/codegen/cython.py:748-805``).  This module consumes the same finalized object (SURVEY.md
+Appendix A) and replaces the second step: every output expression is bilinear (arity 2) or linear
+(arity 1) in the basis function slots ``PartialDerivExpr(u|v, D)``, so evaluating it with symbolic
+slots yields the coefficient ``C[slot_v][slot_u](q)`` of every slot pair at every Gauss point —
+exactly what the generated ``precompute_fields`` + ``combine`` evaluate entry by entry.  The
+coefficient arrays become the field buffer of a ``PB200_FORM_CUSTOM`` device assembler and the matrix
+comes from the sum-factorised pipeline.
+
+Nothing from ``pyiga`` is imported: the nodes are recognised by class name and attributes, so any
+object with the reference's structure is accepted.  Supported: volume integrals over one space,
+derivatives up to first order, scalar and vector-valued basis functions, parametric and physical
+input fields, parameters, ``on_demand`` bounding boxes (``pyiga/codegen/cython.py:421-426,541-559``).
+Input functions are evaluated on the host exactly like the generated ``__init__`` does
+(``pyiga/codegen/cython.py:465-484``, ``pyiga/utils.py:33-52``).
+"""
+import numpy as np
+
+from . import _device, _lib
+from .assemblers import DeviceAssembler, GenericFormAssembler, _AssemblerProtocol
+from .mlmatrix import MLMatrix
+from .quadrature import make_tensor_quadrature
+
+
+def is_reference_vform(obj):
+    return type(obj).__name__ == 'VForm' and hasattr(obj, 'finalize') and hasattr(obj, 'predefined_vars')
+
+
+# ---------------------------------------------------------------------------------------------
+# values that are (bi)linear in the basis function slots
+# ---------------------------------------------------------------------------------------------
+class _Lin:
+    """{(v slot, u slot): coefficient}; a slot is None or (component, D) with D the parametric
+    derivative orders in x, y, z order; a coefficient is a float or an array on the Gauss grid."""
+    __slots__ = ('t',)
+
+    def __init__(self, t):
+        self.t = t
+
+    @staticmethod
+    def const(c):
+        return _Lin({(None, None): c})
+
+    def is_coef(self):
+        return all(k == (None, None) for k in self.t)
+
+    def coef(self):
+        return self.t.get((None, None), 0.0)
+
+    def __add__(self, o):
+        out = dict(self.t)
+        for k, c in o.t.items():
+            out[k] = out[k] + c if k in out else c
+        return _Lin(out)
+
+    def __neg__(self):
+        return _Lin({k: -c for k, c in self.t.items()})
+
+    def __sub__(self, o):
+        return self + (-o)
+
+    def __mul__(self, o):
+        out = {}
+        for (v1, u1), c1 in self.t.items():
+            for (v2, u2), c2 in o.t.items():
+                if (v1 is not None and v2 is not None) or (u1 is not None and u2 is not None):
+                    raise ValueError('expression is not linear in each basis function')
+                k = (v1 if v1 is not None else v2, u1 if u1 is not None else u2)
+                c = c1 * c2
+                out[k] = out[k] + c if k in out else c
+        return _Lin(out)
+
+    def __truediv__(self, o):
+        if not o.is_coef():
+            raise ValueError('division by an expression that contains basis functions')
+        return self * _Lin.const(1.0 / o.coef())
+
+
+_FUNCS = {'abs': np.abs, 'sqrt': np.sqrt, 'exp': np.exp, 'log': np.log, 'sin': np.sin, 'cos': np.cos, 'tan': np.tan}
+
+
+class _Interpreter:
+    """Evaluates the scalar expressions of a finalized VForm on a tensor Gauss grid."""
+
+    def __init__(self, vf, gaussgrid, gaussweights, args, geo):
+        self.vf, self.grid, self.gw, self.args, self.geo = vf, gaussgrid, gaussweights, args, geo
+        self.shape = tuple(len(g) for g in gaussgrid)
+        self.dim = len(gaussgrid)
+        self._vars = {}
+        self._memo = {}
+
+    # ---- variables ---------------------------------------------------------------------------
+    def var_entry(self, var, I):
+        key = (id(var), tuple(I))
+        if key in self._vars:
+            return self._vars[key]
+        if var.expr is not None:
+            e = var.expr
+            if len(I) == 2 and getattr(var, 'symmetric', False) and I[0] > I[1]:
+                I = (I[1], I[0])
+            sub = e if len(I) == 0 else (e[I[0]] if len(I) == 1 else e[I[0], I[1]])
+            val = self.eval(sub)
+        else:
+            val = _Lin.const(self._source_entry(var, I))
+        self._vars[key] = val
+        return val
+
+    def _source_array(self, var):
+        key = ('src', id(var))
+        if key in self._vars:
+            return self._vars[key]
+        src = var.src
+        kind = type(src).__name__
+        if kind == 'Parameter':
+            arr = np.asarray(self.args[src.name], dtype=float)
+        elif kind == 'InputField':
+            f = self.args[src.name]
+            deriv = var.deriv or 0
+            if deriv == 0:
+                arr = self._grid_eval(f, src.physical)
+            elif deriv == 1:
+                assert not src.physical, 'Jacobian of physical input field not implemented'
+                arr = np.asarray(f.grid_jacobian(self.grid), dtype=float)
+            else:
+                raise NotImplementedError('second derivatives of input fields')
+            arr = np.asarray(arr, dtype=float)
+        else:
+            raise TypeError('invalid source %r of variable %s' % (src, var.name))
+        self._vars[key] = arr
+        return arr
+
+    def _grid_eval(self, f, physical):
+        """``grid_eval`` / ``grid_eval_transformed`` of pyiga/utils.py:33-52"""
+        if hasattr(f, 'grid_eval') and not physical:
+            return f.grid_eval(self.grid)
+        if physical:
+            X = np.asarray(self.geo.grid_eval(self.grid), dtype=float)
+            pts = tuple(X[..., i] for i in range(X.shape[-1]))
+        else:
+            pts = list(np.meshgrid(*self.grid, sparse=True, indexing='ij'))
+            pts.reverse()
+        vals = f(*pts)
+        if isinstance(vals, tuple):     # vector-valued function given as a tuple of components
+            vals = np.stack([np.broadcast_to(np.asarray(v, dtype=float), self.shape) for v in vals], axis=-1)
+        vals = np.asarray(vals, dtype=float)
+        target = self.shape + vals.shape[self.dim:]     # functions that ignore an argument return smaller arrays
+        return vals if vals.shape == target else np.broadcast_to(vals, target)
+
+    def _source_entry(self, var, I):
+        arr = self._source_array(var)
+        if type(var.src).__name__ == 'Parameter':
+            return float(arr[tuple(I)]) if len(I) else float(arr)
+        return arr[(Ellipsis,) + tuple(I)] if len(I) else arr
+
+    # ---- expressions -------------------------------------------------------------------------
+    def eval(self, e):
+        k = id(e)
+        if k in self._memo:
+            return self._memo[k]
+        r = self._eval(e)
+        self._memo[k] = r
+        return r
+
+    def _eval(self, e):
+        kind = type(e).__name__
+        if kind == 'ConstExpr':
+            return _Lin.const(float(e.value))
+        if kind == 'VarRefExpr':
+            assert sum(e.D) == 0, 'derivatives of variables must be resolved by finalize()'
+            return self.var_entry(e.var, e.I)
+        if kind == 'NegExpr':
+            return -self.eval(e.x)
+        if kind == 'BuiltinFuncExpr':
+            v = self.eval(e.x)
+            if not v.is_coef():
+                raise ValueError('functions can only be applied to coefficient expressions')
+            return _Lin.const(_FUNCS[e.funcname](v.coef()))
+        if kind == 'ScalarOperExpr':
+            vals = [self.eval(c) for c in e.children]
+            r = vals[0]
+            for v in vals[1:]:
+                r = {'+': r.__add__, '-': r.__sub__, '*': r.__mul__, '/': r.__truediv__}[e.oper](v)
+            return r
+        if kind == 'PartialDerivExpr':
+            assert not e.physical, 'physical derivatives must be resolved by finalize()'
+            bf = e.basisfun
+            slot = (bf.component or 0, tuple(int(d) for d in e.D))
+            if max(slot[1]) > 1 or sum(slot[1]) > 1:
+                raise NotImplementedError('derivatives of order > 1 of the basis functions')
+            # linear forms name their only (test) function 'u' (pyiga/vform.py: names[:arity])
+            is_test = bf.name == 'v' or self.vf.arity == 1
+            return _Lin({(slot, None): 1.0}) if is_test else _Lin({(None, slot): 1.0})
+        if kind == 'GaussWeightExpr':
+            shp = [1] * self.dim
+            shp[e.axis] = -1
+            return _Lin.const(np.asarray(self.gw[e.axis], dtype=float).reshape(shp))
+        raise NotImplementedError('expression node %s after finalize()' % kind)
+
+
+def _slot_to_axis(slot, dim):
+    """parametric slot (component, D in x,y,z order) -> 0 (value) or 1 + tensor axis of the derivative"""
+    if slot is None:
+        return -1
+    D = slot[1]
+    for i, d in enumerate(D):
+        if d:
+            return 1 + (dim - 1 - i)        # x is the last tensor axis (pyiga/codegen/cython.py:170)
+    return 0
+
+
+class _ParametricBlock:
+    """One scalar form given by coefficient arrays of PARAMETRIC slot pairs: tables + field upload."""
+
+    def __init__(self, kvs, nqp, dim, arity, coefs, grid_shape, full_shape=None, box=None):
+        be = _device.backend()
+        keys = sorted(coefs)
+        terms = [(f, bp, ap) for f, (bp, ap) in enumerate(keys)]
+        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms))
+        full = full_shape or grid_shape
+        fields = np.zeros((len(terms),) + tuple(full))
+        for f, key in enumerate(keys):
+            vals = np.broadcast_to(np.asarray(coefs[key], dtype=float), grid_shape)
+            if box is None:
+                fields[f] = vals
+            else:       # on-demand assembler: only the Gauss points of the bounding box carry data
+                fields[(f,) + tuple(slice(a, b) for a, b in box)] = vals
+        buf = be.from_host(np.ascontiguousarray(fields).ravel())
+        self.dev.fields = buf
+        self.dev._geo_bound = None
+        _device.check(be.lib.pb200_asm_bind_fields(self.dev.handle, be.ptr(buf)))
+
+
+class RefVFormAssembler(GenericFormAssembler):
+    """Device assembler class for a finalized reference VForm (what ``compile_vform`` returns)."""
+    _rvf = None
+    _on_demand = False
+
+    @classmethod
+    def inputs(cls):
+        return {inp.name: inp.shape for inp in cls._rvf.inputs}
+
+    @classmethod
+    def parameters(cls):
+        return {par.name: par.shape for par in cls._rvf.params}
+
+    def __init__(self, kvs, kvs_test=None, bbox=None, **args):
+        vf = self._rvf
+        kvs = tuple(kvs)
+        d = vf.dim
+        assert len(kvs) == d, "Assembler requires %d knot vectors" % d
+        if kvs_test is not None:
+            raise NotImplementedError('reference VForms over two spaces: use the string front end')
+        geo = args['geo']
+        assert geo.sdim == d, "Geometry has wrong source dimension"
+        assert geo.dim == vf.geo_dim, "Geometry has wrong dimension"
+        self.arity = vf.arity
+        self.nqp = max(kv.p for kv in kvs) + 1
+        self.kvs = (kvs, kvs)
+        self._geo, self._args = geo, dict(args)
+        self.bbox = bbox
+        self._bd, self._surface = None, False
+        meshes = [np.asarray(kv.mesh) for kv in kvs]
+        full_grid, full_w = make_tensor_quadrature(meshes, self.nqp)
+        box = None
+        if self._on_demand and bbox is not None:
+            # NB (pyiga/codegen/cython.py:541-559): bb[1] is the exclusive upper cell index
+            grid, w = make_tensor_quadrature([m[bb[0]:bb[1] + 1] for m, bb in zip(meshes, bbox)], self.nqp)
+            box = [(bb[0] * self.nqp, bb[1] * self.nqp) for bb in bbox]
+        else:
+            grid, w = full_grid, full_w
+        self.gaussgrid = full_grid
+        self._grid_shape = tuple(len(g) for g in grid)
+        full_shape = tuple(len(g) for g in full_grid)
+        itp = _Interpreter(vf, grid, w, args, geo)
+        nc_u = (vf.basis_funs[0].numcomp or 1) if vf.arity == 2 else 1
+        nc_v = (vf.basis_funs[-1].numcomp or 1)
+        self._vec = bool(vf.vec)
+        self._nc = (nc_u, nc_v)
+        if self._vec:
+            self.num_components = lambda: self._nc
+        # output expressions: scalars, or literal vectors with one entry per (test comp, trial comp)
+        blocks = {}
+        for e in vf.exprs:
+            scal = [e] if e.shape == () else [e[k] for k in range(e.shape[0])]
+            for k, se in enumerate(scal):
+                lin = itp.eval(se)
+                for (vs, us), c in lin.t.items():
+                    # vector-valued forms: finalize() has expressed every component pair through the SCALAR
+                    # basis functions; entry k of the output vector is the block entry (test component
+                    # k // nc_u, trial component k % nc_u)  (pyiga/vform.py:441-458)
+                    if self.arity == 2:
+                        if vs is None or us is None:
+                            raise ValueError('bilinear form with a term that lacks a basis function')
+                        blk = (k // nc_u, k % nc_u) if self._vec else (0, 0)
+                    else:
+                        if vs is None or us is not None:
+                            raise ValueError('linear form must contain v and no u')
+                        blk = (k, None) if self._vec else (0, None)
+                    key = (_slot_to_axis(vs, d), _slot_to_axis(us, d))
+                    dst = blocks.setdefault(blk, {})
+                    dst[key] = dst[key] + c if key in dst else c
+        if not blocks:
+            raise ValueError('the form has no terms')
+        self.blocks = {}
+        for blk, coefs in blocks.items():
+            self.blocks[blk] = _ParametricBlock(kvs, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box)
+        first = next(iter(self.blocks.values()))
+        self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
+
+    def update(self, **kwargs):
+        raise NotImplementedError('update() of reference VForms: rebuild the assembler')
+
+
+def compile_vform(vf, on_demand=False):
+    """``pyiga.compile.compile_vform`` for the device: returns an assembler CLASS for the reference VForm
+    `vf` (finalized here, once; ``pyiga/compile.py:120-132`` keys its cache the same way)."""
+    key = (id(vf), bool(on_demand))
+    cls = _cache.get(key)
+    if cls is None:
+        if not getattr(vf, '_VForm__is_finalized', False):
+            vf.finalize(do_precompute=True)
+        if vf.is_boundary or vf.dim != vf.geo_dim:
+            raise NotImplementedError('boundary / surface integrals of reference VForms: use the string front end')
+        cls = type('RefVFormAssembler%d' % len(_cache), (RefVFormAssembler,), {'_rvf': vf, '_vf': vf, '_on_demand': bool(on_demand)})
+        _cache[key] = cls
+        _keep.append(vf)
+    return cls
+
+
+_cache = {}
+_keep = []

@@ -622,9 +622,15 @@ def compile_vform(vf, on_demand=False, verbose=False):
     """Return an assembler *class* for the form, like ``pyiga.compile.compile_vform``
     (``pyiga/compile.py:120-132``); no code is generated — the class analyses the form when it is
     instantiated on a concrete space.  `on_demand` assemblers of the reference evaluate their fields
-    lazily inside a bounding box of cells (``bbox=`` of the constructor, used by
-    ``HDiscretization._assemble_level``); here the fields of the whole patch are one K2 launch, so the
-    flag and the box are accepted and every entry stays valid."""
+    only inside a bounding box of cells (``bbox=`` of the constructor, used by
+    ``HDiscretization._assemble_level``): forms given as reference ``VForm`` objects honour the box
+    (:mod:`pyiga_b200.refvform`); for forms of this module the fields of the whole patch are one K2
+    launch, so the box is accepted and every entry stays valid."""
+    from . import refvform
+    if refvform.is_reference_vform(vf):
+        # a pyiga.vform.VForm: interpreted after its own finalize() (SURVEY.md Appendix A); `on_demand`
+        # assemblers evaluate their inputs only inside the bounding box given to the constructor
+        return refvform.compile_vform(vf, on_demand=on_demand)
     input_shapes = {'geo': (vf.geo_dim,)}
     input_shapes.update({name: shape for name, shape, _, _ in vf.inputs})
     param_shapes = {name: shape for name, shape in vf.params}

@@ -1,0 +1,64 @@
+"""The reference-VForm cases shared by the fixture generator (make_golden_vform.py, runs the real
+reference incl. its JIT) and the parity check (builds the same pyiga.vform.VForm objects and hands them
+to the device backend).  Needs `pyiga` importable (oracle/_ref)."""
+import numpy as np
+
+
+def spaces():
+    from pyiga import bspline as rbs
+    kv2 = (rbs.make_knots(2, 0.0, 1.0, 4), rbs.make_knots(3, 0.0, 1.0, 3))
+    kv3 = (rbs.make_knots(2, 0.0, 1.0, 3), rbs.make_knots(1, 0.0, 1.0, 4), rbs.make_knots(2, 0.0, 1.0, 2))
+    return kv2, kv3
+
+
+def _A(x, y):
+    one = 1.0 + 0.0 * (x + y)
+    return np.stack([np.stack([(2.0 + x) * one, 0.3 * y * one], -1), np.stack([0.3 * y * one, (1.0 + x * x) * one], -1)], -2)
+
+
+def cases():
+    """name -> (VForm factory, knot vectors, geometry, inputs)"""
+    from pyiga import geometry as rgeo, vform as rvf
+    kv2, kv3 = spaces()
+    geo2, geo3 = rgeo.quarter_annulus(), rgeo.twisted_box()
+    dc = lambda x, y, z: 1.0 + x * y
+
+    def aniso2():
+        vf = rvf.VForm(2)
+        u, v = vf.basisfuns()
+        A = vf.input('A', shape=(2, 2))
+        c = vf.parameter('c')
+        vf.add(rvf.inner(rvf.dot(A, rvf.grad(u)), rvf.grad(v)) * rvf.dx + c * u * v * rvf.dx)
+        return vf
+
+    return {
+        'stiffness2': (lambda: rvf.stiffness_vf(2), kv2, geo2, {}),
+        'mass3': (lambda: rvf.mass_vf(3), kv3, geo3, {}),
+        'convdiff3': (lambda: rvf.parse_vf('(inner(diff_coeff * grad(u), grad(v)) + inner((x[1], -x[0], 1.0), grad(u)) * v) * dx',
+                                           kv3, args={'diff_coeff': dc}), kv3, geo3, {'diff_coeff': dc}),
+        'aniso2': (aniso2, kv2, geo2, {'A': _A, 'c': 2.5}),
+        'divdiv2': (lambda: rvf.divdiv_vf(2), kv2, geo2, {}),
+        'l2func2': (lambda: rvf.L2functional_vf(2, physical=True), kv2, geo2, {'f': lambda x, y: x * y + 1.0}),
+    }
+
+
+def hspace(truncate):
+    from pyiga import bspline as rbs, hierarchical
+    # the example space of the reference's own tests (test/test_hierarchical.py:10-18)
+    kvs = 2 * (rbs.make_knots(3, 0.0, 1.0, 4),)
+    hs = hierarchical.HSpace(kvs, truncate=truncate, disparity=1, bdspecs=[(0, 0), (0, 1), (1, 0), (1, 1)])
+    for lv in range(2):
+        hs.refine_region(lv, lambda *X: min(X) > 1 - 0.5 ** (lv + 1))
+    return hs
+
+
+def hcases():
+    """name -> (VForm factory, inputs, symmetric)"""
+    from pyiga import vform as rvf
+    c = lambda x, y: 1.0 + x * y
+    kvs0 = hspace(False).knotvectors(0)
+    return {
+        'hstiff': (lambda: rvf.stiffness_vf(2), {}, True),
+        'hconv': (lambda: rvf.parse_vf('(inner(grad(u), grad(v)) + inner((1.0, x[0]), grad(u)) * v + c * u * v) * dx', kvs0,
+                                       args={'c': c}), {'c': c}, False),
+    }

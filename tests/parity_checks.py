@@ -997,3 +997,100 @@ def check_native_distributed_cg(world=1, rank=0, p=2, n=(7, 4, 5), rtol=1e-11):
     assert its2 == its and np.abs(be.to_host(x2) - 2.0 * xstar[lo:hi]).max() <= 2e-7 * np.abs(xstar).max()
     cg.close()
     return its
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own VForm objects on the device (pyiga_b200.refvform) and its hierarchical driver
+# ---------------------------------------------------------------------------------------------
+def _import_reference():
+    """the real reference from oracle/_ref (test infrastructure); skips when it is not installed"""
+    import os
+    import sys
+    import pytest
+    refdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(refdir, 'pyiga')):
+        pytest.skip('oracle/_ref is not installed')
+    if refdir not in sys.path:
+        sys.path.insert(0, refdir)
+    try:
+        import pyiga
+        return pyiga
+    except Exception as exc:        # pragma: no cover
+        pytest.skip('reference does not import: %s' % exc)
+
+
+def _vform_fixture():
+    import os
+    import sys
+    from helpers import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import refvform_cases as rc
+    return rc, np.load(os.path.join(GOLDEN, 'ref_vform_objects.npz'))
+
+
+def check_reference_vform_objects():
+    """pyiga.vform.VForm objects (programmatic and parsed from strings by the REFERENCE's parse_vf) go
+    through pyiga_b200.assemble.assemble and give the matrices of the reference's JIT-compiled assemblers
+    (fixture: tests/golden/make_golden_vform.py).  Only the reference's pure-Python vform module runs here."""
+    _import_reference()
+    from pyiga_b200 import assemble
+    rc, fix = _vform_fixture()
+    for name, (make, kvs, geo, inputs) in rc.cases().items():
+        want = fix['vf_' + name]
+        got = assemble.assemble(make(), kvs, geo=geo, **inputs)
+        got = got.toarray() if hasattr(got, 'toarray') else np.asarray(got)
+        assert got.shape == want.shape, name
+        assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), '%s: %.3e' % (name, np.abs(got - want).max())
+
+
+def check_hierarchical_discretization(monkeypatch):
+    """the reference's HDiscretization (pyiga/_hdiscr.py:37-57) assembles HB / THB-spline matrices level by
+    level with on_demand assemblers inside bounding boxes; with its compile_vform replaced by the device
+    backend the matrices equal the reference's own (test/test_hierarchical.py:180-215 pattern)"""
+    _import_reference()
+    from pyiga import _hdiscr, geometry as rgeo
+    from pyiga_b200 import vform as dvform
+    rc, fix = _vform_fixture()
+    geo = rgeo.bspline_quarter_annulus()
+    for name, (make, inputs, sym) in rc.hcases().items():
+        for truncate in (False, True):
+            want = fix['h_%s_%d' % (name, truncate)]
+            calls = []
+
+            def device_compile(vf, on_demand=False):
+                calls.append(on_demand)
+                return dvform.compile_vform(vf, on_demand=on_demand)
+            with monkeypatch.context() as mp:
+                mp.setattr(_hdiscr.compile, 'compile_vform', device_compile)
+                hs = rc.hspace(truncate)
+                got = _hdiscr.HDiscretization(hs, make(), dict(inputs, geo=geo)).assemble_matrix(symmetric=sym).toarray()
+            assert calls and all(calls), 'HDiscretization must have asked for on_demand assemblers'
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max(), (name, truncate, np.abs(got - want).max())
+
+
+def check_entry_func_ptr():
+    """the "entryfunc" capsule (pyiga/genericasm.pxi:780-786): the reference's low-rank (ACA) assembler
+    pyiga.fast_assemble_cy.fast_assemble pulls single entries of a device assembler through it"""
+    import ctypes as C
+    import pytest
+    _import_reference()
+    from pyiga_b200 import assemblers, bspline, geometry
+    kvs = (bspline.make_knots(2, 0.0, 1.0, 6), bspline.make_knots(3, 0.0, 1.0, 5))
+    asm = assemblers.StiffnessAssembler2D(kvs, geometry.bspline_quarter_annulus())
+    A = asm.assemble_csr()
+    cap = asm.entry_func_ptr()
+    get = C.pythonapi.PyCapsule_GetPointer
+    get.restype, get.argtypes = C.c_void_p, [C.py_object, C.c_char_p]
+    fn = C.CFUNCTYPE(C.c_double, C.c_size_t, C.c_size_t, C.c_void_p)(get(cap, b'entryfunc'))
+    for i, j in ((0, 0), (5, 6), (17, 3), (A.shape[0] - 1, A.shape[0] - 2)):
+        assert fn(i, j, None) == A[i, j]
+    try:
+        from pyiga import fast_assemble_cy
+    except Exception as exc:        # pragma: no cover
+        pytest.skip('fast_assemble_cy of the reference does not import: %s' % exc)
+    from pyiga import bspline as rbs
+    rkvs = tuple(rbs.KnotVector(kv.kv, kv.p) for kv in kvs)
+    B = fast_assemble_cy.fast_assemble(asm, rkvs, tol=1e-12, maxiter=200, verbose=0)
+    assert abs(B - A).max() <= 1e-9 * abs(A).max()

@@ -189,3 +189,15 @@ def test_large_fixture_logic(emu, name, nslabs):
 
 def test_large_full_logic(emu):
     pc.check_large_full('tiny_stiff_p2_n6')
+
+
+def test_reference_vform_objects(emu):
+    pc.check_reference_vform_objects()
+
+
+def test_hierarchical_discretization(emu, monkeypatch):
+    pc.check_hierarchical_discretization(monkeypatch)
+
+
+def test_entry_func_ptr(emu):
+    pc.check_entry_func_ptr()

@@ -268,3 +268,15 @@ def test_native_cg_single_gpu(cuda):
     """device-resident CG (CUDA graph batches, device-side convergence flag) on one GPU; the multi-GPU
     path of the same code runs in tests/test_dist_cpu.py (shared-memory windows) and tools/dist_cg_bench.py"""
     pc.check_native_distributed_cg(p=3, n=(9, 6, 7))
+
+
+def test_reference_vform_objects(cuda):
+    pc.check_reference_vform_objects()
+
+
+def test_hierarchical_discretization(cuda, monkeypatch):
+    pc.check_hierarchical_discretization(monkeypatch)
+
+
+def test_entry_func_ptr(cuda):
+    pc.check_entry_func_ptr()
