@@ -1124,7 +1124,7 @@ static void fill_s32_axes(const pb200_assembler* a, PbS32Params& p) {
     p.pair_i0 = D0.pair_i; p.pair_j0 = D0.pair_j; p.tr0 = D0.tr;
     p.G1 = H1.G; p.G2 = H2.G; p.n1 = H1.n; p.n2 = H2.n;
     p.N1 = H1.V.N(); p.N2 = H2.V.N(); p.M1 = H1.M; p.M2 = H2.M;
-    p.first1 = D1.first_u; p.V1 = D1.Vu; p.ret_mu1 = D1.ret_mu; p.tr1 = D1.tr;
+    p.first1 = D1.first_u; p.V1 = D1.Vu; p.ret_mu1 = D1.ret_mu; p.tr1 = D1.tr; p.pair_i1 = D1.pair_i;
     p.first2 = D2.first_u; p.V2 = D2.Vu; p.ret_mu2 = D2.ret_mu; p.tr2 = D2.tr;
 }
 static bool fused_stage23(const pb200_assembler* a) {
@@ -1606,6 +1606,39 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         q.symmetric = 1;
         q.out = d_out; q.out_mu_base = S.mu_lo;
         q.nbatch = pb_lane_batches(H2.n, H2.U.p);
+        {
+            // Tail effect: one block per SM and ~0.3 ms per block — a slab whose blocks fill the GPU 2.4 times
+            // pays for 3 waves.  Cut axis 1 into K pieces (K x as many, shorter blocks; p spans of overlap
+            // each) when that shortens the sum of the waves.
+            long long kept = 0;
+            for (int mu = S.mu_lo; mu < S.mu_hi; ++mu) {
+                const int i0 = H0.pair_i[mu], j0 = H0.pair_j[mu];
+                if (!(j0 >= S.ra && j0 < S.rb && j0 < i0)) ++kept;
+            }
+            const long long tasks = kept * q.nbatch;
+            const int P = H1.U.p, nsp = H1.n, N1 = H1.V.N();
+            int K = 1;
+            if (a->walk_split > 1) {
+                K = std::min(a->walk_split, 4);
+            } else if (a->walk_split == 0 && a->sm_count > 0 && tasks > 0) {
+                double best = (double)((tasks + a->sm_count - 1) / a->sm_count) * nsp;
+                for (int k = 2; k <= 4; ++k) {
+                    if (nsp / k < 4 * (P + 1)) break;
+                    const double cost = (double)((k * tasks + a->sm_count - 1) / a->sm_count) * ((double)nsp / k + P + 2);
+                    if (cost < 0.95 * best) { best = cost; K = k; }
+                }
+            }
+            K = std::min(K, N1);
+            if (K > 1) {
+                q.npiece = K;
+                for (int y = 0; y < K; ++y) {
+                    const int lo = (int)((long long)N1 * y / K), hi = (int)((long long)N1 * (y + 1) / K);
+                    q.pw_lo[y] = lo; q.pw_hi[y] = hi;
+                    q.ps_begin[y] = H1.V.supp[2 * lo];
+                    q.ps_end[y] = H1.V.supp[2 * (hi - 1) + 1];
+                }
+            }
+        }
         mark_stage(a, stiff ? "s23" : "s23_mass", st);
         ++g_launches;
         int e = pb_find_s32(a->form, H1.U.p, H1.q)(&q, st);

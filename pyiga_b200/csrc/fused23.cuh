@@ -48,13 +48,25 @@ struct PbS32Params {
     int symmetric;              // 1: compute upper mu0 only and mirror; 0: every mu0 on its own
     // ---- axis 1 (walked by the consumers) and axis 2 (lane-per-span) ------------------------------
     int G1, G2, n1, n2, N1, N2, M1, M2;
-    const int* first1; const double* V1; const int* ret_mu1; const int* tr1;
+    const int* first1; const double* V1; const int* ret_mu1; const int* tr1; const int* pair_i1;
     const int* first2; const double* V2; const int* ret_mu2; const int* tr2;
     // ---- output: data[(mu0 - out_mu_base)][mu1][mu2] -----------------------------------------------
     double* out;
     int out_mu_base;
     int nbatch;
+    // ---- optional split of axis 1 into pieces (more, shorter blocks: fills the tail wave of small slabs) --
+    // piece y retires the pairs (i1, j1) whose row i1 lies in [pw_lo[y], pw_hi[y]) and walks only the spans
+    // those rows see; the pieces overlap by p spans (same scheme as the walk-axis pieces of walk.cuh)
+    int npiece;
+    int ps_begin[4], ps_end[4], pw_lo[4], pw_hi[4];
 };
+struct PbS32Piece { int s_begin, s_end, w_lo, w_hi; };
+PB_HD PbS32Piece pb_s32_piece(const PbS32Params& prm, int y) {
+    PbS32Piece p;
+    if (prm.npiece > 1) { p.s_begin = prm.ps_begin[y]; p.s_end = prm.ps_end[y]; p.w_lo = prm.pw_lo[y]; p.w_hi = prm.pw_hi[y]; }
+    else { p.s_begin = 0; p.s_end = prm.n1; p.w_lo = 0; p.w_hi = 0x7fffffff; }
+    return p;
+}
 
 // ---- forms ------------------------------------------------------------------------------------------
 // Stiffness.  X1 terms (plans.cuh): 0 (v,v)  1 (v,d1)  2 (v,d2)  3 (d1,d1)  4 (d1,d2)  5 (d2,d2);
@@ -107,7 +119,8 @@ PB_HD bool pb_s32_keep(const PbS32Params& prm, int mu0, bool& mirror) {
 
 // ---- sequential emulation of one (mu0, batch) block (host build; same plans and tables) -------------
 template <class Form, int P, int Q>
-PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, double* Trow /* [G1][NT][TPAD] scratch */) {
+PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, int piece, double* Trow /* [G1][NT][TPAD] scratch */) {
+    const PbS32Piece pc = pb_s32_piece(prm, piece);
     constexpr int P1 = P + 1, NT = Form::NT, TPAD = PbS32Cfg<P>::TPAD;
     bool mirror;
     if (!pb_s32_keep(prm, mu0, mirror)) return;
@@ -129,7 +142,7 @@ PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, double* Trow /
     bool act[TPAD];
     for (int e = 0; e < TPAD; ++e) act[e] = false;
     // phase A for every row
-    for (int r = 0; r < prm.G1; ++r) {
+    for (int r = pc.s_begin * Q; r < pc.s_end * Q; ++r) {
         double Ls[NT][32][P1][P1];
         for (int lane = 0; lane < 32; ++lane) {
             const int s = sb + lane;
@@ -182,7 +195,13 @@ PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, double* Trow /
         w.in_sc = (long long)NT * TPAD;
         w.out[0] = prm.out + (long long)(mu0 - prm.out_mu_base) * prm.M1 * prm.M2 + (mu_lo + e);
         w.out_smu = prm.M2; w.mu_base = 0;
-        w.s_begin = 0; w.s_end = prm.n1; w.N = prm.N1;
+        w.s_begin = pc.s_begin; w.s_end = pc.s_end; w.N = prm.N1;
+        if (prm.npiece > 1) {           // the piece filter of the walk: rows of axis 1 in [w_lo, w_hi)
+            w.nsplit = 2;               // (pb_walk_range reads entry `piece` of the sp_ arrays; only slot 0 is filled)
+            w.sp_s_begin[0] = pc.s_begin; w.sp_s_end[0] = pc.s_end;
+            w.sp_w_lo[0] = pc.w_lo; w.sp_w_hi[0] = pc.w_hi;
+            w.sp_f_lo[0] = prm.first1[pc.s_begin]; w.sp_f_hi[0] = prm.N1;
+        }
         w.first = prm.first1; w.V2 = prm.V1; w.ret_mu = prm.ret_mu1;
         w.f_lo = prm.first1[0]; w.f_hi = prm.N1;
         w.regular = 1;
@@ -190,7 +209,10 @@ PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, double* Trow /
         if (mirror) {
             const double* src = w.out[0];
             double* dst = prm.out + (long long)(mu0t - prm.out_mu_base) * prm.M1 * prm.M2 + prm.tr2[mu_lo + e];
-            for (int mu1 = 0; mu1 < prm.M1; ++mu1) dst[(long long)prm.tr1[mu1] * prm.M2] = src[(long long)mu1 * prm.M2];
+            for (int mu1 = 0; mu1 < prm.M1; ++mu1) {
+                const int i1 = prm.pair_i1[mu1];
+                if (i1 >= pc.w_lo && i1 < pc.w_hi) dst[(long long)prm.tr1[mu1] * prm.M2] = src[(long long)mu1 * prm.M2];
+            }
         }
     }
 }
@@ -264,8 +286,10 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
     double* sT = reinterpret_cast<double*>(pb_s32_raw + lay.tbuf);
     int* sAct = reinterpret_cast<int*>(pb_s32_raw + lay.actv);
 
-    const int batch = blockIdx.x % prm.nbatch;
-    const int mu0 = prm.mu0_begin + blockIdx.x / prm.nbatch;
+    const int npc = prm.npiece > 1 ? prm.npiece : 1;
+    const int batch = (blockIdx.x / npc) % prm.nbatch;
+    const int mu0 = prm.mu0_begin + blockIdx.x / (npc * prm.nbatch);
+    const PbS32Piece pc = pb_s32_piece(prm, blockIdx.x % npc);
     bool mirror;
     if (!pb_s32_keep(prm, mu0, mirror)) return;         // block-uniform
     const int mu0t = prm.symmetric ? prm.tr0[mu0] : mu0;
@@ -275,7 +299,12 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
     // ---- block setup: axis-1 tables, zeroed rings and T buffers, owned positions ---------------------
     for (int t = threadIdx.x; t < prm.G1 * 2 * P1; t += blockDim.x) sV1[t] = prm.V1[t];
     for (int t = threadIdx.x; t < prm.N1 * (2 * P + 1); t += blockDim.x) {
-        const int mu1 = prm.ret_mu1[t];
+        int mu1 = prm.ret_mu1[t];
+        if (mu1 >= 0) {         // piece filter on the row of the pair: entry k of function f is (f, f+k) or (f+k-P, f)
+            const int f1 = t / (2 * P + 1), k = t % (2 * P + 1);
+            const int i1 = (k <= P) ? f1 : f1 + (k - P);
+            if (i1 < pc.w_lo || i1 >= pc.w_hi) mu1 = -1;
+        }
         sOff[2 * t] = mu1 >= 0 ? mu1 * prm.M2 : -1;
         sOff[2 * t + 1] = (mu1 >= 0 && prm.symmetric) ? prm.tr1[mu1] * prm.M2 : -1;
     }
@@ -378,8 +407,9 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
             });
         };
 #pragma unroll
+        const int nsp = pc.s_end - pc.s_begin;
         for (int j = 0; j < NST - 1; ++j) {
-            if (j < prm.n1) issue(j, j);
+            if (j < nsp) issue(pc.s_begin + j, j);
             pb_cp_async_commit();
         }
         // one term: local block, neighbour sums, slots of the T row
@@ -425,10 +455,10 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
             }
         };
         int st = 0;
-        for (int s1 = 0; s1 <= prm.n1; ++s1) {
-            if (s1 < prm.n1) {
+        for (int s1 = 0; s1 <= nsp; ++s1) {
+            if (s1 < nsp) {
                 __syncwarp();
-                if (s1 + NST - 1 < prm.n1) issue(s1 + NST - 1, (st + NST - 1) % NST);
+                if (s1 + NST - 1 < nsp) issue(pc.s_begin + s1 + NST - 1, (st + NST - 1) % NST);
                 pb_cp_async_commit();
                 pb_cp_async_wait<NST - 1>();
                 __syncwarp();
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
     for (int a = 0; a < P1; ++a)
 #pragma unroll
         for (int b = 0; b < P1; ++b) acc[a][b] = 0.0;
-    int f = prm.first1[0];
+    int f = prm.first1[pc.s_begin];
 
     auto retire = [&](auto RC, int fr) {                // RC: phase in which function fr is row / column 0
         constexpr int R = decltype(RC)::value;
@@ -514,7 +544,8 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
         });
     };
     int phase = 0;
-    for (int s1 = 0; s1 <= prm.n1; ++s1) {
+    const int nsp = pc.s_end - pc.s_begin;
+    for (int s1 = 0; s1 <= nsp; ++s1) {
         if (s1 > 0) {
             const int sp = s1 - 1;                      // the span the producers finished before the last barrier
             const double* Tg = sT + (size_t)(sp & 1) * Q * NT * TPAD + e;
@@ -531,7 +562,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
                         }
                     }
 #pragma unroll
-                    for (int gq = 0; gq < Q; ++gq) node(RC, sp * Q + gq, Tg + (size_t)gq * NT * TPAD);
+                    for (int gq = 0; gq < Q; ++gq) node(RC, (pc.s_begin + sp) * Q + gq, Tg + (size_t)gq * NT * TPAD);
                 }
             });
             phase = (phase + 1 == P1) ? 0 : phase + 1;
@@ -539,7 +570,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
         __syncthreads();
     }
     // flush: the functions still in the window, starting in the phase of the last span
-    const int last_ph = (prm.n1 - 1) % P1;
+    const int last_ph = (nsp - 1) % P1;
     for (int t = 0; t < P1; ++t) {
         if (f < prm.N1) {
             pb_static_for<0, P1>([&](auto PH) {

@@ -157,10 +157,11 @@ int launch_s32(const PbS32Params* prm, void* stream) {
     if (!prm->out) return 0;
     std::vector<double> T((size_t)prm->G1 * Form::NT * PbS32Cfg<PB_P>::TPAD);
     for (int u = 0; u < prm->mu0_count; ++u)
-        for (int b = 0; b < prm->nbatch; ++b) {
-            std::fill(T.begin(), T.end(), 0.0);
-            pb_s32_seq<Form, PB_P, PB_Q>(*prm, prm->mu0_begin + u, b, T.data());
-        }
+        for (int b = 0; b < prm->nbatch; ++b)
+            for (int y = 0; y < std::max(1, prm->npiece); ++y) {
+                std::fill(T.begin(), T.end(), 0.0);
+                pb_s32_seq<Form, PB_P, PB_Q>(*prm, prm->mu0_begin + u, b, y, T.data());
+            }
     return 0;
 #else
     const PbS32Smem<Form, PB_P, PB_Q> lay(prm->G1, prm->N1);
@@ -175,7 +176,7 @@ int launch_s32(const PbS32Params* prm, void* stream) {
         if (e != cudaSuccess) return (int)e;
         if (devno < 64) configured |= 1ull << devno;
     }
-    const long long blocks = (long long)prm->mu0_count * prm->nbatch;
+    const long long blocks = (long long)prm->mu0_count * prm->nbatch * std::max(1, prm->npiece);
     if (blocks <= 0) return 0;
     kern<<<(unsigned)blocks, (PB_Q * PbS32Split<Form>::NH + PbS32Cfg<PB_P>::NCW) * 32, lay.total, (cudaStream_t)stream>>>(*prm);
     return (int)cudaGetLastError();
