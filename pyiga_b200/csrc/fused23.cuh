@@ -268,6 +268,7 @@ PB_D void pb_span_block_sd(const double (&x)[Q][Plan::NOPS], const double* sDl, 
 }
 
 template <class Form, int P, int Q>
+// (two blocks per SM for single-term forms were tried: 80 registers per thread spill in the consumers' walk, 2.0 -> 2.7 ms)
 __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) * 32, 1) pb_s32_kernel(const __grid_constant__ PbS32Params prm) {
     constexpr int P1 = P + 1, NIN = Form::NIN, NT = Form::NT;
     using SP = PbS32Split<Form>;

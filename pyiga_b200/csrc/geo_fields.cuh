@@ -123,6 +123,23 @@ PB_HD void pb_geo_eval(const PbGeoDev& geo, const int* g, PbPoint& pt) {
     }
 }
 
+// 1 / x for the field programs of the fused stage 1: the hardware's reciprocal seed (20+ bits) and three
+// Newton steps — full double precision up to the last bit or two (the IEEE division's exact rounding
+// costs a ~90-cycle dependent chain per Gauss point, which the two resident warps per scheduler of that
+// kernel cannot hide).  x is a positive finite number here (|det J| of a regular map).
+PB_HD double pb_rcp_fast(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
 // ---- field programs ---------------------------------------------------------------------------
 template <int DIM> PB_HD double pb_det(const double (&J)[3][3]) {
     if constexpr (DIM == 2) return J[0][0] * J[1][1] - J[0][1] * J[1][0];
@@ -184,10 +201,10 @@ template <int DIM> struct PbProgMass {
     static constexpr int NF = 1;
     static constexpr bool NEED_X = false;
     template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) { point<RAT>(pt, f); }
-    template <bool RAT> PB_HD static void point(PbPoint& pt, double* f) {
+    template <bool RAT, bool FAST = false> PB_HD static void point(PbPoint& pt, double* f) {
         const double d = pt.gw * fabs(pb_det<DIM>(pt.J));
         if constexpr (RAT) {
-            const double r = 1.0 / pt.jden;
+            const double r = FAST ? pb_rcp_fast(pt.jden) : 1.0 / pt.jden;
             f[0] = d * (DIM == 2 ? r * r : r * r * r);
         } else {
             f[0] = d;
@@ -201,7 +218,7 @@ template <int DIM> struct PbProgStiffness {
     static constexpr int NF = DIM * (DIM + 1) / 2;
     static constexpr bool NEED_X = false;
     template <bool RAT> PB_HD static void run(const PbFieldParams&, PbPoint& pt, double* f) { point<RAT>(pt, f); }
-    template <bool RAT> PB_HD static void point(PbPoint& pt, double* f) {
+    template <bool RAT, bool FAST = false> PB_HD static void point(PbPoint& pt, double* f) {
         // with J = N / jden:  W J^-1 J^-T = gw jden^(2-DIM) / |det N| * adj(N) adj(N)^T  -- one division
         double A[3][3];
         pb_adj<DIM>(pt.J, A);
@@ -209,7 +226,7 @@ template <int DIM> struct PbProgStiffness {
         double det = pt.J[0][0] * A[0][0];
         for (int m = 1; m < DIM; ++m) det = fma(pt.J[0][m], A[m][0], det);
         const double den = (RAT && DIM == 3) ? pt.jden * fabs(det) : fabs(det);
-        const double sc = pt.gw / den;
+        const double sc = FAST ? pt.gw * pb_rcp_fast(den) : pt.gw / den;
         int k = 0;
         for (int a = 0; a < DIM; ++a)
             for (int b = a; b < DIM; ++b) {

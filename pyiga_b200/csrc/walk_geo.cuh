@@ -106,7 +106,7 @@ struct PbGeoLoader {
     PB_HD void begin_span(int s) {
         constexpr int GD = 3;
         constexpr bool RAT = (NC == GD + 1);
-#pragma unroll 2
+#pragma unroll (Plan::NOUT > 1 ? 2 : 4)
         for (int gq = 0; gq < Q; ++gq) {
             const int g0 = s * Q + gq;
             const int f0 = F0[g0];
@@ -144,7 +144,7 @@ struct PbGeoLoader {
                     for (int k = 0; k < 3; ++k) pt.J[i][2 - k] = dv[i][k];
             }
             double f[Prog::NF];
-            Prog::template point<RAT>(pt, f);
+            Prog::template point<RAT, true>(pt, f);
             pb_static_for<0, NOPS>([&](auto I) {
                 constexpr int i = decltype(I)::value;
                 F[(long long)(gq * NOPS + i) * fs] = f[Plan::field(i)];
