@@ -112,16 +112,26 @@ struct PbGeoLoader {
             const int f0 = F0[g0];
             const double* Tn = T0 + (long long)g0 * 2 * (pg0 + 1);
             double val[NC], dv[NC][3];
+            {   // first active function assigns (no zero-fill of the 4 NC accumulators), the others accumulate
+                const double w = Tn[0], d = Tn[pg0 + 1];
+                const double* z = Z + (long long)(f0 * NC * 3) * zs;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) val[c] = dv[c][0] = dv[c][1] = dv[c][2] = 0.0;
-            for (int a = 0; a <= pg0; ++a) {
+                for (int c = 0; c < NC; ++c) {
+                    const double z0 = z[(c * 3 + 0) * zs], z1 = z[(c * 3 + 1) * zs], z2 = z[(c * 3 + 2) * zs];
+                    val[c] = w * z0;
+                    dv[c][0] = d * z0;          // derivative along tensor axis 0
+                    dv[c][1] = w * z1;
+                    dv[c][2] = w * z2;
+                }
+            }
+            for (int a = 1; a <= pg0; ++a) {
                 const double w = Tn[a], d = Tn[pg0 + 1 + a];
                 const double* z = Z + (long long)((f0 + a) * NC * 3) * zs;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     const double z0 = z[(c * 3 + 0) * zs], z1 = z[(c * 3 + 1) * zs], z2 = z[(c * 3 + 2) * zs];
                     val[c] = fma(w, z0, val[c]);
-                    dv[c][0] = fma(d, z0, dv[c][0]);        // derivative along tensor axis 0
+                    dv[c][0] = fma(d, z0, dv[c][0]);
                     dv[c][1] = fma(w, z1, dv[c][1]);
                     dv[c][2] = fma(w, z2, dv[c][2]);
                 }

@@ -55,7 +55,7 @@ def main():
            'dram_bytes_per_launch': {k: (v.get('dram__bytes_read.sum', 0.0) + v.get('dram__bytes_write.sum', 0.0)) * unit for k, v in last.items()},
            'dram_bytes_read_per_launch': {k: v.get('dram__bytes_read.sum', 0.0) for k, v in last.items()},
            'dram_bytes_write_per_launch': {k: v.get('dram__bytes_write.sum', 0.0) for k, v in last.items()},
-           'ms_per_launch_under_ncu': {k: v.get('gpu__time_duration.sum', 0.0) for k, v in last.items()}}
+           'ms_per_launch_under_ncu': {k: v.get('gpu__time_duration.sum', 0.0) * 1e-6 for k, v in last.items()}}
     json.dump(res, open(out, 'w'), indent=1)
     print(json.dumps(res, indent=1))
 

@@ -12,8 +12,11 @@ def raw(rep):
     return rows[0], rows[2:]
 
 
-def source(rep):
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+def source(rep, launch=None):
+    cmd = ['ncu', '-i', rep, '--page', 'source', '--csv']
+    if launch is not None:
+        cmd += ['--launch-skip', str(launch), '--launch-count', '1']
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     sect, cur = [], None
     for r in csv.reader(out.splitlines()):
         if r and r[0] == 'Kernel Name':
@@ -35,8 +38,8 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 def main():
     rep = sys.argv[1]
     h, rows = raw(rep)
-    src = source(rep)
     for n, r in enumerate(rows):
+        src = [None] * n + source(rep, n)[:1]
         print('=' * 100)
         print(r[h.index('Kernel Name')][:95], '| grid', r[h.index('Grid Size')], 'block', r[h.index('Block Size')])
         for k in KEYS:
