@@ -225,12 +225,18 @@ PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, int piece, dou
 // Measured on B200 (3D p=3 n=128 stiffness): one warp per row with the lane's basis values in
 // registers 4.9 ms; two warps per row with the values in shared memory (512 threads need <= 128
 // registers) 5.6 ms — the extra shared-memory reads (32 per term and row) cost more than the better
-// balance gains.  PB_S32_SPLIT selects the two-warp variant.
+// balance gains; with the values in registers and the register file re-partitioned by setmaxnreg
+// (PB_S32_SPLIT == 2, below) 4.7 ms against 4.5 ms for one warp per row.  PB_S32_SPLIT selects the variant.
 #ifndef PB_S32_SPLIT
 #define PB_S32_SPLIT 0
 #endif
-template <class Form> struct PbS32Split {
-    static constexpr int NH = (PB_S32_SPLIT && Form::NT > 1) ? 2 : 1;
+// PB_S32_SPLIT == 2: two warps per row AND the values in registers: the block is launched with 512 threads
+// (128 registers each) and re-partitions its register file with `setmaxnreg` — the two producer warpgroups
+// grow to 168 registers, the two consumer warpgroups shrink to 88 (8 x 32 x (168 + 88) = 64 K registers).
+template <class Form, int P, int Q> struct PbS32Split {
+    static constexpr bool ALIGNED = (2 * Q) % 4 == 0 && PbS32Cfg<P>::NCW % 4 == 0;     // setmaxnreg works on warpgroups of 4 warps
+    static constexpr bool REGSPLIT = (PB_S32_SPLIT == 2) && Form::NT > 1 && ALIGNED;
+    static constexpr int NH = ((PB_S32_SPLIT == 1 && Form::NT > 1) || REGSPLIT) ? 2 : 1;
     static constexpr int NSTR = Form::NIN / NH;                 // input streams per half
     static constexpr int half_of_term(int t) { return (NH == 1 || t == 0) ? 0 : 1; }
 };
@@ -238,7 +244,7 @@ template <class Form> struct PbS32Split {
 template <class Form, int P, int Q>
 struct PbS32Smem {     // dynamic shared memory layout (bytes)
     static constexpr int P1 = P + 1, NIN = Form::NIN, NT = Form::NT, NST = 3;
-    static constexpr int NH = PbS32Split<Form>::NH, NSTR = PbS32Split<Form>::NSTR;
+    static constexpr int NH = PbS32Split<Form, P, Q>::NH, NSTR = PbS32Split<Form, P, Q>::NSTR;
     static constexpr int SEG = 32 * Q, TPAD = PbS32Cfg<P>::TPAD;
     size_t v1, ret1, dlane, ring, tbuf, actv, total;
     PB_HD PbS32Smem(int G1, int N1) {
@@ -269,9 +275,9 @@ PB_D void pb_span_block_sd(const double (&x)[Q][Plan::NOPS], const double* sDl, 
 
 template <class Form, int P, int Q>
 // (two blocks per SM for single-term forms were tried: 80 registers per thread spill in the consumers' walk, 2.0 -> 2.7 ms)
-__global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) * 32, 1) pb_s32_kernel(const __grid_constant__ PbS32Params prm) {
+__global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>::NCW) * 32, 1) pb_s32_kernel(const __grid_constant__ PbS32Params prm) {
     constexpr int P1 = P + 1, NIN = Form::NIN, NT = Form::NT;
-    using SP = PbS32Split<Form>;
+    using SP = PbS32Split<Form, P, Q>;
     constexpr int NH = SP::NH, NSTR = SP::NSTR;
     constexpr int TPAD = PbS32Cfg<P>::TPAD, NPROD = Q * NH;
     using SM = PbS32Smem<Form, P, Q>;
@@ -348,13 +354,17 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
     (void)s;
 
     const long long plane = (long long)prm.G1 * prm.G2;
+    if constexpr (SP::REGSPLIT) {
+        if (producer) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    }
     if (producer) {
         // ========================= phase A: one grid row g1 per NH warps and span ====================
         const int prow = warp / NH, half = warp % NH;
         double* ring = sRing + (size_t)warp * NST * STAGE;
         const double* sDl = sD + lane;
-#if !PB_S32_SPLIT
-        double Dreg[Q][2][P1];          // basis values of this lane's span
+#if PB_S32_SPLIT != 1
+        double Dreg[Q][2][P1];          // (also the split variant with re-partitioned registers)          // basis values of this lane's span
 #pragma unroll
         for (int gq = 0; gq < Q; ++gq)
 #pragma unroll
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form>::NH + PbS32Cfg<P>::NCW) 
                 }
             });
             double L[P1][P1];
-#if PB_S32_SPLIT
+#if PB_S32_SPLIT == 1
             pb_span_block_sd<TP, P, Q>(xt, sDl, L);
 #else
             pb_span_block<TP, P, Q>(xt, Dreg, L);
