@@ -24,6 +24,7 @@
 
 #define PB_CG_MAXPEERS 16
 #define PB_CG_NRED 2            // values per all-reduce
+#define PB_CG_TI 8              // outputs per thread of the tiled mode products
 
 struct PbCgDev {
     int rank, world;
@@ -47,6 +48,9 @@ struct PbCgDev {
     size_t off_rstamp;          // long long [2][world]
     size_t off_rval;            // double [2][world][PB_CG_NRED]
     const double* Ainv[3];      // dense inverses of the 1D factors
+    const double* AinvT2;       // transposed copy of Ainv[2] (coalesced reads in the mode-2 product)
+    double* part2;              // per-block partial sums of <r, z> (the tiled mode-0 kernel has its own grid)
+    int nblocks2;
     int N[3];
 };
 
@@ -308,14 +312,116 @@ __global__ void __launch_bounds__(256) pb_cg_mode0_kernel(const __grid_constant_
     const double s = pb_cg_block_sum(v, sh);
     if (threadIdx.x == 0) c.part[(second ? gridDim.x : 0) + blockIdx.x] = s;
 }
+// ---- tiled mode products: 8 outputs per thread, the factor rows / vector rows staged in shared memory --------
+// mode 2 (last axis, contiguous): t1[a, i] = sum_j r[a, j] A2[i, j]; block: PB_CG_TI rows a, threads over i
+__global__ void __launch_bounds__(128) pb_cg_mode2_tiled_kernel(const __grid_constant__ PbCgDev c) {
+    extern __shared__ double pb_cg_sm[];
+    if (c.ctl[0]) return;
+    const int n = c.N[2];
+    const long long rows = c.nloc / n;
+    const long long a0 = (long long)blockIdx.x * PB_CG_TI;
+    for (int t = threadIdx.x; t < PB_CG_TI * n; t += blockDim.x) {
+        const long long a = a0 + t / n;
+        pb_cg_sm[t] = a < rows ? c.r[a * n + t % n] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double acc[PB_CG_TI];
+#pragma unroll
+        for (int k = 0; k < PB_CG_TI; ++k) acc[k] = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double av = c.AinvT2[(long long)j * n + i];
+#pragma unroll
+            for (int k = 0; k < PB_CG_TI; ++k) acc[k] = fma(av, pb_cg_sm[k * n + j], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < PB_CG_TI; ++k)
+            if (a0 + k < rows) c.t1[(a0 + k) * n + i] = acc[k];
+    }
+}
+// modes 1 and 0: y[a, i, cc] = sum_j A[i, j] x[a, j, cc], cc contiguous; block: PB_CG_TI outputs i, 128 values of cc
+//   MODE 1: x = t1 (local planes a), result -> the gather buffers of all ranks
+//   MODE 0: x = the gathered vector (one "a"), rows i of my slab, result -> z and the partial sums of <r, z>
+template <int MODE>
+__global__ void __launch_bounds__(128) pb_cg_modek_tiled_kernel(const __grid_constant__ PbCgDev c, int second) {
+    extern __shared__ double pb_cg_sm[];
+    __shared__ double sh[128];
+    if (c.ctl[0]) return;
+    const long long e = c.ctl[2];
+    const int b = (int)(e & 1);
+    const int n = MODE == 1 ? c.N[1] : c.N0;
+    const long long inner = MODE == 1 ? c.N[2] : c.plane;
+    const int mrows = MODE == 1 ? c.N[1] : (c.rb - c.ra);
+    const int i0 = blockIdx.y * PB_CG_TI;
+    const long long a = MODE == 1 ? blockIdx.z : 0;
+    const double* A = MODE == 1 ? c.Ainv[1] : c.Ainv[0] + (long long)c.ra * c.N0;
+    if (MODE == 0 && threadIdx.x == 0 && c.world > 1)
+        for (int q = 0; q < c.world; ++q) pb_cg_wait(pb_cg_flag(c, c.rank, c.off_gflag) + q, e);
+    for (int t = threadIdx.x; t < PB_CG_TI * n; t += blockDim.x) {
+        const int ii = i0 + t / n;
+        pb_cg_sm[t] = ii < mrows ? A[(long long)ii * n + t % n] : 0.0;
+    }
+    __syncthreads();
+    const long long cc = (long long)blockIdx.x * 128 + threadIdx.x;
+    double dot = 0.0;
+    if (cc < inner) {
+        const double* x = MODE == 1 ? c.t1 + a * n * inner + cc : pb_cg_gath(c, c.rank, b) + cc;
+        double acc[PB_CG_TI];
+#pragma unroll
+        for (int k = 0; k < PB_CG_TI; ++k) acc[k] = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double xv = x[(long long)j * inner];
+#pragma unroll
+            for (int k = 0; k < PB_CG_TI; ++k) acc[k] = fma(pb_cg_sm[k * n + j], xv, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < PB_CG_TI; ++k) {
+            if (i0 + k >= mrows) continue;
+            if (MODE == 1) {
+                const long long g = (long long)c.ra * c.plane + (a * n + i0 + k) * inner + cc;
+                for (int q = 0; q < c.world; ++q) pb_cg_gath(c, q, b)[g] = acc[k];
+            } else {
+                const long long t = (long long)(i0 + k) * inner + cc;
+                c.z[t] = acc[k];
+                dot = fma(acc[k], c.r[t], dot);
+            }
+        }
+    }
+    if (MODE == 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+            const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(c.ctl + 5), 1ull) + 1;
+            if (done == total) {
+                c.ctl[5] = 0;
+                pb_cg_mode1_signal(c);
+            }
+        }
+    } else {
+        sh[threadIdx.x] = dot;
+        __syncthreads();
+        for (int s2 = 64; s2 > 0; s2 >>= 1) {
+            if ((int)threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) c.part2[(long long)blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
+        (void)second;
+    }
+}
+
 __global__ void pb_cg_bump_epoch_kernel(const __grid_constant__ PbCgDev c) { c.ctl[2] = c.ctl[2] + 1; }
 __global__ void __launch_bounds__(256) pb_cg_allreduce_kernel(const __grid_constant__ PbCgDev c, int kind, int nblocks) {
     __shared__ double sh[256];
     if (c.ctl[0] && kind >= 2) return;
     double loc[PB_CG_NRED];
     for (int k = 0; k < PB_CG_NRED; ++k) {
+        // <r, z> (kind 1: value 0, kind 3: value 1) is summed by the tiled mode-0 kernel into part2
+        const bool rz = (kind == 1 && k == 0) || (kind == 3 && k == 1);
+        const double* src = rz ? c.part2 : c.part + (long long)k * nblocks;
+        const int cnt = rz ? c.nblocks2 : nblocks;
         double v = 0.0;
-        for (int i = threadIdx.x; i < nblocks; i += 256) v += c.part[(long long)k * nblocks + i];
+        for (int i = threadIdx.x; i < cnt; i += 256) v += src[i];
         loc[k] = pb_cg_block_sum(v, sh);
         __syncthreads();
     }

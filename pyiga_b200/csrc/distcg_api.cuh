@@ -109,6 +109,7 @@ struct pb200_cg {
     bool own_comm = false;
     void* mem = nullptr;        // device-local buffers
     int nblocks = 0, nb_lo = 0, nb_hi = 0;
+    int grid0x = 0, grid0y = 0;
 #ifndef PB_EMULATE
     cudaGraphExec_t graph = nullptr;
     int graph_iters = 0;
@@ -190,7 +191,12 @@ extern "C" int pb200_cg_create(const pb200_mlstruct* S, int rank, int world, con
     g->nb_hi = rank + 1 < world ? (int)((hrows + 255) / 256) : 0;
     // local buffers: x is the caller's; r z Ap t1 | part | scal | ctl
     const size_t nl = (size_t)d.nloc;
-    size_t bytes = (4 * nl + (size_t)PB_CG_NRED * g->nblocks + 16) * sizeof(double) + 8 * sizeof(long long) + 1024;
+    // grid of the tiled mode-0 kernel: (plane / 128) x (slab rows / PB_CG_TI)
+    g->grid0x = (int)((d.plane + 127) / 128);
+    g->grid0y = (d.rb - d.ra + PB_CG_TI - 1) / PB_CG_TI;
+    d.nblocks2 = g->grid0x * g->grid0y;
+    const size_t n2sq = (size_t)d.N[2] * d.N[2];
+    size_t bytes = (4 * nl + (size_t)PB_CG_NRED * g->nblocks + d.nblocks2 + n2sq + 16) * sizeof(double) + 8 * sizeof(long long) + 1024;
     CK(pbMalloc(&g->mem, bytes));
 #ifdef PB_EMULATE
     memset(g->mem, 0, bytes);
@@ -200,8 +206,20 @@ extern "C" int pb200_cg_create(const pb200_mlstruct* S, int rank, int world, con
     double* b = (double*)g->mem;
     d.r = b; d.z = b + nl; d.Ap = b + 2 * nl; d.t1 = b + 3 * nl;
     d.part = b + 4 * nl;
-    d.scal = d.part + (size_t)PB_CG_NRED * g->nblocks;
+    d.part2 = d.part + (size_t)PB_CG_NRED * g->nblocks;
+    double* at2 = d.part2 + d.nblocks2;
+    d.AinvT2 = at2;
+    d.scal = at2 + n2sq;
     d.ctl = reinterpret_cast<long long*>(d.scal + 16);
+#ifndef PB_EMULATE
+    {   // transposed copy of the last factor (once)
+        std::vector<double> hA(n2sq), hT(n2sq);
+        CK(cudaMemcpy(hA.data(), d_Ainv[2], n2sq * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < d.N[2]; ++i)
+            for (int j = 0; j < d.N[2]; ++j) hT[(size_t)j * d.N[2] + i] = hA[(size_t)i * d.N[2] + j];
+        CK(cudaMemcpy(at2, hT.data(), n2sq * sizeof(double), cudaMemcpyHostToDevice));
+    }
+#endif
     *out = g.release();
     return 0;
 }
@@ -266,9 +284,15 @@ static void cg_precond(pb200_cg* g, int second, pbStream st) {
         for (int q = 0; q < d.world; ++q) pb_cg_wait(pb_cg_flag(d, d.rank, d.off_gflag) + q, d.ctl[2]);
     cg_emu_blocks(d, g->nblocks, d.part + (second ? g->nblocks : 0), [&](long long t, int) { return pb_cg_mode0_elem(d, t); });
 #else
-    pb_cg_mode2_kernel<<<g->nblocks, 256, 0, st>>>(d);
-    pb_cg_mode1_kernel<<<g->nblocks, 256, 0, st>>>(d);
-    pb_cg_mode0_kernel<<<g->nblocks, 256, 0, st>>>(d, second);
+    {
+        const long long rows2 = d.nloc / d.N[2];
+        const size_t sm2 = (size_t)PB_CG_TI * d.N[2] * sizeof(double);
+        pb_cg_mode2_tiled_kernel<<<(unsigned)((rows2 + PB_CG_TI - 1) / PB_CG_TI), 128, sm2, st>>>(d);
+        const dim3 g1((unsigned)((d.N[2] + 127) / 128), (unsigned)((d.N[1] + PB_CG_TI - 1) / PB_CG_TI), (unsigned)(d.rb - d.ra));
+        pb_cg_modek_tiled_kernel<1><<<g1, 128, (size_t)PB_CG_TI * d.N[1] * sizeof(double), st>>>(d, second);
+        const dim3 g0((unsigned)g->grid0x, (unsigned)g->grid0y, 1);
+        pb_cg_modek_tiled_kernel<0><<<g0, 128, (size_t)PB_CG_TI * d.N0 * sizeof(double), st>>>(d, second);
+    }
 #endif
 }
 
