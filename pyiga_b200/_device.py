@@ -95,9 +95,10 @@ def check(rc):
 # spline evaluation on a tensor grid (BSplineFunc / NurbsFunc .grid_eval / .grid_jacobian)
 # ---------------------------------------------------------------------------------------------
 
-def eval_spline_on_grid(func, gridaxes, want):
+def eval_spline_on_grid(func, gridaxes, want, keep_on_device=False):
     """Evaluate a spline function or its Jacobian on a tensor grid on the device and return a
-    numpy array shaped like the reference's result (``pyiga/bspline.py:874-921``)."""
+    numpy array shaped like the reference's result (``pyiga/bspline.py:874-921``); with
+    `keep_on_device` the device buffer itself, viewed in that shape (CUDA backend)."""
     be = backend()
     sdim = func.sdim
     if sdim == 1:
@@ -123,6 +124,9 @@ def eval_spline_on_grid(func, gridaxes, want):
     check(be.lib.pb200_geo_eval_grid(C.byref(desc), npts, grids, be.ptr(vals), be.ptr(jac),
                                       be.device_index, be.stream()))
     scalar = len(func.output_shape()) == 0
+    if keep_on_device and want == 'value':
+        out = vals.reshape(shape + (dim,))
+        return out[..., 0] if scalar else out
     if want == 'value':
         out = be.to_host(vals).reshape(shape + (dim,))
         return out[..., 0] if scalar else out

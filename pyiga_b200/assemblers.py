@@ -490,8 +490,11 @@ class _FormBlock:
             if c.arr is not None:
                 if id(c.arr) not in index:
                     index[id(c.arr)] = len(arrays)
-                    arr = np.ascontiguousarray(np.broadcast_to(c.arr, self._grid_shape), dtype=np.float64)
-                    arrays.append(be.from_host(arr.ravel()))
+                    if hasattr(c.arr, 'device') and hasattr(c.arr, 'expand'):      # already on the GPU
+                        arrays.append(c.arr.expand(self._grid_shape).contiguous().reshape(-1))
+                    else:
+                        arr = np.ascontiguousarray(np.broadcast_to(c.arr, self._grid_shape), dtype=np.float64)
+                        arrays.append(be.from_host(arr.ravel()))
                 inp = index[id(c.arr)]
             phys[t] = _lib.PhysTerm(key[0], key[1], inp, c.scale)
         ptrs = (C.c_void_p * max(len(arrays), 1))(*[be.ptr(a) for a in arrays])
@@ -563,8 +566,12 @@ class GenericFormAssembler(_AssemblerProtocol):
         for name, shape in vf.params:
             self._env[name] = np.asarray(args[name], dtype=float)
         if any(_mentions_x(e) for e in vf.exprs):
-            X = self._physical_points()
-            self._env['@x'] = np.stack([X[..., i] for i in range(X.shape[-1])])
+            if self._device_inputs():
+                Xd = self._physical_points(device=True)
+                self._env['@x'] = Xd.movedim(-1, 0)
+            else:
+                X = self._physical_points()
+                self._env['@x'] = np.stack([X[..., i] for i in range(X.shape[-1])])
         nc_u, nc_v = vf.numcomp
         self._vec = bool(vf.vec)
         self._nc = (nc_u or 1, nc_v or 1)          # (trial, test) components
@@ -653,7 +660,23 @@ class GenericFormAssembler(_AssemblerProtocol):
         return MLMatrix(structure=self._bd_structure(), data=self._bd_select(full, 2))
 
     # ---- input evaluation (host side, like the reference) ------------------------------------
-    def _physical_points(self):
+    def _device_inputs(self):
+        """Coefficient arrays stay on the GPU (CUDA backend, volume forms on spline geometries): the
+        physical Gauss points are evaluated there and a callable written with arithmetic operators runs
+        on the device tensors; the host evaluation of the reference (``pyiga/codegen/cython.py:465-484``)
+        is the fall-back for callables that need numpy."""
+        return (self.dev_backend_name == 'cuda' and self._bd is None and not self._surface and _is_spline_geo(self._geo)
+                and len(self.gaussgrid) >= 2)
+
+    @property
+    def dev_backend_name(self):
+        return _device.backend().name
+
+    def _physical_points(self, device=False):
+        if device:
+            if getattr(self, '_Xd', None) is None:
+                self._Xd = _device.eval_spline_on_grid(self._geo, self.gaussgrid, 'value', keep_on_device=True)
+            return self._Xd
         if self._X is None:
             geo = self._geo
             self._X = np.asarray(geo.grid_eval(self.gaussgrid))     # device evaluation for spline geometries
@@ -663,8 +686,31 @@ class GenericFormAssembler(_AssemblerProtocol):
         from .vform import _grid_values
         if not physical:        # spline function: parametric, evaluated on the Gauss grid
             vals = np.asarray(f.grid_eval(self.gaussgrid))
-            return np.moveaxis(vals, tuple(range(len(self._grid_shape), vals.ndim)), tuple(range(len(shape)))) \
+            vals = np.moveaxis(vals, tuple(range(len(self._grid_shape), vals.ndim)), tuple(range(len(shape)))) \
                 if shape else vals
+            if self._device_inputs():
+                vals = _device.backend().from_host(np.ascontiguousarray(vals)).reshape(vals.shape)
+            return vals
+        if self._device_inputs():
+            Xd = self._physical_points(device=True)
+            coords = tuple(Xd[..., i] for i in range(Xd.shape[-1]))
+            try:
+                vals = _grid_values(f, shape, coords, self._grid_shape)
+            except Exception:       # the callable needs numpy (np.sin, math.*, ...): evaluate it on the host
+                vals = None
+            if vals is not None:
+                if shape == ():
+                    return vals
+                import torch
+                return torch.stack([v.contiguous() for v in vals.ravel()]).reshape(shape + self._grid_shape)
+            X = self._physical_points()
+            coords = tuple(X[..., i] for i in range(X.shape[-1]))
+            vals = _grid_values(f, shape, coords, self._grid_shape)
+            be = _device.backend()
+            if shape == ():
+                return be.from_host(np.ascontiguousarray(vals)).reshape(self._grid_shape)
+            arr = np.stack([np.ascontiguousarray(v) for v in vals.ravel()]).reshape(shape + self._grid_shape)
+            return be.from_host(arr).reshape(arr.shape)
         X = self._physical_points()
         coords = tuple(X[..., i] for i in range(X.shape[-1]))
         vals = _grid_values(f, shape, coords, self._grid_shape)
@@ -829,9 +875,13 @@ class GenericFormAssembler(_AssemblerProtocol):
                 for n2, (shape, physical) in known.items():     # physical inputs move with the geometry
                     if physical:
                         self._env[n2] = self._eval_input(self._args[n2], shape, physical)
+                self._Xd = None
                 if '@x' in self._env:
-                    X = self._physical_points()
-                    self._env['@x'] = np.stack([X[..., i] for i in range(self._vf.dim)])
+                    if self._device_inputs():
+                        self._env['@x'] = self._physical_points(device=True).movedim(-1, 0)
+                    else:
+                        X = self._physical_points()
+                        self._env['@x'] = np.stack([X[..., i] for i in range(self._vf.dim)])
                 continue
             if name not in known:
                 raise ValueError("unknown input '%s'" % name)

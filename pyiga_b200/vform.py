@@ -109,6 +109,9 @@ class Form:
         if not self.is_coef():
             raise ValueError('functions can only be applied to coefficient expressions')
         v = self.coef().value()
+        if _is_dev(v):
+            import torch
+            return Form.const(1.0, getattr(torch, fn.__name__)(v))
         r = fn(v)
         return Form.const(1.0, r) if isinstance(r, np.ndarray) else Form.const(float(r))
 
@@ -208,7 +211,7 @@ class Input(Expr):
 
 
 def _coef_form(v):
-    if isinstance(v, np.ndarray) and v.ndim > 0:
+    if (isinstance(v, np.ndarray) or (hasattr(v, 'device') and hasattr(v, 'expand'))) and v.ndim > 0:
         return Form.const(1.0, v)
     return Form.const(float(v))
 
@@ -598,10 +601,31 @@ def stiffness_vf(dim):
 # ---------------------------------------------------------------------------------------------
 # "compilation": VForm -> assembler class bound to the device pipeline
 # ---------------------------------------------------------------------------------------------
+def _is_dev(a):
+    """a torch tensor (coefficient arrays may live on the GPU, see GenericFormAssembler._eval_input)"""
+    return hasattr(a, 'device') and hasattr(a, 'expand')
+
+
+def _dev_broadcast(v, like, grid_shape):
+    import torch
+    if not _is_dev(v):
+        v = torch.as_tensor(np.asarray(v, dtype=float), dtype=torch.float64, device=like.device)
+    return v.to(torch.float64).expand(grid_shape)
+
+
 def _grid_values(f, shape, coords, grid_shape):
     """evaluate a callable at coordinate arrays (x, y, z order) and bring the result to
-    shape + grid_shape (``pyiga/utils.py:8-31`` _ensure_grid_shape)"""
+    shape + grid_shape (``pyiga/utils.py:8-31`` _ensure_grid_shape).  `coords` may be device tensors:
+    a callable written with arithmetic operators then runs on the GPU."""
     vals = f(*coords)
+    if _is_dev(coords[0]):
+        if shape == ():
+            return _dev_broadcast(vals, coords[0], grid_shape)
+        comps = np.empty(shape, dtype=object)
+        whole = vals if _is_dev(vals) and tuple(vals.shape[:len(shape)]) == shape else None
+        for idx in np.ndindex(*shape):
+            comps[idx] = _dev_broadcast(whole[idx] if whole is not None else _nested_get(vals, idx), coords[0], grid_shape)
+        return comps
     if shape == ():
         return np.broadcast_to(np.asarray(vals, dtype=float), grid_shape)
     comps = np.empty(shape, dtype=object)
