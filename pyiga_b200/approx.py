@@ -67,8 +67,21 @@ def project_L2(kvs, f, f_physical=False, geo=None, rtol=1e-14, maxiter=500):
     prec = GatheredKronecker(KroneckerOperator(*Minv), sa.slabs, 0, plane)
     to_t = (lambda v: torch.from_numpy(np.ascontiguousarray(v))) if be.name == 'emu' else be.from_host
 
+    native = None
+    if len(kvs) == 3:
+        # device-resident CG (csrc/distcg.cuh): scalars, convergence flag and iteration batches stay on the GPU
+        from .distcg import DistributedCG
+        native = DistributedCG(sa.dev.device_structure, op.mlb, sa.slabs, 0, Minv)
+
     def solve(b):
-        x, _it, _hist = cg(lambda v: op._t(op.matvec(v)).clone(), to_t(b.ravel()), M=prec, rtol=rtol, maxiter=maxiter)
+        if native is not None:
+            x, it, res = native.solve(be.from_host(np.ascontiguousarray(b.ravel())), rtol=rtol, maxiter=maxiter, check_every=10)
+            if res > rtol:
+                print('WARNING: project_L2 - CG did not converge (relative residual %.2e after %d iterations)' % (res, it))
+            return be.to_host(x).reshape(b.shape)
+        x, it, hist = cg(lambda v: op._t(op.matvec(v)).clone(), to_t(b.ravel()), M=prec, rtol=rtol, maxiter=maxiter)
+        if hist and hist[-1] > rtol:        # the reference prints a warning as well (pyiga/approx.py:94-95)
+            print('WARNING: project_L2 - CG did not converge (relative residual %.2e after %d iterations)' % (hist[-1], it))
         return (np.asarray(x.cpu()) if hasattr(x, 'cpu') else np.asarray(x)).reshape(b.shape)
     if extra == ():
         return solve(rhs)

@@ -226,6 +226,25 @@ def inner_products(kvs, f, f_physical=False, geo=None):
     if geo is None:
         geo = _default_geo(kvs)
     name = 'L2FunctionalAssembler%s%dD' % ('Phys' if f_physical else '', dim)
+    if not hasattr(f, 'grid_eval'):
+        # vector- or tensor-valued f: the reference returns ndofs + f's shape (``pyiga/assemble.py:318-340``);
+        # one load vector per component, stacked on the trailing axes
+        from . import utils
+        mid = [np.array([0.5 * (kv.support()[0] + kv.support()[1])]) for kv in kvs]
+        probe = np.asarray(utils.grid_eval_transformed(f, mid, geo) if f_physical else utils.grid_eval(f, mid))
+        extra = probe.shape[dim:]
+        if extra != ():
+            def component(idx):
+                def fc(*x):
+                    v = f(*x)
+                    if isinstance(v, tuple):
+                        for i in idx:
+                            v = v[i]
+                        return v
+                    return v[(Ellipsis,) + idx]
+                return fc
+            parts = [np.asarray(getattr(assemblers, name)(kvs, geo, component(idx)).assemble_vector()) for idx in np.ndindex(*extra)]
+            return np.stack(parts, axis=-1).reshape(parts[0].shape + extra)
     return getattr(assemblers, name)(kvs, geo, f).assemble_vector()
 
 

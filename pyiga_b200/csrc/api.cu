@@ -1956,6 +1956,20 @@ extern "C" int pb200_csr_pattern_host(int nlevels, const int* rows, const int* c
 }
 
 // ---- CSR utilities (csr.cuh) ---------------------------------------------------------------------
+// Entry points that take only device pointers (no handle that knows its device): launch on the device
+// the data lives on, whatever the caller's current device is.
+static int use_device_of(const void* d_ptr) {
+#ifndef PB_EMULATE
+    if (!d_ptr) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, d_ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) CK(cudaSetDevice(at.device));
+    else cudaGetLastError();
+#else
+    (void)d_ptr;
+#endif
+    return 0;
+}
+
 extern "C" int pb200_csr_restrict_workspace(long long nrows_new, int idx_bytes, size_t* bytes) {
     if (!bytes || nrows_new < 0 || (idx_bytes != 4 && idx_bytes != 8)) return fail(PB200_EINVAL, "invalid argument");
 #ifdef PB_EMULATE
@@ -1995,6 +2009,7 @@ extern "C" int pb200_csr_restrict_count(long long nrows_new, const int32_t* d_ro
                                         void* d_indptr_new, void* d_work, size_t work_bytes, void* stream) {
     if (nrows_new < 0 || !d_indptr || !d_colmap || !d_indptr_new || (nrows_new > 0 && !d_rows))
         return fail(PB200_EINVAL, "null argument");
+    if (int e = use_device_of(d_indptr)) return e;
     size_t need = 0;
     int rc = pb200_csr_restrict_workspace(nrows_new, idx_bytes, &need);
     if (rc) return rc;
@@ -2032,6 +2047,7 @@ extern "C" int pb200_csr_restrict_fill(long long nrows_new, const int32_t* d_row
                                        double* d_values_new, void* stream) {
     if (nrows_new < 0 || !d_indptr || !d_colmap || !d_indptr_new) return fail(PB200_EINVAL, "null argument");
     if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
+    if (int e = use_device_of(d_indptr)) return e;
     pbStream st = (pbStream)stream;
     if (idx_bytes == 4)
         return csr_restrict_fill<int>(nrows_new, d_rows, (const int*)d_indptr, (const int*)d_indices, d_values, d_colmap,
@@ -2063,6 +2079,7 @@ extern "C" int pb200_csr_matvec(long long nrows, const void* d_indptr, const voi
                                 void* stream) {
     if (nrows < 0 || !d_indptr || !d_x || !d_y_out) return fail(PB200_EINVAL, "null argument");
     if (idx_bytes != 4 && idx_bytes != 8) return fail(PB200_EINVAL, "idx_bytes must be 4 or 8");
+    if (int e = use_device_of(d_indptr)) return e;
     pbStream st = (pbStream)stream;
     if (idx_bytes == 4)
         return csr_matvec<int>(nrows, (const int*)d_indptr, (const int*)d_indices, d_values, d_x, d_y_in, alpha, d_y_out, st);
@@ -2072,6 +2089,7 @@ extern "C" int pb200_csr_matvec(long long nrows, const void* d_indptr, const voi
 
 extern "C" int pb200_vec_gather(long long n, const int32_t* d_idx, const double* d_in, double* d_out, void* stream) {
     if (n < 0 || (n > 0 && (!d_idx || !d_in || !d_out))) return fail(PB200_EINVAL, "null argument");
+    if (int e = use_device_of(d_out)) return e;
     ++g_launches;
 #ifdef PB_EMULATE
     (void)stream;
@@ -2088,6 +2106,7 @@ extern "C" int pb200_vec_gather(long long n, const int32_t* d_idx, const double*
 
 extern "C" int pb200_vec_scatter(long long n, const int32_t* d_idx, const double* d_in, double* d_out, void* stream) {
     if (n < 0 || (n > 0 && (!d_idx || !d_in || !d_out))) return fail(PB200_EINVAL, "null argument");
+    if (int e = use_device_of(d_out)) return e;
     ++g_launches;
 #ifdef PB_EMULATE
     (void)stream;
@@ -2105,6 +2124,7 @@ extern "C" int pb200_vec_scatter(long long n, const int32_t* d_idx, const double
 extern "C" int pb200_kron_matvec(int d, const double* const* d_factors, const int* rows, const int* cols,
                                  const double* d_x, double* d_y, double* d_tmp, void* stream) {
     if (d < 1 || d > 8 || !d_factors || !rows || !cols || !d_x || !d_y) return fail(PB200_EINVAL, "invalid argument");
+    if (int e = use_device_of(d_y)) return e;
     // apply the factors from the last axis to the first; intermediate shape: (rows[0..k-1] ; cols[k..])
     long long maxsz = 1;
     {
@@ -2134,6 +2154,7 @@ extern "C" int pb200_basis_eval(const double* d_knots, int nknots, int p, const 
     if (p < 0 || p > PB_MAXP) return fail(PB200_EUNSUPPORTED, "spline degree %d above the supported maximum %d", p, PB_MAXP);
     if (nderiv < 0 || nderiv > 2) return fail(PB200_EUNSUPPORTED, "derivatives up to order 2 are supported");
     if (m <= 0) return 0;
+    if (int e = use_device_of(d_values)) return e;
     k_basis(d_knots, nknots, p, d_nodes, m, nderiv + 1, d_first, d_values, (pbStream)stream);
     CK(pbLastError());
     return 0;

@@ -35,6 +35,9 @@ class SlabAssembly:
 
     def __init__(self, kvs, geo, form, rank=0, world=1, nqp=None):
         from . import _lib, assemblers
+        n0 = tuple(kvs)[0].numdofs
+        if world > n0:
+            raise ValueError('cannot shard %d rows of the first tensor axis over %d ranks' % (n0, world))
         self.form = {'mass': _lib.FORM_MASS, 'stiffness': _lib.FORM_STIFFNESS}[form]
         self.geo = geo
         self.dev = assemblers.DeviceAssembler(tuple(kvs), None, self.form, nqp=nqp)

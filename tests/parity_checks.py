@@ -951,6 +951,20 @@ def check_large_full(name):
 # native slab-distributed CG (csrc/distcg.cuh): halo, dot products and the preconditioner's gather
 # through peer-mapped windows
 # ---------------------------------------------------------------------------------------------
+def check_inner_products_vector_valued():
+    """inner_products with a vector-valued f returns ndofs + (k,) like the reference (pyiga/assemble.py:318-340)"""
+    from pyiga_b200 import assemble, bspline, geometry
+    kvs = (bspline.make_knots(2, 0.0, 1.0, 4), bspline.make_knots(3, 0.0, 1.0, 3))
+    geo = geometry.quarter_annulus()
+    for phys in (False, True):
+        g = geo if phys else None
+        V = assemble.inner_products(kvs, lambda x, y: (x * y, 1.0 + x), f_physical=phys, geo=g)
+        a = assemble.inner_products(kvs, lambda x, y: x * y, f_physical=phys, geo=g)
+        b = assemble.inner_products(kvs, lambda x, y: 1.0 + x + 0.0 * y, f_physical=phys, geo=g)
+        assert V.shape == a.shape + (2,)
+        assert np.abs(V[..., 0] - a).max() <= 1e-15 and np.abs(V[..., 1] - b).max() <= 1e-15
+
+
 def check_native_distributed_cg(world=1, rank=0, p=2, n=(7, 4, 5), rtol=1e-11):
     """mass matrix on the rational twisted box, b = M x*, Kronecker preconditioner of the inverse 1D
     mass matrices (pyiga/approx.py:82-93): the distributed matvec equals the slab of M p, the solve

@@ -201,3 +201,7 @@ def test_hierarchical_discretization(emu, monkeypatch):
 
 def test_entry_func_ptr(emu):
     pc.check_entry_func_ptr()
+
+
+def test_inner_products_vector_valued(emu):
+    pc.check_inner_products_vector_valued()

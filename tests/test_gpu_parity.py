@@ -280,3 +280,7 @@ def test_hierarchical_discretization(cuda, monkeypatch):
 
 def test_entry_func_ptr(cuda):
     pc.check_entry_func_ptr()
+
+
+def test_inner_products_vector_valued(cuda):
+    pc.check_inner_products_vector_valued()
