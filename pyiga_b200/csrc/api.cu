@@ -1102,7 +1102,7 @@ static bool fused_stage1(const pb200_assembler* a) {
     if (a->form != PB200_FORM_STIFFNESS && a->form != PB200_FORM_MASS) return false;
     if (!a->lane_ok[0] || !a->walk_rot) return false;           // rotating-window walk on axis 0
     const PbGeoDev& g = a->geo_dev;
-    if (g.dim != 3 || g.sdim != 3 || g.Ng[0] * g.nc * 3 > PB_GEO_ZMAX) return false;
+    if (g.dim != 3 || g.sdim != 3 || g.Ng[0] * ((g.nc * 3 + 1) & ~1) > PB_GEO_ZMAX) return false;
     const AxisHost& H = a->hax[0];
     const int P = H.U.p, Q = H.q;
     if (P > 3) return false;        // the 6 x (p+1)^2 window of degree 4 does not fit the register file (ptxas: spills)
@@ -1110,7 +1110,7 @@ static bool fused_stage1(const pb200_assembler* a) {
     // staged tables of the whole axis (slabs and pieces are shorter) next to the Z columns
     const size_t nodes = (size_t)H.G;
     const size_t smem = nodes * 2 * (P + 1) * 8 + ((size_t)H.n + 4 + (size_t)H.V.N() * (2 * P + 1)) * 4
-                        + nodes * (2 * (g.pg[0] + 1) + 1) * 8 + nodes * 4 + ((size_t)g.Ng[0] * g.nc * 3 + (size_t)std::max(Q * 6, (P + 1) * 6)) * 128 * 8 + 1024;
+                        + nodes * (2 * (g.pg[0] + 1) + 1) * 8 + nodes * 4 + ((size_t)g.Ng[0] * ((g.nc * 3 + 1) & ~1) + (size_t)std::max(Q * 6, (P + 1) * 6) + 2) * 128 * 8 + 1024;
     return smem <= 113 * 1024;
 }
 

@@ -403,6 +403,8 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                 double D[2][P1];
 #pragma unroll
                 for (int a = 0; a < P1; ++a) { D[0][a] = Vn[a]; D[1][a] = Vn[P1 + a]; }
+                double xn[NOPS];
+                ld.get_node(gq, xn);
                 pb_static_for<0, NOUT>([&](auto O) {
                     constexpr int o = decltype(O)::value;
                     constexpr bool by_fu = pb_group_by_fu<Plan>(o);
@@ -417,7 +419,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                                 constexpr PbOp op = Plan::op(i);
                                 if constexpr (op.out == o && (by_fu ? op.fu : op.ft) == fl) {
                                     constexpr int other = by_fu ? op.ft : op.fu;
-                                    const double xv = ld.template get<i>(gq);
+                                    const double xv = xn[i];
                                     if constexpr (i == lead) {
 #pragma unroll
                                         for (int c = 0; c < P1; ++c) y[c] = D[other][c] * xv;

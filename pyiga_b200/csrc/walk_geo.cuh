@@ -22,6 +22,15 @@
 
 #define PB_GEO_ZMAX 60
 
+// Thread-private columns in shared memory are laid out in PAIRS: element e of the column of a thread
+// sits at ((e >> 1) * stride) * 2 + (e & 1), stride counted in pairs (128 on the device: the pairs of
+// the 128 threads of a block are contiguous, so that a 16-byte access per thread is conflict-free;
+// 1 in the sequential emulation).  Even / odd neighbours are read with one 128-bit load.
+PB_HD long long pb_col(int e, int stride) { return (long long)(e >> 1) * 2 * stride + (e & 1); }
+PB_HD double2 pb_col_pair(const double* col, int e_even, int stride) {
+    return *reinterpret_cast<const double2*>(col + (long long)(e_even >> 1) * 2 * stride);
+}
+
 struct PbGeoLineParams {
     PbGeoDev geo;
     const double* gw[PB_MAXDIM];    // Gauss weights per axis
@@ -31,6 +40,8 @@ struct PbGeoLineParams {
 template <class Plan, int Q, int NC, class Prog>
 struct PbGeoLoader {
     static constexpr int NOPS = Plan::NOPS;
+    static constexpr int ZI = (NC * 3 + 1) & ~1;        // doubles per control point of the reduced net (padded to pairs)
+    static constexpr int NOPSP = (NOPS + 1) & ~1;       // staged fields per node (padded to pairs)
     static constexpr bool ROLLED = true;    // the walk asks for the inputs node by node (compact code)
     // members the walk fills for memory loaders; unused here
     const double* src[NOPS];
@@ -38,7 +49,7 @@ struct PbGeoLoader {
     long long sc;
     int s_end;
     // geometry of the line
-    const double* Z;        // Z[((i0 * NC + c) * 3 + v) * zs]
+    const double* Z;        // element i0 * ZI + c * 3 + v of the thread's column (pb_col)
     int zs;
     int pg0;
     const double* T0;       // [g0][2][pg0+1]   indexed by absolute node (possibly a staged slice)
@@ -87,20 +98,31 @@ struct PbGeoLoader {
             }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                Zbuf[(long long)((i0 * NC + c) * 3 + 0) * zstride] = s0[c];
-                Zbuf[(long long)((i0 * NC + c) * 3 + 1) * zstride] = s1[c];
-                Zbuf[(long long)((i0 * NC + c) * 3 + 2) * zstride] = s2[c];
+                Zbuf[pb_col(i0 * ZI + c * 3 + 0, zstride)] = s0[c];
+                Zbuf[pb_col(i0 * ZI + c * 3 + 1, zstride)] = s1[c];
+                Zbuf[pb_col(i0 * ZI + c * 3 + 2, zstride)] = s2[c];
             }
         }
     }
 
     PB_HD void prime(int) {}
     PB_HD void next(int, double (&)[Q][NOPS]) {}        // unrolled interface of the walk: not used (ROLLED)
-    template <int I> PB_HD double get(int gq) const { return F[(long long)(gq * NOPS + I) * fs]; }
+    template <int I> PB_HD double get(int gq) const { return F[pb_col(gq * NOPSP + I, fs)]; }
+    // all inputs of node gq with 128-bit loads
+    PB_HD void get_node(int gq, double (&x)[NOPS]) const {
+#pragma unroll
+        for (int k = 0; k < NOPSP / 2; ++k) {
+            const double2 v = pb_col_pair(F, gq * NOPSP + 2 * k, fs);
+            x[2 * k] = v.x;
+            if (2 * k + 1 < NOPS) x[2 * k + 1] = v.y;
+        }
+    }
     // the same column stages finished window entries between the phase-specific code and the store loop
-    PB_HD void stage_put(int e, double v) { F[(long long)e * fs] = v; }
-    PB_HD double stage_get(int e) const { return F[(long long)e * fs]; }
-    static constexpr int stage_doubles(int P) { return (Q * NOPS > (P + 1) * Plan::NOUT) ? Q * NOPS : (P + 1) * Plan::NOUT; }
+    PB_HD void stage_put(int e, double v) { F[pb_col(e, fs)] = v; }
+    PB_HD double stage_get(int e) const { return F[pb_col(e, fs)]; }
+    static constexpr int stage_doubles(int P) {
+        return ((Q * NOPSP > (P + 1) * Plan::NOUT ? Q * NOPSP : (P + 1) * Plan::NOUT) + 1) & ~1;
+    }
 
     // evaluate the fields of the Q nodes of span s into the staging column
     PB_HD void begin_span(int s) {
@@ -112,28 +134,29 @@ struct PbGeoLoader {
             const int f0 = F0[g0];
             const double* Tn = T0 + (long long)g0 * 2 * (pg0 + 1);
             double val[NC], dv[NC][3];
-            {   // first active function assigns (no zero-fill of the 4 NC accumulators), the others accumulate
-                const double w = Tn[0], d = Tn[pg0 + 1];
-                const double* z = Z + (long long)(f0 * NC * 3) * zs;
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const double z0 = z[(c * 3 + 0) * zs], z1 = z[(c * 3 + 1) * zs], z2 = z[(c * 3 + 2) * zs];
-                    val[c] = w * z0;
-                    dv[c][0] = d * z0;          // derivative along tensor axis 0
-                    dv[c][1] = w * z1;
-                    dv[c][2] = w * z2;
-                }
-            }
-            for (int a = 1; a <= pg0; ++a) {
+            for (int a = 0; a <= pg0; ++a) {
                 const double w = Tn[a], d = Tn[pg0 + 1 + a];
-                const double* z = Z + (long long)((f0 + a) * NC * 3) * zs;
+                double z[ZI];
+#pragma unroll
+                for (int k = 0; k < ZI / 2; ++k) {          // the control point's ZI values, 128 bits at a time
+                    const double2 v = pb_col_pair(Z, (f0 + a) * ZI + 2 * k, zs);
+                    z[2 * k] = v.x;
+                    z[2 * k + 1] = v.y;
+                }
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const double z0 = z[(c * 3 + 0) * zs], z1 = z[(c * 3 + 1) * zs], z2 = z[(c * 3 + 2) * zs];
-                    val[c] = fma(w, z0, val[c]);
-                    dv[c][0] = fma(d, z0, dv[c][0]);
-                    dv[c][1] = fma(w, z1, dv[c][1]);
-                    dv[c][2] = fma(w, z2, dv[c][2]);
+                    const double z0 = z[c * 3 + 0], z1 = z[c * 3 + 1], z2 = z[c * 3 + 2];
+                    if (a == 0) {       // first active function assigns (no zero-fill of the accumulators)
+                        val[c] = w * z0;
+                        dv[c][0] = d * z0;          // derivative along tensor axis 0
+                        dv[c][1] = w * z1;
+                        dv[c][2] = w * z2;
+                    } else {
+                        val[c] = fma(w, z0, val[c]);
+                        dv[c][0] = fma(d, z0, dv[c][0]);
+                        dv[c][1] = fma(w, z1, dv[c][1]);
+                        dv[c][2] = fma(w, z2, dv[c][2]);
+                    }
                 }
             }
             PbPoint pt;
@@ -157,7 +180,7 @@ struct PbGeoLoader {
             Prog::template point<RAT, true>(pt, f);
             pb_static_for<0, NOPS>([&](auto I) {
                 constexpr int i = decltype(I)::value;
-                F[(long long)(gq * NOPS + i) * fs] = f[Plan::field(i)];
+                F[pb_col(gq * NOPSP + i, fs)] = f[Plan::field(i)];
             });
         }
     }
@@ -166,7 +189,8 @@ struct PbGeoLoader {
 // sequential emulation of one line
 template <class Plan, int P, int Q, int NC, class Prog>
 PB_HD void pb_walk_geo_line(const PbWalkParams& prm, const PbGeoLineParams& gp, long long tid, int piece) {
-    double Zloc[PB_GEO_ZMAX], Floc[PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P)];
+    alignas(16) double Zloc[PB_GEO_ZMAX + 8];
+    alignas(16) double Floc[PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P)];
     PbGeoLoader<Plan, Q, NC, Prog> ld;
     ld.init(gp, (int)(tid % prm.X), Zloc, 1);
     ld.F = Floc; ld.fs = 1;
@@ -196,7 +220,7 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_geo_kernel(const __grid_con
     __shared__ __align__(8) uint64_t bar;
     const PbWalkRange rg = pb_walk_range(prm, blockIdx.y);
     const int pg0 = gp.geo.pg[0];
-    const int nz = gp.geo.Ng[0] * NC * 3 + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P);
+    const int nz = gp.geo.Ng[0] * PbGeoLoader<Plan, Q, NC, Prog>::ZI + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P);
     size_t vbytes, ibytes, gbytes, zbytes;
     pb_walk_geo_smem<P, Q>(rg, pg0, nz, vbytes, ibytes, gbytes, zbytes);
     const long long first_node = (long long)rg.s_begin * Q;
@@ -259,8 +283,8 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_geo_kernel(const __grid_con
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < prm.nthreads) {
         PbGeoLoader<Plan, Q, NC, Prog> ld;
-        ld.init(gp, (int)(tid % prm.X), sZ + threadIdx.x, 128);
-        ld.F = sZ + (size_t)gp.geo.Ng[0] * NC * 3 * 128 + threadIdx.x;
+        ld.init(gp, (int)(tid % prm.X), sZ + 2 * threadIdx.x, 128);
+        ld.F = sZ + (size_t)gp.geo.Ng[0] * PbGeoLoader<Plan, Q, NC, Prog>::ZI * 128 + 2 * threadIdx.x;
         ld.fs = 128;
         ld.T0 = sT0 - first_node * 2 * (pg0 + 1);
         ld.W0 = sW0 - first_node;

@@ -124,7 +124,7 @@ int launch_geo_nc(const PbWalkParams* prm, const PbGeoLineParams& gp, int use_sm
     size_t smem = 0;
     for (int y = 0; y < ny; ++y) {
         size_t vb, ib, gb, zb;
-        pb_walk_geo_smem<PB_P, PB_Q>(pb_walk_range(*prm, y), gp.geo.pg[0], gp.geo.Ng[0] * NC * 3 + PbGeoLoader<Plan, PB_Q, NC, Prog>::stage_doubles(PB_P), vb, ib, gb, zb);
+        pb_walk_geo_smem<PB_P, PB_Q>(pb_walk_range(*prm, y), gp.geo.pg[0], gp.geo.Ng[0] * PbGeoLoader<Plan, PB_Q, NC, Prog>::ZI + PbGeoLoader<Plan, PB_Q, NC, Prog>::stage_doubles(PB_P), vb, ib, gb, zb);
         smem = std::max(smem, vb + ib + gb + zb);
     }
     if (use_smem < 0) {     // query: resident blocks per SM
@@ -144,7 +144,7 @@ int launch_geo_nc(const PbWalkParams* prm, const PbGeoLineParams& gp, int use_sm
 template <class Plan, class Prog>
 int launch_geo(const PbWalkParams* prm, int use_smem, size_t, void* stream) {
     const PbGeoLineParams* gp = static_cast<const PbGeoLineParams*>(prm->geo_line);
-    if (!gp || gp->geo.Ng[0] * gp->geo.nc * 3 > PB_GEO_ZMAX) return 1;      // cudaErrorInvalidValue
+    if (!gp || gp->geo.Ng[0] * ((gp->geo.nc * 3 + 1) & ~1) > PB_GEO_ZMAX) return 1;      // cudaErrorInvalidValue
     return gp->geo.nc == 4 ? launch_geo_nc<Plan, Prog, 4>(prm, *gp, use_smem, stream)
                            : launch_geo_nc<Plan, Prog, 3>(prm, *gp, use_smem, stream);
 }
