@@ -284,3 +284,31 @@ def test_entry_func_ptr(cuda):
 
 def test_inner_products_vector_valued(cuda):
     pc.check_inner_products_vector_valued()
+
+
+@pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
+@pytest.mark.parametrize('p,ns,split', [(1, (3, 5, 70), None), (2, (3, 4, 66), None), (3, (2, 9, 40), None),
+                                        (3, (3, 36, 35), 2), (2, (4, 40, 33), 3), (3, (3, 3, 33), 4)])
+def test_fused_pipeline_shapes(cuda, form, p, ns, split):
+    """the fused kernels against the oracle on shapes that exercise several 32-span batches of the last
+    axis (with the shorter last batch), the axis-1 pieces and degrees 1..3; every case is also run
+    through the unfused round-1 pipeline (fuse = fuse23 = 0), which must agree"""
+    asm = pc.check_vs_oracle(3, (p, p, p), ns, form, walk_split=split)
+    assert asm.dev.uses_fused_fields()
+    fused = cuda.to_host(asm.dev.assemble_mlb())
+    asm.dev.set_option('fuse', 0)
+    asm.dev.set_option('fuse23', 0)
+    plain = cuda.to_host(asm.dev.assemble_mlb())
+    assert np.abs(fused - plain).max() <= 1e-13 * np.abs(plain).max()
+
+
+def test_fused_fallbacks(cuda):
+    """configurations outside the fused kernels' domain take the unfused pipeline and stay correct: mixed
+    degrees on axes 1 and 2, repeated knots, degree 4, B-spline geometry with a long control net"""
+    from pyiga_b200 import assemblers, bspline, geometry
+    a = pc.check_vs_oracle(3, (3, 2, 3), (3, 5, 4), 'Stiffness')            # mixed degrees: no fused stages 2+3
+    b = pc.check_vs_oracle(3, (2, 2, 2), (3, 2, 12), 'Stiffness', mult=2)   # repeated knots
+    c = pc.check_vs_oracle(3, (4, 4, 4), (3, 3, 4), 'Mass')                 # degree 4
+    assert not c.dev.uses_fused_fields()
+    for asm in (a, b, c):
+        assert asm.dev.fast_path
