@@ -1129,8 +1129,12 @@ static void fill_s32_axes(const pb200_assembler* a, PbS32Params& p) {
 }
 static bool fused_stage23(const pb200_assembler* a) {
     if (!a->fuse23 || a->dim != 3 || a->arity != 2 || !a->fast || a->force_walk) return false;
-    if (a->form != PB200_FORM_STIFFNESS && a->form != PB200_FORM_MASS) return false;
-    if (!(a->mirror_opt && a->symmetric && a->same_space)) return false;
+    if (a->form == PB200_FORM_CUSTOM) {
+        if (!a->same_space) return false;       // general forms: no symmetry is used, every band entry is computed
+    } else {
+        if (a->form != PB200_FORM_STIFFNESS && a->form != PB200_FORM_MASS) return false;
+        if (!(a->mirror_opt && a->symmetric && a->same_space)) return false;
+    }
     if (!a->lane_ok[1] || !a->lane_ok[2] || !a->walk_rot) return false;
     const AxisHost &H1 = a->hax[1], &H2 = a->hax[2];
     if (H1.U.p != H2.U.p || H1.q != H2.q) return false;
@@ -1186,6 +1190,7 @@ static void stage_sizes(const pb200_assembler* a, const Slab& S, size_t& x1_term
         x1_stride = Mext * a->hax[1].G * (a->dim == 3 ? a->hax[2].G : 1);
         x2_terms = a->dim == 3 ? stages[1].out.size() : 0;
         x2_stride = a->dim == 3 ? Mext * a->hax[1].M * a->hax[2].G : 0;
+        if (a->dim == 3 && fused_stage23(a)) { x2_terms = 0; x2_stride = 0; }
         return;
     }
     if (a->dim == 2) {
@@ -1438,6 +1443,49 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         const int dim = a->dim;
         const long long Glast = dim == 3 ? a->hax[2].G : 1;
         for (int k = 0; k < dim; ++k) {
+            if (k == 1 && fuse23) {
+                // stages 2 + 3 in one kernel (fused23.cuh, PbS32Generic): input stream 3 * test + trial reads
+                // the X1 term whose remaining slots are (test, trial) in {v, d1, d2}
+                PbS32Params q;
+                memset(&q, 0, sizeof q);
+                fill_s32_axes(a, q);
+                for (int i = 0; i < 9; ++i) q.in_slot[i] = -1;
+                auto code = [](int slot) { return slot == 0 ? 0 : slot - 1; };         // v -> 0, d1 (slot 2) -> 1, d2 (slot 3) -> 2
+                for (const GenTerm& t : stages[0].out) q.in_slot[3 * code(t.bt) + code(t.bu)] = t.slot;
+                q.X1 = X1; q.x1_stride = (long long)s1; q.x1_mu_base = S.mu_lo;
+                q.mu0_begin = S.mu_lo; q.mu0_count = Mrows;
+                q.u_lo = S.ra; q.u_hi = S.rb;
+                q.symmetric = 0;
+                q.out = d_out; q.out_mu_base = S.mu_lo;
+                q.nbatch = pb_lane_batches(a->hax[2].n, a->hax[2].U.p);
+                const long long tasks = (long long)Mrows * q.nbatch;
+                const int P = H1.U.p, nsp = H1.n, N1 = H1.V.N();
+                int K = 1;
+                if (a->walk_split > 1) K = std::min(a->walk_split, 4);
+                else if (a->walk_split == 0 && a->sm_count > 0 && tasks > 0) {
+                    double best = (double)((tasks + a->sm_count - 1) / a->sm_count) * nsp;
+                    for (int kk = 2; kk <= 4; ++kk) {
+                        if (nsp / kk < 4 * (P + 1)) break;
+                        const double cost = (double)((kk * tasks + a->sm_count - 1) / a->sm_count) * ((double)nsp / kk + P + 2);
+                        if (cost < 0.95 * best) { best = cost; K = kk; }
+                    }
+                }
+                K = std::min(K, N1);
+                if (K > 1) {
+                    q.npiece = K;
+                    for (int y = 0; y < K; ++y) {
+                        const int lo = (int)((long long)N1 * y / K), hi = (int)((long long)N1 * (y + 1) / K);
+                        q.pw_lo[y] = lo; q.pw_hi[y] = hi;
+                        q.ps_begin[y] = H1.V.supp[2 * lo];
+                        q.ps_end[y] = H1.V.supp[2 * (hi - 1) + 1];
+                    }
+                }
+                mark_stage(a, "g23", st);
+                ++g_launches;
+                int e = pb_find_s32(PB200_FORM_CUSTOM, H1.U.p, H1.q)(&q, st);
+                if (e) return fail(PB200_ECUDA, "fused stage 2+3 launch failed: %s", pbErrorString((pbError)e));
+                break;
+            }
             const GenStage& G = stages[k];
             const bool last = (k == dim - 1);
             for (size_t o = 0; o < G.out.size(); ++o) {

@@ -59,6 +59,8 @@ struct PbS32Params {
     // those rows see; the pieces overlap by p spans (same scheme as the walk-axis pieces of walk.cuh)
     int npiece;
     int ps_begin[4], ps_end[4], pw_lo[4], pw_hi[4];
+    // ---- generic forms (PbS32Generic): X1 term read by input stream i, or -1 when the form has no such term ----
+    int in_slot[9];
 };
 struct PbS32Piece { int s_begin, s_end, w_lo, w_hi; };
 PB_HD PbS32Piece pb_s32_piece(const PbS32Params& prm, int y) {
@@ -84,6 +86,7 @@ template <> struct PbS32StiffTerm<2> { using Plan = PbPlanPairU; static constexp
 template <> struct PbS32StiffTerm<3> { using Plan = PbPlanCopy; static constexpr int stream(int) { return 7; } };
 struct PbS32Stiffness {
     static constexpr int NIN = 8, NT = 4;
+    static constexpr bool RUNTIME = false;
     static constexpr int in_term(int i) {       // X1 term read by input stream i
         constexpr int t[8] = {0, 2, 2, 5, 1, 4, 1, 3};
         return t[i];
@@ -95,11 +98,34 @@ struct PbS32Stiffness {
 template <int T> struct PbS32MassTerm { using Plan = PbPlanCopy; static constexpr int stream(int) { return 0; } };
 struct PbS32Mass {
     static constexpr int NIN = 1, NT = 1;
+    static constexpr bool RUNTIME = false;
     static constexpr int in_term(int) { return 0; }
     static constexpr bool in_tr(int) { return false; }
     template <int T> using Term = PbS32MassTerm<T>;
     using PlanB = PbPlanCopy;
 };
+
+// General scalar forms with at most first derivatives (no symmetry assumed: every band entry mu0 is
+// computed, nothing is mirrored).  After axis 0 an X1 term is named by its remaining slots
+// (test, trial) in {v, d1, d2}; input stream 3 * test + trial reads it (prm.in_slot: its position in the
+// X1 buffer, -1 if the form has no such term).  Terms and flags as for stiffness, with nine distinct inputs:
+//   T0 = [0,0](v,v) + [0,1](v,d2) + [1,0](d2,v) + [1,1](d2,d2)      T1 = [0,0](v,d1) + [1,0](d2,d1)
+//   T2 = [0,0](d1,v) + [0,1](d1,d2)                                 T3 = [0,0](d1,d1)
+template <int T> struct PbS32GenTerm;
+template <> struct PbS32GenTerm<0> { using Plan = PbPlanGen4; static constexpr int stream(int i) { constexpr int s[4] = {0, 2, 6, 8}; return s[i]; } };
+template <> struct PbS32GenTerm<1> { using Plan = PbPlanPairT; static constexpr int stream(int i) { return i == 0 ? 1 : 7; } };
+template <> struct PbS32GenTerm<2> { using Plan = PbPlanPairU; static constexpr int stream(int i) { return i == 0 ? 3 : 5; } };
+template <> struct PbS32GenTerm<3> { using Plan = PbPlanCopy; static constexpr int stream(int) { return 4; } };
+struct PbS32Generic {
+    static constexpr int NIN = 9, NT = 4;
+    static constexpr bool RUNTIME = true;
+    static constexpr int in_term(int i) { return i; }
+    static constexpr bool in_tr(int) { return false; }
+    template <int T> using Term = PbS32GenTerm<T>;
+    using PlanB = PbPlanGen4;
+};
+// X1 term of input stream i (-1: absent, reads as zero)
+template <class Form> PB_HD int pb_s32_slot(const PbS32Params& prm, int i) { return Form::RUNTIME ? prm.in_slot[i] : Form::in_term(i); }
 
 template <int P> struct PbS32Cfg {
     static constexpr int TPAD = ((32 + P) * (2 * P + 1) + 31) / 32 * 32;    // band positions of a batch, padded
@@ -160,9 +186,10 @@ PB_HD void pb_s32_seq(const PbS32Params& prm, int mu0, int batch, int piece, dou
                 for (int gq = 0; gq < Q; ++gq)
                     for (int i = 0; i < TP::NOPS; ++i) {
                         const int st = Form::template Term<t>::stream(i);
-                        const double* src = prm.X1 + (long long)Form::in_term(st) * prm.x1_stride
+                        const int slot = pb_s32_slot<Form>(prm, st);
+                        const double* src = prm.X1 + (long long)slot * prm.x1_stride
                                             + (long long)((Form::in_tr(st) ? mu0t : mu0) - prm.x1_mu_base) * plane + (long long)r * prm.G2;
-                        xt[gq][i] = s < prm.n2 ? src[(long long)s * Q + gq] : 0.0;
+                        xt[gq][i] = (s < prm.n2 && slot >= 0) ? src[(long long)s * Q + gq] : 0.0;
                     }
                 pb_span_block<TP, P, Q>(xt, D, Ls[t][lane]);
             });
@@ -397,18 +424,20 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
         pb_static_for<0, NSTR>([&](auto J) {
             constexpr int j = decltype(J)::value;
             // (both halves are instantiated; select at run time)
-            const int t0 = Form::in_term(j), t1 = Form::in_term((NH - 1) * NSTR + j);
+            const int t0 = pb_s32_slot<Form>(prm, j), t1 = pb_s32_slot<Form>(prm, (NH - 1) * NSTR + j);
             const bool r0 = Form::in_tr(j), r1 = Form::in_tr((NH - 1) * NSTR + j);
             const int term = half == 0 ? t0 : t1;
             const bool trn = half == 0 ? r0 : r1;
-            base[j] = prm.X1 + (long long)term * prm.x1_stride + (long long)((trn ? mu0t : mu0) - prm.x1_mu_base) * plane
-                      + seg_node0 + (long long)prow * prm.G2;
+            base[j] = term < 0 ? nullptr        // the form has no such term: the (zero-filled) ring slot is never written
+                               : prm.X1 + (long long)term * prm.x1_stride + (long long)((trn ? mu0t : mu0) - prm.x1_mu_base) * plane
+                                     + seg_node0 + (long long)prow * prm.G2;
         });
         const long long span_stride = (long long)Q * prm.G2;        // rows of consecutive spans handled by this warp
         auto issue = [&](int s1, int st) {
             double* dst = ring + (size_t)st * STAGE;
             pb_static_for<0, NSTR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
+                if (Form::RUNTIME && base[j] == nullptr) return;
                 const double* src = base[j] + (long long)s1 * span_stride;
 #pragma unroll
                 for (int h = 0; h < NPIECE; ++h) {

@@ -216,6 +216,7 @@ struct Registrar {
 #if PB_Q == PB_P + 1 && PB_P <= 3
         pb200_register_s32(2 /* PB200_FORM_STIFFNESS */, PB_P, PB_Q, &launch_s32<PbS32Stiffness>);
         pb200_register_s32(1 /* PB200_FORM_MASS */, PB_P, PB_Q, &launch_s32<PbS32Mass>);
+        pb200_register_s32(100 /* PB200_FORM_CUSTOM */, PB_P, PB_Q, &launch_s32<PbS32Generic>);
 #endif
         pb200_register_walk(PB_PLAN_S1F, PB_P, PB_Q, &launch_geo<PbPlanS1F, PbProgStiffness<3>>);
         pb200_register_walk(PB_PLAN_S1F_MASS, PB_P, PB_Q, &launch_geo<PbPlanS1FMass, PbProgMass<3>>);

@@ -312,3 +312,19 @@ def test_fused_fallbacks(cuda):
     assert not c.dev.uses_fused_fields()
     for asm in (a, b, c):
         assert asm.dev.fast_path
+
+
+@pytest.mark.parametrize('p,ns,split', [(3, (4, 5, 40), None), (2, (3, 34, 36), 2), (1, (3, 3, 70), None)])
+def test_fused_generic_form(cuda, p, ns, split):
+    """non-symmetric custom forms through the fused stages 2+3 (PbS32Generic) against the unfused pipeline"""
+    from pyiga_b200 import assemble, bspline, geometry
+    form = '(inner(diff_coeff * grad(u), grad(v)) + inner((x[1], -x[0], 1.0), grad(u)) * v + 2.0 * u * v) * dx'
+    kvs = tuple(bspline.make_knots(p, 0.0, 1.0, n) for n in ns)
+    asm = assemble.instantiate_assembler(form, kvs, {'geo': geometry.twisted_box(), 'diff_coeff': lambda x, y, z: 1.0 + x * y}, None)
+    dev = asm.dev
+    if split:
+        dev.set_option('walk_split', split)
+    fused = cuda.to_host(dev.assemble_mlb())
+    dev.set_option('fuse23', 0)
+    plain = cuda.to_host(dev.assemble_mlb())
+    assert np.abs(fused - plain).max() <= 1e-13 * np.abs(plain).max()
