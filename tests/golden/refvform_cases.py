@@ -39,6 +39,9 @@ def cases():
         'aniso2': (aniso2, kv2, geo2, {'A': _A, 'c': 2.5}),
         'divdiv2': (lambda: rvf.divdiv_vf(2), kv2, geo2, {}),
         'l2func2': (lambda: rvf.L2functional_vf(2, physical=True), kv2, geo2, {'f': lambda x, y: x * y + 1.0}),
+        # space-time heat form (pyiga/vform.py:1759-1763; the last coordinate is time)
+        'heat_st2': (lambda: rvf.heat_st_vf(2), kv2, rgeo.unit_square(), {}),
+        'heat_st3': (lambda: rvf.heat_st_vf(3), kv3, geo3, {}),
     }
 
 
