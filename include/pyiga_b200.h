@@ -80,7 +80,10 @@ typedef struct {
 
 /* One term of a custom form:  integral of  C(field) * d^{slot_test} v * d^{slot_trial} u.
  * slot 0 = function value, slot 1+k = derivative along tensor axis k (parametric).
+ * Second and mixed derivatives (the reference's numderiv = 2 slots, pyiga/vform.py:1766-1772):
+ * slot = PB200_SLOT_EXT + d0 + 3*d1 + 9*d2 with d_k in 0..2 the derivative order along tensor axis k.
  * Linear forms (arity 1, load vectors) set slot_trial = -1 in every term. */
+#define PB200_SLOT_EXT 16
 typedef struct { int field, slot_test, slot_trial; } pb200_term;
 
 /* One physical coefficient term of a general first-order scalar form (see

@@ -489,7 +489,9 @@ def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatab
         problem = vform.parse_vf(problem, kvs, args=args, bfuns=bfuns, boundary=bool(boundary), updatable=updatable)
     from . import refvform, vform as _vf
     num_spaces = 1
-    if isinstance(problem, _vf.VForm) or refvform.is_reference_vform(problem):
+    if isinstance(problem, _vf._SpaceTimeForm):
+        problem = _vf.compile_vform(problem)
+    elif isinstance(problem, _vf.VForm) or refvform.is_reference_vform(problem):
         num_spaces = problem.num_spaces()
         problem = _vf.compile_vform(problem)
     if isinstance(problem, type):

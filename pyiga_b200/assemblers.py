@@ -998,3 +998,14 @@ class DivDivAssembler2D(_DivDivBase):
 
 class DivDivAssembler3D(_DivDivBase):
     _dim = 3
+
+
+_SPACETIME = ('HeatAssembler_ST2D', 'HeatAssembler_ST3D', 'WaveAssembler_ST2D', 'WaveAssembler_ST3D')
+
+
+def __getattr__(name):
+    # the space-time classes of the reference's predefined set live in .spacetime (which imports this module)
+    if name in _SPACETIME:
+        from . import spacetime
+        return getattr(spacetime, name)
+    raise AttributeError('module %r has no attribute %r' % (__name__, name))

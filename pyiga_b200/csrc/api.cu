@@ -404,6 +404,9 @@ struct pb200_assembler {
     bool fuse23 = true;                                 // 3D mass / stiffness: fused stages 2 + 3 (fused23.cuh), no X2 in HBM
     long long npts = 0, nnz = 0;
     int fast = 0;
+    bool ext_slots = false;                             // some term has a second or mixed derivative slot (PB_SLOT_EXT)
+    const double* walk_table = nullptr;                 // run_stage: table override of the current launch
+    const double* pair_tab[PB_MAXDIM][3] = {};          // two-row tables of derivative orders (0,1) (0,2) (1,2) for the walks
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
     bool lane_v1 = false;                               // use the register-prefetch version of the lane-span kernel
@@ -483,6 +486,7 @@ extern "C" int pb200_asm_get_timing(pb200_assembler* a, int max_stages, float* m
 
 static bool have_plan(int plan, int P, int Q) { return pb_find_walk(plan, P, Q) != nullptr; }
 
+static bool ext_plan_ok(const pb200_assembler* a);
 static int detect_fast_path(const pb200_assembler* a) {
     if (!a->same_space) return 0;
     if (a->form == PB200_FORM_CUSTOM && a->arity == 1) {    // every axis is contracted on its own
@@ -626,10 +630,16 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
         int nlinear = 0;
         for (int t = 0; t < desc->nterms; ++t) {
             const pb200_term& T = desc->terms[t];
-            if (T.field < 0 || T.field >= a->nfields || T.slot_test < 0 || T.slot_test > dim || T.slot_trial < -1 || T.slot_trial > dim)
+            auto slot_ok = [&](int sl) {
+                if (sl >= 0 && sl <= dim) return true;
+                return sl >= PB_SLOT_EXT && sl < PB_SLOT_EXT + (dim == 3 ? 27 : 9);
+            };
+            if (T.field < 0 || T.field >= a->nfields || !slot_ok(T.slot_test) || (T.slot_trial != -1 && !slot_ok(T.slot_trial)))
                 return fail(PB200_EINVAL, "invalid term %d", t);
             nlinear += T.slot_trial < 0;
-            a->terms.push_back(PbTerm{T.field, T.slot_test, T.slot_trial});
+            const int bt = pb_slot_contract(T.slot_test, -1), bu = T.slot_trial < 0 ? -1 : pb_slot_contract(T.slot_trial, -1);
+            a->ext_slots = a->ext_slots || bt >= PB_SLOT_EXT || bu >= PB_SLOT_EXT;
+            a->terms.push_back(PbTerm{T.field, bt, bu});
         }
         if (nlinear != 0 && nlinear != desc->nterms) return fail(PB200_EINVAL, "terms mix linear and bilinear slots");
         a->arity = nlinear ? 1 : 2;
@@ -648,7 +658,7 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
 
     // ---- upload ---------------------------------------------------------------------------------
     CK(pbSetDevice(device));
-    struct Offs { size_t nodes, weights, fu, fv, Vu, Vv, rs, jm, su, sv, pi, pj, tr, ret; } offs[PB_MAXDIM];
+    struct Offs { size_t nodes, weights, fu, fv, Vu, Vv, V3u, V3v, pair02, pair12, rs, jm, su, sv, pi, pj, tr, ret; } offs[PB_MAXDIM];
     Pool& pool = a->pool;
     const int nd = 2;
     for (int k = 0; k < dim; ++k) {
@@ -662,6 +672,30 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
         o.fv = pool.put(H.V.first);
         o.Vu = pool.put(nullptr, (size_t)H.G * nd * (H.U.p + 1) * sizeof(double));
         o.Vv = H.same ? o.Vu : pool.put(nullptr, (size_t)H.G * nd * (H.V.p + 1) * sizeof(double));
+        o.V3u = o.V3v = o.pair02 = o.pair12 = 0;
+        if (a->ext_slots) {
+            // second / mixed derivatives: three-row tables for the per-entry path and two-row tables of the
+            // order pairs (0,2), (1,2) for the walks; small (G rows), computed on the host
+            auto three_rows = [&](const KvHost& Sp) {
+                std::vector<double> T((size_t)H.G * 3 * (Sp.p + 1));
+                for (int g = 0; g < H.G; ++g)
+                    pb_basis_node(Sp.kv.data(), (int)Sp.kv.size(), Sp.p, H.nodes.data(), 3, nullptr, T.data(), g);
+                return T;
+            };
+            const std::vector<double> Tu = three_rows(H.U);
+            o.V3u = pool.put(Tu);
+            o.V3v = H.same ? o.V3u : pool.put(three_rows(H.V));
+            const int w = H.U.p + 1;
+            std::vector<double> P02((size_t)H.G * 2 * w), P12((size_t)H.G * 2 * w);
+            for (int g = 0; g < H.G; ++g)
+                for (int c = 0; c < w; ++c) {
+                    const double* r = &Tu[(size_t)g * 3 * w];
+                    P02[(size_t)g * 2 * w + c] = r[c];     P02[(size_t)g * 2 * w + w + c] = r[2 * w + c];
+                    P12[(size_t)g * 2 * w + c] = r[w + c]; P12[(size_t)g * 2 * w + w + c] = r[2 * w + c];
+                }
+            o.pair02 = pool.put(P02);
+            o.pair12 = pool.put(P12);
+        }
         o.rs = pool.put(H.row_start);
         o.jm = pool.put(H.jmin);
         o.su = pool.put(H.U.supp);
@@ -686,6 +720,11 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
         D.first_v = (const int*)(b + o.fv);
         D.Vu = (const double*)(b + o.Vu);
         D.Vv = (const double*)(b + o.Vv);
+        D.V3u = a->ext_slots ? (const double*)(b + o.V3u) : nullptr;
+        D.V3v = a->ext_slots ? (const double*)(b + o.V3v) : nullptr;
+        a->pair_tab[k][0] = D.Vu;
+        a->pair_tab[k][1] = a->ext_slots ? (const double*)(b + o.pair02) : nullptr;
+        a->pair_tab[k][2] = a->ext_slots ? (const double*)(b + o.pair12) : nullptr;
         D.row_start = (const int*)(b + o.rs);
         D.jmin = (const int*)(b + o.jm);
         D.supp_u = (const int*)(b + o.su);
@@ -699,6 +738,7 @@ extern "C" int pb200_asm_create(const pb200_desc* desc, int device, void* stream
     if (rc) return rc;
     CK(pbStreamSync((pbStream)stream));   // pool.host may be released by the caller's thread later
     a->fast = detect_fast_path(a.get());
+    if (a->fast && a->ext_slots && !ext_plan_ok(a.get())) a->fast = 0;      // the per-entry path serves it
     a->ml.device = device;
     a->ml.dim = dim;
     a->ml.row_start0 = a->hax[0].row_start;
@@ -925,8 +965,8 @@ static int compute_fields_impl(pb200_assembler* a, const pb200_geo_desc* geo, co
     PbFieldParams prm;
     memset(&prm, 0, sizeof prm);
     if (gen) {
-        if (gen->nphys < 1 || gen->nphys > PB_MAXFIELDS || !gen->phys) return fail(PB200_EINVAL, "invalid number of coefficient terms %d", gen->nphys);
-        if (gen->ninputs < 0 || gen->ninputs > PB_MAXFIELDS) return fail(PB200_EINVAL, "invalid number of input arrays %d", gen->ninputs);
+        if (gen->nphys < 1 || gen->nphys > PB_MAXPHYS || !gen->phys) return fail(PB200_EINVAL, "invalid number of coefficient terms %d", gen->nphys);
+        if (gen->ninputs < 0 || gen->ninputs > PB_MAXPHYS) return fail(PB200_EINVAL, "invalid number of input arrays %d", gen->ninputs);
         prm.nphys = gen->nphys;
         for (int t = 0; t < gen->nphys; ++t) {
             const pb200_phys_term& T = gen->phys[t];
@@ -1127,10 +1167,74 @@ static void fill_s32_axes(const pb200_assembler* a, PbS32Params& p) {
     p.first1 = D1.first_u; p.V1 = D1.Vu; p.ret_mu1 = D1.ret_mu; p.tr1 = D1.tr; p.pair_i1 = D1.pair_i;
     p.first2 = D2.first_u; p.V2 = D2.Vu; p.ret_mu2 = D2.ret_mu; p.tr2 = D2.tr;
 }
+// generic forms: a term travels through the stages as (test slot, trial slot, buffer slot)
+struct GenTerm { int bt, bu, slot; };
+struct GenStage {
+    std::vector<GenTerm> out;                    // outputs (slot = index in the stage's output buffer)
+    std::vector<std::array<int, 9>> ops9;        // per output: input slot for derivative orders (test, trial) = 3*ft + fu, or -1
+    std::vector<std::array<int, 4>> ops;         // the same by ROWS (rt, ru) = 2*rt + ru of the two-row table `tab`
+    std::vector<int> tab;                        // per output: table of the orders (0,1) / (0,2) / (1,2) on this axis
+    bool ok = true;                              // false: an output needs all three orders of this axis (no walk for that)
+};
+// rows of the two-row tables: orders {0,1} -> table 0, {0,2} -> table 1, {1,2} -> table 2
+static bool pair_table(unsigned mask, int& tab, int row[3]) {
+    row[0] = row[1] = row[2] = -1;
+    if (!(mask & 4u)) { tab = 0; row[0] = 0; row[1] = 1; return true; }
+    if (!(mask & 2u)) { tab = 1; row[0] = 0; row[2] = 1; return true; }
+    if (!(mask & 1u)) { tab = 2; row[1] = 0; row[2] = 1; return true; }
+    return false;
+}
+// contract `axis`: the derivative order along it leaves the slot
+static GenStage plan_generic_stage(const std::vector<GenTerm>& in, int axis) {
+    GenStage S;
+    for (const GenTerm& t : in) {
+        const int ft = pb_slot_order(t.bt, axis), fu = pb_slot_order(t.bu, axis);
+        const int bt = pb_slot_contract(t.bt, axis), bu = pb_slot_contract(t.bu, axis);
+        size_t o = 0;
+        for (; o < S.out.size(); ++o)
+            if (S.out[o].bt == bt && S.out[o].bu == bu) break;
+        if (o == S.out.size()) {
+            S.out.push_back(GenTerm{bt, bu, (int)o});
+            S.ops9.push_back({-1, -1, -1, -1, -1, -1, -1, -1, -1});
+        }
+        S.ops9[o][ft * 3 + fu] = t.slot;
+    }
+    for (size_t o = 0; o < S.out.size(); ++o) {
+        unsigned mask = 0;
+        for (int c = 0; c < 9; ++c)
+            if (S.ops9[o][c] >= 0) mask |= (1u << (c / 3)) | (1u << (c % 3));
+        int tab = 0, row[3];
+        S.ok = pair_table(mask, tab, row) && S.ok;
+        std::array<int, 4> r4 = {-1, -1, -1, -1};
+        for (int c = 0; c < 9; ++c)
+            if (S.ops9[o][c] >= 0 && row[c / 3] >= 0 && row[c % 3] >= 0) r4[row[c / 3] * 2 + row[c % 3]] = S.ops9[o][c];
+        S.ops.push_back(r4);
+        S.tab.push_back(tab);
+    }
+    return S;
+}
+static bool generic_plan(const pb200_assembler* a, std::vector<GenStage>& stages) {
+    std::vector<GenTerm> cur;
+    bool ok = true;
+    for (const PbTerm& t : a->terms) cur.push_back(GenTerm{t.bt, t.bu, t.field});
+    for (int k = 0; k < a->dim; ++k) {
+        stages.push_back(plan_generic_stage(cur, k));
+        ok = ok && stages.back().ok;
+        cur = stages.back().out;
+    }
+    return ok;
+}
+
 static bool fused_stage23(const pb200_assembler* a) {
     if (!a->fuse23 || a->dim != 3 || a->arity != 2 || !a->fast || a->force_walk) return false;
     if (a->form == PB200_FORM_CUSTOM) {
         if (!a->same_space) return false;       // general forms: no symmetry is used, every band entry is computed
+        if (a->ext_slots) {                     // second / mixed derivatives on axes 1, 2: the unfused walks
+            std::vector<GenStage> stages;
+            generic_plan(a, stages);
+            for (const GenTerm& t : stages[0].out)
+                if (t.bt >= PB_SLOT_EXT || t.bu >= PB_SLOT_EXT) return false;
+        }
     } else {
         if (a->form != PB200_FORM_STIFFNESS && a->form != PB200_FORM_MASS) return false;
         if (!(a->mirror_opt && a->symmetric && a->same_space)) return false;
@@ -1145,38 +1249,6 @@ static bool fused_stage23(const pb200_assembler* a) {
     memset(&q, 0, sizeof q);
     fill_s32_axes(a, q);
     return fn(&q, nullptr) == 0;        // query: shared memory of this configuration fits
-}
-
-// generic forms: a term travels through the stages as (test slot, trial slot, buffer slot)
-struct GenTerm { int bt, bu, slot; };
-struct GenStage {
-    std::vector<GenTerm> out;                    // outputs (slot = index in the stage's output buffer)
-    std::vector<std::array<int, 4>> ops;         // per output: input slot for (ft,fu) = 00,01,10,11 or -1
-};
-// contract `axis`: derivative slot 1+axis turns into the value slot
-static GenStage plan_generic_stage(const std::vector<GenTerm>& in, int axis) {
-    GenStage S;
-    for (const GenTerm& t : in) {
-        const int ft = t.bt == 1 + axis, fu = t.bu == 1 + axis;
-        const int bt = ft ? 0 : t.bt, bu = fu ? 0 : t.bu;
-        size_t o = 0;
-        for (; o < S.out.size(); ++o)
-            if (S.out[o].bt == bt && S.out[o].bu == bu) break;
-        if (o == S.out.size()) {
-            S.out.push_back(GenTerm{bt, bu, (int)o});
-            S.ops.push_back({-1, -1, -1, -1});
-        }
-        S.ops[o][ft * 2 + fu] = t.slot;
-    }
-    return S;
-}
-static void generic_plan(const pb200_assembler* a, std::vector<GenStage>& stages) {
-    std::vector<GenTerm> cur;
-    for (const PbTerm& t : a->terms) cur.push_back(GenTerm{t.bt, t.bu, t.field});
-    for (int k = 0; k < a->dim; ++k) {
-        stages.push_back(plan_generic_stage(cur, k));
-        cur = stages.back().out;
-    }
 }
 
 static void stage_sizes(const pb200_assembler* a, const Slab& S, size_t& x1_terms, size_t& x1_stride, size_t& x2_terms,
@@ -1230,7 +1302,7 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     prm.f_lo = H.U.first[prm.s_begin];
     prm.f_hi = std::min(H.V.N(), H.U.first[prm.s_end - 1] + P + 1);
     prm.first = D.first_u;
-    prm.V2 = D.Vu;
+    prm.V2 = a->walk_table ? a->walk_table : D.Vu;      // generic forms choose the table of the derivative orders they need
     prm.ret_mu = D.ret_mu;
     prm.regular = (a->lane_ok[axis] && a->walk_rot) ? 1 : 0;
     // final stages (node axis contiguous, one output, single interior knots): warp-per-line kernel
@@ -1297,26 +1369,57 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
 // ------------------------------------------------------------------------------------------------
 // linear forms: load vector by three single-function walks
 // ------------------------------------------------------------------------------------------------
-struct Gen1Stage { std::vector<int> out_slot; std::vector<std::array<int, 2>> ops; };   // per output: input for ft = 0 / 1
+struct Gen1Stage {
+    std::vector<int> out_slot;
+    std::vector<std::array<int, 3>> ops3;       // per output: input for test derivative order 0 / 1 / 2 on this axis
+    std::vector<std::array<int, 2>> ops;        // the same by rows of the two-row table `tab`
+    std::vector<int> tab;
+    bool ok = true;
+};
 
-static void plan_linear(const pb200_assembler* a, std::vector<Gen1Stage>& stages) {
+static bool plan_linear(const pb200_assembler* a, std::vector<Gen1Stage>& stages) {
     std::vector<std::pair<int, int>> cur;       // (test slot, buffer slot)
+    bool ok = true;
     for (const PbTerm& t : a->terms) cur.push_back(std::make_pair(t.bt, t.field));
     for (int k = 0; k < a->dim; ++k) {
         Gen1Stage S;
         std::vector<std::pair<int, int>> next;
         for (auto& t : cur) {
-            const int ft = t.first == 1 + k;
-            const int bt = ft ? 0 : t.first;
+            const int ft = pb_slot_order(t.first, k);
+            const int bt = pb_slot_contract(t.first, k);
             size_t o = 0;
             for (; o < S.out_slot.size(); ++o)
                 if (S.out_slot[o] == bt) break;
-            if (o == S.out_slot.size()) { S.out_slot.push_back(bt); S.ops.push_back({-1, -1}); next.push_back(std::make_pair(bt, (int)o)); }
-            S.ops[o][ft] = t.second;
+            if (o == S.out_slot.size()) { S.out_slot.push_back(bt); S.ops3.push_back({-1, -1, -1}); next.push_back(std::make_pair(bt, (int)o)); }
+            S.ops3[o][ft] = t.second;
         }
+        for (size_t o = 0; o < S.out_slot.size(); ++o) {
+            unsigned mask = 0;
+            for (int c = 0; c < 3; ++c)
+                if (S.ops3[o][c] >= 0) mask |= 1u << c;
+            int tab = 0, row[3];
+            S.ok = pair_table(mask, tab, row) && S.ok;
+            std::array<int, 2> r2 = {-1, -1};
+            for (int c = 0; c < 3; ++c)
+                if (S.ops3[o][c] >= 0 && row[c] >= 0) r2[row[c]] = S.ops3[o][c];
+            S.ops.push_back(r2);
+            S.tab.push_back(tab);
+        }
+        ok = ok && S.ok;
         stages.push_back(S);
         cur = next;
     }
+    return ok;
+}
+
+// forms with second / mixed derivatives: every stage output must get by with two derivative orders per axis
+static bool ext_plan_ok(const pb200_assembler* a) {
+    if (a->arity == 1) {
+        std::vector<Gen1Stage> st;
+        return plan_linear(a, st);
+    }
+    std::vector<GenStage> st;
+    return generic_plan(a, st);
 }
 
 extern "C" int pb200_asm_vector_workspace_bytes(const pb200_assembler* a, size_t* bytes) {
@@ -1364,7 +1467,7 @@ extern "C" int pb200_asm_assemble_vector(pb200_assembler* a, double* d_out, void
             p.in1 = stages[k].ops[o][1] >= 0 ? inbase + (long long)stages[k].ops[o][1] * instride : nullptr;
             p.out = outbase + (long long)o * outstride;
             p.n = H.n; p.N = H.V.N();
-            p.first = a->dax[k].first_u; p.V2 = a->dax[k].Vu;
+            p.first = a->dax[k].first_u; p.V2 = a->pair_tab[k][stages[k].tab[o]];
             if (k == 0) {                           // F[g0][g1][g2] -> Y1[i0][g1][g2]
                 p.X = (int)(G1 * G2); p.nthreads = G1 * G2;
                 p.in_sx = 1; p.in_sc = G1 * G2; p.out_sx = 1; p.out_sf = G1 * G2;
@@ -1525,7 +1628,9 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                 const bool copy_only = G.ops[o][1] < 0 && G.ops[o][2] < 0 && G.ops[o][3] < 0;
                 char nm[32];
                 snprintf(nm, sizeof nm, "g%d_%s%d", k + 1, copy_only ? "copy" : "gen", (int)o);
+                a->walk_table = a->pair_tab[k][G.tab[o]];
                 rc = run_stage(copy_only ? PB_PLAN_COPY : PB_PLAN_GEN4, a, k, p, st, nm);
+                a->walk_table = nullptr;
                 if (rc) return rc;
             }
         }
@@ -1773,7 +1878,14 @@ static void fill_entry_params(const pb200_assembler* a, PbEntryParams& prm) {
     prm.fields = a->d_fields;
     prm.npts = a->npts;
     prm.nterms = (int)a->terms.size();
-    for (int t = 0; t < prm.nterms; ++t) prm.terms[t] = a->terms[t];
+    prm.ext = a->ext_slots ? 1 : 0;
+    for (int t = 0; t < prm.nterms; ++t) {
+        prm.terms[t] = a->terms[t];
+        for (int k = 0; k < a->dim; ++k) {
+            prm.ot[t][k] = (unsigned char)pb_slot_order(a->terms[t].bt, k);
+            prm.ou[t][k] = (unsigned char)(a->terms[t].bu < 0 ? 0 : pb_slot_order(a->terms[t].bu, k));
+        }
+    }
 }
 
 extern "C" int pb200_asm_multi_entries(pb200_assembler* a, const uint64_t* d_ij, size_t n, double* d_out, void* stream) {

@@ -9,7 +9,8 @@
 // pipeline has no instantiation for; full-matrix assembly goes through walk.cuh instead.
 //
 // The integrand is a list of terms  C_t(g) * d^{bt} v_i(g) * d^{bu} u_j(g)  where slot 0 is the
-// function value and slot 1+k the derivative along tensor axis k.
+// function value and slot 1+k the derivative along tensor axis k; slots >= PB_SLOT_EXT carry one
+// derivative order per axis (common.cuh) and are evaluated from the three-row tables V3u / V3v.
 #pragma once
 #include "common.cuh"
 
@@ -22,10 +23,23 @@ struct PbEntryParams {
     long long npts;
     int nterms;
     PbTerm terms[PB_MAXTERMS];
+    int ext;                    // some term has a second or mixed derivative slot: orders from ot / ou
+    unsigned char ot[PB_MAXTERMS][PB_MAXDIM], ou[PB_MAXTERMS][PB_MAXDIM];   // derivative order per axis (test / trial)
     const unsigned long long* ij;   // [n][2]
     long long n;
     double* out;                // [n]
 };
+
+// value, first and (when the axis carries the three-row table) second derivative of active function a at node g
+PB_HD void pb_entry_rows(const double* V2, const double* V3, int g, int p, int a, double* r) {
+    if (V3) {
+        const double* T = V3 + (long long)g * 3 * (p + 1);
+        r[0] = T[a]; r[1] = T[p + 1 + a]; r[2] = T[2 * (p + 1) + a];
+    } else {
+        const double* T = V2 + (long long)g * 2 * (p + 1);
+        r[0] = T[a]; r[1] = T[p + 1 + a]; r[2] = 0.0;
+    }
+}
 
 template <int DIM>
 PB_HD double pb_entry(const PbEntryParams& prm, unsigned long long I, unsigned long long J) {
@@ -50,19 +64,24 @@ PB_HD double pb_entry(const PbEntryParams& prm, unsigned long long I, unsigned l
         const int av0 = i[0] - A0.first_v[s0], au0 = j[0] - A0.first_u[s0];
         for (int q0 = 0; q0 < A0.q; ++q0) {
             const int g0 = s0 * A0.q + q0;
-            const double* Tv0 = A0.Vv + (long long)g0 * A0.nd * (A0.pv + 1);
-            const double* Tu0 = A0.Vu + (long long)g0 * A0.nd * (A0.pu + 1);
-            const double v0[2] = {Tv0[av0], Tv0[A0.pv + 1 + av0]};
-            const double u0[2] = {Tu0[au0], Tu0[A0.pu + 1 + au0]};
+            double v0[3], u0[3];
+            pb_entry_rows(A0.Vv, A0.V3v, g0, A0.pv, av0, v0);
+            pb_entry_rows(A0.Vu, A0.V3u, g0, A0.pu, au0, u0);
             for (int s1 = sa[1]; s1 < sb[1]; ++s1) {
                 const int av1 = i[1] - A1.first_v[s1], au1 = j[1] - A1.first_u[s1];
                 for (int q1 = 0; q1 < A1.q; ++q1) {
                     const int g1 = s1 * A1.q + q1;
-                    const double* Tv1 = A1.Vv + (long long)g1 * A1.nd * (A1.pv + 1);
-                    const double* Tu1 = A1.Vu + (long long)g1 * A1.nd * (A1.pu + 1);
-                    const double v1[2] = {Tv1[av1], Tv1[A1.pv + 1 + av1]};
-                    const double u1[2] = {Tu1[au1], Tu1[A1.pu + 1 + au1]};
+                    double v1[3], u1[3];
+                    pb_entry_rows(A1.Vv, A1.V3v, g1, A1.pv, av1, v1);
+                    pb_entry_rows(A1.Vu, A1.V3u, g1, A1.pu, au1, u1);
                     if constexpr (DIM == 2) {
+                        if (prm.ext) {
+                            const long long pt = (long long)g0 * A1.G + g1;
+                            for (int t = 0; t < prm.nterms; ++t)
+                                r += prm.fields[(long long)prm.terms[t].field * prm.npts + pt]
+                                     * (v0[prm.ot[t][0]] * v1[prm.ot[t][1]]) * (u0[prm.ou[t][0]] * u1[prm.ou[t][1]]);
+                            continue;
+                        }
                         const double vt[3] = {v0[0] * v1[0], v0[1] * v1[0], v0[0] * v1[1]};
                         const double ut[3] = {u0[0] * u1[0], u0[1] * u1[0], u0[0] * u1[1]};
                         const long long pt = (long long)g0 * A1.G + g1;
@@ -74,10 +93,17 @@ PB_HD double pb_entry(const PbEntryParams& prm, unsigned long long I, unsigned l
                             const int av2 = i[2] - A2.first_v[s2], au2 = j[2] - A2.first_u[s2];
                             for (int q2 = 0; q2 < A2.q; ++q2) {
                                 const int g2 = s2 * A2.q + q2;
-                                const double* Tv2 = A2.Vv + (long long)g2 * A2.nd * (A2.pv + 1);
-                                const double* Tu2 = A2.Vu + (long long)g2 * A2.nd * (A2.pu + 1);
-                                const double v2[2] = {Tv2[av2], Tv2[A2.pv + 1 + av2]};
-                                const double u2[2] = {Tu2[au2], Tu2[A2.pu + 1 + au2]};
+                                double v2[3], u2[3];
+                                pb_entry_rows(A2.Vv, A2.V3v, g2, A2.pv, av2, v2);
+                                pb_entry_rows(A2.Vu, A2.V3u, g2, A2.pu, au2, u2);
+                                if (prm.ext) {
+                                    const long long pt = ((long long)g0 * A1.G + g1) * A2.G + g2;
+                                    for (int t = 0; t < prm.nterms; ++t)
+                                        r += prm.fields[(long long)prm.terms[t].field * prm.npts + pt]
+                                             * (v0[prm.ot[t][0]] * v1[prm.ot[t][1]] * v2[prm.ot[t][2]])
+                                             * (u0[prm.ou[t][0]] * u1[prm.ou[t][1]] * u2[prm.ou[t][2]]);
+                                    continue;
+                                }
                                 const double vt[4] = {v0[0] * v1[0] * v2[0], v0[1] * v1[0] * v2[0],
                                                       v0[0] * v1[1] * v2[0], v0[0] * v1[0] * v2[1]};
                                 const double ut[4] = {u0[0] * u1[0] * u2[0], u0[1] * u1[0] * u2[0],

@@ -40,10 +40,10 @@ struct PbFieldParams {
     long long pt_begin, pt_end;     // linear range of points evaluated by this launch
     int nf;
     // general first-order scalar forms (PbProgGeneral): physical coefficient terms and output map
-    const double* inputs[PB_MAXFIELDS];  // coefficient arrays on the Gauss grid (null: constant 1)
+    const double* inputs[PB_MAXPHYS];  // coefficient arrays on the Gauss grid (null: constant 1)
     int nphys;
-    struct { int bt, bu, input; double scale; } phys[PB_MAXFIELDS];   // slots: 0 value, 1+a d/dx_a
-    struct { int bp, ap; } outmap[PB_MAXFIELDS];                      // parametric slots of field f
+    struct { int bt, bu, input; double scale; } phys[PB_MAXPHYS];   // slots: 0 value, 1+a d/dx_a
+    struct { int bp, ap; } outmap[PB_MAXPHYS];                      // parametric slots of field f
 };
 
 template <int I> struct PbInt { static constexpr int value = I; };
@@ -245,7 +245,7 @@ template <int DIM> struct PbProgStiffness {
 // This is what the reference's generated precompute_fields computes for such forms
 // (pyiga/codegen/cython.py:673-701 on the finalized VForm, pyiga/vform.py:705-731).
 template <int DIM> struct PbProgGeneral {
-    static constexpr int NF = PB_MAXFIELDS;
+    static constexpr int NF = PB_MAXPHYS;
     static constexpr bool NEED_X = false;
     template <bool RAT> PB_HD static void run(const PbFieldParams& prm, PbPoint& pt, double* f) {
         pb_point_normalize<DIM, RAT>(pt);

@@ -13,7 +13,7 @@ comes from the sum-factorised pipeline.
 
 Nothing from ``pyiga`` is imported: the nodes are recognised by class name and attributes, so any
 object with the reference's structure is accepted.  Supported: volume integrals over one space,
-derivatives up to first order, scalar and vector-valued basis functions, parametric and physical
+derivatives up to second order (incl. mixed ones, as in the space-time wave form), scalar and vector-valued basis functions, parametric and physical
 input fields, parameters, ``on_demand`` bounding boxes (``pyiga/codegen/cython.py:421-426,541-559``).
 Input functions are evaluated on the host exactly like the generated ``__init__`` does
 (``pyiga/codegen/cython.py:465-484``, ``pyiga/utils.py:33-52``).
@@ -125,8 +125,12 @@ class _Interpreter:
             elif deriv == 1:
                 assert not src.physical, 'Jacobian of physical input field not implemented'
                 arr = np.asarray(f.grid_jacobian(self.grid), dtype=float)
+            elif deriv == 2:
+                # symmetric part, linearised: (d_xx, d_xy, d_yy) / (d_xx, d_xy, d_xz, d_yy, d_yz, d_zz)  (pyiga/vform.py:354-360)
+                assert not src.physical, 'Hessian of physical input field not implemented'
+                arr = np.asarray(f.grid_hessian(self.grid), dtype=float)
             else:
-                raise NotImplementedError('second derivatives of input fields')
+                raise NotImplementedError('derivatives of order > 2 of input fields')
             arr = np.asarray(arr, dtype=float)
         else:
             raise TypeError('invalid source %r of variable %s' % (src, var.name))
@@ -189,8 +193,8 @@ class _Interpreter:
             assert not e.physical, 'physical derivatives must be resolved by finalize()'
             bf = e.basisfun
             slot = (bf.component or 0, tuple(int(d) for d in e.D))
-            if max(slot[1]) > 1 or sum(slot[1]) > 1:
-                raise NotImplementedError('derivatives of order > 1 of the basis functions')
+            if max(slot[1]) > 2:
+                raise NotImplementedError('derivatives of order > 2 of the basis functions')
             # linear forms name their only (test) function 'u' (pyiga/vform.py: names[:arity])
             is_test = bf.name == 'v' or self.vf.arity == 1
             return _Lin({(slot, None): 1.0}) if is_test else _Lin({(None, slot): 1.0})
@@ -202,14 +206,20 @@ class _Interpreter:
 
 
 def _slot_to_axis(slot, dim):
-    """parametric slot (component, D in x,y,z order) -> 0 (value) or 1 + tensor axis of the derivative"""
+    """parametric slot (component, D in x,y,z order) -> derivative slot of the C ABI: 0 (value), 1 + tensor axis
+    of a first derivative, or 16 + sum_k order_k * 3**k over the tensor axes k for second and mixed derivatives
+    (``PB_SLOT_EXT``, include/pyiga_b200.h)"""
     if slot is None:
         return -1
     D = slot[1]
+    orders = [0] * dim
     for i, d in enumerate(D):
-        if d:
-            return 1 + (dim - 1 - i)        # x is the last tensor axis (pyiga/codegen/cython.py:170)
-    return 0
+        orders[dim - 1 - i] = int(d)        # x is the last tensor axis (pyiga/codegen/cython.py:170)
+    if sum(orders) == 0:
+        return 0
+    if sum(orders) == 1:
+        return 1 + orders.index(1)
+    return 16 + sum(o * 3 ** k for k, o in enumerate(orders))
 
 
 class _ParametricBlock:
@@ -307,6 +317,10 @@ class RefVFormAssembler(GenericFormAssembler):
             raise ValueError('the form has no terms')
         self.blocks = {}
         for blk, coefs in blocks.items():
+            # slot pairs whose coefficient vanishes identically (e.g. the geometry Hessian terms of a fourth-order
+            # form on an affine map) would only cost launches
+            live = {k: c for k, c in coefs.items() if np.any(np.asarray(c) != 0.0)}
+            coefs = live or dict([next(iter(coefs.items()))])
             self.blocks[blk] = _ParametricBlock(kvs, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev

@@ -18,9 +18,10 @@ pipeline as mass and stiffness (``pb200_asm_assemble_mlb`` with a generic stage 
 
 Linear forms (arity 1, e.g. ``'f * v * dx'``) give load vectors through the same machinery, and
 vector-valued basis functions (``bfuns=[('u', 2), ('v', 2)]``) are handled block by block: every
-pair of components is one scalar form of the family above.  Second derivatives, boundary
-integrals and forms over two different spaces are not part of the device path; they
-raise ``NotImplementedError``.
+pair of components is one scalar form of the family above.  Second derivatives and general space-time
+expressions are not part of THIS front end and raise ``NotImplementedError``; the predefined space-time
+forms ``heat_st_vf`` / ``wave_st_vf`` map to :mod:`pyiga_b200.spacetime`, and the reference's own ``VForm``
+objects (any derivative order up to 2, space-time) are consumed by :mod:`pyiga_b200.refvform`.
 """
 import re
 
@@ -432,7 +433,7 @@ class VForm:
 
     def __init__(self, dim, geo_dim=None, boundary=False, arity=2, spacetime=False):
         if spacetime:
-            raise NotImplementedError('space-time forms are not part of the device path')
+            raise NotImplementedError('general space-time forms: use heat_st_vf / wave_st_vf or a reference VForm object')
         self.dim, self.arity = dim, arity
         # integrals over a dim-dimensional manifold in R^(dim+1): `geo` maps R^dim -> R^geo_dim
         self.geo_dim = dim if geo_dim is None else int(geo_dim)
@@ -598,6 +599,29 @@ def stiffness_vf(dim):
     return vf
 
 
+class _SpaceTimeForm:
+    """The predefined space-time forms (``pyiga/vform.py:1759-1772``).  General space-time expressions are not
+    part of this front end (reference ``VForm(dim, spacetime=True)`` objects are: :mod:`pyiga_b200.refvform`);
+    the two predefined ones map to the assembler classes of :mod:`pyiga_b200.spacetime`."""
+    arity, vec, spacetime = 2, False, True
+
+    def __init__(self, dim, wave):
+        self.dim = self.geo_dim = dim
+        self.wave = wave
+
+    def assembler_class(self):
+        from . import spacetime
+        return getattr(spacetime, '%sAssembler_ST%dD' % ('Wave' if self.wave else 'Heat', self.dim))
+
+
+def heat_st_vf(dim):
+    return _SpaceTimeForm(dim, wave=False)
+
+
+def wave_st_vf(dim):
+    return _SpaceTimeForm(dim, wave=True)
+
+
 # ---------------------------------------------------------------------------------------------
 # "compilation": VForm -> assembler class bound to the device pipeline
 # ---------------------------------------------------------------------------------------------
@@ -651,6 +675,8 @@ def compile_vform(vf, on_demand=False, verbose=False):
     (:mod:`pyiga_b200.refvform`); for forms of this module the fields of the whole patch are one K2
     launch, so the box is accepted and every entry stays valid."""
     from . import refvform
+    if isinstance(vf, _SpaceTimeForm):
+        return vf.assembler_class()
     if refvform.is_reference_vform(vf):
         # a pyiga.vform.VForm: interpreted after its own finalize() (SURVEY.md Appendix A); `on_demand`
         # assemblers evaluate their inputs only inside the bounding box given to the constructor

@@ -31,6 +31,12 @@ def cases():
         vf.add(rvf.inner(rvf.dot(A, rvf.grad(u)), rvf.grad(v)) * rvf.dx + c * u * v * rvf.dx)
         return vf
 
+    def biharmonic2():
+        vf = rvf.VForm(2)
+        u, v = vf.basisfuns()
+        vf.add(rvf.inner(rvf.hess(u), rvf.hess(v)) * rvf.dx)
+        return vf
+
     return {
         'stiffness2': (lambda: rvf.stiffness_vf(2), kv2, geo2, {}),
         'mass3': (lambda: rvf.mass_vf(3), kv3, geo3, {}),
@@ -42,6 +48,11 @@ def cases():
         # space-time heat form (pyiga/vform.py:1759-1763; the last coordinate is time)
         'heat_st2': (lambda: rvf.heat_st_vf(2), kv2, rgeo.unit_square(), {}),
         'heat_st3': (lambda: rvf.heat_st_vf(3), kv3, geo3, {}),
+        # space-time wave form: second time derivative and mixed space-time derivatives (pyiga/vform.py:1766-1772)
+        'wave_st2': (lambda: rvf.wave_st_vf(2), kv2, geo2, {}),
+        'wave_st3': (lambda: rvf.wave_st_vf(3), kv3, geo3, {}),
+        # fourth-order form: all second derivatives and the Hessian of the geometry map (per-entry path)
+        'biharmonic2': (biharmonic2, kv2, geo2, {}),
     }
 
 

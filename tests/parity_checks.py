@@ -6,6 +6,7 @@ Tolerance: the north-star's 1e-12 relative to the max-abs entry of the reference
 arrays bit-exact.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -1056,6 +1057,55 @@ def check_reference_vform_objects():
         got = got.toarray() if hasattr(got, 'toarray') else np.asarray(got)
         assert got.shape == want.shape, name
         assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), '%s: %.3e' % (name, np.abs(got - want).max())
+    # second and mixed derivative slots (numderiv = 2): the wave form runs through the sum-factorised walks with the
+    # (1st, 2nd derivative) tables, and the per-entry kernel gives the same matrix; the fourth-order form needs all
+    # three derivative orders on one axis in one term group and takes the per-entry path
+    from pyiga_b200 import _device, vform as dvform
+    be = _device.backend()
+    for name, fast in (('wave_st2', True), ('wave_st3', True), ('biharmonic2', False)):
+        make, kvs, geo, inputs = rc.cases()[name]
+        asm = dvform.compile_vform(make())(kvs, geo=geo, **inputs)
+        assert bool(asm.dev.fast_path) == fast, name
+        a, b = be.to_host(asm.dev.assemble_mlb()), be.to_host(asm.dev.assemble_mlb(entrywise=True))
+        assert np.abs(a - b).max() <= RTOL * np.abs(b).max(), name
+        want = fix['vf_' + name]
+        I, J = np.nonzero(want)
+        ij = np.stack([I, J], 1)[::3]
+        vals = np.asarray(asm.multi_entries(ij))
+        assert np.abs(vals - want[ij[:, 0], ij[:, 1]]).max() <= RTOL * np.abs(want).max(), name
+
+
+def check_space_time_assemblers():
+    """HeatAssembler_ST / WaveAssembler_ST of the predefined set (pyiga/assemblers.pyx:351-690, 1542-1957) against
+    the matrices of the reference's own classes (fixture entries vf_heat_st*, vf_wave_st*: same spaces and
+    geometries, tests/golden/refvform_cases.py).  No reference code runs here."""
+    from pyiga_b200 import _device, assemble, assemblers, bspline, geometry, vform
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_vform_objects.npz'))
+    kv2 = (bspline.make_knots(2, 0.0, 1.0, 4), bspline.make_knots(3, 0.0, 1.0, 3))
+    kv3 = (bspline.make_knots(2, 0.0, 1.0, 3), bspline.make_knots(1, 0.0, 1.0, 4), bspline.make_knots(2, 0.0, 1.0, 2))
+    be = _device.backend()
+    cases = [('heat_st2', assemblers.HeatAssembler_ST2D, kv2, geometry.unit_square()),
+             ('heat_st3', assemblers.HeatAssembler_ST3D, kv3, geometry.twisted_box()),
+             ('wave_st2', assemblers.WaveAssembler_ST2D, kv2, geometry.quarter_annulus()),
+             ('wave_st3', assemblers.WaveAssembler_ST3D, kv3, geometry.twisted_box())]
+    for name, cls, kvs, geo in cases:
+        want = fix['vf_' + name]
+        asm = cls(kvs, geo)
+        assert asm.dev.fast_path, name                       # the sum-factorised walks, not the per-entry fall-back
+        got = assemble.assemble(asm, symmetric=False).toarray()
+        assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), (name, np.abs(got - want).max())
+        a, b = be.to_host(asm.dev.assemble_mlb()), be.to_host(asm.dev.assemble_mlb(entrywise=True))
+        assert np.abs(a - b).max() <= RTOL * np.abs(b).max(), name
+    # the predefined forms of the front end lead to the same classes
+    got = assemble.assemble(vform.wave_st_vf(2), kv2, geo=geometry.quarter_annulus()).toarray()
+    assert np.abs(got - fix['vf_wave_st2']).max() <= RTOL * np.abs(fix['vf_wave_st2']).max()
+    got = assemble.assemble(vform.heat_st_vf(3), kv3, geo=geometry.twisted_box()).toarray()
+    assert np.abs(got - fix['vf_heat_st3']).max() <= RTOL * np.abs(fix['vf_heat_st3']).max()
+    # a larger 3D case, fast walks against the per-entry kernel (different algorithms, same tables)
+    kvs = (bspline.make_knots(3, 0.0, 1.0, 7), bspline.make_knots(2, 0.0, 1.0, 9), bspline.make_knots(3, 0.0, 1.0, 6))
+    asm = assemblers.WaveAssembler_ST3D(kvs, geometry.twisted_box())
+    a, b = be.to_host(asm.dev.assemble_mlb()), be.to_host(asm.dev.assemble_mlb(entrywise=True))
+    assert asm.dev.fast_path and np.abs(a - b).max() <= RTOL * np.abs(b).max()
 
 
 def check_hierarchical_discretization(monkeypatch):

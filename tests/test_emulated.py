@@ -195,6 +195,10 @@ def test_reference_vform_objects(emu):
     pc.check_reference_vform_objects()
 
 
+def test_space_time_assemblers(emu):
+    pc.check_space_time_assemblers()
+
+
 def test_hierarchical_discretization(emu, monkeypatch):
     pc.check_hierarchical_discretization(monkeypatch)
 

@@ -274,6 +274,10 @@ def test_reference_vform_objects(cuda):
     pc.check_reference_vform_objects()
 
 
+def test_space_time_assemblers(cuda):
+    pc.check_space_time_assemblers()
+
+
 def test_hierarchical_discretization(cuda, monkeypatch):
     pc.check_hierarchical_discretization(monkeypatch)
 
