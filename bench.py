@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary configurations (extra_configs)')
+    ap.add_argument('--no-cg', action='store_true', help='skip the distributed CG check on the mass matrix (config 5, `cg` key)')
     return ap.parse_args()
 
 
@@ -337,6 +338,67 @@ def parity_against_fixture(a, dev, rows, d_out):
     return (float(np.abs(got - z['val'][sel]).max()), int(sel.sum()), scale, name)
 
 
+def run_distributed_cg(a, kvs, geo, rank, world, barrier):
+    """Config 5's solver stage on this run's mesh: preconditioned CG on the geometry mass matrix (the system of
+    pyiga/approx.py:82-96), slab-distributed, device-resident (pyiga_b200.distcg: halo and dot products through
+    peer windows over NVLink, CUDA graph per batch of iterations).  Collective: every rank calls it.  Not part of
+    the timed assembly step; reported under the `cg` key."""
+    import torch
+    import torch.distributed as dist
+    from pyiga_b200 import _device, assemble
+    from pyiga_b200.dist import SlabAssembly
+    from pyiga_b200.distcg import DistributedCG
+    be = _device.backend()
+    ok, cg, err_msg = 1.0, None, None
+    try:
+        sa = SlabAssembly(kvs, geo, 'mass', rank=rank, world=world)
+        mlb = sa.assemble_mlb()
+        Ainv = [np.linalg.inv(assemble.bsp_mass_1d(kv).toarray()) for kv in kvs]
+        cg = DistributedCG(sa.dev.device_structure, mlb, sa.slabs, rank, Ainv)
+    except Exception as exc:        # all ranks must agree before anyone waits on a peer
+        ok, err_msg = 0.0, repr(exc)[:200]
+    if world > 1:
+        t = torch.tensor([ok], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = float(t[0])
+    if not ok:
+        if cg is not None:
+            cg.close()
+        return {'error': err_msg or 'setup failed on another rank'}
+    nloc = cg.nloc
+    ones = torch.ones(nloc, dtype=torch.float64, device='cuda')
+    b = cg.matvec(ones).clone()
+    y, x = be.empty(nloc), be.empty(nloc)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        cg.matvec(ones, y)
+    barrier()
+    e0.record()
+    for _ in range(20):
+        cg.matvec(ones, y)
+    e1.record()
+    barrier()
+    mv_ms = e0.elapsed_time(e1) / 20
+    cg.solve(b, rtol=1e-10, maxiter=10, check_every=10, out=x)         # warm-up: graph capture
+    times = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        _, it, res = cg.solve(b, rtol=1e-10, maxiter=100, check_every=10, out=x)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    t = torch.tensor([min(times), mv_ms, float((x - 1.0).abs().max())], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {'workload': 'CG on the 3D mass matrix p=%d n=%d (%s), Kronecker preconditioner, rtol 1e-10' % (a.p, a.n, a.geo),
+           'nnz': sa.dev.nnz, 'local_nnz_rank0': sa.local_nnz, 'cg_ms': 1e3 * float(t[0]), 'cg_iterations': int(it),
+           'cg_rel_residual': float(res), 'max_err_vs_known_solution': float(t[2]),
+           'matvec_ms': float(t[1]), 'matvec_GBps_local': 8.0 * sa.local_nnz / (float(t[1]) * 1e-3) / 1e9,
+           'timing': 'cg_ms: host clock around pb200_cg_solve (min of 3, max over ranks); matvec_ms: CUDA events, max over ranks'}
+    cg.close()
+    return out
+
+
 def run_extra_configs(be, fp64_peak, hbm_peak):
     """Secondary configurations of BASELINE.json on one GPU, device-resident like `value`: a few steps
     each, nnz/s and the fraction of the SURVEY 8d path bound max(F / FP64 peak, 8 nnz / HBM)."""
@@ -535,6 +597,15 @@ def run_ours(a):
                              % (rank, it, 1e3 * t_call, 1e3 * (time.perf_counter() - t0)))
     e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times) if e2e_times else None
 
+    # ---- config 5's solver stage (all ranks; outside the timed step) --------------------------
+    cg_info = None
+    if not a.no_cg:
+        try:
+            torch.cuda.empty_cache()
+            cg_info = run_distributed_cg(a, kvs, geo, rank, world, barrier)
+        except Exception as exc:
+            cg_info = {'error': repr(exc)[:200]}
+
     # ---- reduce over ranks -------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([ms, e2e_ms or 0.0, par_err], device='cuda', dtype=torch.float64)
@@ -645,6 +716,8 @@ def run_ours(a):
                               'memory overlapped chunk by chunk; indptr/indices (closed form of the band tables) are written into the '
                               'result arrays by host threads meanwhile (pb200_csr_pattern_host)'},
         }
+        if cg_info is not None:
+            line['cg'] = cg_info
         if world == 1 and not a.no_extras:
             try:
                 del out

@@ -379,7 +379,10 @@ class _AssemblerProtocol:
         """The whole matrix as an :class:`~pyiga_b200.mlmatrix.MLMatrix` whose values stay on the device."""
         data = self.dev.assemble_mlb(**kw)
         M = MLMatrix(structure=self.dev.structure, data=data)
-        M._dev = self.dev.device_structure
+        # the matrix owns its band tables: borrowing the assembler's would keep the assembler's field buffers and
+        # scratch alive on the GPU for the lifetime of the matrix
+        own = DeviceStructure(structure=self.dev.structure)
+        M._dev = own if own.supported else self.dev.device_structure
         return M
 
     def assemble_csr(self, **kw):

@@ -68,8 +68,25 @@ PB_HD void pb_cg_fence() {
 }
 #define PB_CG_FENCE() pb_cg_fence()
 
+// A peer that never raises its flag (a rank that died, a window mapped wrongly) must not hang the GPU: the
+// device-side wait gives up after PB_CG_WAIT_NS and records it; the host entry points turn that into an error.
+#define PB_CG_WAIT_NS 5000000000ULL
+#if defined(__CUDACC__)
+__device__ int pb_cg_timed_out = 0;
+#endif
 PB_HD void pb_cg_wait(volatile long long* f, long long stamp) {
+#if defined(__CUDA_ARCH__)
+    if (*f < stamp) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*f < stamp) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > PB_CG_WAIT_NS || *(volatile int*)&pb_cg_timed_out) { pb_cg_timed_out = 1; break; }
+        }
+    }
+#else
     while (*f < stamp) {}
+#endif
     PB_CG_FENCE();
 }
 

@@ -414,6 +414,9 @@ extern "C" int pb200_cg_solve(pb200_cg* g, const double* d_b, double* d_x, doubl
     CK(cudaStreamWaitEvent(caller, g->ev_out, 0));
     if (iters) *iters = (int)h[1];
     if (relres) *relres = h_s[5] > 0 ? std::sqrt(h_s[4] / h_s[5]) : 0.0;
+    int timed_out = 0;
+    CK(cudaMemcpyFromSymbol(&timed_out, pb_cg_timed_out, sizeof(int)));
+    if (timed_out) return fail(PB200_ECUDA, "distributed CG: a peer rank did not answer within %.0f s (halo / all-reduce flag)", PB_CG_WAIT_NS * 1e-9);
     return 0;
 #endif
 }
