@@ -343,6 +343,7 @@ def run_distributed_cg(a, kvs, geo, rank, world, barrier):
     pyiga/approx.py:82-96), slab-distributed, device-resident (pyiga_b200.distcg: halo and dot products through
     peer windows over NVLink, CUDA graph per batch of iterations).  Collective: every rank calls it.  Not part of
     the timed assembly step; reported under the `cg` key."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     from pyiga_b200 import _device, assemble
