@@ -406,6 +406,12 @@ struct pb200_assembler {
     int fast = 0;
     bool ext_slots = false;                             // some term has a second or mixed derivative slot (PB_SLOT_EXT)
     const double* walk_table = nullptr;                 // run_stage: table override of the current launch
+    // fused stages 2 + 3: device list of the band entries of axis 0 a launch computes (cached per slab)
+    int* s32_keep_dev = nullptr;
+    size_t s32_keep_cap = 0;
+    long long s32_keep_key[5] = {-1, -1, -1, -1, -1};
+    int s32_nkeep = 0;
+    bool pack_tails = true;                             // several short last batches share a block
     const double* pair_tab[PB_MAXDIM][3] = {};          // two-row tables of derivative orders (0,1) (0,2) (1,2) for the walks
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
@@ -451,6 +457,7 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!strcmp(name, "mirror")) { a->mirror_opt = value != 0; return 0; }
     if (!strcmp(name, "fuse")) { a->fuse = value != 0; return 0; }
     if (!strcmp(name, "fuse23")) { a->fuse23 = value != 0; return 0; }
+    if (!strcmp(name, "pack_tails")) { a->pack_tails = value != 0; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
 }
 
@@ -811,6 +818,7 @@ extern "C" int pb200_asm_destroy(pb200_assembler* a) {
     pbSetDevice(a->device);
     if (a->pool.dev) pbFree(a->pool.dev);
     if (a->geo_scratch) pbFree(a->geo_scratch);
+    if (a->s32_keep_dev) pbFree(a->s32_keep_dev);
     delete a;
     return 0;
 }
@@ -1166,6 +1174,41 @@ static void fill_s32_axes(const pb200_assembler* a, PbS32Params& p) {
     p.N1 = H1.V.N(); p.N2 = H2.V.N(); p.M1 = H1.M; p.M2 = H2.M;
     p.first1 = D1.first_u; p.V1 = D1.Vu; p.ret_mu1 = D1.ret_mu; p.tr1 = D1.tr; p.pair_i1 = D1.pair_i;
     p.first2 = D2.first_u; p.V2 = D2.Vu; p.ret_mu2 = D2.ret_mu; p.tr2 = D2.tr;
+}
+
+// tasks of a fused stage-2+3 launch: the kept band entries of axis 0 (uploaded once per slab) and the packing of
+// the short last batches (fused23.cuh)
+static int fill_s32_tasks(pb200_assembler* a, const Slab& S, PbS32Params& q, pbStream st) {
+    const AxisHost &H0 = a->hax[0], &H2 = a->hax[2];
+    const long long key[5] = {S.mu_lo, S.mu_hi, S.ra, S.rb, q.symmetric};
+    if (memcmp(key, a->s32_keep_key, sizeof key) != 0 || !a->s32_keep_dev) {
+        std::vector<int> keep;
+        for (int mu = S.mu_lo; mu < S.mu_hi; ++mu) {
+            const int i0 = H0.pair_i[mu], j0 = H0.pair_j[mu];
+            if (!(q.symmetric && j0 >= S.ra && j0 < S.rb && j0 < i0)) keep.push_back(mu);
+        }
+        if (keep.size() > a->s32_keep_cap) {
+            if (a->s32_keep_dev) pbFree(a->s32_keep_dev);
+            a->s32_keep_dev = nullptr;
+            a->s32_keep_cap = keep.size() + 64;
+            CK(pbMalloc((void**)&a->s32_keep_dev, a->s32_keep_cap * sizeof(int)));
+        }
+        if (!keep.empty()) {
+            CK(pbMemcpyH2D(a->s32_keep_dev, keep.data(), keep.size() * sizeof(int), st));
+            CK(pbStreamSync(st));           // `keep` goes out of scope
+        }
+        a->s32_nkeep = (int)keep.size();
+        memcpy(a->s32_keep_key, key, sizeof key);
+    }
+    q.keep = a->s32_keep_dev;
+    q.nkeep = a->s32_nkeep;
+    const int P = H2.U.p;
+    const int sb_tail = (q.nbatch - 1) * (32 - P);
+    const int wt = std::min(32, H2.n + P - sb_tail);       // lanes the last batch needs
+    q.tail_w = wt;
+    q.tail_k = (a->pack_tails && q.nbatch >= 2 && wt > 0) ? std::min(4, 32 / wt) : 1;
+    if (q.tail_k < 2) q.tail_k = 1;
+    return 0;
 }
 // generic forms: a term travels through the stages as (test slot, trial slot, buffer slot)
 struct GenTerm { int bt, bu, slot; };
@@ -1561,7 +1604,9 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                 q.symmetric = 0;
                 q.out = d_out; q.out_mu_base = S.mu_lo;
                 q.nbatch = pb_lane_batches(a->hax[2].n, a->hax[2].U.p);
-                const long long tasks = (long long)Mrows * q.nbatch;
+                rc = fill_s32_tasks(a, S, q, st);
+                if (rc) return rc;
+                const long long tasks = pb_s32_tasks(q);
                 const int P = H1.U.p, nsp = H1.n, N1 = H1.V.N();
                 int K = 1;
                 if (a->walk_split > 1) K = std::min(a->walk_split, 4);
@@ -1759,16 +1804,13 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         q.symmetric = 1;
         q.out = d_out; q.out_mu_base = S.mu_lo;
         q.nbatch = pb_lane_batches(H2.n, H2.U.p);
+        rc = fill_s32_tasks(a, S, q, st);
+        if (rc) return rc;
         {
             // Tail effect: one block per SM and ~0.3 ms per block — a slab whose blocks fill the GPU 2.4 times
             // pays for 3 waves.  Cut axis 1 into K pieces (K x as many, shorter blocks; p spans of overlap
             // each) when that shortens the sum of the waves.
-            long long kept = 0;
-            for (int mu = S.mu_lo; mu < S.mu_hi; ++mu) {
-                const int i0 = H0.pair_i[mu], j0 = H0.pair_j[mu];
-                if (!(j0 >= S.ra && j0 < S.rb && j0 < i0)) ++kept;
-            }
-            const long long tasks = kept * q.nbatch;
+            const long long tasks = pb_s32_tasks(q);
             const int P = H1.U.p, nsp = H1.n, N1 = H1.V.N();
             int K = 1;
             if (a->walk_split > 1) {

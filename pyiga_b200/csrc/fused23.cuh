@@ -61,7 +61,17 @@ struct PbS32Params {
     int ps_begin[4], ps_end[4], pw_lo[4], pw_hi[4];
     // ---- generic forms (PbS32Generic): X1 term read by input stream i, or -1 when the form has no such term ----
     int in_slot[9];
+    // ---- tasks of the CUDA kernel: the band entries mu0 this launch computes (pb_s32_keep), in order ----------
+    // Full batches are one block each.  The LAST batch of an axis rarely fills the warp (n2 = 128, p = 3: 15 of
+    // 32 lanes); when tail_k >= 2 such tails of tail_k consecutive kept entries share one block, tail_w lanes each.
+    const int* keep;
+    int nkeep, tail_k, tail_w;
 };
+// blocks of a launch (per axis-1 piece)
+PB_HD long long pb_s32_tasks(const PbS32Params& prm) {
+    if (prm.tail_k > 1) return (long long)prm.nkeep * (prm.nbatch - 1) + (prm.nkeep + prm.tail_k - 1) / prm.tail_k;
+    return (long long)prm.nkeep * prm.nbatch;
+}
 struct PbS32Piece { int s_begin, s_end, w_lo, w_hi; };
 PB_HD PbS32Piece pb_s32_piece(const PbS32Params& prm, int y) {
     PbS32Piece p;
@@ -321,16 +331,23 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
     int* sAct = reinterpret_cast<int*>(pb_s32_raw + lay.actv);
 
     const int npc = prm.npiece > 1 ? prm.npiece : 1;
-    const int batch = (blockIdx.x / npc) % prm.nbatch;
-    const int mu0 = prm.mu0_begin + blockIdx.x / (npc * prm.nbatch);
     const PbS32Piece pc = pb_s32_piece(prm, blockIdx.x % npc);
-    bool mirror;
-    if (!pb_s32_keep(prm, mu0, mirror)) return;         // block-uniform
+    // task -> (kept entries, batch): one entry and 32 lanes, or up to tail_k entries with tail_w lanes each
+    const int task = blockIdx.x / npc;
+    const int nb_full = prm.tail_k > 1 ? prm.nbatch - 1 : prm.nbatch;
+    const bool packed = task >= prm.nkeep * nb_full;
+    const int kidx = packed ? (task - prm.nkeep * nb_full) * prm.tail_k : task / nb_full;
+    const int batch = packed ? prm.nbatch - 1 : task % nb_full;
+    const int ngrp = packed ? pb_min(prm.tail_k, prm.nkeep - kidx) : 1;
+    const int GL = packed ? prm.tail_w : 32;                    // lanes per entry
+    const int TG = packed ? prm.tail_w * (2 * P + 1) : TPAD;    // T positions per entry
+    const int mu0 = prm.keep[kidx];                             // entry of group 0
     const int mu0t = prm.symmetric ? prm.tr0[mu0] : mu0;
     // (broadcast from lane 0: tells the compiler that the role is uniform across the warp — otherwise every
     // shuffle of the producers is wrapped in a convergence barrier, ~35 % more instructions per row)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const bool producer = warp < NPROD;
+    const int gl = lane / GL, lg = lane - gl * GL;              // entry and lane inside it (gl = 0, lg = lane unless packed)
 
     // ---- block setup: axis-1 tables, zeroed rings and T buffers, owned positions ---------------------
     for (int t = threadIdx.x; t < prm.G1 * 2 * P1; t += blockDim.x) sV1[t] = prm.V1[t];
@@ -352,15 +369,15 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
         for (int t = threadIdx.x; t < Q * 2 * P1 * 32; t += blockDim.x) {
             const int l = t & 31, c = t >> 5;                       // c = (gq*2 + fl)*P1 + a
             const int gq = c / (2 * P1), r = c % (2 * P1);
-            const int sp = sb + l;
-            sD[t] = sp < prm.n2 ? prm.V2[(long long)(sp * Q + gq) * 2 * P1 + r] : 0.0;
+            const int sp = sb + l % GL;
+            sD[t] = (sp < prm.n2 && l / GL < ngrp) ? prm.V2[(long long)(sp * Q + gq) * 2 * P1 + r] : 0.0;
         }
     }
     __syncthreads();
 
-    const int s = sb + lane;
-    const int m = prm.first2[0] + sb + lane;
-    const bool writer = (batch == 0 || lane >= P) && m < prm.N2;
+    const int s = sb + lg;
+    const int m = prm.first2[0] + sb + lg;
+    const bool writer = (batch == 0 || lg >= P) && m < prm.N2 && gl < ngrp;
     // band positions of this lane's entries and the smallest one of the batch (every warp computes it)
     int mu[2 * P + 1];
     int mu_lo = 0x7fffffff;
@@ -375,7 +392,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k <= 2 * P; ++k)
-            if (mu[k] >= 0) sAct[mu[k] - mu_lo] = 1;
+            if (mu[k] >= 0) sAct[gl * TG + mu[k] - mu_lo] = 1;
     }
     __syncthreads();
     (void)s;
@@ -402,25 +419,33 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
         // slot offsets of this lane's entries in a T row (-1: not a writer)
         int tpos[2 * P + 1];
 #pragma unroll
-        for (int k = 0; k <= 2 * P; ++k) tpos[k] = mu[k] >= 0 ? mu[k] - mu_lo : -1;
+        for (int k = 0; k <= 2 * P; ++k) tpos[k] = mu[k] >= 0 ? gl * TG + mu[k] - mu_lo : -1;
         const long long seg_node0 = (long long)sb * Q;
-        const long long seg_nodes = (long long)(pb_min(prm.n2, sb + 32) - sb) * Q;
+        const int seg_nodes = (pb_min(prm.n2, sb + GL) - sb) * Q;   // nodes of one entry's segment
+        const int ent_nodes = GL * Q;                                  // ring doubles per entry
         constexpr int NPIECE = VEC ? (SEG / 2 + 31) / 32 : (SEG + 31) / 32;
+        // ring element -> (entry, node of its segment); entries other than the first read another plane of X1:
+        // dpl[h][0] for the streams read at mu0, dpl[h][1] for those read at the transposed entry
         int goff[NPIECE], soff[NPIECE];
+        long long dpl[NPIECE][2];
 #pragma unroll
         for (int h = 0; h < NPIECE; ++h) {
             const int c = lane + 32 * h;
-            if constexpr (VEC) {
-                const int pc = (Q == 4) ? (c ^ ((c >> 3) & 1)) : c;
-                goff[h] = (c < SEG / 2 && 2 * c < seg_nodes) ? 2 * c : -1;
-                soff[h] = 2 * pc;
-            } else {
-                goff[h] = (c < SEG && c < seg_nodes) ? c : -1;
-                soff[h] = c;
+            const int r = VEC ? 2 * c : c;                              // first ring double of this copy
+            const int ge = r / ent_nodes, within = r - ge * ent_nodes;
+            goff[h] = (r < SEG && ge < ngrp && within < seg_nodes) ? within : -1;
+            if constexpr (VEC) soff[h] = 2 * ((Q == 4) ? (c ^ ((c >> 3) & 1)) : c);
+            else soff[h] = c;
+            dpl[h][0] = dpl[h][1] = 0;
+            if (goff[h] >= 0 && ge > 0) {
+                const int mg = prm.keep[kidx + ge];
+                dpl[h][0] = (long long)(mg - mu0) * ((long long)prm.G1 * prm.G2);
+                dpl[h][1] = (long long)((prm.symmetric ? prm.tr0[mg] : mg) - mu0t) * ((long long)prm.G1 * prm.G2);
             }
         }
         // the input streams of this half: global stream index = half * NSTR + j
         const double* base[NSTR];
+        bool btr[NSTR];
         pb_static_for<0, NSTR>([&](auto J) {
             constexpr int j = decltype(J)::value;
             // (both halves are instantiated; select at run time)
@@ -428,6 +453,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
             const bool r0 = Form::in_tr(j), r1 = Form::in_tr((NH - 1) * NSTR + j);
             const int term = half == 0 ? t0 : t1;
             const bool trn = half == 0 ? r0 : r1;
+            btr[j] = trn;
             base[j] = term < 0 ? nullptr        // the form has no such term: the (zero-filled) ring slot is never written
                                : prm.X1 + (long long)term * prm.x1_stride + (long long)((trn ? mu0t : mu0) - prm.x1_mu_base) * plane
                                      + seg_node0 + (long long)prow * prm.G2;
@@ -442,8 +468,9 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
 #pragma unroll
                 for (int h = 0; h < NPIECE; ++h) {
                     if (goff[h] >= 0) {
-                        if constexpr (VEC) pb_cp_async16(dst + j * SEG + soff[h], src + goff[h]);
-                        else pb_cp_async8(dst + j * SEG + soff[h], src + goff[h]);
+                        const double* sp = src + goff[h] + (btr[j] ? dpl[h][1] : dpl[h][0]);
+                        if constexpr (VEC) pb_cp_async16(dst + j * SEG + soff[h], sp);
+                        else pb_cp_async8(dst + j * SEG + soff[h], sp);
                     }
                 }
             });
@@ -490,7 +517,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
                 for (int q = 1; q <= P; ++q) {
                     if (q <= P - d) {
                         const double vsh = __shfl_up_sync(0xffffffffu, (kk <= P) ? L[q][q + d] : L[q + d][q], q);
-                        if (lane >= q) sum += vsh;
+                        if (lg >= q) sum += vsh;
                     }
                 }
                 if (tpos[kk] >= 0) Tw[t * TPAD + tpos[kk]] = sum;
@@ -519,12 +546,16 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
 
     // ==================================== phase B: walk along axis 1 ==================================
     using PB = typename Form::PlanB;
-    const int e = threadIdx.x - NPROD * 32;             // band position of the batch owned by this thread
+    const int e = threadIdx.x - NPROD * 32;             // T position owned by this thread: entry ge, band position mu_lo + el
     const bool act = sAct[e] != 0;
-    double* outp = prm.out + (long long)(mu0 - prm.out_mu_base) * prm.M1 * prm.M2 + (mu_lo + e);
+    const int ge = e / TG, el = e - ge * TG;
+    const int mu0e = act ? prm.keep[kidx + ge] : mu0;
+    bool mirror;
+    pb_s32_keep(prm, mu0e, mirror);
+    double* outp = prm.out + (long long)(mu0e - prm.out_mu_base) * prm.M1 * prm.M2 + (mu_lo + el);
     double* outp_t = outp;
     if (mirror && act)
-        outp_t = prm.out + (long long)(mu0t - prm.out_mu_base) * prm.M1 * prm.M2 + __ldg(prm.tr2 + mu_lo + e);
+        outp_t = prm.out + (long long)(prm.tr0[mu0e] - prm.out_mu_base) * prm.M1 * prm.M2 + __ldg(prm.tr2 + mu_lo + el);
     double acc[P1][P1];
 #pragma unroll
     for (int a = 0; a < P1; ++a)
