@@ -412,6 +412,7 @@ struct pb200_assembler {
     long long s32_keep_key[5] = {-1, -1, -1, -1, -1};
     int s32_nkeep = 0;
     bool pack_tails = true;                             // several short last batches share a block
+    int s32_whole = -1;                                 // tests: with walk_split > 1, this many tasks stay unsplit
     const double* pair_tab[PB_MAXDIM][3] = {};          // two-row tables of derivative orders (0,1) (0,2) (1,2) for the walks
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
     bool force_walk = false;                            // debugging / tests: never use the lane-span kernels
@@ -458,6 +459,7 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!strcmp(name, "fuse")) { a->fuse = value != 0; return 0; }
     if (!strcmp(name, "fuse23")) { a->fuse23 = value != 0; return 0; }
     if (!strcmp(name, "pack_tails")) { a->pack_tails = value != 0; return 0; }
+    if (!strcmp(name, "s32_whole")) { a->s32_whole = value; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
 }
 
@@ -1176,6 +1178,53 @@ static void fill_s32_axes(const pb200_assembler* a, PbS32Params& p) {
     p.first2 = D2.first_u; p.V2 = D2.Vu; p.ret_mu2 = D2.ret_mu; p.tr2 = D2.tr;
 }
 
+// Tail effect of the fused stages 2 + 3: one block per SM and equal tasks — a slab whose tasks fill the GPU 2.01
+// times pays for 3 waves.  Two remedies, whichever gives the shorter sum of waves (in span steps of axis 1):
+//   * cut axis 1 into K pieces for ALL tasks (K x as many, shorter blocks, p spans of overlap each);
+//   * run the full waves of whole tasks first and cut only the remainder, so that it fits one more, short wave.
+static void choose_s32_pieces(const pb200_assembler* a, PbS32Params& q) {
+    const AxisHost& H1 = a->hax[1];
+    const long long tasks = pb_s32_tasks(q);
+    const int P = H1.U.p, nsp = H1.n, N1 = H1.V.N(), S = a->sm_count;
+    int K = 1;
+    long long n_whole = 0;
+    if (a->walk_split > 1) {
+        K = std::min(a->walk_split, 4);
+        if (a->s32_whole >= 0) n_whole = std::min<long long>(tasks, a->s32_whole);
+    } else if (a->walk_split == 0 && S > 0 && tasks > 0) {
+        double best = (double)((tasks + S - 1) / S) * nsp;
+        for (int k = 2; k <= 4; ++k) {
+            if (nsp / k < 4 * (P + 1)) break;
+            const double cost = (double)((k * tasks + S - 1) / S) * ((double)nsp / k + P + 2);
+            if (cost < 0.95 * best) { best = cost; K = k; }
+        }
+        const long long w = tasks / S, r = tasks - w * S;
+        if (w >= 1 && r > 0) {
+            int k = (int)std::min<long long>(4, S / r);
+            while (k > 1 && nsp / k < 4 * (P + 1)) --k;
+            if (k > 1) {
+                const double cost = (double)w * nsp + ((double)nsp / k + P + 2);
+                if (cost < 0.97 * best) { best = cost; K = k; n_whole = w * S; }
+            }
+        }
+    }
+    K = std::min(K, N1);
+    q.npiece = 0;
+    q.n_whole = 0;
+    if (K > 1) {
+        q.npiece = K;
+        q.n_whole = (int)n_whole;
+        for (int y = 0; y < K; ++y) {
+            const int lo = (int)((long long)N1 * y / K), hi = (int)((long long)N1 * (y + 1) / K);
+            q.pw_lo[y] = lo; q.pw_hi[y] = hi;
+            q.ps_begin[y] = H1.V.supp[2 * lo];
+            q.ps_end[y] = H1.V.supp[2 * (hi - 1) + 1];
+        }
+    }
+    static const bool debug_split = getenv("PB200_DEBUG_SPLIT") != nullptr;
+    if (debug_split) fprintf(stderr, "[pb200] fused stage 2+3: %lld tasks, %d pieces, %d tasks unsplit\n", tasks, q.npiece, q.n_whole);
+}
+
 // tasks of a fused stage-2+3 launch: the kept band entries of axis 0 (uploaded once per slab) and the packing of
 // the short last batches (fused23.cuh)
 static int fill_s32_tasks(pb200_assembler* a, const Slab& S, PbS32Params& q, pbStream st) {
@@ -1606,28 +1655,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                 q.nbatch = pb_lane_batches(a->hax[2].n, a->hax[2].U.p);
                 rc = fill_s32_tasks(a, S, q, st);
                 if (rc) return rc;
-                const long long tasks = pb_s32_tasks(q);
-                const int P = H1.U.p, nsp = H1.n, N1 = H1.V.N();
-                int K = 1;
-                if (a->walk_split > 1) K = std::min(a->walk_split, 4);
-                else if (a->walk_split == 0 && a->sm_count > 0 && tasks > 0) {
-                    double best = (double)((tasks + a->sm_count - 1) / a->sm_count) * nsp;
-                    for (int kk = 2; kk <= 4; ++kk) {
-                        if (nsp / kk < 4 * (P + 1)) break;
-                        const double cost = (double)((kk * tasks + a->sm_count - 1) / a->sm_count) * ((double)nsp / kk + P + 2);
-                        if (cost < 0.95 * best) { best = cost; K = kk; }
-                    }
-                }
-                K = std::min(K, N1);
-                if (K > 1) {
-                    q.npiece = K;
-                    for (int y = 0; y < K; ++y) {
-                        const int lo = (int)((long long)N1 * y / K), hi = (int)((long long)N1 * (y + 1) / K);
-                        q.pw_lo[y] = lo; q.pw_hi[y] = hi;
-                        q.ps_begin[y] = H1.V.supp[2 * lo];
-                        q.ps_end[y] = H1.V.supp[2 * (hi - 1) + 1];
-                    }
-                }
+                choose_s32_pieces(a, q);
                 mark_stage(a, "g23", st);
                 ++g_launches;
                 int e = pb_find_s32(PB200_FORM_CUSTOM, H1.U.p, H1.q)(&q, st);
@@ -1806,34 +1834,7 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
         q.nbatch = pb_lane_batches(H2.n, H2.U.p);
         rc = fill_s32_tasks(a, S, q, st);
         if (rc) return rc;
-        {
-            // Tail effect: one block per SM and ~0.3 ms per block — a slab whose blocks fill the GPU 2.4 times
-            // pays for 3 waves.  Cut axis 1 into K pieces (K x as many, shorter blocks; p spans of overlap
-            // each) when that shortens the sum of the waves.
-            const long long tasks = pb_s32_tasks(q);
-            const int P = H1.U.p, nsp = H1.n, N1 = H1.V.N();
-            int K = 1;
-            if (a->walk_split > 1) {
-                K = std::min(a->walk_split, 4);
-            } else if (a->walk_split == 0 && a->sm_count > 0 && tasks > 0) {
-                double best = (double)((tasks + a->sm_count - 1) / a->sm_count) * nsp;
-                for (int k = 2; k <= 4; ++k) {
-                    if (nsp / k < 4 * (P + 1)) break;
-                    const double cost = (double)((k * tasks + a->sm_count - 1) / a->sm_count) * ((double)nsp / k + P + 2);
-                    if (cost < 0.95 * best) { best = cost; K = k; }
-                }
-            }
-            K = std::min(K, N1);
-            if (K > 1) {
-                q.npiece = K;
-                for (int y = 0; y < K; ++y) {
-                    const int lo = (int)((long long)N1 * y / K), hi = (int)((long long)N1 * (y + 1) / K);
-                    q.pw_lo[y] = lo; q.pw_hi[y] = hi;
-                    q.ps_begin[y] = H1.V.supp[2 * lo];
-                    q.ps_end[y] = H1.V.supp[2 * (hi - 1) + 1];
-                }
-            }
-        }
+        choose_s32_pieces(a, q);
         mark_stage(a, stiff ? "s23" : "s23_mass", st);
         ++g_launches;
         int e = pb_find_s32(a->form, H1.U.p, H1.q)(&q, st);

@@ -66,6 +66,8 @@ struct PbS32Params {
     // 32 lanes); when tail_k >= 2 such tails of tail_k consecutive kept entries share one block, tail_w lanes each.
     const int* keep;
     int nkeep, tail_k, tail_w;
+    // tasks [0, n_whole) run unsplit even when npiece > 1: full waves of whole tasks, only the remainder in pieces
+    int n_whole;
 };
 // blocks of a launch (per axis-1 piece)
 PB_HD long long pb_s32_tasks(const PbS32Params& prm) {
@@ -75,7 +77,7 @@ PB_HD long long pb_s32_tasks(const PbS32Params& prm) {
 struct PbS32Piece { int s_begin, s_end, w_lo, w_hi; };
 PB_HD PbS32Piece pb_s32_piece(const PbS32Params& prm, int y) {
     PbS32Piece p;
-    if (prm.npiece > 1) { p.s_begin = prm.ps_begin[y]; p.s_end = prm.ps_end[y]; p.w_lo = prm.pw_lo[y]; p.w_hi = prm.pw_hi[y]; }
+    if (prm.npiece > 1 && y >= 0) { p.s_begin = prm.ps_begin[y]; p.s_end = prm.ps_end[y]; p.w_lo = prm.pw_lo[y]; p.w_hi = prm.pw_hi[y]; }
     else { p.s_begin = 0; p.s_end = prm.n1; p.w_lo = 0; p.w_hi = 0x7fffffff; }
     return p;
 }
@@ -331,9 +333,11 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
     int* sAct = reinterpret_cast<int*>(pb_s32_raw + lay.actv);
 
     const int npc = prm.npiece > 1 ? prm.npiece : 1;
-    const PbS32Piece pc = pb_s32_piece(prm, blockIdx.x % npc);
+    // block -> (task, piece of axis 1); the first n_whole tasks are not cut
+    const bool whole = (int)blockIdx.x < prm.n_whole;
+    const int task = whole ? (int)blockIdx.x : prm.n_whole + ((int)blockIdx.x - prm.n_whole) / npc;
+    const PbS32Piece pc = pb_s32_piece(prm, whole ? -1 : ((int)blockIdx.x - prm.n_whole) % npc);
     // task -> (kept entries, batch): one entry and 32 lanes, or up to tail_k entries with tail_w lanes each
-    const int task = blockIdx.x / npc;
     const int nb_full = prm.tail_k > 1 ? prm.nbatch - 1 : prm.nbatch;
     const bool packed = task >= prm.nkeep * nb_full;
     const int kidx = packed ? (task - prm.nkeep * nb_full) * prm.tail_k : task / nb_full;

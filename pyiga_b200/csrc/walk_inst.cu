@@ -176,7 +176,7 @@ int launch_s32(const PbS32Params* prm, void* stream) {
         if (e != cudaSuccess) return (int)e;
         if (devno < 64) configured |= 1ull << devno;
     }
-    const long long blocks = pb_s32_tasks(*prm) * std::max(1, prm->npiece);
+    const long long blocks = prm->n_whole + (pb_s32_tasks(*prm) - prm->n_whole) * std::max(1, prm->npiece);
     if (blocks <= 0) return 0;
     kern<<<(unsigned)blocks, (PB_Q * PbS32Split<Form, PB_P, PB_Q>::NH + PbS32Cfg<PB_P>::NCW) * 32, lay.total, (cudaStream_t)stream>>>(*prm);
     return (int)cudaGetLastError();

@@ -306,6 +306,20 @@ def test_fused_pipeline_shapes(cuda, form, p, ns, split):
     assert np.abs(fused - plain).max() <= 1e-13 * np.abs(plain).max()
 
 
+@pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
+@pytest.mark.parametrize('whole', [0, 7, 10 ** 6])
+def test_fused_mixed_pieces(cuda, form, whole):
+    """fused stages 2+3 with the first `whole` tasks unsplit and the rest cut into axis-1 pieces (what the
+    scheduler does with the remainder of the last wave), with and without packed last batches"""
+    asm = pc.check_vs_oracle(3, (3, 3, 3), (3, 36, 35), form, walk_split=3)
+    ref = cuda.to_host(asm.dev.assemble_mlb())
+    asm.dev.set_option('s32_whole', whole)
+    for pack in (1, 0):
+        asm.dev.set_option('pack_tails', pack)
+        got = cuda.to_host(asm.dev.assemble_mlb())
+        assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), (whole, pack)
+
+
 def test_fused_fallbacks(cuda):
     """configurations outside the fused kernels' domain take the unfused pipeline and stay correct: mixed
     degrees on axes 1 and 2, repeated knots, degree 4, B-spline geometry with a long control net"""
