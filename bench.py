@@ -352,7 +352,7 @@ def run_distributed_cg(a, kvs, geo, rank, world, barrier):
     be = _device.backend()
     ok, cg, err_msg = 1.0, None, None
     try:
-        sa = SlabAssembly(kvs, geo, 'mass', rank=rank, world=world)
+        sa = SlabAssembly(kvs, geo, 'mass', rank=rank, world=world, balance='entries')
         mlb = sa.assemble_mlb()
         Ainv = [np.linalg.inv(assemble.bsp_mass_1d(kv).toarray()) for kv in kvs]
         cg = DistributedCG(sa.dev.device_structure, mlb, sa.slabs, rank, Ainv)

@@ -37,6 +37,7 @@ class DeviceAssembler:
         dim = len(kvs0)
         assert len(kvs1) == dim
         self.dim = dim
+        self.form = form
         self.kvs = (kvs0, kvs1)
         self.nqp = int(nqp) if nqp else max(kv.p for kv in kvs0) + 1
         meshes = [kv.mesh for kv in kvs0]

@@ -8,13 +8,21 @@ the two neighbouring ranks), see :class:`SlabOperator`.
 import numpy as np
 
 
-def partition_rows(dev, nparts):
-    """Split the rows of axis 0 into `nparts` contiguous slabs with balanced band counts
-    (boundary rows have shorter bands).  Returns a list of (row_begin, row_end); slabs may be
-    empty only if there are fewer rows than parts."""
+def partition_rows(dev, nparts, balance='entries'):
+    """Split the rows of axis 0 into `nparts` contiguous slabs.  Returns a list of (row_begin, row_end); slabs may
+    be empty only if there are fewer rows than parts.
+
+    balance='entries': equal numbers of band entries (what a matvec or CG on the slabs costs; boundary rows have
+    shorter bands).  balance='assembly': equal ASSEMBLY work — a slab pays for every span its rows see in stage 1
+    (p more than it owns unless it starts at the boundary) and, in stages 2 + 3, for the band entries it computes:
+    for the symmetric forms the upper ones plus the lower ones whose partner row lies in another slab."""
     rs = np.asarray(dev.row_start0(), dtype=np.int64)
     n = len(rs) - 1
     nparts = int(nparts)
+    if balance == 'assembly' and 1 < nparts <= n:
+        cuts = _partition_by_work(dev, nparts)
+        if cuts is not None:
+            return [(cuts[i], cuts[i + 1]) for i in range(nparts)]
     cuts = [0]
     for r in range(1, nparts):
         target = rs[-1] * r / nparts
@@ -26,6 +34,65 @@ def partition_rows(dev, nparts):
     return [(cuts[i], cuts[i + 1]) for i in range(nparts) if cuts[i + 1] > cuts[i]]
 
 
+def _partition_by_work(dev, nparts):
+    """contiguous partition of the axis-0 rows minimising the largest slab cost
+        cost(ra, rb) = ALPHA * spans(ra, rb) + entries(ra, rb)
+    with spans = mesh spans in the supports of rows [ra, rb) and entries = band entries of axis 0 the slab computes.
+    ALPHA = 0.8 (p + 1): ratio of the measured stage-1 time per span to the stage-2+3 time per band entry of the
+    fused kernels (B200, p = 3: 28 us per span, 8.9 us per entry at n = 128; mass 12 / 3.8 us)."""
+    from . import _lib
+    kv = dev.kvs[1][0]
+    supp = np.asarray(kv.mesh_support_idx_all(), dtype=np.int64)
+    bidx = np.asarray(dev.structure.bidx[0], dtype=np.int64)
+    I, J = bidx[:, 0], bidx[:, 1]
+    n = supp.shape[0]
+    symmetric = dev.same_space and dev.form in (_lib.FORM_MASS, _lib.FORM_STIFFNESS)
+    alpha = 0.8 * (kv.p + 1)
+    rs = np.searchsorted(I, np.arange(n + 1))
+    upper = np.concatenate(([0], np.cumsum(np.bincount(I[J >= I], minlength=n)))) if symmetric else rs
+
+    def cost(ra, rb):
+        spans = supp[rb - 1, 1] - supp[ra, 0]
+        ent = upper[rb] - upper[ra]
+        if symmetric:       # lower entries whose partner row is outside the slab
+            lo, hi = rs[ra], rs[min(rb, ra + kv.p + 1)]
+            ent += int(np.count_nonzero(J[lo:hi] < ra))
+        return alpha * spans + ent
+
+    def cuts_for(limit):
+        cuts, ra = [0], 0
+        for _ in range(nparts):
+            rb = ra + 1
+            if rb > n or cost(ra, rb) > limit:
+                return None
+            while rb < n and cost(ra, rb + 1) <= limit:
+                rb += 1
+            cuts.append(rb)
+            ra = rb
+            if ra == n:
+                break
+        return cuts if cuts[-1] == n else None
+
+    lo, hi = 0.0, float(cost(0, n))
+    best = None
+    for _ in range(48):
+        mid = 0.5 * (lo + hi)
+        c = cuts_for(mid)
+        if c is None:
+            lo = mid
+        else:
+            best, hi = c, mid
+    if best is None or len(best) - 1 > nparts:
+        return None
+    # the greedy fill may need fewer slabs than ranks: split the largest ones until every rank has rows
+    while len(best) - 1 < nparts:
+        k = max(range(len(best) - 1), key=lambda i: best[i + 1] - best[i])
+        if best[k + 1] - best[k] < 2:
+            return None
+        best.insert(k + 1, (best[k] + best[k + 1]) // 2)
+    return best
+
+
 class SlabAssembly:
     """One rank's share of a slab-sharded assembly (public multi-GPU entry point).
 
@@ -33,7 +100,9 @@ class SlabAssembly:
     on the Gauss planes its rows see, and assembles its row slab independently — no collective.
     """
 
-    def __init__(self, kvs, geo, form, rank=0, world=1, nqp=None):
+    def __init__(self, kvs, geo, form, rank=0, world=1, nqp=None, balance='assembly'):
+        """`balance`: 'assembly' (equal assembly work per rank) or 'entries' (equal band entries: the choice when
+        the slabs are then used by the distributed matvec / CG), see :func:`partition_rows`"""
         from . import _lib, assemblers
         n0 = tuple(kvs)[0].numdofs
         if world > n0:
@@ -41,7 +110,7 @@ class SlabAssembly:
         self.form = {'mass': _lib.FORM_MASS, 'stiffness': _lib.FORM_STIFFNESS}[form]
         self.geo = geo
         self.dev = assemblers.DeviceAssembler(tuple(kvs), None, self.form, nqp=nqp)
-        slabs = partition_rows(self.dev, world)
+        slabs = partition_rows(self.dev, world, balance=balance)
         self.slabs = slabs
         self.rows = slabs[rank] if rank < len(slabs) else None
         self.rank, self.world = rank, world

@@ -35,7 +35,7 @@ def main():
     be = _device.backend()
     kvs = 3 * (bspline.make_knots(a.p, 0.0, 1.0, a.n),)
     geo = geometry.twisted_nurbs_box() if a.geo == 'nurbs' else geometry.twisted_box()
-    sa = SlabAssembly(kvs, geo, 'mass', rank=rank, world=world)
+    sa = SlabAssembly(kvs, geo, 'mass', rank=rank, world=world, balance='entries')
     mlb = sa.assemble_mlb()
     Ainv = [np.linalg.inv(assemble.bsp_mass_1d(kv).toarray()) for kv in kvs]
     cg = DistributedCG(sa.dev.device_structure, mlb, sa.slabs, rank, Ainv)

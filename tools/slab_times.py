@@ -36,10 +36,10 @@ def main():
             sa.assemble_mlb(out=out, workspace=ws, tabulate=True)
         e1.record()
         torch.cuda.synchronize()
-        sa.dev.set_option('timing', 1)
+        sa.dev.set_timing(True)
         sa.assemble_mlb(out=out, workspace=ws, tabulate=True)
         torch.cuda.synchronize()
-        st = sa.dev.stage_times() if hasattr(sa.dev, 'stage_times') else {}
+        st = dict(sa.dev.stage_times())
         res.append({'rank': rank, 'rows': list(sa.rows), 'nnz': sa.local_nnz, 'ms': e0.elapsed_time(e1) / 10,
                     'stages': {k: round(v, 4) for k, v in st.items()}})
         del sa, out, ws
