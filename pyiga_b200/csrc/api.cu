@@ -883,15 +883,19 @@ static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, co
     auto reserve = [&](size_t b) { size_t o = (bytes + 255) & ~size_t(255); bytes = o + b; return o; };
     size_t off_k[PB_MAXDIM], off_f[PB_MAXDIM], off_v[PB_MAXDIM], off_c;
     long long ncoef = 1;
+    // host data (knot vectors, control net) first and contiguous: ONE host->device copy per call
     for (int k = 0; k < dim; ++k) {
         if (geo->p[k] < 0 || geo->p[k] > PB_MAXP) return fail(PB200_EUNSUPPORTED, "geometry degree %d not supported", geo->p[k]);
         if (!geo->h_knots[k] || geo->nknots[k] < 2 * (geo->p[k] + 1)) return fail(PB200_EINVAL, "invalid geometry knot vector");
         off_k[k] = reserve(sizeof(double) * geo->nknots[k]);
-        off_f[k] = reserve(sizeof(int) * G[k]);
-        off_v[k] = reserve(sizeof(double) * G[k] * 2 * (geo->p[k] + 1));
         ncoef *= geo->nknots[k] - geo->p[k] - 1;
     }
     off_c = reserve(sizeof(double) * ncoef * nc);
+    const size_t host_bytes = bytes;
+    for (int k = 0; k < dim; ++k) {
+        off_f[k] = reserve(sizeof(int) * G[k]);
+        off_v[k] = reserve(sizeof(double) * G[k] * 2 * (geo->p[k] + 1));
+    }
     if (reuse && *reuse && *reuse_bytes >= bytes + 256) {
         T.mem = *reuse;
     } else {
@@ -902,11 +906,16 @@ static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, co
     char* b = (char*)T.mem;
     PbGeoDev& D = T.dev;
     D.sdim = dim; D.dim = geo->dim; D.nc = nc; D.rational = geo->rational ? 1 : 0;
+    {
+        std::vector<char> stage(host_bytes, 0);
+        for (int k = 0; k < dim; ++k) memcpy(stage.data() + off_k[k], geo->h_knots[k], sizeof(double) * geo->nknots[k]);
+        memcpy(stage.data() + off_c, geo->h_coeffs, sizeof(double) * ncoef * nc);
+        CK(pbMemcpyH2D(b, stage.data(), host_bytes, st));       // pageable source: staged by the driver before it returns
+    }
     BasisJobs J;
     for (int k = 0; k < dim; ++k) {
         D.pg[k] = geo->p[k];
         D.Ng[k] = geo->nknots[k] - geo->p[k] - 1;
-        CK(pbMemcpyH2D(b + off_k[k], geo->h_knots[k], sizeof(double) * geo->nknots[k], st));
         D.gfirst[k] = (const int*)(b + off_f[k]);
         D.GV[k] = (const double*)(b + off_v[k]);
         J.add((const double*)(b + off_k[k]), geo->nknots[k], geo->p[k], d_nodes[k], G[k], 2, (int*)(b + off_f[k]),
@@ -914,7 +923,6 @@ static int build_geo_tables(const pb200_geo_desc* geo, int dim, const int* G, co
     }
     k_basis_batch(J, st);
     for (int k = dim; k < PB_MAXDIM; ++k) { D.pg[k] = 0; D.Ng[k] = 1; D.gfirst[k] = nullptr; D.GV[k] = nullptr; }
-    CK(pbMemcpyH2D(b + off_c, geo->h_coeffs, sizeof(double) * ncoef * nc, st));
     D.coeffs = (const double*)(b + off_c);
     CK(pbLastError());
     return 0;
@@ -1189,7 +1197,7 @@ static void choose_s32_pieces(const pb200_assembler* a, PbS32Params& q) {
     int K = 1;
     long long n_whole = 0;
     if (a->walk_split > 1) {
-        K = std::min(a->walk_split, 4);
+        K = std::min(a->walk_split, PB_S32_MAXPIECE);
         if (a->s32_whole >= 0) n_whole = std::min<long long>(tasks, a->s32_whole);
     } else if (a->walk_split == 0 && S > 0 && tasks > 0) {
         double best = (double)((tasks + S - 1) / S) * nsp;
@@ -1200,7 +1208,7 @@ static void choose_s32_pieces(const pb200_assembler* a, PbS32Params& q) {
         }
         const long long w = tasks / S, r = tasks - w * S;
         if (w >= 1 && r > 0) {
-            int k = (int)std::min<long long>(4, S / r);
+            int k = (int)std::min<long long>(PB_S32_MAXPIECE, S / r);
             while (k > 1 && nsp / k < 4 * (P + 1)) --k;
             if (k > 1) {
                 const double cost = (double)w * nsp + ((double)nsp / k + P + 2);

@@ -34,6 +34,7 @@ struct PbPlanPairU {    // [0,0] + [0,1] -> one output
     }
 };
 
+#define PB_S32_MAXPIECE 8
 struct PbS32Params {
     // ---- input: X1 terms, plane (mu0 - x1_mu_base) of term t at X1 + t * x1_stride ----------------
     const double* X1;
@@ -58,7 +59,7 @@ struct PbS32Params {
     // piece y retires the pairs (i1, j1) whose row i1 lies in [pw_lo[y], pw_hi[y]) and walks only the spans
     // those rows see; the pieces overlap by p spans (same scheme as the walk-axis pieces of walk.cuh)
     int npiece;
-    int ps_begin[4], ps_end[4], pw_lo[4], pw_hi[4];
+    int ps_begin[PB_S32_MAXPIECE], ps_end[PB_S32_MAXPIECE], pw_lo[PB_S32_MAXPIECE], pw_hi[PB_S32_MAXPIECE];
     // ---- generic forms (PbS32Generic): X1 term read by input stream i, or -1 when the form has no such term ----
     int in_slot[9];
     // ---- tasks of the CUDA kernel: the band entries mu0 this launch computes (pb_s32_keep), in order ----------
