@@ -1810,7 +1810,8 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
                 const long long nf2 = g.Ng[2] - g.pg[2];
                 const long long ng0 = (long long)(S.sb - S.sa) * a->hax[0].q;
                 const size_t need = (size_t)(nf2 * ng0 * G1) * (size_t)pb_geo_u_row(g) * sizeof(double);
-                if (a->geo_utab && nf2 >= 1 && nf2 <= 4 && need <= ((size_t)1 << 30)) {
+                // (a warp must sit on one line index g1 and one geometry span of axis 2: its 32 lines share the rows)
+                if (a->geo_utab && nf2 == 1 && G2 % 32 == 0 && need <= ((size_t)1 << 30)) {
                     if (need > a->geo_u_bytes) {
                         if (a->geo_u) { CK(pbStreamSync(st)); CK(pbFree(a->geo_u)); a->geo_u = nullptr; a->geo_u_bytes = 0; }
                         CK(pbMalloc((void**)&a->geo_u, need + 256));

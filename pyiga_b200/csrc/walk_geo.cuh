@@ -43,7 +43,7 @@ struct PbGeoLineParams {
     const double* gw[PB_MAXDIM];    // Gauss weights per axis
     int G1, G2;                     // nodes on axes 1 and 2 (the line index is g1 * G2 + g2)
     // Optional (UTAB variant of the loader): the part of the geometry evaluation that does not depend on g2,
-    //     U[f2][g0 - u_g0][g1][a2][v][c] = sum_{a0,a1} w_v(a0, a1) coeffs[f0+a0][f1+a1][f2+a2][c],
+    //     U[f2][g1][g0 - u_g0][a2][v][c] = sum_{a0,a1} w_v(a0, a1) coeffs[f0+a0][f1+a1][f2+a2][c],
     // w_0 = N0 N1, w_1 = N0' N1, w_2 = N0 N1', tabulated by pb_geo_u_point for the nodes [u_g0, u_g0 + u_ng0) of
     // axis 0 and every geometry span f2 of axis 2 (PB_GEO_UC components per entry, padded with zeros).
     const double* U;
@@ -55,9 +55,9 @@ PB_HD int pb_geo_u_row(const PbGeoDev& geo) { return (geo.pg[2] + 1) * 3 * PB_GE
 // one (f2, g0, g1) row of the table U
 PB_HD void pb_geo_u_point(const PbGeoLineParams& gp, double* U, long long t) {
     const PbGeoDev& geo = gp.geo;
-    const int g1 = (int)(t % gp.G1);
-    const long long r = t / gp.G1;
-    const int g0 = gp.u_g0 + (int)(r % gp.u_ng0), f2 = (int)(r / gp.u_ng0);
+    const int g0 = gp.u_g0 + (int)(t % gp.u_ng0);
+    const long long r = t / gp.u_ng0;
+    const int g1 = (int)(r % gp.G1), f2 = (int)(r / gp.G1);
     const int pg0 = geo.pg[0], pg1 = geo.pg[1], pg2 = geo.pg[2], nc = geo.nc;
     const int f0 = geo.gfirst[0][g0], f1 = geo.gfirst[1][g1];
     const double* T0 = geo.GV[0] + (long long)g0 * 2 * (pg0 + 1);
@@ -104,9 +104,11 @@ struct PbGeoLoader {
     double* F;              // staged fields of the current span: F[(gq * NOPS + i) * fs], private to the thread
     int fs;
     // UTAB: the thread's column Z holds the pairs (N2_a2, N2'_a2)(g2); U rows of the line, node g0 at Ub + (g0 - u_g0) * ustep
-    const double* Ub;
-    long long ustep;
+    const double* Ub;       // row of node u_g0 of this line; consecutive nodes follow each other (urow doubles each)
+    int urow;
     int u_g0, pg2;
+    double* Us;             // device: the warp's staging buffer for the rows of two spans (cp.async one span ahead)
+    int u_issued;           // device: first span whose rows have not been requested yet
 
     // reduce the control net over axes 1 and 2 at (g1, g2) into Zbuf (stride zstride)
     PB_HD void init(const PbGeoLineParams& gp, int x, double* Zbuf, int zstride) {
@@ -118,9 +120,9 @@ struct PbGeoLoader {
         if constexpr (UTAB) {
             pg2 = geo.pg[2];
             u_g0 = gp.u_g0;
-            const int row = pb_geo_u_row(geo);
-            ustep = (long long)gp.G1 * row;
-            Ub = gp.U + ((long long)geo.gfirst[2][g2] * gp.u_ng0 * gp.G1 + g1) * row;
+            urow = pb_geo_u_row(geo);
+            Ub = gp.U + ((long long)geo.gfirst[2][g2] * gp.G1 + g1) * gp.u_ng0 * urow;
+            u_issued = -1;
             const double* T2 = geo.GV[2] + (long long)g2 * 2 * (pg2 + 1);
             for (int a2 = 0; a2 <= pg2; ++a2) {
                 Zbuf[pb_col(2 * a2, zstride)] = T2[a2];
@@ -187,17 +189,40 @@ struct PbGeoLoader {
     }
 
     // evaluate the fields of the Q nodes of span s into the staging column
+#if defined(__CUDA_ARCH__)
+    // request the U rows of span sp (Q consecutive rows, contiguous) into half sp & 1 of the warp's buffer
+    PB_D void u_issue(int sp) {
+        const int lane = threadIdx.x & 31;
+        const double* src = Ub + (long long)(sp * Q - u_g0) * urow;
+        double* dst = Us + (sp & 1) * (Q * urow);
+        for (int c = lane; c < Q * urow / 2; c += 32) pb_cp_async16(dst + 2 * c, src + 2 * c);
+        pb_cp_async_commit();
+    }
+#endif
     PB_HD void begin_span(int s) {
         constexpr int GD = 3;
         constexpr bool RAT = (NC == GD + 1);
+        const double* urows = nullptr;
+        if constexpr (UTAB) {
+#if defined(__CUDA_ARCH__)
+            // rows of this span: requested one span ago (or now, at the start of the walk); then ask for the next
+            if (u_issued < 0) { u_issue(s); u_issued = s + 1; }
+            pb_cp_async_wait<0>();
+            __syncwarp();
+            if (s + 1 < s_end) u_issue(s + 1);
+            urows = Us + (s & 1) * (Q * urow);
+#else
+            urows = Ub + (long long)(s * Q - u_g0) * urow;
+#endif
+        }
 #pragma unroll (Plan::NOUT > 1 ? 2 : 4)
         for (int gq = 0; gq < Q; ++gq) {
             const int g0 = s * Q + gq;
             double val[NC], dv[NC][3];
             if constexpr (UTAB) {
-                // the g2-independent sums come from the table (the same address for the whole warp unless it
-                // straddles a geometry knot of axis 2: one wavefront per load instead of four)
-                const double* row = Ub + (long long)(g0 - u_g0) * ustep;
+                // the g2-independent sums come from the table (staged in shared memory per warp; the same address for
+                // all lanes: one wavefront per load instead of four)
+                const double* row = urows + gq * urow;
                 for (int a2 = 0; a2 <= pg2; ++a2) {
                     const double2 wd = pb_col_pair(Z, 2 * a2, zs);
                     double u[3][PB_GEO_UC];
@@ -205,7 +230,7 @@ struct PbGeoLoader {
                     for (int v = 0; v < 3; ++v)
 #pragma unroll
                         for (int k = 0; k < PB_GEO_UC / 2; ++k) {
-                            const double2 t = pb_ldg2(row + (a2 * 3 + v) * PB_GEO_UC + 2 * k);
+                            const double2 t = *reinterpret_cast<const double2*>(row + (a2 * 3 + v) * PB_GEO_UC + 2 * k);
                             u[v][2 * k] = t.x;
                             u[v][2 * k + 1] = t.y;
                         }
@@ -320,7 +345,9 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_geo_kernel(const __grid_con
     const int pg0 = gp.geo.pg[0];
     // doubles of the thread's column in front of the staging part: the reduced control net, or (UTAB) the basis pairs of axis 2
     const int zcol = UTAB ? 2 * (gp.geo.pg[2] + 1) : gp.geo.Ng[0] * PbGeoLoader<Plan, Q, NC, Prog>::ZI;
-    const int nz = zcol + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P);
+    // UTAB: per warp, the U rows of two spans (2 Q rows), expressed in doubles per thread
+    const int nu = UTAB ? (2 * Q * pb_geo_u_row(gp.geo) + 31) / 32 : 0;
+    const int nz = zcol + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P) + nu;
     size_t vbytes, ibytes, gbytes, zbytes;
     pb_walk_geo_smem<P, Q>(rg, pg0, nz, vbytes, ibytes, gbytes, zbytes);
     const long long first_node = (long long)rg.s_begin * Q;
@@ -385,6 +412,7 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_geo_kernel(const __grid_con
         PbGeoLoader<Plan, Q, NC, Prog, UTAB> ld;
         ld.init(gp, (int)(tid % prm.X), sZ + 2 * threadIdx.x, 128);
         ld.F = sZ + (size_t)zcol * 128 + 2 * threadIdx.x;
+        if constexpr (UTAB) ld.Us = sZ + (size_t)(zcol + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P)) * 128 + (size_t)(threadIdx.x >> 5) * nu * 32;
         ld.fs = 128;
         ld.T0 = sT0 - first_node * 2 * (pg0 + 1);
         ld.W0 = sW0 - first_node;

@@ -129,7 +129,8 @@ int launch_geo_nc(const PbWalkParams* prm, const PbGeoLineParams& gp, int use_sm
     size_t smem = 0;
     for (int y = 0; y < ny; ++y) {
         size_t vb, ib, gb, zb;
-        pb_walk_geo_smem<PB_P, PB_Q>(pb_walk_range(*prm, y), gp.geo.pg[0], zcol + PbGeoLoader<Plan, PB_Q, NC, Prog>::stage_doubles(PB_P), vb, ib, gb, zb);
+        const int nu = UTAB ? (2 * PB_Q * pb_geo_u_row(gp.geo) + 31) / 32 : 0;
+        pb_walk_geo_smem<PB_P, PB_Q>(pb_walk_range(*prm, y), gp.geo.pg[0], zcol + PbGeoLoader<Plan, PB_Q, NC, Prog>::stage_doubles(PB_P) + nu, vb, ib, gb, zb);
         smem = std::max(smem, vb + ib + gb + zb);
     }
     if (use_smem < 0) {     // query: resident blocks per SM
