@@ -412,9 +412,6 @@ struct pb200_assembler {
     long long s32_keep_key[5] = {-1, -1, -1, -1, -1};
     int s32_nkeep = 0;
     bool pack_tails = true;                             // several short last batches share a block
-    bool geo_utab = true;                               // fused stage 1: tabulate the g2-independent part of the geometry (walk_geo.cuh)
-    double* geo_u = nullptr;                            // that table, kept between calls
-    size_t geo_u_bytes = 0;
     int s32_whole = -1;                                 // tests: with walk_split > 1, this many tasks stay unsplit
     const double* pair_tab[PB_MAXDIM][3] = {};          // two-row tables of derivative orders (0,1) (0,2) (1,2) for the walks
     bool lane_ok[PB_MAXDIM] = {false, false, false};   // single interior knots on the axis
@@ -462,7 +459,6 @@ extern "C" int pb200_asm_set_option(pb200_assembler* a, const char* name, int va
     if (!strcmp(name, "fuse")) { a->fuse = value != 0; return 0; }
     if (!strcmp(name, "fuse23")) { a->fuse23 = value != 0; return 0; }
     if (!strcmp(name, "pack_tails")) { a->pack_tails = value != 0; return 0; }
-    if (!strcmp(name, "geo_utab")) { a->geo_utab = value != 0; return 0; }
     if (!strcmp(name, "s32_whole")) { a->s32_whole = value; return 0; }
     return fail(PB200_EINVAL, "unknown option '%s'", name);
 }
@@ -825,7 +821,6 @@ extern "C" int pb200_asm_destroy(pb200_assembler* a) {
     if (a->pool.dev) pbFree(a->pool.dev);
     if (a->geo_scratch) pbFree(a->geo_scratch);
     if (a->s32_keep_dev) pbFree(a->s32_keep_dev);
-    if (a->geo_u) pbFree(a->geo_u);
     delete a;
     return 0;
 }
@@ -1801,25 +1796,6 @@ extern "C" int pb200_asm_assemble_mlb(pb200_assembler* a, int row0_begin, int ro
             gl.geo = a->geo_dev;
             for (int k = 0; k < 3; ++k) gl.gw[k] = a->dax[k].weights;
             gl.G1 = (int)G1; gl.G2 = (int)G2;
-            gl.U = nullptr; gl.u_g0 = 0; gl.u_ng0 = 0;
-            {
-                // geometries with few spans along axis 2 (all stock ones have one): the part of the evaluation that
-                // does not depend on g2 is tabulated per launch and read warp-uniformly instead of the thread-private
-                // control-net columns (4x fewer shared-memory wavefronts for the geometry)
-                const PbGeoDev& g = a->geo_dev;
-                const long long nf2 = g.Ng[2] - g.pg[2];
-                const long long ng0 = (long long)(S.sb - S.sa) * a->hax[0].q;
-                const size_t need = (size_t)(nf2 * ng0 * G1) * (size_t)pb_geo_u_row(g) * sizeof(double);
-                // (a warp must sit on one line index g1 and one geometry span of axis 2: its 32 lines share the rows)
-                if (a->geo_utab && nf2 == 1 && G2 % 32 == 0 && need <= ((size_t)1 << 30)) {
-                    if (need > a->geo_u_bytes) {
-                        if (a->geo_u) { CK(pbStreamSync(st)); CK(pbFree(a->geo_u)); a->geo_u = nullptr; a->geo_u_bytes = 0; }
-                        CK(pbMalloc((void**)&a->geo_u, need + 256));
-                        a->geo_u_bytes = need;
-                    }
-                    gl.U = a->geo_u; gl.u_g0 = S.sa * a->hax[0].q; gl.u_ng0 = (int)ng0;
-                }
-            }
             p.geo_line = &gl;
             if (stiff) {
                 for (int t = 0; t < 6; ++t) { p.out[t] = X1 + t * s1; p.w_mode[t] = modes1[t]; }

@@ -26,13 +26,6 @@
 // sits at ((e >> 1) * stride) * 2 + (e & 1), stride counted in pairs (128 on the device: the pairs of
 // the 128 threads of a block are contiguous, so that a 16-byte access per thread is conflict-free;
 // 1 in the sequential emulation).  Even / odd neighbours are read with one 128-bit load.
-PB_HD double2 pb_ldg2(const double* p) {
-#if defined(__CUDA_ARCH__)
-    return __ldg(reinterpret_cast<const double2*>(p));
-#else
-    double2 v; v.x = p[0]; v.y = p[1]; return v;
-#endif
-}
 PB_HD long long pb_col(int e, int stride) { return (long long)(e >> 1) * 2 * stride + (e & 1); }
 PB_HD double2 pb_col_pair(const double* col, int e_even, int stride) {
     return *reinterpret_cast<const double2*>(col + (long long)(e_even >> 1) * 2 * stride);
@@ -42,47 +35,9 @@ struct PbGeoLineParams {
     PbGeoDev geo;
     const double* gw[PB_MAXDIM];    // Gauss weights per axis
     int G1, G2;                     // nodes on axes 1 and 2 (the line index is g1 * G2 + g2)
-    // Optional (UTAB variant of the loader): the part of the geometry evaluation that does not depend on g2,
-    //     U[f2][g1][g0 - u_g0][a2][v][c] = sum_{a0,a1} w_v(a0, a1) coeffs[f0+a0][f1+a1][f2+a2][c],
-    // w_0 = N0 N1, w_1 = N0' N1, w_2 = N0 N1', tabulated by pb_geo_u_point for the nodes [u_g0, u_g0 + u_ng0) of
-    // axis 0 and every geometry span f2 of axis 2 (PB_GEO_UC components per entry, padded with zeros).
-    const double* U;
-    int u_g0, u_ng0;
 };
-#define PB_GEO_UC 4
-PB_HD int pb_geo_u_row(const PbGeoDev& geo) { return (geo.pg[2] + 1) * 3 * PB_GEO_UC; }     // doubles per (g0, g1)
 
-// one (f2, g0, g1) row of the table U
-PB_HD void pb_geo_u_point(const PbGeoLineParams& gp, double* U, long long t) {
-    const PbGeoDev& geo = gp.geo;
-    const int g0 = gp.u_g0 + (int)(t % gp.u_ng0);
-    const long long r = t / gp.u_ng0;
-    const int g1 = (int)(r % gp.G1), f2 = (int)(r / gp.G1);
-    const int pg0 = geo.pg[0], pg1 = geo.pg[1], pg2 = geo.pg[2], nc = geo.nc;
-    const int f0 = geo.gfirst[0][g0], f1 = geo.gfirst[1][g1];
-    const double* T0 = geo.GV[0] + (long long)g0 * 2 * (pg0 + 1);
-    const double* T1 = geo.GV[1] + (long long)g1 * 2 * (pg1 + 1);
-    double* row = U + t * pb_geo_u_row(geo);
-    for (int a2 = 0; a2 <= pg2; ++a2) {
-        double s[3][PB_GEO_UC];
-        for (int v = 0; v < 3; ++v)
-            for (int c = 0; c < PB_GEO_UC; ++c) s[v][c] = 0.0;
-        for (int a0 = 0; a0 <= pg0; ++a0)
-            for (int a1 = 0; a1 <= pg1; ++a1) {
-                const double* cf = geo.coeffs + (((long long)(f0 + a0) * geo.Ng[1] + (f1 + a1)) * geo.Ng[2] + (f2 + a2)) * nc;
-                const double w00 = T0[a0] * T1[a1], w10 = T0[pg0 + 1 + a0] * T1[a1], w01 = T0[a0] * T1[pg1 + 1 + a1];
-                for (int c = 0; c < nc; ++c) {
-                    s[0][c] = fma(w00, cf[c], s[0][c]);
-                    s[1][c] = fma(w10, cf[c], s[1][c]);
-                    s[2][c] = fma(w01, cf[c], s[2][c]);
-                }
-            }
-        for (int v = 0; v < 3; ++v)
-            for (int c = 0; c < PB_GEO_UC; ++c) row[(a2 * 3 + v) * PB_GEO_UC + c] = s[v][c];
-    }
-}
-
-template <class Plan, int Q, int NC, class Prog, bool UTAB = false>
+template <class Plan, int Q, int NC, class Prog>
 struct PbGeoLoader {
     static constexpr int NOPS = Plan::NOPS;
     static constexpr int ZI = (NC * 3 + 1) & ~1;        // doubles per control point of the reduced net (padded to pairs)
@@ -103,12 +58,6 @@ struct PbGeoLoader {
     double gw12;
     double* F;              // staged fields of the current span: F[(gq * NOPS + i) * fs], private to the thread
     int fs;
-    // UTAB: the thread's column Z holds the pairs (N2_a2, N2'_a2)(g2); U rows of the line, node g0 at Ub + (g0 - u_g0) * ustep
-    const double* Ub;       // row of node u_g0 of this line; consecutive nodes follow each other (urow doubles each)
-    int urow;
-    int u_g0, pg2;
-    double* Us;             // device: the warp's staging buffer for the rows of two spans (cp.async one span ahead)
-    int u_issued;           // device: first span whose rows have not been requested yet
 
     // reduce the control net over axes 1 and 2 at (g1, g2) into Zbuf (stride zstride)
     PB_HD void init(const PbGeoLineParams& gp, int x, double* Zbuf, int zstride) {
@@ -117,19 +66,6 @@ struct PbGeoLoader {
         gw12 = gp.gw[1][g1] * gp.gw[2][g2];
         Z = Zbuf; zs = zstride; pg0 = geo.pg[0];
         T0 = geo.GV[0]; F0 = geo.gfirst[0]; W0 = gp.gw[0];
-        if constexpr (UTAB) {
-            pg2 = geo.pg[2];
-            u_g0 = gp.u_g0;
-            urow = pb_geo_u_row(geo);
-            Ub = gp.U + ((long long)geo.gfirst[2][g2] * gp.G1 + g1) * gp.u_ng0 * urow;
-            u_issued = -1;
-            const double* T2 = geo.GV[2] + (long long)g2 * 2 * (pg2 + 1);
-            for (int a2 = 0; a2 <= pg2; ++a2) {
-                Zbuf[pb_col(2 * a2, zstride)] = T2[a2];
-                Zbuf[pb_col(2 * a2 + 1, zstride)] = T2[pg2 + 1 + a2];
-            }
-            return;
-        }
         const int pg1 = geo.pg[1], pg2 = geo.pg[2];
         const int f1 = geo.gfirst[1][g1], f2 = geo.gfirst[2][g2];
         const double* T1 = geo.GV[1] + (long long)g1 * 2 * (pg1 + 1);
@@ -189,70 +125,16 @@ struct PbGeoLoader {
     }
 
     // evaluate the fields of the Q nodes of span s into the staging column
-#if defined(__CUDA_ARCH__)
-    // request the U rows of span sp (Q consecutive rows, contiguous) into half sp & 1 of the warp's buffer
-    PB_D void u_issue(int sp) {
-        const int lane = threadIdx.x & 31;
-        const double* src = Ub + (long long)(sp * Q - u_g0) * urow;
-        double* dst = Us + (sp & 1) * (Q * urow);
-        for (int c = lane; c < Q * urow / 2; c += 32) pb_cp_async16(dst + 2 * c, src + 2 * c);
-        pb_cp_async_commit();
-    }
-#endif
     PB_HD void begin_span(int s) {
         constexpr int GD = 3;
         constexpr bool RAT = (NC == GD + 1);
-        const double* urows = nullptr;
-        if constexpr (UTAB) {
-#if defined(__CUDA_ARCH__)
-            // rows of this span: requested one span ago (or now, at the start of the walk); then ask for the next
-            if (u_issued < 0) { u_issue(s); u_issued = s + 1; }
-            pb_cp_async_wait<0>();
-            __syncwarp();
-            if (s + 1 < s_end) u_issue(s + 1);
-            urows = Us + (s & 1) * (Q * urow);
-#else
-            urows = Ub + (long long)(s * Q - u_g0) * urow;
-#endif
-        }
 #pragma unroll (Plan::NOUT > 1 ? 2 : 4)
         for (int gq = 0; gq < Q; ++gq) {
             const int g0 = s * Q + gq;
-            double val[NC], dv[NC][3];
-            if constexpr (UTAB) {
-                // the g2-independent sums come from the table (staged in shared memory per warp; the same address for
-                // all lanes: one wavefront per load instead of four)
-                const double* row = urows + gq * urow;
-                for (int a2 = 0; a2 <= pg2; ++a2) {
-                    const double2 wd = pb_col_pair(Z, 2 * a2, zs);
-                    double u[3][PB_GEO_UC];
-#pragma unroll
-                    for (int v = 0; v < 3; ++v)
-#pragma unroll
-                        for (int k = 0; k < PB_GEO_UC / 2; ++k) {
-                            const double2 t = *reinterpret_cast<const double2*>(row + (a2 * 3 + v) * PB_GEO_UC + 2 * k);
-                            u[v][2 * k] = t.x;
-                            u[v][2 * k + 1] = t.y;
-                        }
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        if (a2 == 0) {
-                            val[c] = wd.x * u[0][c];
-                            dv[c][0] = wd.x * u[1][c];
-                            dv[c][1] = wd.x * u[2][c];
-                            dv[c][2] = wd.y * u[0][c];
-                        } else {
-                            val[c] = fma(wd.x, u[0][c], val[c]);
-                            dv[c][0] = fma(wd.x, u[1][c], dv[c][0]);
-                            dv[c][1] = fma(wd.x, u[2][c], dv[c][1]);
-                            dv[c][2] = fma(wd.y, u[0][c], dv[c][2]);
-                        }
-                    }
-                }
-            }
-            const int f0 = UTAB ? 0 : F0[g0];
+            const int f0 = F0[g0];
             const double* Tn = T0 + (long long)g0 * 2 * (pg0 + 1);
-            for (int a = 0; a <= (UTAB ? -1 : pg0); ++a) {
+            double val[NC], dv[NC][3];
+            for (int a = 0; a <= pg0; ++a) {
                 const double w = Tn[a], d = Tn[pg0 + 1 + a];
                 double z[ZI];
 #pragma unroll
@@ -305,11 +187,11 @@ struct PbGeoLoader {
 };
 
 // sequential emulation of one line
-template <class Plan, int P, int Q, int NC, class Prog, bool UTAB = false>
+template <class Plan, int P, int Q, int NC, class Prog>
 PB_HD void pb_walk_geo_line(const PbWalkParams& prm, const PbGeoLineParams& gp, long long tid, int piece) {
     alignas(16) double Zloc[PB_GEO_ZMAX + 8];
     alignas(16) double Floc[PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P)];
-    PbGeoLoader<Plan, Q, NC, Prog, UTAB> ld;
+    PbGeoLoader<Plan, Q, NC, Prog> ld;
     ld.init(gp, (int)(tid % prm.X), Zloc, 1);
     ld.F = Floc; ld.fs = 1;
     PbWalkTables tb;
@@ -319,11 +201,6 @@ PB_HD void pb_walk_geo_line(const PbWalkParams& prm, const PbGeoLineParams& gp, 
 }
 
 #if defined(__CUDACC__)
-static __global__ void __launch_bounds__(128) pb_geo_u_kernel(const __grid_constant__ PbGeoLineParams gp, double* U, long long n) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) pb_geo_u_point(gp, U, t);
-}
-
 // shared memory: [ V slice | first + retire tables | geometry axis-0 slice (T0, weights, first) | Z columns ]
 template <int P, int Q>
 PB_HD void pb_walk_geo_smem(const PbWalkRange& rg, int pg0, int nz, size_t& vbytes, size_t& ibytes, size_t& gbytes, size_t& zbytes) {
@@ -336,18 +213,14 @@ PB_HD void pb_walk_geo_smem(const PbWalkRange& rg, int pg0, int nz, size_t& vbyt
     zbytes = (size_t)nz * 128 * sizeof(double);
 }
 
-template <class Plan, int P, int Q, int NC, class Prog, int MINB, bool UTAB = false>
+template <class Plan, int P, int Q, int NC, class Prog, int MINB>
 __global__ void __launch_bounds__(128, MINB) pb_walk_geo_kernel(const __grid_constant__ PbWalkParams prm,
                                                                 const __grid_constant__ PbGeoLineParams gp) {
     extern __shared__ __align__(128) unsigned char pb_smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const PbWalkRange rg = pb_walk_range(prm, blockIdx.y);
     const int pg0 = gp.geo.pg[0];
-    // doubles of the thread's column in front of the staging part: the reduced control net, or (UTAB) the basis pairs of axis 2
-    const int zcol = UTAB ? 2 * (gp.geo.pg[2] + 1) : gp.geo.Ng[0] * PbGeoLoader<Plan, Q, NC, Prog>::ZI;
-    // UTAB: per warp, the U rows of two spans (2 Q rows), expressed in doubles per thread
-    const int nu = UTAB ? (2 * Q * pb_geo_u_row(gp.geo) + 31) / 32 : 0;
-    const int nz = zcol + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P) + nu;
+    const int nz = gp.geo.Ng[0] * PbGeoLoader<Plan, Q, NC, Prog>::ZI + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P);
     size_t vbytes, ibytes, gbytes, zbytes;
     pb_walk_geo_smem<P, Q>(rg, pg0, nz, vbytes, ibytes, gbytes, zbytes);
     const long long first_node = (long long)rg.s_begin * Q;
@@ -409,10 +282,9 @@ __global__ void __launch_bounds__(128, MINB) pb_walk_geo_kernel(const __grid_con
     tb.ret_mu = s_ret - (long long)f_lo * (2 * P + 1);
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < prm.nthreads) {
-        PbGeoLoader<Plan, Q, NC, Prog, UTAB> ld;
+        PbGeoLoader<Plan, Q, NC, Prog> ld;
         ld.init(gp, (int)(tid % prm.X), sZ + 2 * threadIdx.x, 128);
-        ld.F = sZ + (size_t)zcol * 128 + 2 * threadIdx.x;
-        if constexpr (UTAB) ld.Us = sZ + (size_t)(zcol + PbGeoLoader<Plan, Q, NC, Prog>::stage_doubles(P)) * 128 + (size_t)(threadIdx.x >> 5) * nu * 32;
+        ld.F = sZ + (size_t)gp.geo.Ng[0] * PbGeoLoader<Plan, Q, NC, Prog>::ZI * 128 + 2 * threadIdx.x;
         ld.fs = 128;
         ld.T0 = sT0 - first_node * 2 * (pg0 + 1);
         ld.W0 = sW0 - first_node;

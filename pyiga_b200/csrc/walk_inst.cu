@@ -103,19 +103,15 @@ int launch_lane(const PbWalkParams* prm, int lines_per_warp, size_t, void* strea
 }
 
 // fused stage 1 (walk_geo.cuh): geometry and fields are evaluated by the walk itself
-template <class Plan, class Prog, int NC, bool UTAB>
+template <class Plan, class Prog, int NC>
 int launch_geo_nc(const PbWalkParams* prm, const PbGeoLineParams& gp, int use_smem, void* stream) {
 #ifdef PB_EMULATE
     (void)use_smem; (void)stream;
-    if (UTAB) {
-        const long long n = (long long)(gp.geo.Ng[2] - gp.geo.pg[2]) * gp.u_ng0 * gp.G1;
-        pb_emu_for(n, [&](long long t) { pb_geo_u_point(gp, const_cast<double*>(gp.U), t); });
-    }
     for (int y = 0; y < std::max(1, prm->nsplit); ++y)
-        pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_geo_line<Plan, PB_P, PB_Q, NC, Prog, UTAB>(*prm, gp, tid, y); });
+        pb_emu_for(prm->nthreads, [&](long long tid) { pb_walk_geo_line<Plan, PB_P, PB_Q, NC, Prog>(*prm, gp, tid, y); });
     return 0;
 #else
-    auto kern = pb_walk_geo_kernel<Plan, PB_P, PB_Q, NC, Prog, (PB_P >= 4 ? Plan::MINB4 : Plan::MINB), UTAB>;
+    auto kern = pb_walk_geo_kernel<Plan, PB_P, PB_Q, NC, Prog, (PB_P >= 4 ? Plan::MINB4 : Plan::MINB)>;
     static unsigned long long configured = 0;       // bit d: done on device d
     int devno = 0;
     cudaGetDevice(&devno);
@@ -125,12 +121,10 @@ int launch_geo_nc(const PbWalkParams* prm, const PbGeoLineParams& gp, int use_sm
         if (devno < 64) configured |= 1ull << devno;
     }
     const int ny = std::max(1, prm->nsplit);
-    const int zcol = UTAB ? 2 * (gp.geo.pg[2] + 1) : gp.geo.Ng[0] * PbGeoLoader<Plan, PB_Q, NC, Prog>::ZI;
     size_t smem = 0;
     for (int y = 0; y < ny; ++y) {
         size_t vb, ib, gb, zb;
-        const int nu = UTAB ? (2 * PB_Q * pb_geo_u_row(gp.geo) + 31) / 32 : 0;
-        pb_walk_geo_smem<PB_P, PB_Q>(pb_walk_range(*prm, y), gp.geo.pg[0], zcol + PbGeoLoader<Plan, PB_Q, NC, Prog>::stage_doubles(PB_P) + nu, vb, ib, gb, zb);
+        pb_walk_geo_smem<PB_P, PB_Q>(pb_walk_range(*prm, y), gp.geo.pg[0], gp.geo.Ng[0] * PbGeoLoader<Plan, PB_Q, NC, Prog>::ZI + PbGeoLoader<Plan, PB_Q, NC, Prog>::stage_doubles(PB_P), vb, ib, gb, zb);
         smem = std::max(smem, vb + ib + gb + zb);
     }
     if (use_smem < 0) {     // query: resident blocks per SM
@@ -141,10 +135,6 @@ int launch_geo_nc(const PbWalkParams* prm, const PbGeoLineParams& gp, int use_sm
     const long long blocks = (prm->nthreads + 127) / 128;
     if (blocks <= 0) return 0;
     if (prm->out_smu >= (1LL << 31)) return (int)cudaErrorInvalidValue;
-    if (UTAB) {             // the g2-independent part of the geometry evaluation, for the nodes this launch walks
-        const long long n = (long long)(gp.geo.Ng[2] - gp.geo.pg[2]) * gp.u_ng0 * gp.G1;
-        pb_geo_u_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gp, const_cast<double*>(gp.U), n);
-    }
     dim3 grid((unsigned)blocks, (unsigned)ny);
     kern<<<grid, 128, smem, (cudaStream_t)stream>>>(*prm, gp);
     return (int)cudaGetLastError();
@@ -155,11 +145,8 @@ template <class Plan, class Prog>
 int launch_geo(const PbWalkParams* prm, int use_smem, size_t, void* stream) {
     const PbGeoLineParams* gp = static_cast<const PbGeoLineParams*>(prm->geo_line);
     if (!gp || gp->geo.Ng[0] * ((gp->geo.nc * 3 + 1) & ~1) > PB_GEO_ZMAX) return 1;      // cudaErrorInvalidValue
-    if (gp->U)
-        return gp->geo.nc == 4 ? launch_geo_nc<Plan, Prog, 4, true>(prm, *gp, use_smem, stream)
-                               : launch_geo_nc<Plan, Prog, 3, true>(prm, *gp, use_smem, stream);
-    return gp->geo.nc == 4 ? launch_geo_nc<Plan, Prog, 4, false>(prm, *gp, use_smem, stream)
-                           : launch_geo_nc<Plan, Prog, 3, false>(prm, *gp, use_smem, stream);
+    return gp->geo.nc == 4 ? launch_geo_nc<Plan, Prog, 4>(prm, *gp, use_smem, stream)
+                           : launch_geo_nc<Plan, Prog, 3>(prm, *gp, use_smem, stream);
 }
 
 // fused stages 2 + 3 (fused23.cuh); prm->out == nullptr: query, 0 if the configuration can be launched
