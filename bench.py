@@ -179,7 +179,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=f,
+                                          '--format=csv,noheader,nounits', '-lms', os.environ.get('PB200_BENCH_SMI_MS', '20')], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

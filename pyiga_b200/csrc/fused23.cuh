@@ -486,6 +486,9 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
             if (j < nsp) issue(pc.s_begin + j, j);
             pb_cp_async_commit();
         }
+        double nmask[P > 0 ? P : 1];             // 1.0 where the lane has a neighbour q spans below inside its entry
+#pragma unroll
+        for (int q = 1; q <= P; ++q) nmask[q - 1] = lg >= q ? 1.0 : 0.0;
         // one term: local block, neighbour sums, slots of the T row
         auto do_term = [&](auto TT, const double* src, double* Tw) {
             constexpr int t = decltype(TT)::value;
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
                 for (int q = 1; q <= P; ++q) {
                     if (q <= P - d) {
                         const double vsh = __shfl_up_sync(0xffffffffu, (kk <= P) ? L[q][q + d] : L[q + d][q], q);
-                        if (lg >= q) sum += vsh;
+                        sum = fma(nmask[q - 1], vsh, sum);      // lanes below q take nothing (0/1 mask: one FMA, no select)
                     }
                 }
                 if (tpos[kk] >= 0) Tw[t * TPAD + tpos[kk]] = sum;
