@@ -421,10 +421,11 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
 #pragma unroll
                 for (int a = 0; a < P1; ++a) Dreg[gq][fl][a] = sDl[((gq * 2 + fl) * P1 + a) * 32];
 #endif
-        // slot offsets of this lane's entries in a T row (-1: not a writer)
+        // slot offsets of this lane's entries in a T row (TPAD - 1, a slot no entry uses: not a writer)
         int tpos[2 * P + 1];
 #pragma unroll
-        for (int k = 0; k <= 2 * P; ++k) tpos[k] = mu[k] >= 0 ? gl * TG + mu[k] - mu_lo : -1;
+        static_assert((32 + P) * (2 * P + 1) < TPAD, "the T rows need a spare slot");
+        for (int k = 0; k <= 2 * P; ++k) tpos[k] = mu[k] >= 0 ? gl * TG + mu[k] - mu_lo : TPAD - 1;
         const long long seg_node0 = (long long)sb * Q;
         const int seg_nodes = (pb_min(prm.n2, sb + GL) - sb) * Q;   // nodes of one entry's segment
         const int ent_nodes = GL * Q;                                  // ring doubles per entry
@@ -517,18 +518,28 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
 #else
             pb_span_block<TP, P, Q>(xt, Dreg, L);
 #endif
+            // a single input with the same derivative flag on both sides gives a symmetric block: the entry (f+d, f)
+            // equals (f, f+d) of the same lane — no second neighbour sum, and the lower half of L is never formed
+            constexpr bool tsym = TP::NOPS == 1 && TP::op(0).ft == TP::op(0).fu;
+            double upper[P1];
 #pragma unroll
             for (int kk = 0; kk <= 2 * P; ++kk) {
                 const int d = (kk <= P) ? kk : kk - P;
-                double sum = (kk <= P) ? L[0][d] : L[d][0];
+                double sum;
+                if (tsym && kk > P) {
+                    sum = upper[d];
+                } else {
+                    sum = (kk <= P) ? L[0][d] : L[d][0];
 #pragma unroll
-                for (int q = 1; q <= P; ++q) {
-                    if (q <= P - d) {
-                        const double vsh = __shfl_up_sync(0xffffffffu, (kk <= P) ? L[q][q + d] : L[q + d][q], q);
-                        sum = fma(nmask[q - 1], vsh, sum);      // lanes below q take nothing (0/1 mask: one FMA, no select)
+                    for (int q = 1; q <= P; ++q) {
+                        if (q <= P - d) {
+                            const double vsh = __shfl_up_sync(0xffffffffu, (kk <= P) ? L[q][q + d] : L[q + d][q], q);
+                            sum = fma(nmask[q - 1], vsh, sum);      // lanes below q take nothing (0/1 mask: one FMA, no select)
+                        }
                     }
+                    if (kk <= P) upper[d] = sum;
                 }
-                if (tpos[kk] >= 0) Tw[t * TPAD + tpos[kk]] = sum;
+                Tw[t * TPAD + tpos[kk]] = sum;          // entries this lane does not own go to the spare last slot of the row
             }
         };
         int st = 0;
