@@ -449,42 +449,47 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
                 dpl[h][1] = (long long)((prm.symmetric ? prm.tr0[mg] : mg) - mu0t) * ((long long)prm.G1 * prm.G2);
             }
         }
-        // the input streams of this half: global stream index = half * NSTR + j
-        const double* base[NSTR];
-        bool btr[NSTR];
-        pb_static_for<0, NSTR>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            // (both halves are instantiated; select at run time)
-            const int t0 = pb_s32_slot<Form>(prm, j), t1 = pb_s32_slot<Form>(prm, (NH - 1) * NSTR + j);
-            const bool r0 = Form::in_tr(j), r1 = Form::in_tr((NH - 1) * NSTR + j);
-            const int term = half == 0 ? t0 : t1;
-            const bool trn = half == 0 ? r0 : r1;
-            btr[j] = trn;
-            base[j] = term < 0 ? nullptr        // the form has no such term: the (zero-filled) ring slot is never written
-                               : prm.X1 + (long long)term * prm.x1_stride + (long long)((trn ? mu0t : mu0) - prm.x1_mu_base) * plane
-                                     + seg_node0 + (long long)prow * prm.G2;
-        });
-        const long long span_stride = (long long)Q * prm.G2;        // rows of consecutive spans handled by this warp
-        auto issue = [&](int s1, int st) {
+        // Source addresses.  Per copy piece and per kind of stream (read at mu0 / at the transposed entry) the lane
+        // keeps ONE running byte pointer for the next span to request; a stream adds the (warp-uniform) offset of
+        // its X1 term.  (Composing every address from scratch cost six integer instructions per copy, a tenth of
+        // the producers' instruction stream.)
+        const long long span_bytes = (long long)Q * prm.G2 * (long long)sizeof(double);     // consecutive spans of this warp's row
+        const char* cpn[NPIECE][2];
+#pragma unroll
+        for (int h = 0; h < NPIECE; ++h)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                cpn[h][k] = reinterpret_cast<const char*>(prm.X1 + ((long long)((k ? mu0t : mu0) - prm.x1_mu_base) * plane + seg_node0
+                                                                    + (long long)prow * prm.G2 + (goff[h] >= 0 ? goff[h] : 0) + dpl[h][k]
+                                                                    + (long long)pc.s_begin * Q * prm.G2));
+        // requests must come in span order (each call is for the span after the previous one)
+        auto issue = [&](int st) {
             double* dst = ring + (size_t)st * STAGE;
             pb_static_for<0, NSTR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
-                if (Form::RUNTIME && base[j] == nullptr) return;
-                const double* src = base[j] + (long long)s1 * span_stride;
+                // the input stream of this half: global stream index = half * NSTR + j (both halves are instantiated)
+                const int t0 = pb_s32_slot<Form>(prm, j), t1 = pb_s32_slot<Form>(prm, (NH - 1) * NSTR + j);
+                const bool r0 = Form::in_tr(j), r1 = Form::in_tr((NH - 1) * NSTR + j);
+                const int term = half == 0 ? t0 : t1;
+                const bool trn = half == 0 ? r0 : r1;
+                if (Form::RUNTIME && term < 0) return;      // the form has no such term: the (zero-filled) ring slot is never written
+                const long long toff = (long long)term * prm.x1_stride * (long long)sizeof(double);
 #pragma unroll
                 for (int h = 0; h < NPIECE; ++h) {
                     if (goff[h] >= 0) {
-                        const double* sp = src + goff[h] + (btr[j] ? dpl[h][1] : dpl[h][0]);
+                        const char* sp = (trn ? cpn[h][1] : cpn[h][0]) + toff;
                         if constexpr (VEC) pb_cp_async16(dst + j * SEG + soff[h], sp);
                         else pb_cp_async8(dst + j * SEG + soff[h], sp);
                     }
                 }
             });
+#pragma unroll
+            for (int h = 0; h < NPIECE; ++h) { cpn[h][0] += span_bytes; cpn[h][1] += span_bytes; }
         };
 #pragma unroll
         const int nsp = pc.s_end - pc.s_begin;
         for (int j = 0; j < NST - 1; ++j) {
-            if (j < nsp) issue(pc.s_begin + j, j);
+            if (j < nsp) issue(j);
             pb_cp_async_commit();
         }
         double nmask[P > 0 ? P : 1];             // 1.0 where the lane has a neighbour q spans below inside its entry
@@ -546,7 +551,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
         for (int s1 = 0; s1 <= nsp; ++s1) {
             if (s1 < nsp) {
                 __syncwarp();
-                if (s1 + NST - 1 < nsp) issue(pc.s_begin + s1 + NST - 1, (st + NST - 1) % NST);
+                if (s1 + NST - 1 < nsp) issue((st + NST - 1) % NST);
                 pb_cp_async_commit();
                 pb_cp_async_wait<NST - 1>();
                 __syncwarp();
