@@ -472,6 +472,7 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                     });
                 }
             };
+            const long long out_stride = NOUT > 1 ? (long long)(prm.out[NOUT > 1 ? 1 : 0] - prm.out[0]) : 0;
             auto store_staged = [&](int fr, int k0, int k1) {
                 const int* rm = tb.ret_mu + (long long)fr * (2 * P + 1);
                 // unrolled (P+1 entries at most): the table look-ups and staged values of all entries
@@ -493,10 +494,12 @@ PB_HD void pb_walk_line_impl(const PbWalkParams& prm, const PbWalkRange& rg, lon
                         });
                     }
                     mask &= wantbits;
-                    const long long boff = (long long)(band - mu_base) * (long long)smu;
+                    // (the outputs of a rolled walk are equally spaced in memory — the X1 terms of the fused stage 1 —
+                    // so one address per entry plus a warp-uniform stride per output replaces NOUT pointer look-ups)
+                    double* const p0 = outp[0] + (long long)(band - mu_base) * (long long)smu;
                     pb_static_for<0, NOUT>([&](auto O) {
                         constexpr int o = decltype(O)::value;
-                        if (mask & (1 << o)) outp[o][boff] = ld.stage_get((k - k0) * NOUT + o);
+                        if (mask & (1 << o)) p0[o * out_stride] = ld.stage_get((k - k0) * NOUT + o);
                     });
                 }
             };
