@@ -288,14 +288,20 @@ def own_fp64_ops(dev, rows, form, p):
     sym, non = P1 + P1 * (P1 + 1) // 2, P1 + P1 * P1
     n2 = G[2] // P1
     nbatch = 1 + max(0, -(-(n2 + p - 32) // (32 - p)))
-    overlap = nbatch * 32.0 / n2 if n2 >= 32 else 1.0
+    # lanes a band entry of axis 0 occupies: full batches of 32, and the last batch shares its warp with the
+    # tails of other entries when it is narrow enough (fused23.cuh)
+    tail_w = min(32, n2 + p - (nbatch - 1) * (32 - p))
+    tail_k = min(4, 32 // tail_w) if nbatch >= 2 else 1
+    lanes = (nbatch - 1) * 32.0 + 32.0 / max(tail_k, 1)
+    overlap = lanes / n2 if n2 >= 32 else 1.0
     if form == 'stiffness':
         s1 = pts * (4 * sym + 2 * non)
-        a = c3 * G[1] * G[2] * overlap * (9 * P1 + 5 * P1 * P1)
+        # phase A: terms T0 (4 inputs), T1, T2 (2 inputs each) with full blocks, T3 (1 input) with a symmetric one
+        a = c3 * G[1] * G[2] * overlap * (9 * P1 + 4 * P1 * P1 + P1 * (P1 + 1) // 2)
         b = c3 * G[1] * M[2] * (4 * P1 + 2 * P1 * P1)
     else:
         s1 = pts * sym
-        a = c3 * G[1] * G[2] * overlap * non
+        a = c3 * G[1] * G[2] * overlap * sym
         b = c3 * G[1] * M[2] * non
     return {'stage1': float(s1), 'stage23_phaseA': float(a), 'stage23_phaseB': float(b)}
 
