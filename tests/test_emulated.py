@@ -1,6 +1,7 @@
 """CPU run of the parity checks through the sequential host emulation of the kernels
 (tests/emu): covers the host logic of the package and the index logic of every kernel body.
 The numbers that count are produced by tests/test_gpu_parity.py on the B200."""
+import numpy as np
 import pytest
 
 import parity_checks as pc
@@ -209,3 +210,27 @@ def test_entry_func_ptr(emu):
 
 def test_inner_products_vector_valued(emu):
     pc.check_inner_products_vector_valued()
+
+
+@pytest.mark.parametrize('p,n', [(3, 40), (2, 21), (1, 9)])
+def test_partition_by_assembly_work(emu, p, n):
+    """the work-balanced slab partition (dist.partition_rows(balance='assembly')): contiguous cover with one slab
+    per rank, and its largest slab is not more expensive than the entry-balanced one's under the same cost model"""
+    from pyiga_b200 import _lib, assemblers, bspline
+    from pyiga_b200.dist import partition_rows
+    kvs = 3 * (bspline.make_knots(p, 0.0, 1.0, n),)
+    dev = assemblers.DeviceAssembler(kvs, None, _lib.FORM_STIFFNESS)
+    N = kvs[0].numdofs
+    supp = np.asarray(kvs[0].mesh_support_idx_all())
+    bidx = np.asarray(dev.structure.bidx[0], dtype=np.int64)
+
+    def cost(ra, rb):       # the model of dist._partition_by_work
+        rows = (bidx[:, 0] >= ra) & (bidx[:, 0] < rb)
+        ent = np.count_nonzero(rows & ((bidx[:, 1] >= bidx[:, 0]) | (bidx[:, 1] < ra)))
+        return 0.8 * (p + 1) * (supp[rb - 1, 1] - supp[ra, 0]) + ent
+    for world in (2, 3, 5, 8):
+        a = partition_rows(dev, world, balance='assembly')
+        b = partition_rows(dev, world)
+        assert len(a) == world and a[0][0] == 0 and a[-1][1] == N
+        assert all(x[1] == y[0] and x[1] > x[0] for x, y in zip(a, a[1:]))
+        assert max(cost(*s) for s in a) <= max(cost(*s) for s in b) + 1e-9
