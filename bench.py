@@ -457,10 +457,16 @@ def run_extra_configs(be, fp64_peak, hbm_peak):
         form = '(inner(diff_coeff * grad(u), grad(v)) + inner((x[1], -x[0], 1.0), grad(u)) * v) * dx'
         kvs = 3 * (bspline.make_knots(3, 0.0, 1.0, 96),)
         geo = geometry.twisted_box()
-        t0 = time.perf_counter()
-        asm = assemble.instantiate_assembler(form, kvs, {'geo': geo, 'diff_coeff': lambda x, y, z: 1.0 + x * y}, None)
-        torch.cuda.synchronize()
-        setup_ms = 1e3 * (time.perf_counter() - t0)
+        setups = []
+        asm = None
+        for _ in range(2):      # the first call pays for cudaMalloc of the 4.5 GB field buffer (the allocator cache is empty here)
+            del asm
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            asm = assemble.instantiate_assembler(form, kvs, {'geo': geo, 'diff_coeff': lambda x, y, z: 1.0 + x * y}, None)
+            torch.cuda.synchronize()
+            setups.append(1e3 * (time.perf_counter() - t0))
+        setup_ms = setups[-1]
         dev = asm.dev
         res = be.empty(dev.nnz)
         ws = be.empty(dev.workspace_bytes(), np.uint8)
@@ -470,6 +476,7 @@ def run_extra_configs(be, fp64_peak, hbm_peak):
         t_bound = max(F / (fp64_peak * 1e12), 8.0 * nnz / (hbm_peak * 1e9))
         out.append({'workload': '3D convection-diffusion vform p=3 n=96, twisted_box B-spline', 'nnz': int(nnz), 'ms_per_step': ms,
                     'value': nnz / (ms * 1e-3), 'unit': UNIT, 'setup_ms_host_coefficients_and_fields': setup_ms,
+                    'setup_ms_first_call': setups[0],
                     'path_frac': t_bound / (ms * 1e-3), 'path_bound': 'fp64'})
     except Exception as exc:
         out.append({'workload': '3D convection-diffusion vform p=3 n=96', 'error': repr(exc)[:200]})
