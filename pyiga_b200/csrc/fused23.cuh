@@ -421,11 +421,10 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
 #pragma unroll
                 for (int a = 0; a < P1; ++a) Dreg[gq][fl][a] = sDl[((gq * 2 + fl) * P1 + a) * 32];
 #endif
-        // slot offsets of this lane's entries in a T row (TPAD - 1, a slot no entry uses: not a writer)
+        // slot offsets of this lane's entries in a T row (-1: not a writer)
         int tpos[2 * P + 1];
 #pragma unroll
-        static_assert((32 + P) * (2 * P + 1) < TPAD, "the T rows need a spare slot");
-        for (int k = 0; k <= 2 * P; ++k) tpos[k] = mu[k] >= 0 ? gl * TG + mu[k] - mu_lo : TPAD - 1;
+        for (int k = 0; k <= 2 * P; ++k) tpos[k] = mu[k] >= 0 ? gl * TG + mu[k] - mu_lo : -1;
         const long long seg_node0 = (long long)sb * Q;
         const int seg_nodes = (pb_min(prm.n2, sb + GL) - sb) * Q;   // nodes of one entry's segment
         const int ent_nodes = GL * Q;                                  // ring doubles per entry
@@ -544,7 +543,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
                     }
                     if (kk <= P) upper[d] = sum;
                 }
-                Tw[t * TPAD + tpos[kk]] = sum;          // entries this lane does not own go to the spare last slot of the row
+                if (tpos[kk] >= 0) Tw[t * TPAD + tpos[kk]] = sum;
             }
         };
         int st = 0;
