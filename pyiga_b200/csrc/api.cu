@@ -407,6 +407,8 @@ struct pb200_assembler {
     bool ext_slots = false;                             // some term has a second or mixed derivative slot (PB_SLOT_EXT)
     const double* walk_table = nullptr;                 // run_stage: table override of the current launch
     // fused stages 2 + 3: device list of the band entries of axis 0 a launch computes (cached per slab)
+    std::vector<int> s32_keep_host[2];
+    int s32_keep_flip = 0;
     int* s32_keep_dev = nullptr;
     size_t s32_keep_cap = 0;
     long long s32_keep_key[5] = {-1, -1, -1, -1, -1};
@@ -1239,7 +1241,9 @@ static int fill_s32_tasks(pb200_assembler* a, const Slab& S, PbS32Params& q, pbS
     const AxisHost &H0 = a->hax[0], &H2 = a->hax[2];
     const long long key[5] = {S.mu_lo, S.mu_hi, S.ra, S.rb, q.symmetric};
     if (memcmp(key, a->s32_keep_key, sizeof key) != 0 || !a->s32_keep_dev) {
-        std::vector<int> keep;
+        // (the host copy is a member: an asynchronous copy from pageable memory may still read it after this call)
+        std::vector<int>& keep = a->s32_keep_host[a->s32_keep_flip ^= 1];
+        keep.clear();
         for (int mu = S.mu_lo; mu < S.mu_hi; ++mu) {
             const int i0 = H0.pair_i[mu], j0 = H0.pair_j[mu];
             if (!(q.symmetric && j0 >= S.ra && j0 < S.rb && j0 < i0)) keep.push_back(mu);
@@ -1247,13 +1251,10 @@ static int fill_s32_tasks(pb200_assembler* a, const Slab& S, PbS32Params& q, pbS
         if (keep.size() > a->s32_keep_cap) {
             if (a->s32_keep_dev) pbFree(a->s32_keep_dev);
             a->s32_keep_dev = nullptr;
-            a->s32_keep_cap = keep.size() + 64;
+            a->s32_keep_cap = std::max(keep.size(), (size_t)H0.M) + 64;       // every slab of this assembler fits
             CK(pbMalloc((void**)&a->s32_keep_dev, a->s32_keep_cap * sizeof(int)));
         }
-        if (!keep.empty()) {
-            CK(pbMemcpyH2D(a->s32_keep_dev, keep.data(), keep.size() * sizeof(int), st));
-            CK(pbStreamSync(st));           // `keep` goes out of scope
-        }
+        if (!keep.empty()) CK(pbMemcpyH2D(a->s32_keep_dev, keep.data(), keep.size() * sizeof(int), st));
         a->s32_nkeep = (int)keep.size();
         memcpy(a->s32_keep_key, key, sizeof key);
     }
