@@ -159,7 +159,11 @@ PB200_API int pb200_asm_compute_fields_slab(pb200_assembler* a, const pb200_geo_
  * generated precompute_fields of compiled vforms (pyiga/codegen/cython.py:673-701).  d_inputs are
  * coefficient arrays on the full Gauss grid (user callables are evaluated on the host by the
  * caller, exactly as pyiga does, pyiga/codegen/cython.py:465-484).  Give either `geo` or `d_jac`;
- * row0_begin < 0 selects the whole grid. */
+ * row0_begin < 0 selects the whole grid.
+ * This call is also the ABI form of the generated `update(name=func)` / `update_params(name=value)`
+ * (pyiga/codegen/cython.py:703-744): an updated input is a new coefficient array in `d_inputs`, an updated
+ * parameter a new `scale`; the name -> array bookkeeping stays in the host layer (Assembler.update,
+ * pyiga/assemble.py:984-994), nothing else of the assembler is rebuilt. */
 PB200_API int pb200_asm_compute_fields_general(pb200_assembler* a, const pb200_geo_desc* geo, const double* d_jac,
                                                int nphys, const pb200_phys_term* phys, int ninputs,
                                                const double* const* d_inputs, int row0_begin, int row0_end,
