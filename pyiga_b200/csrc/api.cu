@@ -1157,6 +1157,24 @@ static bool uses_transposes(const pb200_assembler* a) { return a->form == PB200_
 
 // 3D mass / stiffness on a bound spline geometry: stage 1 evaluates geometry and fields itself
 // (walk_geo.cuh) — no K2 launch, no field buffer
+// Shared memory of the fused stage 1: the 1D tables of the walked spans are staged per block next to the
+// thread-private columns, and two blocks must fit an SM.  Long axes are therefore walked in pieces (grid.y; the
+// pieces overlap by p spans): the smallest number of pieces for `nspans` spans, 0 if even PB_WALK_MAXSPLIT do not fit.
+static int s1f_pieces(const pb200_assembler* a, int nspans) {
+    const PbGeoDev& g = a->geo_dev;
+    const AxisHost& H = a->hax[0];
+    const int P = H.U.p, Q = H.q;
+    for (int K = 1; K <= PB_WALK_MAXSPLIT; ++K) {
+        const size_t sp = (size_t)std::min(nspans, (nspans + K - 1) / K + (K > 1 ? P + 1 : 0));
+        const size_t nodes = sp * Q;
+        const size_t smem = nodes * 2 * (P + 1) * 8 + (sp + 4 + (sp + P) * (2 * P + 1)) * 4
+                            + nodes * (2 * (g.pg[0] + 1) + 1) * 8 + nodes * 4
+                            + ((size_t)g.Ng[0] * ((g.nc * 3 + 1) & ~1) + (size_t)std::max(Q * 6, (P + 1) * 6) + 2) * 128 * 8 + 1024;
+        if (smem <= 113 * 1024) return K;
+    }
+    return 0;
+}
+
 static bool fused_stage1(const pb200_assembler* a) {
     if (!a->fuse || a->dim != 3 || !a->geo_valid || a->arity != 2 || !a->fast || a->force_walk) return false;
     if (a->form != PB200_FORM_STIFFNESS && a->form != PB200_FORM_MASS) return false;
@@ -1167,11 +1185,7 @@ static bool fused_stage1(const pb200_assembler* a) {
     const int P = H.U.p, Q = H.q;
     if (P > 3) return false;        // the 6 x (p+1)^2 window of degree 4 does not fit the register file (ptxas: spills)
     if (!have_plan(a->form == PB200_FORM_STIFFNESS ? PB_PLAN_S1F : PB_PLAN_S1F_MASS, P, Q)) return false;
-    // staged tables of the whole axis (slabs and pieces are shorter) next to the Z columns
-    const size_t nodes = (size_t)H.G;
-    const size_t smem = nodes * 2 * (P + 1) * 8 + ((size_t)H.n + 4 + (size_t)H.V.N() * (2 * P + 1)) * 4
-                        + nodes * (2 * (g.pg[0] + 1) + 1) * 8 + nodes * 4 + ((size_t)g.Ng[0] * ((g.nc * 3 + 1) & ~1) + (size_t)std::max(Q * 6, (P + 1) * 6) + 2) * 128 * 8 + 1024;
-    return smem <= 113 * 1024;
+    return s1f_pieces(a, H.n) > 0;
 }
 
 extern "C" int pb200_asm_uses_fused_fields(const pb200_assembler* a) { return a && fused_stage1(a) ? 1 : 0; }
@@ -1186,6 +1200,13 @@ static void fill_s32_axes(const pb200_assembler* a, PbS32Params& p) {
     p.N1 = H1.V.N(); p.N2 = H2.V.N(); p.M1 = H1.M; p.M2 = H2.M;
     p.first1 = D1.first_u; p.V1 = D1.Vu; p.ret_mu1 = D1.ret_mu; p.tr1 = D1.tr; p.pair_i1 = D1.pair_i;
     p.first2 = D2.first_u; p.V2 = D2.Vu; p.ret_mu2 = D2.ret_mu; p.tr2 = D2.tr;
+}
+
+// nodes of axis 1 a block of the fused stages 2 + 3 walks when the axis is cut into K pieces (upper bound)
+static int s32_piece_rows(const pb200_assembler* a, int K) {
+    const AxisHost& H1 = a->hax[1];
+    if (K <= 1) return H1.G;
+    return std::min(H1.n, (H1.n + K - 1) / K + H1.U.p + 2) * H1.q;
 }
 
 // Tail effect of the fused stages 2 + 3: one block per SM and equal tasks — a slab whose tasks fill the GPU 2.01
@@ -1219,8 +1240,21 @@ static void choose_s32_pieces(const pb200_assembler* a, PbS32Params& q) {
         }
     }
     K = std::min(K, N1);
+    // long axes: the staged axis-1 table must fit shared memory — cut ALL tasks into at least Kfit pieces
+    {
+        PbS32Launch fn = pb_find_s32(a->form, H1.U.p, H1.q);
+        int Kfit = 1;
+        for (; fn && Kfit < PB_S32_MAXPIECE; ++Kfit) {
+            PbS32Params t = q;
+            t.out = nullptr;
+            t.v1_rows = s32_piece_rows(a, Kfit);
+            if (fn(&t, nullptr) == 0) break;
+        }
+        if (Kfit > 1) { K = std::max(K, Kfit); n_whole = 0; }
+    }
     q.npiece = 0;
     q.n_whole = 0;
+    q.v1_rows = H1.G;
     if (K > 1) {
         q.npiece = K;
         q.n_whole = (int)n_whole;
@@ -1229,6 +1263,11 @@ static void choose_s32_pieces(const pb200_assembler* a, PbS32Params& q) {
             q.pw_lo[y] = lo; q.pw_hi[y] = hi;
             q.ps_begin[y] = H1.V.supp[2 * lo];
             q.ps_end[y] = H1.V.supp[2 * (hi - 1) + 1];
+        }
+        if (q.n_whole == 0) {       // no task walks the whole axis: stage only the longest piece
+            int longest = 0;
+            for (int y = 0; y < K; ++y) longest = std::max(longest, q.ps_end[y] - q.ps_begin[y]);
+            q.v1_rows = longest * H1.q;
         }
     }
     static const bool debug_split = getenv("PB200_DEBUG_SPLIT") != nullptr;
@@ -1349,7 +1388,8 @@ static bool fused_stage23(const pb200_assembler* a) {
     PbS32Params q;
     memset(&q, 0, sizeof q);
     fill_s32_axes(a, q);
-    return fn(&q, nullptr) == 0;        // query: shared memory of this configuration fits
+    q.v1_rows = s32_piece_rows(a, PB_S32_MAXPIECE);
+    return fn(&q, nullptr) == 0;        // query: shared memory fits, if need be with axis 1 cut into pieces
 }
 
 static void stage_sizes(const pb200_assembler* a, const Slab& S, size_t& x1_terms, size_t& x1_stride, size_t& x2_terms,
@@ -1426,10 +1466,14 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
     prm.nsplit = 0;
     // rows the pieces partition: all rows of the axis, or the (extended) slab of a filtered stage
     const int r_lo = nofilter ? 0 : prm.w_ext_lo, r_hi = nofilter ? H.V.N() : prm.w_ext_hi;
-    if (r_hi > r_lo && a->walk_split != 1) {
+    // the fused stage 1 needs its staged tables to fit shared memory: a lower bound on the pieces
+    const int Kmin = (plan == PB_PLAN_S1F || plan == PB_PLAN_S1F_MASS) ? std::max(1, s1f_pieces(a, prm.s_end - prm.s_begin)) : 1;
+    if (r_hi > r_lo && (a->walk_split != 1 || Kmin > 1)) {
         const int nsp = prm.s_end - prm.s_begin;
         int K = 1;
-        if (a->walk_split > 1) {
+        if (a->walk_split == 1) {
+            K = 1;
+        } else if (a->walk_split > 1) {
             K = a->walk_split;
         } else {
             const int occ = fn(&prm, -1, use_smem ? smem + ismem + 256 : 0, st);
@@ -1445,7 +1489,7 @@ static int run_stage(int plan, pb200_assembler* a, int axis, PbWalkParams& prm, 
                 }
             }
         }
-        K = std::min(K, std::min(PB_WALK_MAXSPLIT, r_hi - r_lo));
+        K = std::min(std::max(K, Kmin), std::min(PB_WALK_MAXSPLIT, r_hi - r_lo));
         static const bool debug_split = getenv("PB200_DEBUG_SPLIT") != nullptr;
         if (K > 1 && debug_split) fprintf(stderr, "[pb200] stage %s: walk axis cut into %d pieces\n", name, K);
         if (K > 1) {

@@ -69,6 +69,9 @@ struct PbS32Params {
     int nkeep, tail_k, tail_w;
     // tasks [0, n_whole) run unsplit even when npiece > 1: full waves of whole tasks, only the remainder in pieces
     int n_whole;
+    // nodes of axis 1 whose basis table a block stages in shared memory: G1, or the longest piece when all tasks are
+    // cut (long axes: the table of the whole axis would not fit)
+    int v1_rows;
 };
 // blocks of a launch (per axis-1 piece)
 PB_HD long long pb_s32_tasks(const PbS32Params& prm) {
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
     constexpr bool VEC = (Q % 2 == 0);
     constexpr int STAGE = NSTR * SEG;
     extern __shared__ __align__(128) unsigned char pb_s32_raw[];
-    const SM lay(prm.G1, prm.N1);
+    const SM lay(prm.v1_rows, prm.N1);
     double* sV1 = reinterpret_cast<double*>(pb_s32_raw + lay.v1);
     int* sOff = reinterpret_cast<int*>(pb_s32_raw + lay.ret1);      // per (function, k) of axis 1: mu1 * M2 and tr1[mu1] * M2 (or -1)
     double* sD = reinterpret_cast<double*>(pb_s32_raw + lay.dlane);
@@ -355,7 +358,12 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
     const int gl = lane / GL, lg = lane - gl * GL;              // entry and lane inside it (gl = 0, lg = lane unless packed)
 
     // ---- block setup: axis-1 tables, zeroed rings and T buffers, owned positions ---------------------
-    for (int t = threadIdx.x; t < prm.G1 * 2 * P1; t += blockDim.x) sV1[t] = prm.V1[t];
+    const int v1_row0 = pc.s_begin * Q;                 // the axis-1 table of the spans this block walks
+    {
+        const int cnt = (pc.s_end - pc.s_begin) * Q * 2 * P1;
+        const double* src = prm.V1 + (long long)v1_row0 * 2 * P1;
+        for (int t = threadIdx.x; t < cnt; t += blockDim.x) sV1[t] = src[t];
+    }
     for (int t = threadIdx.x; t < prm.N1 * (2 * P + 1); t += blockDim.x) {
         int mu1 = prm.ret_mu1[t];
         if (mu1 >= 0) {         // piece filter on the row of the pair: entry k of function f is (f, f+k) or (f+k-P, f)
@@ -603,7 +611,7 @@ __global__ void __launch_bounds__((Q * PbS32Split<Form, P, Q>::NH + PbS32Cfg<P>:
     };
     auto node = [&](auto RC, int row, const double* Tg) {
         constexpr int R = decltype(RC)::value;
-        const double* Vn = sV1 + (long long)row * (2 * P1);
+        const double* Vn = sV1 + (long long)(row - v1_row0) * (2 * P1);
         double D[2][P1];
 #pragma unroll
         for (int a = 0; a < P1; ++a) { D[0][a] = Vn[a]; D[1][a] = Vn[P1 + a]; }

@@ -164,7 +164,7 @@ int launch_s32(const PbS32Params* prm, void* stream) {
             }
     return 0;
 #else
-    const PbS32Smem<Form, PB_P, PB_Q> lay(prm->G1, prm->N1);
+    const PbS32Smem<Form, PB_P, PB_Q> lay(prm->v1_rows > 0 ? prm->v1_rows : prm->G1, prm->N1);
     if (lay.total > 227 * 1024) return 1;
     if (!prm->out) return 0;
     auto kern = pb_s32_kernel<Form, PB_P, PB_Q>;
