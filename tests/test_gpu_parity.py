@@ -292,7 +292,9 @@ def test_inner_products_vector_valued(cuda):
 
 @pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
 @pytest.mark.parametrize('p,ns,split', [(1, (3, 5, 70), None), (2, (3, 4, 66), None), (3, (2, 9, 40), None),
-                                        (3, (3, 36, 35), 2), (2, (4, 40, 33), 3), (3, (3, 3, 33), 4)])
+                                        (3, (3, 36, 35), 2), (2, (4, 40, 33), 3), (3, (3, 3, 33), 4),
+                                        # long axes: the staged tables force pieces on axis 0 (stage 1) / axis 1 (stages 2+3)
+                                        (3, (140, 3, 33), None), (3, (3, 180, 34), None)])
 def test_fused_pipeline_shapes(cuda, form, p, ns, split):
     """the fused kernels against the oracle on shapes that exercise several 32-span batches of the last
     axis (with the shorter last batch), the axis-1 pieces and degrees 1..3; every case is also run
