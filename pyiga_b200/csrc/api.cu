@@ -1183,7 +1183,9 @@ static bool fused_stage1(const pb200_assembler* a) {
     if (g.dim != 3 || g.sdim != 3 || g.Ng[0] * ((g.nc * 3 + 1) & ~1) > PB_GEO_ZMAX) return false;
     const AxisHost& H = a->hax[0];
     const int P = H.U.p, Q = H.q;
-    if (P > 3) return false;        // the 6 x (p+1)^2 window of degree 4 does not fit the register file (ptxas: spills)
+    // (degree 4: the six (p+1)^2 windows of the stiffness form do not fit the register file — ptxas spills; the single
+    // symmetric window of the mass form does)
+    if (P > 4 || (P > 3 && a->form != PB200_FORM_MASS)) return false;
     if (!have_plan(a->form == PB200_FORM_STIFFNESS ? PB_PLAN_S1F : PB_PLAN_S1F_MASS, P, Q)) return false;
     return s1f_pieces(a, H.n) > 0;
 }

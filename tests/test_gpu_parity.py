@@ -328,9 +328,11 @@ def test_fused_fallbacks(cuda):
     from pyiga_b200 import assemblers, bspline, geometry
     a = pc.check_vs_oracle(3, (3, 2, 3), (3, 5, 4), 'Stiffness')            # mixed degrees: no fused stages 2+3
     b = pc.check_vs_oracle(3, (2, 2, 2), (3, 2, 12), 'Stiffness', mult=2)   # repeated knots
-    c = pc.check_vs_oracle(3, (4, 4, 4), (3, 3, 4), 'Mass')                 # degree 4
+    c = pc.check_vs_oracle(3, (4, 4, 4), (3, 3, 4), 'Stiffness')            # degree 4: the six windows do not fit the registers
     assert not c.dev.uses_fused_fields()
-    for asm in (a, b, c):
+    d = pc.check_vs_oracle(3, (4, 4, 4), (9, 3, 4), 'Mass')                 # degree 4 mass: fused stage 1, unfused stages 2 + 3
+    assert d.dev.uses_fused_fields()
+    for asm in (a, b, c, d):
         assert asm.dev.fast_path
 
 
