@@ -482,6 +482,19 @@ def integrate(kvs, f, f_physical=False, geo=None):
     return out
 
 
+def _jac_to_boundary_matrix(bdspec, dim):
+    """``dim x (dim-1)`` matrix that restricts the Jacobian of the volume map to the side `bdspec`; the signs make the
+    resulting normal point outwards for a positively oriented patch (``pyiga/assemble.py:899-912``)."""
+    ax, side = bdspec
+    col = dim - 1 - ax                  # the last tensor axis is the x coordinate
+    B = np.zeros((dim, dim - 1))
+    for k, c in enumerate(c for c in range(dim) if c != col):
+        B[c, k] = -1.0 if c % 2 == 0 else 1.0
+    if side != 0:
+        B[:, 0] = -B[:, 0]
+    return B
+
+
 def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatable=[]):
     """Turn a problem description into an assembler object (``pyiga/assemble.py:914-956``)."""
     if isinstance(problem, str):
@@ -498,6 +511,8 @@ def instantiate_assembler(problem, kvs, args, bfuns=None, boundary=None, updatab
         used = {}
         if boundary:
             used['boundary'] = bspline._parse_bdspec(boundary, len(kvs))
+            if 'Jac_to_boundary' in problem.parameters():       # reference VForms take the restriction matrix as a parameter
+                args = dict(args, Jac_to_boundary=_jac_to_boundary_matrix(used['boundary'], len(kvs)))
         for name in list(problem.inputs().keys()) + list(problem.parameters().keys()):
             if name not in args:
                 raise ValueError("required input parameter '%s' missing" % name)

@@ -12,7 +12,7 @@ coefficient arrays become the field buffer of a ``PB200_FORM_CUSTOM`` device ass
 comes from the sum-factorised pipeline.
 
 Nothing from ``pyiga`` is imported: the nodes are recognised by class name and attributes, so any
-object with the reference's structure is accepted.  Supported: volume integrals over one space,
+object with the reference's structure is accepted.  Supported: volume integrals and integrals over a side of the patch (``boundary=``) over one space,
 derivatives up to second order (incl. mixed ones, as in the space-time wave form), scalar and vector-valued basis functions, parametric and physical
 input fields, parameters, ``on_demand`` bounding boxes (``pyiga/codegen/cython.py:421-426,541-559``).
 Input functions are evaluated on the host exactly like the generated ``__init__`` does
@@ -225,11 +225,11 @@ def _slot_to_axis(slot, dim):
 class _ParametricBlock:
     """One scalar form given by coefficient arrays of PARAMETRIC slot pairs: tables + field upload."""
 
-    def __init__(self, kvs, nqp, dim, arity, coefs, grid_shape, full_shape=None, box=None):
+    def __init__(self, kvs, nqp, dim, arity, coefs, grid_shape, full_shape=None, box=None, quad=None):
         be = _device.backend()
         keys = sorted(coefs)
         terms = [(f, bp, ap) for f, (bp, ap) in enumerate(keys)]
-        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms))
+        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
         full = full_shape or grid_shape
         fields = np.zeros((len(terms),) + tuple(full))
         for f, key in enumerate(keys):
@@ -257,7 +257,7 @@ class RefVFormAssembler(GenericFormAssembler):
     def parameters(cls):
         return {par.name: par.shape for par in cls._rvf.params}
 
-    def __init__(self, kvs, kvs_test=None, bbox=None, **args):
+    def __init__(self, kvs, kvs_test=None, bbox=None, boundary=None, **args):
         vf = self._rvf
         kvs = tuple(kvs)
         d = vf.dim
@@ -276,6 +276,18 @@ class RefVFormAssembler(GenericFormAssembler):
         meshes = [np.asarray(kv.mesh) for kv in kvs]
         full_grid, full_w = make_tensor_quadrature(meshes, self.nqp)
         box = None
+        quad = None
+        kvs_dev = kvs
+        if vf.is_boundary:
+            # one side of the patch (pyiga/codegen/cython.py:549-590): the rule of the normal axis is the boundary point
+            # with weight 1; the device tables get the linear stand-in of GenericFormAssembler._setup_boundary
+            if self._on_demand and bbox is not None:
+                raise NotImplementedError('on_demand boundary assemblers')
+            self.gaussgrid = full_grid
+            kvs_dev, quad = self._setup_boundary(kvs, boundary)
+            bdax = self._bd[0]
+            full_grid = self.gaussgrid
+            full_w = tuple(np.ones(1) if k == bdax else w for k, w in enumerate(full_w))
         if self._on_demand and bbox is not None:
             # NB (pyiga/codegen/cython.py:541-559): bb[1] is the exclusive upper cell index
             grid, w = make_tensor_quadrature([m[bb[0]:bb[1] + 1] for m, bb in zip(meshes, bbox)], self.nqp)
@@ -310,6 +322,10 @@ class RefVFormAssembler(GenericFormAssembler):
                         if vs is None or us is not None:
                             raise ValueError('linear form must contain v and no u')
                         blk = (k, None) if self._vec else (0, None)
+                    if self._bd is not None:        # the stand-in of the normal axis is linear: value and first derivative only
+                        for sl in (vs, us):
+                            if sl is not None and sl[1][d - 1 - self._bd[0]] > 1:
+                                raise NotImplementedError('second normal derivatives in boundary integrals')
                     key = (_slot_to_axis(vs, d), _slot_to_axis(us, d))
                     dst = blocks.setdefault(blk, {})
                     dst[key] = dst[key] + c if key in dst else c
@@ -321,7 +337,7 @@ class RefVFormAssembler(GenericFormAssembler):
             # form on an affine map) would only cost launches
             live = {k: c for k, c in coefs.items() if np.any(np.asarray(c) != 0.0)}
             coefs = live or dict([next(iter(coefs.items()))])
-            self.blocks[blk] = _ParametricBlock(kvs, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box)
+            self.blocks[blk] = _ParametricBlock(kvs_dev, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box, quad=quad)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
 
@@ -337,8 +353,8 @@ def compile_vform(vf, on_demand=False):
     if cls is None:
         if not getattr(vf, '_VForm__is_finalized', False):
             vf.finalize(do_precompute=True)
-        if vf.is_boundary or vf.dim != vf.geo_dim:
-            raise NotImplementedError('boundary / surface integrals of reference VForms: use the string front end')
+        if vf.dim != vf.geo_dim:
+            raise NotImplementedError('surface integrals of reference VForms: use the string front end')
         cls = type('RefVFormAssembler%d' % len(_cache), (RefVFormAssembler,), {'_rvf': vf, '_vf': vf, '_on_demand': bool(on_demand)})
         _cache[key] = cls
         _keep.append(vf)

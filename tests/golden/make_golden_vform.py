@@ -18,6 +18,10 @@ out = {}
 for name, (make, kvs, geo, inputs) in rc.cases().items():
     A = assemble.assemble(make(), kvs, geo=geo, **inputs)
     out['vf_' + name] = A.toarray() if hasattr(A, 'toarray') else np.asarray(A)
+for name, (make, kvs, geo, inputs, sides) in rc.bcases().items():
+    for bd in sides:
+        A = assemble.assemble(make(), kvs, geo=geo, boundary=bd, **inputs)
+        out['bd_%s_%s' % (name, bd)] = A.toarray() if hasattr(A, 'toarray') else np.asarray(A)
 geo = geometry.bspline_quarter_annulus()
 for name, (make, inputs, sym) in rc.hcases().items():
     for truncate in (False, True):

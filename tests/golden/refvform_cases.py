@@ -56,6 +56,44 @@ def cases():
     }
 
 
+def _g2(x, y):
+    return x + 2.0 * y
+
+
+def bcases():
+    """integrals over a side of the patch: name -> (VForm factory, knot vectors, geometry, inputs, sides)"""
+    from pyiga import geometry as rgeo, vform as rvf
+    kv2, kv3 = spaces()
+
+    def robin(d):
+        vf = rvf.VForm(d, boundary=True)
+        u, v = vf.basisfuns()
+        vf.add(u * v * rvf.ds)
+        return vf
+
+    def neumann(d):
+        vf = rvf.VForm(d, arity=1, boundary=True)
+        v = vf.basisfuns()
+        g = vf.input('g')
+        vf.add(g * v * rvf.ds)
+        return vf
+
+    def nitsche(d):       # normal flux of u against v: normal vector and gradients at the boundary
+        vf = rvf.VForm(d, boundary=True)
+        u, v = vf.basisfuns()
+        vf.add(rvf.inner(rvf.grad(u), vf.normal) * v * rvf.ds)
+        return vf
+
+    geo2, geo3 = rgeo.quarter_annulus(), rgeo.twisted_box()
+    return {
+        'robin2': (lambda: robin(2), kv2, geo2, {}, ('left', 'right', 'top', 'bottom')),
+        'robin3': (lambda: robin(3), kv3, geo3, {}, ('left', 'back', 'top')),
+        'neumann2': (lambda: neumann(2), kv2, geo2, {'g': _g2}, ('right', 'bottom')),
+        'nitsche2': (lambda: nitsche(2), kv2, geo2, {}, ('left', 'top')),
+        'nitsche3': (lambda: nitsche(3), kv3, geo3, {}, ('front', 'bottom')),
+    }
+
+
 def hspace(truncate):
     from pyiga import bspline as rbs, hierarchical
     # the example space of the reference's own tests (test/test_hierarchical.py:10-18)

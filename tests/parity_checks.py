@@ -1057,6 +1057,14 @@ def check_reference_vform_objects():
         got = got.toarray() if hasattr(got, 'toarray') else np.asarray(got)
         assert got.shape == want.shape, name
         assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), '%s: %.3e' % (name, np.abs(got - want).max())
+    # integrals over a side of the patch (VForm(dim, boundary=True): ds, the normal vector, Jac_to_boundary)
+    for name, (make, kvs, geo, inputs, sides) in rc.bcases().items():
+        for bd in sides:
+            want = fix['bd_%s_%s' % (name, bd)]
+            got = assemble.assemble(make(), kvs, geo=geo, boundary=bd, **inputs)
+            got = got.toarray() if hasattr(got, 'toarray') else np.asarray(got)
+            assert got.shape == want.shape, (name, bd)
+            assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), (name, bd, np.abs(got - want).max())
     # second and mixed derivative slots (numderiv = 2): the wave form runs through the sum-factorised walks with the
     # (1st, 2nd derivative) tables, and the per-entry kernel gives the same matrix; the fourth-order form needs all
     # three derivative orders on one axis in one term group and takes the per-entry path
