@@ -12,7 +12,8 @@ coefficient arrays become the field buffer of a ``PB200_FORM_CUSTOM`` device ass
 comes from the sum-factorised pipeline.
 
 Nothing from ``pyiga`` is imported: the nodes are recognised by class name and attributes, so any
-object with the reference's structure is accepted.  Supported: volume integrals and integrals over a side of the patch (``boundary=``) over one space,
+object with the reference's structure is accepted.  Supported: volume integrals, integrals over a side of the patch (``boundary=``) and surface integrals
+(``geo_dim = dim + 1``) over one space,
 derivatives up to second order (incl. mixed ones, as in the space-time wave form), scalar and vector-valued basis functions, parametric and physical
 input fields, parameters, ``on_demand`` bounding boxes (``pyiga/codegen/cython.py:421-426,541-559``).
 Input functions are evaluated on the host exactly like the generated ``__init__`` does
@@ -351,10 +352,10 @@ def compile_vform(vf, on_demand=False):
     key = (id(vf), bool(on_demand))
     cls = _cache.get(key)
     if cls is None:
+        if vf.dim < 2 or vf.dim > 3:
+            raise NotImplementedError('the device assemblers take 2 or 3 knot vectors (form of dimension %d)' % vf.dim)
         if not getattr(vf, '_VForm__is_finalized', False):
             vf.finalize(do_precompute=True)
-        if vf.dim != vf.geo_dim:
-            raise NotImplementedError('surface integrals of reference VForms: use the string front end')
         cls = type('RefVFormAssembler%d' % len(_cache), (RefVFormAssembler,), {'_rvf': vf, '_vf': vf, '_on_demand': bool(on_demand)})
         _cache[key] = cls
         _keep.append(vf)

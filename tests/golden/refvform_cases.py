@@ -31,6 +31,18 @@ def cases():
         vf.add(rvf.inner(rvf.dot(A, rvf.grad(u)), rvf.grad(v)) * rvf.dx + c * u * v * rvf.dx)
         return vf
 
+    def surf_mass2():
+        vf = rvf.VForm(2, geo_dim=3)
+        u, v = vf.basisfuns()
+        vf.add(u * v * rvf.ds)
+        return vf
+
+    def surf_flux2():
+        vf = rvf.VForm(2, geo_dim=3, arity=1)
+        v = vf.basisfuns()
+        vf.add(rvf.inner(vf.normal, (1.0, 2.0, 3.0)) * v * rvf.ds)
+        return vf
+
     def biharmonic2():
         vf = rvf.VForm(2)
         u, v = vf.basisfuns()
@@ -48,6 +60,9 @@ def cases():
         # space-time heat form (pyiga/vform.py:1759-1763; the last coordinate is time)
         'heat_st2': (lambda: rvf.heat_st_vf(2), kv2, rgeo.unit_square(), {}),
         'heat_st3': (lambda: rvf.heat_st_vf(3), kv3, geo3, {}),
+        # surface integrals over a face of the twisted box (geo: R^2 -> R^3): surface measure and unit normal
+        'surf_mass2': (surf_mass2, kv2, geo3.boundary('left'), {}),
+        'surf_flux2': (surf_flux2, kv2, geo3.boundary('left'), {}),
         # space-time wave form: second time derivative and mixed space-time derivatives (pyiga/vform.py:1766-1772)
         'wave_st2': (lambda: rvf.wave_st_vf(2), kv2, geo2, {}),
         'wave_st3': (lambda: rvf.wave_st_vf(3), kv3, geo3, {}),
