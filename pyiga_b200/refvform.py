@@ -13,7 +13,7 @@ comes from the sum-factorised pipeline.
 
 Nothing from ``pyiga`` is imported: the nodes are recognised by class name and attributes, so any
 object with the reference's structure is accepted.  Supported: volume integrals, integrals over a side of the patch (``boundary=``) and surface integrals
-(``geo_dim = dim + 1``) over one space,
+(``geo_dim = dim + 1``), one space or trial / test functions in two spaces on the same mesh,
 derivatives up to second order (incl. mixed ones, as in the space-time wave form), scalar and vector-valued basis functions, parametric and physical
 input fields, parameters, ``on_demand`` bounding boxes (``pyiga/codegen/cython.py:421-426,541-559``).
 Input functions are evaluated on the host exactly like the generated ``__init__`` does
@@ -226,11 +226,11 @@ def _slot_to_axis(slot, dim):
 class _ParametricBlock:
     """One scalar form given by coefficient arrays of PARAMETRIC slot pairs: tables + field upload."""
 
-    def __init__(self, kvs, nqp, dim, arity, coefs, grid_shape, full_shape=None, box=None, quad=None):
+    def __init__(self, kvs, nqp, dim, arity, coefs, grid_shape, full_shape=None, box=None, quad=None, kvs_test=None):
         be = _device.backend()
         keys = sorted(coefs)
         terms = [(f, bp, ap) for f, (bp, ap) in enumerate(keys)]
-        self.dev = DeviceAssembler(kvs, kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
+        self.dev = DeviceAssembler(kvs, kvs_test or kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
         full = full_shape or grid_shape
         fields = np.zeros((len(terms),) + tuple(full))
         for f, key in enumerate(keys):
@@ -263,14 +263,23 @@ class RefVFormAssembler(GenericFormAssembler):
         kvs = tuple(kvs)
         d = vf.dim
         assert len(kvs) == d, "Assembler requires %d knot vectors" % d
-        if kvs_test is not None:
-            raise NotImplementedError('reference VForms over two spaces: use the string front end')
+        if vf.num_spaces() == 2:
+            # trial functions in `kvs` (space 0, columns), test functions in `kvs_test` (space 1, rows), on the
+            # same mesh (pyiga/assemble.py:947-951, generated __init__(kvs0, kvs1))
+            assert kvs_test is not None and len(kvs_test) == d, "Assembler requires %d knot vectors" % d
+            kvs_test = tuple(kvs_test)
+            assert all(np.array_equal(a.mesh, b.mesh) for a, b in zip(kvs, kvs_test)), 'both spaces must share the mesh'
+            spaces = {bf.name: bf.space for bf in vf.basis_funs}
+            if vf.arity != 2 or spaces.get('u') != 0 or spaces.get('v') != 1:
+                raise NotImplementedError('two-space forms need the trial function in space 0 and the test function in space 1')
+        else:
+            kvs_test = None
         geo = args['geo']
         assert geo.sdim == d, "Geometry has wrong source dimension"
         assert geo.dim == vf.geo_dim, "Geometry has wrong dimension"
         self.arity = vf.arity
-        self.nqp = max(kv.p for kv in kvs) + 1
-        self.kvs = (kvs, kvs)
+        self.nqp = max(kv.p for kv in kvs + (kvs_test or ())) + 1
+        self.kvs = (kvs, kvs_test or kvs)
         self._geo, self._args = geo, dict(args)
         self.bbox = bbox
         self._bd, self._surface = None, False
@@ -279,6 +288,8 @@ class RefVFormAssembler(GenericFormAssembler):
         box = None
         quad = None
         kvs_dev = kvs
+        if vf.is_boundary and kvs_test is not None:
+            raise NotImplementedError('boundary integrals over two different spaces')
         if vf.is_boundary:
             # one side of the patch (pyiga/codegen/cython.py:549-590): the rule of the normal axis is the boundary point
             # with weight 1; the device tables get the linear stand-in of GenericFormAssembler._setup_boundary
@@ -338,7 +349,8 @@ class RefVFormAssembler(GenericFormAssembler):
             # form on an affine map) would only cost launches
             live = {k: c for k, c in coefs.items() if np.any(np.asarray(c) != 0.0)}
             coefs = live or dict([next(iter(coefs.items()))])
-            self.blocks[blk] = _ParametricBlock(kvs_dev, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box, quad=quad)
+            self.blocks[blk] = _ParametricBlock(kvs_dev, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box, quad=quad,
+                                                kvs_test=kvs_test)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
 

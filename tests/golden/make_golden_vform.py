@@ -22,6 +22,8 @@ for name, (make, kvs, geo, inputs, sides) in rc.bcases().items():
     for bd in sides:
         A = assemble.assemble(make(), kvs, geo=geo, boundary=bd, **inputs)
         out['bd_%s_%s' % (name, bd)] = A.toarray() if hasattr(A, 'toarray') else np.asarray(A)
+for name, (make, kvs2, geo, inputs) in rc.pgcases().items():
+    out['pg_' + name] = assemble.assemble(make(), kvs2, geo=geo, **inputs).toarray()
 geo = geometry.bspline_quarter_annulus()
 for name, (make, inputs, sym) in rc.hcases().items():
     for truncate in (False, True):

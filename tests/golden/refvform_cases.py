@@ -71,6 +71,35 @@ def cases():
     }
 
 
+def _c2(x, y):
+    return 1.0 + x * y
+
+
+def _c3(x, y, z):
+    return 1.0 + x * y + z
+
+
+def pgcases():
+    """Petrov-Galerkin forms (trial space 0, test space 1 on the same mesh): name -> (factory, (kvs0, kvs1), geo, inputs)"""
+    from pyiga import bspline as rbs, geometry as rgeo, vform as rvf
+
+    def pg(d):
+        vf = rvf.VForm(d)
+        u, v = vf.basisfuns(spaces=(0, 1))
+        c = vf.input('c')
+        vf.add((rvf.inner(rvf.grad(u), rvf.grad(v)) + c * u * v) * rvf.dx)
+        return vf
+
+    kva = (rbs.make_knots(2, 0.0, 1.0, 4), rbs.make_knots(2, 0.0, 1.0, 3))
+    kvb = (rbs.make_knots(3, 0.0, 1.0, 4), rbs.make_knots(1, 0.0, 1.0, 3))
+    kva3 = (rbs.make_knots(2, 0.0, 1.0, 3), rbs.make_knots(1, 0.0, 1.0, 2), rbs.make_knots(2, 0.0, 1.0, 2))
+    kvb3 = (rbs.make_knots(1, 0.0, 1.0, 3), rbs.make_knots(2, 0.0, 1.0, 2), rbs.make_knots(3, 0.0, 1.0, 2))
+    return {
+        'pg2': (lambda: pg(2), (kva, kvb), rgeo.quarter_annulus(), {'c': _c2}),
+        'pg3': (lambda: pg(3), (kva3, kvb3), rgeo.twisted_box(), {'c': _c3}),
+    }
+
+
 def _g2(x, y):
     return x + 2.0 * y
 

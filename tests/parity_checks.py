@@ -1065,6 +1065,12 @@ def check_reference_vform_objects():
             got = got.toarray() if hasattr(got, 'toarray') else np.asarray(got)
             assert got.shape == want.shape, (name, bd)
             assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), (name, bd, np.abs(got - want).max())
+    # Petrov-Galerkin forms: trial and test functions in different spaces on the same mesh
+    for name, (make, kvs2, geo, inputs) in rc.pgcases().items():
+        want = fix['pg_' + name]
+        got = assemble.assemble(make(), kvs2, geo=geo, **inputs).toarray()
+        assert got.shape == want.shape, name
+        assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), (name, np.abs(got - want).max())
     # second and mixed derivative slots (numderiv = 2): the wave form runs through the sum-factorised walks with the
     # (1st, 2nd derivative) tables, and the per-entry kernel gives the same matrix; the fourth-order form needs all
     # three derivative orders on one axis in one term group and takes the per-entry path
