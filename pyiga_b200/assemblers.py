@@ -666,9 +666,10 @@ class GenericFormAssembler(_AssemblerProtocol):
     # ---- input evaluation (host side, like the reference) ------------------------------------
     def _device_inputs(self):
         """Coefficient arrays stay on the GPU (CUDA backend, volume forms on spline geometries): the
-        physical Gauss points are evaluated there and a callable written with arithmetic operators runs
-        on the device tensors; the host evaluation of the reference (``pyiga/codegen/cython.py:465-484``)
-        is the fall-back for callables that need numpy."""
+        physical Gauss points are evaluated there and the callable runs on the device tensors, which answer
+        arithmetic and the numpy protocols (``np.sin``, ``np.where`` ...; :mod:`pyiga_b200._devarray`); the host
+        evaluation of the reference (``pyiga/codegen/cython.py:465-484``) is the fall-back for callables that
+        need more (``math.*``, reductions, ``np.asarray``)."""
         return (self.dev_backend_name == 'cuda' and self._bd is None and not self._surface and _is_spline_geo(self._geo)
                 and len(self.gaussgrid) >= 2)
 
@@ -700,7 +701,7 @@ class GenericFormAssembler(_AssemblerProtocol):
             coords = tuple(Xd[..., i] for i in range(Xd.shape[-1]))
             try:
                 vals = _grid_values(f, shape, coords, self._grid_shape)
-            except Exception:       # the callable needs numpy (np.sin, math.*, ...): evaluate it on the host
+            except Exception:       # the callable needs a real numpy array (math.*, reductions, ...): evaluate it on the host
                 vals = None
             if vals is not None:
                 if shape == ():

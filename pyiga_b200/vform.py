@@ -640,8 +640,17 @@ def _dev_broadcast(v, like, grid_shape):
 def _grid_values(f, shape, coords, grid_shape):
     """evaluate a callable at coordinate arrays (x, y, z order) and bring the result to
     shape + grid_shape (``pyiga/utils.py:8-31`` _ensure_grid_shape).  `coords` may be device tensors:
-    a callable written with arithmetic operators then runs on the GPU."""
-    vals = f(*coords)
+    the callable then runs on the GPU — behind the numpy protocols of :class:`pyiga_b200._devarray.DevArray`
+    (arithmetic, comparisons, ``np.sin`` / ``np.where`` / ...), or on the raw tensors if it does something the
+    wrapper does not know."""
+    if _is_dev(coords[0]):
+        from ._devarray import DevArray, unwrap
+        try:
+            vals = unwrap(f(*[DevArray(c) for c in coords]))
+        except Exception:
+            vals = f(*coords)
+    else:
+        vals = f(*coords)
     if _is_dev(coords[0]):
         if shape == ():
             return _dev_broadcast(vals, coords[0], grid_shape)

@@ -9,6 +9,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
 from helpers import RTOL, assert_close_rel, case_space, geo_arrays, load_golden, make_geo, make_space
 from oracle import pyiga_oracle as orc
@@ -1172,3 +1173,76 @@ def check_entry_func_ptr():
     rkvs = tuple(rbs.KnotVector(kv.kv, kv.p) for kv in kvs)
     B = fast_assemble_cy.fast_assemble(asm, rkvs, tol=1e-12, maxiter=200, verbose=0)
     assert abs(B - A).max() <= 1e-9 * abs(A).max()
+
+
+def check_device_callables(ref):
+    """Coefficient callables written against numpy (np.sin, np.where, ...) run on device tensors behind
+    the numpy protocols of pyiga_b200._devarray.DevArray and give what the host evaluation of the
+    reference gives (pyiga/utils.py:8-52)."""
+    import torch
+    from pyiga_b200 import _device, assemble
+    from pyiga_b200._devarray import DevArray, unwrap
+    from pyiga_b200.vform import _grid_values
+    on_gpu = _device.backend().name == 'cuda'
+    devname = 'cuda' if on_gpu else 'cpu'
+    rng = np.random.default_rng(5)
+    shape = (6, 5, 7)
+    X = [rng.uniform(0.1, 1.9, shape) for _ in range(3)]
+    Xd = [torch.as_tensor(x, device=devname) for x in X]
+    funcs = [
+        ((), lambda x, y, z: np.sin(x) * np.exp(-y) + np.sqrt(z) / (1.0 + x * x)),
+        ((), lambda x, y, z: np.where(x > 1.0, 2.0, 0.5) + np.maximum(y, z) - np.minimum(x, 1.2)),
+        ((), lambda x, y, z: np.where((x > 0.5) & (y < 1.5), x, -y) + abs(z - 1.0) ** 1.5),
+        ((), lambda x, y, z: np.arctan2(y, x) + np.hypot(x, z) + np.log(1.0 + y) + 2.0 ** x + np.float64(3.0) * z),
+        ((), lambda x, y, z: np.cos(np.pi * x) * np.tanh(y) + np.clip(z, 0.5, 1.0) + np.zeros_like(x) + np.ones_like(y)),
+        ((), lambda x, y, z: 1.0 + 0 * x),
+        ((), lambda x, y, z: 3.5),
+        ((3,), lambda x, y, z: (np.sin(y), -x * z, 1.0)),
+        ((3,), lambda x, y, z: np.stack([np.cos(x), y * y, np.full_like(z, 2.0)])),
+        ((2, 2), lambda x, y, z: ((1.0 + x, np.exp(z)), (np.abs(y - 1.0), 0.0))),
+    ]
+    for shp, f in funcs:
+        seen = []
+
+        def spy(*c, f=f):
+            seen.append(type(c[0]).__name__)
+            return f(*c)
+        got = _grid_values(spy, shp, tuple(Xd), shape)
+        want = _grid_values(f, shp, tuple(X), shape)
+        assert seen == ['DevArray'], seen          # no fall-back to raw tensors
+        if shp == ():
+            assert tuple(got.shape) == shape and got.dtype == torch.float64
+            np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-14, atol=1e-15)
+        else:
+            for idx in np.ndindex(*shp):
+                assert tuple(got[idx].shape) == shape and got[idx].dtype == torch.float64
+                np.testing.assert_allclose(got[idx].cpu().numpy(), want[idx], rtol=1e-14, atol=1e-15)
+    # what the wrapper does not know raises (the caller then evaluates on the host)
+    import math
+    a = DevArray(Xd[0])
+    for bad in (lambda: math.sin(a), lambda: np.linalg.norm(a), lambda: np.asarray(a), lambda: bool(a > 1.0),
+                lambda: np.add.reduce(a)):
+        with pytest.raises(Exception):
+            bad()
+    assert unwrap((a, [a, 1.0]))[1][0] is Xd[0]
+
+    # the same through an assembled form: numpy callable (device tensors on the GPU) vs a callable that
+    # can only run on the host
+    kvs = make_space(ref, 'a3_tb')
+    geo = make_geo(ref, 'tb')
+    fdev = lambda x, y, z: np.sin(x + y) * np.exp(-z) + np.where(x > 0.5, 2.0, 1.0)
+    types = []
+
+    def fspy(x, y, z):
+        types.append(type(x).__name__)
+        return fdev(x, y, z)
+
+    def fhost(x, y, z):
+        return fdev(np.asarray(x), np.asarray(y), np.asarray(z))      # np.asarray of a device array raises
+    bvec = lambda x, y, z: (np.cos(y), x * z, 1.0 + 0 * x)
+    form = 'f * inner(grad(u), grad(v)) * dx + inner(b, grad(u)) * v * dx'
+    A = assemble.assemble(form, kvs, geo=geo, f=fspy, b=bvec)
+    B = assemble.assemble(form, kvs, geo=geo, f=fhost, b=lambda x, y, z: bvec(np.asarray(x), np.asarray(y), np.asarray(z)))
+    if on_gpu:
+        assert types and types[0] == 'DevArray', types
+    assert abs(A - B).max() <= RTOL * abs(B).max()

@@ -234,3 +234,7 @@ def test_partition_by_assembly_work(emu, p, n):
         assert len(a) == world and a[0][0] == 0 and a[-1][1] == N
         assert all(x[1] == y[0] and x[1] > x[0] for x, y in zip(a, a[1:]))
         assert max(cost(*s) for s in a) <= max(cost(*s) for s in b) + 1e-9
+
+
+def test_device_callables(emu, ref):
+    pc.check_device_callables(ref)
