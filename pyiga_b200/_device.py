@@ -130,6 +130,9 @@ def eval_spline_on_grid(func, gridaxes, want, keep_on_device=False):
     if want == 'value':
         out = be.to_host(vals).reshape(shape + (dim,))
         return out[..., 0] if scalar else out
+    if keep_on_device:
+        out = jac.reshape(shape + (dim, sdim))
+        return out[..., 0, :] if scalar else out
     out = be.to_host(jac).reshape(shape + (dim, sdim))
     return out[..., 0, :] if scalar else out
 

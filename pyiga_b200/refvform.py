@@ -16,13 +16,19 @@ object with the reference's structure is accepted.  Supported: volume integrals,
 (``geo_dim = dim + 1``), one space or trial / test functions in two spaces on the same mesh,
 derivatives up to second order (incl. mixed ones, as in the space-time wave form), scalar and vector-valued basis functions, parametric and physical
 input fields, parameters, ``on_demand`` bounding boxes (``pyiga/codegen/cython.py:421-426,541-559``).
-Input functions are evaluated on the host exactly like the generated ``__init__`` does
-(``pyiga/codegen/cython.py:465-484``, ``pyiga/utils.py:33-52``).
+On the CUDA backend the coefficient arrays never exist on the host: the geometry (values, Jacobian) is
+evaluated on the Gauss grid by the device kernels, input callables run on device arrays
+(:mod:`pyiga_b200._devarray`), and the interpreter's arithmetic is elementwise device operations; the
+result is bound as the field buffer without a copy.  What the device cannot evaluate (Hessians of input
+fields, callables that need a real numpy array, geometries that are not splines) is evaluated on the host
+exactly like the generated ``__init__`` does (``pyiga/codegen/cython.py:465-484``,
+``pyiga/utils.py:33-52``) and uploaded.
 """
 import numpy as np
 
 from . import _device, _lib
-from .assemblers import DeviceAssembler, GenericFormAssembler, _AssemblerProtocol
+from ._devarray import DevArray, unwrap
+from .assemblers import DeviceAssembler, GenericFormAssembler, _AssemblerProtocol, _is_spline_geo
 from .mlmatrix import MLMatrix
 from .quadrature import make_tensor_quadrature
 
@@ -83,6 +89,24 @@ class _Lin:
 
 _FUNCS = {'abs': np.abs, 'sqrt': np.sqrt, 'exp': np.exp, 'log': np.log, 'sin': np.sin, 'cos': np.cos, 'tan': np.tan}
 
+# test switch: run the interpreter on CPU torch tensors (the code path of the CUDA backend) under the emulation backend
+_FORCE_TENSORS = False
+
+
+def _tensor_device():
+    """torch device the coefficient arrays live on, or None (numpy arrays on the host)"""
+    be = _device.backend()
+    if be.name == 'cuda':
+        return be.device
+    if _FORCE_TENSORS:
+        import torch
+        return torch.device('cpu')
+    return None
+
+
+def _is_tensor(a):
+    return hasattr(a, 'device') and hasattr(a, 'expand')
+
 
 class _Interpreter:
     """Evaluates the scalar expressions of a finalized VForm on a tensor Gauss grid."""
@@ -91,8 +115,23 @@ class _Interpreter:
         self.vf, self.grid, self.gw, self.args, self.geo = vf, gaussgrid, gaussweights, args, geo
         self.shape = tuple(len(g) for g in gaussgrid)
         self.dim = len(gaussgrid)
+        self.tdev = _tensor_device()
         self._vars = {}
         self._memo = {}
+
+    def _up(self, arr):
+        """host array -> where the coefficient arrays live"""
+        if self.tdev is None or _is_tensor(arr):
+            return arr
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(arr, dtype=float), device=self.tdev)
+
+    def _spline(self, f, want):
+        """values / Jacobian of a spline function on the Gauss grid, evaluated where the arrays live"""
+        if (self.tdev is not None and self.tdev.type == 'cuda' and _is_spline_geo(f) and 2 <= len(f.kvs) <= 3
+                and len(f.kvs) == self.dim):
+            return _device.eval_spline_on_grid(f, self.grid, want, keep_on_device=True)
+        return self._up(np.asarray(f.grid_eval(self.grid) if want == 'value' else f.grid_jacobian(self.grid), dtype=float))
 
     # ---- variables ---------------------------------------------------------------------------
     def var_entry(self, var, I):
@@ -125,14 +164,14 @@ class _Interpreter:
                 arr = self._grid_eval(f, src.physical)
             elif deriv == 1:
                 assert not src.physical, 'Jacobian of physical input field not implemented'
-                arr = np.asarray(f.grid_jacobian(self.grid), dtype=float)
+                arr = self._spline(f, 'jacobian')
             elif deriv == 2:
                 # symmetric part, linearised: (d_xx, d_xy, d_yy) / (d_xx, d_xy, d_xz, d_yy, d_yz, d_zz)  (pyiga/vform.py:354-360)
                 assert not src.physical, 'Hessian of physical input field not implemented'
-                arr = np.asarray(f.grid_hessian(self.grid), dtype=float)
+                arr = self._up(np.asarray(f.grid_hessian(self.grid), dtype=float))
             else:
                 raise NotImplementedError('derivatives of order > 2 of input fields')
-            arr = np.asarray(arr, dtype=float)
+            arr = self._up(arr) if self.tdev is not None else np.asarray(arr, dtype=float)
         else:
             raise TypeError('invalid source %r of variable %s' % (src, var.name))
         self._vars[key] = arr
@@ -141,7 +180,12 @@ class _Interpreter:
     def _grid_eval(self, f, physical):
         """``grid_eval`` / ``grid_eval_transformed`` of pyiga/utils.py:33-52"""
         if hasattr(f, 'grid_eval') and not physical:
-            return f.grid_eval(self.grid)
+            return self._spline(f, 'value')
+        if self.tdev is not None:
+            try:
+                return self._grid_eval_tensors(f, physical)
+            except Exception:       # the callable needs a real numpy array: host evaluation below, then upload
+                pass
         if physical:
             X = np.asarray(self.geo.grid_eval(self.grid), dtype=float)
             pts = tuple(X[..., i] for i in range(X.shape[-1]))
@@ -154,6 +198,34 @@ class _Interpreter:
         vals = np.asarray(vals, dtype=float)
         target = self.shape + vals.shape[self.dim:]     # functions that ignore an argument return smaller arrays
         return vals if vals.shape == target else np.broadcast_to(vals, target)
+
+    def _grid_eval_tensors(self, f, physical):
+        """the same with device arrays behind the numpy protocols (see _devarray.py)"""
+        import torch
+        if physical:
+            if 'X' not in self._vars:
+                self._vars['X'] = self._spline(self.geo, 'value')
+            X = self._vars['X']
+            X = X.reshape(self.shape + (-1,))
+            pts = [X[..., i] for i in range(X.shape[-1])]
+        else:
+            pts = []
+            for k, g in enumerate(self.grid):
+                shp = [1] * self.dim
+                shp[k] = -1
+                pts.append(self._up(np.asarray(g, dtype=float)).reshape(shp))
+            pts.reverse()
+        vals = unwrap(f(*[DevArray(c) for c in pts]))
+
+        def as_tensor(v):
+            if not _is_tensor(v):
+                v = torch.as_tensor(np.asarray(v, dtype=float), device=self.tdev)
+            return v.to(torch.float64)
+        if isinstance(vals, (tuple, list)):     # vector-valued function given as a tuple of components
+            vals = torch.stack([as_tensor(v).expand(self.shape) for v in vals], dim=-1)
+        vals = as_tensor(vals)
+        target = self.shape + tuple(vals.shape[self.dim:])
+        return vals if tuple(vals.shape) == target else vals.expand(target)
 
     def _source_entry(self, var, I):
         arr = self._source_array(var)
@@ -183,7 +255,11 @@ class _Interpreter:
             v = self.eval(e.x)
             if not v.is_coef():
                 raise ValueError('functions can only be applied to coefficient expressions')
-            return _Lin.const(_FUNCS[e.funcname](v.coef()))
+            c = v.coef()
+            if _is_tensor(c):
+                import torch
+                return _Lin.const(getattr(torch, e.funcname)(c))
+            return _Lin.const(_FUNCS[e.funcname](c))
         if kind == 'ScalarOperExpr':
             vals = [self.eval(c) for c in e.children]
             r = vals[0]
@@ -202,7 +278,7 @@ class _Interpreter:
         if kind == 'GaussWeightExpr':
             shp = [1] * self.dim
             shp[e.axis] = -1
-            return _Lin.const(np.asarray(self.gw[e.axis], dtype=float).reshape(shp))
+            return _Lin.const(self._up(np.asarray(self.gw[e.axis], dtype=float)).reshape(shp))
         raise NotImplementedError('expression node %s after finalize()' % kind)
 
 
@@ -232,14 +308,31 @@ class _ParametricBlock:
         terms = [(f, bp, ap) for f, (bp, ap) in enumerate(keys)]
         self.dev = DeviceAssembler(kvs, kvs_test or kvs, _lib.FORM_CUSTOM, nqp=nqp, terms=terms, nfields=len(terms), quad=quad)
         full = full_shape or grid_shape
-        fields = np.zeros((len(terms),) + tuple(full))
-        for f, key in enumerate(keys):
-            vals = np.broadcast_to(np.asarray(coefs[key], dtype=float), grid_shape)
+        if any(_is_tensor(c) for c in coefs.values()):
+            # coefficient arrays computed on the device: they become the field buffer without touching the host
+            import torch
+            tdev = next(c.device for c in coefs.values() if _is_tensor(c))
             if box is None:
-                fields[f] = vals
-            else:       # on-demand assembler: only the Gauss points of the bounding box carry data
-                fields[(f,) + tuple(slice(a, b) for a, b in box)] = vals
-        buf = be.from_host(np.ascontiguousarray(fields).ravel())
+                fields = torch.empty((len(terms),) + tuple(full), dtype=torch.float64, device=tdev)
+            else:
+                fields = torch.zeros((len(terms),) + tuple(full), dtype=torch.float64, device=tdev)
+            for f, key in enumerate(keys):
+                c = coefs[key]
+                vals = (c if _is_tensor(c) else torch.as_tensor(np.asarray(c, dtype=float), device=tdev)).expand(grid_shape)
+                if box is None:
+                    fields[f] = vals
+                else:
+                    fields[(f,) + tuple(slice(a, b) for a, b in box)] = vals
+            buf = fields.reshape(-1) if be.name == 'cuda' else be.from_host(fields.numpy().ravel())
+        else:
+            fields = np.zeros((len(terms),) + tuple(full))
+            for f, key in enumerate(keys):
+                vals = np.broadcast_to(np.asarray(coefs[key], dtype=float), grid_shape)
+                if box is None:
+                    fields[f] = vals
+                else:       # on-demand assembler: only the Gauss points of the bounding box carry data
+                    fields[(f,) + tuple(slice(a, b) for a, b in box)] = vals
+            buf = be.from_host(np.ascontiguousarray(fields).ravel())
         self.dev.fields = buf
         self.dev._geo_bound = None
         _device.check(be.lib.pb200_asm_bind_fields(self.dev.handle, be.ptr(buf)))
@@ -347,7 +440,7 @@ class RefVFormAssembler(GenericFormAssembler):
         for blk, coefs in blocks.items():
             # slot pairs whose coefficient vanishes identically (e.g. the geometry Hessian terms of a fourth-order
             # form on an affine map) would only cost launches
-            live = {k: c for k, c in coefs.items() if np.any(np.asarray(c) != 0.0)}
+            live = {k: c for k, c in coefs.items() if (bool((c != 0.0).any()) if _is_tensor(c) else np.any(np.asarray(c) != 0.0))}
             coefs = live or dict([next(iter(coefs.items()))])
             self.blocks[blk] = _ParametricBlock(kvs_dev, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box, quad=quad,
                                                 kvs_test=kvs_test)

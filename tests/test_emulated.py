@@ -196,6 +196,33 @@ def test_reference_vform_objects(emu):
     pc.check_reference_vform_objects()
 
 
+def test_reference_vform_objects_tensor_interpreter(emu, monkeypatch):
+    """the code path of the CUDA backend (coefficient arrays as tensors, callables on DevArray) on CPU tensors"""
+    from pyiga_b200 import refvform
+    monkeypatch.setattr(refvform, '_FORCE_TENSORS', True)
+    log = {'ok': 0, 'failed': 0, 'tensor_blocks': 0, 'host_blocks': 0}
+    inner = refvform._Interpreter._grid_eval_tensors
+
+    def spy(self, f, physical):
+        try:
+            r = inner(self, f, physical)
+        except Exception:
+            log['failed'] += 1
+            raise
+        log['ok'] += 1
+        return r
+    monkeypatch.setattr(refvform._Interpreter, '_grid_eval_tensors', spy)
+    block_init = refvform._ParametricBlock.__init__
+
+    def block_spy(self, kvs, nqp, dim, arity, coefs, *a, **k):
+        log['tensor_blocks' if all(refvform._is_tensor(c) for c in coefs.values()) else 'host_blocks'] += 1
+        return block_init(self, kvs, nqp, dim, arity, coefs, *a, **k)
+    monkeypatch.setattr(refvform._ParametricBlock, '__init__', block_spy)
+    pc.check_reference_vform_objects()
+    pc.check_hierarchical_discretization(monkeypatch)
+    assert log['ok'] > 0 and log['failed'] == 0 and log['tensor_blocks'] > 0 and log['host_blocks'] == 0, log
+
+
 def test_space_time_assemblers(emu):
     pc.check_space_time_assemblers()
 
