@@ -55,6 +55,19 @@ def csr_sizes(dev, rows=None):
     return nrows, nnz, (np.int32 if max(nnz, ncols) < 2 ** 31 else np.int64)
 
 
+def pattern_split(rs, ra, rb, nthr, inner_r, inner_b):
+    """Rows [ra, rm) of the first axis for `nthr` pattern threads, rows [rm, rb) — about 1 / (nthr + 1) of the
+    band entries — for the calling thread.  Returns (rm, None) or (rm, (rm, rb, first local row of the second
+    part, first local entry of the second part))."""
+    rm = rb
+    if rb - ra >= 2:
+        target = rs[ra] + (rs[rb] - rs[ra]) * nthr / (nthr + 1.0)
+        rm = int(np.clip(np.searchsorted(rs, target), ra + 1, rb))
+    if rm < rb:
+        return rm, (rm, rb, (rm - ra) * inner_r, int(rs[rm] - rs[ra]) * inner_b)
+    return rm, None
+
+
 def assemble_csr_host(dev, rows=None, host=None, nchunks=8, workspace=None, pattern='host', pattern_threads=None,
                       timings=None):
     """Assemble the rows `rows` of the first axis (default: all) and deliver (indptr, indices, data) in
@@ -105,10 +118,18 @@ def assemble_csr_host(dev, rows=None, host=None, nchunks=8, workspace=None, patt
     worker, err = None, []
     tm['setup_ms'] = 1e3 * (time.perf_counter() - t_start)
     ds = dev.device_structure
+    own_share = None
     if pattern == 'host':
+        # host cores of this rank (torchrun sets LOCAL_WORLD_SIZE): all but one write the pattern from the start;
+        # the calling thread joins them with the last rows once every chunk is enqueued, instead of idling in the
+        # stream synchronisation (with 8 ranks on 16 cores that doubles the writers of a rank)
+        import os
+        nthr = pattern_threads or max(1, (os.cpu_count() or 2) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))) - 1)
+        rm, own_share = pattern_split(rs, ra, rb, nthr, inner_r, inner_b)
+
         def fill():
             try:
-                ds.csr_pattern_host(host[0], host[1], row0=(ra, rb), nthreads=pattern_threads)
+                ds.csr_pattern_host(host[0], host[1], row0=(ra, rm), nthreads=nthr)
             except Exception as exc:        # surfaced after the join
                 err.append(exc)
         worker = threading.Thread(target=fill)
@@ -142,6 +163,10 @@ def assemble_csr_host(dev, rows=None, host=None, nchunks=8, workspace=None, patt
         row_off += cr
         nnz_off += cn
     tm['enqueue_ms'] = 1e3 * (time.perf_counter() - t_start) - tm['setup_ms']
+    if own_share is not None:
+        rm, _, row_m, nnz_m = own_share
+        ds.csr_pattern_host(host[0][row_m:], host[1][nnz_m:], row0=(rm, rb), indptr_offset=nnz_m, nthreads=1)
+        tm['own_pattern_ms'] = 1e3 * (time.perf_counter() - t_start) - tm['setup_ms'] - tm['enqueue_ms']
     copy_stream.synchronize()
     main.synchronize()
     tm['device_done_ms'] = 1e3 * (time.perf_counter() - t_start)

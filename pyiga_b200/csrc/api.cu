@@ -2135,50 +2135,140 @@ extern "C" int pb200_mlb_matvec(const pb200_mlstruct* a, int ra, int rb, const d
     return 0;
 }
 
-// host-only: CSR pattern of the rows [row0_begin, row0_end) of axis 0 of a multi-level banded structure
+// host-only: CSR pattern of the rows [row0_begin, row0_end) of axis 0 of a multi-level banded structure.
+// Every thread writes one contiguous piece of `indices`.  Rows are built in an L1-resident staging buffer (an
+// interior row is the previous row shifted by one column) and leave it in whole cache lines with non-temporal
+// stores: no read-for-ownership of the result arrays, which the GPU's D2H copies of the values are filling at
+// the same time (1.4-2.3x the rate of plain stores on 1-8 threads).
+#include <cstdint>
+#if defined(__SSE2__) || defined(__x86_64__)
+#include <emmintrin.h>
+#define PB_NT_STORES 1
+#endif
+
+template <class IT>
+struct PbRowStream {
+    static constexpr int CAP = 4096;                    // staging entries (16 / 32 KB)
+    static constexpr int LINE = 64 / (int)sizeof(IT);   // entries per cache line
+    IT* dst;                                            // next output position
+    int fill = 0;
+    bool aligned = false;                               // dst is on a cache-line boundary
+    alignas(64) IT buf[CAP];
+    explicit PbRowStream(IT* d) : dst(d) {}
+    static bool misaligned(const IT* q) { return ((uintptr_t)q & 63) != 0; }
+    // room for a row of `len` entries.  Earlier rows may leave; the row at buf[keep] (if keep >= 0) stays
+    // addressable and `keep` follows it.
+    IT* reserve(int len, int& keep) {
+        if (fill + len > CAP) flush(keep);
+        return buf + fill;
+    }
+    void flush(int& keep) {
+        const int upto = keep >= 0 ? keep : fill;       // entries [0, upto) may leave
+        int done = 0;
+        if (!aligned) {                                 // head of the piece: plain stores up to the first boundary
+            while (done < upto && misaligned(dst + done)) { dst[done] = buf[done]; ++done; }
+            aligned = !misaligned(dst + done);
+        }
+        if (aligned) {
+            const int lines = (upto - done) / LINE;
+#ifdef PB_NT_STORES
+            const __m128i* s = (const __m128i*)(buf + done);
+            __m128i* d = (__m128i*)(dst + done);
+            for (int l = 0; l < lines; ++l, s += 4, d += 4) {
+                const __m128i a = _mm_loadu_si128(s), b = _mm_loadu_si128(s + 1), c = _mm_loadu_si128(s + 2), e = _mm_loadu_si128(s + 3);
+                _mm_stream_si128(d, a); _mm_stream_si128(d + 1, b); _mm_stream_si128(d + 2, c); _mm_stream_si128(d + 3, e);
+            }
+#else
+            memcpy(dst + done, buf + done, (size_t)lines * 64);
+#endif
+            done += lines * LINE;
+        }
+        dst += done;
+        const int rest = fill - done;
+        if (rest > 0 && done > 0) memmove(buf, buf + done, (size_t)rest * sizeof(IT));
+        fill = rest;
+        if (keep >= 0) keep -= done;
+    }
+    void finish() {                                     // everything out (the tail of less than a line: plain stores)
+        int none = -1;
+        flush(none);
+        for (int e = 0; e < fill; ++e) dst[e] = buf[e];
+        dst += fill;
+        fill = 0;
+#ifdef PB_NT_STORES
+        _mm_sfence();
+#endif
+    }
+};
+
+template <class IT>
+static void pb_pattern_row(int L, const int* Nu, const int* nb, const int* j0, IT* o) {
+    if (L == 2) {
+        for (int k0 = 0; k0 < nb[0]; ++k0) {
+            const long long base = (long long)(j0[0] + k0) * Nu[1] + j0[1];
+            for (int k1 = 0; k1 < nb[1]; ++k1) *o++ = (IT)(base + k1);
+        }
+    } else {
+        for (int k0 = 0; k0 < nb[0]; ++k0)
+            for (int k1 = 0; k1 < nb[1]; ++k1) {
+                const long long base = ((long long)(j0[0] + k0) * Nu[1] + j0[1] + k1) * Nu[2] + j0[2];
+                for (int k2 = 0; k2 < nb[2]; ++k2) *o++ = (IT)(base + k2);
+            }
+    }
+}
+
 template <class IT>
 static void csr_pattern_rows(int L, const int* Nv, const int* Nu, const int* const* rs, const int* const* jm, const int* M,
                              int ra, long long r_begin, long long r_end, IT* indptr, IT* indices, long long off0) {
+    if (r_begin >= r_end) return;
     const long long m1 = L > 1 ? M[1] : 1, m2 = L > 2 ? M[2] : 1;
-    const long long inner = (long long)(L > 1 ? Nv[1] : 1) * (L > 2 ? Nv[2] : 1);
-    const IT* prev = nullptr;
-    long long prev_r = -2;
+    std::unique_ptr<PbRowStream<IT>> st(new PbRowStream<IT>(indices));
+    int prev = -1;                                      // the previous row in the staging buffer
     int prev_nb = 0, prev_j0 = 0, prev_len = 0;
-    for (long long r = r_begin; r < r_end; ++r) {
-        int i[3] = {0, 0, 0};
-        long long t = r;
+    int i[3] = {0, 0, 0};                               // per-axis row indices, advanced like an odometer
+    {
+        long long t = r_begin;
         for (int k = L - 1; k >= 1; --k) { i[k] = (int)(t % Nv[k]); t /= Nv[k]; }
         i[0] = (int)t + ra;
+    }
+    for (long long r = r_begin; r < r_end; ++r) {
         int nb[3] = {1, 1, 1}, j0[3] = {0, 0, 0};
         for (int k = 0; k < L; ++k) { nb[k] = rs[k][i[k] + 1] - rs[k][i[k]]; j0[k] = jm[k][i[k]]; }
         long long off = (long long)(rs[0][i[0]] - rs[0][ra]) * m1 * m2;
         if (L == 2) off += (long long)nb[0] * rs[1][i[1]];
         if (L == 3) off += (long long)nb[0] * ((long long)rs[1][i[1]] * m2 + (long long)nb[1] * rs[2][i[2]]);
         indptr[r] = (IT)(off0 + off);
-        IT* out = indices + off;
         const int len = nb[0] * nb[1] * nb[2];
-        // interior rows: the pattern of (.., i_last + 1) is the pattern of (.., i_last) shifted by one column
-        if (prev != nullptr && r == prev_r + 1 && i[L - 1] > 0 && nb[L - 1] == prev_nb && j0[L - 1] == prev_j0 + 1 && len == prev_len) {
-            const IT* __restrict src = prev;
-            IT* __restrict dst = out;
-            for (int e = 0; e < len; ++e) dst[e] = src[e] + 1;
-        } else if (L == 2) {
-            IT* o = out;
-            for (int k0 = 0; k0 < nb[0]; ++k0) {
-                const long long base = (long long)(j0[0] + k0) * Nu[1] + j0[1];
-                for (int k1 = 0; k1 < nb[1]; ++k1) *o++ = (IT)(base + k1);
-            }
-        } else {
-            IT* o = out;
-            for (int k0 = 0; k0 < nb[0]; ++k0)
-                for (int k1 = 0; k1 < nb[1]; ++k1) {
-                    const long long base = ((long long)(j0[0] + k0) * Nu[1] + j0[1] + k1) * Nu[2] + j0[2];
-                    for (int k2 = 0; k2 < nb[2]; ++k2) *o++ = (IT)(base + k2);
-                }
+        if (st->dst + st->fill != indices + off) {      // first row of the piece (rows of a piece are contiguous in CSR order)
+            st->finish();
+            st->dst = indices + off;
+            st->aligned = false;
+            prev = -1;
         }
-        prev = out; prev_r = r; prev_nb = nb[L - 1]; prev_j0 = j0[L - 1]; prev_len = len;
+        if (len > PbRowStream<IT>::CAP / 2) {           // very wide rows are not staged
+            st->finish();
+            pb_pattern_row<IT>(L, Nu, nb, j0, indices + off);
+            st->dst = indices + off + len;
+            st->aligned = false;
+            prev = -1;
+        } else {
+            IT* __restrict cur = st->reserve(len, prev);
+            // interior rows: the pattern of (.., i_last + 1) is the pattern of (.., i_last) shifted by one column
+            if (prev >= 0 && i[L - 1] > 0 && nb[L - 1] == prev_nb && j0[L - 1] == prev_j0 + 1 && len == prev_len) {
+                const IT* src = st->buf + prev;
+                for (int e = 0; e < len; ++e) cur[e] = src[e] + 1;
+            } else {
+                pb_pattern_row<IT>(L, Nu, nb, j0, cur);
+            }
+            prev = (int)(cur - st->buf);
+            st->fill += len;
+        }
+        prev_nb = nb[L - 1]; prev_j0 = j0[L - 1]; prev_len = len;
+        int k = L - 1;
+        while (k >= 1 && ++i[k] == Nv[k]) { i[k] = 0; --k; }
+        if (k == 0) ++i[0];
     }
-    (void)inner;
+    st->finish();
 }
 
 extern "C" int pb200_csr_pattern_host(int nlevels, const int* rows, const int* cols, const int* nband,

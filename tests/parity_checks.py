@@ -708,6 +708,50 @@ def check_csr_pattern_host(ref):
             ds.csr_pattern_host(got_ptr, got_idx, row0=(ra, rb), indptr_offset=5, nthreads=nthr)
             assert np.array_equal(got_ptr, want_ptr + 5), (case, ra, rb)
             assert np.array_equal(got_idx, want_idx), (case, ra, rb)
+    # larger structures: the staging buffer of the writer is flushed many times, pieces of several threads start
+    # at arbitrary (unaligned) positions of the result, rows of different widths alternate at the patch boundary
+    import scipy.sparse
+    from pyiga_b200 import bspline
+    from pyiga_b200._mlb import DeviceStructure
+    from pyiga_b200.mlmatrix import MLStructure
+    for kvs, kvs_test in [(tuple(bspline.make_knots(2, 0.0, 1.0, n) for n in (9, 10, 11)), None),
+                          ((bspline.make_knots(3, 0.0, 1.0, 40), bspline.make_knots(1, 0.0, 1.0, 50)), None),
+                          (tuple(bspline.make_knots(3, 0.0, 1.0, n) for n in (4, 6, 5)),
+                           tuple(bspline.make_knots(2, 0.0, 1.0, n) for n in (4, 6, 5)))]:
+        S = MLStructure.from_kvs(kvs_test or kvs, kvs)
+        I, J = (a.astype(np.int64) for a in S.nonzero())
+        A = scipy.sparse.csr_matrix((np.ones(I.size), (I, J)), shape=S.shape)
+        A.sort_indices()
+        ds = DeviceStructure(S)
+        n0 = S.bs[0][0]
+        inner = S.shape[0] // n0
+        for (ra, rb), idt, nthr, shift in [((0, n0), np.int32, 1, 0), ((0, n0), np.int32, 8, 3), ((0, n0), np.int64, 5, 1),
+                                           ((2, n0 - 1), np.int32, 3, 7), ((1, 2), np.int64, 2, 5)]:
+            r0, r1 = ra * inner, rb * inner
+            want_ptr = A.indptr[r0:r1 + 1].astype(np.int64) - A.indptr[r0]
+            want_idx = A.indices[A.indptr[r0]:A.indptr[r1]]
+            # `shift` entries of padding in front: the result does not start on a cache line
+            buf_ptr = np.full(want_ptr.size + shift + 16, -7, dtype=idt)
+            buf_idx = np.full(want_idx.size + shift + 16, -7, dtype=idt)
+            got_ptr, got_idx = buf_ptr[shift:shift + want_ptr.size], buf_idx[shift:shift + want_idx.size]
+            ds.csr_pattern_host(got_ptr, got_idx, row0=(ra, rb), nthreads=nthr)
+            assert np.array_equal(got_ptr, want_ptr) and np.array_equal(got_idx, want_idx), (S.shape, ra, rb, nthr)
+            assert (buf_idx[:shift] == -7).all() and (buf_idx[shift + want_idx.size:] == -7).all()     # nothing outside
+            assert (buf_ptr[:shift] == -7).all() and (buf_ptr[shift + want_ptr.size:] == -7).all()
+            # the two-part fill of the pipelined delivery (_hostcsr: pattern threads + the calling thread)
+            from pyiga_b200._hostcsr import pattern_split
+            rs0 = np.asarray(S._row_tables(0)[0])
+            inner_b = int(np.prod([len(b) for b in S.bidx[1:]], dtype=np.int64))
+            for nthr2 in (1, 3):
+                rm, own = pattern_split(rs0, ra, rb, nthr2, inner, inner_b)
+                two_ptr, two_idx = np.full_like(got_ptr, -9), np.full_like(got_idx, -9)
+                ds.csr_pattern_host(two_ptr, two_idx, row0=(ra, rm), nthreads=nthr2)
+                if own is not None:
+                    assert own[0] == rm and own[1] == rb and ra < rm < rb
+                    ds.csr_pattern_host(two_ptr[own[2]:], two_idx[own[3]:], row0=(rm, rb), indptr_offset=own[3], nthreads=1)
+                else:
+                    assert rm == rb
+                assert np.array_equal(two_ptr, want_ptr) and np.array_equal(two_idx, want_idx), (S.shape, ra, rb, nthr2)
 
 
 def check_boundary_reference_tests():

@@ -140,3 +140,44 @@ def test_argument_checks_of_device_entry_points():
     assert lib.pb200_vec_gather(3, None, None, None, None) == -1
     assert lib.pb200_asm_rows_count(None, None, 0, None) == -1
     assert b'null' in lib.pb200_last_error()
+
+
+def test_host_csr_pattern_product_library():
+    """pb200_csr_pattern_host of the PRODUCT library (host-only entry point: staged rows, non-temporal stores)
+    against the pattern built from MLStructure.nonzero — whole matrices and slabs, several threads, results that
+    do not start on a cache line, 32- and 64-bit indices"""
+    import scipy.sparse
+    from pyiga_b200 import _lib, bspline
+    from pyiga_b200.mlmatrix import MLStructure
+    lib = _lib.load()
+    for ps, ns in [((3, 3, 3), (9, 8, 10)), ((2, 4), (30, 41)), ((1, 2, 3), (5, 6, 7))]:
+        kvs = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(ps, ns))
+        S = MLStructure.from_kvs(kvs, kvs)
+        L = S.L
+        I, J = (a.astype(np.int64) for a in S.nonzero())
+        A = scipy.sparse.csr_matrix((np.ones(I.size), (I, J)), shape=S.shape)
+        A.sort_indices()
+        tabs = [S._row_tables(k) for k in range(L)]
+        rows = (C.c_int * L)(*[b[0] for b in S.bs])
+        cols = (C.c_int * L)(*[b[1] for b in S.bs])
+        nband = (C.c_int * L)(*[len(b) for b in S.bidx])
+        rs = [np.ascontiguousarray(t[0], dtype=np.int32) for t in tabs]
+        jm = [np.ascontiguousarray(t[1], dtype=np.int32) for t in tabs]
+        p_rs = (C.c_void_p * L)(*[a.ctypes.data for a in rs])
+        p_jm = (C.c_void_p * L)(*[a.ctypes.data for a in jm])
+        n0 = S.bs[0][0]
+        inner = S.shape[0] // n0
+        for (ra, rb), idt, nthr, shift in [((0, n0), np.int32, 1, 0), ((0, n0), np.int32, 7, 5), ((1, n0 - 1), np.int64, 4, 3),
+                                           ((n0 - 1, n0), np.int32, 16, 9)]:
+            r0, r1 = ra * inner, rb * inner
+            want_ptr = A.indptr[r0:r1 + 1].astype(np.int64) - A.indptr[r0] + 11
+            want_idx = A.indices[A.indptr[r0]:A.indptr[r1]]
+            buf_ptr = np.full(want_ptr.size + shift + 16, -7, dtype=idt)
+            buf_idx = np.full(want_idx.size + shift + 16, -7, dtype=idt)
+            got_ptr, got_idx = buf_ptr[shift:shift + want_ptr.size], buf_idx[shift:shift + want_idx.size]
+            rc = lib.pb200_csr_pattern_host(L, rows, cols, nband, p_rs, p_jm, ra, rb, got_ptr.ctypes.data, got_idx.ctypes.data,
+                                            np.dtype(idt).itemsize, 11, nthr)
+            assert rc == 0, lib.pb200_last_error()
+            assert np.array_equal(got_ptr, want_ptr) and np.array_equal(got_idx, want_idx), (ps, ns, ra, rb, nthr)
+            assert (buf_idx[:shift] == -7).all() and (buf_idx[shift + want_idx.size:] == -7).all()
+            assert (buf_ptr[:shift] == -7).all() and (buf_ptr[shift + want_ptr.size:] == -7).all()
