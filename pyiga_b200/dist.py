@@ -48,16 +48,33 @@ def _partition_by_work(dev, nparts):
     n = supp.shape[0]
     symmetric = dev.same_space and dev.form in (_lib.FORM_MASS, _lib.FORM_STIFFNESS)
     alpha = 0.8 * (kv.p + 1)
+    key = (kv.kv.tobytes(), int(kv.p), int(nparts), bool(symmetric))
+    if key in _work_partitions:
+        return list(_work_partitions[key])
     rs = np.searchsorted(I, np.arange(n + 1))
     upper = np.concatenate(([0], np.cumsum(np.bincount(I[J >= I], minlength=n)))) if symmetric else rs
+    # plain Python numbers: the search below evaluates the cost several thousand times
+    s_lo, s_hi = supp[:, 0].tolist(), supp[:, 1].tolist()
+    upper = [int(u) for u in upper]
+    if symmetric:
+        # lower[ra][k]: band entries of the rows [ra, ra + k) whose column lies below ra (k <= p + 1: rows further
+        # down do not reach below ra) — the lower entries a slab starting at ra computes itself because their
+        # partner row belongs to another slab
+        lower = []
+        for ra in range(n):
+            acc, row = 0, [0]
+            for k in range(1, kv.p + 2):
+                if ra + k <= n:
+                    acc += int(np.count_nonzero(J[rs[ra + k - 1]:rs[ra + k]] < ra))
+                row.append(acc)
+            lower.append(row)
+    pmax = kv.p + 1
 
     def cost(ra, rb):
-        spans = supp[rb - 1, 1] - supp[ra, 0]
         ent = upper[rb] - upper[ra]
-        if symmetric:       # lower entries whose partner row is outside the slab
-            lo, hi = rs[ra], rs[min(rb, ra + kv.p + 1)]
-            ent += int(np.count_nonzero(J[lo:hi] < ra))
-        return alpha * spans + ent
+        if symmetric:
+            ent += lower[ra][min(rb - ra, pmax)]
+        return alpha * (s_hi[rb - 1] - s_lo[ra]) + ent
 
     def cuts_for(limit):
         cuts, ra = [0], 0
@@ -90,7 +107,13 @@ def _partition_by_work(dev, nparts):
         if best[k + 1] - best[k] < 2:
             return None
         best.insert(k + 1, (best[k] + best[k + 1]) // 2)
+    if len(_work_partitions) > 64:
+        _work_partitions.clear()
+    _work_partitions[key] = tuple(best)
     return best
+
+
+_work_partitions = {}       # (knots, degree, parts, symmetric) -> cuts: every assembler of a rank asks again
 
 
 class SlabAssembly:
