@@ -218,7 +218,9 @@ def inner_products(kvs, f, f_physical=False, geo=None):
     if dim == 1:
         # marginal of the 2D functional on (kv) x (one linear element), as in _assemble_1d: the two
         # functions of the dummy axis sum to 1, and f only sees the first coordinate
-        assert geo is None, "Geometry map not supported for 1D inner products"
+        if geo is not None:     # (``test/test_assemble.py:441-444``) the load vector of 'f * v * dx' on the mapped interval
+            fin = f if (f_physical or hasattr(f, 'grid_eval')) else assemblers._ParametricCallable(f, (kvs,))
+            return assemble('f * v * dx', (kvs,), geo=geo, f=fin)
         unit = bspline.make_knots(1, 0.0, 1.0, 1)
         kvs2 = (kvs, unit)
         v = assemblers.L2FunctionalAssembler2D(kvs2, geometry.identity(kvs2), lambda x, y: f(y)).assemble_vector()

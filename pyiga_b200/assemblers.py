@@ -25,6 +25,54 @@ def _is_spline_geo(geo):
     return hasattr(geo, 'kvs') and hasattr(geo, 'coeffs')
 
 
+# ---- forms over ONE knot vector ---------------------------------------------------------------
+# The device pipeline takes 2 or 3 tensor axes.  A form over (kv,) (``test/test_assemble.py:436-445``) runs on the
+# lifted space (one linear element in eta) x (kv) with the geometry (x(xi), eta) and coefficients that do not
+# depend on eta: the lifted matrix is  M_eta (x) A  with the 2 x 2 mass matrix of the linear element, whose entries
+# sum to 1 — A is the sum of the four eta blocks (and a load vector the sum of its two eta rows).
+def _lift_axis():
+    from . import bspline
+    return bspline.make_knots(1, 0.0, 1.0, 1)
+
+
+class _LiftedGeo1D:
+    """(eta, xi) -> (x(xi), eta) for a geometry that is not a spline (Jacobian evaluated on the host)"""
+
+    def __init__(self, geo):
+        self.geo, self.sdim, self.dim = geo, 2, 2
+
+    def grid_jacobian(self, grid):
+        d = np.asarray(self.geo.grid_jacobian((grid[1],)), dtype=float).reshape(len(grid[1]))
+        J = np.zeros((len(grid[0]), len(grid[1]), 2, 2))
+        J[..., 0, 0] = d[None, :]           # x depends on xi_0 = the last grid axis
+        J[..., 1, 1] = 1.0
+        return J
+
+
+def _lift_geo_1d(geo):
+    """the geometry (eta, xi) -> (x(xi), eta) as a spline of our own classes when `geo` is a spline"""
+    from . import bspline, geometry
+    if not _is_spline_geo(geo):
+        return _LiftedGeo1D(geo)
+    kv = tuple(geo.kvs)[0]
+    kvs = (_lift_axis(), bspline.KnotVector(np.asarray(kv.kv, dtype=float), int(kv.p)))
+    n = kvs[1].numdofs
+    c = np.asarray(geo.coeffs, dtype=float).reshape(n, -1)
+    eta = np.array([0.0, 1.0])
+    rational = bool(getattr(geo, '_rational', False)) or type(geo).__name__ == 'NurbsFunc'
+    if rational:        # homogeneous, premultiplied: (w x, w) -> (w x, w eta, w)
+        assert c.shape[1] == 2, 'geometry of a 1D form must map to R'
+        C = np.empty((2, n, 3))
+        C[..., 0], C[..., 2] = c[None, :, 0], c[None, :, 1]
+        C[..., 1] = eta[:, None] * c[None, :, 1]
+        return geometry.NurbsFunc(kvs, C, None, premultiplied=True)
+    assert c.shape[1] == 1, 'geometry of a 1D form must map to R'
+    C = np.empty((2, n, 2))
+    C[..., 0] = c[None, :, 0]
+    C[..., 1] = eta[:, None]
+    return bspline.BSplineFunc(kvs, C)
+
+
 class DeviceAssembler:
     """Handle on a ``pb200_assembler``: tables, fields and kernels for one (spaces, form, geometry)."""
 
@@ -527,6 +575,7 @@ class GenericFormAssembler(_AssemblerProtocol):
     (test component, trial component) is one scalar form.
     """
     _vf = None
+    _lift1d = False
 
     def __init__(self, kvs, kvs_test=None, bbox=None, **args):
         vf = self._vf
@@ -534,6 +583,7 @@ class GenericFormAssembler(_AssemblerProtocol):
         self.bbox = bbox            # on-demand box of the reference's generated classes: not needed here
         d = vf.dim
         assert len(kvs) == d, "Assembler requires %d knot vectors" % d
+        self._lift1d = (d == 1)
         if vf.num_spaces() == 2:
             # Petrov-Galerkin: trial functions in `kvs` (space 0, columns), test functions in
             # `kvs_test` (space 1, rows), on the same mesh (``pyiga/assemble.py:947-951``)
@@ -582,10 +632,37 @@ class GenericFormAssembler(_AssemblerProtocol):
         if self._vec:
             self.num_components = lambda: self._nc
         self.blocks = {}
+        if self._lift1d:
+            if self._bd is not None or self._surface or self._vec:
+                raise NotImplementedError('boundary, surface and vector-valued forms over one knot vector')
+            lift = _lift_axis()
+            kvs, kvs_test, d = (lift,) + kvs, ((lift,) + kvs_test if kvs_test is not None else None), 2
+            self._lift_grid = make_tensor_quadrature([kv.mesh for kv in kvs], self.nqp)[0]
         for blk, coefs in self._analyse().items():
-            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, geo, self.gaussgrid, quad=quad, kvs_test=kvs_test, host_pullback=self._surface)
+            self.blocks[blk] = _FormBlock(kvs, self.nqp, d, self.arity, coefs, self._block_geo(), self._block_grid(), quad=quad,
+                                          kvs_test=kvs_test, host_pullback=self._surface)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
+
+    def _block_geo(self):
+        """the geometry the device blocks are built on (lifted for forms over one knot vector)"""
+        return _lift_geo_1d(self._geo) if self._lift1d else self._geo
+
+    def _block_grid(self):
+        return self._lift_grid if self._lift1d else self.gaussgrid
+
+    # ---- forms over one knot vector: marginals of the lifted results -----------------------------
+    def _marginal_matrix(self):
+        """scipy CSR matrix of a scalar form over (kv,): the four eta blocks of the lifted MLB tensor summed"""
+        import scipy.sparse
+        dev = self.dev
+        S = dev.structure
+        data = dev.be.to_host(dev.assemble_mlb()).reshape(tuple(len(b) for b in S.bidx))
+        bidx = np.asarray(S.bidx[1], dtype=np.int64)
+        shape = (self.kvs[1][0].numdofs, self.kvs[0][0].numdofs)
+        A = scipy.sparse.csr_matrix((data.sum(axis=0), (bidx[:, 0], bidx[:, 1])), shape=shape)
+        A.sort_indices()
+        return A
 
     # ---- boundary integrals --------------------------------------------------------------------
     def _setup_boundary(self, kvs, boundary):
@@ -751,7 +828,7 @@ class GenericFormAssembler(_AssemblerProtocol):
         if sorted(blocks, key=str) != sorted(self.blocks, key=str):
             raise RuntimeError('update() changed the structure of the form')
         for blk, coefs in blocks.items():
-            self.blocks[blk].compute_fields(coefs, self._geo)
+            self.blocks[blk].compute_fields(coefs, self._block_geo())
 
     # ---- vector-valued forms -----------------------------------------------------------------
     def _block_mlb(self):
@@ -770,6 +847,12 @@ class GenericFormAssembler(_AssemblerProtocol):
         return out
 
     def assemble_mlb(self, layout='packed', **kw):
+        if self._lift1d:
+            from .mlmatrix import MLStructure
+            A = self._marginal_matrix()
+            S = MLStructure.from_kvs(self.kvs[1], self.kvs[0])
+            bidx = np.asarray(S.bidx[0], dtype=np.int64)
+            return MLMatrix(structure=S, data=np.asarray(A[bidx[:, 0], bidx[:, 1]]).ravel())
         if self._bd is not None:
             if self._vec:
                 raise NotImplementedError('vector-valued boundary forms in MLB format')
@@ -791,6 +874,8 @@ class GenericFormAssembler(_AssemblerProtocol):
         return X
 
     def assemble_csr(self, layout='blocked', format='csr', **kw):
+        if self._lift1d:
+            return self._marginal_matrix()
         if self._bd is not None and not self._vec:
             return self._bd_matrix(self.blocks[(0, 0)]).asmatrix('csr')
         if not self._vec:
@@ -824,6 +909,8 @@ class GenericFormAssembler(_AssemblerProtocol):
         if self.arity != 1:
             return None
         be = self.dev.be
+        if self._lift1d:
+            return be.to_host(self.dev.assemble_vector_device()).reshape(self.dev.ndofs_test).sum(axis=0)
         sel = (lambda a: a) if self._bd is None else (lambda a: self._bd_select(a, 1))
         if not self._vec:
             return sel(be.to_host(self.dev.assemble_vector_device()).reshape(self.dev.ndofs_test))
@@ -846,6 +933,11 @@ class GenericFormAssembler(_AssemblerProtocol):
     def multi_entries(self, indices):
         if self.arity == 1:
             return self.multi_entries1(indices)
+        if self._lift1d:
+            if not isinstance(indices, np.ndarray):
+                indices = np.array(list(indices), dtype=np.int64)
+            indices = np.asarray(indices, dtype=np.int64).reshape(-1, 2)
+            return np.asarray(self._marginal_matrix()[indices[:, 0], indices[:, 1]]).ravel()
         if self._bd is not None:
             if not isinstance(indices, np.ndarray):
                 indices = np.array(list(indices), dtype=np.int64)
@@ -863,6 +955,8 @@ class GenericFormAssembler(_AssemblerProtocol):
         return float(self.multi_entries1([i])[0]) if self.arity == 1 else 0.0
 
     def entry(self, i, j):
+        if self._lift1d and self.arity == 2:
+            return float(self.multi_entries(np.array([[i, j]]))[0])
         return super().entry(i, j) if self.arity == 2 else 0.0
 
     def update(self, **kwargs):
@@ -953,8 +1047,16 @@ class _L2FunctionalBase(GenericFormAssembler):
 
 class _ParametricCallable:
     """plain callable evaluated on the parameter grid (``pyiga/utils.py:33-41`` grid_eval)"""
-    def __init__(self, f):
+    def __init__(self, f, kvs=None):
         self.f = f
+        if kvs is not None:         # lets the form parser treat it like a (scalar) spline function: parametric input
+            self.kvs = tuple(kvs)
+
+    def output_shape(self):
+        return ()
+
+    def __call__(self, *x):
+        return self.f(*x)
 
     def grid_eval(self, grid):
         mesh = list(np.meshgrid(*grid, sparse=True, indexing='ij'))

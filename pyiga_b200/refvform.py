@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _device, _lib
 from ._devarray import DevArray, unwrap
-from .assemblers import DeviceAssembler, GenericFormAssembler, _AssemblerProtocol, _is_spline_geo
+from .assemblers import DeviceAssembler, GenericFormAssembler, _AssemblerProtocol, _is_spline_geo, _lift_axis
 from .mlmatrix import MLMatrix
 from .quadrature import make_tensor_quadrature
 
@@ -376,6 +376,9 @@ class RefVFormAssembler(GenericFormAssembler):
         self._geo, self._args = geo, dict(args)
         self.bbox = bbox
         self._bd, self._surface = None, False
+        self._lift1d = (d == 1)     # one knot vector: the lifted space of GenericFormAssembler (assemblers.py)
+        if self._lift1d and (vf.is_boundary or (self._on_demand and bbox is not None) or vf.vec):
+            raise NotImplementedError('boundary, on_demand and vector-valued forms over one knot vector')
         meshes = [np.asarray(kv.mesh) for kv in kvs]
         full_grid, full_w = make_tensor_quadrature(meshes, self.nqp)
         box = None
@@ -403,6 +406,15 @@ class RefVFormAssembler(GenericFormAssembler):
         self._grid_shape = tuple(len(g) for g in grid)
         full_shape = tuple(len(g) for g in full_grid)
         itp = _Interpreter(vf, grid, w, args, geo)
+        if self._lift1d:
+            lift = _lift_axis()
+            kvs_dev, kvs_test = (lift,) + kvs, ((lift,) + kvs_test if kvs_test is not None else None)
+            _, (w_eta, _w) = make_tensor_quadrature([np.asarray(lift.mesh), meshes[0]], self.nqp)
+            weta = itp._up(np.asarray(w_eta, dtype=float)).reshape(-1, 1)
+            self._grid_shape = full_shape = (len(w_eta),) + self._grid_shape
+            d_dev = 2
+        else:
+            d_dev = d
         nc_u = (vf.basis_funs[0].numcomp or 1) if vf.arity == 2 else 1
         nc_v = (vf.basis_funs[-1].numcomp or 1)
         self._vec = bool(vf.vec)
@@ -431,7 +443,12 @@ class RefVFormAssembler(GenericFormAssembler):
                         for sl in (vs, us):
                             if sl is not None and sl[1][d - 1 - self._bd[0]] > 1:
                                 raise NotImplementedError('second normal derivatives in boundary integrals')
-                    key = (_slot_to_axis(vs, d), _slot_to_axis(us, d))
+                    if self._lift1d:        # (eta, xi): no derivative in eta, the weights of the eta rule
+                        vs, us = ((sl[0], tuple(sl[1]) + (0,)) if sl is not None else None for sl in (vs, us))
+                        key = (_slot_to_axis(vs, 2), _slot_to_axis(us, 2))
+                        c = weta * c
+                    else:
+                        key = (_slot_to_axis(vs, d), _slot_to_axis(us, d))
                     dst = blocks.setdefault(blk, {})
                     dst[key] = dst[key] + c if key in dst else c
         if not blocks:
@@ -442,7 +459,7 @@ class RefVFormAssembler(GenericFormAssembler):
             # form on an affine map) would only cost launches
             live = {k: c for k, c in coefs.items() if (bool((c != 0.0).any()) if _is_tensor(c) else np.any(np.asarray(c) != 0.0))}
             coefs = live or dict([next(iter(coefs.items()))])
-            self.blocks[blk] = _ParametricBlock(kvs_dev, self.nqp, d, self.arity, coefs, self._grid_shape, full_shape, box, quad=quad,
+            self.blocks[blk] = _ParametricBlock(kvs_dev, self.nqp, d_dev, self.arity, coefs, self._grid_shape, full_shape, box, quad=quad,
                                                 kvs_test=kvs_test)
         first = next(iter(self.blocks.values()))
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
@@ -457,8 +474,8 @@ def compile_vform(vf, on_demand=False):
     key = (id(vf), bool(on_demand))
     cls = _cache.get(key)
     if cls is None:
-        if vf.dim < 2 or vf.dim > 3:
-            raise NotImplementedError('the device assemblers take 2 or 3 knot vectors (form of dimension %d)' % vf.dim)
+        if vf.dim < 1 or vf.dim > 3:
+            raise NotImplementedError('forms over 1 to 3 knot vectors (form of dimension %d)' % vf.dim)
         if not getattr(vf, '_VForm__is_finalized', False):
             vf.finalize(do_precompute=True)
         cls = type('RefVFormAssembler%d' % len(_cache), (RefVFormAssembler,), {'_rvf': vf, '_vf': vf, '_on_demand': bool(on_demand)})

@@ -158,3 +158,34 @@ def hcases():
         'hconv': (lambda: rvf.parse_vf('(inner(grad(u), grad(v)) + inner((1.0, x[0]), grad(u)) * v + c * u * v) * dx', kvs0,
                                        args={'c': c}), {'c': c}, False),
     }
+
+
+def cases1d():
+    """forms over ONE knot vector (test/test_assemble.py:436-445): name -> (string or VForm factory, kvs, geo, inputs).
+    Strings go through the string front end of the package under test, factories build reference VForm objects."""
+    from pyiga import bspline as rbs, geometry as rgeo, vform as rvf
+    kv = rbs.make_knots(3, 0.0, 1.0, 7)
+    kvm = rbs.make_knots(2, 0.0, 1.0, 5, mult=2)
+    kvg = rbs.make_knots(2, 0.0, 1.0, 2)
+    geo_id = rgeo.unit_cube(dim=1)
+    geo_c = rbs.BSplineFunc((kvg,), np.array([[0.0], [0.2], [0.5], [1.3]]))
+    geo_r = rgeo.NurbsFunc((kvg,), np.array([[0.5], [0.9], [1.2], [2.0]]), np.array([1.0, 0.8, 1.3, 1.0]))
+    a = lambda x: 1.0 + x * x
+    f = lambda x: 1.0 + x ** 2
+
+    def mass_f():
+        vf = rvf.VForm(1)
+        u, v = vf.basisfuns()
+        c = vf.input('c', physical=True)
+        vf.add(c * u * v * rvf.dx)
+        return vf
+
+    return {
+        's_stiff': ('inner(grad(u), grad(v)) * dx', (kv,), geo_id, {}),
+        's_rhs': ('f * v * dx', (kv,), geo_id, {'f': f}),
+        's_cd_curved': ('(a * inner(grad(u), grad(v)) + Dx(u, 0) * v + u * v) * dx', (kvm,), geo_c, {'a': a}),
+        's_rhs_nurbs': ('f * v * dx', (kv,), geo_r, {'f': f}),
+        'o_stiff': (lambda: rvf.stiffness_vf(1), (kvm,), geo_c, {}),
+        'o_mass_c': (mass_f, (kv,), geo_r, {'c': a}),
+        'o_l2': (lambda: rvf.L2functional_vf(1, physical=True), (kv,), geo_c, {'f': f}),
+    }

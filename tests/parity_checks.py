@@ -1290,3 +1290,51 @@ def check_device_callables(ref):
     if on_gpu:
         assert 'DevArray' in types and 'ndarray' not in types, types      # (a scalar probe of the output shape comes first)
     assert abs(A - B).max() <= RTOL * abs(B).max()
+
+
+def check_forms_1d():
+    """Forms over ONE knot vector (test/test_assemble.py:436-445) — strings through the package's front end, VForm
+    objects of the reference through refvform — against the reference's JIT-compiled assemblers
+    (tests/golden/make_golden_1d.py).  The device runs them on a lifted two-axis space (assemblers.py)."""
+    _import_reference()
+    from pyiga_b200 import assemble, bspline
+    rc, _ = _vform_fixture()
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_forms_1d.npz'))
+    for name, (problem, kvs, geo, inputs) in rc.cases1d().items():
+        want = fix['f1_' + name]
+        got = assemble.assemble(problem if isinstance(problem, str) else problem(), kvs, geo=geo, **inputs)
+        got = got.toarray() if hasattr(got, 'toarray') else np.asarray(got)
+        assert got.shape == want.shape, name
+        assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), (name, np.abs(got - want).max())
+    # the reference's own assertions: the forms equal the 1D helpers
+    kv = bspline.make_knots(3, 0.0, 1.0, 7)
+    from pyiga_b200 import geometry
+    geo = geometry.unit_cube(dim=1)
+    A1 = assemble.assemble('inner(grad(u), grad(v)) * dx', (kv,), geo=geo)
+    assert np.allclose(A1.toarray(), assemble.stiffness(kv).toarray(), rtol=0, atol=1e-12 * abs(A1).max())
+    f = lambda x: 1 + x ** 2
+    f1 = assemble.assemble('f * v * dx', (kv,), geo=geo, f=f)
+    assert np.allclose(f1, assemble.inner_products(kv, f=f, f_physical=True, geo=geo), rtol=0, atol=1e-14)
+    # inner_products over a mapped interval, f in parameter and in physical coordinates, against the reference's function
+    from pyiga import assemble as rasm
+    _, rkvs, rgeo_c, _ = rc.cases1d()['o_stiff']
+    g = lambda t: np.cos(2.0 * t) + t
+    for phys in (False, True):
+        want = rasm.inner_products(rkvs[0], g, f_physical=phys, geo=rgeo_c)
+        got = assemble.inner_products(rkvs[0], g, f_physical=phys, geo=rgeo_c)
+        assert got.shape == want.shape and np.abs(got - want).max() <= RTOL * np.abs(want).max(), phys
+    # assembler protocol on a form over one knot vector: entries, MLB format, updatable inputs
+    problem, kvs, geo, inputs = rc.cases1d()['s_cd_curved']
+    want = fix['f1_s_cd_curved']
+    asm = assemble.Assembler(problem, kvs, geo=geo, updatable=['a'], **inputs)
+    A = asm.assemble()
+    assert np.abs(A.toarray() - want).max() <= RTOL * np.abs(want).max()
+    ij = np.array([[0, 0], [3, 4], [4, 3], [10, 9], [0, 7]])
+    vals = asm.asm.multi_entries(ij)
+    assert np.abs(vals - want[ij[:, 0], ij[:, 1]]).max() <= RTOL * np.abs(want).max()
+    assert abs(asm.asm.entry(3, 4) - want[3, 4]) <= RTOL * np.abs(want).max()
+    M = asm.assemble(format='mlb')
+    assert np.abs(M.asmatrix().toarray() - want).max() <= RTOL * np.abs(want).max()
+    B = asm.assemble(a=lambda x: 2.0 + 2.0 * x * x).toarray()          # a -> 2a: only the diffusion term doubles
+    K = assemble.assemble('a * inner(grad(u), grad(v)) * dx', kvs, geo=geo, a=inputs['a']).toarray()
+    assert np.abs(B - (want + K)).max() <= 1e-11 * np.abs(want).max()

@@ -265,3 +265,10 @@ def test_partition_by_assembly_work(emu, p, n):
 
 def test_device_callables(emu, ref):
     pc.check_device_callables(ref)
+
+
+@pytest.mark.parametrize('tensors', [False, True])
+def test_forms_1d(emu, monkeypatch, tensors):
+    from pyiga_b200 import refvform
+    monkeypatch.setattr(refvform, '_FORCE_TENSORS', tensors)
+    pc.check_forms_1d()

@@ -294,6 +294,10 @@ def test_device_callables(cuda, ref):
     pc.check_device_callables(ref)
 
 
+def test_forms_1d(cuda):
+    pc.check_forms_1d()
+
+
 @pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
 @pytest.mark.parametrize('p,ns,split', [(1, (3, 5, 70), None), (2, (3, 4, 66), None), (3, (2, 9, 40), None),
                                         (3, (3, 36, 35), 2), (2, (4, 40, 33), 3), (3, (3, 3, 33), 4),
