@@ -42,39 +42,49 @@ def _assemble_1d(kv, form):
     return scipy.sparse.csr_matrix((vals, (b[:, 0].astype(np.int64), b[:, 1].astype(np.int64))), shape=(n, n))
 
 
-def bsp_mixed_deriv_biform_1d_asym(knotvec1, knotvec2, du, dv, quadgrid=None, nqp=None):
-    """Matrix of ``a(u, v) = (u^(du), v^(dv))`` between two B-spline bases on one mesh: trial functions
-    in `knotvec1` (columns), test functions in `knotvec2` (rows), derivative orders 0 or 1
-    (``pyiga/assemble.py:192-222``).  Computed on the device as the marginal of the lifted 2D
-    Petrov-Galerkin form over (kv) x (one linear element), see :func:`_assemble_1d`; the Gauss rule
-    has max(p)+1 points per span, which is exact for these polynomial integrands like the reference's."""
+def bsp_mixed_deriv_biform_1d_asym(knotvec1, knotvec2, du, dv, quadgrid=None, nqp=None, weightfunc=None):
+    """Matrix of ``a(u, v) = (w u^(du), v^(dv))`` between two B-spline bases on one mesh: trial functions
+    in `knotvec1` (columns), test functions in `knotvec2` (rows), derivative orders 0, 1 or 2
+    (``pyiga/assemble.py:192-222``).  Computed on the device as the marginal of a lifted two-axis form over
+    (one linear element) x (kv) whose only coefficient field is the product of the Gauss weights (and of the
+    weight function at the nodes), see :func:`_assemble_1d`; the Gauss rule has max(p)+1 points per span,
+    which is exact for these polynomial integrands like the reference's."""
     import scipy.sparse
-    if quadgrid is not None or nqp is not None:
-        raise NotImplementedError('custom quadrature grids are not part of the device path')
-    if du not in (0, 1) or dv not in (0, 1):
-        raise NotImplementedError('derivative orders above 1 are not part of the device path')
-    unit = bspline.make_knots(1, 0.0, 1.0, 1)
-    kvs0, kvs1 = (knotvec1, unit), (knotvec2, unit)
-    eu = 'Dx(u, 1)' if du else 'u'          # axis 0 of the lifted space is the y coordinate
-    ev = 'Dx(v, 1)' if dv else 'v'
+    from . import refvform
+    from .quadrature import make_tensor_quadrature
+    same_mesh = np.array_equal(np.asarray(knotvec1.mesh), np.asarray(knotvec2.mesh))
+    if not same_mesh or (quadgrid is not None and not np.array_equal(np.asarray(quadgrid), np.asarray(knotvec1.mesh))):
+        raise NotImplementedError('both bases and the quadrature grid must share one mesh on the device path')
+    nq = max(knotvec1.p, knotvec2.p) + 1
+    if nqp is not None and nqp != nq:
+        raise NotImplementedError('custom numbers of quadrature nodes are not part of the device path')
+    if weightfunc is not None and nqp is None and du + dv > 0:
+        # the reference takes ceil((p1 + p2 - du - dv + 1) / 2) nodes: exact for polynomial integrands, so the
+        # rule does not matter without a weight — with one it does, and the device tables have p+1 nodes
+        raise NotImplementedError('weighted forms with derivatives use the (p+1)-node rule here: pass nqp=%d '
+                                  '(to the reference as well) to get the same quadrature' % nq)
+    if du not in (0, 1, 2) or dv not in (0, 1, 2):
+        raise NotImplementedError('derivative orders above 2 are not part of the device path')
+    lift = assemblers._lift_axis()
+    (g_eta, g_x), (w_eta, w_x) = make_tensor_quadrature([np.asarray(lift.mesh), np.asarray(knotvec1.mesh)], nq)
+    coef = np.asarray(w_eta)[:, None] * np.asarray(w_x)[None, :]
+    if weightfunc is not None:
+        coef = coef * np.asarray(weightfunc(np.asarray(g_x)), dtype=float)[None, :]
+    key = (refvform._slot_to_axis((0, (dv, 0)), 2), refvform._slot_to_axis((0, (du, 0)), 2))
     same = knotvec1 == knotvec2
-    if same:
-        M = assemble('%s * %s * dx' % (eu, ev), kvs0, geo=geometry.identity(kvs0), format='mlb')
-    else:
-        M = assemble('%s * %s * dx' % (eu, ev), (kvs0, kvs1), geo=geometry.identity(kvs0),
-                     bfuns=[('u', 1, 0), ('v', 1, 1)], format='mlb')
-    vals = M.data.sum(axis=1)
-    b = M.structure.bidx[0]
-    return scipy.sparse.csr_matrix((vals, (b[:, 0].astype(np.int64), b[:, 1].astype(np.int64))),
-                                   shape=(knotvec2.numdofs, knotvec1.numdofs))
+    blk = refvform._ParametricBlock((lift, knotvec1), nq, 2, 2, {key: coef}, coef.shape,
+                                    kvs_test=None if same else (lift, knotvec2))
+    S = blk.dev.structure
+    data = blk.dev.be.to_host(blk.dev.assemble_mlb()).reshape(tuple(len(b) for b in S.bidx))
+    b = np.asarray(S.bidx[1], dtype=np.int64)
+    A = scipy.sparse.csr_matrix((data.sum(axis=0), (b[:, 0], b[:, 1])), shape=(knotvec2.numdofs, knotvec1.numdofs))
+    A.sort_indices()
+    return A
 
 
 def bsp_mixed_deriv_biform_1d(knotvec, du, dv, nqp=None, weightfunc=None):
-    """``a(u, v) = (u^(du), v^(dv))`` on one knot vector (``pyiga/assemble.py:179-190``)."""
-    if weightfunc is not None:
-        raise NotImplementedError('weight functions in the 1D helpers are not part of the device path '
-                                  "(use assemble('w * u * v * dx', ...) on a 2D/3D space)")
-    return bsp_mixed_deriv_biform_1d_asym(knotvec, knotvec, du, dv, nqp=nqp)
+    """``a(u, v) = (w u^(du), v^(dv))`` on one knot vector (``pyiga/assemble.py:179-190``)."""
+    return bsp_mixed_deriv_biform_1d_asym(knotvec, knotvec, du, dv, nqp=nqp, weightfunc=weightfunc)
 
 
 def bsp_mass_1d(knotvec, weightfunc=None):

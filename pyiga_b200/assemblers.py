@@ -766,7 +766,9 @@ class GenericFormAssembler(_AssemblerProtocol):
 
     def _eval_input(self, f, shape, physical):
         from .vform import _grid_values
-        if not physical:        # spline function: parametric, evaluated on the Gauss grid
+        if not physical:        # parametric: a spline function, or a plain callable of the parameters (``pyiga/utils.py:33-41``)
+            if not hasattr(f, 'grid_eval'):
+                f = _ParametricCallable(f)
             vals = np.asarray(f.grid_eval(self.gaussgrid))
             vals = np.moveaxis(vals, tuple(range(len(self._grid_shape), vals.ndim)), tuple(range(len(shape)))) \
                 if shape else vals
@@ -1059,10 +1061,8 @@ class _ParametricCallable:
         return self.f(*x)
 
     def grid_eval(self, grid):
-        mesh = list(np.meshgrid(*grid, sparse=True, indexing='ij'))
-        mesh.reverse()
-        shape = tuple(len(g) for g in grid)
-        return np.broadcast_to(np.asarray(self.f(*mesh), dtype=float), shape)
+        from . import utils
+        return np.asarray(utils.grid_eval(self.f, grid), dtype=float)       # grid + the shape of f's values
 
 
 class L2FunctionalAssembler2D(_L2FunctionalBase):

@@ -260,6 +260,56 @@ class _SplineFuncBase:
         assert len(gridaxes) == self.sdim, "Input has wrong dimension"
         return self._device_eval(gridaxes, 'jacobian')
 
+    def grid_hessian(self, gridaxes):
+        """Second derivatives on a tensor grid: per point (and per component of a vector function) the upper
+        triangle of the Hessian in x, y, z order — (d_xx, d_xy, d_yy) / (d_xx, d_xy, d_xz, d_yy, d_yz, d_zz) —
+        shape ``grid + [dim] + (n_hess,)`` (``pyiga/bspline.py:923-980``, ``pyiga/geometry.py:125-150``).
+        Host evaluation from the device-tabulated 1D derivative matrices; only fourth-order forms need it."""
+        assert len(gridaxes) == self.sdim, "Input has wrong dimension"
+        d = self.sdim
+        grid = [np.asarray(np.squeeze(g) if np.ndim(g) != 1 else g, dtype=float) for g in gridaxes]
+        tabs = [collocation_derivs(kv, g, derivs=2) for kv, g in zip(self.kvs, grid)]
+        C = np.asarray(self.coeffs, dtype=float)
+        C = C.reshape(C.shape[:d] + (-1,))                  # components (homogeneous ones for NURBS) last
+
+        def partial(orders):                                # orders[k]: derivative order along tensor axis k
+            out = C
+            for k in range(d):
+                M = tabs[k][orders[k]]
+                moved = np.moveaxis(out, k, 0)
+                out = np.moveaxis((M @ moved.reshape(moved.shape[0], -1)).reshape((M.shape[0],) + moved.shape[1:]), 0, k)
+            return out                                      # grid + (components,)
+
+        def orders_of(*xyz):                                # derivative directions in x, y, z numbering
+            o = [0] * d
+            for a in xyz:
+                o[d - 1 - a] += 1                           # x is the last tensor axis
+            return o
+        pairs = [(a, b) for a in range(d) for b in range(a, d)]
+        if not self._rational:
+            H = np.stack([partial(orders_of(a, b)) for a, b in pairs], axis=-1)     # grid + (comp, n_hess)
+        else:
+            # quotient rule on the homogeneous spline (V, W), N = V / W:
+            #   N_ab = (V_ab - N_a W_b - N_b W_a - N W_ab) / W,   N_a = (V_a - N W_a) / W
+            P0 = partial(orders_of())
+            V, W = P0[..., :-1], P0[..., -1:]
+            N = V / W
+            first = [partial(orders_of(a)) for a in range(d)]
+            Na = [(P[..., :-1] - N * P[..., -1:]) / W for P in first]
+            Wa = [P[..., -1:] for P in first]
+            cols = []
+            for a, b in pairs:
+                P2 = partial(orders_of(a, b))
+                cols.append((P2[..., :-1] - Na[a] * Wa[b] - Na[b] * Wa[a] - N * P2[..., -1:]) / W)
+            H = np.stack(cols, axis=-1)
+        return H[..., 0, :] if self.is_scalar() else H
+
+    def cylinderize(self, z0=0.0, z1=1.0, support=(0.0, 1.0)):
+        """Patch with one more dimension: linear extrusion along a new last coordinate from `z0` to `z1`
+        (``pyiga/bspline.py:1097-1106``); the space-time cylinders of the heat / wave assemblers."""
+        from .geometry import line_segment, tensor_product
+        return tensor_product(line_segment(z0, z1, support=support), self)
+
     def eval(self, *x):
         """Evaluate at a single point given in x,y,z order."""
         coords = tuple(np.atleast_1d(np.asarray(t, dtype=float)) for t in reversed(x))

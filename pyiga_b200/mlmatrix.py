@@ -291,6 +291,12 @@ class MLMatrix(scipy.sparse.linalg.LinearOperator):
         assert self._data is not None or self._ddata is not None, 'matrix has no data'
         x = np.asarray(x)
         assert x.shape[0] == self.shape[1], 'Invalid input size'
+        if self.L == 1:
+            # the device kernels take 2 or 3 levels: a one-level matrix is the second level under a dense 1 x 1 level
+            if getattr(self, '_lifted', None) is None:
+                self._lifted = MLMatrix(structure=MLStructure.dense((1, 1)).join(self.structure),
+                                        data=np.asarray(self.data, dtype=np.float64).reshape(1, -1))
+            return self._lifted._matvec(x)
         h = self._device_handle()
         if not h.supported:
             raise NotImplementedError('matvec needs a 2- or 3-level matrix with contiguous row patterns')

@@ -229,6 +229,11 @@ class Measure(Expr):
         return _obj((), [Form.const(1.0)])
 
 
+# module-level measures, as in ``from pyiga.vform import dx, ds`` (``test/test_assemble.py:289,316``)
+dx = Measure()
+ds = Measure(surface=True)
+
+
 class BinOp(Expr):
     def __init__(self, op, a, b):
         self.op, self.a, self.b = op, a, b

@@ -1338,3 +1338,88 @@ def check_forms_1d():
     B = asm.assemble(a=lambda x: 2.0 + 2.0 * x * x).toarray()          # a -> 2a: only the diffusion term doubles
     K = assemble.assemble('a * inner(grad(u), grad(v)) * dx', kvs, geo=geo, a=inputs['a']).toarray()
     assert np.abs(B - (want + K)).max() <= 1e-11 * np.abs(want).max()
+
+
+def check_reference_api_extras():
+    """Pieces of the reference's API around the path that its own tests of the path use
+    (test/test_assemble.py, test/test_geometry.py, test/test_mlmatrix.py), against the live reference:
+    Hessians of spline geometries, cylinderize, module-level dx / ds, 1D bilinear helpers with second
+    derivatives and weight functions, parametric callables as form inputs, one-level MLMatrix products."""
+    _import_reference()
+    from pyiga import assemble as rasm, bspline as rbs, geometry as rgeo
+    from pyiga_b200 import assemble, assemblers, bspline, geometry, mlmatrix, vform
+    rng = np.random.default_rng(3)
+    # grid_hessian (pyiga/bspline.py:923-980, pyiga/geometry.py:125-150)
+    for d in (2, 3):
+        for comps in ((), (d,), (2,)):
+            ps, ns = (2, 3, 2)[:d], (4, 3, 5)[:d]
+            rk = tuple(rbs.make_knots(p, 0.0, 1.0, n) for p, n in zip(ps, ns))
+            ok = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(ps, ns))
+            N = tuple(k.numdofs for k in rk)
+            c, w = rng.standard_normal(N + comps), rng.uniform(0.5, 1.5, N)
+            grid = [np.linspace(0.03, 0.97, 5 + k) for k in range(d)]
+            for a, b in ((rbs.BSplineFunc(rk, c), bspline.BSplineFunc(ok, c)), (rgeo.NurbsFunc(rk, c, w), geometry.NurbsFunc(ok, c, w))):
+                want, got = a.grid_hessian(grid), b.grid_hessian(grid)
+                assert got.shape == want.shape and np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (d, comps)
+    # a fourth-order form on a geometry object of THIS package (the Hessian of the geometry enters)
+    rc, fix = _vform_fixture()
+    make, kvs, _, inputs = rc.cases()['biharmonic2']
+    got = assemble.assemble(make(), kvs, geo=geometry.quarter_annulus(), **inputs).toarray()
+    want = fix['vf_biharmonic2']
+    assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
+    # cylinderize (pyiga/bspline.py:1097-1106)
+    g, r = geometry.bspline_quarter_annulus().cylinderize(0.0, 2.0, support=(0.0, 2.0)), rgeo.bspline_quarter_annulus().cylinderize(0.0, 2.0, support=(0.0, 2.0))
+    grid = [np.linspace(0, 2, 4), np.linspace(0, 1, 3), np.linspace(0, 1, 5)]
+    assert (g.sdim, g.dim) == (3, 3) and np.abs(np.asarray(g.grid_eval(grid)) - r.grid_eval(grid)).max() <= 1e-14
+    assert np.abs(np.asarray(g.grid_jacobian(grid)) - r.grid_jacobian(grid)).max() <= 1e-13
+    # the reference's own space-time test of the wave assembler (test/test_assemble.py:118-131)
+    import scipy.sparse
+    T_end = 2.0
+    geo = geometry.unit_cube(dim=1).cylinderize(0.0, T_end, support=(0.0, T_end))
+    kv_t, kv = bspline.make_knots(2, 0.0, T_end, 6), bspline.make_knots(3, 0.0, 1.0, 8)
+    D0Dt, DttDt = assemble.bsp_mixed_deriv_biform_1d(kv_t, 0, 1), assemble.bsp_mixed_deriv_biform_1d(kv_t, 2, 1)
+    A_ref = (scipy.sparse.kron(DttDt, assemble.mass(kv)) + scipy.sparse.kron(D0Dt, assemble.stiffness(kv))).tocsr()
+    A = assemble.assemble_entries(assemblers.WaveAssembler_ST2D((kv_t, kv), geo))
+    assert abs(A_ref - A).max() < 1e-12
+    # 1D bilinear helpers: derivative orders up to 2, weight functions (pyiga/assemble.py:179-222)
+    rkv, okv = rbs.make_knots(4, 0.0, 1.0, 9), bspline.make_knots(4, 0.0, 1.0, 9)
+    wf = lambda x: 1.0 + np.sin(3 * x) ** 2
+    for du, dv in ((2, 0), (2, 1), (2, 2), (0, 2), (1, 0), (0, 0)):
+        for weight in (None, wf):
+            # with a weight the quadrature rule matters: both sides take the (p+1)-node rule of the device tables
+            nq = 5 if weight is not None else None
+            want = rasm.bsp_mixed_deriv_biform_1d(rkv, du, dv, nqp=nq, weightfunc=weight).toarray()
+            got = assemble.bsp_mixed_deriv_biform_1d(okv, du, dv, nqp=nq, weightfunc=weight).toarray()
+            assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (du, dv, weight is not None)
+    rkv2, okv2 = rbs.make_knots(2, 0.0, 1.0, 9), bspline.make_knots(2, 0.0, 1.0, 9)
+    want = rasm.bsp_mixed_deriv_biform_1d_asym(rkv, rkv2, 2, 1).toarray()
+    got = assemble.bsp_mixed_deriv_biform_1d_asym(okv, okv2, 2, 1, quadgrid=okv.mesh).toarray()
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    # module-level measures and a parametric plain callable as input (test/test_assemble.py:287-312)
+    kvs = 2 * (bspline.make_knots(3, 0.0, 1.0, 6),)
+    qa = geometry.quarter_annulus()
+    vf = vform.VForm(2)
+    u, v = vf.basisfuns()
+    vf.add(vform.inner(vform.grad(u), vform.grad(v)) * vform.dx)
+    K = assemble.assemble_vf(vf, kvs, geo=qa)
+    K2 = assemble.stiffness(kvs, qa)
+    assert abs(K - K2).max() <= 1e-12 * abs(K2).max()
+    vf_f = vform.VForm(2, arity=1)
+    f = vf_f.input('f')
+    v = vf_f.basisfuns()
+    vf_f.add(f * v * vform.dx)
+    fun = lambda x, y: np.exp(x + y)
+    f1 = assemble.assemble_vf(vf_f, kvs, geo=qa, f=fun)
+    f2 = assemble.inner_products(kvs, fun, geo=qa)
+    rk = 2 * (rbs.make_knots(3, 0.0, 1.0, 6),)
+    f3 = rasm.inner_products(rk, fun, geo=rgeo.quarter_annulus())
+    assert np.abs(f1 - f3).max() <= 1e-13 and np.abs(f2 - f3).max() <= 1e-13
+    # one-level MLMatrix: matrix and product (test/test_mlmatrix.py:60-70)
+    S = mlmatrix.MLStructure.multi_banded((20,), (3,))
+    A = np.zeros((20, 20))
+    for i in range(20):
+        for j in range(max(0, i - 3), min(20, i + 4)):
+            A[i, j] = rng.standard_normal()
+    X = mlmatrix.MLMatrix(structure=S, matrix=A)
+    x = rng.standard_normal(20)
+    assert np.allclose(A, X.asmatrix().toarray()) and np.allclose(A @ x, X.dot(x), rtol=0, atol=1e-13)

@@ -272,3 +272,7 @@ def test_forms_1d(emu, monkeypatch, tensors):
     from pyiga_b200 import refvform
     monkeypatch.setattr(refvform, '_FORCE_TENSORS', tensors)
     pc.check_forms_1d()
+
+
+def test_reference_api_extras(emu):
+    pc.check_reference_api_extras()

@@ -298,6 +298,10 @@ def test_forms_1d(cuda):
     pc.check_forms_1d()
 
 
+def test_reference_api_extras(cuda):
+    pc.check_reference_api_extras()
+
+
 @pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
 @pytest.mark.parametrize('p,ns,split', [(1, (3, 5, 70), None), (2, (3, 4, 66), None), (3, (2, 9, 40), None),
                                         (3, (3, 36, 35), 2), (2, (4, 40, 33), 3), (3, (3, 3, 33), 4),
