@@ -108,10 +108,24 @@ def eval_spline_on_grid(func, gridaxes, want, keep_on_device=False):
         raise NotImplementedError('grid evaluation is implemented for up to 3 parameters')
     axes = [np.ascontiguousarray(np.squeeze(ax) if np.ndim(ax) != 1 else ax, dtype=np.float64) for ax in gridaxes]
     assert all(ax.ndim == 1 for ax in axes), "Grid axes should be one-dimensional"
+    tail = tuple(np.shape(func.coeffs)[sdim:])
+    rational = bool(getattr(func, '_rational', False)) or type(func).__name__ == 'NurbsFunc'
+    if not rational and (len(tail) > 1 or (len(tail) == 1 and tail[0] > 3)):
+        # tensor-valued functions and vectors of more than 3 components: the kernel evaluates up to 3 components
+        # per launch — evaluate the flattened components in groups and restore the shape on the host
+        from .bspline import BSplineFunc
+        flat = np.asarray(func.coeffs, dtype=np.float64).reshape(np.shape(func.coeffs)[:sdim] + (-1,))
+        parts = [np.asarray(eval_spline_on_grid(BSplineFunc(func.kvs, flat[..., a:a + 3]), gridaxes, want))
+                 for a in range(0, flat.shape[-1], 3)]
+        if want == 'value':
+            out = np.concatenate(parts, axis=-1)
+            return out.reshape(out.shape[:sdim] + tail)
+        out = np.concatenate(parts, axis=-2)                # grid + (components, sdim)
+        return out.reshape(out.shape[:sdim] + tail + (sdim,))
     desc, keep = _lib.make_geo_desc(func)
     dim = desc.dim
     if dim > 3:
-        raise NotImplementedError('functions with more than 3 components')
+        raise NotImplementedError('rational functions with more than 3 components')
     npts = (C.c_int * sdim)(*[ax.size for ax in axes])
     grids = (_lib.c_double_p * sdim)(*[_lib.as_double_p(ax) for ax in axes])
     total = int(np.prod([ax.size for ax in axes]))

@@ -238,6 +238,11 @@ def inner_products(kvs, f, f_physical=False, geo=None):
     if geo is None:
         geo = _default_geo(kvs)
     name = 'L2FunctionalAssembler%s%dD' % ('Phys' if f_physical else '', dim)
+    if hasattr(f, 'grid_eval') and hasattr(f, 'output_shape') and tuple(f.output_shape()) != ():
+        # vector- or tensor-valued spline function: one load vector per component (``pyiga/assemble.py:318-340``)
+        extra = tuple(f.output_shape())
+        parts = [np.asarray(getattr(assemblers, name)(kvs, geo, _ComponentOf(f, idx)).assemble_vector()) for idx in np.ndindex(*extra)]
+        return np.stack(parts, axis=-1).reshape(parts[0].shape + extra)
     if not hasattr(f, 'grid_eval'):
         # vector- or tensor-valued f: the reference returns ndofs + f's shape (``pyiga/assemble.py:318-340``);
         # one load vector per component, stacked on the trailing axes
@@ -258,6 +263,19 @@ def inner_products(kvs, f, f_physical=False, geo=None):
             parts = [np.asarray(getattr(assemblers, name)(kvs, geo, component(idx)).assemble_vector()) for idx in np.ndindex(*extra)]
             return np.stack(parts, axis=-1).reshape(parts[0].shape + extra)
     return getattr(assemblers, name)(kvs, geo, f).assemble_vector()
+
+
+class _ComponentOf:
+    """one scalar component of a vector- or tensor-valued spline function (parametric input of a linear form)"""
+
+    def __init__(self, f, idx):
+        self.f, self.idx, self.kvs = f, tuple(idx), f.kvs
+
+    def output_shape(self):
+        return ()
+
+    def grid_eval(self, grid):
+        return np.asarray(self.f.grid_eval(grid))[(Ellipsis,) + self.idx]
 
 
 ################################################################################

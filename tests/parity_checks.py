@@ -1414,6 +1414,20 @@ def check_reference_api_extras():
     rk = 2 * (rbs.make_knots(3, 0.0, 1.0, 6),)
     f3 = rasm.inner_products(rk, fun, geo=rgeo.quarter_annulus())
     assert np.abs(f1 - f3).max() <= 1e-13 and np.abs(f2 - f3).max() <= 1e-13
+    # vector- and tensor-valued spline functions: values / Jacobians of more than 3 components, load vectors per component
+    # (test/test_approx.py:5-17 with degrees the device tables cover)
+    rk = tuple(rbs.make_knots(p, 0.0, 1.0, 4 + p) for p in (2, 3, 4))
+    ok = tuple(bspline.make_knots(p, 0.0, 1.0, 4 + p) for p in (2, 3, 4))
+    N = tuple(k.numdofs for k in rk)
+    grid = [np.linspace(0.0, 1.0, 4 + k) for k in range(3)]
+    for extra in ((3,), (5,), (2, 2)):
+        c = rng.standard_normal(N + extra)
+        fr, fo = rbs.BSplineFunc(rk, c), bspline.BSplineFunc(ok, c)
+        assert np.abs(np.asarray(fo.grid_eval(grid)) - fr.grid_eval(grid)).max() <= 1e-13
+        if len(extra) == 1:
+            assert np.abs(np.asarray(fo.grid_jacobian(grid)) - fr.grid_jacobian(grid)).max() <= 1e-12
+        want, got = rasm.inner_products(rk, fr), assemble.inner_products(ok, fo)
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max()), extra
     # one-level MLMatrix: matrix and product (test/test_mlmatrix.py:60-70)
     S = mlmatrix.MLStructure.multi_banded((20,), (3,))
     A = np.zeros((20, 20))
