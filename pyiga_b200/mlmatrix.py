@@ -301,3 +301,55 @@ class MLMatrix(scipy.sparse.linalg.LinearOperator):
         if not h.supported:
             raise NotImplementedError('matvec needs a 2- or 3-level matrix with contiguous row patterns')
         return h.matvec(self._device_data(), np.ascontiguousarray(x, dtype=np.float64).ravel())
+
+
+# ---------------------------------------------------------------------------------------------
+# index conversions between sequential and multilevel numbering (``pyiga/mlmatrix.py:312-416``)
+# ---------------------------------------------------------------------------------------------
+def from_seq(i, dims):
+    """lexicographic index -> multi-index (a list), last dimension fastest"""
+    return [int(t) for t in np.unravel_index(int(i), tuple(int(d) for d in dims))]
+
+
+def to_seq(I, dims):
+    """multi-index -> lexicographic index"""
+    return int(np.ravel_multi_index(tuple(int(t) for t in I), tuple(int(d) for d in dims)))
+
+
+def reindex_to_multilevel(i, j, bs):
+    """Entry (i, j) of a multilevel matrix with block sizes `bs` (L x 2) -> per level the raveled position
+    (row, column) inside that level's block."""
+    bs = np.asarray(bs, dtype=np.int64).reshape(-1, 2)
+    rows, cols = from_seq(i, bs[:, 0]), from_seq(j, bs[:, 1])
+    return tuple(r * int(b[1]) + c for r, c, b in zip(rows, cols, bs))
+
+
+def reindex_from_multilevel(M, bs):
+    """inverse of :func:`reindex_to_multilevel`: per-level block positions -> entry (i, j)"""
+    bs = np.asarray(bs, dtype=np.int64).reshape(-1, 2)
+    i = j = 0
+    for m, (nr, nc) in zip(M, bs):
+        r, c = divmod(int(m), int(nc))
+        i, j = i * int(nr) + r, j * int(nc) + c
+    return (i, j)
+
+
+def reorder(X, m1, n1):
+    """Van Loan - Pitsianis rearrangement of a dense matrix of m1 x n1 blocks: row (i * n1 + j) of the result is
+    the row-wise vectorisation of block (i, j)."""
+    X = np.asarray(X)
+    m2, n2 = X.shape[0] // m1, X.shape[1] // n1
+    assert X.shape == (m1 * m2, n1 * n2), "Invalid block size"
+    return X.reshape(m1, m2, n1, n2).transpose(0, 2, 1, 3).reshape(m1 * n1, m2 * n2)
+
+
+def reindex_from_reordered(i, j, m1, n1, m2, n2):
+    """position (i, j) in ``reorder(X, m1, n1)`` -> position in X"""
+    (bi, bj), (ii, jj) = divmod(int(i), int(n1)), divmod(int(j), int(n2))
+    return (bi * int(m2) + ii, bj * int(n2) + jj)
+
+
+def compute_banded_sparsity(n, bw):
+    """raveled positions of the nonzeros of a square banded matrix of size n and bandwidth bw"""
+    ij = compute_banded_sparsity_ij(n, bw).astype(np.int64)
+    return ij[:, 0] * int(n) + ij[:, 1]

@@ -43,3 +43,13 @@ def grid_eval_transformed(f, grid, geo):
     pts = grid_eval(geo, grid)
     coords = [pts[..., k] for k in range(pts.shape[-1])]
     return _on_grid(f(*coords), tuple(len(g) for g in grid))
+
+
+def multi_kron_sparse(As, format='csr'):
+    """Kronecker product of a sequence of sparse matrices (``pyiga/utils.py:62-67``)"""
+    import functools
+    import scipy.sparse
+    As = list(As)
+    if len(As) == 1:
+        return As[0].asformat(format, copy=True)
+    return functools.reduce(lambda A, B: scipy.sparse.kron(A, B, format='csr'), As).asformat(format)

@@ -1,0 +1,72 @@
+"""Run the REFERENCE's own test functions against pyiga_b200: the names `pyiga.<module>` are bound to the modules
+of this package, the test file is executed unmodified (optionally with textual substitutions given as
+--sub OLD=NEW, e.g. to pick spline degrees the device tables cover), and every `test_*` function is called.
+
+    python tools/run_reference_tests.py [--backend emu|cuda] [--sub OLD=NEW ...] /root/reference/test/test_assemble.py [names ...]
+
+Prints one JSON object {test name: "ok" | "FAIL line N: Error: message"}.  `--backend emu` routes the package
+through the sequential host emulation of its kernels (tests/emu: CPU-only containers); `cuda` is the product.
+The reference test files are read where they lie; nothing of them is copied."""
+import argparse
+import importlib
+import json
+import os
+import sys
+import traceback
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+MODULES = ('bspline', 'geometry', 'assemble', 'vform', 'utils', 'approx', 'operators', 'mlmatrix', 'quadrature', 'assemblers')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--backend', default='emu', choices=['emu', 'cuda'])
+    ap.add_argument('--sub', action='append', default=[])
+    ap.add_argument('testfile')
+    ap.add_argument('names', nargs='*')
+    a = ap.parse_args()
+    import numpy as np
+    import scipy.sparse
+    from pyiga_b200 import _device
+    if a.backend == 'emu':
+        from emu import build_emu
+        from emu.emu_backend import EmuBackend
+        _device._backend = EmuBackend(build_emu.build())
+    shim = types.ModuleType('pyiga')
+    shim.__path__ = []
+    sys.modules['pyiga'] = shim
+    for name in MODULES:
+        mod = importlib.import_module('pyiga_b200.' + name)
+        sys.modules['pyiga.' + name] = mod
+        setattr(shim, name, mod)
+
+    def read_sparse_matrix(fname):      # loader of the reference's golden .mtx.gz files (pyiga/utils.py:54-60): test I/O only
+        I, J, vals = np.loadtxt(fname, skiprows=1, unpack=True)
+        return scipy.sparse.coo_matrix((vals, (I.astype(int) - 1, J.astype(int) - 1))).tocsr()
+    if not hasattr(sys.modules['pyiga.utils'], 'read_sparse_matrix'):
+        sys.modules['pyiga.utils'].read_sparse_matrix = read_sparse_matrix
+    src = open(a.testfile).read()
+    for sub in a.sub:
+        old, new = sub.split('=', 1)
+        assert old in src, 'substitution %r does not apply' % old
+        src = src.replace(old, new)
+    g = {'__name__': 'reference_test', '__file__': a.testfile}
+    exec(compile(src, a.testfile, 'exec'), g)
+    res = {}
+    for k, fn in list(g.items()):
+        if k.startswith('test_') and callable(fn) and (not a.names or k in a.names):
+            try:
+                fn()
+                res[k] = 'ok'
+            except BaseException as e:      # noqa: BLE001 - report, do not stop
+                tb = [t for t in traceback.extract_tb(e.__traceback__) if t.filename == a.testfile]
+                res[k] = 'FAIL line %s: %s: %s' % (tb[-1].lineno if tb else '?', type(e).__name__, str(e)[:160])
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()
