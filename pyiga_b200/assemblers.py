@@ -97,6 +97,7 @@ class DeviceAssembler:
                 grid[k], wts[k], nq_axis[k] = np.asarray(nodes, dtype=float), np.asarray(weights, dtype=float), int(nq)
             self.gaussgrid, self.gaussweights = tuple(grid), tuple(wts)
         self.same_space = all(a is b or a == b for a, b in zip(kvs0, kvs1))
+        self._ctor = dict(terms=list(terms) if terms is not None else None, nfields=nfields, quad=quad)
 
         desc = _lib.Desc()
         desc.dim = dim
@@ -313,6 +314,20 @@ class DeviceAssembler:
         """load vector of a linear form as a flat device buffer (C order of the test space)"""
         be = self.be
         self.need_fields()
+        terms = self._ctor['terms']
+        if not self.fast_path and self.form == _lib.FORM_CUSTOM and terms and all(t[2] < 0 for t in terms):
+            # degrees without instantiated vector kernels (p = 5 ...): the B-splines of the trial space sum to 1, so
+            # the load vector of  sum_t c_t d^bt v  is the vector of row sums of the bilinear form
+            # sum_t c_t d^bt v * u, which the per-entry quadrature kernel serves for every degree
+            twin = DeviceAssembler(self.kvs[0], self.kvs[1], _lib.FORM_CUSTOM, nqp=self.nqp,
+                                   terms=[(f, bp, 0) for f, bp, _ in terms], nfields=self._ctor['nfields'], quad=self._ctor['quad'])
+            twin.fields = self.fields
+            _device.check(be.lib.pb200_asm_bind_fields(twin.handle, be.ptr(self.fields)))
+            mlb = twin.assemble_mlb(entrywise=True)
+            ones = be.from_host(np.ones(int(np.prod(twin.ndofs_trial, dtype=np.int64))))
+            out = twin.device_structure.matvec_device(mlb, ones)
+            be.synchronize()
+            return out
         n = C.c_size_t()
         _device.check(be.lib.pb200_asm_vector_workspace_bytes(self.handle, C.byref(n)))
         ws = be.empty(n.value, np.uint8)

@@ -1437,3 +1437,34 @@ def check_reference_api_extras():
     X = mlmatrix.MLMatrix(structure=S, matrix=A)
     x = rng.standard_normal(20)
     assert np.allclose(A, X.asmatrix().toarray()) and np.allclose(A @ x, X.dot(x), rtol=0, atol=1e-13)
+
+
+def check_high_degree():
+    """Degrees without instantiated sum-factorisation kernels (p = 5): matrices come from the per-entry quadrature
+    kernel, load vectors from the row sums of the twin bilinear form (DeviceAssembler.assemble_vector_device);
+    against the live reference (test/test_assemble.py:223-246 uses degrees 3, 4, 5)."""
+    _import_reference()
+    from pyiga import assemble as rasm, bspline as rbs, geometry as rgeo
+    from pyiga_b200 import assemble, assemblers, bspline, geometry
+    ps, ns = (3, 5, 4), (2, 2, 3)
+    kvs = tuple(bspline.make_knots(p, 0.0, 1.0, n) for p, n in zip(ps, ns))
+    rk = tuple(rbs.make_knots(p, 0.0, 1.0, n) for p, n in zip(ps, ns))
+    f = lambda x, y, z: np.cos(x) * np.exp(y) * np.sin(z)
+    geo, rg = geometry.twisted_box(), rgeo.twisted_box()
+    for kw in ({}, {'geo': (geo, rg)}, {'geo': (geo, rg), 'f_physical': True}):
+        kw_o = {k: (v[0] if k == 'geo' else v) for k, v in kw.items()}
+        kw_r = {k: (v[1] if k == 'geo' else v) for k, v in kw.items()}
+        want, got = rasm.inner_products(rk, f, **kw_r), assemble.inner_products(kvs, f, **kw_o)
+        assert got.shape == want.shape and np.abs(got - want).max() <= RTOL * np.abs(want).max(), kw
+    asm = assemblers.L2FunctionalAssemblerPhys3D(kvs, geo, f=f)
+    assert not asm.dev.fast_path
+    assert np.abs(asm.assemble_vector() - rasm.inner_products(rk, f, f_physical=True, geo=rg)).max() <= 1e-13
+    for form in ('mass', 'stiffness'):
+        A, B = getattr(assemble, form)(kvs, geo), getattr(rasm, form)(rk, rg)
+        assert abs(A - B).max() <= 1e-12 * abs(B).max(), form
+    # 2D, degree 6
+    kv2, rk2 = 2 * (bspline.make_knots(6, 0.0, 1.0, 3),), 2 * (rbs.make_knots(6, 0.0, 1.0, 3),)
+    g2 = lambda x, y: x * y + 1.0
+    want = rasm.inner_products(rk2, g2, f_physical=True, geo=rgeo.quarter_annulus())
+    got = assemble.inner_products(kv2, g2, f_physical=True, geo=geometry.quarter_annulus())
+    assert np.abs(got - want).max() <= RTOL * np.abs(want).max()

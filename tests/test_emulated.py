@@ -276,3 +276,7 @@ def test_forms_1d(emu, monkeypatch, tensors):
 
 def test_reference_api_extras(emu):
     pc.check_reference_api_extras()
+
+
+def test_high_degree(emu):
+    pc.check_high_degree()

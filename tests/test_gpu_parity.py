@@ -302,6 +302,10 @@ def test_reference_api_extras(cuda):
     pc.check_reference_api_extras()
 
 
+def test_high_degree(cuda):
+    pc.check_high_degree()
+
+
 @pytest.mark.parametrize('form', ['Mass', 'Stiffness'])
 @pytest.mark.parametrize('p,ns,split', [(1, (3, 5, 70), None), (2, (3, 4, 66), None), (3, (2, 9, 40), None),
                                         (3, (3, 36, 35), 2), (2, (4, 40, 33), 3), (3, (3, 3, 33), 4),

@@ -17,6 +17,8 @@ CASES = {
     # file: (substitutions, {test that cannot pass: why})
     'test_mlmatrix.py': ([], {}),
     'test_assemble.py': ([], {
+        'test_inner_products': 'SKIP: degree 5 takes the per-entry fallback, minutes in the sequential emulation (passes: '
+                               'tools/run_reference_tests.py; the fallback is checked at small size by check_high_degree)',
         'test_mass_asym': 'two bases on DIFFERENT meshes (1D helper off the device path)',
         'test_stiffness_asym': 'two bases on different meshes',
         'test_assemble_asym': 'two bases on different meshes',
@@ -24,7 +26,6 @@ CASES = {
         'test_fast_stiffness_geo_2d': 'ACA low-rank module',
         'test_fast_mass_geo_3d': 'ACA low-rank module',
         'test_fast_stiffness_geo_3d': 'ACA low-rank module',
-        'test_inner_products': 'spline degree 5 (device tables cover p <= 4)',
         'test_assemble_nonsym_vec': 'asserts BITWISE equality of multi_blocks and the assembled matrix: here these are '
                                     'two algorithms (per-entry quadrature / sum factorisation) that agree to 1 ulp',
         'test_multipatch': 'multipatch module (out of scope)',
@@ -45,6 +46,9 @@ def test_reference_test_file(name, emu_lib):
     cmd = [sys.executable, os.path.join(ROOT, 'tools', 'run_reference_tests.py'), '--backend', 'emu']
     for s in subs:
         cmd += ['--sub', s]
+    for k, why in known.items():
+        if why.startswith('SKIP'):
+            cmd += ['--skip', k]
     r = subprocess.run(cmd + [path], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
@@ -52,5 +56,5 @@ def test_reference_test_file(name, emu_lib):
     failed = {k: v for k, v in res.items() if v != 'ok'}
     unexpected = {k: v for k, v in failed.items() if k not in known}
     assert not unexpected, unexpected
-    fixed = [k for k in known if res.get(k) == 'ok']
+    fixed = [k for k in known if res.get(k) == 'ok' and not known[k].startswith('SKIP')]
     assert not fixed, 'listed as known failures but passing: %s' % fixed

@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--backend', default='emu', choices=['emu', 'cuda'])
     ap.add_argument('--sub', action='append', default=[])
+    ap.add_argument('--skip', action='append', default=[], help='test function not to run')
     ap.add_argument('testfile')
     ap.add_argument('names', nargs='*')
     a = ap.parse_args()
@@ -58,7 +59,7 @@ def main():
     exec(compile(src, a.testfile, 'exec'), g)
     res = {}
     for k, fn in list(g.items()):
-        if k.startswith('test_') and callable(fn) and (not a.names or k in a.names):
+        if k.startswith('test_') and callable(fn) and (not a.names or k in a.names) and k not in a.skip:
             try:
                 fn()
                 res[k] = 'ok'
