@@ -26,7 +26,7 @@ def main():
     for t in pinned:
         t.zero_()
     ds = sl.dev.device_structure
-    for thr in (1, 2, 4, 8, 15, 31):
+    for thr in (1, 4, 8, 15):
         if thr > (os.cpu_count() or 1):
             break
         t0 = time.perf_counter()
@@ -44,8 +44,11 @@ def main():
         t2 = time.perf_counter()
         sl.assemble_csr_host(host=pinned, pattern='device')
         t3 = time.perf_counter()
-    for thr in (2, 4, 8, 12, 15):
-        for nch in (8, 16):
+    out['phases_default_threads'] = dict(sl.last_timings) if getattr(sl, 'last_timings', None) else None
+    sl.assemble_csr_host(host=pinned, pattern='host')
+    out['phases_default_threads'] = dict(sl.last_timings)
+    for thr in (1, 4, 15):
+        for nch in (8,):
             ts = []
             for rep in range(3):
                 torch.cuda.synchronize()
