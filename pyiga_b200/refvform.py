@@ -354,6 +354,7 @@ class RefVFormAssembler(GenericFormAssembler):
     def __init__(self, kvs, kvs_test=None, bbox=None, boundary=None, **args):
         vf = self._rvf
         kvs = tuple(kvs)
+        self._ctor_args = (kvs, kvs_test, bbox, boundary)
         d = vf.dim
         assert len(kvs) == d, "Assembler requires %d knot vectors" % d
         if vf.num_spaces() == 2:
@@ -465,7 +466,24 @@ class RefVFormAssembler(GenericFormAssembler):
         self.dev = self.blocks.get((0, 0) if self.arity == 2 else (0, None), first).dev
 
     def update(self, **kwargs):
-        raise NotImplementedError('update() of reference VForms: rebuild the assembler')
+        """Re-evaluate input functions (``pyiga/codegen/cython.py:703-724``): the finalized expressions are interpreted
+        again with the new inputs (device arrays on the CUDA backend) and the field buffers rebuilt."""
+        unknown = [k for k in kwargs if k not in self.inputs()]
+        if unknown:
+            raise ValueError("unknown input '%s'" % unknown[0])
+        self._rebuild(kwargs)
+
+    def update_params(self, **kwargs):
+        unknown = [k for k in kwargs if k not in self.parameters()]
+        if unknown:
+            raise ValueError("unknown parameter '%s'" % unknown[0])
+        self._rebuild(kwargs)
+
+    def _rebuild(self, changed):
+        kvs, kvs_test, bbox, boundary = self._ctor_args
+        args = dict(self._args)
+        args.update(changed)
+        self.__init__(kvs, kvs_test, bbox=bbox, boundary=boundary, **args)
 
 
 def compile_vform(vf, on_demand=False):

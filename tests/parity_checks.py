@@ -1102,6 +1102,20 @@ def check_reference_vform_objects():
         got = got.toarray() if hasattr(got, 'toarray') else np.asarray(got)
         assert got.shape == want.shape, name
         assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), '%s: %.3e' % (name, np.abs(got - want).max())
+    # Assembler with updatable inputs on a reference VForm (pyiga/assemble.py:958-1003): update == fresh assembler
+    make, kvs, geo, inputs = rc.cases()['aniso2']
+    A2 = lambda x, y: 2.0 * rc._A(x, y) + np.eye(2)
+    asm = assemble.Assembler(make(), kvs, geo=geo, updatable=['A'], **inputs)
+    first = asm.assemble().toarray()
+    assert np.abs(first - fix['vf_aniso2']).max() <= RTOL * np.abs(fix['vf_aniso2']).max()
+    upd = asm.assemble(A=A2).toarray()
+    fresh = assemble.assemble(make(), kvs, geo=geo, **dict(inputs, A=A2)).toarray()
+    assert np.abs(upd - fresh).max() <= 1e-14 * np.abs(fresh).max() and np.abs(upd - first).max() > 0.1 * np.abs(first).max()
+    asm.asm.update_params(c=7.0)
+    fresh = assemble.assemble(make(), kvs, geo=geo, **dict(inputs, A=A2, c=7.0)).toarray()
+    assert np.abs(asm.assemble().toarray() - fresh).max() <= 1e-14 * np.abs(fresh).max()
+    with pytest.raises(ValueError):
+        asm.asm.update(nonexistent=A2)
     # integrals over a side of the patch (VForm(dim, boundary=True): ds, the normal vector, Jac_to_boundary)
     for name, (make, kvs, geo, inputs, sides) in rc.bcases().items():
         for bd in sides:
