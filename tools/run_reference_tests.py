@@ -25,6 +25,8 @@ MODULES = ('bspline', 'geometry', 'assemble', 'vform', 'utils', 'approx', 'opera
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--backend', default='emu', choices=['emu', 'cuda'])
+    ap.add_argument('--mode', default='alias', choices=['alias', 'patch'],
+                    help="alias: pyiga.* are this package's modules; patch: the real reference with its assembly entry points rebound")
     ap.add_argument('--sub', action='append', default=[])
     ap.add_argument('--skip', action='append', default=[], help='test function not to run')
     ap.add_argument('testfile')
@@ -37,18 +39,38 @@ def main():
         from emu import build_emu
         from emu.emu_backend import EmuBackend
         _device._backend = EmuBackend(build_emu.build())
-    shim = types.ModuleType('pyiga')
-    shim.__path__ = []
-    sys.modules['pyiga'] = shim
-    for name in MODULES:
-        mod = importlib.import_module('pyiga_b200.' + name)
-        sys.modules['pyiga.' + name] = mod
-        setattr(shim, name, mod)
+    if a.mode == 'patch':
+        # the REAL reference (oracle/_ref) with its assembly entry points rebound to this package: what a maintainer
+        # who integrates the library would do; the reference's other modules (hierarchical spaces,
+        # solvers, ...) then drive the device assemblers
+        sys.path.insert(0, os.path.join(ROOT, 'oracle', '_ref'))
+        import pyiga
+        import pyiga.assemble
+        import pyiga.assemblers
+        import pyiga.compile
+        from pyiga_b200 import assemble as oa, assemblers as oas, vform as ovf
+        sys.modules['pyiga.assemblers'] = oas
+        pyiga.assemblers = oas
+        pyiga.assemble.assemblers = oas
+        pyiga.compile.compile_vform = ovf.compile_vform
+        # (pyiga.assemble.assemble itself stays: it dispatches hierarchical spaces and otherwise calls the two below)
+        for name in ('mass', 'stiffness', 'divdiv', 'assemble_entries', 'assemble_entries_vec',
+                     'instantiate_assembler', 'Assembler', 'inner_products', 'bsp_mass_2d', 'bsp_mass_3d', 'bsp_stiffness_2d',
+                     'bsp_stiffness_3d', 'integrate'):
+            setattr(pyiga.assemble, name, getattr(oa, name))
+    else:
+        shim = types.ModuleType('pyiga')
+        shim.__path__ = []
+        sys.modules['pyiga'] = shim
+        for name in MODULES:
+            mod = importlib.import_module('pyiga_b200.' + name)
+            sys.modules['pyiga.' + name] = mod
+            setattr(shim, name, mod)
 
     def read_sparse_matrix(fname):      # loader of the reference's golden .mtx.gz files (pyiga/utils.py:54-60): test I/O only
         I, J, vals = np.loadtxt(fname, skiprows=1, unpack=True)
         return scipy.sparse.coo_matrix((vals, (I.astype(int) - 1, J.astype(int) - 1))).tocsr()
-    if not hasattr(sys.modules['pyiga.utils'], 'read_sparse_matrix'):
+    if a.mode == 'alias' and not hasattr(sys.modules['pyiga.utils'], 'read_sparse_matrix'):
         sys.modules['pyiga.utils'].read_sparse_matrix = read_sparse_matrix
     src = open(a.testfile).read()
     for sub in a.sub:
