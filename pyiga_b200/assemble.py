@@ -247,7 +247,8 @@ def inner_products(kvs, f, f_physical=False, geo=None):
         # vector- or tensor-valued f: the reference returns ndofs + f's shape (``pyiga/assemble.py:318-340``);
         # one load vector per component, stacked on the trailing axes
         from . import utils
-        mid = [np.array([0.5 * (kv.support()[0] + kv.support()[1])]) for kv in kvs]
+        # (two points per axis: callables that np.squeeze their arguments still see one-dimensional axes)
+        mid = [kv.support()[0] + np.array([0.25, 0.75]) * (kv.support()[1] - kv.support()[0]) for kv in kvs]
         probe = np.asarray(utils.grid_eval_transformed(f, mid, geo) if f_physical else utils.grid_eval(f, mid))
         extra = probe.shape[dim:]
         if extra != ():

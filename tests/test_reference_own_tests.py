@@ -54,6 +54,7 @@ PATCHED = {
     'test_solve.py': ([], {}),
     'test_lowrank.py': ([], {}),
     'test_localmg.py': ([_LOCALMG_IMPORT], {}),      # the relative import of a helper, resolved by file path
+    'test_approx.py': (['range(3,6)=range(2,5)'], {}),   # pyiga's project_L2 / interpolate on the device mass matrix and load vectors
 }
 
 
