@@ -55,6 +55,15 @@ def csr_sizes(dev, rows=None):
     return nrows, nnz, (np.int32 if max(nnz, ncols) < 2 ** 31 else np.int64)
 
 
+def host_cores():
+    """cores this process may run on (the affinity mask where the platform has one, else the machine's count)"""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 2
+
+
 def pattern_split(rs, ra, rb, nthr, inner_r, inner_b):
     """Rows [ra, rm) of the first axis for `nthr` pattern threads, rows [rm, rb) — about 1 / (nthr + 1) of the
     band entries — for the calling thread.  Returns (rm, None) or (rm, (rm, rb, first local row of the second
@@ -124,7 +133,7 @@ def assemble_csr_host(dev, rows=None, host=None, nchunks=8, workspace=None, patt
         # the calling thread joins them with the last rows once every chunk is enqueued, instead of idling in the
         # stream synchronisation (with 8 ranks on 16 cores that doubles the writers of a rank)
         import os
-        nthr = pattern_threads or max(1, (os.cpu_count() or 2) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))) - 1)
+        nthr = pattern_threads or max(1, host_cores() // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))) - 1)
         rm, own_share = pattern_split(rs, ra, rb, nthr, inner_r, inner_b)
 
         def fill():

@@ -111,7 +111,8 @@ class DeviceStructure:
             return a.element_size() if hasattr(a, 'element_size') else a.itemsize
         assert itemsize(h_indptr) == itemsize(h_indices)
         # share the host cores with the other ranks of the node (torchrun sets LOCAL_WORLD_SIZE)
-        nthreads = nthreads or max(1, (os.cpu_count() or 2) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))) - 1)
+        from ._hostcsr import host_cores
+        nthreads = nthreads or max(1, host_cores() // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))) - 1)
         _device.check(self.be.lib.pb200_csr_pattern_host(L, rows, cols, nband, p_rs, p_jm, ra, rb, addr(h_indptr),
                                                          addr(h_indices), itemsize(h_indptr), int(indptr_offset),
                                                          int(nthreads)))
