@@ -1337,6 +1337,12 @@ def check_forms_1d():
         want = rasm.inner_products(rkvs[0], g, f_physical=phys, geo=rgeo_c)
         got = assemble.inner_products(rkvs[0], g, f_physical=phys, geo=rgeo_c)
         assert got.shape == want.shape and np.abs(got - want).max() <= RTOL * np.abs(want).max(), phys
+    # two spaces over one mesh (trial: space 0 = columns, test: space 1 = rows) vs the reference's 1D helper
+    from pyiga import bspline as rbs
+    A = assemble.assemble('Dx(u, 0) * v * dx', ((bspline.make_knots(3, 0.0, 1.0, 6),), (bspline.make_knots(2, 0.0, 1.0, 6),)),
+                          geo=geometry.unit_cube(dim=1), bfuns=[('u', 1, 0), ('v', 1, 1)])
+    B = rasm.bsp_mixed_deriv_biform_1d_asym(rbs.make_knots(3, 0.0, 1.0, 6), rbs.make_knots(2, 0.0, 1.0, 6), 1, 0)
+    assert A.shape == B.shape == (8, 9) and abs(A - B).max() <= RTOL * abs(B).max()
     # assembler protocol on a form over one knot vector: entries, MLB format, updatable inputs
     problem, kvs, geo, inputs = rc.cases1d()['s_cd_curved']
     want = fix['f1_s_cd_curved']
